@@ -1,0 +1,73 @@
+"""ctypes binding of libfvgn_b200.so (include/fvgn_b200.h).  There is NO fallback: if the library is missing or the
+device is not sm_100, every op raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfvgn_b200.so")
+
+MATH_FP32_SIMT, MATH_BF16_TC, MATH_BF16X3_TC = 0, 1, 2
+MATH_MODES = {"fp32": MATH_FP32_SIMT, "bf16": MATH_BF16_TC, "bf16x3": MATH_BF16X3_TC}
+
+
+class MlpT(C.Structure):
+    _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p),
+                ("b3", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("k_in", C.c_int), ("n_out", C.c_int)]
+
+
+_P, _I, _F, _S = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_SIGS = {
+    "fvgn_abi_version": (C.c_int, []),
+    "fvgn_last_error": (C.c_char_p, []),
+    "fvgn_device_check": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "fvgn_connectivity_workspace_bytes": (_S, [_I]),
+    "fvgn_connectivity_faces": (_I, [_P, _I, _I, _P, C.POINTER(C.c_int), _P, _S, _P]),
+    "fvgn_connectivity_tables": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S, _P]),
+    "fvgn_csr_workspace_bytes": (_S, [_I]),
+    "fvgn_build_csr": (_I, [_P, _I, _I, _P, _P, _P, _S, _P]),
+    "fvgn_interp_nodes": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "fvgn_assemble_edge_attr": (_I, [_P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P]),
+    "fvgn_create_next_graph": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "fvgn_normalizer_accumulate": (_I, [_P, _I, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
+    "fvgn_norm_workspace_floats": (_S, [_I]),
+    "fvgn_normalizer_apply": (_I, [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P]),
+    "fvgn_mlp_rows_fwd": (_I, [C.POINTER(MlpT), _P, _I, _I, _P, _I, _I, _P]),
+    "fvgn_node_aggregate_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "fvgn_cell_block_fwd": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P, _I, _P]),
+    "fvgn_edge_block_fwd": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P, _I, _P]),
+    "fvgn_face_area_bn_fwd": (_I, [_P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fvgn_integrator_fwd": (_I, [_P, _P, _P, _P, _I, _F, _F, _P, _P, _P]),
+    "fvgn_loss_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P]),
+    "fvgn_loss_workspace_floats": (_S, [_I]),
+}
+
+_lib = None
+
+
+def declared_symbols():
+    return sorted(_SIGS.keys())
+
+
+def lib():
+    """Loads the shared library once.  Raises (never degrades) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python finite-volume-graph-network_b200/build.py` "
+                "(there is no CPU / eager fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if L.fvgn_abi_version() != 1:
+            raise RuntimeError("libfvgn_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().fvgn_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libfvgn_b200 {what} failed (code {rc}): {msg}")

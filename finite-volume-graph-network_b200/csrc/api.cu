@@ -1,0 +1,107 @@
+// api.cu — C-ABI entry points of libfvgn_b200.so that dispatch to the MLP kernels, plus error/device plumbing.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace fvgn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// mlp_simt.cu
+int simt_mlp_rows(const fvgn_mlp_t*, const float*, int, int, float*, int, cudaStream_t);
+int simt_cell_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, cudaStream_t);
+int simt_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, cudaStream_t);
+int node_aggregate(const float*, const int32_t*, const int32_t*, int, int, float*, cudaStream_t);
+// mlp_tc.cu (tcgen05)
+int tc_mlp_rows(const fvgn_mlp_t*, const float*, int, int, float*, int, int, cudaStream_t);
+int tc_cell_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, int, cudaStream_t);
+int tc_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, int, cudaStream_t);
+
+static int check_device() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      set_error("no CUDA device (libfvgn_b200 has no CPU fallback)");
+      return FVGN_E_NO_DEVICE;
+    }
+    if (major != 10) {
+      set_error("device compute capability %d.x is not sm_100 (this library is built for sm_100a only)", major);
+      return FVGN_E_NO_DEVICE;
+    }
+    ok = 1;
+  }
+  return 0;
+}
+
+}  // namespace fvgn
+
+using namespace fvgn;
+
+extern "C" int fvgn_abi_version(void) { return FVGN_ABI_VERSION; }
+extern "C" const char* fvgn_last_error(void) { return g_err; }
+
+extern "C" int fvgn_device_check(int* sm, int* major, int* minor) {
+  int dev = 0, a = 0, b = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device"); return FVGN_E_NO_DEVICE; }
+  cudaDeviceGetAttribute(&a, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMinor, dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (sm) *sm = n;
+  if (major) *major = a;
+  if (minor) *minor = b;
+  return check_device();
+}
+
+extern "C" int fvgn_mlp_rows_fwd(const fvgn_mlp_t* mlp, const float* in, int ld_in, int rows, float* out, int ld_out, int math_mode,
+                                 fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  if (math_mode == FVGN_MATH_FP32_SIMT) return simt_mlp_rows(mlp, in, ld_in, rows, out, ld_out, as_stream(stream));
+  if (math_mode == FVGN_MATH_BF16_TC || math_mode == FVGN_MATH_BF16X3_TC)
+    return tc_mlp_rows(mlp, in, ld_in, rows, out, ld_out, math_mode, as_stream(stream));
+  set_error("unknown math_mode %d", math_mode);
+  return FVGN_E_BADARG;
+}
+
+extern "C" int fvgn_node_aggregate_fwd(const float* e, const int32_t* node_ptr, const int32_t* node_items, int n_nodes, int n_faces,
+                                       float* node_agg, fvgn_stream_t stream) {
+  if (int er = check_device()) return er;
+  return node_aggregate(e, node_ptr, node_items, n_nodes, n_faces, node_agg, as_stream(stream));
+}
+
+extern "C" int fvgn_cell_block_fwd(const fvgn_mlp_t* mlp, const float* x, const float* node_agg, const int32_t* cells_node_T, int n_cells,
+                                   float* x_prime, float* x_out, int math_mode, fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  if (math_mode == FVGN_MATH_FP32_SIMT) return simt_cell_block(mlp, x, node_agg, cells_node_T, n_cells, x_prime, x_out, as_stream(stream));
+  if (math_mode == FVGN_MATH_BF16_TC || math_mode == FVGN_MATH_BF16X3_TC)
+    return tc_cell_block(mlp, x, node_agg, cells_node_T, n_cells, x_prime, x_out, math_mode, as_stream(stream));
+  set_error("unknown math_mode %d", math_mode);
+  return FVGN_E_BADARG;
+}
+
+extern "C" int fvgn_edge_block_fwd(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, const int32_t* neighbour_cell, int n_faces,
+                                   float* e_prime, float* e_out, int math_mode, fvgn_stream_t stream) {
+  if (int er = check_device()) return er;
+  if (math_mode == FVGN_MATH_FP32_SIMT) return simt_edge_block(mlp, x_prime, e, neighbour_cell, n_faces, e_prime, e_out, as_stream(stream));
+  if (math_mode == FVGN_MATH_BF16_TC || math_mode == FVGN_MATH_BF16X3_TC)
+    return tc_edge_block(mlp, x_prime, e, neighbour_cell, n_faces, e_prime, e_out, math_mode, as_stream(stream));
+  set_error("unknown math_mode %d", math_mode);
+  return FVGN_E_BADARG;
+}

@@ -1,0 +1,70 @@
+"""Attribute bags with the torch_geometric.data.Data / Batch behaviour the reference relies on (PyG is not a
+dependency of this package): `keys` is a property, `num_nodes == x.shape[0]`, block-diagonal batching offsets keys
+containing 'index' or equal to 'face' (SURVEY.md §8b "Graph objects")."""
+import torch
+
+
+class Data:
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            if v is not None:
+                setattr(self, k, v)
+
+    @property
+    def keys(self):
+        return [k for k in self.__dict__ if not k.startswith("_")]
+
+    @property
+    def num_nodes(self):
+        return self.x.shape[0]
+
+    def _apply(self, fn):
+        for k, v in list(self.__dict__.items()):
+            if torch.is_tensor(v):
+                self.__dict__[k] = fn(v)
+        return self
+
+    def to(self, device, non_blocking=False):
+        return self._apply(lambda t: t.to(device, non_blocking=non_blocking))
+
+    def cuda(self, device=None, non_blocking=False):
+        return self.to(torch.device("cuda", torch.cuda.current_device()) if device is None else device, non_blocking)
+
+    def pin_memory(self):
+        return self._apply(lambda t: t.pin_memory())
+
+    def clone(self):
+        out = self.__class__()
+        for k, v in self.__dict__.items():
+            out.__dict__[k] = v.clone() if torch.is_tensor(v) else v
+        return out
+
+
+class Batch(Data):
+    @classmethod
+    def from_data_list(cls, lst):
+        out = cls()
+        off = 0
+        cols = {k: [] for k in lst[0].keys}
+        bvec, ptr = [], [0]
+        for gi, g in enumerate(lst):
+            n = g.num_nodes
+            for k in cols:
+                v = getattr(g, k)
+                cols[k].append(v + off if _is_index(k) else v)
+            bvec.append(torch.full((n,), gi, dtype=torch.long, device=g.x.device))
+            off += n
+            ptr.append(off)
+        for k, vs in cols.items():
+            if torch.is_tensor(vs[0]):
+                setattr(out, k, torch.cat(vs, dim=-1 if _is_index(k) else 0) if vs[0].dim() > 0 else torch.stack(vs))
+            else:
+                setattr(out, k, vs)
+        out.batch = torch.cat(bvec)
+        out.ptr = torch.tensor(ptr, dtype=torch.long)
+        out.num_graphs = len(lst)
+        return out
+
+
+def _is_index(k):
+    return ("index" in k and k != "graph_index") or k == "face"

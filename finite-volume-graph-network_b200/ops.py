@@ -1,0 +1,261 @@
+"""Tensor-level wrappers over the C-ABI (include/fvgn_b200.h).  torch is used for device memory and streams only;
+all arithmetic happens in libfvgn_b200.so on the current CUDA stream.  CPU tensors are an error (no fallback)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import MlpT, check
+
+HID = 128
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _req(t, dtype, name, dim=None, rowmajor=True):
+    if not torch.is_tensor(t):
+        raise TypeError(f"{name}: expected a tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (fvgn_b200 has no CPU path), got {t.device}")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise ValueError(f"{name}: expected {dim} dims, got shape {tuple(t.shape)}")
+    if rowmajor and t.dim() >= 1 and t.numel() > 0 and t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise ValueError(f"{name}: innermost dimension must be contiguous (strides {t.stride()})")
+    return t
+
+
+def _ld(t):
+    """row stride of a 2-D (possibly sliced) row-major tensor"""
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def as_i32(t):
+    """The reference keeps int64 tables (Load_mesh.py:506-507,531-533,542); the kernels take int32."""
+    return t.to(torch.int32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ MLP weights
+class MlpRef:
+    """Borrowed pointers to one build_mlp's parameters (reference state_dict layout)."""
+
+    __slots__ = ("tensors", "struct", "k_in", "n_out")
+
+    def __init__(self, w1, b1, w2, b2, w3, b3, ln_w=None, ln_b=None):
+        ts = [w1, b1, w2, b2, w3, b3] + ([ln_w, ln_b] if ln_w is not None else [])
+        for i, t in enumerate(ts):
+            _req(t, torch.float32, f"mlp tensor {i}")
+            if not t.is_contiguous():
+                raise ValueError("mlp parameters must be contiguous")
+        if w1.shape[0] != HID or tuple(w2.shape) != (HID, HID) or w3.shape[1] != HID:
+            raise ValueError("build_mlp hidden width must be 128 (the reference ignores --hidden_size)")
+        self.tensors = ts  # keep alive
+        self.k_in, self.n_out = int(w1.shape[1]), int(w3.shape[0])
+        self.struct = MlpT(w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(),
+                           ln_w.data_ptr() if ln_w is not None else None, ln_b.data_ptr() if ln_b is not None else None,
+                           self.k_in, self.n_out)
+
+
+def mlp_rows_fwd(mlp: MlpRef, x, math_mode=0, out=None):
+    _req(x, torch.float32, "x", 2)
+    rows = x.shape[0]
+    if x.shape[1] != mlp.k_in:
+        raise ValueError(f"mlp input width {x.shape[1]} != {mlp.k_in}")
+    if out is None:
+        out = torch.empty((rows, mlp.n_out), dtype=torch.float32, device=x.device)
+    check(_lib.lib().fvgn_mlp_rows_fwd(C.byref(mlp.struct), _p(x), _ld(x), rows, _p(out), _ld(out), math_mode, _stream()), "mlp_rows_fwd")
+    return out
+
+
+def node_aggregate_fwd(e, node_ptr, node_items, n_nodes, out=None):
+    _req(e, torch.float32, "edge_attr", 2)
+    F = e.shape[0]
+    if e.shape[1] != HID or not e.is_contiguous():
+        raise ValueError("edge latent must be contiguous [F,128]")
+    if out is None:
+        out = torch.empty((n_nodes, 64), dtype=torch.float32, device=e.device)
+    check(_lib.lib().fvgn_node_aggregate_fwd(_p(e), _p(node_ptr), _p(node_items), n_nodes, F, _p(out), _stream()), "node_aggregate_fwd")
+    return out
+
+
+def cell_block_fwd(mlp: MlpRef, x, node_agg, cells_node_T, math_mode=0, x_prime=None, x_out=None, want_out=True):
+    _req(x, torch.float32, "x", 2)
+    _req(node_agg, torch.float32, "node_agg", 2)
+    _req(cells_node_T, torch.int32, "cells_node_T", 2)
+    Cn = x.shape[0]
+    if not (x.is_contiguous() and node_agg.is_contiguous() and cells_node_T.is_contiguous()) or x.shape[1] != HID or cells_node_T.shape != (3, Cn):
+        raise ValueError("cell_block_fwd: bad shapes/strides")
+    if x_prime is None:
+        x_prime = torch.empty_like(x)
+    if x_out is None and want_out:
+        x_out = torch.empty_like(x)
+    check(_lib.lib().fvgn_cell_block_fwd(C.byref(mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(x_prime), _p(x_out), math_mode,
+                                         _stream()), "cell_block_fwd")
+    return x_prime, x_out
+
+
+def edge_block_fwd(mlp: MlpRef, x_prime, e, neighbour_cell, math_mode=0, e_prime=None, e_out=None, want_prime=False, want_out=True):
+    _req(x_prime, torch.float32, "x_prime", 2)
+    _req(e, torch.float32, "edge_attr", 2)
+    _req(neighbour_cell, torch.int32, "neighbour_cell", 2)
+    F = e.shape[0]
+    if not (x_prime.is_contiguous() and e.is_contiguous() and neighbour_cell.is_contiguous()) or e.shape[1] != HID or neighbour_cell.shape != (2, F):
+        raise ValueError("edge_block_fwd: bad shapes/strides")
+    if e_prime is None and want_prime:
+        e_prime = torch.empty_like(e)
+    if e_out is None and want_out:
+        e_out = torch.empty_like(e)
+    check(_lib.lib().fvgn_edge_block_fwd(C.byref(mlp.struct), _p(x_prime), _p(e), _p(neighbour_cell), F, _p(e_prime), _p(e_out), math_mode,
+                                         _stream()), "edge_block_fwd")
+    return e_prime, e_out
+
+
+# ------------------------------------------------------------------------------------------------ connectivity
+def build_connectivity(cells, mesh_pos, node_type, face_rule="B"):
+    """a1 on device.  cells int32[C,3], mesh_pos f32[N,2], node_type int32[N] (CUDA) -> dict of tables in the H5 layout of
+    extract_mesh_state (without the leading [1,...] axis)."""
+    cells = _req(cells, torch.int32, "cells", 2).contiguous()
+    mesh_pos = _req(mesh_pos, torch.float32, "mesh_pos", 2).contiguous()
+    node_type = _req(node_type.reshape(-1), torch.int32, "node_type", 1).contiguous()
+    Cn, N = cells.shape[0], mesh_pos.shape[0]
+    dev = cells.device
+    L = _lib.lib()
+    nbytes = L.fvgn_connectivity_workspace_bytes(Cn)
+    ws = _ws(nbytes, dev)
+    cells_node = torch.empty((Cn, 3), dtype=torch.int32, device=dev)
+    nf = C.c_int(0)
+    check(L.fvgn_connectivity_faces(_p(cells), Cn, N, _p(cells_node), C.byref(nf), _p(ws), nbytes, _stream()), "connectivity_faces")
+    F = nf.value
+    i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
+    f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    t = dict(cells_node=cells_node, face=i32(2, F), cells_face=i32(Cn, 3), neighbour_cell=i32(2, F), face_type=i32(F, 1), cells_type=i32(Cn, 1),
+             face_length=f32(F, 1), unit_norm_v=f32(Cn, 3, 2), centroid=f32(Cn, 2), cells_area=f32(Cn, 1), cell_factor=f32(Cn, 3))
+    rule = {"A": 0, "B": 1}[face_rule]
+    check(L.fvgn_connectivity_tables(_p(mesh_pos), _p(node_type), _p(cells_node), Cn, N, F, rule, _p(t["face"]), _p(t["cells_face"]),
+                                     _p(t["neighbour_cell"]), _p(t["face_type"]), _p(t["cells_type"]), _p(t["face_length"]),
+                                     _p(t["unit_norm_v"]), _p(t["centroid"]), _p(t["cells_area"]), _p(t["cell_factor"]), _p(ws), nbytes,
+                                     _stream()), "connectivity_tables")
+    t["mesh_pos"], t["node_type"] = mesh_pos, node_type.view(-1, 1)
+    return t
+
+
+def build_csr(dst, n_dst):
+    dst = _req(dst, torch.int32, "dst", 1).contiguous()
+    n = dst.numel()
+    L = _lib.lib()
+    nbytes = L.fvgn_csr_workspace_bytes(n)
+    ws = _ws(nbytes, dst.device)
+    ptr = torch.empty(n_dst + 1, dtype=torch.int32, device=dst.device)
+    items = torch.empty(n, dtype=torch.int32, device=dst.device)
+    check(L.fvgn_build_csr(_p(dst), n, n_dst, _p(ptr), _p(items), _p(ws), nbytes, _stream()), "build_csr")
+    return ptr, items
+
+
+# ------------------------------------------------------------------------------------------------ pre / post
+def interp_nodes(node_field, col0, width, cells_node_T=None, cell_factor=None, face_node=None, want_cell=True, want_face=True):
+    _req(node_field, torch.float32, "node_field", 2)
+    dev = node_field.device
+    Cn = cells_node_T.shape[1] if want_cell else 0
+    F = face_node.shape[1] if want_face else 0
+    on_cell = torch.empty((Cn, width), dtype=torch.float32, device=dev) if want_cell else None
+    on_face = torch.empty((F, width), dtype=torch.float32, device=dev) if want_face else None
+    check(_lib.lib().fvgn_interp_nodes(_p(node_field), _ld(node_field), col0, width, _p(cells_node_T), _p(cell_factor), _p(face_node), Cn, F,
+                                       _p(on_cell), _p(on_face), _stream()), "interp_nodes")
+    return on_cell, on_face
+
+
+def assemble_edge_attr(cell_uv, centroid, neighbour_cell, face_type_len, bc_uv, flip_keep=None, want_mask=True):
+    F = neighbour_cell.shape[1]
+    dev = cell_uv.device
+    ea = torch.empty((F, 5), dtype=torch.float32, device=dev)
+    mask = torch.empty(F, dtype=torch.uint8, device=dev) if want_mask else None
+    if flip_keep is not None:
+        flip_keep = flip_keep.to(torch.uint8).contiguous()
+    check(_lib.lib().fvgn_assemble_edge_attr(_p(cell_uv), _ld(cell_uv), _p(centroid), _p(neighbour_cell), _p(face_type_len), _p(bc_uv), _ld(bc_uv),
+                                             _p(flip_keep), F, _p(ea), _p(mask), _stream()), "assemble_edge_attr")
+    return ea, (mask.bool() if want_mask else None)
+
+
+def create_next_graph_(x, edge_attr, next_uv, neighbour_cell, face_type_len, bc_uv):
+    """in-place on x[C,4] and edge_attr[F,5]"""
+    Cn, F = x.shape[0], edge_attr.shape[0]
+    if not (x.is_contiguous() and edge_attr.is_contiguous() and next_uv.is_contiguous()):
+        raise ValueError("create_next_graph_: contiguous tensors required")
+    check(_lib.lib().fvgn_create_next_graph(_p(next_uv), _p(neighbour_cell), _p(face_type_len), _p(bc_uv), _ld(bc_uv), Cn, F, _p(x), _p(edge_attr),
+                                            _stream()), "create_next_graph")
+
+
+# ------------------------------------------------------------------------------------------------ normalizer
+def normalizer_accumulate(x, acc_count, num_acc, acc_sum, acc_sq, max_accumulations, type_col=None, one_hot=0):
+    _req(x, torch.float32, "x", 2)
+    width = x.shape[1] + one_hot
+    L = _lib.lib()
+    ws = torch.empty(L.fvgn_norm_workspace_floats(width) // 2 + 8, dtype=torch.float64, device=x.device)
+    check(L.fvgn_normalizer_accumulate(_p(x), _ld(x), x.shape[1], _p(type_col), _ld(type_col) if type_col is not None else 0, one_hot, x.shape[0],
+                                       float(max_accumulations), _p(acc_count), _p(num_acc), _p(acc_sum), _p(acc_sq), _p(ws), _stream()),
+          "normalizer_accumulate")
+
+
+def normalizer_apply(x, acc_count, acc_sum, acc_sq, inverse=False, type_col=None, one_hot=0, addend=None, width=None, out=None):
+    _req(x, torch.float32, "x", 2)
+    wr = x.shape[1] if width is None else width
+    w = wr + one_hot
+    if out is None:
+        out = torch.empty((x.shape[0], w), dtype=torch.float32, device=x.device)
+    check(_lib.lib().fvgn_normalizer_apply(_p(x), _ld(x), wr, _p(type_col), _ld(type_col) if type_col is not None else 0, one_hot, x.shape[0],
+                                           _p(acc_count), _p(acc_sum), _p(acc_sq), 1 if inverse else 0, _p(addend),
+                                           _ld(addend) if addend is not None else 0, _p(out), _ld(out), _stream()), "normalizer_apply")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ FV head
+def face_area_bn_fwd(face_type_len, cell_area, neighbour_cell, dt, training, bn_weight, bn_bias, running_mean, running_var, want_raw=False):
+    F = neighbour_cell.shape[1]
+    dev = cell_area.device
+    L = _lib.lib()
+    out = torch.empty((F, 1), dtype=torch.float32, device=dev)
+    raw = torch.empty((F, 1), dtype=torch.float32, device=dev) if want_raw else None
+    stats = torch.empty(2, dtype=torch.float32, device=dev)
+    ws = torch.empty(L.fvgn_norm_workspace_floats(1) // 2 + 8, dtype=torch.float64, device=dev)
+    check(L.fvgn_face_area_bn_fwd(_p(face_type_len), _p(cell_area), _p(neighbour_cell), F, float(dt), 1 if training else 0, _p(bn_weight),
+                                  _p(bn_bias), _p(running_mean), _p(running_var), _p(out), _p(raw), _p(stats), _p(ws), _stream()), "face_area_bn_fwd")
+    return out, raw, stats
+
+
+def integrator_fwd(decoded, unv, face_area, cells_face_T, rho, rhs_coef=1.0, want_continuity=False):
+    Cn = cells_face_T.shape[1]
+    dev = decoded.device
+    du = torch.empty((Cn, 2), dtype=torch.float32, device=dev)
+    cont = torch.empty((Cn, 1), dtype=torch.float32, device=dev) if want_continuity else None
+    if not (decoded.is_contiguous() and unv.is_contiguous() and face_area.is_contiguous()):
+        raise ValueError("integrator_fwd: contiguous tensors required")
+    check(_lib.lib().fvgn_integrator_fwd(_p(decoded), _p(unv), _p(face_area), _p(cells_face_T), Cn, float(rho), float(rhs_coef), _p(du), _p(cont),
+                                         _stream()), "integrator_fwd")
+    return du, cont
+
+
+LOSS_MODES = {"direct_mean_loss": 0, "global_mean_sum": 1, "global_mean": 2}
+
+
+def loss_fwd(pred_du, target_du, pred_edge, target_face, mask_interior, cell_batch, face_batch, n_graphs, mode, w_mom, w_uv, w_p):
+    dev = pred_du.device
+    L = _lib.lib()
+    out = torch.empty(5, dtype=torch.float32, device=dev)
+    ws = torch.empty(L.fvgn_loss_workspace_floats(n_graphs) // 2 + 8, dtype=torch.float64, device=dev)
+    m8 = mask_interior.to(torch.uint8).contiguous()
+    check(L.fvgn_loss_fwd(_p(pred_du), _p(target_du), _p(pred_edge), _p(target_face), _p(m8), _p(cell_batch), _p(face_batch), pred_du.shape[0],
+                          pred_edge.shape[0], n_graphs, mode, float(w_mom), float(w_uv), float(w_p), _p(out), _p(ws), _stream()), "loss_fwd")
+    return out, ws

@@ -1,0 +1,64 @@
+"""MeshTopology: the int32 index tables + destination-sorted CSR incidence tables the kernels walk, derived ONCE per mesh
+batch from the reference-layout graph objects (int64 `edge_index` / `face` tensors) and cached.
+
+Reference layouts:  graph.edge_index[2,F] = neighbour_cell, graph_node.edge_index[2,F] = face (nodes),
+graph_node.face[3,C] = cells_node.T, graph_edge.face[3,C] = cells_face.T."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class MeshTopology:
+    def __init__(self, neighbour_cell, face_node, cells_node_T, cells_face_T, n_nodes):
+        self.nc = ops.as_i32(neighbour_cell)      # [2,F]
+        self.fn = ops.as_i32(face_node)           # [2,F]
+        self.cnT = ops.as_i32(cells_node_T)       # [3,C]
+        self.cfT = ops.as_i32(cells_face_T)       # [3,C]
+        self.F = int(self.nc.shape[1])
+        self.C = int(self.cnT.shape[1])
+        self.N = int(n_nodes)
+        # node <- (face, half): stable CSR over cat(face[0], face[1])  ==  the reference's scatter_add order (GN_blocks.py:111-122)
+        self.node_ptr, self.node_items = ops.build_csr(self.fn.reshape(-1), self.N)
+        self._bwd = None
+
+    def backward_tables(self):
+        """CSR transposes needed by the backward kernels: cell<-(face,side), node<-(cell,k), face<-(cell,k)."""
+        if self._bwd is None:
+            self._bwd = dict(
+                cell_from_face=ops.build_csr(self.nc.reshape(-1), self.C),
+                node_from_cell=ops.build_csr(self.cnT.reshape(-1), self.N),
+                face_from_cell=ops.build_csr(self.cfT.reshape(-1), self.F),
+            )
+        return self._bwd
+
+
+_CACHE: dict = {}
+_CACHE_MAX = 16
+
+
+def _key(t):
+    return (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
+
+
+def topology_of(graph, graph_node, graph_edge=None) -> MeshTopology:
+    """Cached MeshTopology for a (graph_cell, graph_node[, graph_edge]) triple of reference-layout bags."""
+    cfT = graph_edge.face if graph_edge is not None and hasattr(graph_edge, "face") else None
+    k = (_key(graph.edge_index), _key(graph_node.edge_index), _key(graph_node.face), _key(cfT) if cfT is not None else None,
+         int(graph_node.num_nodes))
+    topo = _CACHE.get(k)
+    if topo is None:
+        if cfT is None:
+            cfT = torch.zeros_like(graph_node.face)
+        topo = MeshTopology(graph.edge_index, graph_node.edge_index, graph_node.face, cfT, graph_node.num_nodes)
+        # keep the source tensors alive so data_ptr keys cannot be recycled while cached
+        topo._src = (graph.edge_index, graph_node.edge_index, graph_node.face, cfT)
+        if len(_CACHE) >= _CACHE_MAX:
+            _CACHE.pop(next(iter(_CACHE)))
+        _CACHE[k] = topo
+    return topo
+
+
+def clear_cache():
+    _CACHE.clear()

@@ -1,0 +1,182 @@
+/* fvgn_b200.h — C-ABI of the B200-native FVGN hot path (libfvgn_b200.so).
+ *
+ * The reference (Litianyu141/Finite-Volume-Graph-Network) is pure Python: it has no FFI layer of its own, so
+ * each entry point below replaces the *Python function* cited beside it (paths relative to
+ * /root/reference/FVGN-src/main).  INTEGRATION.md shows the ctypes binding a maintainer adds on the
+ * reference side.  Conventions:
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - all floating point is fp32, all indices int32 (the reference's int64 tables are narrowed once by the host);
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it (CUDA-graph capturable)
+ *     unless documented "synchronous";
+ *   - return 0 on success, a non-zero cudaError_t / negative FVGN_E* code otherwise; fvgn_last_error() gives text;
+ *   - no CPU fallback: a call on a machine without an sm_100 device fails with FVGN_E_NO_DEVICE.
+ *   - index tables use the reference's own layouts: [2,F] / [3,C] row-major ("edge_index", "face" of PyG Data).
+ */
+#ifndef FVGN_B200_H
+#define FVGN_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVGN_ABI_VERSION 1
+#define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
+
+#define FVGN_E_BADARG (-1)
+#define FVGN_E_NO_DEVICE (-2)
+#define FVGN_E_WORKSPACE (-3)
+#define FVGN_E_UNSUPPORTED (-4)
+
+/* arithmetic mode of the 128-wide MLP tiles */
+#define FVGN_MATH_FP32_SIMT 0 /* FFMA, strict fp32 (rel 1e-5/step vs the reference)            */
+#define FVGN_MATH_BF16_TC 1   /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM       */
+#define FVGN_MATH_BF16X3_TC 2 /* tcgen05, 3-way bf16 operand split (6 MMAs) ~ fp32 accuracy      */
+
+#if defined(__GNUC__)
+#define FVGN_API __attribute__((visibility("default")))
+#else
+#define FVGN_API
+#endif
+
+typedef void* fvgn_stream_t;
+
+FVGN_API int fvgn_abi_version(void);
+FVGN_API const char* fvgn_last_error(void);
+/* 0 if the current device is sm_100; fills sm count. */
+FVGN_API int fvgn_device_check(int* sm_count, int* cc_major, int* cc_minor);
+
+/* One MLP of build_mlp (FVGN_model/EncoderProcesserDecoder.py:12-48): Linear(k_in,128)-SiLU-Linear(128,128)-SiLU-
+ * Linear(128,n_out) [+ LayerNorm(n_out), eps 1e-5].  Pointers are the nn.Linear tensors as they sit in the
+ * state_dict: weight [out,in] row-major, bias [out].  ln_w/ln_b may be NULL (decoder). */
+typedef struct {
+  const float* w1; const float* b1; /* [128,k_in], [128] */
+  const float* w2; const float* b2; /* [128,128],  [128] */
+  const float* w3; const float* b3; /* [n_out,128],[n_out] */
+  const float* ln_w; const float* ln_b; /* [n_out] or NULL */
+  int k_in;
+  int n_out;
+} fvgn_mlp_t;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a1. connectivity + geometry tables  — replaces extract_mesh_state + triangles_to_faces + reorder_face
+ *     (Extract_mesh/parse_tfrecord_refactor.py:419-971, 1412-1457, 1343-1375).  Integer tables are bit-exact.
+ * Two phases because F (number of unique faces) is data dependent.
+ * ---------------------------------------------------------------------------------------------------------- */
+FVGN_API size_t fvgn_connectivity_workspace_bytes(int n_cells);
+/* Phase 1 (synchronous on `stream`): sorts each cell's nodes, packs the 3C (max,min) edges, radix-sorts them,
+ * and counts unique faces.  Writes cells_node[C,3] and *n_faces_host. */
+FVGN_API int fvgn_connectivity_faces(const int32_t* cells /*[C,3]*/, int n_cells, int n_nodes, int32_t* cells_node /*[C,3]*/,
+                            int* n_faces_host, void* workspace, size_t workspace_bytes, fvgn_stream_t stream);
+/* Phase 2: fills every table for the F found by phase 1 (same workspace, untouched in between).
+ * face_rule: 0 = "A" (the branch the shipped converter takes, parse_tfrecord_refactor.py:491-509),
+ *            1 = "B" (the wall/inflow/outflow branch, :511-620). */
+FVGN_API int fvgn_connectivity_tables(const float* mesh_pos /*[N,2]*/, const int32_t* node_type /*[N]*/, const int32_t* cells_node,
+                             int n_cells, int n_nodes, int n_faces, int face_rule,
+                             int32_t* face /*[2,F]*/, int32_t* cells_face /*[C,3]*/, int32_t* neighbour_cell /*[2,F]*/,
+                             int32_t* face_type /*[F]*/, int32_t* cells_type /*[C]*/, float* face_length /*[F]*/,
+                             float* unit_norm_v /*[C,3,2]*/, float* centroid /*[C,2]*/, float* cells_area /*[C]*/,
+                             float* cell_factor /*[C,3]*/, void* workspace, size_t workspace_bytes, fvgn_stream_t stream);
+
+/* Destination-sorted CSR of an incidence list (stable: items of one destination keep list order, which is what makes
+ * the segment sums reproduce the reference's scatter_add order, GN_blocks.py:111-122).
+ *   dst[n_items] in [0,n_dst)  ->  ptr[n_dst+1], items[n_items] (positions into dst). */
+FVGN_API size_t fvgn_csr_workspace_bytes(int n_items);
+FVGN_API int fvgn_build_csr(const int32_t* dst, int n_items, int n_dst, int32_t* ptr, int32_t* items, void* workspace,
+                   size_t workspace_bytes, fvgn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a2/a3. pre/post step — replaces Data_Pool.valid_datapreprocessing / train_datapreprocessing / create_next_graph
+ *        (dataset/Load_mesh.py:904-981, 983-1074, 1076-1115), dual_edge=False.
+ * node_field [N, ld] rows hold (u,v,p) at column col0 (current) and, for training, col1 (next step).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* node->cell (cell_factor-weighted 3-gather) and node->face (2-gather mean) interpolation of `width` columns. */
+FVGN_API int fvgn_interp_nodes(const float* node_field, int ld, int col0, int width, const int32_t* cells_node_T /*[3,C]*/,
+                      const float* cell_factor /*[C,3]*/, const int32_t* face_node /*[2,F]*/, int n_cells, int n_faces,
+                      float* on_cell /*[C,width] or NULL*/, float* on_face /*[F,width] or NULL*/, fvgn_stream_t stream);
+/* edge_attr[F,5] = [u_a-u_b, v_a-v_b, x_a-x_b, y_a-y_b, face_len] with (a,b)=(s,r), or (r,s) where flip_keep[f]==0
+ * (training's random direction, Load_mesh.py:1046-1061; NULL = never flipped); boundary faces (type not NORMAL/OUTFLOW)
+ * get their first two entries overwritten by bc_uv[f,0:2] (row stride ld_bc).  Also writes mask_interior[F] (uint8). */
+FVGN_API int fvgn_assemble_edge_attr(const float* cell_uv, int ld_uv, const float* centroid /*[C,2]*/, const int32_t* neighbour_cell /*[2,F]*/,
+                            const float* face_type_len /*[F,2]*/, const float* bc_uv, int ld_bc, const uint8_t* flip_keep,
+                            int n_faces, float* edge_attr /*[F,5]*/, uint8_t* mask_interior /*[F] or NULL*/, fvgn_stream_t stream);
+/* create_next_graph: x[C,4] <- [cell_type, Re, next_uv];  edge_attr[:,0:2] <- uv[s]-uv[r] (boundary <- bc_uv), cols 2:5 kept. */
+FVGN_API int fvgn_create_next_graph(const float* next_uv /*[C,2]*/, const int32_t* neighbour_cell, const float* face_type_len,
+                           const float* bc_uv, int ld_bc, int n_cells, int n_faces, float* x /*[C,4] in/out*/,
+                           float* edge_attr /*[F,5] in/out*/, fvgn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a4/a13. online Normalizer (utils/normalization.py:5-86) and the feature assembly of FVGN.update_cell_attr /
+ *         update_edge_attr (FVGN_model/FVGN.py:83-138).  stats = [acc_count, num_accumulations] scalars and
+ *         acc_sum[w], acc_sum_squared[w] device buffers (the module's registered buffers, updated in place).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* acc_sum += sum_rows(x), acc_sum_squared += sum_rows(x^2), acc_count += rows, num_accumulations += 1 — skipped on
+ * device when num_accumulations >= max_accumulations.  one_hot>0: x is [rows,width_raw] and the accumulated features
+ * are [x, one_hot(type,one_hot)] (type read from type_col[rows*ld_type]).  Deterministic two-level reduction. */
+FVGN_API int fvgn_normalizer_accumulate(const float* x, int ld_x, int width_raw, const float* type_col, int ld_type, int one_hot,
+                               int rows, float max_accumulations, float* acc_count, float* num_accumulations, float* acc_sum,
+                               float* acc_sum_squared, float* workspace /*>= fvgn_norm_workspace_floats()*/, fvgn_stream_t stream);
+FVGN_API size_t fvgn_norm_workspace_floats(int width);
+/* out[rows, width] = ([x, one_hot(type)] - mean) / std   (inverse=0)   or   x*std + mean (+ addend)   (inverse=1). */
+FVGN_API int fvgn_normalizer_apply(const float* x, int ld_x, int width_raw, const float* type_col, int ld_type, int one_hot, int rows,
+                          const float* acc_count, const float* acc_sum, const float* acc_sum_squared, int inverse,
+                          const float* addend, int ld_addend, float* out, int ld_out, fvgn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a5/a9. Encoder / Decoder MLPs over rows (EncoderProcesserDecoder.py:51-76, 127-169) — also build_mlp's forward.
+ * ---------------------------------------------------------------------------------------------------------- */
+FVGN_API int fvgn_mlp_rows_fwd(const fvgn_mlp_t* mlp, const float* in, int ld_in, int rows, float* out, int ld_out, int math_mode,
+                      fvgn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a6. CellBlock.forward (FVGN_model/GN_blocks.py:78-145), mp_times>=2, dual_edge=False.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* first aggregation: node_agg[n,0:64] = sum_{f: face_node[0,f]=n} e[f,0:64] + sum_{f: face_node[1,f]=n} e[f,64:128],
+ * summed in the reference's scatter order through the node CSR (ptr[N+1], items[2F] = positions in cat(face[0],face[1])). */
+FVGN_API int fvgn_node_aggregate_fwd(const float* e /*[F,128]*/, const int32_t* node_ptr, const int32_t* node_items, int n_nodes, int n_faces,
+                            float* node_agg /*[N,64]*/, fvgn_stream_t stream);
+/* second aggregation + cell MLP + (fused GnBlock residual, EncoderProcesserDecoder.py:121-122):
+ *   x_prime = LN(MLP([x[c] | (na[n0]+na[n1]+na[n2])/3]))      -> x_prime [C,128] (what EdgeBlock gathers)
+ *   x_out   = x + x_prime                                     -> x_out  [C,128] (may alias x; NULL to skip) */
+FVGN_API int fvgn_cell_block_fwd(const fvgn_mlp_t* mlp, const float* x /*[C,128]*/, const float* node_agg /*[N,64]*/,
+                        const int32_t* cells_node_T /*[3,C]*/, int n_cells, float* x_prime, float* x_out, int math_mode,
+                        fvgn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a7/a8. EdgeBlock.forward (GN_blocks.py:16-54) + residual:  e_prime = LN(MLP([x'[s] | x'[r] | e]));  e_out = e + e_prime.
+ *        e_prime / e_out may be NULL; e_out may alias e. */
+FVGN_API int fvgn_edge_block_fwd(const fvgn_mlp_t* mlp, const float* x_prime /*[C,128]*/, const float* e /*[F,128]*/,
+                        const int32_t* neighbour_cell /*[2,F]*/, int n_faces, float* e_prime, float* e_out, int math_mode,
+                        fvgn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a10. face-area feature + BatchNorm1d(1) (FVGN.py:77-79, 209-227 / 286-304):
+ *      raw = len*dt/((A[s]+A[r])/2);  training: batch statistics (biased var for the output, unbiased into running_var,
+ *      momentum 0.1) ; eval: running statistics.  bn = [weight, bias, running_mean, running_var] device scalars. */
+FVGN_API int fvgn_face_area_bn_fwd(const float* face_type_len /*[F,2]*/, const float* cell_area /*[C]*/, const int32_t* neighbour_cell,
+                          int n_faces, float dt, int training, const float* bn_weight, const float* bn_bias, float* running_mean,
+                          float* running_var, float* face_area /*[F]*/, float* raw /*[F] or NULL*/, float* batch_stats /*[2] mean,invstd or NULL*/,
+                          float* workspace /*>= fvgn_norm_workspace_floats(1)*/, fvgn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a11. Intergrator.forward (EncoderProcesserDecoder.py:251-331): face flux -> cell divergence.
+ *      decoded [F,5] = [u_f,v_f,p_f,Dx,Dy];  delta_u[C,2] = -(A + P/rho) + D;  continuity[C] (optional, loss_cont>0). */
+FVGN_API int fvgn_integrator_fwd(const float* decoded /*[F,5]*/, const float* unv /*[C,3,2]*/, const float* face_area /*[F]*/,
+                        const int32_t* cells_face_T /*[3,C]*/, int n_cells, float rho, float rhs_coef, float* delta_u /*[C,2]*/,
+                        float* continuity /*[C] or NULL*/, fvgn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a12. compute_FVM_loss (utils/loss_compute.py:24-115).  mode 0 = direct_mean_loss, 1 = global_mean_sum,
+ *      2 = global_mean (mean over channels).  batch vectors are int32 graph ids.  out_host-free: writes
+ *      out[5] = [loss, 0 (continuity, App. D.2), loss_mom(mean), loss_face_uv(mean), loss_face_p(mean)] on device. */
+FVGN_API int fvgn_loss_fwd(const float* pred_delta_u, const float* target_delta_u, const float* pred_edge /*[F,5]*/,
+                  const float* target_face /*[F,3]*/, const uint8_t* mask_interior, const int32_t* cell_batch,
+                  const int32_t* face_batch, int n_cells, int n_faces, int n_graphs, int mode, float w_mom, float w_uv,
+                  float w_p, float* out /*[5]*/, float* workspace /*>= fvgn_loss_workspace_floats(n_graphs)*/, fvgn_stream_t stream);
+FVGN_API size_t fvgn_loss_workspace_floats(int n_graphs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVGN_B200_H */

@@ -1,0 +1,91 @@
+"""CPU: host-side logic — C-ABI surface, loader behaviour, module tree / state_dict contract, batching."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import fvgn_b200 as fv
+from oracle import fvgn_oracle as O
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "fvgn_b200.h")).read()
+    declared = sorted(set(re.findall(r"FVGN_API\s+[\w\s\*]+?\b(fvgn_\w+)\s*\(", hdr)))
+    assert declared == fv._lib.declared_symbols(), "ctypes table and header disagree"
+    assert os.path.exists(fv._lib.LIB_PATH), "build the library first: python __graft_entry__.py"
+    L = ctypes.CDLL(fv._lib.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert L.fvgn_abi_version() == 1
+    # size queries are pure host code and must work without a device
+    L.fvgn_norm_workspace_floats.restype = ctypes.c_size_t
+    assert L.fvgn_norm_workspace_floats(14) > 0
+
+
+def test_ops_reject_cpu_tensors_loudly():
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        fv.ops.build_csr(torch.zeros(3, dtype=torch.int32), 2)
+    m = fv.build_mlp(14, 128, 128, drop_out=False)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 14))
+
+
+def test_state_dict_contract_and_seeded_init():
+    torch.manual_seed(0)
+    m = fv.FVGN(device="cpu", params=H.params())
+    sd = m.state_dict()
+    ref = H.torch_reference_state_dict(0)
+    assert len(sd) == 283 and sum(p.numel() for p in m.parameters()) == 2210695
+    assert sorted(sd.keys()) == sorted(ref.keys())
+    for k in ref:
+        assert sd[k].shape == ref[k].shape and sd[k].dtype == ref[k].dtype and torch.equal(sd[k], ref[k]), k
+    assert sd["_cell_normalizer.acc_sum"].tolist() == [1.0, 1.0]  # buffers start at ONE (App. D.1)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    m = fv.FVGN(device="cpu", params=H.params())
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    path = str(tmp_path / "0.state")
+    m.save_checkpoint(path=path, optimizer=opt, scheduler=None, trian_time_steps=np.arange(3))
+    d = torch.load(path, weights_only=False)
+    assert set(d.keys()) >= {"model", "trian_time_steps", "optimizer0"}
+    m2 = fv.FVGN(device="cpu", params=H.params())
+    steps = m2.load_checkpoint(optimizer=torch.optim.AdamW(m2.parameters(), lr=1e-3), ckpdir=path, device="cpu")
+    assert np.array_equal(steps, np.arange(3))
+    for a, b in zip(m.state_dict().values(), m2.state_dict().values()):
+        assert torch.equal(a, b)
+
+
+def test_unsupported_variants_raise():
+    with pytest.raises(NotImplementedError):
+        fv.build_mlp(4, 128, 128, drop_out=False, nn_act="ReLU")
+    with pytest.raises(NotImplementedError):
+        fv.EdgeBlock(custom_func=None, dual_edge=True)
+    with pytest.raises(ValueError):
+        fv.CellBlock(128, 128, MultiHead=3)
+
+
+def test_batching_matches_pyg_rule():
+    ms = [fv.synthetic.make("tiny", seed=s, T=3) for s in (1, 2)]
+    tabs = [O.build_connectivity(m["mesh_pos"], m["cells"], m["node_type"]) for m in ms]
+    mine = fv.dataset.collate([fv.dataset.build_graphs(t, m["velocity"], m["pressure"], training_pair=0) for t, m in zip(tabs, ms)])
+    theirs = [O.batch_graphs([O.build_graphs(t, m["velocity"], m["pressure"], training_pair=0)[k] for t, m in zip(tabs, ms)]) for k in range(3)]
+    for a, b in zip(mine, theirs):
+        for k in b.keys:
+            va, vb = getattr(a, k), getattr(b, k)
+            if torch.is_tensor(vb):
+                assert torch.equal(va.reshape(vb.shape).to(vb.dtype), vb), k
+
+
+def test_synthetic_meshes_shapes():
+    cyl = fv.synthetic.make("cyl", seed=0)
+    assert 1700 < cyl["mesh_pos"].shape[0] < 2100 and 3200 < cyl["cells"].shape[0] < 4000
+    t = O.build_connectivity(cyl["mesh_pos"], cyl["cells"], cyl["node_type"])
+    assert cyl["mesh_pos"].shape[0] - t["face"].shape[1] + cyl["cells"].shape[0] == 0  # one hole
+    assert (t["cells_area"] > 0).all()
