@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — FVGN hot-path benchmark (contract: see the task statement / DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cyl16|mesh1m|foil16] [--math fp32|bf16|bf16x3]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...     # the reference's CPU torch path (oracle port) on the host cores
+
+A "step" is one autoregressive rollout step of the hot path over one batch of synthetic meshes:
+FVGN.forward (normalise -> encoder -> 15 GnBlocks -> decoder -> face-area BN -> flux integrator -> de-normalise)
+followed by create_next_graph — i.e. one cell-update for every cell of the batch.
+Metric: cell-updates/s = cells_in_batch x steps / seconds (whole job, all ranks).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+RHO, MU, DT = 1.0, 1e-3, 0.01
+WORKLOADS = {
+    # name: (mesh kind, kwargs, graphs per rank, description)
+    "cyl16": ("cyl", {}, 16, "16 synthetic cylinder_flow-shaped meshes (~1.9k nodes / ~3.5k cells each), batch 16, fp32 (BASELINE configs[1] shape)"),
+    "foil16": ("foil", {"n_target": 6400}, 16, "16 synthetic airfoil-shaped meshes (~5k nodes each)"),
+    "mesh1m": ("grid", {"nx": 708, "ny": 708}, 1, "one scaled synthetic mesh of ~1.0M cells (BASELINE configs[4] kernel roofline sweep)"),
+    "tiny": ("grid", {"nx": 25, "ny": 17}, 2, "debug"),
+}
+
+
+def params():
+    from tests.helpers import params as P
+
+    return P()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_meshes(workload, rank):
+    import fvgn_b200 as fv
+
+    kind, kw, n_graphs, _ = WORKLOADS[workload]
+    return [fv.synthetic.make(kind, seed=1000 * rank + i, T=3, **kw) for i in range(n_graphs)]
+
+
+def device_batch(meshes, device):
+    """connectivity on device (a1) -> reference-layout graphs -> PyG-style batch -> valid_datapreprocessing (a3)."""
+    import fvgn_b200 as fv
+
+    lists = []
+    for m in meshes:
+        t = lambda a, dt: torch.as_tensor(a).to(dt).to(device)
+        tab = fv.ops.build_connectivity(t(m["cells"], torch.int32), t(m["mesh_pos"], torch.float32), t(m["node_type"], torch.int32), "B")
+        lists.append(fv.dataset.build_graphs(tab, m["velocity"], m["pressure"], device=device))
+    gn, ge, gc = fv.dataset.collate(lists)
+    gn, ge, gc, mi, mb = fv.dataset.valid_datapreprocessing(gn, ge, gc, 0)
+    return gn, ge, gc, mi, mb
+
+
+def native(args, rank, world, local_rank):
+    import fvgn_b200 as fv
+    from fvgn_b200 import ops
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    fv._lib.lib()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    meshes = make_meshes(args.workload, rank)
+    gn, ge, gc, mi, mb = device_batch(meshes, dev)
+    C, F, N = gc.x.shape[0], ge.x.shape[0], gn.x.shape[0]
+    torch.manual_seed(0)
+    model = fv.FVGN(device="cpu", params=params()).to(dev)
+    model.set_math_mode(args.math)
+    # prime the normalisers like the reference's first training rounds (2 accumulating forwards), then rollout mode
+    model.train()
+    with torch.no_grad():
+        for _ in range(2):
+            gtmp = gc.clone()
+            gtmp.y = gc.y[:, 0, :]
+            getmp = ge.clone()
+            getmp.y = ge.y[:, 0, :]
+            model(graph=gtmp, graph_edge=getmp, graph_node=gn, rho=RHO, mu=MU, dt=DT, edge_one_hot=9, cell_one_hot=0)
+    model.eval()
+    state = fv.dataset.RolloutState(gc, ge)
+    x_host0 = gc.x.cpu().pin_memory()
+    ea_host0 = gc.edge_attr.cpu().pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        uvp, nuv = model(graph=gc, graph_edge=ge, graph_node=gn, rho=RHO, mu=MU, dt=DT, edge_one_hot=9, cell_one_hot=0)
+        state.advance_(gc, nuv)
+        return uvp, nuv
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step()
+        # ---------------- device-resident timing: K steps, L2 flushed between steps, CUDA events per step
+        ops.TIMING = {"edge_block": [], "cell_block": [], "node_aggregate": []}
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        l0 = ops.LAUNCHES
+        with ClockSampler(local_rank) as clk:
+            for k in range(args.steps):
+                flush.zero_()
+                ev[k][0].record()
+                step()
+                ev[k][1].record()
+            barrier()
+        launches = ops.LAUNCHES - l0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        kern = {k: [a.elapsed_time(b) for a, b in v] for k, v in ops.TIMING.items()}
+        ops.TIMING = None
+        # ---------------- end-to-end through the public API with HOST buffers: H2D inputs + D2H results every step
+        x_host, ea_host = x_host0.clone().pin_memory(), ea_host0.clone().pin_memory()
+        nuv_host = torch.empty((C, 2), dtype=torch.float32).pin_memory()
+        uvp_host = torch.empty((F, 3), dtype=torch.float32).pin_memory()
+        for k in range(2):
+            gc.x, gc.edge_attr = x_host.to(dev, non_blocking=True), ea_host.to(dev, non_blocking=True)
+            uvp, nuv = step()
+            nuv_host.copy_(nuv, non_blocking=True), uvp_host.copy_(uvp, non_blocking=True)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for k in range(args.steps):
+            gc.x, gc.edge_attr = x_host.to(dev, non_blocking=True), ea_host.to(dev, non_blocking=True)
+            uvp, nuv = step()
+            nuv_host.copy_(nuv, non_blocking=True), uvp_host.copy_(uvp, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller consumes the result on the host every step
+            x_host[:, 2:4].copy_(nuv_host)              # host-side autoregression (next step's input comes from the host)
+        t1.record()
+        barrier()
+        e2e_ms = t0.elapsed_time(t1)
+
+    tms = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    cells = torch.tensor([float(C)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cells, op=dist.ReduceOp.SUM)
+    ms, e2e_ms = float(tms[0]), float(tms[1])
+    total_cells = float(cells[0])
+    result = None
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        # dominant kernel: the fused EdgeBlock kernel.  Algorithmic bytes per launch:
+        #   e read + e written (2*512 B/face) + every x' row read once (512 B/cell) + neighbour_cell (8 B/face)
+        edge_bytes = F * (2 * 512 + 8) + C * 512
+        edge_ms = float(np.mean(kern["edge_block"])) if kern["edge_block"] else None
+        ach = edge_bytes / (edge_ms * 1e-3) / 1e9 if edge_ms else None
+        shares = {k: (sum(v) / ms if v else 0.0) for k, v in kern.items()}
+        result = {
+            "metric": "cell_updates_per_sec", "value": total_cells * args.steps / (ms * 1e-3), "unit": "cell-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16": "bf16 tiles, f32 accumulate/residual", "bf16x3": "bf16x3 split tiles (~f32)"}[args.math],
+            "data": "synthetic",
+            "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "cells_per_rank": C, "faces_per_rank": F,
+                       "nodes_per_rank": N, "graphs_per_rank": len(meshes), "message_passing_layers": 15, "hidden": 128, "math": args.math,
+                       "step": "FVGN.forward (eval) + create_next_graph", "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": f"replicas x{world} (independent mesh batches, no collective)"},
+            "graphs_per_sec": len(meshes) * world * args.steps / (ms * 1e-3),
+            "e2e": {"value": total_cells * args.steps / (e2e_ms * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": int(C * 16 + F * 20),
+                    "d2h_bytes_per_step": int(C * 8 + F * 12), "ms_per_step": e2e_ms / args.steps,
+                    "note": "pinned host inputs copied H2D and results D2H + host sync every step"},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"kernel": "fused_mlp_simt_kernel<EDGE>" if args.math == "fp32" else "fused_mlp_tc_kernel<EDGE>", "bound": "hbm",
+                         "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": None,
+                         "peak_source": peak_src, "avg_launch_ms": edge_ms, "algorithmic_bytes_per_launch": int(edge_bytes),
+                         "launches_timed": len(kern["edge_block"]), "share_of_step": shares,
+                         "note": "fp32 mode is FFMA(compute)-bound, not HBM-bound: see DESIGN.md" if args.math == "fp32" else ""},
+        }
+        if not args.no_cpu_baseline:
+            result["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_seconds)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_setup(workload, n_graphs):
+    """The reference's torch-CPU path restated (oracle/fvgn_oracle.py, kind 'port': the reference itself is Python and is not
+    present on the GPU box).  Bounded sample: `n_graphs` meshes of the workload."""
+    import fvgn_b200 as fv
+    from oracle import fvgn_oracle as O
+    from tests import helpers as H
+
+    kind, kw, _, _ = WORKLOADS[workload]
+    bags = []
+    for i in range(n_graphs):
+        m = fv.synthetic.make(kind, seed=i, T=3, **kw)
+        tab = O.build_connectivity(m["mesh_pos"], m["cells"], m["node_type"], "B")
+        bags.append(O.build_graphs(tab, m["velocity"], m["pressure"]))
+    gn, ge, gc = [O.batch_graphs([b[k] for b in bags]) for k in range(3)]
+    gn, ge, gc, mi, mb = O.valid_datapreprocessing(gn, ge, gc, 0)
+    orc = O.FVGNOracle(H.torch_reference_state_dict(0), H.params()).eval()
+    ct, Re, rmp = gc.x[:, 0:1].clone(), gc.x[:, 1:2].clone(), gc.edge_attr[:, 2:5].clone()
+
+    def step(gc=gc):
+        with torch.no_grad():
+            uvp, nuv = orc(gc, ge, gn, RHO, MU, DT, 9, 0)
+            O.create_next_graph(gc, ge, mb, nuv, ct, Re, rmp)
+        return nuv
+
+    return step, gc.x.shape[0]
+
+
+def cpu_baseline(args, budget_s=15.0):
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n_graphs = 1 if args.workload != "tiny" else 2
+    step, C = cpu_setup(args.workload, n_graphs)
+    step()
+    t0 = time.perf_counter()
+    step()
+    one = time.perf_counter() - t0
+    n = int(max(2, min(50, budget_s / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": C * n / dt, "unit": "cell-updates/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} rollout steps of {n_graphs} {WORKLOADS[args.workload][0]} mesh(es) ({C} cells) on the host CPU, torch {torch.__version__}, "
+                      f"{threads} threads; oracle/fvgn_oracle.py (restatement of the reference's torch path, pinned against it)",
+            "ms_per_step": dt / n * 1e3}
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port), all host threads."""
+    if rank != 0:
+        return None
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n_graphs = 1 if args.workload != "tiny" else 2
+    step, C = cpu_setup(args.workload, n_graphs)
+    for _ in range(max(1, min(args.warmup, 3))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = C * args.steps / dt
+    sample = f"{args.steps} rollout steps of {n_graphs} {WORKLOADS[args.workload][0]} mesh(es) ({C} cells): bounded sample of workload {args.workload}"
+    return {"impl": "reference", "metric": "cell_updates_per_sec", "value": v, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "sample_cells": C, "message_passing_layers": 15,
+                       "hidden": 128, "step": "FVGN.forward (eval) + create_next_graph"},
+            "cpu_baseline": {"value": v, "unit": "cell-updates/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="cyl16", choices=sorted(WORKLOADS))
+    ap.add_argument("--math", default="fp32", choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        res = reference_arm(args, rank, world)
+    else:
+        res = native(args, rank, world, local_rank)
+    if rank == 0 and res is not None:
+        print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

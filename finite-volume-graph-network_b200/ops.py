@@ -11,6 +11,33 @@ from ._lib import MlpT, check
 
 HID = 128
 
+# bench instrumentation: number of kernels launched through this module and optional per-kernel CUDA-event timing
+LAUNCHES = 0
+TIMING = None  # None, or {"edge_block": [(ev0, ev1), ...], ...}
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMING is not None and self.name in TIMING:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if TIMING is not None and self.name in TIMING:
+            self.e1.record()
+            TIMING[self.name].append((self.e0, self.e1))
+        return False
+
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -31,6 +58,23 @@ def _req(t, dtype, name, dim=None, rowmajor=True):
         raise ValueError(f"{name}: expected {dim} dims, got shape {tuple(t.shape)}")
     if rowmajor and t.dim() >= 1 and t.numel() > 0 and t.stride(-1) != 1 and t.shape[-1] != 1:
         raise ValueError(f"{name}: innermost dimension must be contiguous (strides {t.stride()})")
+    return t
+
+
+def _ci(t, name, shape0=None):
+    """int32, C-contiguous index table (kernels index it as plain row-major memory)"""
+    _req(t, torch.int32, name)
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: index table must be C-contiguous (strides {t.stride()})")
+    if shape0 is not None and t.shape[0] != shape0:
+        raise ValueError(f"{name}: expected leading dimension {shape0}, got shape {tuple(t.shape)}")
+    return t
+
+
+def _cf(t, name):
+    _req(t, torch.float32, name)
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be C-contiguous (strides {t.stride()})")
     return t
 
 
@@ -76,7 +120,9 @@ def mlp_rows_fwd(mlp: MlpRef, x, math_mode=0, out=None):
         raise ValueError(f"mlp input width {x.shape[1]} != {mlp.k_in}")
     if out is None:
         out = torch.empty((rows, mlp.n_out), dtype=torch.float32, device=x.device)
-    check(_lib.lib().fvgn_mlp_rows_fwd(C.byref(mlp.struct), _p(x), _ld(x), rows, _p(out), _ld(out), math_mode, _stream()), "mlp_rows_fwd")
+    _count(1)
+    with _timed("mlp_rows"):
+        check(_lib.lib().fvgn_mlp_rows_fwd(C.byref(mlp.struct), _p(x), _ld(x), rows, _p(out), _ld(out), math_mode, _stream()), "mlp_rows_fwd")
     return out
 
 
@@ -85,9 +131,12 @@ def node_aggregate_fwd(e, node_ptr, node_items, n_nodes, out=None):
     F = e.shape[0]
     if e.shape[1] != HID or not e.is_contiguous():
         raise ValueError("edge latent must be contiguous [F,128]")
+    _ci(node_ptr, "node_ptr"), _ci(node_items, "node_items")
     if out is None:
         out = torch.empty((n_nodes, 64), dtype=torch.float32, device=e.device)
-    check(_lib.lib().fvgn_node_aggregate_fwd(_p(e), _p(node_ptr), _p(node_items), n_nodes, F, _p(out), _stream()), "node_aggregate_fwd")
+    _count(1)
+    with _timed("node_aggregate"):
+        check(_lib.lib().fvgn_node_aggregate_fwd(_p(e), _p(node_ptr), _p(node_items), n_nodes, F, _p(out), _stream()), "node_aggregate_fwd")
     return out
 
 
@@ -102,8 +151,10 @@ def cell_block_fwd(mlp: MlpRef, x, node_agg, cells_node_T, math_mode=0, x_prime=
         x_prime = torch.empty_like(x)
     if x_out is None and want_out:
         x_out = torch.empty_like(x)
-    check(_lib.lib().fvgn_cell_block_fwd(C.byref(mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(x_prime), _p(x_out), math_mode,
-                                         _stream()), "cell_block_fwd")
+    _count(1)
+    with _timed("cell_block"):
+        check(_lib.lib().fvgn_cell_block_fwd(C.byref(mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(x_prime), _p(x_out), math_mode,
+                                             _stream()), "cell_block_fwd")
     return x_prime, x_out
 
 
@@ -118,8 +169,10 @@ def edge_block_fwd(mlp: MlpRef, x_prime, e, neighbour_cell, math_mode=0, e_prime
         e_prime = torch.empty_like(e)
     if e_out is None and want_out:
         e_out = torch.empty_like(e)
-    check(_lib.lib().fvgn_edge_block_fwd(C.byref(mlp.struct), _p(x_prime), _p(e), _p(neighbour_cell), F, _p(e_prime), _p(e_out), math_mode,
-                                         _stream()), "edge_block_fwd")
+    _count(1)
+    with _timed("edge_block"):
+        check(_lib.lib().fvgn_edge_block_fwd(C.byref(mlp.struct), _p(x_prime), _p(e), _p(neighbour_cell), F, _p(e_prime), _p(e_out), math_mode,
+                                             _stream()), "edge_block_fwd")
     return e_prime, e_out
 
 
@@ -160,6 +213,7 @@ def build_csr(dst, n_dst):
     ws = _ws(nbytes, dst.device)
     ptr = torch.empty(n_dst + 1, dtype=torch.int32, device=dst.device)
     items = torch.empty(n, dtype=torch.int32, device=dst.device)
+    _count(4)
     check(L.fvgn_build_csr(_p(dst), n, n_dst, _p(ptr), _p(items), _p(ws), nbytes, _stream()), "build_csr")
     return ptr, items
 
@@ -167,23 +221,31 @@ def build_csr(dst, n_dst):
 # ------------------------------------------------------------------------------------------------ pre / post
 def interp_nodes(node_field, col0, width, cells_node_T=None, cell_factor=None, face_node=None, want_cell=True, want_face=True):
     _req(node_field, torch.float32, "node_field", 2)
+    if want_cell:
+        _ci(cells_node_T, "cells_node_T", 3), _cf(cell_factor, "cell_factor")
+    if want_face:
+        _ci(face_node, "face_node", 2)
     dev = node_field.device
     Cn = cells_node_T.shape[1] if want_cell else 0
     F = face_node.shape[1] if want_face else 0
     on_cell = torch.empty((Cn, width), dtype=torch.float32, device=dev) if want_cell else None
     on_face = torch.empty((F, width), dtype=torch.float32, device=dev) if want_face else None
+    _count(1)
     check(_lib.lib().fvgn_interp_nodes(_p(node_field), _ld(node_field), col0, width, _p(cells_node_T), _p(cell_factor), _p(face_node), Cn, F,
                                        _p(on_cell), _p(on_face), _stream()), "interp_nodes")
     return on_cell, on_face
 
 
 def assemble_edge_attr(cell_uv, centroid, neighbour_cell, face_type_len, bc_uv, flip_keep=None, want_mask=True):
+    _ci(neighbour_cell, "neighbour_cell", 2), _cf(centroid, "centroid"), _cf(face_type_len, "face_type_len")
+    _req(cell_uv, torch.float32, "cell_uv", 2), _req(bc_uv, torch.float32, "bc_uv", 2)
     F = neighbour_cell.shape[1]
     dev = cell_uv.device
     ea = torch.empty((F, 5), dtype=torch.float32, device=dev)
     mask = torch.empty(F, dtype=torch.uint8, device=dev) if want_mask else None
     if flip_keep is not None:
         flip_keep = flip_keep.to(torch.uint8).contiguous()
+    _count(1)
     check(_lib.lib().fvgn_assemble_edge_attr(_p(cell_uv), _ld(cell_uv), _p(centroid), _p(neighbour_cell), _p(face_type_len), _p(bc_uv), _ld(bc_uv),
                                              _p(flip_keep), F, _p(ea), _p(mask), _stream()), "assemble_edge_attr")
     return ea, (mask.bool() if want_mask else None)
@@ -191,9 +253,11 @@ def assemble_edge_attr(cell_uv, centroid, neighbour_cell, face_type_len, bc_uv, 
 
 def create_next_graph_(x, edge_attr, next_uv, neighbour_cell, face_type_len, bc_uv):
     """in-place on x[C,4] and edge_attr[F,5]"""
+    _ci(neighbour_cell, "neighbour_cell", 2), _cf(face_type_len, "face_type_len"), _req(bc_uv, torch.float32, "bc_uv", 2)
     Cn, F = x.shape[0], edge_attr.shape[0]
     if not (x.is_contiguous() and edge_attr.is_contiguous() and next_uv.is_contiguous()):
         raise ValueError("create_next_graph_: contiguous tensors required")
+    _count(1)
     check(_lib.lib().fvgn_create_next_graph(_p(next_uv), _p(neighbour_cell), _p(face_type_len), _p(bc_uv), _ld(bc_uv), Cn, F, _p(x), _p(edge_attr),
                                             _stream()), "create_next_graph")
 
@@ -204,6 +268,7 @@ def normalizer_accumulate(x, acc_count, num_acc, acc_sum, acc_sq, max_accumulati
     width = x.shape[1] + one_hot
     L = _lib.lib()
     ws = torch.empty(L.fvgn_norm_workspace_floats(width) // 2 + 8, dtype=torch.float64, device=x.device)
+    _count(2)
     check(L.fvgn_normalizer_accumulate(_p(x), _ld(x), x.shape[1], _p(type_col), _ld(type_col) if type_col is not None else 0, one_hot, x.shape[0],
                                        float(max_accumulations), _p(acc_count), _p(num_acc), _p(acc_sum), _p(acc_sq), _p(ws), _stream()),
           "normalizer_accumulate")
@@ -215,6 +280,7 @@ def normalizer_apply(x, acc_count, acc_sum, acc_sq, inverse=False, type_col=None
     w = wr + one_hot
     if out is None:
         out = torch.empty((x.shape[0], w), dtype=torch.float32, device=x.device)
+    _count(1)
     check(_lib.lib().fvgn_normalizer_apply(_p(x), _ld(x), wr, _p(type_col), _ld(type_col) if type_col is not None else 0, one_hot, x.shape[0],
                                            _p(acc_count), _p(acc_sum), _p(acc_sq), 1 if inverse else 0, _p(addend),
                                            _ld(addend) if addend is not None else 0, _p(out), _ld(out), _stream()), "normalizer_apply")
@@ -223,6 +289,7 @@ def normalizer_apply(x, acc_count, acc_sum, acc_sq, inverse=False, type_col=None
 
 # ------------------------------------------------------------------------------------------------ FV head
 def face_area_bn_fwd(face_type_len, cell_area, neighbour_cell, dt, training, bn_weight, bn_bias, running_mean, running_var, want_raw=False):
+    _ci(neighbour_cell, "neighbour_cell", 2), _cf(face_type_len, "face_type_len"), _cf(cell_area, "cell_area")
     F = neighbour_cell.shape[1]
     dev = cell_area.device
     L = _lib.lib()
@@ -230,18 +297,21 @@ def face_area_bn_fwd(face_type_len, cell_area, neighbour_cell, dt, training, bn_
     raw = torch.empty((F, 1), dtype=torch.float32, device=dev) if want_raw else None
     stats = torch.empty(2, dtype=torch.float32, device=dev)
     ws = torch.empty(L.fvgn_norm_workspace_floats(1) // 2 + 8, dtype=torch.float64, device=dev)
+    _count(3)
     check(L.fvgn_face_area_bn_fwd(_p(face_type_len), _p(cell_area), _p(neighbour_cell), F, float(dt), 1 if training else 0, _p(bn_weight),
                                   _p(bn_bias), _p(running_mean), _p(running_var), _p(out), _p(raw), _p(stats), _p(ws), _stream()), "face_area_bn_fwd")
     return out, raw, stats
 
 
 def integrator_fwd(decoded, unv, face_area, cells_face_T, rho, rhs_coef=1.0, want_continuity=False):
+    _ci(cells_face_T, "cells_face_T", 3)
     Cn = cells_face_T.shape[1]
     dev = decoded.device
     du = torch.empty((Cn, 2), dtype=torch.float32, device=dev)
     cont = torch.empty((Cn, 1), dtype=torch.float32, device=dev) if want_continuity else None
     if not (decoded.is_contiguous() and unv.is_contiguous() and face_area.is_contiguous()):
         raise ValueError("integrator_fwd: contiguous tensors required")
+    _count(1)
     check(_lib.lib().fvgn_integrator_fwd(_p(decoded), _p(unv), _p(face_area), _p(cells_face_T), Cn, float(rho), float(rhs_coef), _p(du), _p(cont),
                                          _stream()), "integrator_fwd")
     return du, cont
@@ -256,6 +326,7 @@ def loss_fwd(pred_du, target_du, pred_edge, target_face, mask_interior, cell_bat
     out = torch.empty(5, dtype=torch.float32, device=dev)
     ws = torch.empty(L.fvgn_loss_workspace_floats(n_graphs) // 2 + 8, dtype=torch.float64, device=dev)
     m8 = mask_interior.to(torch.uint8).contiguous()
+    _count(2)
     check(L.fvgn_loss_fwd(_p(pred_du), _p(target_du), _p(pred_edge), _p(target_face), _p(m8), _p(cell_batch), _p(face_batch), pred_du.shape[0],
                           pred_edge.shape[0], n_graphs, mode, float(w_mom), float(w_uv), float(w_p), _p(out), _p(ws), _stream()), "loss_fwd")
     return out, ws

@@ -115,9 +115,9 @@ def test_cell_and_edge_block(fv, golden):
     x, e = torch.randn(C, 128, generator=gen), torch.randn(F, 128, generator=gen)
     cb, sdc = _mlp_module(fv, 192, seed=4)
     eb, sde = _mlp_module(fv, 384, seed=5)
-    fn = torch.as_tensor(tab["face"]).long()
+    fn = torch.as_tensor(np.ascontiguousarray(tab["face"])).long()
     cnT = torch.as_tensor(tab["cells_node"]).long().T.contiguous()
-    nc = torch.as_tensor(tab["neighbour_cell"]).long()
+    nc = torch.as_tensor(np.ascontiguousarray(tab["neighbour_cell"])).long()
     sd64 = lambda sd: {k: v.double() for k, v in sd.items()}
     xp_ref = O.cell_block(sd64({"net." + k: v for k, v in sdc.items()}), "", x.double(), e.double(), fn, cnT, N)
     ep_ref = O.edge_block(sd64({"net." + k: v for k, v in sde.items()}), "", xp_ref, e.double(), nc)
@@ -155,7 +155,7 @@ def test_integrator_and_face_area(fv, golden):
     # face area + BatchNorm, training and eval
     ftl = torch.cat((torch.as_tensor(tab["face_type"]).float(), torch.as_tensor(tab["face_length"])), 1)
     area = torch.as_tensor(tab["cells_area"])
-    nc = torch.as_tensor(tab["neighbour_cell"]).long()
+    nc = torch.as_tensor(np.ascontiguousarray(tab["neighbour_cell"])).long()
     raw = (ftl[:, 1:2] * (0.01 / ((area[nc[0]] + area[nc[1]]) / 2))).view(-1, 1)
     bn = torch.nn.BatchNorm1d(1)
     with torch.no_grad():
@@ -320,6 +320,16 @@ def test_training_forward_tuple_and_loss(fv, golden):
         loss = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=out[3],
                                    target_face_uvp_normalized=out[4], predicted_delta_u=out[1], target_delta_u=out[2])
         assert abs(float(loss[0]) - g[tag + ".loss"][0]) < 2e-5
+
+
+def test_non_contiguous_tables_rejected(fv, golden):
+    g, tab = _tiny(golden)
+    nc = torch.as_tensor(np.asfortranarray(tab["neighbour_cell"])).to(torch.int32).cuda()
+    assert not nc.is_contiguous()
+    F = nc.shape[1]
+    with pytest.raises(ValueError, match="contiguous"):
+        fv.ops.face_area_bn_fwd(torch.ones(F, 2).cuda(), torch.ones(tab["cells_node"].shape[0], 1).cuda(), nc, 0.01, False, torch.ones(1).cuda(),
+                                torch.zeros(1).cuda(), torch.zeros(1).cuda(), torch.ones(1).cuda())
 
 
 def test_no_cpu_fallback(fv):
