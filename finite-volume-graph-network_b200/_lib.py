@@ -12,7 +12,7 @@ MATH_MODES = {"fp32": MATH_FP32_SIMT, "bf16": MATH_BF16_TC, "bf16x3": MATH_BF16X
 
 class MlpT(C.Structure):
     _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p),
-                ("b3", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("k_in", C.c_int), ("n_out", C.c_int)]
+                ("b3", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("k_in", C.c_int), ("n_out", C.c_int), ("packed", C.c_void_p)]
 
 
 _P, _I, _F, _S = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -31,6 +31,8 @@ _SIGS = {
     "fvgn_normalizer_accumulate": (_I, [_P, _I, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "fvgn_norm_workspace_floats": (_S, [_I]),
     "fvgn_normalizer_apply": (_I, [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P]),
+    "fvgn_mlp_packed_bytes": (_S, [_I]),
+    "fvgn_mlp_pack_bf16": (_I, [C.POINTER(MlpT), _P, _S, _P]),
     "fvgn_mlp_rows_fwd": (_I, [C.POINTER(MlpT), _P, _I, _I, _P, _I, _I, _P]),
     "fvgn_node_aggregate_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "fvgn_cell_block_fwd": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P, _I, _P]),

@@ -34,6 +34,9 @@ int tc_mlp_rows(const fvgn_mlp_t*, const float*, int, int, float*, int, int, cud
 int tc_cell_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, int, cudaStream_t);
 int tc_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, int, cudaStream_t);
 
+size_t tc_packed_bytes(int k_in);
+int tc_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
+
 static int check_device() {
   static int ok = -1;
   if (ok < 0) {
@@ -68,6 +71,13 @@ extern "C" int fvgn_device_check(int* sm, int* major, int* minor) {
   if (major) *major = a;
   if (minor) *minor = b;
   return check_device();
+}
+
+extern "C" size_t fvgn_mlp_packed_bytes(int k_in) { return tc_packed_bytes(k_in); }
+
+extern "C" int fvgn_mlp_pack_bf16(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  return tc_pack(mlp, packed, packed_bytes, as_stream(stream));
 }
 
 extern "C" int fvgn_mlp_rows_fwd(const fvgn_mlp_t* mlp, const float* in, int ld_in, int rows, float* out, int ld_out, int math_mode,

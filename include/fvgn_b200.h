@@ -57,7 +57,12 @@ typedef struct {
   const float* ln_w; const float* ln_b; /* [n_out] or NULL */
   int k_in;
   int n_out;
+  const void* packed; /* tensor-core modes only: buffer filled by fvgn_mlp_pack_bf16 for the CURRENT weights; NULL otherwise */
 } fvgn_mlp_t;
+
+/* Tensor-core modes read the weights as pre-swizzled bf16 tiles.  Re-pack whenever the fp32 weights change. */
+FVGN_API size_t fvgn_mlp_packed_bytes(int k_in);
+FVGN_API int fvgn_mlp_pack_bf16(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * a1. connectivity + geometry tables  — replaces extract_mesh_state + triangles_to_faces + reorder_face

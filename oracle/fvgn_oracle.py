@@ -319,12 +319,26 @@ class NormState:
 # ----------------------------------------------------------------------------------------------
 # a5-a9. network: FVGN_model/EncoderProcesserDecoder.py, GN_blocks.py
 # ----------------------------------------------------------------------------------------------
+# Emulation of the tensor-core modes for the parity tests of the bf16 path (NOT part of the reference): when set to
+# torch.bfloat16, both operands of every nn.Linear are rounded to bf16 (round-to-nearest-even) before the product,
+# accumulation stays in the working dtype — exactly what SURVEY.md Appendix E measured.
+OPERAND_ROUND = None
+
+
+def _rnd(t):
+    return t if OPERAND_ROUND is None else t.to(OPERAND_ROUND).to(t.dtype)
+
+
+def _linear(x, w, b):
+    return Fnn.linear(_rnd(x), _rnd(w), b)
+
+
 def mlp(sd, prefix, x, layer_norm=True):
     """build_mlp (EncoderProcesserDecoder.py:12-48): Linear-SiLU-Linear-SiLU-Linear [+ LayerNorm eps 1e-5]."""
     p = prefix + ("0." if layer_norm else "")
-    h = Fnn.silu(Fnn.linear(x, sd[p + "0.weight"], sd[p + "0.bias"]))
-    h = Fnn.silu(Fnn.linear(h, sd[p + "2.weight"], sd[p + "2.bias"]))
-    h = Fnn.linear(h, sd[p + "4.weight"], sd[p + "4.bias"])
+    h = Fnn.silu(_linear(x, sd[p + "0.weight"], sd[p + "0.bias"]))
+    h = Fnn.silu(_linear(h, sd[p + "2.weight"], sd[p + "2.bias"]))
+    h = _linear(h, sd[p + "4.weight"], sd[p + "4.bias"])
     if layer_norm:
         h = Fnn.layer_norm(h, (h.shape[-1],), sd[prefix + "1.weight"], sd[prefix + "1.bias"], 1e-5)
     return h
