@@ -30,6 +30,7 @@ WORKLOADS = {
     "cyl16": ("cyl", {}, 16, "16 synthetic cylinder_flow-shaped meshes (~1.9k nodes / ~3.5k cells each), batch 16, fp32 (BASELINE configs[1] shape)"),
     "foil16": ("foil", {"n_target": 6400}, 16, "16 synthetic airfoil-shaped meshes (~5k nodes each)"),
     "mesh1m": ("grid", {"nx": 708, "ny": 708}, 1, "one scaled synthetic mesh of ~1.0M cells (BASELINE configs[4] kernel roofline sweep)"),
+    "mesh1m_ordered": ("grid", {"nx": 708, "ny": 708, "shuffle": False}, 1, "~1.0M cells, cells numbered in generation (row-major) order"),
     "tiny": ("grid", {"nx": 25, "ny": 17}, 2, "debug"),
 }
 

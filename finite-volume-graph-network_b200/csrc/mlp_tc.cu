@@ -1,17 +1,19 @@
 // mlp_tc.cu — tcgen05 / TMEM tensor-core path of the fused gather -> MLP -> LayerNorm -> residual kernels (sm_100a).
 //
-// One persistent CTA per SM, 128-row tiles, warp-specialised:
-//   warps 0-7  workers : gather the tile's operand rows from HBM (128-bit loads), convert to bf16 and write them into shared
-//                        memory in the canonical K-major SWIZZLE_128B UMMA layout; epilogues: tcgen05.ld the fp32 accumulator
-//                        from TMEM (one row per thread), bias + SiLU -> bf16 A operand of the next layer, or bias + LayerNorm
-//                        (thread-local row statistics) + residual -> HBM
-//   warp 8     MMA     : one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM, M=128 N=128 K=16)
-//   warp 9     loader  : streams the first-layer weight K-tiles through a 3-slot ring with cp.async.bulk (TMA bulk copy) on
-//                        mbarriers; W2/W3 are loaded once and stay resident
+// One persistent CTA per SM, 128-row tiles, fully decoupled warp-specialised pipeline (14 warps):
+//   warps 0-3   producers : gather the tile's operand rows from HBM (16 x 128-bit loads in flight per thread), convert to
+//                           bf16 and write 64-column K-tiles into a 5-slot shared-memory ring in the canonical K-major
+//                           SWIZZLE_128B UMMA layout.  They run up to one tile + 5 K-tiles ahead of the epilogues.
+//   warps 4-11  epilogue  : tcgen05.ld the fp32 accumulator from TMEM (one row per thread), bias + SiLU -> bf16 A operand
+//                           of the next layer (H tile), or bias + LayerNorm + residual -> HBM through a swizzled smem
+//                           staging tile so that every global access is a full 128-byte line
+//   warp 12     MMA       : one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM, M=128 N=128 K=16).
+//                           Two TMEM accumulators ping-pong: layer 1 of tile i+1 runs while tile i is in its epilogues.
+//   warp 13     loader    : streams the first-layer weight K-tiles through a 2-slot ring with cp.async.bulk (TMA bulk copy)
+//                           on mbarriers; W2/W3 are loaded once and stay resident
 // Weights are pre-packed once per weight version (fvgn_mlp_pack_bf16) into bf16 tiles that are byte images of the
 // swizzled shared-memory layout, so the loader needs no tensor map: each K-tile is one 16 KB bulk copy.
-// Pipelines: full/empty mbarriers (loader <-> MMA, released by tcgen05.commit), a_ready (workers -> MMA), d_ready
-// (tcgen05.commit -> workers).  Every mbarrier wait has a watchdog that traps instead of hanging the device.
+// Every mbarrier wait has a watchdog that traps instead of hanging the device.
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -21,9 +23,14 @@ constexpr int TM = 128;            // rows per tile (= UMMA M)
 constexpr int HIDN = 128;          // N of every layer (padded)
 constexpr int KTILE = 64;          // bf16 elements per 128-byte swizzle row
 constexpr int TILE_BYTES = 16384;  // [128 rows][128 B]
-constexpr int RING = 3;            // W1 K-tile ring slots
-constexpr int NWORK = 256;         // worker threads (8 warps)
-constexpr int NTHREADS = 320;      // + MMA warp + loader warp
+constexpr int ARING = 5;           // A-operand K-tile ring slots
+constexpr int WRING = 2;           // W1 K-tile ring slots
+constexpr int NPROD = 256;         // producer threads (warps 0-7)
+constexpr int NPW = NPROD / 32;    // producer warps
+constexpr int NEPI = 256;          // epilogue threads (warps 8-15)
+constexpr int WARP_EPI0 = NPW, WARP_MMA = NPW + 8, WARP_LOAD = NPW + 9;
+constexpr int NTHREADS = (NPW + 10) * 32;
+constexpr int RPT = TM / (NPROD / 16);  // rows per producer thread per K-tile (8)
 
 enum { TC_ROWS = 0, TC_CELL = 1, TC_EDGE = 2 };
 
@@ -135,7 +142,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// x * sigmoid(x) = 0.5 x (1 + tanh(x/2)): one MUFU per element (tanh.approx rel. error ~2^-11, below the bf16 rounding of H)
+__device__ __forceinline__ float silu_fast(float v) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+  const float hv = 0.5f * v;
+  return fmaf(hv, t, hv);
+}
 
 // store 4 consecutive fp32 (columns 4*hl .. 4*hl+3 of a 64-wide K-tile) as bf16 into row r of a swizzled tile
 __device__ __forceinline__ void st_tile_f4(unsigned char* tile, int r, int hl, float4 v) {
@@ -146,53 +159,58 @@ __device__ __forceinline__ void st_tile_f4(unsigned char* tile, int r, int hl, f
   *reinterpret_cast<uint2*>(tile + off) = pk;
 }
 
-// ------------------------------------------------------------------------------------------------ the fused kernel
+// ------------------------------------------------------------------------------------------------ shared memory map
 struct SmemLayout {
-  uint32_t a_off, w2_off, w3_off, ring_off, par_off, red_off, bar_off, total;
+  uint32_t a_off, h_off, w2_off, w3_off, wring_off, par_off, red_off, bar_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int kt1) {
+__host__ __device__ inline SmemLayout smem_layout() {
   SmemLayout L;
-  const int kta = kt1 < 2 ? 2 : kt1;
   uint32_t o = 0;
-  L.a_off = o; o += kta * TILE_BYTES;
-  L.w2_off = o; o += 2 * TILE_BYTES;
-  L.w3_off = o; o += 2 * TILE_BYTES;
-  L.ring_off = o; o += RING * TILE_BYTES;
-  L.par_off = o; o += 5 * 128 * 4;
-  L.red_off = o; o += 2 * 2 * 128 * 4;
-  L.bar_off = o; o += 128;
-  L.total = o + 1024;  // slack for the 1024-byte alignment of the dynamic smem base
+  L.a_off = o; o += ARING * TILE_BYTES;      // 80 KB  A-operand K-tile ring
+  L.h_off = o; o += 2 * TILE_BYTES;          // 32 KB  hidden activations (A operand of layers 2,3) / fp32 output staging
+  L.w2_off = o; o += 2 * TILE_BYTES;         // 32 KB
+  L.w3_off = o; o += 2 * TILE_BYTES;         // 32 KB
+  L.wring_off = o; o += WRING * TILE_BYTES;  // 32 KB  W1 K-tile ring
+  L.par_off = o; o += 5 * 128 * 4;           // b1 | b2 | b3 | ln_w | ln_b
+  L.red_off = o; o += 2 * 2 * 128 * 4;       // LayerNorm cross-warp exchange
+  L.bar_off = o; o += 256;
+  L.total = o + 1024;                        // slack for the 1024-byte alignment of the dynamic smem base
   return L;
 }
+
+// barrier indices (8 bytes each)
+enum { B_AFULL = 0, B_AEMPTY = B_AFULL + ARING, B_WFULL = B_AEMPTY + ARING, B_WEMPTY = B_WFULL + WRING, B_WRES = B_WEMPTY + WRING,
+       B_DFULL = B_WRES + 1, B_DFREE = B_DFULL + 2, B_HREADY = B_DFREE + 2, B_COUNT = B_HREADY + 1 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const SmemLayout L = smem_layout(p.kt1);
+  const SmemLayout L = smem_layout();
   unsigned char* sA = smem + L.a_off;
+  unsigned char* sH = smem + L.h_off;
   unsigned char* sW2 = smem + L.w2_off;
   unsigned char* sW3 = smem + L.w3_off;
-  unsigned char* sRing = smem + L.ring_off;
-  float* sPar = reinterpret_cast<float*>(smem + L.par_off);  // b1 | b2 | b3 | ln_w | ln_b
-  float* sRed = reinterpret_cast<float*>(smem + L.red_off);  // [2 passes][2 halves][128 rows]
+  unsigned char* sWr = smem + L.wring_off;
+  float* sPar = reinterpret_cast<float*>(smem + L.par_off);
+  float* sRed = reinterpret_cast<float*>(smem + L.red_off);
   const uint32_t bar0 = smem_u32(smem + L.bar_off);
-  // barrier map: full[RING] empty[RING] wres a_ready d_ready | tmem slot
-  const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * RING, bar_wres = bar0 + 16 * RING, bar_a = bar_wres + 8, bar_d = bar_wres + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 16 * RING + 24);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * B_COUNT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt1 = p.kt1;
 
   if (tid == 0) {
-    for (int i = 0; i < RING; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    mbar_init(bar_wres, 1);
-    mbar_init(bar_a, 8);  // one arrive per worker warp
-    mbar_init(bar_d, 1);  // tcgen05.commit
+    for (int i = 0; i < ARING; ++i) { mbar_init(BAR(B_AFULL + i), NPW); mbar_init(BAR(B_AEMPTY + i), 1); }
+    for (int i = 0; i < WRING; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
+    mbar_init(BAR(B_WRES), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_DFULL + b), 1); mbar_init(BAR(B_DFREE + b), 8); }
+    mbar_init(BAR(B_HREADY), 8);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 128);
-  if (tid < NWORK) {
-    for (int i = tid; i < 5 * 128; i += NWORK) {
+  if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp >= WARP_EPI0 && warp < WARP_EPI0 + 8) {
+    for (int i = tid - NPROD; i < 5 * 128; i += NEPI) {
       const int which = i >> 7, c = i & 127;
       float v = 0.f;
       if (which == 0) v = p.b1[c];
@@ -206,157 +224,183 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 9) {
-    // ================================================================= loader warp
+  if (warp < NPW) {
+    // ================================================================= producers: gather -> A ring
+    constexpr int NHW = NPROD / 16;          // half-warps: half-warp hw owns rows hw, hw+NHW, ...
+    const int hw = tid >> 4, hl = tid & 15;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int row0 = tile * TM;
+      for (int t = 0; t < kt1; ++t, ++g) {
+        const uint32_t slot = g % ARING;
+        // issue the loads of this K-tile before waiting for the slot: the wait overlaps the memory latency
+        float4 v[RPT];
+        if (p.mode == TC_EDGE) {
+          const int F = p.rows;
+          int src[RPT];
+          if (t < 4) {
+            const int32_t* ip = p.idx + (t >= 2 ? (size_t)F : 0);
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) { const int f = row0 + hw + NHW * i; src[i] = (f < F) ? __ldg(ip + f) : -1; }
+            const float* base = p.src0 + (t & 1) * 64 + hl * 4;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) v[i] = (src[i] >= 0) ? ldg4(base + (size_t)src[i] * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+            const float* base = p.src1 + (t & 1) * 64 + hl * 4;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+              const int f = row0 + hw + NHW * i;
+              v[i] = (f < F) ? *reinterpret_cast<const float4*>(base + (size_t)f * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        } else if (p.mode == TC_CELL) {
+          const int C = p.rows;
+          if (t < 2) {
+            const float* base = p.src0 + t * 64 + hl * 4;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+              const int c = row0 + hw + NHW * i;
+              v[i] = (c < C) ? *reinterpret_cast<const float4*>(base + (size_t)c * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+              const int c = row0 + hw + NHW * i;
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (c < C) {
+                const int n0 = __ldg(p.idx + c), n1 = __ldg(p.idx + (size_t)C + c), n2 = __ldg(p.idx + 2 * (size_t)C + c);
+                const float4 a = ldg4(p.src1 + (size_t)n0 * 64 + hl * 4);
+                const float4 b = ldg4(p.src1 + (size_t)n1 * 64 + hl * 4);
+                const float4 d = ldg4(p.src1 + (size_t)n2 * 64 + hl * 4);
+                o.x = ((a.x + b.x) + d.x) / 3.0f; o.y = ((a.y + b.y) + d.y) / 3.0f;
+                o.z = ((a.z + b.z) + d.z) / 3.0f; o.w = ((a.w + b.w) + d.w) / 3.0f;
+              }
+              v[i] = o;
+            }
+          }
+        } else {  // TC_ROWS: generic [rows, k_in] fp32 input, zero padded to 64*kt1
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int gr = row0 + hw + NHW * i;
+            float x4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (gr < p.rows) {
+              const int k0 = t * KTILE + hl * 4;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (k0 + j < p.k_in) x4[j] = p.in[(size_t)gr * p.ld_in + k0 + j];
+            }
+            v[i] = make_float4(x4[0], x4[1], x4[2], x4[3]);
+          }
+        }
+        if (g >= ARING) mbar_wait(BAR(B_AEMPTY + slot), ((g / ARING) - 1) & 1, 1);
+        unsigned char* dst = sA + slot * TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) st_tile_f4(dst, hw + NHW * i, hl, v[i]);
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_AFULL + slot));
+      }
+    }
+  } else if (warp == WARP_LOAD) {
+    // ================================================================= loader: W2/W3 once, W1 K-tiles through the ring
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_wres, 4 * TILE_BYTES);
-      bulk_g2s(smem_u32(sW2), p.packed + (size_t)kt1 * TILE_BYTES, 2 * TILE_BYTES, bar_wres);
-      bulk_g2s(smem_u32(sW3), p.packed + (size_t)(kt1 + 2) * TILE_BYTES, 2 * TILE_BYTES, bar_wres);
+      mbar_arrive_expect_tx(BAR(B_WRES), 4 * TILE_BYTES);
+      bulk_g2s(smem_u32(sW2), p.packed + (size_t)kt1 * TILE_BYTES, 2 * TILE_BYTES, BAR(B_WRES));
+      bulk_g2s(smem_u32(sW3), p.packed + (size_t)(kt1 + 2) * TILE_BYTES, 2 * TILE_BYTES, BAR(B_WRES));
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         for (int t = 0; t < kt1; ++t, ++g) {
-          const uint32_t slot = g % RING;
-          if (g >= RING) mbar_wait(bar_empty + 8 * slot, ((g / RING) - 1) & 1, 1);
-          mbar_arrive_expect_tx(bar_full + 8 * slot, TILE_BYTES);
-          bulk_g2s(smem_u32(sRing + slot * TILE_BYTES), p.packed + (size_t)t * TILE_BYTES, TILE_BYTES, bar_full + 8 * slot);
+          const uint32_t slot = g % WRING;
+          if (g >= WRING) mbar_wait(BAR(B_WEMPTY + slot), ((g / WRING) - 1) & 1, 2);
+          mbar_arrive_expect_tx(BAR(B_WFULL + slot), TILE_BYTES);
+          bulk_g2s(smem_u32(sWr + slot * TILE_BYTES), p.packed + (size_t)t * TILE_BYTES, TILE_BYTES, BAR(B_WFULL + slot));
         }
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
-    // ================================================================= MMA warp (single issuing thread)
+  } else if (warp == WARP_MMA) {
+    // ================================================================= MMA issuer (single thread)
     if (lane == 0) {
-      uint32_t g = 0, aphase = 0;
-      bool wres_ok = false;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        // ---- layer 1: D = A[128 x 64*kt1] * W1^T
-        mbar_wait(bar_a, aphase, 2); aphase ^= 1;
+      uint32_t g = 0;           // K-tile counter shared by the A ring and the W1 ring
+      uint32_t hphase = 0;      // h_ready parity
+      uint32_t dfree_uses[2] = {0, 0};
+      // layer 1 of local tile j into accumulator j&1
+      auto issue_layer1 = [&](int j) {
+        const int b = j & 1;
+        if (j >= 2) { mbar_wait(BAR(B_DFREE + b), dfree_uses[b] & 1, 3); ++dfree_uses[b]; }
         tc_fence_after();
+        const uint32_t d = tmem_base + 128u * (uint32_t)b;
         for (int t = 0; t < kt1; ++t, ++g) {
-          const uint32_t slot = g % RING;
-          mbar_wait(bar_full + 8 * slot, (g / RING) & 1, 3);
+          const uint32_t sa = g % ARING, sw = g % WRING;
+          mbar_wait(BAR(B_AFULL + sa), (g / ARING) & 1, 4);
+          mbar_wait(BAR(B_WFULL + sw), (g / WRING) & 1, 5);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + t * TILE_BYTES), b_base = smem_u32(sRing + slot * TILE_BYTES);
+          const uint32_t a_base = smem_u32(sA + sa * TILE_BYTES), b_base = smem_u32(sWr + sw * TILE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tmem_d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (t | kk) != 0);
-          umma_commit(bar_empty + 8 * slot);  // frees the ring slot when these MMAs have read it
+            umma_bf16(d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (t | kk) != 0);
+          umma_commit(BAR(B_AEMPTY + sa));  // both ring slots are free once these MMAs have read them
+          umma_commit(BAR(B_WEMPTY + sw));
         }
-        umma_commit(bar_d);
-        if (!wres_ok) { mbar_wait(bar_wres, 0, 4); wres_ok = true; }
-        // ---- layer 2, 3: D = H[128 x 128] * W^T with resident weights
+        umma_commit(BAR(B_DFULL + b));
+      };
+      int j = 0;
+      const int first = blockIdx.x;
+      if (first < p.ntiles) issue_layer1(0);
+      mbar_wait(BAR(B_WRES), 0, 6);
+      for (int tile = first; tile < p.ntiles; tile += gridDim.x, ++j) {
+        const int b = j & 1;
+        if (tile + (int)gridDim.x < p.ntiles) issue_layer1(j + 1);  // runs under tile j's epilogues
+        const uint32_t d = tmem_base + 128u * (uint32_t)b;
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
-          mbar_wait(bar_a, aphase, 5); aphase ^= 1;
+          mbar_wait(BAR(B_HREADY), hphase, 7); hphase ^= 1;
           tc_fence_after();
           const unsigned char* w = layer == 0 ? sW2 : sW3;
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            const uint32_t a_base = smem_u32(sA + t * TILE_BYTES), b_base = smem_u32(w + t * TILE_BYTES);
+            const uint32_t a_base = smem_u32(sH + t * TILE_BYTES), b_base = smem_u32(w + t * TILE_BYTES);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(tmem_d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (t | kk) != 0);
+              umma_bf16(d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (t | kk) != 0);
           }
-          umma_commit(bar_d);
+          umma_commit(BAR(B_DFULL + b));
         }
       }
     }
     __syncwarp();
   } else {
-    // ================================================================= worker warps 0..7
-    const int q = warp & 3, h = warp >> 2;   // TMEM lane quadrant, column half
-    const int hw = tid >> 4, hl = tid & 15;  // half-warp id (0..15), lane within it
-    const int erow = 32 * q + lane;          // epilogue: this thread's row inside the tile
-    const uint32_t t_addr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * h);
-    uint32_t dphase = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    // ================================================================= epilogue warps 4..11
+    const int ew = warp - WARP_EPI0;
+    const int q = warp & 3, h = ew >> 2;  // TMEM lane quadrant (= warp id % 4), column half
+    const int erow = 32 * q + lane;       // this thread's row inside the tile
+    const int et = tid - NPROD;           // 0..255
+    const int ht = et & 127;              // thread index inside its column-half team
+    uint32_t dfull_uses[2] = {0, 0};
+    int j = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++j) {
       const int row0 = tile * TM;
-      // ---------------------------------------------------------------- gather -> A tile (bf16, swizzled)
-      if (p.mode == TC_EDGE) {
-        const int F = p.rows;
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-          const int r = hw + 16 * i;
-          const int f = row0 + r;
-          float4 v[6];
-          if (f < F) {
-            const int s = __ldg(p.idx + f), rr = __ldg(p.idx + (size_t)F + f);
-            const float* ps = p.src0 + (size_t)s * 128 + hl * 4;
-            const float* pr = p.src0 + (size_t)rr * 128 + hl * 4;
-            const float* pe = p.src1 + (size_t)f * 128 + hl * 4;
-            v[0] = ldg4(ps); v[1] = ldg4(ps + 64); v[2] = ldg4(pr); v[3] = ldg4(pr + 64);
-            v[4] = *reinterpret_cast<const float4*>(pe); v[5] = *reinterpret_cast<const float4*>(pe + 64);
-          } else {
-#pragma unroll
-            for (int t = 0; t < 6; ++t) v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int t = 0; t < 6; ++t) st_tile_f4(sA + t * TILE_BYTES, r, hl, v[t]);
-        }
-      } else if (p.mode == TC_CELL) {
-        const int C = p.rows;
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-          const int r = hw + 16 * i;
-          const int c = row0 + r;
-          float4 v0, v1, ag;
-          if (c < C) {
-            const float* px = p.src0 + (size_t)c * 128 + hl * 4;
-            v0 = *reinterpret_cast<const float4*>(px);
-            v1 = *reinterpret_cast<const float4*>(px + 64);
-            const int n0 = __ldg(p.idx + c), n1 = __ldg(p.idx + (size_t)C + c), n2 = __ldg(p.idx + 2 * (size_t)C + c);
-            const float4 a = ldg4(p.src1 + (size_t)n0 * 64 + hl * 4);
-            const float4 b = ldg4(p.src1 + (size_t)n1 * 64 + hl * 4);
-            const float4 d = ldg4(p.src1 + (size_t)n2 * 64 + hl * 4);
-            ag.x = ((a.x + b.x) + d.x) / 3.0f; ag.y = ((a.y + b.y) + d.y) / 3.0f;
-            ag.z = ((a.z + b.z) + d.z) / 3.0f; ag.w = ((a.w + b.w) + d.w) / 3.0f;
-          } else {
-            v0 = v1 = ag = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          st_tile_f4(sA, r, hl, v0);
-          st_tile_f4(sA + TILE_BYTES, r, hl, v1);
-          st_tile_f4(sA + 2 * TILE_BYTES, r, hl, ag);
-        }
-      } else {  // TC_ROWS: generic [rows, k_in] fp32 input, zero padded to 64*kt1
-        for (int t = 0; t < kt1; ++t) {
-#pragma unroll 2
-          for (int i = 0; i < 8; ++i) {
-            const int r = hw + 16 * i;
-            const int g = row0 + r;
-            float x4[4] = {0.f, 0.f, 0.f, 0.f};
-            if (g < p.rows) {
-              const int k0 = t * KTILE + hl * 4;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (k0 + j < p.k_in) x4[j] = p.in[(size_t)g * p.ld_in + k0 + j];
-            }
-            st_tile_f4(sA + t * TILE_BYTES, r, hl, make_float4(x4[0], x4[1], x4[2], x4[3]));
-          }
-        }
-      }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_a);
-
-      // ---------------------------------------------------------------- epilogues 1, 2: bias + SiLU -> bf16 H (A tiles 0,1)
+      const int b = j & 1;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(32 * q) << 16) + 128u * (uint32_t)b + (uint32_t)(64 * h);
+      // ---------------------------------------------------------------- epilogues 1, 2: bias + SiLU -> bf16 H tiles
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
-        mbar_wait(bar_d, dphase, 6); dphase ^= 1;
+        mbar_wait(BAR(B_DFULL + b), dfull_uses[b] & 1, 8); ++dfull_uses[b];
         tc_fence_after();
         const float* bias = sPar + layer * 128 + 64 * h;
-        unsigned char* hrow = sA + h * TILE_BYTES + (uint32_t)erow * 128u;
+        unsigned char* hrow = sH + h * TILE_BYTES + (uint32_t)erow * 128u;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float v[32];
           tmem_ld32(t_addr + 32 * half, v);
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {  // 8 columns = one 16-byte chunk
-            uint4 pk;
             float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = silu_fast(v[c4 * 8 + j] + bias[half * 32 + c4 * 8 + j]);
+            for (int jj = 0; jj < 8; ++jj) o[jj] = silu_fast(v[c4 * 8 + jj] + bias[half * 32 + c4 * 8 + jj]);
+            uint4 pk;
             pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]); pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
             const uint32_t chunk = (uint32_t)(half * 4 + c4);
             *reinterpret_cast<uint4*>(hrow + ((chunk ^ ((uint32_t)erow & 7u)) << 4)) = pk;
@@ -365,63 +409,91 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
         tc_fence_before();
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_a);
+        if (lane == 0) mbar_arrive(BAR(B_HREADY));
       }
       // ---------------------------------------------------------------- epilogue 3: bias (+ LayerNorm) (+ residual) -> HBM
-      mbar_wait(bar_d, dphase, 7); dphase ^= 1;
+      mbar_wait(BAR(B_DFULL + b), dfull_uses[b] & 1, 9); ++dfull_uses[b];
       tc_fence_after();
-      float v[64];
-      tmem_ld32(t_addr, v);
-      tmem_ld32(t_addr + 32, v + 32);
-      tc_fence_before();
-      {
-        const float* b3 = sPar + 2 * 128 + 64 * h;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] += b3[j];
-      }
-      if (p.ln_w != nullptr) {
+      const float* b3 = sPar + 2 * 128 + 64 * h;
+      float mean = 0.f, rstd = 1.f;
+      const bool has_ln = (p.ln_w != nullptr);
+      if (has_ln) {
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) s += v[j];
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          tmem_ld32(t_addr + 32 * half, v);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) s += v[jj] + b3[half * 32 + jj];
+        }
         sRed[h * 128 + erow] = s;
-        named_bar_sync(1, NWORK);
-        const float mean = (sRed[erow] + sRed[128 + erow]) * (1.0f / 128.0f);
+        named_bar_sync(1, NEPI);
+        mean = (sRed[erow] + sRed[128 + erow]) * (1.0f / 128.0f);
         float qv = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) { const float d = v[j] - mean; qv = fmaf(d, d, qv); }
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          tmem_ld32(t_addr + 32 * half, v);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) { const float d = v[jj] + b3[half * 32 + jj] - mean; qv = fmaf(d, d, qv); }
+        }
         sRed[256 + h * 128 + erow] = qv;
-        named_bar_sync(1, NWORK);
-        const float rstd = 1.0f / sqrtf((sRed[256 + erow] + sRed[256 + 128 + erow]) * (1.0f / 128.0f) + 1e-5f);
-        const float* gw = sPar + 3 * 128 + 64 * h;
-        const float* gb = sPar + 4 * 128 + 64 * h;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = (v[j] - mean) * rstd * gw[j] + gb[j];
+        named_bar_sync(1, NEPI);
+        rstd = 1.0f / sqrtf((sRed[256 + erow] + sRed[256 + 128 + erow]) * (1.0f / 128.0f) + 1e-5f);
       }
-      const int grow = row0 + erow;
-      if (grow < p.rows) {
-        if (p.mode == TC_ROWS) {
-          if (p.n_out == HIDN && (p.ld_out & 3) == 0) {
-            float* o = p.out0 + (size_t)grow * p.ld_out + 64 * h;
+      const bool staged = (p.mode != TC_ROWS) || (p.n_out == HIDN && (p.ld_out & 3) == 0);
+      const float* gw = sPar + 3 * 128 + 64 * h;
+      const float* gb = sPar + 4 * 128 + 64 * h;
+      unsigned char* stage = sH + h * TILE_BYTES;  // [128 rows][32 fp32], 16-byte chunks XOR-swizzled by (row & 7)
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld32(t_addr + 32 * half, v);
+        if (half == 1) {  // last TMEM read of this tile: the accumulator may be overwritten by layer 1 of tile j+2
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_DFREE + b));
+        }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) *reinterpret_cast<float4*>(o + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
+        for (int jj = 0; jj < 32; ++jj) {
+          float y = v[jj] + b3[half * 32 + jj];
+          if (has_ln) y = (y - mean) * rstd * gw[half * 32 + jj] + gb[half * 32 + jj];
+          v[jj] = y;
+        }
+        if (staged) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (64 * h + j < p.n_out) p.out0[(size_t)grow * p.ld_out + 64 * h + j] = v[j];
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(stage + (uint32_t)erow * 128u + (((uint32_t)c ^ ((uint32_t)erow & 7u)) << 4)) =
+                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          named_bar_sync(2 + h, 128);
+          // coalesced read-out: 8 threads per row -> every warp access covers 4 full 128-byte lines
+          const int col0 = 64 * h + 32 * half;
+#pragma unroll 4
+          for (int pass = 0; pass < 8; ++pass) {
+            const int r = pass * 16 + (ht >> 3), cp = ht & 7;
+            const int grow = row0 + r;
+            if (grow < p.rows) {
+              const float4 y = *reinterpret_cast<const float4*>(stage + (uint32_t)r * 128u + ((uint32_t)cp << 4));
+              const int col = col0 + 4 * (cp ^ (r & 7));
+              if (p.mode == TC_ROWS) {
+                *reinterpret_cast<float4*>(p.out0 + (size_t)grow * p.ld_out + col) = y;
+              } else {
+                if (p.out0) *reinterpret_cast<float4*>(p.out0 + (size_t)grow * 128 + col) = y;
+                if (p.out1) {
+                  const float4 rv = *reinterpret_cast<const float4*>((p.mode == TC_CELL ? p.src0 : p.src1) + (size_t)grow * 128 + col);
+                  *reinterpret_cast<float4*>(p.out1 + (size_t)grow * 128 + col) = make_float4(rv.x + y.x, rv.y + y.y, rv.z + y.z, rv.w + y.w);
+                }
+              }
+            }
           }
+          named_bar_sync(2 + h, 128);  // staging tile is rewritten by the next half / the next tile's H
         } else {
-          if (p.out0) {
-            float* o = p.out0 + (size_t)grow * 128 + 64 * h;
+          const int grow = row0 + erow;
+          if (grow < p.rows) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) *reinterpret_cast<float4*>(o + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.out1) {
-            const float* res = (p.mode == TC_CELL ? p.src0 : p.src1) + (size_t)grow * 128 + 64 * h;  // fp32 residual stream (x or e)
-            float* o = p.out1 + (size_t)grow * 128 + 64 * h;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float4 rv = *reinterpret_cast<const float4*>(res + 4 * j);
-              *reinterpret_cast<float4*>(o + 4 * j) = make_float4(rv.x + v[4 * j], rv.y + v[4 * j + 1], rv.z + v[4 * j + 2], rv.w + v[4 * j + 3]);
+            for (int jj = 0; jj < 32; ++jj) {
+              const int col = 64 * h + 32 * half + jj;
+              if (col < p.n_out) p.out0[(size_t)grow * p.ld_out + col] = v[jj];
             }
           }
         }
@@ -431,9 +503,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
   // ---------------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_d, 128);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -482,11 +554,11 @@ static int launch_tc(TcParams& p, const fvgn_mlp_t* m, cudaStream_t st) {
   p.k_in = m->k_in; p.n_out = m->n_out;
   p.kt1 = kt_of(m->k_in);
   p.ntiles = cdiv(p.rows, TM);
-  const SmemLayout L = smem_layout(p.kt1);
-  static int configured_max = 0;
-  if ((int)L.total > configured_max) {
+  const SmemLayout L = smem_layout();
+  static bool configured = false;
+  if (!configured) {
     FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    configured_max = (int)L.total;
+    configured = true;
   }
   const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
   fused_mlp_tc_kernel<<<grid, NTHREADS, L.total, st>>>(p);

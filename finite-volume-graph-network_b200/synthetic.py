@@ -203,7 +203,7 @@ def airfoil_mesh(seed=0, n_target=5200, T=3, xlim=(-10.0, 20.0), ylim=(-10.0, 10
                 meta=dict(kind="airfoil", seed=seed, aoa=float(aoa)))
 
 
-def grid_mesh(nx=61, ny=31, seed=0, T=3, jitter=0.25, hole=True, xlim=(0.0, 1.6), ylim=(0.0, 0.41)):
+def grid_mesh(nx=61, ny=31, seed=0, T=3, jitter=0.25, hole=True, xlim=(0.0, 1.6), ylim=(0.0, 0.41), shuffle=True):
     """Jittered structured triangulation with one rectangular hole (WALL_BOUNDARY) — the shape of the
     1M-cell sweep (nx=ny=708 -> C~1.0e6, F~1.5e6, N~0.5e6).  Vectorised, O(N)."""
     rng = np.random.default_rng(seed)
@@ -236,8 +236,9 @@ def grid_mesh(nx=61, ny=31, seed=0, T=3, jitter=0.25, hole=True, xlim=(0.0, 1.6)
     t2 = np.where(flip[:, None], np.stack([b, c, d], 1), np.stack([a, c, d], 1))
     in_hole = ((q_i >= i0) & (q_i < i1) & (q_j >= j0) & (q_j < j1)).reshape(-1)
     tri = np.concatenate([t1[~in_hole], t2[~in_hole]]).astype(np.int32)
-    perm = rng.permutation(tri.shape[0])  # reference meshes are not cell-ordered; neither is this one
-    tri = tri[perm]
+    perm = rng.permutation(tri.shape[0])  # shuffle=True: worst case, cell numbering carries no locality at all
+    if shuffle:
+        tri = tri[perm]
     pos, tri, used = _compact(pos, tri)
     pos32 = pos.astype(np.float32)
     nt = _box_types(pos32, np.float32(xmin), np.float32(xmax), np.float32(ymin), np.float32(ymax),
