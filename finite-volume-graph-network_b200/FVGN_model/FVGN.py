@@ -84,9 +84,19 @@ class FVGN(nn.Module):
         graph.x, graph.edge_attr = x_in, e_in
         if capture is not None:
             capture["cell_in"], capture["edge_in"] = x_in, e_in
-        _, decoded = self.model(graph, graph_node, topo=topo, capture=capture)
-        face_area, _, _ = self._face_area(graph, graph_edge, topo, dt)
-        loss_cont, delta_u = self.intergator(decoded=decoded, unv=graph.unv, rho=rho, rhs_coef=1.0, face_area=face_area, cells_face_T=topo.cfT)
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # differentiable path: forward and backward both run in libfvgn_b200 kernels (autograd.NetFunction)
+            if self.math_mode != "fp32":
+                raise NotImplementedError("training runs in strict fp32; call set_math_mode('fp32')")
+            from ..autograd import NetFunction, network_params
+
+            decoded, delta_u, face_area = NetFunction.apply(self, topo, x_in, e_in, graph_edge.x.contiguous(), graph.cell_area.contiguous(),
+                                                            graph.unv.contiguous(), rho, dt, *network_params(self))
+            loss_cont = 0
+        else:
+            _, decoded = self.model(graph, graph_node, topo=topo, capture=capture)
+            face_area, _, _ = self._face_area(graph, graph_edge, topo, dt)
+            loss_cont, delta_u = self.intergator(decoded=decoded, unv=graph.unv, rho=rho, rhs_coef=1.0, face_area=face_area, cells_face_T=topo.cfT)
         if capture is not None:
             capture["decoded"], capture["face_area"], capture["delta_u"] = decoded, face_area, delta_u
         if self.training:

@@ -41,6 +41,16 @@ _SIGS = {
     "fvgn_integrator_fwd": (_I, [_P, _P, _P, _P, _I, _F, _F, _P, _P, _P]),
     "fvgn_loss_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P]),
     "fvgn_loss_workspace_floats": (_S, [_I]),
+    "fvgn_mlp_grad_floats": (_S, [_I]),
+    "fvgn_mlp_bwd_workspace_floats": (_S, [_I]),
+    "fvgn_mlp_rows_bwd": (_I, [C.POINTER(MlpT), _P, _I, _I, _P, _I, _P, _I, _P, _P, _P]),
+    "fvgn_cell_block_bwd": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P]),
+    "fvgn_edge_block_bwd": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "fvgn_segment_sum_rows": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _F, _P, _I, _P]),
+    "fvgn_edge_grad_combine": (_I, [_P, _P, _P, _P, _I, _P, _P]),
+    "fvgn_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "fvgn_integrator_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P]),
+    "fvgn_face_area_bn_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P]),
 }
 
 _lib = None

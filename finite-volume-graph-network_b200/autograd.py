@@ -1,0 +1,112 @@
+"""Training path: torch.autograd.Function wrappers whose forward AND backward run entirely in libfvgn_b200 kernels, so the
+reference's `loss.backward(); optimizer.step()` flow (train.py:194-225) works unchanged on this module.
+
+  NetFunction   normalised features -> Encoder -> 15 GnBlocks -> Decoder -> face-area BatchNorm -> Intergrator
+                saves only the per-layer INPUTS (x, e, x', node_agg); the backward kernels recompute inside their tiles
+  LossFunction  compute_FVM_loss forward / backward
+Strict fp32 (FFMA kernels); every reduction is a fixed-order segment sum => gradients are run-to-run deterministic."""
+import torch
+
+from . import ops
+
+
+def network_mlps(model):
+    """FusedMLPs in `model.parameters()` registration order"""
+    epd = model.model
+    mlps = [epd.encoder.eb_encoder, epd.encoder.cb_encoder]
+    for blk in epd.processer_list:
+        mlps += [blk.eb_module.net, blk.cb_module.net]
+    mlps.append(epd.decoder.edge_decode_module)
+    return mlps
+
+
+def network_params(model):
+    mlps = network_mlps(model)
+    params = [p for m in mlps for p in m.parameters()]
+    assert [id(p) for p in params] == [id(p) for p in model.model.parameters()], "parameter order drifted from the module tree"
+    bn = model._grid_feature_normalizer
+    return params + [bn.weight, bn.bias]
+
+
+class NetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, topo, cell_in, edge_in, graph_edge_x, cell_area, unv, rho, dt, *params):
+        epd = model.model
+        enc_c, enc_e = epd.encoder.cb_encoder, epd.encoder.eb_encoder
+        x = ops.mlp_rows_fwd(enc_c.mlp_ref(), cell_in, 0)
+        e = ops.mlp_rows_fwd(enc_e.mlp_ref(), edge_in, 0)
+        saved = []
+        for blk in epd.processer_list:
+            cb, eb = blk.cb_module.net, blk.eb_module.net
+            na = ops.node_aggregate_fwd(e, topo.node_ptr, topo.node_items, topo.N)
+            xp, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, na, topo.cnT, 0)
+            _, e_new = ops.edge_block_fwd(eb.mlp_ref(), xp, e, topo.nc, 0)
+            saved.append((x, e, xp, na))
+            x, e = x_new, e_new
+        decoded = ops.mlp_rows_fwd(epd.decoder.edge_decode_module.mlp_ref(), e, 0)
+        bn = model._grid_feature_normalizer
+        use_batch = model.training or not bn.track_running_stats
+        face_area, raw, stats = ops.face_area_bn_fwd(graph_edge_x, cell_area, topo.nc, dt, use_batch, bn.weight.detach(), bn.bias.detach(),
+                                                     bn.running_mean, bn.running_var, want_raw=True)
+        if model.training:
+            bn.num_batches_tracked += 1
+        delta_u, _ = ops.integrator_fwd(decoded, unv, face_area, topo.cfT, rho, 1.0)
+        ctx.model, ctx.topo, ctx.rho = model, topo, rho
+        ctx.saved = saved
+        ctx.aux = (cell_in, edge_in, e, decoded, face_area, raw, stats, unv)
+        ctx.mark_non_differentiable(face_area)
+        return decoded, delta_u, face_area
+
+    @staticmethod
+    def backward(ctx, g_decoded, g_delta_u, _g_fa):
+        model, topo = ctx.model, ctx.topo
+        epd = model.model
+        cell_in, edge_in, e_final, decoded, face_area, raw, stats, unv = ctx.aux
+        bt = topo.backward_tables()
+        dev = decoded.device
+        g_dec = (g_decoded.contiguous().clone() if g_decoded is not None else torch.zeros_like(decoded))
+        if g_delta_u is None:
+            g_delta_u = torch.zeros((topo.C, 2), dtype=torch.float32, device=dev)
+        # Intergrator^T (p_face is detached in the forward, FVGN.py:231) and the BatchNorm affine pair
+        fptr, fitems = bt["face_from_cell"]
+        g_fa = ops.integrator_bwd_(g_dec, decoded, unv, face_area, g_delta_u.contiguous(), fptr, fitems, topo.C, ctx.rho, 1.0)
+        g_bn = ops.face_area_bn_bwd(g_fa, raw, stats)
+        grads = {}
+        dec = epd.decoder.edge_decode_module
+        grads[id(dec)], g_e = ops.mlp_rows_bwd(dec.mlp_ref(), e_final, g_dec, want_d_in=True)
+        g_x = None  # the last layer's cell latent feeds nothing but its own EdgeBlock
+        cptr, citems = bt["cell_from_face"]
+        nptr, nitems = bt["node_from_cell"]
+        for blk, (x_in, e_in, xp, na) in zip(reversed(epd.processer_list), reversed(ctx.saved)):
+            cb, eb = blk.cb_module.net, blk.eb_module.net
+            grads[id(eb)], dA_e = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e)
+            # d x' = residual path + transpose of the x'[s], x'[r] gathers (cell <- face segment sum)
+            g_xp = ops.segment_sum_rows(dA_e, topo.F, 0, 128, 128, cptr, citems, topo.C, base=g_x, scale=1.0)
+            grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, topo.cnT, g_xp, d_x_base=g_x)
+            # transposes of the twice-message aggregation: cell -> node (x 1/3), node -> face halves
+            g_na = ops.segment_sum_rows(dA_c, topo.C, 128, 0, 64, nptr, nitems, topo.N, base=None, scale=1.0 / 3.0)
+            g_e = ops.edge_grad_combine(g_e, dA_e, g_na, topo.fn)
+            g_x = dA_c[:, 0:128]
+        grads[id(epd.encoder.cb_encoder)], _ = ops.mlp_rows_bwd(epd.encoder.cb_encoder.mlp_ref(), cell_in, g_x)
+        grads[id(epd.encoder.eb_encoder)], _ = ops.mlp_rows_bwd(epd.encoder.eb_encoder.mlp_ref(), edge_in, g_e)
+        flat = [g for m in network_mlps(model) for g in grads[id(m)]]
+        flat += [g_bn[0:1], g_bn[1:2]]
+        return (None,) * 9 + tuple(flat)
+
+
+class LossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_du, target_du, pred_edge, target_face, mask, cell_batch, face_batch, n_graphs, mode, w_mom, w_uv, w_p):
+        m8 = mask.to(torch.uint8).contiguous()
+        pred_du, target_du = pred_du.contiguous(), target_du.contiguous()
+        pred_edge, target_face = pred_edge.contiguous(), target_face.contiguous()
+        out, ws = ops.loss_fwd(pred_du, target_du, pred_edge, target_face, m8, cell_batch, face_batch, n_graphs, mode, w_mom, w_uv, w_p)
+        ctx.args = (pred_du, target_du, pred_edge, target_face, m8, cell_batch, face_batch, n_graphs, mode, w_mom, w_uv, w_p, ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        pred_du, target_du, pred_edge, target_face, m8, cb, fb, n_graphs, mode, w_mom, w_uv, w_p, ws = ctx.args
+        g_loss = g_out[0:1].contiguous()  # only out[0] (the loss) is a differentiable quantity; stays on the device
+        g_du, g_edge = ops.loss_bwd(pred_du, target_du, pred_edge, target_face, m8, cb, fb, n_graphs, mode, w_mom, w_uv, w_p, g_loss, ws)
+        return (g_du, None, g_edge) + (None,) * 9

@@ -314,6 +314,97 @@ __global__ void loss_final_kernel(const double* __restrict__ part, int n_seg, in
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ backward of the head
+// coef[seg][3] = d loss / d (sum of squared errors of momentum | face uv | face p) for that segment
+__global__ void loss_coef_kernel(const double* __restrict__ part, const float* __restrict__ seg_terms, int n_seg, int mode, float w_mom,
+                                 float w_uv, float w_p, const float* __restrict__ g_loss, float* __restrict__ coef) {
+  const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= n_seg) return;
+  double nint = 0;
+  for (int k = 0; k < LOSS_CHUNKS; ++k) nint += part[((size_t)seg * LOSS_CHUNKS + k) * 6 + 3];
+  const double nc = part[(size_t)seg * LOSS_CHUNKS * 6 + 1], nf = part[(size_t)seg * LOSS_CHUNKS * 6 + 5];
+  const float g = (g_loss ? *g_loss : 1.0f) / ((float)n_seg * seg_terms[4 * seg + 3]);  // d mean(log tot) / d tot_seg
+  const float dm = (mode == 1) ? 1.0f : 0.5f;                                            // mean over 2 channels vs sum
+  const float du = (mode == 0) ? 0.5f : 1.0f;
+  coef[3 * seg + 0] = g * w_mom * dm / (float)fmax(nc, 1.0);
+  coef[3 * seg + 1] = g * w_uv * du / (float)fmax(nint, 1.0);
+  coef[3 * seg + 2] = g * w_p / (float)fmax(nf, 1.0);
+}
+
+__global__ void loss_bwd_kernel(const float* __restrict__ pdu, const float* __restrict__ tdu, const float* __restrict__ pe,
+                                const float* __restrict__ tf, const uint8_t* __restrict__ mask, const int32_t* __restrict__ cb,
+                                const int32_t* __restrict__ fb, int C, int F, int segmented, const float* __restrict__ coef,
+                                float* __restrict__ g_du, float* __restrict__ g_edge) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    const float k = 2.0f * coef[3 * (segmented ? cb[i] : 0) + 0];
+    g_du[2 * (size_t)i] = k * (pdu[2 * (size_t)i] - tdu[2 * (size_t)i]);
+    g_du[2 * (size_t)i + 1] = k * (pdu[2 * (size_t)i + 1] - tdu[2 * (size_t)i + 1]);
+  }
+  if (i < F) {
+    const int seg = segmented ? fb[i] : 0;
+    const float ku = mask[i] ? 2.0f * coef[3 * seg + 1] : 0.0f, kp = 2.0f * coef[3 * seg + 2];
+    float* g = g_edge + 5 * (size_t)i;
+    g[0] = ku * (pe[5 * (size_t)i] - tf[3 * (size_t)i]);
+    g[1] = ku * (pe[5 * (size_t)i + 1] - tf[3 * (size_t)i + 1]);
+    g[2] = kp * (pe[5 * (size_t)i + 2] - tf[3 * (size_t)i + 2]);
+    g[3] = 0.0f;
+    g[4] = 0.0f;
+  }
+}
+
+// transpose of the Intergrator's three gathers: one thread per face walks its incident (cell, k) pairs in CSR order
+__global__ void integrator_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ unv, const float* __restrict__ fa,
+                                      const float* __restrict__ g_du, const int32_t* __restrict__ ptr, const int32_t* __restrict__ items,
+                                      int C, int F, float inv_rho, float rhs, float* __restrict__ g_dec, float* __restrict__ g_fa) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const float u = dec[5 * (size_t)f], v = dec[5 * (size_t)f + 1], p = dec[5 * (size_t)f + 2], a = fa[f];
+  float gu = 0.f, gv = 0.f, gdx = 0.f, gdy = 0.f, ga = 0.f;
+  for (int i = ptr[f]; i < ptr[f + 1]; ++i) {
+    const int pos = items[i];
+    const int k = pos / C, c = pos - k * C;
+    const float gx = g_du[2 * (size_t)c], gy = g_du[2 * (size_t)c + 1];
+    const float nx = unv[(size_t)c * 6 + 2 * k], ny = unv[(size_t)c * 6 + 2 * k + 1];
+    gu += -rhs * a * (gx * (2.0f * u * nx + v * ny) + gy * (v * nx));
+    gv += -rhs * a * (gx * (u * ny) + gy * (u * nx + 2.0f * v * ny));
+    gdx += gx;
+    gdy += gy;
+    ga += -rhs * (gx * ((u * u) * nx + (u * v) * ny) + gy * ((v * u) * nx + (v * v) * ny) + inv_rho * p * (gx * nx + gy * ny));
+  }
+  float* g = g_dec + 5 * (size_t)f;
+  g[0] += gu;
+  g[1] += gv;  // g[2] (pressure) gets no gradient from the integrator: p_face is detached (FVGN.py:231)
+  g[3] += gdx;
+  g[4] += gdy;
+  g_fa[f] = ga;
+}
+
+// d BN weight = sum g * xhat ; d BN bias = sum g       (xhat from the saved raw feature and the (mean, invstd) used forward)
+__global__ void __launch_bounds__(RED_THREADS) bn_bwd_partial_kernel(const float* __restrict__ g_fa, const float* __restrict__ raw,
+                                                                    const float* __restrict__ stats, int F, double* __restrict__ part) {
+  __shared__ double sh[32];
+  const int per = (F + gridDim.x - 1) / gridDim.x;
+  const int f0 = blockIdx.x * per, f1 = min(F, f0 + per);
+  double sw = 0.0, sb = 0.0;
+  for (int f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
+    const float xh = (raw[f] - stats[0]) * stats[1];
+    sw += (double)(g_fa[f] * xh);
+    sb += (double)g_fa[f];
+  }
+  sw = block_reduce_sum(sw, sh);
+  sb = block_reduce_sum(sb, sh);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = sw; part[2 * blockIdx.x + 1] = sb; }
+}
+__global__ void bn_bwd_final_kernel(const double* __restrict__ part, int nb, float* __restrict__ g_wb) {
+  if (threadIdx.x != 0) return;
+  double sw = 0.0, sb = 0.0;
+  for (int b = 0; b < nb; ++b) { sw += part[2 * b]; sb += part[2 * b + 1]; }
+  g_wb[0] = (float)sw;
+  g_wb[1] = (float)sb;
+}
+
 }  // namespace fvgn
 
 using namespace fvgn;
@@ -442,6 +533,52 @@ extern "C" int fvgn_loss_fwd(const float* pred_delta_u, const float* target_delt
                                                                         cell_batch, face_batch, n_cells, n_faces, mode != 0, part);
   FVGN_LAUNCH_CHECK();
   loss_final_kernel<<<1, 256, 0, st>>>(part, n_seg, mode, w_mom, w_uv, w_p, out, seg_terms);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fvgn_loss_bwd(const float* pred_delta_u, const float* target_delta_u, const float* pred_edge, const float* target_face,
+                             const uint8_t* mask_interior, const int32_t* cell_batch, const int32_t* face_batch, int n_cells, int n_faces,
+                             int n_graphs, int mode, float w_mom, float w_uv, float w_p, const float* g_loss, const float* fwd_workspace,
+                             float* g_delta_u, float* g_edge, float* coef_scratch, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(pred_delta_u && target_delta_u && pred_edge && target_face && mask_interior && fwd_workspace && g_delta_u && g_edge && coef_scratch,
+                 "NULL pointer");
+  FVGN_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0,1,2");
+  FVGN_CHECK_ARG(mode == 0 || (cell_batch && face_batch && n_graphs >= 1 && n_graphs <= 1024), "global_mean needs batch vectors");
+  const int n_seg = (mode == 0) ? 1 : n_graphs;
+  const double* part = reinterpret_cast<const double*>(fwd_workspace);
+  const float* seg_terms = reinterpret_cast<const float*>(part + (size_t)n_seg * LOSS_CHUNKS * 6);
+  cudaStream_t st = as_stream(stream);
+  loss_coef_kernel<<<cdiv(n_seg, 128), 128, 0, st>>>(part, seg_terms, n_seg, mode, w_mom, w_uv, w_p, g_loss, coef_scratch);
+  FVGN_LAUNCH_CHECK();
+  const int n = max(n_cells, n_faces);
+  loss_bwd_kernel<<<cdiv(n, 256), 256, 0, st>>>(pred_delta_u, target_delta_u, pred_edge, target_face, mask_interior, cell_batch, face_batch,
+                                                 n_cells, n_faces, mode != 0, coef_scratch, g_delta_u, g_edge);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fvgn_integrator_bwd(const float* decoded, const float* unv, const float* face_area, const float* g_delta_u,
+                                   const int32_t* face_ptr, const int32_t* face_items, int n_cells, int n_faces, float rho, float rhs_coef,
+                                   float* g_decoded, float* g_face_area, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(decoded && unv && face_area && g_delta_u && face_ptr && face_items && g_decoded && g_face_area, "NULL pointer");
+  FVGN_CHECK_ARG(rho != 0.f, "rho must be non-zero");
+  if (n_faces <= 0) return 0;
+  integrator_bwd_kernel<<<cdiv(n_faces, 256), 256, 0, as_stream(stream)>>>(decoded, unv, face_area, g_delta_u, face_ptr, face_items, n_cells,
+                                                                           n_faces, 1.0f / rho, rhs_coef, g_decoded, g_face_area);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fvgn_face_area_bn_bwd(const float* g_face_area, const float* raw, const float* batch_stats, int n_faces, float* g_weight_bias,
+                                     float* workspace, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(g_face_area && raw && batch_stats && g_weight_bias && workspace && n_faces > 0, "NULL pointer");
+  FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "workspace must be 8B aligned");
+  double* part = reinterpret_cast<double*>(workspace);
+  const int nb = min(RED_BLOCKS, cdiv(n_faces, RED_THREADS));
+  bn_bwd_partial_kernel<<<nb, RED_THREADS, 0, as_stream(stream)>>>(g_face_area, raw, batch_stats, n_faces, part);
+  FVGN_LAUNCH_CHECK();
+  bn_bwd_final_kernel<<<1, 32, 0, as_stream(stream)>>>(part, nb, g_weight_bias);
   FVGN_LAUNCH_CHECK();
   return 0;
 }

@@ -352,3 +352,107 @@ def loss_fwd(pred_du, target_du, pred_edge, target_face, mask_interior, cell_bat
     check(L.fvgn_loss_fwd(_p(pred_du), _p(target_du), _p(pred_edge), _p(target_face), _p(m8), _p(cell_batch), _p(face_batch), pred_du.shape[0],
                           pred_edge.shape[0], n_graphs, mode, float(w_mom), float(w_uv), float(w_p), _p(out), _p(ws), _stream()), "loss_fwd")
     return out, ws
+
+
+# ------------------------------------------------------------------------------------------------ backward (training)
+def _mlp_grad_views(mlp: MlpRef, g):
+    """split the flat gradient buffer of fvgn_mlp_*_bwd into tensors shaped like the parameters"""
+    k = mlp.k_in
+    o = 0
+    dW1 = g[o:o + 128 * k].view(128, k); o += 128 * k
+    dW2 = g[o:o + 16384].view(128, 128); o += 16384
+    dW3 = g[o:o + 16384].view(128, 128)[:mlp.n_out]; o += 16384
+    db1, db2, db3, dg, dbeta = (g[o + 128 * i:o + 128 * (i + 1)] for i in range(5))
+    out = [dW1, db1, dW2, db2, dW3, db3[:mlp.n_out]]
+    if len(mlp.tensors) == 8:
+        out += [dg, dbeta]
+    return out
+
+
+def _bwd_buffers(mlp: MlpRef, device):
+    L = _lib.lib()
+    grads = torch.empty(L.fvgn_mlp_grad_floats(mlp.k_in), dtype=torch.float32, device=device)
+    ws = torch.empty(L.fvgn_mlp_bwd_workspace_floats(mlp.k_in), dtype=torch.float32, device=device)
+    return grads, ws
+
+
+def mlp_rows_bwd(mlp: MlpRef, x, d_out, want_d_in=False):
+    _req(x, torch.float32, "x", 2), _req(d_out, torch.float32, "d_out", 2)
+    grads, ws = _bwd_buffers(mlp, x.device)
+    d_in = torch.empty((x.shape[0], mlp.k_in), dtype=torch.float32, device=x.device) if want_d_in else None
+    _count(2)
+    check(_lib.lib().fvgn_mlp_rows_bwd(C.byref(mlp.struct), _p(x), _ld(x), x.shape[0], _p(d_out), _ld(d_out), _p(d_in),
+                                       _ld(d_in) if d_in is not None else 0, _p(grads), _p(ws), _stream()), "mlp_rows_bwd")
+    return _mlp_grad_views(mlp, grads), d_in
+
+
+def cell_block_bwd(mlp: MlpRef, x, node_agg, cells_node_T, d_x_prime, d_x_base=None):
+    _cf(x, "x"), _cf(node_agg, "node_agg"), _ci(cells_node_T, "cells_node_T", 3), _cf(d_x_prime, "d_x_prime")
+    Cn = x.shape[0]
+    grads, ws = _bwd_buffers(mlp, x.device)
+    d_in = torch.empty((Cn, 192), dtype=torch.float32, device=x.device)
+    _count(2)
+    check(_lib.lib().fvgn_cell_block_bwd(C.byref(mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(d_x_prime), _p(d_x_base),
+                                         _ld(d_x_base) if d_x_base is not None else 0, _p(d_in), _p(grads), _p(ws), _stream()), "cell_block_bwd")
+    return _mlp_grad_views(mlp, grads), d_in
+
+
+def edge_block_bwd(mlp: MlpRef, x_prime, e, neighbour_cell, d_e_prime):
+    _cf(x_prime, "x_prime"), _cf(e, "e"), _ci(neighbour_cell, "neighbour_cell", 2), _cf(d_e_prime, "d_e_prime")
+    F = e.shape[0]
+    grads, ws = _bwd_buffers(mlp, e.device)
+    d_in = torch.empty((F, 384), dtype=torch.float32, device=e.device)
+    _count(2)
+    check(_lib.lib().fvgn_edge_block_bwd(C.byref(mlp.struct), _p(x_prime), _p(e), _p(neighbour_cell), F, _p(d_e_prime), _p(d_in), _p(grads), _p(ws),
+                                         _stream()), "edge_block_bwd")
+    return _mlp_grad_views(mlp, grads), d_in
+
+
+def segment_sum_rows(src, n_src, col0, part_stride, width, ptr, items, n_dst, base=None, scale=1.0):
+    _req(src, torch.float32, "src", 2), _ci(ptr, "ptr"), _ci(items, "items")
+    out = torch.empty((n_dst, width), dtype=torch.float32, device=src.device)
+    _count(1)
+    check(_lib.lib().fvgn_segment_sum_rows(_p(src), _ld(src), n_src, col0, part_stride, width, _p(ptr), _p(items), n_dst, _p(base),
+                                           _ld(base) if base is not None else 0, float(scale), _p(out), width, _stream()), "segment_sum_rows")
+    return out
+
+
+def edge_grad_combine(g_e_out, dA_edge, g_node, face_node):
+    _cf(g_e_out, "g_e_out"), _cf(dA_edge, "dA_edge"), _cf(g_node, "g_node"), _ci(face_node, "face_node", 2)
+    out = torch.empty_like(g_e_out)
+    _count(1)
+    check(_lib.lib().fvgn_edge_grad_combine(_p(g_e_out), _p(dA_edge), _p(g_node), _p(face_node), g_e_out.shape[0], _p(out), _stream()),
+          "edge_grad_combine")
+    return out
+
+
+def loss_bwd(pred_du, target_du, pred_edge, target_face, mask8, cell_batch, face_batch, n_graphs, mode, w_mom, w_uv, w_p, g_loss, fwd_ws):
+    dev = pred_du.device
+    g_du = torch.empty_like(pred_du)
+    g_edge = torch.empty((pred_edge.shape[0], 5), dtype=torch.float32, device=dev)
+    coef = torch.empty(3 * max(n_graphs, 1), dtype=torch.float32, device=dev)
+    _count(2)
+    check(_lib.lib().fvgn_loss_bwd(_p(pred_du), _p(target_du), _p(pred_edge), _p(target_face), _p(mask8), _p(cell_batch), _p(face_batch),
+                                   pred_du.shape[0], pred_edge.shape[0], n_graphs, mode, float(w_mom), float(w_uv), float(w_p), _p(g_loss),
+                                   _p(fwd_ws), _p(g_du), _p(g_edge), _p(coef), _stream()), "loss_bwd")
+    return g_du, g_edge
+
+
+def integrator_bwd_(g_decoded, decoded, unv, face_area, g_delta_u, face_ptr, face_items, n_cells, rho, rhs_coef=1.0):
+    """g_decoded[F,5] is updated in place; returns g_face_area[F,1]"""
+    _cf(g_decoded, "g_decoded"), _cf(decoded, "decoded"), _cf(unv, "unv"), _cf(face_area, "face_area"), _cf(g_delta_u, "g_delta_u")
+    F = decoded.shape[0]
+    g_fa = torch.empty((F, 1), dtype=torch.float32, device=decoded.device)
+    _count(1)
+    check(_lib.lib().fvgn_integrator_bwd(_p(decoded), _p(unv), _p(face_area), _p(g_delta_u), _p(face_ptr), _p(face_items), n_cells, F, float(rho),
+                                         float(rhs_coef), _p(g_decoded), _p(g_fa), _stream()), "integrator_bwd")
+    return g_fa
+
+
+def face_area_bn_bwd(g_face_area, raw, stats):
+    L = _lib.lib()
+    out = torch.empty(2, dtype=torch.float32, device=raw.device)
+    ws = torch.empty(L.fvgn_norm_workspace_floats(1) // 2 + 8, dtype=torch.float64, device=raw.device)
+    _count(2)
+    check(L.fvgn_face_area_bn_bwd(_p(g_face_area), _p(raw), _p(stats), raw.shape[0], _p(out), _p(ws), _stream()), "face_area_bn_bwd")
+    return out

@@ -16,7 +16,8 @@ def compute_FVM_loss(params=None, graph_cell=None, graph_edge=None, mask_face_in
         cb = ops.as_i32(graph_cell.batch)
         fb = ops.as_i32(graph_edge.batch)
         n_graphs = int(getattr(graph_cell, "num_graphs", 0)) or int(graph_cell.batch[-1].item()) + 1
-    out, _ = ops.loss_fwd(predicted_delta_u.contiguous(), target_delta_u.contiguous(), predicted_edge_attr.contiguous(),
-                          target_face_uvp_normalized.contiguous(), mask_face_interior, cb, fb, n_graphs, mode,
-                          params.loss_mom, params.loss_face_uv, params.loss_face_p)
-    return out[0], 0.0, out[2], out[3], out[4]
+    from ..autograd import LossFunction
+
+    out = LossFunction.apply(predicted_delta_u, target_delta_u, predicted_edge_attr, target_face_uvp_normalized, mask_face_interior, cb, fb,
+                             n_graphs, mode, params.loss_mom, params.loss_face_uv, params.loss_face_p)
+    return out[0], 0.0, out[2].detach(), out[3].detach(), out[4].detach()

@@ -181,6 +181,46 @@ FVGN_API int fvgn_loss_fwd(const float* pred_delta_u, const float* target_delta_
                   float w_p, float* out /*[5]*/, float* workspace /*>= fvgn_loss_workspace_floats(n_graphs)*/, fvgn_stream_t stream);
 FVGN_API size_t fvgn_loss_workspace_floats(int n_graphs);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Backward (training) path — the reference gets these from torch autograd over train.py:194-218.  Strict fp32 (FFMA).
+ * MLP gradients come back in one buffer `grads` of fvgn_mlp_grad_floats(k_in) floats laid out as
+ *   dW1[128,k_in] | dW2[128,128] | dW3[128,128] (rows >= n_out unused) | db1[128] | db2[128] | db3[128] | dLN_w[128] | dLN_b[128].
+ * The kernels recompute the forward inside each tile from the layer INPUTS (nothing else is saved) and are deterministic.
+ * ---------------------------------------------------------------------------------------------------------- */
+FVGN_API size_t fvgn_mlp_grad_floats(int k_in);
+FVGN_API size_t fvgn_mlp_bwd_workspace_floats(int k_in);
+FVGN_API int fvgn_mlp_rows_bwd(const fvgn_mlp_t* mlp, const float* in, int ld_in, int rows, const float* d_out, int ld_dout,
+                               float* d_in /*[rows,k_in] or NULL*/, int ld_din, float* grads, float* workspace, fvgn_stream_t stream);
+FVGN_API int fvgn_cell_block_bwd(const fvgn_mlp_t* mlp, const float* x, const float* node_agg, const int32_t* cells_node_T, int n_cells,
+                                 const float* d_x_prime /*[C,128]*/, const float* d_x_base /*[C,>=128] or NULL: residual-path gradient added onto
+                                 d_in[:,0:128]*/, int ld_base, float* d_in /*[C,192] = d[x | cell_agg]*/, float* grads, float* workspace,
+                                 fvgn_stream_t stream);
+FVGN_API int fvgn_edge_block_bwd(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, const int32_t* neighbour_cell, int n_faces,
+                                 const float* d_e_prime /*[F,128]*/, float* d_in /*[F,384] = d[x'_s | x'_r | e]*/, float* grads, float* workspace,
+                                 fvgn_stream_t stream);
+/* Transposes of the gathers as deterministic CSR segment sums:
+ *   out[d, 0:width] = base[d] + scale * sum_{pos in CSR(d)} src[pos % n_src, col0 + (pos / n_src) * part_stride + 0:width] */
+FVGN_API int fvgn_segment_sum_rows(const float* src, int ld_src, int n_src, int col0, int part_stride, int width, const int32_t* ptr,
+                                   const int32_t* items, int n_dst, const float* base, int ld_base, float scale, float* out, int ld_out,
+                                   fvgn_stream_t stream);
+/* g_e_in[F,128] = g_e_out + dA_edge[:,256:384] + gather(g_node_agg[N,64] by face_node halves)  (transposes of GN_blocks.py:91-122) */
+FVGN_API int fvgn_edge_grad_combine(const float* g_e_out, const float* dA_edge /*[F,384]*/, const float* g_node /*[N,64]*/,
+                                    const int32_t* face_node /*[2,F]*/, int n_faces, float* g_e_in, fvgn_stream_t stream);
+/* d loss / d predicted_delta_u [C,2] and d loss / d predicted_edge_attr [F,5] (direct terms only) from fvgn_loss_fwd's workspace */
+FVGN_API int fvgn_loss_bwd(const float* pred_delta_u, const float* target_delta_u, const float* pred_edge, const float* target_face,
+                           const uint8_t* mask_interior, const int32_t* cell_batch, const int32_t* face_batch, int n_cells, int n_faces,
+                           int n_graphs, int mode, float w_mom, float w_uv, float w_p, const float* g_loss /*scalar or NULL (=1)*/,
+                           const float* fwd_workspace, float* g_delta_u, float* g_edge, float* coef_scratch /*>= 3*n_graphs*/,
+                           fvgn_stream_t stream);
+/* Intergrator transpose: g_decoded[F,5] += (d/du, d/dv, 0, d/dDx, d/dDy); g_face_area[F] = d/d face_area.  (face_ptr, face_items) = CSR of
+ * cells_face_T.reshape(-1) by face. */
+FVGN_API int fvgn_integrator_bwd(const float* decoded, const float* unv, const float* face_area, const float* g_delta_u,
+                                 const int32_t* face_ptr, const int32_t* face_items, int n_cells, int n_faces, float rho, float rhs_coef,
+                                 float* g_decoded /*in/out*/, float* g_face_area, fvgn_stream_t stream);
+/* BatchNorm1d(1) affine gradients: g_weight_bias[2] from g_face_area, the saved raw feature and (mean, invstd) */
+FVGN_API int fvgn_face_area_bn_bwd(const float* g_face_area, const float* raw, const float* batch_stats, int n_faces, float* g_weight_bias,
+                                   float* workspace, fvgn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
