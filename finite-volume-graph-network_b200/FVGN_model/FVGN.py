@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops, parallel
 from ..topology import topology_of
 from ..utils import normalization
 from .EncoderProcesserDecoder import EncoderProcesserDecoder, Intergrator
@@ -75,12 +75,20 @@ class FVGN(nn.Module):
         cells_type = graph.x[:, 0:1]
         faces_type = graph_edge.x[:, 0:1]
         uv = graph.x[:, 2:4]
+        norm_before = parallel.snapshot_normalizers(self) if (self.training and parallel.is_distributed()) else None
         if self.training:
             target_acc = self.velocity_to_accelation(uv, graph.y[:, 0:2])
             target_delta_u = self._acc_output_normalizer(target_acc, True)
             target_face = self._face_uvp_flux_output_normalizer(graph_edge.y[:, 0:3], True)
         x_in = self.update_cell_attr(uv, cell_one_hot, cells_type, self.training, normalizer="1")
         e_in = self.update_edge_attr(graph.edge_attr, edge_one_hot, faces_type, self.training, normalizer="1", dual_edge=self.dual_edge)
+        if norm_before is not None:
+            # DP: every rank must normalise with the statistics of the WHOLE batch
+            parallel.sync_normalizer_increments_(self, norm_before)
+            target_delta_u = self._acc_output_normalizer(target_acc, False)
+            target_face = self._face_uvp_flux_output_normalizer(graph_edge.y[:, 0:3], False)
+            x_in = self.update_cell_attr(uv, cell_one_hot, cells_type, False, normalizer="1")
+            e_in = self.update_edge_attr(graph.edge_attr, edge_one_hot, faces_type, False, normalizer="1", dual_edge=self.dual_edge)
         graph.x, graph.edge_attr = x_in, e_in
         if capture is not None:
             capture["cell_in"], capture["edge_in"] = x_in, e_in

@@ -38,6 +38,7 @@ _SIGS = {
     "fvgn_cell_block_fwd": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P, _I, _P]),
     "fvgn_edge_block_fwd": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P, _I, _P]),
     "fvgn_face_area_bn_fwd": (_I, [_P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fvgn_face_area_sums": (_I, [_P, _P, _P, _I, _F, _P, _P, _P, _P]),
     "fvgn_integrator_fwd": (_I, [_P, _P, _P, _P, _I, _F, _F, _P, _P, _P]),
     "fvgn_loss_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P]),
     "fvgn_loss_workspace_floats": (_S, [_I]),

@@ -7,7 +7,7 @@ reference's `loss.backward(); optimizer.step()` flow (train.py:194-225) works un
 Strict fp32 (FFMA kernels); every reduction is a fixed-order segment sum => gradients are run-to-run deterministic."""
 import torch
 
-from . import ops
+from . import ops, parallel
 
 
 def network_mlps(model):
@@ -46,8 +46,16 @@ class NetFunction(torch.autograd.Function):
         decoded = ops.mlp_rows_fwd(epd.decoder.edge_decode_module.mlp_ref(), e, 0)
         bn = model._grid_feature_normalizer
         use_batch = model.training or not bn.track_running_stats
-        face_area, raw, stats = ops.face_area_bn_fwd(graph_edge_x, cell_area, topo.nc, dt, use_batch, bn.weight.detach(), bn.bias.detach(),
-                                                     bn.running_mean, bn.running_var, want_raw=True)
+        if use_batch and parallel.is_distributed():
+            # cross-rank batch statistics: 3 floats all-reduced, then the kernel applies the given stats
+            raw0, sums = ops.face_area_sums(graph_edge_x, cell_area, topo.nc, dt)
+            gstats, mean, var, n = parallel.global_bn_stats(sums, topo.F)
+            parallel.update_running_stats_(bn, mean, var, n)
+            face_area, raw, stats = ops.face_area_bn_fwd(graph_edge_x, cell_area, topo.nc, dt, True, bn.weight.detach(), bn.bias.detach(),
+                                                         bn.running_mean, bn.running_var, want_raw=True, stats=gstats)
+        else:
+            face_area, raw, stats = ops.face_area_bn_fwd(graph_edge_x, cell_area, topo.nc, dt, use_batch, bn.weight.detach(), bn.bias.detach(),
+                                                         bn.running_mean, bn.running_var, want_raw=True)
         if model.training:
             bn.num_batches_tracked += 1
         delta_u, _ = ops.integrator_fwd(decoded, unv, face_area, topo.cfT, rho, 1.0)

@@ -493,11 +493,37 @@ extern "C" int fvgn_face_area_bn_fwd(const float* face_type_len, const float* ce
   float* stats = batch_stats ? batch_stats : reinterpret_cast<float*>(part + 2 * RED_BLOCKS);
   float* rawbuf = raw ? raw : face_area;  // in-place when the caller does not keep the raw feature
   const int nb = min(RED_BLOCKS, cdiv(n_faces, RED_THREADS));
-  face_area_raw_kernel<<<nb, RED_THREADS, 0, st>>>(face_type_len, cell_area, neighbour_cell, n_faces, dt, rawbuf, training ? part : nullptr);
+  FVGN_CHECK_ARG(training >= 0 && training <= 2, "training must be 0 (running stats), 1 (batch stats) or 2 (caller-provided stats)");
+  FVGN_CHECK_ARG(training != 2 || batch_stats, "training == 2 needs batch_stats = [mean, invstd]");
+  face_area_raw_kernel<<<nb, RED_THREADS, 0, st>>>(face_type_len, cell_area, neighbour_cell, n_faces, dt, rawbuf, training == 1 ? part : nullptr);
   FVGN_LAUNCH_CHECK();
-  bn_stats_kernel<<<1, 32, 0, st>>>(part, nb, n_faces, training, running_mean, running_var, stats);
-  FVGN_LAUNCH_CHECK();
+  if (training != 2) {
+    bn_stats_kernel<<<1, 32, 0, st>>>(part, nb, n_faces, training, running_mean, running_var, stats);
+    FVGN_LAUNCH_CHECK();
+  }
   bn_apply_kernel<<<cdiv(n_faces, 256), 256, 0, st>>>(rawbuf, n_faces, stats, bn_weight, bn_bias, face_area);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+namespace fvgn {
+__global__ void sum_partials2_kernel(const double* __restrict__ part, int nb, double* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nb; ++b) { s += part[2 * b]; q += part[2 * b + 1]; }
+  out[0] = s; out[1] = q;
+}
+}  // namespace fvgn
+
+extern "C" int fvgn_face_area_sums(const float* face_type_len, const float* cell_area, const int32_t* neighbour_cell, int n_faces, float dt,
+                                   float* raw, double* sums, float* workspace, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(face_type_len && cell_area && neighbour_cell && raw && sums && workspace && n_faces > 0, "NULL pointer");
+  FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7) == 0 && (reinterpret_cast<uintptr_t>(sums) & 7) == 0, "8B alignment");
+  double* part = reinterpret_cast<double*>(workspace);
+  const int nb = min(RED_BLOCKS, cdiv(n_faces, RED_THREADS));
+  face_area_raw_kernel<<<nb, RED_THREADS, 0, as_stream(stream)>>>(face_type_len, cell_area, neighbour_cell, n_faces, dt, raw, part);
+  FVGN_LAUNCH_CHECK();
+  sum_partials2_kernel<<<1, 32, 0, as_stream(stream)>>>(part, nb, sums);
   FVGN_LAUNCH_CHECK();
   return 0;
 }

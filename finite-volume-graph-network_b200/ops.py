@@ -310,7 +310,21 @@ def normalizer_apply(x, acc_count, acc_sum, acc_sq, inverse=False, type_col=None
 
 
 # ------------------------------------------------------------------------------------------------ FV head
-def face_area_bn_fwd(face_type_len, cell_area, neighbour_cell, dt, training, bn_weight, bn_bias, running_mean, running_var, want_raw=False):
+def face_area_sums(face_type_len, cell_area, neighbour_cell, dt):
+    """local raw feature [F,1] and float64 [sum, sum of squares] (for the cross-rank BatchNorm statistics)"""
+    _ci(neighbour_cell, "neighbour_cell", 2), _cf(face_type_len, "face_type_len"), _cf(cell_area, "cell_area")
+    F = neighbour_cell.shape[1]
+    L = _lib.lib()
+    raw = torch.empty((F, 1), dtype=torch.float32, device=cell_area.device)
+    sums = torch.empty(2, dtype=torch.float64, device=cell_area.device)
+    ws = torch.empty(L.fvgn_norm_workspace_floats(1) // 2 + 8, dtype=torch.float64, device=cell_area.device)
+    _count(2)
+    check(L.fvgn_face_area_sums(_p(face_type_len), _p(cell_area), _p(neighbour_cell), F, float(dt), _p(raw), _p(sums), _p(ws), _stream()), "face_area_sums")
+    return raw, sums
+
+
+def face_area_bn_fwd(face_type_len, cell_area, neighbour_cell, dt, training, bn_weight, bn_bias, running_mean, running_var, want_raw=False,
+                     stats=None):
     _ci(neighbour_cell, "neighbour_cell", 2), _cf(face_type_len, "face_type_len"), _cf(cell_area, "cell_area")
     F = neighbour_cell.shape[1]
     dev = cell_area.device

@@ -157,12 +157,17 @@ FVGN_API int fvgn_edge_block_fwd(const fvgn_mlp_t* mlp, const float* x_prime /*[
 
 /* ------------------------------------------------------------------------------------------------------------
  * a10. face-area feature + BatchNorm1d(1) (FVGN.py:77-79, 209-227 / 286-304):
- *      raw = len*dt/((A[s]+A[r])/2);  training: batch statistics (biased var for the output, unbiased into running_var,
- *      momentum 0.1) ; eval: running statistics.  bn = [weight, bias, running_mean, running_var] device scalars. */
+ *      raw = len*dt/((A[s]+A[r])/2);  training=1: batch statistics (biased var for the output, unbiased into running_var,
+ *      momentum 0.1) ; training=0: running statistics ; training=2: caller-provided batch_stats=[mean, invstd] (DDP).  bn = [weight, bias, running_mean, running_var] device scalars. */
 FVGN_API int fvgn_face_area_bn_fwd(const float* face_type_len /*[F,2]*/, const float* cell_area /*[C]*/, const int32_t* neighbour_cell,
                           int n_faces, float dt, int training, const float* bn_weight, const float* bn_bias, float* running_mean,
                           float* running_var, float* face_area /*[F]*/, float* raw /*[F] or NULL*/, float* batch_stats /*[2] mean,invstd or NULL*/,
                           float* workspace /*>= fvgn_norm_workspace_floats(1)*/, fvgn_stream_t stream);
+
+/* Data-parallel training: local (sum, sum of squares) of the raw face-area feature (float64) for the cross-rank BatchNorm
+ * statistics; the caller all-reduces them and passes [mean, invstd] back through fvgn_face_area_bn_fwd(training = 2). */
+FVGN_API int fvgn_face_area_sums(const float* face_type_len, const float* cell_area, const int32_t* neighbour_cell, int n_faces, float dt,
+                                 float* raw /*[F]*/, double* sums /*[2]*/, float* workspace, fvgn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * a11. Intergrator.forward (EncoderProcesserDecoder.py:251-331): face flux -> cell divergence.
