@@ -61,7 +61,9 @@ class NetFunction(torch.autograd.Function):
         delta_u, _ = ops.integrator_fwd(decoded, unv, face_area, topo.cfT, rho, 1.0)
         ctx.model, ctx.topo, ctx.rho = model, topo, rho
         ctx.saved = saved
-        ctx.aux = (cell_in, edge_in, e, decoded, face_area, raw, stats, unv)
+        # detached aliases: storing the OUTPUT tensors themselves on ctx would close a reference cycle (output -> grad_fn -> ctx ->
+        # output) that only the cyclic GC can free, i.e. ~2 GB per layer of saved latents would pile up between collections
+        ctx.aux = (cell_in.detach(), edge_in.detach(), e, decoded.detach(), face_area.detach(), raw, stats, unv.detach())
         ctx.mark_non_differentiable(face_area)
         return decoded, delta_u, face_area
 
@@ -70,6 +72,7 @@ class NetFunction(torch.autograd.Function):
         model, topo = ctx.model, ctx.topo
         epd = model.model
         cell_in, edge_in, e_final, decoded, face_area, raw, stats, unv = ctx.aux
+        saved_layers, ctx.saved, ctx.aux = ctx.saved, None, None  # release the saved latents as the backward sweep consumes them
         bt = topo.backward_tables()
         dev = decoded.device
         g_dec = (g_decoded.contiguous().clone() if g_decoded is not None else torch.zeros_like(decoded))
@@ -85,7 +88,8 @@ class NetFunction(torch.autograd.Function):
         g_x = None  # the last layer's cell latent feeds nothing but its own EdgeBlock
         cptr, citems = bt["cell_from_face"]
         nptr, nitems = bt["node_from_cell"]
-        for blk, (x_in, e_in, xp, na) in zip(reversed(epd.processer_list), reversed(ctx.saved)):
+        for blk in reversed(epd.processer_list):
+            x_in, e_in, xp, na = saved_layers.pop()
             cb, eb = blk.cb_module.net, blk.eb_module.net
             grads[id(eb)], dA_e = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e)
             # d x' = residual path + transpose of the x'[s], x'[r] gathers (cell <- face segment sum)

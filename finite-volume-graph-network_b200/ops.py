@@ -331,10 +331,15 @@ def face_area_bn_fwd(face_type_len, cell_area, neighbour_cell, dt, training, bn_
     L = _lib.lib()
     out = torch.empty((F, 1), dtype=torch.float32, device=dev)
     raw = torch.empty((F, 1), dtype=torch.float32, device=dev) if want_raw else None
-    stats = torch.empty(2, dtype=torch.float32, device=dev)
+    mode = 1 if training else 0
+    if stats is not None:  # caller-provided [mean, invstd] (cross-rank batch statistics, parallel.global_bn_stats)
+        stats = _cf(stats, "stats")
+        mode = 2
+    else:
+        stats = torch.empty(2, dtype=torch.float32, device=dev)
     ws = torch.empty(L.fvgn_norm_workspace_floats(1) // 2 + 8, dtype=torch.float64, device=dev)
-    _count(3)
-    check(L.fvgn_face_area_bn_fwd(_p(face_type_len), _p(cell_area), _p(neighbour_cell), F, float(dt), 1 if training else 0, _p(bn_weight),
+    _count(3 if mode != 2 else 2)
+    check(L.fvgn_face_area_bn_fwd(_p(face_type_len), _p(cell_area), _p(neighbour_cell), F, float(dt), mode, _p(bn_weight),
                                   _p(bn_bias), _p(running_mean), _p(running_var), _p(out), _p(raw), _p(stats), _p(ws), _stream()), "face_area_bn_fwd")
     return out, raw, stats
 
