@@ -1,20 +1,24 @@
 // mlp_tc.cu — tcgen05 / TMEM tensor-core path of the fused gather -> MLP -> LayerNorm -> residual kernels (sm_100a).
 //
-// One persistent CTA per SM, 128-row tiles, fully decoupled warp-specialised pipeline (14 warps):
-//   warps 0-3   producers : gather the tile's operand rows from HBM (16 x 128-bit loads in flight per thread), convert to
-//                           bf16 and write 64-column K-tiles into a 5-slot shared-memory ring in the canonical K-major
-//                           SWIZZLE_128B UMMA layout.  They run up to one tile + 5 K-tiles ahead of the epilogues.
-//   warps 4-11  epilogue  : tcgen05.ld the fp32 accumulator from TMEM (one row per thread), bias + SiLU -> bf16 A operand
-//                           of the next layer (H tile), or bias + LayerNorm + residual -> HBM through a swizzled smem
-//                           staging tile so that every global access is a full 128-byte line
-//   warp 12     MMA       : one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM, M=128 N=128 K=16).
-//                           Two TMEM accumulators ping-pong: layer 1 of tile i+1 runs while tile i is in its epilogues.
-//   warp 13     loader    : streams the first-layer weight K-tiles through a 2-slot ring with cp.async.bulk (TMA bulk copy)
+// One persistent CTA per SM, 128-row tiles, TWO tiles in flight per SM, fully decoupled warp-specialised pipeline (18 warps):
+//   warps 0-3   epilogue group 0 (tiles 0,2,4,.. of this CTA)  } one thread per tile row: tcgen05.ld the fp32 accumulator,
+//   warps 4-7   epilogue group 1 (tiles 1,3,5,..)              } bias + SiLU -> bf16 -> tcgen05.st into TMEM, where the hidden
+//                           activations stay as the A operand of the next layer's MMA (A-from-TMEM form: no shared-memory round trip,
+//                           no proxy fence); last layer: bias + LayerNorm (row-local, no cross-thread exchange) + residual -> HBM
+//                           through a per-warp swizzled 4 KB staging tile so that every global access is a full 128-byte line.
+//   warps 8-15  producers : gather the tile's operand rows from HBM (software-pipelined: the loads of K-tile g+1 are in flight while
+//                           K-tile g is converted), convert to bf16 and write 64-column K-tiles into a shared-memory ring in the
+//                           canonical K-major SWIZZLE_128B UMMA layout.
+//   warp 16     MMA       : one elected thread runs an event loop over mbarriers (try_wait polling) and issues whichever tcgen05.mma
+//                           batch is ready: layer 2/3 of either in-flight tile (A from TMEM, W2/W3 resident in smem) or the next
+//                           K-tile of layer 1 (A ring x W1 ring).  TMEM: 2 x 128 accumulator columns + 2 x 64 hidden-activation columns.
+//   warp 17     loader    : streams the first-layer weight K-tiles through a 2-slot ring with cp.async.bulk (TMA bulk copy)
 //                           on mbarriers; W2/W3 are loaded once and stay resident
 // Weights are pre-packed once per weight version (fvgn_mlp_pack_bf16) into bf16 tiles that are byte images of the
 // swizzled shared-memory layout, so the loader needs no tensor map: each K-tile is one 16 KB bulk copy.
 // Every mbarrier wait has a watchdog that traps instead of hanging the device.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace fvgn {
@@ -25,12 +29,15 @@ constexpr int KTILE = 64;          // bf16 elements per 128-byte swizzle row
 constexpr int TILE_BYTES = 16384;  // [128 rows][128 B]
 constexpr int ARING = 5;           // A-operand K-tile ring slots
 constexpr int WRING = 2;           // W1 K-tile ring slots
-constexpr int NPROD = 256;         // producer threads (warps 0-7)
+constexpr int NEPI = 256;          // epilogue threads: warps 0-3 = group 0, warps 4-7 = group 1
+constexpr int NPROD = 256;         // producer threads (warps 8-15)
 constexpr int NPW = NPROD / 32;    // producer warps
-constexpr int NEPI = 256;          // epilogue threads (warps 8-15)
-constexpr int WARP_EPI0 = NPW, WARP_MMA = NPW + 8, WARP_LOAD = NPW + 9;
-constexpr int NTHREADS = (NPW + 10) * 32;
+constexpr int WARP_PROD0 = NEPI / 32, WARP_MMA = WARP_PROD0 + NPW;
+constexpr int NTHREADS = (WARP_MMA + 1) * 32;
+constexpr int NACC = 3;                 // TMEM accumulators: two tiles in their epilogues + one being filled by layer 1
 constexpr int RPT = TM / (NPROD / 16);  // rows per producer thread per K-tile (8)
+constexpr uint32_t TMEM_COLS = 512;     // acc0 [0,128) | acc1 [128,256) | acc2 [256,384) | H0 [384,448) | H1 [448,512)
+constexpr uint32_t TMEM_H0 = 384;
 
 enum { TC_ROWS = 0, TC_CELL = 1, TC_EDGE = 2 };
 
@@ -41,6 +48,7 @@ struct TcParams {
   int kt1;    // K-tiles of layer 1
   int k_in;   // ROWS: valid input width
   int n_out;  // valid outputs of layer 3
+  int use_red;  // residual output aliases the residual input: add with red.global.add.v4.f32 (no load on the SM)
   const float* in; int ld_in;                               // ROWS
   const float* src0; const float* src1; const int32_t* idx;  // CELL: x, node_agg, cells_node_T ; EDGE: x', e, neighbour_cell
   float* out0; int ld_out;
@@ -120,9 +128,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets TMEM lane (lane_base + t)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets TMEM lane (lane_base + t).  Asynchronous: the registers
+// are valid only after tmem_ld_wait(r) (tcgen05.wait::ld with r as in/out operands, so no use of r can be scheduled above it).
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, "
@@ -133,9 +141,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -159,20 +173,42 @@ __device__ __forceinline__ void st_tile_f4(unsigned char* tile, int r, int hl, f
   *reinterpret_cast<uint2*>(tile + off) = pk;
 }
 
+// A operand from TMEM (bf16 pairs packed in 32-bit columns: row i = lane i, elements (2c, 2c+1) in column c), B from smem
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns: thread t of the warp writes TMEM lane (lane_base + t)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void red_add_f4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ shared memory map
 struct SmemLayout {
-  uint32_t a_off, h_off, w2_off, w3_off, wring_off, par_off, red_off, bar_off, total;
+  uint32_t a_off, w2_off, w3_off, wring_off, stage_off, par_off, bar_off, total;
 };
 __host__ __device__ inline SmemLayout smem_layout() {
   SmemLayout L;
   uint32_t o = 0;
   L.a_off = o; o += ARING * TILE_BYTES;      // 80 KB  A-operand K-tile ring
-  L.h_off = o; o += 2 * TILE_BYTES;          // 32 KB  hidden activations (A operand of layers 2,3) / fp32 output staging
   L.w2_off = o; o += 2 * TILE_BYTES;         // 32 KB
   L.w3_off = o; o += 2 * TILE_BYTES;         // 32 KB
   L.wring_off = o; o += WRING * TILE_BYTES;  // 32 KB  W1 K-tile ring
+  L.stage_off = o; o += 8 * 4096;            // 32 KB  per-epilogue-warp output staging [32 rows][32 fp32]
   L.par_off = o; o += 5 * 128 * 4;           // b1 | b2 | b3 | ln_w | ln_b
-  L.red_off = o; o += 2 * 2 * 128 * 4;       // LayerNorm cross-warp exchange
   L.bar_off = o; o += 256;
   L.total = o + 1024;                        // slack for the 1024-byte alignment of the dynamic smem base
   return L;
@@ -180,37 +216,47 @@ __host__ __device__ inline SmemLayout smem_layout() {
 
 // barrier indices (8 bytes each)
 enum { B_AFULL = 0, B_AEMPTY = B_AFULL + ARING, B_WFULL = B_AEMPTY + ARING, B_WEMPTY = B_WFULL + WRING, B_WRES = B_WEMPTY + WRING,
-       B_DFULL = B_WRES + 1, B_DFREE = B_DFULL + 2, B_HREADY = B_DFREE + 2, B_COUNT = B_HREADY + 1 };
+       B_DFULL = B_WRES + 1, B_DFREE = B_DFULL + NACC, B_HREADY = B_DFREE + NACC, B_COUNT = B_HREADY + 2 };
 
+// bias + SiLU of one 32-column accumulator chunk -> 16 packed bf16 pairs (bias read as broadcast LDS.128)
+__device__ __forceinline__ void silu_chunk(const uint32_t* r, const float* bias, uint32_t* pk) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * j4);
+    pk[2 * j4] = pack_bf16(silu_fast(__uint_as_float(r[4 * j4]) + b.x), silu_fast(__uint_as_float(r[4 * j4 + 1]) + b.y));
+    pk[2 * j4 + 1] = pack_bf16(silu_fast(__uint_as_float(r[4 * j4 + 2]) + b.z), silu_fast(__uint_as_float(r[4 * j4 + 3]) + b.w));
+  }
+}
+
+template <int MODE, bool RED>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const SmemLayout L = smem_layout();
   unsigned char* sA = smem + L.a_off;
-  unsigned char* sH = smem + L.h_off;
   unsigned char* sW2 = smem + L.w2_off;
   unsigned char* sW3 = smem + L.w3_off;
   unsigned char* sWr = smem + L.wring_off;
   float* sPar = reinterpret_cast<float*>(smem + L.par_off);
-  float* sRed = reinterpret_cast<float*>(smem + L.red_off);
   const uint32_t bar0 = smem_u32(smem + L.bar_off);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * B_COUNT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kt1 = p.kt1;
+  const int kt1 = (MODE == TC_EDGE) ? 6 : (MODE == TC_CELL) ? 3 : p.kt1;
+  const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
     for (int i = 0; i < ARING; ++i) { mbar_init(BAR(B_AFULL + i), NPW); mbar_init(BAR(B_AEMPTY + i), 1); }
     for (int i = 0; i < WRING; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
     mbar_init(BAR(B_WRES), 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_DFULL + b), 1); mbar_init(BAR(B_DFREE + b), 8); }
-    mbar_init(BAR(B_HREADY), 8);
+    for (int a = 0; a < NACC; ++a) { mbar_init(BAR(B_DFULL + a), 1); mbar_init(BAR(B_DFREE + a), 4); }
+    for (int g = 0; g < 2; ++g) mbar_init(BAR(B_HREADY + g), 4);
     fence_mbar_init();
   }
-  if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), 256);
-  if (warp >= WARP_EPI0 && warp < WARP_EPI0 + 8) {
-    for (int i = tid - NPROD; i < 5 * 128; i += NEPI) {
+  if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp >= WARP_PROD0 && warp < WARP_MMA) {
+    for (int i = tid - NEPI; i < 5 * 128; i += NPROD) {
       const int which = i >> 7, c = i & 127;
       float v = 0.f;
       if (which == 0) v = p.b1[c];
@@ -226,273 +272,316 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < NPW) {
-    // ================================================================= producers: gather -> A ring
+  if (warp >= WARP_PROD0 && warp < WARP_MMA) {
+    // ================================================================= producers: gather -> A ring (software pipelined)
     constexpr int NHW = NPROD / 16;          // half-warps: half-warp hw owns rows hw, hw+NHW, ...
-    const int hw = tid >> 4, hl = tid & 15;
-    uint32_t g = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      const int row0 = tile * TM;
-      for (int t = 0; t < kt1; ++t, ++g) {
-        const uint32_t slot = g % ARING;
-        // issue the loads of this K-tile before waiting for the slot: the wait overlaps the memory latency
-        float4 v[RPT];
-        if (p.mode == TC_EDGE) {
-          const int F = p.rows;
-          int src[RPT];
-          if (t < 4) {
-            const int32_t* ip = p.idx + (t >= 2 ? (size_t)F : 0);
+    const int ptid = tid - NEPI;
+    const int hw = ptid >> 4, hl = ptid & 15;
+    const int S = n_local * kt1;             // K-tile steps of this CTA
+    // loads of K-tile step s (tile s / kt1, K-tile s % kt1) into registers.  Rows past the end of the last tile are clamped to
+    // the last valid row (their results are never stored), so the hot path carries no bounds predicates.
+    auto load = [&](int s, float4* v) {
+      const int jl = s / kt1, t = s - jl * kt1;
+      const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+      if (MODE == TC_EDGE) {
+        const int last = p.rows - 1;
+        // K-tiles 0,1: x'[sender] halves; 2,3: x'[receiver] halves; 4,5: e halves (identity "gather")
+        const bool gath = t < 4;
+        const int32_t* ip = p.idx + (t >= 2 ? (size_t)p.rows : 0);
+        const float* base = (gath ? p.src0 : p.src1) + (t & 1) * 64 + hl * 4;
+        int src[RPT];
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) { const int f = row0 + hw + NHW * i; src[i] = (f < F) ? __ldg(ip + f) : -1; }
-            const float* base = p.src0 + (t & 1) * 64 + hl * 4;
+        for (int i = 0; i < RPT; ++i) {
+          const int f = min(row0 + hw + NHW * i, last);
+          src[i] = gath ? __ldg(ip + f) : f;
+        }
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) v[i] = (src[i] >= 0) ? ldg4(base + (size_t)src[i] * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-          } else {
-            const float* base = p.src1 + (t & 1) * 64 + hl * 4;
+        for (int i = 0; i < RPT; ++i) v[i] = ldg4(base + (size_t)src[i] * 128);
+      } else if (MODE == TC_CELL) {
+        const int C = p.rows;
+        if (t < 2) {
+          const float* base = p.src0 + t * 64 + hl * 4;
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-              const int f = row0 + hw + NHW * i;
-              v[i] = (f < F) ? *reinterpret_cast<const float4*>(base + (size_t)f * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-        } else if (p.mode == TC_CELL) {
-          const int C = p.rows;
-          if (t < 2) {
-            const float* base = p.src0 + t * 64 + hl * 4;
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-              const int c = row0 + hw + NHW * i;
-              v[i] = (c < C) ? *reinterpret_cast<const float4*>(base + (size_t)c * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-              const int c = row0 + hw + NHW * i;
-              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (c < C) {
-                const int n0 = __ldg(p.idx + c), n1 = __ldg(p.idx + (size_t)C + c), n2 = __ldg(p.idx + 2 * (size_t)C + c);
-                const float4 a = ldg4(p.src1 + (size_t)n0 * 64 + hl * 4);
-                const float4 b = ldg4(p.src1 + (size_t)n1 * 64 + hl * 4);
-                const float4 d = ldg4(p.src1 + (size_t)n2 * 64 + hl * 4);
-                o.x = ((a.x + b.x) + d.x) / 3.0f; o.y = ((a.y + b.y) + d.y) / 3.0f;
-                o.z = ((a.z + b.z) + d.z) / 3.0f; o.w = ((a.w + b.w) + d.w) / 3.0f;
-              }
-              v[i] = o;
-            }
-          }
-        } else {  // TC_ROWS: generic [rows, k_in] fp32 input, zero padded to 64*kt1
+          for (int i = 0; i < RPT; ++i) v[i] = ldg4(base + (size_t)min(row0 + hw + NHW * i, C - 1) * 128);
+        } else {
+          int n0[RPT], n1[RPT], n2[RPT];
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
-            const int gr = row0 + hw + NHW * i;
-            float x4[4] = {0.f, 0.f, 0.f, 0.f};
-            if (gr < p.rows) {
-              const int k0 = t * KTILE + hl * 4;
+            const int c = min(row0 + hw + NHW * i, C - 1);
+            n0[i] = __ldg(p.idx + c);
+            n1[i] = __ldg(p.idx + (size_t)C + c);
+            n2[i] = __ldg(p.idx + 2 * (size_t)C + c);
+          }
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (k0 + j < p.k_in) x4[j] = p.in[(size_t)gr * p.ld_in + k0 + j];
-            }
-            v[i] = make_float4(x4[0], x4[1], x4[2], x4[3]);
+          for (int i = 0; i < RPT; ++i) {
+            const float4 a = ldg4(p.src1 + (size_t)n0[i] * 64 + hl * 4);
+            const float4 b = ldg4(p.src1 + (size_t)n1[i] * 64 + hl * 4);
+            const float4 d = ldg4(p.src1 + (size_t)n2[i] * 64 + hl * 4);
+            // the mean is rounded to bf16 right after: a multiply by 1/3 (<= 1 ulp fp32 from the reference's division) is invisible there
+            constexpr float k3 = 1.0f / 3.0f;
+            v[i] = make_float4(((a.x + b.x) + d.x) * k3, ((a.y + b.y) + d.y) * k3, ((a.z + b.z) + d.z) * k3, ((a.w + b.w) + d.w) * k3);
           }
         }
-        if (g >= ARING) mbar_wait(BAR(B_AEMPTY + slot), ((g / ARING) - 1) & 1, 1);
-        unsigned char* dst = sA + slot * TILE_BYTES;
+      } else {  // TC_ROWS: generic [rows, k_in] fp32 input, zero padded to 64*kt1
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) st_tile_f4(dst, hw + NHW * i, hl, v[i]);
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_AFULL + slot));
+        for (int i = 0; i < RPT; ++i) {
+          const int gr = row0 + hw + NHW * i;
+          float x4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (gr < p.rows) {
+            const int k0 = t * KTILE + hl * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (k0 + j < p.k_in) x4[j] = p.in[(size_t)gr * p.ld_in + k0 + j];
+          }
+          v[i] = make_float4(x4[0], x4[1], x4[2], x4[3]);
+        }
       }
+    };
+    auto store = [&](int s, const float4* v) {
+      const uint32_t slot = (uint32_t)s % ARING;
+      if (s >= ARING) mbar_wait(BAR(B_AEMPTY + slot), (((uint32_t)s / ARING) - 1) & 1, 1);
+      unsigned char* dst = sA + slot * TILE_BYTES;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) st_tile_f4(dst, hw + NHW * i, hl, v[i]);
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_AFULL + slot));
+    };
+    // two register buffers: the loads of step s+1 are in flight while step s is converted and stored (two code copies, no prologue)
+    float4 va[RPT], vb[RPT];
+#pragma unroll 1
+    for (int s = -1; s < S; s += 2) {
+      if (s + 1 < S) load(s + 1, va);
+      if (s >= 0) store(s, vb);
+      if (s + 2 < S) load(s + 2, vb);
+      if (s + 1 < S) store(s + 1, va);
     }
-  } else if (warp == WARP_LOAD) {
-    // ================================================================= loader: W2/W3 once, W1 K-tiles through the ring
-    if (lane == 0) {
+  } else if (warp == WARP_MMA) {
+    // ================================================================= MMA issuer + weight loader: one thread, event loop over mbarriers
+    if (lane == 0 && n_local > 0) {
+      // W2/W3 once, resident
       mbar_arrive_expect_tx(BAR(B_WRES), 4 * TILE_BYTES);
       bulk_g2s(smem_u32(sW2), p.packed + (size_t)kt1 * TILE_BYTES, 2 * TILE_BYTES, BAR(B_WRES));
       bulk_g2s(smem_u32(sW3), p.packed + (size_t)(kt1 + 2) * TILE_BYTES, 2 * TILE_BYTES, BAR(B_WRES));
-      uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        for (int t = 0; t < kt1; ++t, ++g) {
-          const uint32_t slot = g % WRING;
-          if (g >= WRING) mbar_wait(BAR(B_WEMPTY + slot), ((g / WRING) - 1) & 1, 2);
-          mbar_arrive_expect_tx(BAR(B_WFULL + slot), TILE_BYTES);
-          bulk_g2s(smem_u32(sWr + slot * TILE_BYTES), p.packed + (size_t)t * TILE_BYTES, TILE_BYTES, BAR(B_WFULL + slot));
+      const uint32_t S = (uint32_t)(n_local * kt1);
+      uint32_t wl = 0, wt = 0;         // W1 K-tiles issued to the ring, K-tile index inside the tile
+      uint32_t gk = 0;                 // K-tile counter shared by the A ring and the W1 ring (consumer side)
+      int jl = 0, tl = 0;              // layer-1 cursor: local tile, K-tile.  jl tiles have their layer 1 fully issued.
+      bool acc_ok = false;             // accumulator of the cursor's tile is free
+      int stage[2] = {0, 0};           // per epilogue group: 0 idle, 1 waiting for H1 (-> layer 2), 2 waiting for H2 (-> layer 3)
+      int cur[2] = {0, 1};             // per group: local tile in (or next to enter) layers 2/3
+      uint32_t hphase[2] = {0, 0};
+      int done = 0;
+      bool wres = false;
+      long long t_last = clock64();
+      while (done < n_local) {
+        bool progress = false;
+        // ---- stream W1 K-tiles (TMA bulk copies) as ring slots free up
+        if (wl < S) {
+          const uint32_t slot = wl % WRING;
+          if (wl < WRING || mbar_try_wait(BAR(B_WEMPTY + slot), ((wl / WRING) - 1) & 1)) {
+            mbar_arrive_expect_tx(BAR(B_WFULL + slot), TILE_BYTES);
+            bulk_g2s(smem_u32(sWr + slot * TILE_BYTES), p.packed + (size_t)wt * TILE_BYTES, TILE_BYTES, BAR(B_WFULL + slot));
+            ++wl;
+            if (++wt == (uint32_t)kt1) wt = 0;
+            progress = true;
+          }
         }
-      }
-    }
-    __syncwarp();
-  } else if (warp == WARP_MMA) {
-    // ================================================================= MMA issuer (single thread)
-    if (lane == 0) {
-      uint32_t g = 0;           // K-tile counter shared by the A ring and the W1 ring
-      uint32_t hphase = 0;      // h_ready parity
-      uint32_t dfree_uses[2] = {0, 0};
-      // layer 1 of local tile j into accumulator j&1
-      auto issue_layer1 = [&](int j) {
-        const int b = j & 1;
-        if (j >= 2) { mbar_wait(BAR(B_DFREE + b), dfree_uses[b] & 1, 3); ++dfree_uses[b]; }
-        tc_fence_after();
-        const uint32_t d = tmem_base + 128u * (uint32_t)b;
-        for (int t = 0; t < kt1; ++t, ++g) {
-          const uint32_t sa = g % ARING, sw = g % WRING;
-          mbar_wait(BAR(B_AFULL + sa), (g / ARING) & 1, 4);
-          mbar_wait(BAR(B_WFULL + sw), (g / WRING) & 1, 5);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + sa * TILE_BYTES), b_base = smem_u32(sWr + sw * TILE_BYTES);
+        // ---- layers 2 / 3 of the two in-flight tiles: A = hidden activations in TMEM, B = resident W2 / W3
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (t | kk) != 0);
-          umma_commit(BAR(B_AEMPTY + sa));  // both ring slots are free once these MMAs have read them
-          umma_commit(BAR(B_WEMPTY + sw));
+        for (int g = 0; g < 2; ++g) {
+          if (stage[g] == 0 && cur[g] < jl) stage[g] = 1;
+          if (stage[g] != 0 && mbar_try_wait(BAR(B_HREADY + g), hphase[g])) {
+            hphase[g] ^= 1;
+            if (!wres) { mbar_wait(BAR(B_WRES), 0, 6); wres = true; }
+            tc_fence_after();
+            const uint32_t d = tmem_base + 128u * (uint32_t)(cur[g] % NACC);
+            const uint32_t h = tmem_base + TMEM_H0 + 64u * (uint32_t)g;
+            const unsigned char* w = stage[g] == 1 ? sW2 : sW3;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16_ts(d, h + 8u * (uint32_t)kk, umma_desc(smem_u32(w + (kk >> 2) * TILE_BYTES) + (kk & 3) * 32), IDESC_BF16_M128_N128, kk != 0);
+            umma_commit(BAR(B_DFULL + cur[g] % NACC));
+            if (stage[g] == 1) stage[g] = 2;
+            else { stage[g] = 0; cur[g] += 2; ++done; }
+            progress = true;
+          }
         }
-        umma_commit(BAR(B_DFULL + b));
-      };
-      int j = 0;
-      const int first = blockIdx.x;
-      if (first < p.ntiles) issue_layer1(0);
-      mbar_wait(BAR(B_WRES), 0, 6);
-      for (int tile = first; tile < p.ntiles; tile += gridDim.x, ++j) {
-        const int b = j & 1;
-        if (tile + (int)gridDim.x < p.ntiles) issue_layer1(j + 1);  // runs under tile j's epilogues
-        const uint32_t d = tmem_base + 128u * (uint32_t)b;
-#pragma unroll 1
-        for (int layer = 0; layer < 2; ++layer) {
-          mbar_wait(BAR(B_HREADY), hphase, 7); hphase ^= 1;
-          tc_fence_after();
-          const unsigned char* w = layer == 0 ? sW2 : sW3;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const uint32_t a_base = smem_u32(sH + t * TILE_BYTES), b_base = smem_u32(w + t * TILE_BYTES);
+        // ---- layer 1 of the next tile: A ring x W1 ring into a free accumulator (runs up to one tile ahead of the epilogues)
+        if (jl < n_local) {
+          const int a = jl % NACC;
+          bool ok = true;
+          if (tl == 0 && !acc_ok) {
+            ok = (jl < NACC) || mbar_try_wait(BAR(B_DFREE + a), (uint32_t)(jl / NACC - 1) & 1);
+            acc_ok = ok;
+          }
+          const uint32_t sa = gk % ARING, sw = gk % WRING;
+          if (ok) ok = mbar_try_wait(BAR(B_AFULL + sa), (gk / ARING) & 1) && mbar_try_wait(BAR(B_WFULL + sw), (gk / WRING) & 1);
+          if (ok) {
+            tc_fence_after();
+            const uint32_t d = tmem_base + 128u * (uint32_t)a;
+            const uint32_t a_base = smem_u32(sA + sa * TILE_BYTES), b_base = smem_u32(sWr + sw * TILE_BYTES);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (t | kk) != 0);
+              umma_bf16(d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (tl | kk) != 0);
+            umma_commit(BAR(B_AEMPTY + sa));  // both ring slots are free once these MMAs have read them
+            umma_commit(BAR(B_WEMPTY + sw));
+            ++gk;
+            if (++tl == kt1) {
+              umma_commit(BAR(B_DFULL + a));
+              ++jl; tl = 0; acc_ok = false;
+            }
+            progress = true;
           }
-          umma_commit(BAR(B_DFULL + b));
         }
+        if (progress) t_last = clock64();
+        else if (clock64() - t_last > 4000000000LL) mbar_timeout(0, 0, 100 + stage[0] * 10 + stage[1]);
       }
     }
     __syncwarp();
   } else {
-    // ================================================================= epilogue warps 4..11
-    const int ew = warp - WARP_EPI0;
-    const int q = warp & 3, h = ew >> 2;  // TMEM lane quadrant (= warp id % 4), column half
-    const int erow = 32 * q + lane;       // this thread's row inside the tile
-    const int et = tid - NPROD;           // 0..255
-    const int ht = et & 127;              // thread index inside its column-half team
-    uint32_t dfull_uses[2] = {0, 0};
-    int j = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++j) {
-      const int row0 = tile * TM;
-      const int b = j & 1;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(32 * q) << 16) + 128u * (uint32_t)b + (uint32_t)(64 * h);
-      // ---------------------------------------------------------------- epilogues 1, 2: bias + SiLU -> bf16 H tiles
+    // ================================================================= epilogue groups (warps 0-3 / 4-7), one thread per row
+    const int g = warp >> 2, q = warp & 3;  // group = tile parity; TMEM lane quadrant = warp id % 4
+    const int erow = 32 * q + lane;         // this thread's row inside the tile
+    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t t_h = t_lane + TMEM_H0 + 64u * (uint32_t)g;
+    unsigned char* stage = smem + L.stage_off + warp * 4096;  // [32 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
+    const bool has_ln = (p.ln_w != nullptr);
+    const bool staged = (MODE != TC_ROWS) || (p.n_out == HIDN && (p.ld_out & 3) == 0);
+    const float* b3 = sPar + 2 * 128;
+    const float* gw = sPar + 3 * 128;
+    const float* gb = sPar + 4 * 128;
+#pragma unroll 1
+    for (int jl = g; jl < n_local; jl += 2) {
+      const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+      const int acc = jl % NACC;
+      const uint32_t t_acc = t_lane + 128u * (uint32_t)acc;
+      const uint32_t dfull = BAR(B_DFULL + acc);
+      const uint32_t use0 = 3u * (uint32_t)(jl / NACC);  // completions this accumulator's barrier has seen before this tile
+      uint32_t r[32];
+      // ---------------------------------------------------------------- epilogues 1, 2: bias + SiLU -> bf16 hidden activations in TMEM
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
-        mbar_wait(BAR(B_DFULL + b), dfull_uses[b] & 1, 8); ++dfull_uses[b];
+        mbar_wait(dfull, (use0 + (uint32_t)layer) & 1, 8);
         tc_fence_after();
-        const float* bias = sPar + layer * 128 + 64 * h;
-        unsigned char* hrow = sH + h * TILE_BYTES + (uint32_t)erow * 128u;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-          tmem_ld32(t_addr + 32 * half, v);
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {  // 8 columns = one 16-byte chunk
-            float o[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) o[jj] = silu_fast(v[c4 * 8 + jj] + bias[half * 32 + c4 * 8 + jj]);
-            uint4 pk;
-            pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]); pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
-            const uint32_t chunk = (uint32_t)(half * 4 + c4);
-            *reinterpret_cast<uint4*>(hrow + ((chunk ^ ((uint32_t)erow & 7u)) << 4)) = pk;
-          }
+        const float* bias = sPar + layer * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+          tmem_ld32_issue(t_acc + 32 * c, r);
+          tmem_ld_wait(r);
+          silu_chunk(r, bias + 32 * c, pk);
+          tmem_st16(t_h + 16 * c, pk);
         }
+        tmem_wait_st();
         tc_fence_before();
-        fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_HREADY));
+        if (lane == 0) mbar_arrive(BAR(B_HREADY + g));
       }
       // ---------------------------------------------------------------- epilogue 3: bias (+ LayerNorm) (+ residual) -> HBM
-      mbar_wait(BAR(B_DFULL + b), dfull_uses[b] & 1, 9); ++dfull_uses[b];
+      mbar_wait(dfull, (use0 + 2u) & 1, 9);
       tc_fence_after();
-      const float* b3 = sPar + 2 * 128 + 64 * h;
       float mean = 0.f, rstd = 1.f;
-      const bool has_ln = (p.ln_w != nullptr);
       if (has_ln) {
-        float s = 0.f;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-          tmem_ld32(t_addr + 32 * half, v);
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) s += v[jj] + b3[half * 32 + jj];
-        }
-        sRed[h * 128 + erow] = s;
-        named_bar_sync(1, NEPI);
-        mean = (sRed[erow] + sRed[128 + erow]) * (1.0f / 128.0f);
-        float qv = 0.f;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-          tmem_ld32(t_addr + 32 * half, v);
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) { const float d = v[jj] + b3[half * 32 + jj] - mean; qv = fmaf(d, d, qv); }
-        }
-        sRed[256 + h * 128 + erow] = qv;
-        named_bar_sync(1, NEPI);
-        rstd = 1.0f / sqrtf((sRed[256 + erow] + sRed[256 + 128 + erow]) * (1.0f / 128.0f) + 1e-5f);
-      }
-      const bool staged = (p.mode != TC_ROWS) || (p.n_out == HIDN && (p.ld_out & 3) == 0);
-      const float* gw = sPar + 3 * 128 + 64 * h;
-      const float* gb = sPar + 4 * 128 + 64 * h;
-      unsigned char* stage = sH + h * TILE_BYTES;  // [128 rows][32 fp32], 16-byte chunks XOR-swizzled by (row & 7)
+        // shifted one-pass statistics (shift = the row's first element): no catastrophic cancellation, no extra TMEM sweep
+        float s1 = 0.f, s2 = 0.f, x0 = 0.f;
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        float v[32];
-        tmem_ld32(t_addr + 32 * half, v);
-        if (half == 1) {  // last TMEM read of this tile: the accumulator may be overwritten by layer 1 of tile j+2
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32_issue(t_acc + 32 * c, r);
+          tmem_ld_wait(r);
+          if (c == 0) x0 = __uint_as_float(r[0]) + b3[0];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(b3 + 32 * c + 4 * j4);
+            float d;
+            d = (__uint_as_float(r[4 * j4]) + b.x) - x0; s1 += d; s2 = fmaf(d, d, s2);
+            d = (__uint_as_float(r[4 * j4 + 1]) + b.y) - x0; s1 += d; s2 = fmaf(d, d, s2);
+            d = (__uint_as_float(r[4 * j4 + 2]) + b.z) - x0; s1 += d; s2 = fmaf(d, d, s2);
+            d = (__uint_as_float(r[4 * j4 + 3]) + b.w) - x0; s1 += d; s2 = fmaf(d, d, s2);
+          }
+        }
+        const float m1 = s1 * (1.0f / 128.0f);
+        mean = x0 + m1;
+        rstd = 1.0f / sqrtf(fmaxf(s2 * (1.0f / 128.0f) - m1 * m1, 0.f) + 1e-5f);
+      }
+      const float* res = (MODE == TC_CELL) ? p.src0 : p.src1;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        // one 32-column chunk: finish y in place, stage through the warp's swizzled tile, write full 128-byte lines
+        tmem_ld32_issue(t_acc + 32 * c, r);
+        tmem_ld_wait(r);
+        if (c == 3) {  // last TMEM read of this tile: the accumulator may be overwritten by layer 1 of tile jl + NACC
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(B_DFREE + b));
+          if (lane == 0) mbar_arrive(BAR(B_DFREE + acc));
         }
+        float* v = reinterpret_cast<float*>(r);
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          float y = v[jj] + b3[half * 32 + jj];
-          if (has_ln) y = (y - mean) * rstd * gw[half * 32 + jj] + gb[half * 32 + jj];
-          v[jj] = y;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b = *reinterpret_cast<const float4*>(b3 + 32 * c + 4 * j4);
+          float y0 = v[4 * j4] + b.x, y1 = v[4 * j4 + 1] + b.y, y2 = v[4 * j4 + 2] + b.z, y3 = v[4 * j4 + 3] + b.w;
+          if (has_ln) {
+            const float4 w = *reinterpret_cast<const float4*>(gw + 32 * c + 4 * j4);
+            const float4 o = *reinterpret_cast<const float4*>(gb + 32 * c + 4 * j4);
+            y0 = (y0 - mean) * rstd * w.x + o.x; y1 = (y1 - mean) * rstd * w.y + o.y;
+            y2 = (y2 - mean) * rstd * w.z + o.z; y3 = (y3 - mean) * rstd * w.w + o.w;
+          }
+          v[4 * j4] = y0; v[4 * j4 + 1] = y1; v[4 * j4 + 2] = y2; v[4 * j4 + 3] = y3;
         }
         if (staged) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(stage + (uint32_t)erow * 128u + (((uint32_t)c ^ ((uint32_t)erow & 7u)) << 4)) =
-                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          named_bar_sync(2 + h, 128);
-          // coalesced read-out: 8 threads per row -> every warp access covers 4 full 128-byte lines
-          const int col0 = 64 * h + 32 * half;
-#pragma unroll 4
-          for (int pass = 0; pass < 8; ++pass) {
-            const int r = pass * 16 + (ht >> 3), cp = ht & 7;
-            const int grow = row0 + r;
-            if (grow < p.rows) {
-              const float4 y = *reinterpret_cast<const float4*>(stage + (uint32_t)r * 128u + ((uint32_t)cp << 4));
-              const int col = col0 + 4 * (cp ^ (r & 7));
-              if (p.mode == TC_ROWS) {
-                *reinterpret_cast<float4*>(p.out0 + (size_t)grow * p.ld_out + col) = y;
-              } else {
-                if (p.out0) *reinterpret_cast<float4*>(p.out0 + (size_t)grow * 128 + col) = y;
-                if (p.out1) {
-                  const float4 rv = *reinterpret_cast<const float4*>((p.mode == TC_CELL ? p.src0 : p.src1) + (size_t)grow * 128 + col);
-                  *reinterpret_cast<float4*>(p.out1 + (size_t)grow * 128 + col) = make_float4(rv.x + y.x, rv.y + y.y, rv.z + y.z, rv.w + y.w);
-                }
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(stage + (uint32_t)lane * 128u + (((uint32_t)k ^ ((uint32_t)lane & 7u)) << 4)) =
+                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          __syncwarp();
+          // coalesced read-out: 8 lanes per row -> every warp access covers 4 full 128-byte lines
+          const int rr0 = lane >> 3, cp = lane & 7;
+          if (MODE == TC_ROWS) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = 4 * it + rr0, grow = row0 + 32 * q + rr;
+              if (grow < p.rows)
+                *reinterpret_cast<float4*>(p.out0 + (size_t)grow * p.ld_out + 32 * c + 4 * (cp ^ (rr & 7))) =
+                    *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 128u + ((uint32_t)cp << 4));
+            }
+          } else if (RED) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = 4 * it + rr0, grow = row0 + 32 * q + rr;
+              if (grow < p.rows) {
+                const float4 y = *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 128u + ((uint32_t)cp << 4));
+                const size_t off = (size_t)grow * 128 + 32 * c + 4 * (cp ^ (rr & 7));
+                if (p.out0) *reinterpret_cast<float4*>(p.out0 + off) = y;
+                red_add_f4(p.out1 + off, y);
+              }
+            }
+          } else {
+            float4 rv[8];
+            if (p.out1) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = 4 * it + rr0, grow = min(row0 + 32 * q + rr, p.rows - 1);
+                rv[it] = *reinterpret_cast<const float4*>(res + (size_t)grow * 128 + 32 * c + 4 * (cp ^ (rr & 7)));
+              }
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = 4 * it + rr0, grow = row0 + 32 * q + rr;
+              if (grow < p.rows) {
+                const float4 y = *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 128u + ((uint32_t)cp << 4));
+                const size_t off = (size_t)grow * 128 + 32 * c + 4 * (cp ^ (rr & 7));
+                if (p.out0) *reinterpret_cast<float4*>(p.out0 + off) = y;
+                if (p.out1) *reinterpret_cast<float4*>(p.out1 + off) = make_float4(rv[it].x + y.x, rv[it].y + y.y, rv[it].z + y.z, rv[it].w + y.w);
               }
             }
           }
-          named_bar_sync(2 + h, 128);  // staging tile is rewritten by the next half / the next tile's H
+          __syncwarp();  // the staging tile is rewritten by the next chunk
         } else {
           const int grow = row0 + erow;
           if (grow < p.rows) {
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
-              const int col = 64 * h + 32 * half + jj;
+              const int col = 32 * c + jj;
               if (col < p.n_out) p.out0[(size_t)grow * p.ld_out + col] = v[jj];
             }
           }
@@ -505,7 +594,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
   __syncthreads();
   if (warp == WARP_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -546,6 +635,15 @@ int tc_pack(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t st) {
   return 0;
 }
 
+// in-place residual (x_out == x / e_out == e): add in L2 with red.global.add.v4.f32 instead of load + add + store on the SM.
+// Each address is touched by exactly one thread once per launch, so the result is the same IEEE add, deterministically.
+// FVGN_TC_RED=0 selects the load/add/store epilogue (A/B measurements).
+static bool red_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FVGN_TC_RED"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 static int launch_tc(TcParams& p, const fvgn_mlp_t* m, cudaStream_t st) {
   if (p.rows <= 0) return 0;
   FVGN_CHECK_ARG(m->packed != nullptr, "tensor-core modes need packed weights: call fvgn_mlp_pack_bf16 first");
@@ -557,11 +655,19 @@ static int launch_tc(TcParams& p, const fvgn_mlp_t* m, cudaStream_t st) {
   const SmemLayout L = smem_layout();
   static bool configured = false;
   if (!configured) {
-    FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<TC_ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<TC_CELL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<TC_CELL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<TC_EDGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<TC_EDGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     configured = true;
   }
   const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
-  fused_mlp_tc_kernel<<<grid, NTHREADS, L.total, st>>>(p);
+  if (p.mode == TC_ROWS) fused_mlp_tc_kernel<TC_ROWS, false><<<grid, NTHREADS, L.total, st>>>(p);
+  else if (p.mode == TC_CELL && p.use_red) fused_mlp_tc_kernel<TC_CELL, true><<<grid, NTHREADS, L.total, st>>>(p);
+  else if (p.mode == TC_CELL) fused_mlp_tc_kernel<TC_CELL, false><<<grid, NTHREADS, L.total, st>>>(p);
+  else if (p.use_red) fused_mlp_tc_kernel<TC_EDGE, true><<<grid, NTHREADS, L.total, st>>>(p);
+  else fused_mlp_tc_kernel<TC_EDGE, false><<<grid, NTHREADS, L.total, st>>>(p);
   FVGN_LAUNCH_CHECK();
   return 0;
 }
@@ -592,6 +698,7 @@ int tc_cell_block(const fvgn_mlp_t* mlp, const float* x, const float* node_agg, 
   FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && node_agg && cells_node_T)), "NULL input");
   TcParams p{};
   p.mode = TC_CELL; p.rows = n_cells; p.src0 = x; p.src1 = node_agg; p.idx = cells_node_T; p.out0 = x_prime; p.out1 = x_out; p.ld_out = 128;
+  p.use_red = (x_out != nullptr && x_out == x && red_enabled()) ? 1 : 0;
   return launch_tc(p, mlp, st);
 }
 
@@ -602,6 +709,7 @@ int tc_edge_block(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, c
   FVGN_CHECK_ARG(n_faces >= 0 && (n_faces == 0 || (x_prime && e && neighbour_cell)), "NULL input");
   TcParams p{};
   p.mode = TC_EDGE; p.rows = n_faces; p.src0 = x_prime; p.src1 = e; p.idx = neighbour_cell; p.out0 = e_prime; p.out1 = e_out; p.ld_out = 128;
+  p.use_red = (e_out != nullptr && e_out == e && red_enabled()) ? 1 : 0;
   return launch_tc(p, mlp, st);
 }
 
