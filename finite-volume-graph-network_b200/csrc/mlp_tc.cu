@@ -27,13 +27,15 @@ constexpr int TM = 128;            // rows per tile (= UMMA M)
 constexpr int HIDN = 128;          // N of every layer (padded)
 constexpr int KTILE = 64;          // bf16 elements per 128-byte swizzle row
 constexpr int TILE_BYTES = 16384;  // [128 rows][128 B]
-constexpr int ARING = 5;           // A-operand K-tile ring slots
-constexpr int WRING = 2;           // W1 K-tile ring slots
+constexpr int ARING = 4;           // A-operand K-tile ring slots
+constexpr int WRING = 3;           // W1 K-tile ring slots (L2 -> smem bulk-copy latency ~2k cycles: 2 slots starve the MMA);
+                                   // layers with kt1 <= WRING (CellBlock, encoders, decoder) keep W1 resident instead
 constexpr int NEPI = 256;          // epilogue threads: warps 0-3 = group 0, warps 4-7 = group 1
 constexpr int NPROD = 256;         // producer threads (warps 8-15)
 constexpr int NPW = NPROD / 32;    // producer warps
-constexpr int WARP_PROD0 = NEPI / 32, WARP_MMA = WARP_PROD0 + NPW;
-constexpr int NTHREADS = (WARP_MMA + 1) * 32;
+constexpr int WARP_PROD0 = NEPI / 32, WARP_L1 = WARP_PROD0 + NPW, WARP_L23 = WARP_L1 + 1, WARP_LOAD = WARP_L23 + 2;
+constexpr int WARP_MMA = WARP_L1;  // (also allocates / frees TMEM)
+constexpr int NTHREADS = (WARP_LOAD + 1) * 32;
 constexpr int NACC = 3;                 // TMEM accumulators: two tiles in their epilogues + one being filled by layer 1
 constexpr int RPT = TM / (NPROD / 16);  // rows per producer thread per K-tile (8)
 constexpr uint32_t TMEM_COLS = 512;     // acc0 [0,128) | acc1 [128,256) | acc2 [256,384) | H0 [384,448) | H1 [448,512)
@@ -48,6 +50,7 @@ struct TcParams {
   int kt1;    // K-tiles of layer 1
   int k_in;   // ROWS: valid input width
   int n_out;  // valid outputs of layer 3
+  int dbg;      // FVGN_TC_DBG bit mask (timing experiments only; results are garbage when non-zero)
   int use_red;  // residual output aliases the residual input: add with red.global.add.v4.f32 (no load on the SM)
   const float* in; int ld_in;                               // ROWS
   const float* src0; const float* src1; const int32_t* idx;  // CELL: x, node_agg, cells_node_T ; EDGE: x', e, neighbour_cell
@@ -74,6 +77,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is not complete yet: fine for a
+// dedicated waiter, wrong for the MMA thread's event loop, which must go on to probe the other barriers)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -203,10 +219,10 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout smem_layout() {
   SmemLayout L;
   uint32_t o = 0;
-  L.a_off = o; o += ARING * TILE_BYTES;      // 80 KB  A-operand K-tile ring
+  L.a_off = o; o += ARING * TILE_BYTES;      // 64 KB  A-operand K-tile ring
   L.w2_off = o; o += 2 * TILE_BYTES;         // 32 KB
   L.w3_off = o; o += 2 * TILE_BYTES;         // 32 KB
-  L.wring_off = o; o += WRING * TILE_BYTES;  // 32 KB  W1 K-tile ring
+  L.wring_off = o; o += WRING * TILE_BYTES;  // 48 KB  W1 K-tile ring / resident W1
   L.stage_off = o; o += 8 * 4096;            // 32 KB  per-epilogue-warp output staging [32 rows][32 fp32]
   L.par_off = o; o += 5 * 128 * 4;           // b1 | b2 | b3 | ln_w | ln_b
   L.bar_off = o; o += 256;
@@ -281,6 +297,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
     // loads of K-tile step s (tile s / kt1, K-tile s % kt1) into registers.  Rows past the end of the last tile are clamped to
     // the last valid row (their results are never stored), so the hot path carries no bounds predicates.
     auto load = [&](int s, float4* v) {
+      if (p.dbg & 1) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+      }
       const int jl = s / kt1, t = s - jl * kt1;
       const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
       if (MODE == TC_EDGE) {
@@ -341,8 +362,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
       const uint32_t slot = (uint32_t)s % ARING;
       if (s >= ARING) mbar_wait(BAR(B_AEMPTY + slot), (((uint32_t)s / ARING) - 1) & 1, 1);
       unsigned char* dst = sA + slot * TILE_BYTES;
+      if (!(p.dbg & 16)) {
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) st_tile_f4(dst, hw + NHW * i, hl, v[i]);
+        for (int i = 0; i < RPT; ++i) st_tile_f4(dst, hw + NHW * i, hl, v[i]);
+      }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_AFULL + slot));
@@ -356,86 +379,77 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
       if (s + 2 < S) load(s + 2, vb);
       if (s + 1 < S) store(s + 1, va);
     }
-  } else if (warp == WARP_MMA) {
-    // ================================================================= MMA issuer + weight loader: one thread, event loop over mbarriers
+  } else if (warp == WARP_L1) {
+    // ================================================================= layer-1 MMA issuer: A ring x W1 ring -> accumulator jl % NACC
+    // One thread per dependency stream, each a plain sequential loop of blocking mbarrier waits (an earlier single-thread event loop
+    // over all barriers cost ~7k cycles per tile in polling latency alone).
+    if (lane == 0) {
+      const bool w1_resident = kt1 <= WRING;
+      uint32_t gk = 0;
+#pragma unroll 1
+      for (int jl = 0; jl < n_local; ++jl) {
+        const int a = jl % NACC;
+        if (jl >= NACC) mbar_wait(BAR(B_DFREE + a), (uint32_t)(jl / NACC - 1) & 1, 3);  // tile jl - NACC has left this accumulator
+        const uint32_t d = tmem_base + 128u * (uint32_t)a;
+#pragma unroll 1
+        for (int t = 0; t < kt1; ++t, ++gk) {
+          const uint32_t sa = gk % ARING, sw = w1_resident ? (uint32_t)t : gk % WRING;
+          mbar_wait(BAR(B_AFULL + sa), (gk / ARING) & 1, 4);
+          mbar_wait(BAR(B_WFULL + sw), w1_resident ? 0u : (gk / WRING) & 1, 5);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + sa * TILE_BYTES), b_base = smem_u32(sWr + sw * TILE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            if (!(p.dbg & 8)) umma_bf16(d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (t | kk) != 0);
+          umma_commit(BAR(B_AEMPTY + sa));  // both ring slots are free once these MMAs have read them
+          if (!w1_resident) umma_commit(BAR(B_WEMPTY + sw));
+        }
+        umma_commit(BAR(B_DFULL + a));
+      }
+    }
+    __syncwarp();
+  } else if (warp == WARP_L23 || warp == WARP_L23 + 1) {
+    // ================================================================= layer-2/3 MMA issuer of epilogue group g: A = hidden activations
+    // in TMEM (written by the group's epilogue), B = resident W2 / W3
+    if (lane == 0) {
+      const int g = warp - WARP_L23;
+      if (g < n_local) mbar_wait(BAR(B_WRES), 0, 6);
+      uint32_t hphase = 0;
+      const uint32_t h = tmem_base + TMEM_H0 + 64u * (uint32_t)g;
+#pragma unroll 1
+      for (int jl = g; jl < n_local; jl += 2) {
+        const int a = jl % NACC;
+        const uint32_t d = tmem_base + 128u * (uint32_t)a;
+#pragma unroll 1
+        for (int layer = 0; layer < 2; ++layer) {
+          mbar_wait(BAR(B_HREADY + g), hphase, 7); hphase ^= 1;
+          tc_fence_after();
+          const unsigned char* w = layer == 0 ? sW2 : sW3;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            if (!(p.dbg & 8)) umma_bf16_ts(d, h + 8u * (uint32_t)kk, umma_desc(smem_u32(w + (kk >> 2) * TILE_BYTES) + (kk & 3) * 32), IDESC_BF16_M128_N128, kk != 0);
+          umma_commit(BAR(B_DFULL + a));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == WARP_LOAD) {
+    // ================================================================= weight loader: W2/W3 once (resident); W1 K-tiles resident when they
+    // fit the ring (kt1 <= WRING), else streamed through it with TMA bulk copies
     if (lane == 0 && n_local > 0) {
-      // W2/W3 once, resident
       mbar_arrive_expect_tx(BAR(B_WRES), 4 * TILE_BYTES);
       bulk_g2s(smem_u32(sW2), p.packed + (size_t)kt1 * TILE_BYTES, 2 * TILE_BYTES, BAR(B_WRES));
       bulk_g2s(smem_u32(sW3), p.packed + (size_t)(kt1 + 2) * TILE_BYTES, 2 * TILE_BYTES, BAR(B_WRES));
-      const uint32_t S = (uint32_t)(n_local * kt1);
-      uint32_t wl = 0, wt = 0;         // W1 K-tiles issued to the ring, K-tile index inside the tile
-      uint32_t gk = 0;                 // K-tile counter shared by the A ring and the W1 ring (consumer side)
-      int jl = 0, tl = 0;              // layer-1 cursor: local tile, K-tile.  jl tiles have their layer 1 fully issued.
-      bool acc_ok = false;             // accumulator of the cursor's tile is free
-      int stage[2] = {0, 0};           // per epilogue group: 0 idle, 1 waiting for H1 (-> layer 2), 2 waiting for H2 (-> layer 3)
-      int cur[2] = {0, 1};             // per group: local tile in (or next to enter) layers 2/3
-      uint32_t hphase[2] = {0, 0};
-      int done = 0;
-      bool wres = false;
-      long long t_last = clock64();
-      while (done < n_local) {
-        bool progress = false;
-        // ---- stream W1 K-tiles (TMA bulk copies) as ring slots free up
-        if (wl < S) {
-          const uint32_t slot = wl % WRING;
-          if (wl < WRING || mbar_try_wait(BAR(B_WEMPTY + slot), ((wl / WRING) - 1) & 1)) {
-            mbar_arrive_expect_tx(BAR(B_WFULL + slot), TILE_BYTES);
-            bulk_g2s(smem_u32(sWr + slot * TILE_BYTES), p.packed + (size_t)wt * TILE_BYTES, TILE_BYTES, BAR(B_WFULL + slot));
-            ++wl;
-            if (++wt == (uint32_t)kt1) wt = 0;
-            progress = true;
-          }
-        }
-        // ---- layers 2 / 3 of the two in-flight tiles: A = hidden activations in TMEM, B = resident W2 / W3
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (stage[g] == 0 && cur[g] < jl) stage[g] = 1;
-          if (stage[g] != 0 && mbar_try_wait(BAR(B_HREADY + g), hphase[g])) {
-            hphase[g] ^= 1;
-            if (!wres) { mbar_wait(BAR(B_WRES), 0, 6); wres = true; }
-            tc_fence_after();
-            const uint32_t d = tmem_base + 128u * (uint32_t)(cur[g] % NACC);
-            const uint32_t h = tmem_base + TMEM_H0 + 64u * (uint32_t)g;
-            const unsigned char* w = stage[g] == 1 ? sW2 : sW3;
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              umma_bf16_ts(d, h + 8u * (uint32_t)kk, umma_desc(smem_u32(w + (kk >> 2) * TILE_BYTES) + (kk & 3) * 32), IDESC_BF16_M128_N128, kk != 0);
-            umma_commit(BAR(B_DFULL + cur[g] % NACC));
-            if (stage[g] == 1) stage[g] = 2;
-            else { stage[g] = 0; cur[g] += 2; ++done; }
-            progress = true;
-          }
-        }
-        // ---- layer 1 of the next tile: A ring x W1 ring into a free accumulator (runs up to one tile ahead of the epilogues)
-        if (jl < n_local) {
-          const int a = jl % NACC;
-          bool ok = true;
-          if (tl == 0 && !acc_ok) {
-            ok = (jl < NACC) || mbar_try_wait(BAR(B_DFREE + a), (uint32_t)(jl / NACC - 1) & 1);
-            acc_ok = ok;
-          }
-          const uint32_t sa = gk % ARING, sw = gk % WRING;
-          if (ok) ok = mbar_try_wait(BAR(B_AFULL + sa), (gk / ARING) & 1) && mbar_try_wait(BAR(B_WFULL + sw), (gk / WRING) & 1);
-          if (ok) {
-            tc_fence_after();
-            const uint32_t d = tmem_base + 128u * (uint32_t)a;
-            const uint32_t a_base = smem_u32(sA + sa * TILE_BYTES), b_base = smem_u32(sWr + sw * TILE_BYTES);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (tl | kk) != 0);
-            umma_commit(BAR(B_AEMPTY + sa));  // both ring slots are free once these MMAs have read them
-            umma_commit(BAR(B_WEMPTY + sw));
-            ++gk;
-            if (++tl == kt1) {
-              umma_commit(BAR(B_DFULL + a));
-              ++jl; tl = 0; acc_ok = false;
-            }
-            progress = true;
-          }
-        }
-        if (progress) t_last = clock64();
-        else if (clock64() - t_last > 4000000000LL) mbar_timeout(0, 0, 100 + stage[0] * 10 + stage[1]);
+      const bool w1_resident = kt1 <= WRING;
+      const uint32_t S = w1_resident ? (uint32_t)kt1 : (uint32_t)(n_local * kt1);
+      uint32_t wt = 0;
+#pragma unroll 1
+      for (uint32_t wl = 0; wl < S; ++wl) {
+        const uint32_t slot = wl % WRING;
+        if (wl >= WRING) mbar_wait(BAR(B_WEMPTY + slot), ((wl / WRING) - 1) & 1, 2);
+        mbar_arrive_expect_tx(BAR(B_WFULL + slot), TILE_BYTES);
+        bulk_g2s(smem_u32(sWr + slot * TILE_BYTES), p.packed + (size_t)wt * TILE_BYTES, TILE_BYTES, BAR(B_WFULL + slot));
+        if (++wt == (uint32_t)kt1) wt = 0;
       }
     }
     __syncwarp();
@@ -468,9 +482,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
+          if (p.dbg & 4) continue;
           tmem_ld32_issue(t_acc + 32 * c, r);
           tmem_ld_wait(r);
-          silu_chunk(r, bias + 32 * c, pk);
+          if (p.dbg & 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = r[j];
+          } else silu_chunk(r, bias + 32 * c, pk);
           tmem_st16(t_h + 16 * c, pk);
         }
         tmem_wait_st();
@@ -487,6 +505,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
         float s1 = 0.f, s2 = 0.f, x0 = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+          if (p.dbg & 6) continue;
           tmem_ld32_issue(t_acc + 32 * c, r);
           tmem_ld_wait(r);
           if (c == 0) x0 = __uint_as_float(r[0]) + b3[0];
@@ -508,14 +527,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         // one 32-column chunk: finish y in place, stage through the warp's swizzled tile, write full 128-byte lines
-        tmem_ld32_issue(t_acc + 32 * c, r);
-        tmem_ld_wait(r);
+        if (!(p.dbg & 4)) {
+          tmem_ld32_issue(t_acc + 32 * c, r);
+          tmem_ld_wait(r);
+        }
         if (c == 3) {  // last TMEM read of this tile: the accumulator may be overwritten by layer 1 of tile jl + NACC
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_DFREE + acc));
         }
         float* v = reinterpret_cast<float*>(r);
+        if (p.dbg & 6) continue;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 b = *reinterpret_cast<const float4*>(b3 + 32 * c + 4 * j4);
@@ -646,6 +668,7 @@ static bool red_enabled() {
 
 static int launch_tc(TcParams& p, const fvgn_mlp_t* m, cudaStream_t st) {
   if (p.rows <= 0) return 0;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FVGN_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   FVGN_CHECK_ARG(m->packed != nullptr, "tensor-core modes need packed weights: call fvgn_mlp_pack_bf16 first");
   p.packed = reinterpret_cast<const unsigned char*>(m->packed);
   p.b1 = m->b1; p.b2 = m->b2; p.b3 = m->b3; p.ln_w = m->ln_w; p.ln_b = m->ln_b;
