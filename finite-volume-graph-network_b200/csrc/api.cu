@@ -31,8 +31,8 @@ int simt_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t
 int node_aggregate(const float*, const int32_t*, const int32_t*, int, int, float*, cudaStream_t);
 // mlp_tc.cu (tcgen05)
 int tc_mlp_rows(const fvgn_mlp_t*, const float*, int, int, float*, int, int, cudaStream_t);
-int tc_cell_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, int, cudaStream_t);
-int tc_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, int, cudaStream_t);
+int tc_cell_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, int, cudaStream_t, uint16_t* = nullptr);
+int tc_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, int, cudaStream_t, const uint16_t* = nullptr);
 
 size_t tc_packed_bytes(int k_in);
 int tc_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
@@ -114,4 +114,20 @@ extern "C" int fvgn_edge_block_fwd(const fvgn_mlp_t* mlp, const float* x_prime, 
     return tc_edge_block(mlp, x_prime, e, neighbour_cell, n_faces, e_prime, e_out, math_mode, as_stream(stream));
   set_error("unknown math_mode %d", math_mode);
   return FVGN_E_BADARG;
+}
+
+extern "C" int fvgn_cell_block_fwd_xbf16(const fvgn_mlp_t* mlp, float* x, const float* node_agg, const int32_t* cells_node_T, int n_cells,
+                                         uint16_t* x_prime_bf16, int math_mode, fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  if (math_mode != FVGN_MATH_BF16_TC) { set_error("fvgn_cell_block_fwd_xbf16: tensor-core math mode only"); return FVGN_E_BADARG; }
+  if (!x_prime_bf16) { set_error("fvgn_cell_block_fwd_xbf16: x_prime_bf16 is NULL"); return FVGN_E_BADARG; }
+  return tc_cell_block(mlp, x, node_agg, cells_node_T, n_cells, nullptr, x, math_mode, as_stream(stream), x_prime_bf16);
+}
+
+extern "C" int fvgn_edge_block_fwd_xbf16(const fvgn_mlp_t* mlp, const uint16_t* x_prime_bf16, float* e, const int32_t* neighbour_cell,
+                                         int n_faces, int math_mode, fvgn_stream_t stream) {
+  if (int er = check_device()) return er;
+  if (math_mode != FVGN_MATH_BF16_TC) { set_error("fvgn_edge_block_fwd_xbf16: tensor-core math mode only"); return FVGN_E_BADARG; }
+  if (!x_prime_bf16) { set_error("fvgn_edge_block_fwd_xbf16: x_prime_bf16 is NULL"); return FVGN_E_BADARG; }
+  return tc_edge_block(mlp, nullptr, e, neighbour_cell, n_faces, nullptr, e, math_mode, as_stream(stream), x_prime_bf16);
 }

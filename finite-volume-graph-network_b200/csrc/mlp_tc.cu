@@ -27,9 +27,10 @@ constexpr int TM = 128;            // rows per tile (= UMMA M)
 constexpr int HIDN = 128;          // N of every layer (padded)
 constexpr int KTILE = 64;          // bf16 elements per 128-byte swizzle row
 constexpr int TILE_BYTES = 16384;  // [128 rows][128 B]
-constexpr int ARING = 4;           // A-operand K-tile ring slots
+constexpr int ARING_MAX = 5;       // A-operand K-tile ring slots: 5 for the EdgeBlock kernel, 4 otherwise (aring(mode))
 constexpr int WRING = 3;           // W1 K-tile ring slots (L2 -> smem bulk-copy latency ~2k cycles: 2 slots starve the MMA);
                                    // layers with kt1 <= WRING (CellBlock, encoders, decoder) keep W1 resident instead
+constexpr int GRING = 3, ERING = 2;  // EdgeBlock with the bf16 x' shadow: cp.async gather ring (slots 0-2) + fp32->bf16 stream ring (3-4)
 constexpr int NEPI = 256;          // epilogue threads: warps 0-3 = group 0, warps 4-7 = group 1
 constexpr int NPROD = 256;         // producer threads (warps 8-15)
 constexpr int NPW = NPROD / 32;    // producer warps
@@ -42,6 +43,7 @@ constexpr uint32_t TMEM_COLS = 512;     // acc0 [0,128) | acc1 [128,256) | acc2 
 constexpr uint32_t TMEM_H0 = 384;
 
 enum { TC_ROWS = 0, TC_CELL = 1, TC_EDGE = 2 };
+__host__ __device__ constexpr int aring(int mode) { return mode == TC_EDGE ? 5 : 4; }
 
 struct TcParams {
   int mode;
@@ -54,6 +56,8 @@ struct TcParams {
   int use_red;  // residual output aliases the residual input: add with red.global.add.v4.f32 (no load on the SM)
   const float* in; int ld_in;                               // ROWS
   const float* src0; const float* src1; const int32_t* idx;  // CELL: x, node_agg, cells_node_T ; EDGE: x', e, neighbour_cell
+  const __nv_bfloat16* xbf_in;  // EDGE<XBF>: bf16 shadow of x' [C,128] (gathered with cp.async straight into the operand tiles)
+  __nv_bfloat16* xbf_out;       // CELL<XBF>: x' is written as bf16 [C,128] (its only consumer is the EdgeBlock's bf16 A operand)
   float* out0; int ld_out;
   float* out1;
   const unsigned char* packed;  // [kt1 + 4] tiles: W1 tiles, W2 (2), W3 (2)
@@ -207,6 +211,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void red_add_f4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -216,22 +225,22 @@ __device__ __forceinline__ void red_add_f4(float* p, float4 v) {
 struct SmemLayout {
   uint32_t a_off, w2_off, w3_off, wring_off, stage_off, par_off, bar_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout() {
+__host__ __device__ inline SmemLayout smem_layout(int mode) {
   SmemLayout L;
   uint32_t o = 0;
-  L.a_off = o; o += ARING * TILE_BYTES;      // 64 KB  A-operand K-tile ring
-  L.w2_off = o; o += 2 * TILE_BYTES;         // 32 KB
-  L.w3_off = o; o += 2 * TILE_BYTES;         // 32 KB
-  L.wring_off = o; o += WRING * TILE_BYTES;  // 48 KB  W1 K-tile ring / resident W1
-  L.stage_off = o; o += 8 * 4096;            // 32 KB  per-epilogue-warp output staging [32 rows][32 fp32]
-  L.par_off = o; o += 5 * 128 * 4;           // b1 | b2 | b3 | ln_w | ln_b
+  L.a_off = o; o += aring(mode) * TILE_BYTES;  // 64 / 80 KB  A-operand K-tile ring(s)
+  L.w2_off = o; o += 2 * TILE_BYTES;           // 32 KB
+  L.w3_off = o; o += 2 * TILE_BYTES;           // 32 KB
+  L.wring_off = o; o += WRING * TILE_BYTES;    // 48 KB  W1 K-tile ring / resident W1
+  L.stage_off = o; o += 8 * 4096;              // 32 KB  per-epilogue-warp output staging [32 rows][32 fp32]
+  L.par_off = o; o += 5 * 128 * 4;             // b1 | b2 | b3 | ln_w | ln_b
   L.bar_off = o; o += 256;
-  L.total = o + 1024;                        // slack for the 1024-byte alignment of the dynamic smem base
+  L.total = o;                                 // EDGE: 232,192 B of the 232,448 B limit: the base must be 1024-aligned as declared
   return L;
 }
 
 // barrier indices (8 bytes each)
-enum { B_AFULL = 0, B_AEMPTY = B_AFULL + ARING, B_WFULL = B_AEMPTY + ARING, B_WEMPTY = B_WFULL + WRING, B_WRES = B_WEMPTY + WRING,
+enum { B_AFULL = 0, B_AEMPTY = B_AFULL + ARING_MAX, B_WFULL = B_AEMPTY + ARING_MAX, B_WEMPTY = B_WFULL + WRING, B_WRES = B_WEMPTY + WRING,
        B_DFULL = B_WRES + 1, B_DFREE = B_DFULL + NACC, B_HREADY = B_DFREE + NACC, B_COUNT = B_HREADY + 2 };
 
 // bias + SiLU of one 32-column accumulator chunk -> 16 packed bf16 pairs (bias read as broadcast LDS.128)
@@ -244,11 +253,14 @@ __device__ __forceinline__ void silu_chunk(const uint32_t* r, const float* bias,
   }
 }
 
-template <int MODE, bool RED>
+// MODE: TC_ROWS / TC_CELL / TC_EDGE.  RED: the residual output aliases its input (in-place add in L2).  XBF: x' travels between the
+// CellBlock and EdgeBlock kernels as a bf16 shadow (CELL writes it, EDGE gathers it with cp.async).
+template <int MODE, bool RED, bool XBF>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParams p) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const SmemLayout L = smem_layout();
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw;
+  constexpr int ARING = aring(MODE);
+  const SmemLayout L = smem_layout(MODE);
   unsigned char* sA = smem + L.a_off;
   unsigned char* sW2 = smem + L.w2_off;
   unsigned char* sW3 = smem + L.w3_off;
@@ -263,7 +275,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
   const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
-    for (int i = 0; i < ARING; ++i) { mbar_init(BAR(B_AFULL + i), NPW); mbar_init(BAR(B_AEMPTY + i), 1); }
+    if (smem_u32(smem) & 1023u) { printf("fvgn mlp_tc: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
+    for (int i = 0; i < ARING; ++i) { mbar_init(BAR(B_AFULL + i), (MODE == TC_EDGE && XBF) ? 4 : NPW); mbar_init(BAR(B_AEMPTY + i), 1); }
     for (int i = 0; i < WRING; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
     mbar_init(BAR(B_WRES), 1);
     for (int a = 0; a < NACC; ++a) { mbar_init(BAR(B_DFULL + a), 1); mbar_init(BAR(B_DFREE + a), 4); }
@@ -289,7 +302,99 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= WARP_PROD0 && warp < WARP_MMA) {
-    // ================================================================= producers: gather -> A ring (software pipelined)
+    // ================================================================= producers
+    if (MODE == TC_EDGE && XBF) {
+      const int last = p.rows - 1;
+      if (warp < WARP_PROD0 + 4) {
+        // ---- gather warps: x'[sender] / x'[receiver] halves from the bf16 shadow, 16-byte cp.async straight into the swizzled operand
+        // tiles (no registers, no conversion); ring of GRING slots, one commit group per K-tile, signalled one step behind the issue
+        const int gt = tid - NEPI;               // 0..127: 8 lanes per row (one 128-byte line), 16 rows per pass, 8 passes per K-tile
+        const int rl = gt >> 3, ch = gt & 7;
+        const uint32_t sw16 = (uint32_t)rl * 128u + ((((uint32_t)ch) ^ ((uint32_t)rl & 7u)) << 4);
+        int is_[8], ir_[8], ns[8], nr[8];
+        auto load_idx = [&](int jl, int* s_, int* r_) {
+          const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int f = min(row0 + rl + 16 * i, last);
+            s_[i] = __ldg(p.idx + f);
+            r_[i] = __ldg(p.idx + (size_t)p.rows + f);
+          }
+        };
+        if (n_local > 0) load_idx(0, ns, nr);
+        uint32_t gi = 0;
+#pragma unroll 1
+        for (int jl = 0; jl < n_local; ++jl) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { is_[i] = ns[i]; ir_[i] = nr[i]; }
+          if (jl + 1 < n_local) load_idx(jl + 1, ns, nr);  // next tile's indices: off the critical path of its row gathers
+#pragma unroll
+          for (int t = 0; t < 4; ++t, ++gi) {
+            const uint32_t slot = gi % GRING;
+            if (gi >= GRING) mbar_wait(BAR(B_AEMPTY + slot), ((gi / GRING) - 1) & 1, 1);
+            const uint32_t dst = smem_u32(sA + slot * TILE_BYTES) + sw16;
+            const __nv_bfloat16* src = p.xbf_in + (t & 1) * 64 + ch * 8;
+            if (!(p.dbg & 1)) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) cp_async16(dst + (uint32_t)i * 2048u, src + (size_t)(t < 2 ? is_[i] : ir_[i]) * 128);
+            }
+            cp_async_commit();
+            if (gi >= 1) {  // K-tile gi-1 has landed: publish it
+              cp_async_wait<1>();
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(BAR(B_AFULL + (gi - 1) % GRING));
+            }
+          }
+        }
+        if (gi >= 1) {
+          cp_async_wait<0>();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_AFULL + (gi - 1) % GRING));
+        }
+      } else {
+        // ---- stream warps: this tile's own e rows (fp32, contiguous) -> bf16 K-tiles 4,5 in ring slots GRING..GRING+ERING-1;
+        // half K-tiles (64 rows) per step so that two register buffers keep the next step's loads in flight
+        const int st_ = tid - NEPI - 128;        // 0..127
+        const int hw = st_ >> 4, hl = st_ & 15;  // half-warp hw owns rows 64*half + hw + 8*i
+        const int S = n_local * 4;               // half-K-tile steps
+        auto load = [&](int s, float4* v) {
+          const int jl = s >> 2, u = s & 3;      // u = 2*(t-4) + half
+          const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM + 64 * (u & 1);
+          const float* base = p.src1 + (u >> 1) * 64 + hl * 4;
+          if (p.dbg & 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            return;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = ldg4(base + (size_t)min(row0 + hw + 8 * i, last) * 128);
+        };
+        auto store = [&](int s, const float4* v) {
+          const uint32_t ei = (uint32_t)s >> 1;  // K-tile counter of the stream ring
+          const uint32_t slot = GRING + ei % ERING;
+          if ((s & 1) == 0 && ei >= ERING) mbar_wait(BAR(B_AEMPTY + slot), ((ei / ERING) - 1) & 1, 1);
+          unsigned char* dst = sA + slot * TILE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) st_tile_f4(dst, 64 * (s & 1) + hw + 8 * i, hl, v[i]);
+          if (s & 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(B_AFULL + slot));
+          }
+        };
+        float4 va[8], vb[8];
+#pragma unroll 1
+        for (int s = -1; s < S; s += 2) {
+          if (s + 1 < S) load(s + 1, va);
+          if (s >= 0) store(s, vb);
+          if (s + 2 < S) load(s + 2, vb);
+          if (s + 1 < S) store(s + 1, va);
+        }
+      }
+    } else {
+    // ----------------------------------------------------------------- generic producer: gather -> A ring (software pipelined)
     constexpr int NHW = NPROD / 16;          // half-warps: half-warp hw owns rows hw, hw+NHW, ...
     const int ptid = tid - NEPI;
     const int hw = ptid >> 4, hl = ptid & 15;
@@ -379,6 +484,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
       if (s + 2 < S) load(s + 2, vb);
       if (s + 1 < S) store(s + 1, va);
     }
+    }
   } else if (warp == WARP_L1) {
     // ================================================================= layer-1 MMA issuer: A ring x W1 ring -> accumulator jl % NACC
     // One thread per dependency stream, each a plain sequential loop of blocking mbarrier waits (an earlier single-thread event loop
@@ -393,8 +499,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
         const uint32_t d = tmem_base + 128u * (uint32_t)a;
 #pragma unroll 1
         for (int t = 0; t < kt1; ++t, ++gk) {
-          const uint32_t sa = gk % ARING, sw = w1_resident ? (uint32_t)t : gk % WRING;
-          mbar_wait(BAR(B_AFULL + sa), (gk / ARING) & 1, 4);
+          uint32_t sa = gk % ARING, pa = (gk / ARING) & 1;
+          if (MODE == TC_EDGE && XBF) {  // K-tiles 0-3 come through the cp.async gather ring, 4-5 through the stream ring
+            const uint32_t gi = 4u * (uint32_t)jl + (uint32_t)t, ei = 2u * (uint32_t)jl + (uint32_t)t - 4u;
+            sa = t < 4 ? gi % GRING : GRING + ei % ERING;
+            pa = t < 4 ? (gi / GRING) & 1 : (ei / ERING) & 1;
+          }
+          const uint32_t sw = w1_resident ? (uint32_t)t : gk % WRING;
+          mbar_wait(BAR(B_AFULL + sa), pa, 4);
           mbar_wait(BAR(B_WFULL + sw), w1_resident ? 0u : (gk / WRING) & 1, 5);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + sa * TILE_BYTES), b_base = smem_u32(sWr + sw * TILE_BYTES);
@@ -573,7 +685,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
               if (grow < p.rows) {
                 const float4 y = *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 128u + ((uint32_t)cp << 4));
                 const size_t off = (size_t)grow * 128 + 32 * c + 4 * (cp ^ (rr & 7));
-                if (p.out0) *reinterpret_cast<float4*>(p.out0 + off) = y;
+                if (MODE == TC_CELL && XBF) {
+                  uint2 pk;
+                  pk.x = pack_bf16(y.x, y.y); pk.y = pack_bf16(y.z, y.w);
+                  *reinterpret_cast<uint2*>(p.xbf_out + off) = pk;
+                } else if (p.out0) *reinterpret_cast<float4*>(p.out0 + off) = y;
                 red_add_f4(p.out1 + off, y);
               }
             }
@@ -675,22 +791,26 @@ static int launch_tc(TcParams& p, const fvgn_mlp_t* m, cudaStream_t st) {
   p.k_in = m->k_in; p.n_out = m->n_out;
   p.kt1 = kt_of(m->k_in);
   p.ntiles = cdiv(p.rows, TM);
-  const SmemLayout L = smem_layout();
-  static bool configured = false;
-  if (!configured) {
-    FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<TC_ROWS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<TC_CELL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<TC_CELL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<TC_EDGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<TC_EDGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    configured = true;
-  }
+  const SmemLayout L = smem_layout(p.mode);
   const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
-  if (p.mode == TC_ROWS) fused_mlp_tc_kernel<TC_ROWS, false><<<grid, NTHREADS, L.total, st>>>(p);
-  else if (p.mode == TC_CELL && p.use_red) fused_mlp_tc_kernel<TC_CELL, true><<<grid, NTHREADS, L.total, st>>>(p);
-  else if (p.mode == TC_CELL) fused_mlp_tc_kernel<TC_CELL, false><<<grid, NTHREADS, L.total, st>>>(p);
-  else if (p.use_red) fused_mlp_tc_kernel<TC_EDGE, true><<<grid, NTHREADS, L.total, st>>>(p);
-  else fused_mlp_tc_kernel<TC_EDGE, false><<<grid, NTHREADS, L.total, st>>>(p);
+  const bool xbf = (p.mode == TC_CELL && p.xbf_out) || (p.mode == TC_EDGE && p.xbf_in);
+#define FVGN_TC_LAUNCH(MODE, RED, XBF)                                                                                           \
+  do {                                                                                                                           \
+    static bool configured = false;                                                                                              \
+    if (!configured) {                                                                                                           \
+      FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<MODE, RED, XBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
+      configured = true;                                                                                                         \
+    }                                                                                                                            \
+    fused_mlp_tc_kernel<MODE, RED, XBF><<<grid, NTHREADS, L.total, st>>>(p);                                                     \
+  } while (0)
+  if (p.mode == TC_ROWS) FVGN_TC_LAUNCH(TC_ROWS, false, false);
+  else if (p.mode == TC_CELL && xbf) FVGN_TC_LAUNCH(TC_CELL, true, true);
+  else if (p.mode == TC_CELL && p.use_red) FVGN_TC_LAUNCH(TC_CELL, true, false);
+  else if (p.mode == TC_CELL) FVGN_TC_LAUNCH(TC_CELL, false, false);
+  else if (xbf) FVGN_TC_LAUNCH(TC_EDGE, true, true);
+  else if (p.use_red) FVGN_TC_LAUNCH(TC_EDGE, true, false);
+  else FVGN_TC_LAUNCH(TC_EDGE, false, false);
+#undef FVGN_TC_LAUNCH
   FVGN_LAUNCH_CHECK();
   return 0;
 }
@@ -715,24 +835,36 @@ int tc_mlp_rows(const fvgn_mlp_t* mlp, const float* in, int ld_in, int rows, flo
 }
 
 int tc_cell_block(const fvgn_mlp_t* mlp, const float* x, const float* node_agg, const int32_t* cells_node_T, int n_cells, float* x_prime,
-                  float* x_out, int math_mode, cudaStream_t st) {
+                  float* x_out, int math_mode, cudaStream_t st, uint16_t* x_prime_bf16) {
   if (int e = check_tc_mlp(mlp, true, math_mode)) return e;
   FVGN_CHECK_ARG(mlp->k_in == 192, "CellBlock MLP must have k_in == 192");
   FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && node_agg && cells_node_T)), "NULL input");
   TcParams p{};
   p.mode = TC_CELL; p.rows = n_cells; p.src0 = x; p.src1 = node_agg; p.idx = cells_node_T; p.out0 = x_prime; p.out1 = x_out; p.ld_out = 128;
   p.use_red = (x_out != nullptr && x_out == x && red_enabled()) ? 1 : 0;
+  if (x_prime_bf16) {
+    FVGN_CHECK_ARG(x_out != nullptr && x_out == x, "the bf16-shadow CellBlock updates x in place: x_out must alias x");
+    FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(x_prime_bf16) & 15) == 0, "x_prime_bf16 must be 16B aligned");
+    p.xbf_out = reinterpret_cast<__nv_bfloat16*>(x_prime_bf16);
+    p.use_red = 1;
+  }
   return launch_tc(p, mlp, st);
 }
 
 int tc_edge_block(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, const int32_t* neighbour_cell, int n_faces, float* e_prime,
-                  float* e_out, int math_mode, cudaStream_t st) {
+                  float* e_out, int math_mode, cudaStream_t st, const uint16_t* x_prime_bf16) {
   if (int er = check_tc_mlp(mlp, true, math_mode)) return er;
   FVGN_CHECK_ARG(mlp->k_in == 384, "EdgeBlock MLP must have k_in == 384");
-  FVGN_CHECK_ARG(n_faces >= 0 && (n_faces == 0 || (x_prime && e && neighbour_cell)), "NULL input");
+  FVGN_CHECK_ARG(n_faces >= 0 && (n_faces == 0 || ((x_prime || x_prime_bf16) && e && neighbour_cell)), "NULL input");
   TcParams p{};
   p.mode = TC_EDGE; p.rows = n_faces; p.src0 = x_prime; p.src1 = e; p.idx = neighbour_cell; p.out0 = e_prime; p.out1 = e_out; p.ld_out = 128;
   p.use_red = (e_out != nullptr && e_out == e && red_enabled()) ? 1 : 0;
+  if (x_prime_bf16) {
+    FVGN_CHECK_ARG(e_out != nullptr && e_out == e, "the bf16-shadow EdgeBlock updates e in place: e_out must alias e");
+    FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(x_prime_bf16) & 15) == 0, "x_prime_bf16 must be 16B aligned");
+    p.xbf_in = reinterpret_cast<const __nv_bfloat16*>(x_prime_bf16);
+    p.use_red = 1;
+  }
   return launch_tc(p, mlp, st);
 }
 

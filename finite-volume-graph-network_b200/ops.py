@@ -198,6 +198,28 @@ def edge_block_fwd(mlp: MlpRef, x_prime, e, neighbour_cell, math_mode=0, e_prime
     return e_prime, e_out
 
 
+def gn_block_fwd_inplace_bf16(cell_mlp: MlpRef, edge_mlp: MlpRef, x, e, node_agg, cells_node_T, neighbour_cell, x_prime_bf16):
+    """Tensor-core inference fast path of one GnBlock after the node aggregation: x += x', e += e' in place; x' only exists as the
+    bf16 shadow the EdgeBlock gathers (fvgn_cell_block_fwd_xbf16 / fvgn_edge_block_fwd_xbf16)."""
+    _req(x, torch.float32, "x", 2), _req(e, torch.float32, "edge_attr", 2), _req(node_agg, torch.float32, "node_agg", 2)
+    _req(x_prime_bf16, torch.bfloat16, "x_prime_bf16", 2)
+    _ci(cells_node_T, "cells_node_T", 3), _ci(neighbour_cell, "neighbour_cell", 2)
+    Cn, F = x.shape[0], e.shape[0]
+    if not (x.is_contiguous() and e.is_contiguous() and node_agg.is_contiguous() and x_prime_bf16.is_contiguous()) or x.shape[1] != HID \
+            or e.shape[1] != HID or tuple(x_prime_bf16.shape) != (Cn, HID) or cells_node_T.shape[1] != Cn or neighbour_cell.shape[1] != F:
+        raise ValueError("gn_block_fwd_inplace_bf16: bad shapes/strides")
+    cell_mlp.ensure_packed(), edge_mlp.ensure_packed()
+    L = _lib.lib()
+    _count(2)
+    with _timed("cell_block"):
+        check(L.fvgn_cell_block_fwd_xbf16(C.byref(cell_mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(x_prime_bf16), 1, _stream()),
+              "cell_block_fwd_xbf16")
+    with _timed("edge_block"):
+        check(L.fvgn_edge_block_fwd_xbf16(C.byref(edge_mlp.struct), _p(x_prime_bf16), _p(e), _p(neighbour_cell), F, 1, _stream()),
+              "edge_block_fwd_xbf16")
+    return x, e
+
+
 # ------------------------------------------------------------------------------------------------ connectivity
 def build_connectivity(cells, mesh_pos, node_type, face_rule="B"):
     """a1 on device.  cells int32[C,3], mesh_pos f32[N,2], node_type int32[N] (CUDA) -> dict of tables in the H5 layout of

@@ -155,6 +155,15 @@ FVGN_API int fvgn_edge_block_fwd(const fvgn_mlp_t* mlp, const float* x_prime /*[
                         const int32_t* neighbour_cell /*[2,F]*/, int n_faces, float* e_prime, float* e_out, int math_mode,
                         fvgn_stream_t stream);
 
+/* Tensor-core inference fast path of one GnBlock (EncoderProcesserDecoder.py:112-124): x' only ever feeds the EdgeBlock's bf16
+ * MMA operand, so it travels between the two kernels as a bf16 shadow [C,128] (half the gather bytes, cp.async straight into the
+ * operand tiles) and both latents are updated IN PLACE (x += x', e += e').  Results are bit-identical to
+ * fvgn_cell_block_fwd + fvgn_edge_block_fwd in FVGN_MATH_BF16_TC mode. */
+FVGN_API int fvgn_cell_block_fwd_xbf16(const fvgn_mlp_t* mlp, float* x /*[C,128] in/out*/, const float* node_agg, const int32_t* cells_node_T,
+                                       int n_cells, uint16_t* x_prime_bf16 /*[C,128] out*/, int math_mode, fvgn_stream_t stream);
+FVGN_API int fvgn_edge_block_fwd_xbf16(const fvgn_mlp_t* mlp, const uint16_t* x_prime_bf16 /*[C,128]*/, float* e /*[F,128] in/out*/,
+                                       const int32_t* neighbour_cell, int n_faces, int math_mode, fvgn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * a10. face-area feature + BatchNorm1d(1) (FVGN.py:77-79, 209-227 / 286-304):
  *      raw = len*dt/((A[s]+A[r])/2);  training=1: batch statistics (biased var for the output, unbiased into running_var,

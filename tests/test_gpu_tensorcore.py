@@ -69,6 +69,36 @@ def test_tc_cell_and_edge_block(fv, bf16_oracle, golden):
     ep, eo = fv.ops.edge_block_fwd(eb.mlp_ref(), xp, e.cuda(), nc.to(torch.int32).cuda(), math_mode=1, want_prime=True)
     assert H.rel_l2(ep.cpu(), ep_ref) < 2e-3, H.rel_l2(ep.cpu(), ep_ref)
     assert H.rel_l2(eo.cpu(), e.double() + ep_ref) < 2e-3
+    # in-place fast path with the bf16 x' shadow (fvgn_*_fwd_xbf16): same arithmetic => bit-identical to the two-call path above
+    x2, e2 = x.cuda().clone(), e.cuda().clone()
+    xb = torch.empty((C, 128), dtype=torch.bfloat16, device="cuda")
+    fv.ops.gn_block_fwd_inplace_bf16(cb.mlp_ref(), eb.mlp_ref(), x2, e2, na, cnT.to(torch.int32).cuda(), nc.to(torch.int32).cuda(), xb)
+    assert torch.equal(xb, xp.to(torch.bfloat16))
+    assert torch.equal(x2, xo) and torch.equal(e2, eo)
+
+
+@pytest.mark.parametrize("nx,ny", [(9, 7), (40, 33), (130, 97)])
+def test_tc_gn_block_fast_path_matches_two_call_path(fv, nx, ny):
+    """ragged sizes (last tile partial, fewer tiles than SMs / several tiles per SM): xbf16 fast path == generic tensor-core path"""
+    m = fv.synthetic.make("grid", seed=3, nx=nx, ny=ny, T=3)
+    tab = O.build_connectivity(m["mesh_pos"], m["cells"], m["node_type"], "B")
+    C, F, N = tab["cells_node"].shape[0], tab["face"].shape[1], tab["mesh_pos"].shape[0]
+    gen = torch.Generator().manual_seed(11)
+    x, e = torch.randn(C, 128, generator=gen).cuda(), torch.randn(F, 128, generator=gen).cuda()
+    cb, _ = _mlp_module(fv, 192, seed=6)
+    eb, _ = _mlp_module(fv, 384, seed=7)
+    cnT = torch.as_tensor(tab["cells_node"]).T.contiguous().to(torch.int32).cuda()
+    nc = torch.as_tensor(np.ascontiguousarray(tab["neighbour_cell"])).to(torch.int32).cuda()
+    ptr, items = fv.ops.build_csr(dev(tab["face"], torch.int32).reshape(-1), N)
+    na = fv.ops.node_aggregate_fwd(e, ptr, items, N)
+    xp, xo = fv.ops.cell_block_fwd(cb.mlp_ref(), x, na, cnT, math_mode=1)
+    _, eo = fv.ops.edge_block_fwd(eb.mlp_ref(), xp, e, nc, math_mode=1)
+    x2, e2 = x.clone(), e.clone()
+    xb = torch.empty((C, 128), dtype=torch.bfloat16, device="cuda")
+    for _ in range(2):  # twice from the same inputs: also run-to-run determinism
+        x2.copy_(x), e2.copy_(e)
+        fv.ops.gn_block_fwd_inplace_bf16(cb.mlp_ref(), eb.mlp_ref(), x2, e2, na, cnT, nc, xb)
+        assert torch.equal(xb, xp.to(torch.bfloat16)) and torch.equal(x2, xo) and torch.equal(e2, eo)
 
 
 def test_tc_forward_bound_and_determinism(fv):
