@@ -211,6 +211,27 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// L2 eviction-priority hints.  The residual rows (x / e) are read by the producers and read-modify-written by the epilogue's
+// red.global.add about three tile-times later: evict_last keeps them in L2 across that window (otherwise the add misses and the
+// row is fetched from HBM twice); the bf16 x' shadow is write-once here / read by the next kernel: evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg4_hint(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st2_hint(void* p, uint2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -236,8 +257,10 @@ __host__ __device__ inline SmemLayout smem_layout(int mode) {
   L.par_off = o; o += 5 * 128 * 4;             // b1 | b2 | b3 | ln_w | ln_b
   L.bar_off = o; o += 256;
   L.total = o;                                 // EDGE: 232,192 B of the 232,448 B limit: the base must be 1024-aligned as declared
-  return L;
+  return L;                                    // (CELL appends a 6 KB node-index ring behind L.total: smem_bytes(mode))
 }
+
+__host__ __device__ inline uint32_t smem_bytes(int mode) { return smem_layout(mode).total + (mode == TC_CELL ? 4 * 3 * 128 * 4 : 0); }
 
 // barrier indices (8 bytes each)
 enum { B_AFULL = 0, B_AEMPTY = B_AFULL + ARING_MAX, B_WFULL = B_AEMPTY + ARING_MAX, B_WEMPTY = B_WFULL + WRING, B_WRES = B_WEMPTY + WRING,
@@ -276,7 +299,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) { printf("fvgn mlp_tc: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
-    for (int i = 0; i < ARING; ++i) { mbar_init(BAR(B_AFULL + i), (MODE == TC_EDGE && XBF) ? 4 : NPW); mbar_init(BAR(B_AEMPTY + i), 1); }
+    for (int i = 0; i < ARING; ++i) { mbar_init(BAR(B_AFULL + i), ((MODE == TC_EDGE || MODE == TC_CELL) && XBF) ? 4 : NPW); mbar_init(BAR(B_AEMPTY + i), 1); }
     for (int i = 0; i < WRING; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
     mbar_init(BAR(B_WRES), 1);
     for (int a = 0; a < NACC; ++a) { mbar_init(BAR(B_DFULL + a), 1); mbar_init(BAR(B_DFREE + a), 4); }
@@ -303,9 +326,77 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
 
   if (warp >= WARP_PROD0 && warp < WARP_MMA) {
     // ================================================================= producers
-    if (MODE == TC_EDGE && XBF) {
+    if ((MODE == TC_EDGE || MODE == TC_CELL) && XBF) {
       const int last = p.rows - 1;
-      if (warp < WARP_PROD0 + 4) {
+      // stream ring: EDGE slots GRING.. (K-tiles 4,5 = e halves), CELL slots 0,1 (K-tiles 0,1 = x halves); both 2 slots
+      constexpr uint32_t SLOT_S0 = (MODE == TC_EDGE) ? GRING : 0;
+      if (MODE == TC_CELL && warp < WARP_PROD0 + 4) {
+        // ---- CellBlock gather warps: K-tile 2 = mean of the cell's three node_agg rows (fp32 gathers, summed in the reference's
+        // order), one tile per ring slot (slots 2,3).  The tile's 3 x 128 node indices are staged in a shared-memory ring by
+        // 4-byte cp.async two tiles ahead (they are the head of a dependent-load chain); rows are gathered in 16-row batches, two
+        // batches of registers so that the next batch's rows are in flight while this one is reduced.
+        const int gt = tid - NEPI;               // 0..127
+        const int hw = gt >> 4, hl = gt & 15;    // half-warp hw owns rows 16*b + hw + 8*i of batch b
+        const int C = p.rows;
+        int32_t* sIdx = reinterpret_cast<int32_t*>(smem + L.total);  // [4 tiles][3][128]
+        auto issue_idx = [&](int jl) {
+          if (jl < n_local) {
+            const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+            int32_t* dst = sIdx + (jl & 3) * 384;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const int c = min(row0 + gt, last);
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + k * 128 + gt)), "l"(p.idx + (size_t)k * C + c) : "memory");
+            }
+          }
+          cp_async_commit();
+        };
+        issue_idx(0);
+        issue_idx(1);
+        float4 fa[2][3], fb[2][3];
+        constexpr float k3 = 1.0f / 3.0f;  // rounded to bf16 right after: indistinguishable from the reference's division by 3
+#pragma unroll 1
+        for (int jl = 0; jl < n_local; ++jl) {
+          issue_idx(jl + 2);
+          cp_async_wait<2>();
+          named_bar_sync(1, 128);  // tile jl's indices (written by all four warps' copies) are visible
+          const int32_t* ix = sIdx + (jl & 3) * 384;
+          const uint32_t gi = (uint32_t)jl, slot = 2 + (gi & 1);
+          unsigned char* dst = sA + slot * TILE_BYTES;
+          auto load = [&](int bq, float4 (*f)[3]) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int r = 16 * bq + hw + 8 * i;
+              const int n0 = ix[r], n1 = ix[128 + r], n2 = ix[256 + r];
+              if (p.dbg & 1) { f[i][0] = f[i][1] = f[i][2] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+              f[i][0] = ldg4(p.src1 + (size_t)n0 * 64 + hl * 4);
+              f[i][1] = ldg4(p.src1 + (size_t)n1 * 64 + hl * 4);
+              f[i][2] = ldg4(p.src1 + (size_t)n2 * 64 + hl * 4);
+            }
+          };
+          auto reduce_store = [&](int bq, float4 (*f)[3]) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              st_tile_f4(dst, 16 * bq + hw + 8 * i, hl,
+                         make_float4(((f[i][0].x + f[i][1].x) + f[i][2].x) * k3, ((f[i][0].y + f[i][1].y) + f[i][2].y) * k3,
+                                     ((f[i][0].z + f[i][1].z) + f[i][2].z) * k3, ((f[i][0].w + f[i][1].w) + f[i][2].w) * k3));
+          };
+          load(0, fa);
+          load(1, fb);
+          if (gi >= 2) mbar_wait(BAR(B_AEMPTY + slot), ((gi >> 1) - 1) & 1, 1);
+#pragma unroll 1
+          for (int bq = 0; bq < 8; bq += 2) {
+            reduce_store(bq, fa);
+            if (bq + 2 < 8) load(bq + 2, fa);
+            reduce_store(bq + 1, fb);
+            if (bq + 3 < 8) load(bq + 3, fb);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_AFULL + slot));
+        }
+        cp_async_wait<0>();
+      } else if (MODE == TC_EDGE && warp < WARP_PROD0 + 4) {
         // ---- gather warps: x'[sender] / x'[receiver] halves from the bf16 shadow, 16-byte cp.async straight into the swizzled operand
         // tiles (no registers, no conversion); ring of GRING slots, one commit group per K-tile, signalled one step behind the issue
         const int gt = tid - NEPI;               // 0..127: 8 lanes per row (one 128-byte line), 16 rows per pass, 8 passes per K-tile
@@ -354,26 +445,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
           if (lane == 0) mbar_arrive(BAR(B_AFULL + (gi - 1) % GRING));
         }
       } else {
-        // ---- stream warps: this tile's own e rows (fp32, contiguous) -> bf16 K-tiles 4,5 in ring slots GRING..GRING+ERING-1;
-        // half K-tiles (64 rows) per step so that two register buffers keep the next step's loads in flight
+        // ---- stream warps: this tile's own residual rows (EDGE: e, CELL: x; fp32, contiguous) -> the two bf16 K-tiles of the stream
+        // ring; half K-tiles (64 rows) per step so that two register buffers keep the next step's loads in flight
         const int st_ = tid - NEPI - 128;        // 0..127
         const int hw = st_ >> 4, hl = st_ & 15;  // half-warp hw owns rows 64*half + hw + 8*i
         const int S = n_local * 4;               // half-K-tile steps
+        const uint64_t pol_keep = l2_policy_evict_last();
         auto load = [&](int s, float4* v) {
           const int jl = s >> 2, u = s & 3;      // u = 2*(t-4) + half
           const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM + 64 * (u & 1);
-          const float* base = p.src1 + (u >> 1) * 64 + hl * 4;
+          const float* base = (MODE == TC_EDGE ? p.src1 : p.src0) + (u >> 1) * 64 + hl * 4;
           if (p.dbg & 1) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             return;
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = ldg4(base + (size_t)min(row0 + hw + 8 * i, last) * 128);
+          for (int i = 0; i < 8; ++i) v[i] = ldg4_hint(base + (size_t)min(row0 + hw + 8 * i, last) * 128, pol_keep);
         };
         auto store = [&](int s, const float4* v) {
           const uint32_t ei = (uint32_t)s >> 1;  // K-tile counter of the stream ring
-          const uint32_t slot = GRING + ei % ERING;
+          const uint32_t slot = SLOT_S0 + ei % ERING;
           if ((s & 1) == 0 && ei >= ERING) mbar_wait(BAR(B_AEMPTY + slot), ((ei / ERING) - 1) & 1, 1);
           unsigned char* dst = sA + slot * TILE_BYTES;
 #pragma unroll
@@ -399,6 +491,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
     const int ptid = tid - NEPI;
     const int hw = ptid >> 4, hl = ptid & 15;
     const int S = n_local * kt1;             // K-tile steps of this CTA
+    const uint64_t pol_keep = l2_policy_evict_last();
     // loads of K-tile step s (tile s / kt1, K-tile s % kt1) into registers.  Rows past the end of the last tile are clamped to
     // the last valid row (their results are never stored), so the hot path carries no bounds predicates.
     auto load = [&](int s, float4* v) {
@@ -428,7 +521,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
         if (t < 2) {
           const float* base = p.src0 + t * 64 + hl * 4;
 #pragma unroll
-          for (int i = 0; i < RPT; ++i) v[i] = ldg4(base + (size_t)min(row0 + hw + NHW * i, C - 1) * 128);
+          for (int i = 0; i < RPT; ++i) v[i] = ldg4_hint(base + (size_t)min(row0 + hw + NHW * i, C - 1) * 128, pol_keep);
         } else {
           int n0[RPT], n1[RPT], n2[RPT];
 #pragma unroll
@@ -505,6 +598,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
             sa = t < 4 ? gi % GRING : GRING + ei % ERING;
             pa = t < 4 ? (gi / GRING) & 1 : (ei / ERING) & 1;
           }
+          if (MODE == TC_CELL && XBF) {  // K-tiles 0,1 (x) through stream slots 0,1; K-tile 2 (node_agg mean) through slots 2,3
+            const uint32_t ei = 2u * (uint32_t)jl + (uint32_t)t, gi = (uint32_t)jl;
+            sa = t < 2 ? ei % ERING : 2 + (gi & 1);
+            pa = t < 2 ? (ei / ERING) & 1 : (gi >> 1) & 1;
+          }
           const uint32_t sw = w1_resident ? (uint32_t)t : gk % WRING;
           mbar_wait(BAR(B_AFULL + sa), pa, 4);
           mbar_wait(BAR(B_WFULL + sw), w1_resident ? 0u : (gk / WRING) & 1, 5);
@@ -572,6 +670,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
     const uint32_t t_h = t_lane + TMEM_H0 + 64u * (uint32_t)g;
     unsigned char* stage = smem + L.stage_off + warp * 4096;  // [32 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
+    const uint64_t pol_stream = l2_policy_evict_first();
     const bool has_ln = (p.ln_w != nullptr);
     const bool staged = (MODE != TC_ROWS) || (p.n_out == HIDN && (p.ld_out & 3) == 0);
     const float* b3 = sPar + 2 * 128;
@@ -688,7 +787,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
                 if (MODE == TC_CELL && XBF) {
                   uint2 pk;
                   pk.x = pack_bf16(y.x, y.y); pk.y = pack_bf16(y.z, y.w);
-                  *reinterpret_cast<uint2*>(p.xbf_out + off) = pk;
+                  st2_hint(p.xbf_out + off, pk, pol_stream);
                 } else if (p.out0) *reinterpret_cast<float4*>(p.out0 + off) = y;
                 red_add_f4(p.out1 + off, y);
               }
@@ -798,10 +897,10 @@ static int launch_tc(TcParams& p, const fvgn_mlp_t* m, cudaStream_t st) {
   do {                                                                                                                           \
     static bool configured = false;                                                                                              \
     if (!configured) {                                                                                                           \
-      FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<MODE, RED, XBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
+      FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<MODE, RED, XBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MODE))); \
       configured = true;                                                                                                         \
     }                                                                                                                            \
-    fused_mlp_tc_kernel<MODE, RED, XBF><<<grid, NTHREADS, L.total, st>>>(p);                                                     \
+    fused_mlp_tc_kernel<MODE, RED, XBF><<<grid, NTHREADS, smem_bytes(MODE), st>>>(p);                                            \
   } while (0)
   if (p.mode == TC_ROWS) FVGN_TC_LAUNCH(TC_ROWS, false, false);
   else if (p.mode == TC_CELL && xbf) FVGN_TC_LAUNCH(TC_CELL, true, true);
