@@ -104,24 +104,18 @@ def device_batch(meshes, device):
     return gn, ge, gc, mi, mb
 
 
-def native(args, rank, world, local_rank):
+def measure_forward(args, workload, math, steps, rank, local_rank, dev, dist):
+    """One rollout benchmark: K steps of FVGN.forward (eval) + create_next_graph on `workload` in math mode `math`.
+    Returns device-resident timing, end-to-end (host buffers) timing, per-kernel CUDA-event timings and clock samples."""
     import fvgn_b200 as fv
     from fvgn_b200 import ops
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    fv._lib.lib()
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
-    meshes = make_meshes(args.workload, rank)
+    meshes = make_meshes(workload, rank)
     gn, ge, gc, mi, mb = device_batch(meshes, dev)
     C, F, N = gc.x.shape[0], ge.x.shape[0], gn.x.shape[0]
     torch.manual_seed(0)
     model = fv.FVGN(device="cpu", params=params()).to(dev)
-    model.set_math_mode(args.math)
+    model.set_math_mode(math)
     # prime the normalisers like the reference's first training rounds (2 accumulating forwards), then rollout mode
     model.train()
     with torch.no_grad():
@@ -152,11 +146,11 @@ def native(args, rank, world, local_rank):
             step()
         # ---------------- device-resident timing: K steps, L2 flushed between steps, CUDA events per step
         ops.TIMING = {"edge_block": [], "cell_block": [], "node_aggregate": []}
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         l0 = ops.LAUNCHES
         with ClockSampler(local_rank) as clk:
-            for k in range(args.steps):
+            for k in range(steps):
                 flush.zero_()
                 ev[k][0].record()
                 step()
@@ -177,7 +171,7 @@ def native(args, rank, world, local_rank):
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
-        for k in range(args.steps):
+        for k in range(steps):
             gc.x, gc.edge_attr = x_host.to(dev, non_blocking=True), ea_host.to(dev, non_blocking=True)
             uvp, nuv = step()
             nuv_host.copy_(nuv, non_blocking=True), uvp_host.copy_(uvp, non_blocking=True)
@@ -186,53 +180,100 @@ def native(args, rank, world, local_rank):
         t1.record()
         barrier()
         e2e_ms = t0.elapsed_time(t1)
-
     tms = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     cells = torch.tensor([float(C)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         dist.all_reduce(cells, op=dist.ReduceOp.SUM)
-    ms, e2e_ms = float(tms[0]), float(tms[1])
-    total_cells = float(cells[0])
+    del flush
+    torch.cuda.empty_cache()
+    return dict(ms=float(tms[0]), e2e_ms=float(tms[1]), total_cells=float(cells[0]), C=C, F=F, N=N, graphs=len(meshes), launches=int(launches),
+                kern=kern, clocks=clk.summary(), meshes=meshes, steps=steps)
+
+
+def roofline_of(m, math, workload):
+    """roofline object of the dominant kernel (the fused EdgeBlock kernel) from a measure_forward() result"""
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    C, F = m["C"], m["F"]
+    # Algorithmic bytes per launch, fp32 contract (DESIGN.md §4): e read + e written (2*512 B/face) + every x' row read once
+    # (512 B/cell) + neighbour_cell (8 B/face).  (The bf16 x' shadow of the tensor-core path moves 256 B/cell instead.)
+    edge_bytes = F * (2 * 512 + 8) + C * 512
+    kern = m["kern"]
+    edge_ms = float(np.mean(kern["edge_block"])) if kern["edge_block"] else None
+    ach = edge_bytes / (edge_ms * 1e-3) / 1e9 if edge_ms else None
+    shares = {k: (sum(v) / m["ms"] if v else 0.0) for k, v in kern.items()}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp)).get(f"{workload}:{math}:edge_block")
+        traffic = t["dram_bytes_per_launch"] if t else None
+    name = "fused_mlp_simt_kernel<EDGE>" if math == "fp32" else "fused_mlp_tc_kernel<TC_EDGE, RED, XBF>"
+    return {"kernel": name, "workload": workload, "math": math, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+            "frac": (ach / hbm) if ach else None, "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": edge_ms,
+            "algorithmic_bytes_per_launch": int(edge_bytes), "launches_timed": len(kern["edge_block"]), "share_of_step": shares,
+            "note": ("strict-fp32 mode is FFMA(compute)-bound (5.68 MFLOP/cell-update on the FP32 pipes), not HBM-bound: see DESIGN.md §4.2"
+                     if math == "fp32" else "")}
+
+
+DTYPES = {"fp32": "f32", "bf16": "bf16 tiles, f32 accumulate/residual", "bf16x3": "bf16x3 split tiles (~f32)"}
+
+
+def native(args, rank, world, local_rank):
+    import fvgn_b200 as fv
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    fv._lib.lib()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    m = measure_forward(args, args.workload, args.math, args.steps, rank, local_rank, dev, dist)
+    meshes = m["meshes"]
+    C, F, N = m["C"], m["F"], m["N"]
     result = None
     if rank == 0:
-        peaks = {}
-        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk):
-            peaks = json.load(open(pk))
-        hbm = peaks.get("hbm_gbs", 6650.0)
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        # dominant kernel: the fused EdgeBlock kernel.  Algorithmic bytes per launch:
-        #   e read + e written (2*512 B/face) + every x' row read once (512 B/cell) + neighbour_cell (8 B/face)
-        edge_bytes = F * (2 * 512 + 8) + C * 512
-        edge_ms = float(np.mean(kern["edge_block"])) if kern["edge_block"] else None
-        ach = edge_bytes / (edge_ms * 1e-3) / 1e9 if edge_ms else None
-        shares = {k: (sum(v) / ms if v else 0.0) for k, v in kern.items()}
         result = {
-            "metric": "cell_updates_per_sec", "value": total_cells * args.steps / (ms * 1e-3), "unit": "cell-updates/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16": "bf16 tiles, f32 accumulate/residual", "bf16x3": "bf16x3 split tiles (~f32)"}[args.math],
-            "data": "synthetic",
+            "metric": "cell_updates_per_sec", "value": m["total_cells"] * args.steps / (m["ms"] * 1e-3), "unit": "cell-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": m["ms"] / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.math], "data": "synthetic",
             "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "cells_per_rank": C, "faces_per_rank": F,
                        "nodes_per_rank": N, "graphs_per_rank": len(meshes), "message_passing_layers": 15, "hidden": 128, "math": args.math,
                        "step": "FVGN.forward (eval) + create_next_graph", "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": f"replicas x{world} (independent mesh batches, no collective)"},
-            "graphs_per_sec": len(meshes) * world * args.steps / (ms * 1e-3),
-            "e2e": {"value": total_cells * args.steps / (e2e_ms * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": int(C * 16 + F * 20),
-                    "d2h_bytes_per_step": int(C * 8 + F * 12), "ms_per_step": e2e_ms / args.steps,
+            "graphs_per_sec": len(meshes) * world * args.steps / (m["ms"] * 1e-3),
+            "e2e": {"value": m["total_cells"] * args.steps / (m["e2e_ms"] * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": int(C * 16 + F * 20),
+                    "d2h_bytes_per_step": int(C * 8 + F * 12), "ms_per_step": m["e2e_ms"] / args.steps,
                     "note": "pinned host inputs copied H2D and results D2H + host sync every step"},
-            "gpu_launches": int(launches),
-            "clocks": clk.summary(),
-            "roofline": {"kernel": "fused_mlp_simt_kernel<EDGE>" if args.math == "fp32" else "fused_mlp_tc_kernel<EDGE>", "bound": "hbm",
-                         "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": None,
-                         "peak_source": peak_src, "avg_launch_ms": edge_ms, "algorithmic_bytes_per_launch": int(edge_bytes),
-                         "launches_timed": len(kern["edge_block"]), "share_of_step": shares,
-                         "note": "fp32 mode is FFMA(compute)-bound, not HBM-bound: see DESIGN.md" if args.math == "fp32" else ""},
+            "gpu_launches": m["launches"],
+            "clocks": m["clocks"],
+            "roofline": roofline_of(m, args.math, args.workload),
         }
+    # ---- kernel roofline sweep (BASELINE configs[4]): the tcgen05 kernels on the 1M-cell mesh; its EdgeBlock kernel is the one the
+    # north star's ">= 50 % of HBM roofline" refers to, so it becomes the line's `roofline` (the default-mode kernel stays beside it)
+    if args.sweep != "none" and tuple(args.sweep.split(":")) != (args.workload, args.math):
+        sw_work, sw_math = args.sweep.split(":")
+        sm = measure_forward(args, sw_work, sw_math, min(args.steps, 5), rank, local_rank, dev, dist)
+        if rank == 0:
+            result["roofline_default_mode"] = result["roofline"]
+            result["roofline"] = roofline_of(sm, sw_math, sw_work)
+            result["sweep"] = {"workload": sw_work, "math": sw_math, "dtype": DTYPES[sw_math], "cells_per_rank": sm["C"], "faces_per_rank": sm["F"],
+                               "value": sm["total_cells"] * sm["steps"] / (sm["ms"] * 1e-3), "unit": "cell-updates/s",
+                               "ms_per_step": sm["ms"] / sm["steps"], "steps": sm["steps"],
+                               "e2e": {"value": sm["total_cells"] * sm["steps"] / (sm["e2e_ms"] * 1e-3), "unit": "cell-updates/s"},
+                               "whole_step_roofline": {"bytes_per_cell_update": 64200, "peak": result["roofline"]["peak"], "unit": "GB/s",
+                                                       "frac": 64200 * sm["total_cells"] * sm["steps"] / (sm["ms"] * 1e-3) / 1e9 / world
+                                                       / result["roofline"]["peak"]},
+                               "clocks": sm["clocks"], "gpu_launches": sm["launches"]}
+        del sm
     train = None
     if not args.no_training:
-        del flush
         torch.cuda.empty_cache()
         train = training_measure(args, rank, world, dev, meshes, dist)
     if rank == 0:
@@ -424,6 +465,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-training", action="store_true", help="skip the training graphs/s leg")
     ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--sweep", default="mesh1m:bf16", help="<workload>:<math> of the kernel roofline sweep leg, or 'none'")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
