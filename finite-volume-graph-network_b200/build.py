@@ -22,6 +22,7 @@ SOURCES = {
     "api.cu": [],
     "mlp_simt.cu": [],
     "mlp_tc.cu": [],
+    "mlp_tc3.cu": ["--fmad=false"],
     "mlp_bwd.cu": [],
     "connectivity.cu": ["--fmad=false"],
     "prepost.cu": ["--fmad=false"],

@@ -34,6 +34,13 @@ int tc_mlp_rows(const fvgn_mlp_t*, const float*, int, int, float*, int, int, cud
 int tc_cell_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, int, cudaStream_t, uint16_t* = nullptr);
 int tc_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, int, cudaStream_t, const uint16_t* = nullptr);
 
+// mlp_tc3.cu (tcgen05, 3-way split bf16 ~ fp32)
+int tc3_mlp_rows(const fvgn_mlp_t*, const float*, int, int, float*, int, cudaStream_t);
+int tc3_cell_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, cudaStream_t);
+int tc3_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, cudaStream_t);
+size_t tc3_packed_bytes(int k_in);
+int tc3_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
+
 size_t tc_packed_bytes(int k_in);
 int tc_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
 
@@ -80,12 +87,19 @@ extern "C" int fvgn_mlp_pack_bf16(const fvgn_mlp_t* mlp, void* packed, size_t pa
   return tc_pack(mlp, packed, packed_bytes, as_stream(stream));
 }
 
+extern "C" size_t fvgn_mlp_packed_x3_bytes(int k_in) { return tc3_packed_bytes(k_in); }
+
+extern "C" int fvgn_mlp_pack_bf16x3(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  return tc3_pack(mlp, packed, packed_bytes, as_stream(stream));
+}
+
 extern "C" int fvgn_mlp_rows_fwd(const fvgn_mlp_t* mlp, const float* in, int ld_in, int rows, float* out, int ld_out, int math_mode,
                                  fvgn_stream_t stream) {
   if (int e = check_device()) return e;
   if (math_mode == FVGN_MATH_FP32_SIMT) return simt_mlp_rows(mlp, in, ld_in, rows, out, ld_out, as_stream(stream));
-  if (math_mode == FVGN_MATH_BF16_TC || math_mode == FVGN_MATH_BF16X3_TC)
-    return tc_mlp_rows(mlp, in, ld_in, rows, out, ld_out, math_mode, as_stream(stream));
+  if (math_mode == FVGN_MATH_BF16_TC) return tc_mlp_rows(mlp, in, ld_in, rows, out, ld_out, math_mode, as_stream(stream));
+  if (math_mode == FVGN_MATH_BF16X3_TC) return tc3_mlp_rows(mlp, in, ld_in, rows, out, ld_out, as_stream(stream));
   set_error("unknown math_mode %d", math_mode);
   return FVGN_E_BADARG;
 }
@@ -100,8 +114,8 @@ extern "C" int fvgn_cell_block_fwd(const fvgn_mlp_t* mlp, const float* x, const 
                                    float* x_prime, float* x_out, int math_mode, fvgn_stream_t stream) {
   if (int e = check_device()) return e;
   if (math_mode == FVGN_MATH_FP32_SIMT) return simt_cell_block(mlp, x, node_agg, cells_node_T, n_cells, x_prime, x_out, as_stream(stream));
-  if (math_mode == FVGN_MATH_BF16_TC || math_mode == FVGN_MATH_BF16X3_TC)
-    return tc_cell_block(mlp, x, node_agg, cells_node_T, n_cells, x_prime, x_out, math_mode, as_stream(stream));
+  if (math_mode == FVGN_MATH_BF16_TC) return tc_cell_block(mlp, x, node_agg, cells_node_T, n_cells, x_prime, x_out, math_mode, as_stream(stream));
+  if (math_mode == FVGN_MATH_BF16X3_TC) return tc3_cell_block(mlp, x, node_agg, cells_node_T, n_cells, x_prime, x_out, as_stream(stream));
   set_error("unknown math_mode %d", math_mode);
   return FVGN_E_BADARG;
 }
@@ -110,8 +124,8 @@ extern "C" int fvgn_edge_block_fwd(const fvgn_mlp_t* mlp, const float* x_prime, 
                                    float* e_prime, float* e_out, int math_mode, fvgn_stream_t stream) {
   if (int er = check_device()) return er;
   if (math_mode == FVGN_MATH_FP32_SIMT) return simt_edge_block(mlp, x_prime, e, neighbour_cell, n_faces, e_prime, e_out, as_stream(stream));
-  if (math_mode == FVGN_MATH_BF16_TC || math_mode == FVGN_MATH_BF16X3_TC)
-    return tc_edge_block(mlp, x_prime, e, neighbour_cell, n_faces, e_prime, e_out, math_mode, as_stream(stream));
+  if (math_mode == FVGN_MATH_BF16_TC) return tc_edge_block(mlp, x_prime, e, neighbour_cell, n_faces, e_prime, e_out, math_mode, as_stream(stream));
+  if (math_mode == FVGN_MATH_BF16X3_TC) return tc3_edge_block(mlp, x_prime, e, neighbour_cell, n_faces, e_prime, e_out, as_stream(stream));
   set_error("unknown math_mode %d", math_mode);
   return FVGN_E_BADARG;
 }

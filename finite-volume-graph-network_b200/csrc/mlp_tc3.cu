@@ -1,0 +1,548 @@
+// mlp_tc3.cu — fp32-accurate tensor-core path (FVGN_MATH_BF16X3_TC): every GEMM operand (gathered rows, hidden activations, weights)
+// is split exactly into three bf16 terms a = a0 + a1 + a2 (8 + 8 + 8 significand bits = fp32's 24) and each product is evaluated as
+//   a.w ~= a0.w0 + a0.w1 + a1.w0 + a0.w2 + a1.w1 + a2.w0          (dropped terms <= 2^-24 |a.w|)
+// by six tcgen05.mma (kind::f16, bf16 operands, fp32 accumulation in TMEM).  Bias, SiLU (expf + IEEE division, as the strict FFMA
+// path), LayerNorm (two-pass) and the residual are fp32 in the epilogue, so results stay within the reference's 1e-5 per-step
+// relative tolerance (tests/test_gpu_parity.py runs the whole parity suite in this mode) at ~1/10 of the FFMA path's time.
+//
+// Tensor-bound (240 MMAs per 128-row EdgeBlock tile), so the pipeline is simpler than mlp_tc.cu: one persistent CTA per SM,
+//   warps 0-3   epilogue  : one thread per row; tcgen05.ld -> bias + SiLU -> 3-way split -> tcgen05.st (hidden activations stay in TMEM
+//                           as the A operand of the next layer); last layer: bias + LayerNorm + residual -> HBM via per-warp staging
+//   warps 4-11  producers : gather / stream the operand rows (fp32), split, write three swizzled bf16 K-tiles per 64 columns
+//   warp 12     MMA issuer: layer 1 of tile j+1 is issued before layers 2/3 of tile j (two accumulators)
+//   warp 13     loader    : ALL weights are streamed (3 x 160 KB per EdgeBlock MLP cannot stay resident): one 48 KB cp.async.bulk
+//                           per K-tile step through a 2-slot ring, in the MMA issuer's consumption order
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace fvgn {
+namespace x3 {
+
+constexpr int TM = 128, HIDN = 128, KTILE = 64;
+constexpr int TILE_BYTES = TC_TILE_BYTES, SLOT_BYTES = 3 * TILE_BYTES;  // one K-tile step = three split sub-tiles
+constexpr int ARING = 2, WRING = 2;
+constexpr int NEPI = 128, NPROD = 256, NPW = NPROD / 32;
+constexpr int WARP_PROD0 = NEPI / 32, WARP_MMA = WARP_PROD0 + NPW, WARP_LOAD = WARP_MMA + 1;
+constexpr int NTHREADS = (WARP_LOAD + 1) * 32;  // 448
+constexpr int RPT = TM / (NPROD / 16);          // 8 rows per producer thread per K-tile
+constexpr uint32_t TMEM_COLS = 512;             // acc0 [0,128) | acc1 [128,256) | H split 0 [256,320) | 1 [320,384) | 2 [384,448)
+constexpr uint32_t TMEM_H0 = 256;
+
+enum { TC_ROWS = 0, TC_CELL = 1, TC_EDGE = 2 };
+
+struct Params {
+  int mode, rows, ntiles, kt1, k_in, n_out;
+  const float* in; int ld_in;                               // ROWS
+  const float* src0; const float* src1; const int32_t* idx;  // CELL: x, node_agg, cells_node_T ; EDGE: x', e, neighbour_cell
+  float* out0; int ld_out;
+  float* out1;
+  const unsigned char* packed;  // [kt1 + 4] steps x [3 splits] x 16 KB
+  const float* b1; const float* b2; const float* b3; const float* ln_w; const float* ln_b;
+};
+
+// exact 3-way split of two fp32 values into three packed bf16 pairs (a = s0 + s1 + s2 up to 2^-24 relative)
+__device__ __forceinline__ void split3_pair(float a, float b, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  const __nv_bfloat16 a0 = __float2bfloat16_rn(a), b0 = __float2bfloat16_rn(b);
+  const float ra = a - __bfloat162float(a0), rb = b - __bfloat162float(b0);  // exact
+  const __nv_bfloat16 a1 = __float2bfloat16_rn(ra), b1 = __float2bfloat16_rn(rb);
+  const float sa = ra - __bfloat162float(a1), sb = rb - __bfloat162float(b1);  // exact
+  const __nv_bfloat16 a2 = __float2bfloat16_rn(sa), b2 = __float2bfloat16_rn(sb);
+  p0 = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
+  p1 = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+  p2 = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+}
+
+// 4 consecutive fp32 (columns 4*hl .. 4*hl+3 of a 64-wide K-tile) -> row r of the three swizzled split sub-tiles of one ring slot
+__device__ __forceinline__ void st_slot_f4(unsigned char* slot, int r, int hl, float4 v) {
+  const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)hl >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)hl & 1u) * 8u;
+  uint2 q0, q1, q2;
+  split3_pair(v.x, v.y, q0.x, q1.x, q2.x);
+  split3_pair(v.z, v.w, q0.y, q1.y, q2.y);
+  *reinterpret_cast<uint2*>(slot + off) = q0;
+  *reinterpret_cast<uint2*>(slot + TILE_BYTES + off) = q1;
+  *reinterpret_cast<uint2*>(slot + 2 * TILE_BYTES + off) = q2;
+}
+
+struct SmemLayout {
+  uint32_t a_off, w_off, stage_off, par_off, bar_off, total;
+};
+__host__ __device__ inline SmemLayout smem_layout() {
+  SmemLayout L;
+  uint32_t o = 0;
+  L.a_off = o; o += ARING * SLOT_BYTES;   // 96 KB
+  L.w_off = o; o += WRING * SLOT_BYTES;   // 96 KB
+  L.stage_off = o; o += 4 * 4096;         // 16 KB per-epilogue-warp output staging
+  L.par_off = o; o += 5 * 128 * 4;
+  L.bar_off = o; o += 256;
+  L.total = o;
+  return L;
+}
+
+enum { B_AFULL = 0, B_AEMPTY = B_AFULL + ARING, B_WFULL = B_AEMPTY + ARING, B_WEMPTY = B_WFULL + WRING, B_DFULL = B_WEMPTY + WRING,
+       B_DFREE = B_DFULL + 2, B_HREADY = B_DFREE + 2, B_COUNT = B_HREADY + 1 };
+
+// the six split products, most significant first: (A split, W split)
+__host__ __device__ constexpr int prod_a(int q) { return q == 2 || q == 4 ? 1 : (q == 5 ? 2 : 0); }  // 0 0 1 0 1 2
+__host__ __device__ constexpr int prod_w(int q) { return q == 1 || q == 4 ? 1 : (q == 3 ? 2 : 0); }  // 0 1 0 2 1 0
+
+template <int MODE, bool RED>
+__global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const SmemLayout L = smem_layout();
+  unsigned char* sA = smem + L.a_off;
+  unsigned char* sW = smem + L.w_off;
+  float* sPar = reinterpret_cast<float*>(smem + L.par_off);
+  const uint32_t bar0 = smem_u32(smem + L.bar_off);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * B_COUNT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kt1 = (MODE == TC_EDGE) ? 6 : (MODE == TC_CELL) ? 3 : p.kt1;
+  const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) { printf("fvgn mlp_tc3: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
+    for (int i = 0; i < ARING; ++i) { mbar_init(BAR(B_AFULL + i), NPW); mbar_init(BAR(B_AEMPTY + i), 1); }
+    for (int i = 0; i < WRING; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(BAR(B_DFULL + a), 1); mbar_init(BAR(B_DFREE + a), 4); }
+    mbar_init(BAR(B_HREADY), 4);
+    fence_mbar_init();
+  }
+  if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp >= WARP_PROD0 && warp < WARP_MMA) {
+    for (int i = tid - NEPI; i < 5 * 128; i += NPROD) {
+      const int which = i >> 7, c = i & 127;
+      float v = 0.f;
+      if (which == 0) v = p.b1[c];
+      else if (which == 1) v = p.b2[c];
+      else if (which == 2) v = (c < p.n_out) ? p.b3[c] : 0.f;
+      else if (which == 3) v = p.ln_w ? p.ln_w[c] : 1.f;
+      else v = p.ln_b ? p.ln_b[c] : 0.f;
+      sPar[i] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= WARP_PROD0 && warp < WARP_MMA) {
+    // ================================================================= producers: gather (fp32) -> split -> A ring
+    constexpr int NHW = NPROD / 16;
+    const int ptid = tid - NEPI;
+    const int hw = ptid >> 4, hl = ptid & 15;
+    const int S = n_local * kt1;
+    const int last = p.rows - 1;
+    auto load = [&](int s, float4* v) {
+      const int jl = s / kt1, t = s - jl * kt1;
+      const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+      if (MODE == TC_EDGE) {
+        const bool gath = t < 4;
+        const int32_t* ip = p.idx + (t >= 2 ? (size_t)p.rows : 0);
+        const float* base = (gath ? p.src0 : p.src1) + (t & 1) * 64 + hl * 4;
+        int src[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int f = min(row0 + hw + NHW * i, last);
+          src[i] = gath ? __ldg(ip + f) : f;
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) v[i] = ldg4(base + (size_t)src[i] * 128);
+      } else if (MODE == TC_CELL) {
+        const int C = p.rows;
+        if (t < 2) {
+          const float* base = p.src0 + t * 64 + hl * 4;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) v[i] = ldg4(base + (size_t)min(row0 + hw + NHW * i, last) * 128);
+        } else {
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int c = min(row0 + hw + NHW * i, last);
+            const int n0 = __ldg(p.idx + c), n1 = __ldg(p.idx + (size_t)C + c), n2 = __ldg(p.idx + 2 * (size_t)C + c);
+            const float4 a = ldg4(p.src1 + (size_t)n0 * 64 + hl * 4);
+            const float4 b = ldg4(p.src1 + (size_t)n1 * 64 + hl * 4);
+            const float4 d = ldg4(p.src1 + (size_t)n2 * 64 + hl * 4);
+            // the reference's arithmetic: (a + b) + c, then a true division by 3.0 (GN_blocks.py:125-129)
+            v[i] = make_float4(__fdiv_rn(__fadd_rn(__fadd_rn(a.x, b.x), d.x), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.y, b.y), d.y), 3.0f),
+                               __fdiv_rn(__fadd_rn(__fadd_rn(a.z, b.z), d.z), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.w, b.w), d.w), 3.0f));
+          }
+        }
+      } else {  // TC_ROWS
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int gr = row0 + hw + NHW * i;
+          float x4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (gr < p.rows) {
+            const int k0 = t * KTILE + hl * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (k0 + j < p.k_in) x4[j] = p.in[(size_t)gr * p.ld_in + k0 + j];
+          }
+          v[i] = make_float4(x4[0], x4[1], x4[2], x4[3]);
+        }
+      }
+    };
+    auto store = [&](int s, const float4* v) {
+      const uint32_t slot = (uint32_t)s % ARING;
+      if (s >= ARING) mbar_wait(BAR(B_AEMPTY + slot), (((uint32_t)s / ARING) - 1) & 1, 1);
+      unsigned char* dst = sA + slot * SLOT_BYTES;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) st_slot_f4(dst, hw + NHW * i, hl, v[i]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_AFULL + slot));
+    };
+    float4 va[RPT], vb[RPT];
+#pragma unroll 1
+    for (int s = -1; s < S; s += 2) {
+      if (s + 1 < S) load(s + 1, va);
+      if (s >= 0) store(s, vb);
+      if (s + 2 < S) load(s + 2, vb);
+      if (s + 1 < S) store(s + 1, va);
+    }
+  } else if (warp == WARP_LOAD) {
+    // ================================================================= weight loader: 48 KB per K-tile step, MMA consumption order
+    if (lane == 0 && n_local > 0) {
+      uint32_t wl = 0;
+      auto put = [&](int step) {
+        const uint32_t slot = wl % WRING;
+        if (wl >= WRING) mbar_wait(BAR(B_WEMPTY + slot), ((wl / WRING) - 1) & 1, 2);
+        mbar_arrive_expect_tx(BAR(B_WFULL + slot), SLOT_BYTES);
+        bulk_g2s(smem_u32(sW + slot * SLOT_BYTES), p.packed + (size_t)step * SLOT_BYTES, SLOT_BYTES, BAR(B_WFULL + slot));
+        ++wl;
+      };
+      for (int t = 0; t < kt1; ++t) put(t);
+#pragma unroll 1
+      for (int jl = 0; jl < n_local; ++jl) {
+        if (jl + 1 < n_local)
+          for (int t = 0; t < kt1; ++t) put(t);
+        for (int t = 0; t < 4; ++t) put(kt1 + t);  // W2 (2 steps), W3 (2 steps)
+      }
+    }
+    __syncwarp();
+  } else if (warp == WARP_MMA) {
+    // ================================================================= MMA issuer
+    if (lane == 0 && n_local > 0) {
+      uint32_t ak = 0, wk = 0, hphase = 0;
+      auto layer1 = [&](int jl) {
+        const int a = jl & 1;
+        if (jl >= 2) mbar_wait(BAR(B_DFREE + a), (uint32_t)((jl >> 1) - 1) & 1, 3);
+        const uint32_t d = tmem_base + 128u * (uint32_t)a;
+#pragma unroll 1
+        for (int t = 0; t < kt1; ++t, ++ak, ++wk) {
+          const uint32_t sa = ak % ARING, sw = wk % WRING;
+          mbar_wait(BAR(B_AFULL + sa), (ak / ARING) & 1, 4);
+          mbar_wait(BAR(B_WFULL + sw), (wk / WRING) & 1, 5);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + sa * SLOT_BYTES), b_base = smem_u32(sW + sw * SLOT_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+              umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
+                        IDESC_BF16_M128_N128, (t | kk | q) != 0);
+          umma_commit(BAR(B_AEMPTY + sa));
+          umma_commit(BAR(B_WEMPTY + sw));
+        }
+        umma_commit(BAR(B_DFULL + a));
+      };
+      auto layer23 = [&](int jl) {
+        const int a = jl & 1;
+        const uint32_t d = tmem_base + 128u * (uint32_t)a;
+#pragma unroll 1
+        for (int layer = 0; layer < 2; ++layer) {
+          mbar_wait(BAR(B_HREADY), hphase, 7); hphase ^= 1;
+#pragma unroll 1
+          for (int t = 0; t < 2; ++t, ++wk) {
+            const uint32_t sw = wk % WRING;
+            mbar_wait(BAR(B_WFULL + sw), (wk / WRING) & 1, 6);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(sW + sw * SLOT_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+              for (int q = 0; q < 6; ++q)
+                umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
+                             umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32), IDESC_BF16_M128_N128, (t | kk | q) != 0);
+            umma_commit(BAR(B_WEMPTY + sw));
+          }
+          umma_commit(BAR(B_DFULL + a));
+        }
+      };
+      layer1(0);
+#pragma unroll 1
+      for (int jl = 0; jl < n_local; ++jl) {
+        if (jl + 1 < n_local) layer1(jl + 1);  // runs under tile jl's epilogues (second accumulator)
+        layer23(jl);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================= epilogue warps 0-3: one thread per row
+    const int q = warp & 3;
+    const int erow = 32 * q + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t t_h = t_lane + TMEM_H0;
+    unsigned char* stage = smem + L.stage_off + warp * 4096;
+    const bool has_ln = (p.ln_w != nullptr);
+    const bool staged = (MODE != TC_ROWS) || (p.n_out == HIDN && (p.ld_out & 3) == 0);
+    const float* b3 = sPar + 2 * 128;
+    const float* gw = sPar + 3 * 128;
+    const float* gb = sPar + 4 * 128;
+#pragma unroll 1
+    for (int jl = 0; jl < n_local; ++jl) {
+      const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+      const int acc = jl & 1;
+      const uint32_t t_acc = t_lane + 128u * (uint32_t)acc;
+      const uint32_t dfull = BAR(B_DFULL + acc);
+      const uint32_t use0 = 3u * (uint32_t)(jl >> 1);
+      uint32_t r[32];
+#pragma unroll 1
+      for (int layer = 0; layer < 2; ++layer) {
+        mbar_wait(dfull, (use0 + (uint32_t)layer) & 1, 8);
+        tc_fence_after();
+        const float* bias = sPar + layer * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32_issue(t_acc + 32 * c, r);
+          tmem_ld_wait(r);
+          uint32_t p0[16], p1[16], p2[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float u = silu_f(__uint_as_float(r[2 * j]) + bias[32 * c + 2 * j]);
+            const float w = silu_f(__uint_as_float(r[2 * j + 1]) + bias[32 * c + 2 * j + 1]);
+            split3_pair(u, w, p0[j], p1[j], p2[j]);
+          }
+          tmem_st16(t_h + 16 * c, p0);
+          tmem_st16(t_h + 64 + 16 * c, p1);
+          tmem_st16(t_h + 128 + 16 * c, p2);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_HREADY));
+      }
+      mbar_wait(dfull, (use0 + 2u) & 1, 9);
+      tc_fence_after();
+      float mean = 0.f, rstd = 1.f;
+      if (has_ln) {  // two-pass LayerNorm statistics, as torch
+        float s = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32_issue(t_acc + 32 * c, r);
+          tmem_ld_wait(r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += __uint_as_float(r[j]) + b3[32 * c + j];
+        }
+        mean = s * (1.0f / 128.0f);
+        float qv = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32_issue(t_acc + 32 * c, r);
+          tmem_ld_wait(r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float d = (__uint_as_float(r[j]) + b3[32 * c + j]) - mean; qv = fmaf(d, d, qv); }
+        }
+        rstd = 1.0f / sqrtf(qv * (1.0f / 128.0f) + 1e-5f);
+      }
+      const float* res = (MODE == TC_CELL) ? p.src0 : p.src1;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32_issue(t_acc + 32 * c, r);
+        tmem_ld_wait(r);
+        if (c == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_DFREE + acc));
+        }
+        float* v = reinterpret_cast<float*>(r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float y = v[j] + b3[32 * c + j];
+          if (has_ln) y = (y - mean) * rstd * gw[32 * c + j] + gb[32 * c + j];
+          v[j] = y;
+        }
+        if (staged) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(stage + (uint32_t)lane * 128u + (((uint32_t)k ^ ((uint32_t)lane & 7u)) << 4)) =
+                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          __syncwarp();
+          const int rr0 = lane >> 3, cp = lane & 7;
+          if (MODE == TC_ROWS) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = 4 * it + rr0, grow = row0 + 32 * q + rr;
+              if (grow < p.rows)
+                *reinterpret_cast<float4*>(p.out0 + (size_t)grow * p.ld_out + 32 * c + 4 * (cp ^ (rr & 7))) =
+                    *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 128u + ((uint32_t)cp << 4));
+            }
+          } else if (RED) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = 4 * it + rr0, grow = row0 + 32 * q + rr;
+              if (grow < p.rows) {
+                const float4 y = *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 128u + ((uint32_t)cp << 4));
+                const size_t off = (size_t)grow * 128 + 32 * c + 4 * (cp ^ (rr & 7));
+                if (p.out0) *reinterpret_cast<float4*>(p.out0 + off) = y;
+                red_add_f4(p.out1 + off, y);
+              }
+            }
+          } else {
+            float4 rv[8];
+            if (p.out1) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = 4 * it + rr0, grow = min(row0 + 32 * q + rr, p.rows - 1);
+                rv[it] = *reinterpret_cast<const float4*>(res + (size_t)grow * 128 + 32 * c + 4 * (cp ^ (rr & 7)));
+              }
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = 4 * it + rr0, grow = row0 + 32 * q + rr;
+              if (grow < p.rows) {
+                const float4 y = *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 128u + ((uint32_t)cp << 4));
+                const size_t off = (size_t)grow * 128 + 32 * c + 4 * (cp ^ (rr & 7));
+                if (p.out0) *reinterpret_cast<float4*>(p.out0 + off) = y;
+                if (p.out1) *reinterpret_cast<float4*>(p.out1 + off) = make_float4(rv[it].x + y.x, rv[it].y + y.y, rv[it].z + y.z, rv[it].w + y.w);
+              }
+            }
+          }
+          __syncwarp();
+        } else {
+          const int grow = row0 + erow;
+          if (grow < p.rows) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = 32 * c + j;
+              if (col < p.n_out) p.out0[(size_t)grow * p.ld_out + col] = v[j];
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// W [n_valid, k_valid] fp32 row-major -> steps [kt][3 splits][128 rows][64 k] bf16, each sub-tile a byte image of the swizzled layout
+__global__ void pack_tiles3_kernel(const float* __restrict__ W, int ldw, int n_valid, int k_valid, int kt, unsigned char* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (tile, n, chunk)
+  if (idx >= kt * 128 * 8) return;
+  const int c = idx & 7, n = (idx >> 3) & 127, t = idx >> 10;
+  uint4 q0, q1, q2;
+  uint32_t* a0 = reinterpret_cast<uint32_t*>(&q0);
+  uint32_t* a1 = reinterpret_cast<uint32_t*>(&q1);
+  uint32_t* a2 = reinterpret_cast<uint32_t*>(&q2);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = t * KTILE + c * 8 + 2 * j;
+    const float x = (n < n_valid && k < k_valid) ? W[(size_t)n * ldw + k] : 0.f;
+    const float y = (n < n_valid && k + 1 < k_valid) ? W[(size_t)n * ldw + k + 1] : 0.f;
+    split3_pair(x, y, a0[j], a1[j], a2[j]);
+  }
+  const size_t off = (size_t)t * SLOT_BYTES + (size_t)n * 128 + (((uint32_t)c ^ ((uint32_t)n & 7u)) << 4);
+  *reinterpret_cast<uint4*>(out + off) = q0;
+  *reinterpret_cast<uint4*>(out + TILE_BYTES + off) = q1;
+  *reinterpret_cast<uint4*>(out + 2 * TILE_BYTES + off) = q2;
+}
+
+static int kt_of(int k_in) { return (k_in + KTILE - 1) / KTILE; }
+
+}  // namespace x3
+
+size_t tc3_packed_bytes(int k_in) { return (size_t)(x3::kt_of(k_in) + 4) * x3::SLOT_BYTES; }
+
+int tc3_pack(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t st) {
+  using namespace x3;
+  FVGN_CHECK_ARG(m && packed, "NULL pointer");
+  FVGN_CHECK_ARG(m->k_in >= 1 && m->k_in <= 384 && m->n_out >= 1 && m->n_out <= 128, "bad mlp dims");
+  FVGN_CHECK_ARG(bytes >= tc3_packed_bytes(m->k_in), "packed buffer too small");
+  FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed buffer must be 16B aligned");
+  const int kt1 = kt_of(m->k_in);
+  unsigned char* o = reinterpret_cast<unsigned char*>(packed);
+  pack_tiles3_kernel<<<cdiv(kt1 * 1024, 256), 256, 0, st>>>(m->w1, m->k_in, 128, m->k_in, kt1, o);
+  FVGN_LAUNCH_CHECK();
+  pack_tiles3_kernel<<<cdiv(2 * 1024, 256), 256, 0, st>>>(m->w2, 128, 128, 128, 2, o + (size_t)kt1 * SLOT_BYTES);
+  FVGN_LAUNCH_CHECK();
+  pack_tiles3_kernel<<<cdiv(2 * 1024, 256), 256, 0, st>>>(m->w3, 128, m->n_out, 128, 2, o + (size_t)(kt1 + 2) * SLOT_BYTES);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t st) {
+  using namespace x3;
+  if (p.rows <= 0) return 0;
+  FVGN_CHECK_ARG(m->packed_x3 != nullptr, "FVGN_MATH_BF16X3_TC needs split-packed weights: call fvgn_mlp_pack_bf16x3 first");
+  p.packed = reinterpret_cast<const unsigned char*>(m->packed_x3);
+  p.b1 = m->b1; p.b2 = m->b2; p.b3 = m->b3; p.ln_w = m->ln_w; p.ln_b = m->ln_b;
+  p.k_in = m->k_in; p.n_out = m->n_out;
+  p.kt1 = kt_of(m->k_in);
+  p.ntiles = cdiv(p.rows, TM);
+  const SmemLayout L = smem_layout();
+  const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
+#define FVGN_TC3_LAUNCH(MODE, RED)                                                                                       \
+  do {                                                                                                                   \
+    static bool configured = false;                                                                                      \
+    if (!configured) {                                                                                                   \
+      FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc3_kernel<MODE, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
+      configured = true;                                                                                                 \
+    }                                                                                                                    \
+    fused_mlp_tc3_kernel<MODE, RED><<<grid, NTHREADS, L.total, st>>>(p);                                                 \
+  } while (0)
+  if (p.mode == TC_ROWS) FVGN_TC3_LAUNCH(TC_ROWS, false);
+  else if (p.mode == TC_CELL && red) FVGN_TC3_LAUNCH(TC_CELL, true);
+  else if (p.mode == TC_CELL) FVGN_TC3_LAUNCH(TC_CELL, false);
+  else if (red) FVGN_TC3_LAUNCH(TC_EDGE, true);
+  else FVGN_TC3_LAUNCH(TC_EDGE, false);
+#undef FVGN_TC3_LAUNCH
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+static int check_mlp3(const fvgn_mlp_t* m, bool need_ln) {
+  FVGN_CHECK_ARG(m != nullptr, "mlp is NULL");
+  FVGN_CHECK_ARG(m->w1 && m->b1 && m->w2 && m->b2 && m->w3 && m->b3, "mlp weight pointer is NULL");
+  if (m->ln_w || need_ln) FVGN_CHECK_ARG(m->ln_w && m->ln_b && m->n_out == 128, "LayerNorm needs weight/bias and n_out == 128");
+  return 0;
+}
+
+int tc3_mlp_rows(const fvgn_mlp_t* mlp, const float* in, int ld_in, int rows, float* out, int ld_out, cudaStream_t st) {
+  if (int e = check_mlp3(mlp, false)) return e;
+  FVGN_CHECK_ARG(mlp->k_in <= 384, "k_in too large");
+  FVGN_CHECK_ARG(rows >= 0 && (rows == 0 || (in && out)), "in/out NULL");
+  FVGN_CHECK_ARG(ld_in >= mlp->k_in && ld_out >= mlp->n_out, "leading dimension too small");
+  if (mlp->n_out == 128 && (ld_out & 3) == 0) FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "output must be 16B aligned");
+  x3::Params p{};
+  p.mode = x3::TC_ROWS; p.rows = rows; p.in = in; p.ld_in = ld_in; p.out0 = out; p.ld_out = ld_out;
+  return launch_tc3(p, mlp, false, st);
+}
+
+int tc3_cell_block(const fvgn_mlp_t* mlp, const float* x, const float* node_agg, const int32_t* cells_node_T, int n_cells, float* x_prime,
+                   float* x_out, cudaStream_t st) {
+  if (int e = check_mlp3(mlp, true)) return e;
+  FVGN_CHECK_ARG(mlp->k_in == 192, "CellBlock MLP must have k_in == 192");
+  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && node_agg && cells_node_T)), "NULL input");
+  x3::Params p{};
+  p.mode = x3::TC_CELL; p.rows = n_cells; p.src0 = x; p.src1 = node_agg; p.idx = cells_node_T; p.out0 = x_prime; p.out1 = x_out; p.ld_out = 128;
+  return launch_tc3(p, mlp, x_out != nullptr && x_out == x, st);
+}
+
+int tc3_edge_block(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, const int32_t* neighbour_cell, int n_faces, float* e_prime,
+                   float* e_out, cudaStream_t st) {
+  if (int er = check_mlp3(mlp, true)) return er;
+  FVGN_CHECK_ARG(mlp->k_in == 384, "EdgeBlock MLP must have k_in == 384");
+  FVGN_CHECK_ARG(n_faces >= 0 && (n_faces == 0 || (x_prime && e && neighbour_cell)), "NULL input");
+  x3::Params p{};
+  p.mode = x3::TC_EDGE; p.rows = n_faces; p.src0 = x_prime; p.src1 = e; p.idx = neighbour_cell; p.out0 = e_prime; p.out1 = e_out; p.ld_out = 128;
+  return launch_tc3(p, mlp, e_out != nullptr && e_out == e, st);
+}
+
+}  // namespace fvgn

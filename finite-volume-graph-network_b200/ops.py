@@ -96,7 +96,7 @@ def as_i32(t):
 class MlpRef:
     """Borrowed pointers to one build_mlp's parameters (reference state_dict layout)."""
 
-    __slots__ = ("tensors", "struct", "k_in", "n_out", "packed", "packed_versions")
+    __slots__ = ("tensors", "struct", "k_in", "n_out", "packed", "packed_versions", "packed3", "packed3_versions")
 
     def __init__(self, w1, b1, w2, b2, w3, b3, ln_w=None, ln_b=None):
         ts = [w1, b1, w2, b2, w3, b3] + ([ln_w, ln_b] if ln_w is not None else [])
@@ -110,13 +110,27 @@ class MlpRef:
         self.k_in, self.n_out = int(w1.shape[1]), int(w3.shape[0])
         self.struct = MlpT(w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(),
                            ln_w.data_ptr() if ln_w is not None else None, ln_b.data_ptr() if ln_b is not None else None,
-                           self.k_in, self.n_out, None)
+                           self.k_in, self.n_out, None, None)
         self.packed = None
         self.packed_versions = None
+        self.packed3 = None
+        self.packed3_versions = None
 
-    def ensure_packed(self):
-        """(Re)build the bf16 swizzled weight tiles the tcgen05 path reads, if the fp32 weights changed since the last pack."""
+    def ensure_packed(self, math_mode=1):
+        """(Re)build the swizzled weight tiles the tcgen05 paths read (math_mode 1: bf16; 2: exact 3-way bf16 split), if the fp32
+        weights changed since the last pack."""
         ver = tuple(t._version for t in self.tensors[:6:2])
+        if math_mode == 2:
+            if self.packed3 is None or self.packed3_versions != ver:
+                L = _lib.lib()
+                nbytes = L.fvgn_mlp_packed_x3_bytes(self.k_in)
+                if self.packed3 is None:
+                    self.packed3 = torch.empty(nbytes, dtype=torch.uint8, device=self.tensors[0].device)
+                    self.struct.packed_x3 = self.packed3.data_ptr()
+                _count(3)
+                check(L.fvgn_mlp_pack_bf16x3(C.byref(self.struct), _p(self.packed3), nbytes, _stream()), "mlp_pack_bf16x3")
+                self.packed3_versions = ver
+            return self
         if self.packed is None or self.packed_versions != ver:
             L = _lib.lib()
             nbytes = L.fvgn_mlp_packed_bytes(self.k_in)
@@ -137,7 +151,7 @@ def mlp_rows_fwd(mlp: MlpRef, x, math_mode=0, out=None):
     if out is None:
         out = torch.empty((rows, mlp.n_out), dtype=torch.float32, device=x.device)
     if math_mode != 0:
-        mlp.ensure_packed()
+        mlp.ensure_packed(math_mode)
     _count(1)
     with _timed("mlp_rows"):
         check(_lib.lib().fvgn_mlp_rows_fwd(C.byref(mlp.struct), _p(x), _ld(x), rows, _p(out), _ld(out), math_mode, _stream()), "mlp_rows_fwd")
@@ -170,7 +184,7 @@ def cell_block_fwd(mlp: MlpRef, x, node_agg, cells_node_T, math_mode=0, x_prime=
     if x_out is None and want_out:
         x_out = torch.empty_like(x)
     if math_mode != 0:
-        mlp.ensure_packed()
+        mlp.ensure_packed(math_mode)
     _count(1)
     with _timed("cell_block"):
         check(_lib.lib().fvgn_cell_block_fwd(C.byref(mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(x_prime), _p(x_out), math_mode,
@@ -190,7 +204,7 @@ def edge_block_fwd(mlp: MlpRef, x_prime, e, neighbour_cell, math_mode=0, e_prime
     if e_out is None and want_out:
         e_out = torch.empty_like(e)
     if math_mode != 0:
-        mlp.ensure_packed()
+        mlp.ensure_packed(math_mode)
     _count(1)
     with _timed("edge_block"):
         check(_lib.lib().fvgn_edge_block_fwd(C.byref(mlp.struct), _p(x_prime), _p(e), _p(neighbour_cell), F, _p(e_prime), _p(e_out), math_mode,

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FVGN_ABI_VERSION 1
+#define FVGN_ABI_VERSION 2
 #define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
 
 #define FVGN_E_BADARG (-1)
@@ -32,7 +32,8 @@ extern "C" {
 /* arithmetic mode of the 128-wide MLP tiles */
 #define FVGN_MATH_FP32_SIMT 0 /* FFMA, strict fp32 (rel 1e-5/step vs the reference)            */
 #define FVGN_MATH_BF16_TC 1   /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM       */
-#define FVGN_MATH_BF16X3_TC 2 /* tcgen05, 3-way bf16 operand split (6 MMAs) ~ fp32 accuracy      */
+#define FVGN_MATH_BF16X3_TC 2 /* tcgen05, exact 3-way bf16 split of every operand, 6 MMAs per product, fp32 epilogue:
+                                 fp32-equivalent (rel 1e-5/step vs the reference) at ~1/10 of the FFMA time     */
 
 #if defined(__GNUC__)
 #define FVGN_API __attribute__((visibility("default")))
@@ -57,12 +58,16 @@ typedef struct {
   const float* ln_w; const float* ln_b; /* [n_out] or NULL */
   int k_in;
   int n_out;
-  const void* packed; /* tensor-core modes only: buffer filled by fvgn_mlp_pack_bf16 for the CURRENT weights; NULL otherwise */
+  const void* packed;    /* FVGN_MATH_BF16_TC only: buffer filled by fvgn_mlp_pack_bf16 for the CURRENT weights; NULL otherwise */
+  const void* packed_x3; /* FVGN_MATH_BF16X3_TC only: buffer filled by fvgn_mlp_pack_bf16x3 for the CURRENT weights; NULL otherwise */
 } fvgn_mlp_t;
 
 /* Tensor-core modes read the weights as pre-swizzled bf16 tiles.  Re-pack whenever the fp32 weights change. */
 FVGN_API size_t fvgn_mlp_packed_bytes(int k_in);
 FVGN_API int fvgn_mlp_pack_bf16(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream);
+/* FVGN_MATH_BF16X3_TC: every weight split exactly into three bf16 terms (w = w0 + w1 + w2), three swizzled tiles per K-tile. */
+FVGN_API size_t fvgn_mlp_packed_x3_bytes(int k_in);
+FVGN_API int fvgn_mlp_pack_bf16x3(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * a1. connectivity + geometry tables  — replaces extract_mesh_state + triangles_to_faces + reorder_face

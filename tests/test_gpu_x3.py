@@ -1,0 +1,103 @@
+"""GPU (B200): the fp32-equivalent tensor-core mode (FVGN_MATH_BF16X3_TC, csrc/mlp_tc3.cu: exact 3-way bf16 operand split, six
+tcgen05 MMAs per product, fp32 epilogue) is held to the SAME bound as the strict FFMA path: relative L2 <= 1e-5 per step against
+the oracle / the reference fixtures (north_star), per op <= 5e-6 against the fp64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fvgn_oracle as O
+from tests import helpers as H
+from tests.test_gpu_parity import fv, dev, _mlp_module, _tiny, _model, _graphs, TOL  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+X3 = 2
+
+
+def _d(sd):
+    return {k: v.double() for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("k_in,n_out,ln,rows", [(2, 128, True, 77), (14, 128, True, 150), (128, 5, False, 150), (128, 128, True, 1),
+                                                (192, 128, True, 64), (384, 128, True, 65), (37, 128, True, 200), (384, 128, True, 40000)])
+def test_x3_mlp_rows(fv, k_in, n_out, ln, rows):
+    m, sd = _mlp_module(fv, k_in, n_out, ln)
+    m.math_mode = "bf16x3"
+    x = torch.randn(rows, k_in, generator=torch.Generator().manual_seed(2))
+    got = m(x.cuda()).cpu()
+    want64 = O.mlp(_d(sd), "", x.double(), layer_norm=ln)
+    err = H.rel_l2(got, want64)
+    print("x3 mlp_rows", k_in, n_out, rows, "rel-L2 vs fp64 %.2e" % err)
+    assert err < 5e-6, err
+    with torch.no_grad():  # re-pack follows weight updates
+        for p_ in m.parameters():
+            p_.mul_(0.5)
+    sd2 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    assert H.rel_l2(m(x.cuda()).cpu(), O.mlp(_d(sd2), "", x.double(), layer_norm=ln)) < 5e-6
+
+
+def test_x3_cell_and_edge_block(fv, golden):
+    g, tab = _tiny(golden)
+    C, F, N = tab["cells_node"].shape[0], tab["face"].shape[1], tab["mesh_pos"].shape[0]
+    gen = torch.Generator().manual_seed(3)
+    x, e = torch.randn(C, 128, generator=gen), torch.randn(F, 128, generator=gen)
+    cb, sdc = _mlp_module(fv, 192, seed=4)
+    eb, sde = _mlp_module(fv, 384, seed=5)
+    fn = torch.as_tensor(np.ascontiguousarray(tab["face"])).long()
+    cnT = torch.as_tensor(tab["cells_node"]).long().T.contiguous()
+    nc = torch.as_tensor(np.ascontiguousarray(tab["neighbour_cell"])).long()
+    xp_ref = O.cell_block(_d({"net." + k: v for k, v in sdc.items()}), "", x.double(), e.double(), fn, cnT, N)
+    ep_ref = O.edge_block(_d({"net." + k: v for k, v in sde.items()}), "", xp_ref, e.double(), nc)
+    ptr, items = fv.ops.build_csr(dev(tab["face"], torch.int32).reshape(-1), N)
+    na = fv.ops.node_aggregate_fwd(e.cuda(), ptr, items, N)
+    xp, xo = fv.ops.cell_block_fwd(cb.mlp_ref(), x.cuda(), na, cnT.to(torch.int32).cuda(), math_mode=X3)
+    assert H.rel_l2(xp.cpu(), xp_ref) < 5e-6 and H.rel_l2(xo.cpu(), x.double() + xp_ref) < 5e-6
+    ep, eo = fv.ops.edge_block_fwd(eb.mlp_ref(), xp, e.cuda(), nc.to(torch.int32).cuda(), math_mode=X3, want_prime=True)
+    assert H.rel_l2(ep.cpu(), ep_ref) < 5e-6 and H.rel_l2(eo.cpu(), e.double() + ep_ref) < 5e-6
+    # in-place residual (red.global.add) variant gives the same bits as the out-of-place one
+    x2, e2 = x.cuda().clone(), e.cuda().clone()
+    xp2, _ = fv.ops.cell_block_fwd(cb.mlp_ref(), x2, na, cnT.to(torch.int32).cuda(), math_mode=X3, x_out=x2)
+    fv.ops.edge_block_fwd(eb.mlp_ref(), xp2, e2, nc.to(torch.int32).cuda(), math_mode=X3, e_out=e2)
+    assert torch.equal(xp2, xp) and torch.equal(x2, xo) and torch.equal(e2, eo)
+
+
+def test_x3_forward_against_reference_fixture_and_rollout(fv, golden):
+    g = golden("fwd_tiny.npz")
+    model = _model(fv, g).set_math_mode("bf16x3")
+    gn, ge, gc = _graphs(fv, g)
+    gn, ge, gc, mi, mb = fv.dataset.valid_datapreprocessing(gn, ge, gc, 0)
+    cell_type, Re, rmp = gc.x[:, 0:1].clone(), gc.x[:, 1:2].clone(), gc.edge_attr[:, 2:5].clone()
+    with torch.no_grad():
+        for step in range(3):
+            cap = {} if step == 0 else None
+            uvp, nuv = model(graph=gc, graph_edge=ge, graph_node=gn, rho=H.RHO, mu=H.MU, dt=H.DT, edge_one_hot=9, cell_one_hot=0, capture=cap)
+            if step == 0:
+                for k in ["enc_x", "enc_e", "x_l0", "e_l0", "x_l1", "e_l1", "x_l14", "e_l14", "decoded", "delta_u"]:
+                    err = H.rel_l2(cap[k].cpu(), g["cap." + k])
+                    assert err < TOL, (k, err)
+            e1, e2 = H.rel_l2(nuv.cpu(), g["roll_uv"][step]), H.rel_l2(uvp.cpu(), g["roll_uvp"][step])
+            print("x3 step", step, "rel-L2 vs the reference fixture: next_uv %.2e uvp %.2e" % (e1, e2))
+            assert e1 < TOL * (step + 1) and e2 < TOL * (step + 1)
+            gc = fv.dataset.create_next_graph(gc, ge, mb, nuv, cell_type, Re, rmp)
+
+
+def test_x3_cylinder_rollout_10_and_determinism(fv, golden):
+    g = golden("fwd_cyl.npz")
+    model = _model(fv, g).set_math_mode("bf16x3")
+
+    def run():
+        gn, ge, gc = _graphs(fv, g)
+        gn, ge, gc, mi, mb = fv.dataset.valid_datapreprocessing(gn, ge, gc, 0)
+        cell_type, Re, rmp = gc.x[:, 0:1].clone(), gc.x[:, 1:2].clone(), gc.edge_attr[:, 2:5].clone()
+        outs = []
+        with torch.no_grad():
+            for step in range(10):
+                uvp, nuv = model(graph=gc, graph_edge=ge, graph_node=gn, rho=H.RHO, mu=H.MU, dt=H.DT, edge_one_hot=9, cell_one_hot=0)
+                outs.append((uvp.clone(), nuv.clone()))
+                gc = fv.dataset.create_next_graph(gc, ge, mb, nuv, cell_type, Re, rmp)
+        return outs
+
+    a, b = run(), run()
+    assert H.rel_l2(a[0][1].cpu(), g["uv_step1"]) < TOL and H.rel_l2(a[0][0].cpu(), g["uvp_step1"]) < TOL
+    assert H.rel_l2(a[9][1].cpu(), g["uv_step10"]) < 10 * TOL and H.rel_l2(a[9][0].cpu(), g["uvp_step10"]) < 10 * TOL
+    for (u1, v1), (u2, v2) in zip(a, b):
+        assert torch.equal(u1, u2) and torch.equal(v1, v2)
