@@ -54,6 +54,16 @@ __device__ __forceinline__ void split3_pair(float a, float b, uint32_t& p0, uint
   p2 = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
 }
 
+// SiLU for the fp32-equivalent mode: x * rcp(1 + 2^(-x log2 e)) with ex2.approx and rcp.approx (each <= 1 ulp-level, 2^-22/2^-23
+// relative): <= ~4e-7 relative overall, well inside this mode's 1e-5 budget.  Both are single MUFU instructions: no slow-path
+// branches (as in expf / IEEE division / __frcp_rn), so the 32 independent elements of a chunk pipeline through the SFU.
+__device__ __forceinline__ float silu_x3(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return v * r;
+}
+
 // 4 consecutive fp32 (columns 4*hl .. 4*hl+3 of a 64-wide K-tile) -> row r of the three swizzled split sub-tiles of one ring slot
 __device__ __forceinline__ void st_slot_f4(unsigned char* slot, int r, int hl, float4 v) {
   const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)hl >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)hl & 1u) * 8u;
@@ -311,8 +321,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           uint32_t p0[16], p1[16], p2[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float u = silu_f(__uint_as_float(r[2 * j]) + bias[32 * c + 2 * j]);
-            const float w = silu_f(__uint_as_float(r[2 * j + 1]) + bias[32 * c + 2 * j + 1]);
+            const float u = silu_x3(__uint_as_float(r[2 * j]) + bias[32 * c + 2 * j]);
+            const float w = silu_x3(__uint_as_float(r[2 * j + 1]) + bias[32 * c + 2 * j + 1]);
             split3_pair(u, w, p0[j], p1[j], p2[j]);
           }
           tmem_st16(t_h + 16 * c, p0);
