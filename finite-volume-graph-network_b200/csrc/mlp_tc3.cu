@@ -42,16 +42,19 @@ struct Params {
   const float* b1; const float* b2; const float* b3; const float* ln_w; const float* ln_b;
 };
 
-// exact 3-way split of two fp32 values into three packed bf16 pairs (a = s0 + s1 + s2 up to 2^-24 relative)
+// exact 3-way split of two fp32 values into three packed bf16 pairs (a = s0 + s1 + s2 up to 2^-24 relative).  Packed
+// cvt.rn.bf16x2.f32 conversions; a bf16 is the top half of its fp32, so widening back is a shift / mask.
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ void split3_pair(float a, float b, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
-  const __nv_bfloat16 a0 = __float2bfloat16_rn(a), b0 = __float2bfloat16_rn(b);
-  const float ra = a - __bfloat162float(a0), rb = b - __bfloat162float(b0);  // exact
-  const __nv_bfloat16 a1 = __float2bfloat16_rn(ra), b1 = __float2bfloat16_rn(rb);
-  const float sa = ra - __bfloat162float(a1), sb = rb - __bfloat162float(b1);  // exact
-  const __nv_bfloat16 a2 = __float2bfloat16_rn(sa), b2 = __float2bfloat16_rn(sb);
-  p0 = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
-  p1 = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
-  p2 = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+  p0 = cvt_bf16x2(a, b);
+  const float ra = a - __uint_as_float(p0 << 16), rb = b - __uint_as_float(p0 & 0xffff0000u);  // exact
+  p1 = cvt_bf16x2(ra, rb);
+  const float sa = ra - __uint_as_float(p1 << 16), sb = rb - __uint_as_float(p1 & 0xffff0000u);  // exact
+  p2 = cvt_bf16x2(sa, sb);
 }
 
 // SiLU for the fp32-equivalent mode: x * rcp(1 + 2^(-x log2 e)) with ex2.approx and rcp.approx (each <= 1 ulp-level, 2^-22/2^-23
@@ -203,8 +206,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       const uint32_t slot = (uint32_t)s % ARING;
       if (s >= ARING) mbar_wait(BAR(B_AEMPTY + slot), (((uint32_t)s / ARING) - 1) & 1, 1);
       unsigned char* dst = sA + slot * SLOT_BYTES;
+      if (!(p.dbg & 64)) {
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) st_slot_f4(dst, hw + NHW * i, hl, v[i]);
+        for (int i = 0; i < RPT; ++i) st_slot_f4(dst, hw + NHW * i, hl, v[i]);
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_AFULL + slot));
@@ -224,8 +229,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       auto put = [&](int step) {
         const uint32_t slot = wl % WRING;
         if (wl >= WRING) mbar_wait(BAR(B_WEMPTY + slot), ((wl / WRING) - 1) & 1, 2);
-        mbar_arrive_expect_tx(BAR(B_WFULL + slot), SLOT_BYTES);
-        bulk_g2s(smem_u32(sW + slot * SLOT_BYTES), p.packed + (size_t)step * SLOT_BYTES, SLOT_BYTES, BAR(B_WFULL + slot));
+        const uint32_t nbytes = (p.dbg & 16) ? TILE_BYTES : SLOT_BYTES;  // timing experiment: a third of the weight bytes
+        mbar_arrive_expect_tx(BAR(B_WFULL + slot), nbytes);
+        bulk_g2s(smem_u32(sW + slot * SLOT_BYTES), p.packed + (size_t)step * SLOT_BYTES, nbytes, BAR(B_WFULL + slot));
         ++wl;
       };
       for (int t = 0; t < kt1; ++t) put(t);
@@ -329,10 +335,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             for (int j = 0; j < 16; ++j) { p0[j] = r[j]; p1[j] = r[j + 16]; p2[j] = 0; }
           } else
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float u = silu_x3(__uint_as_float(r[2 * j]) + bias[32 * c + 2 * j]);
-            const float w = silu_x3(__uint_as_float(r[2 * j + 1]) + bias[32 * c + 2 * j + 1]);
-            split3_pair(u, w, p0[j], p1[j], p2[j]);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + 32 * c + 4 * j4);
+            split3_pair(silu_x3(__uint_as_float(r[4 * j4]) + b.x), silu_x3(__uint_as_float(r[4 * j4 + 1]) + b.y), p0[2 * j4], p1[2 * j4], p2[2 * j4]);
+            split3_pair(silu_x3(__uint_as_float(r[4 * j4 + 2]) + b.z), silu_x3(__uint_as_float(r[4 * j4 + 3]) + b.w), p0[2 * j4 + 1], p1[2 * j4 + 1],
+                        p2[2 * j4 + 1]);
           }
           tmem_st16(t_h + 16 * c, p0);
           tmem_st16(t_h + 64 + 16 * c, p1);
@@ -346,14 +353,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       mbar_wait(dfull, (use0 + 2u) & 1, 9);
       tc_fence_after();
       float mean = 0.f, rstd = 1.f;
-      if (has_ln) {  // two-pass LayerNorm statistics, as torch
+      if (has_ln && !(p.dbg & 32)) {  // two-pass LayerNorm statistics, as torch
         float s = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           tmem_ld32_issue(t_acc + 32 * c, r);
           tmem_ld_wait(r);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += __uint_as_float(r[j]) + b3[32 * c + j];
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(b3 + 32 * c + 4 * j4);
+            s += __uint_as_float(r[4 * j4]) + b.x; s += __uint_as_float(r[4 * j4 + 1]) + b.y;
+            s += __uint_as_float(r[4 * j4 + 2]) + b.z; s += __uint_as_float(r[4 * j4 + 3]) + b.w;
+          }
         }
         mean = s * (1.0f / 128.0f);
         float qv = 0.f;
@@ -362,7 +373,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           tmem_ld32_issue(t_acc + 32 * c, r);
           tmem_ld_wait(r);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { const float d = (__uint_as_float(r[j]) + b3[32 * c + j]) - mean; qv = fmaf(d, d, qv); }
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(b3 + 32 * c + 4 * j4);
+            float d;
+            d = (__uint_as_float(r[4 * j4]) + b.x) - mean; qv = fmaf(d, d, qv);
+            d = (__uint_as_float(r[4 * j4 + 1]) + b.y) - mean; qv = fmaf(d, d, qv);
+            d = (__uint_as_float(r[4 * j4 + 2]) + b.z) - mean; qv = fmaf(d, d, qv);
+            d = (__uint_as_float(r[4 * j4 + 3]) + b.w) - mean; qv = fmaf(d, d, qv);
+          }
         }
         rstd = 1.0f / sqrtf(qv * (1.0f / 128.0f) + 1e-5f);
       }
@@ -377,11 +395,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           if (lane == 0) mbar_arrive(BAR(B_DFREE + acc));
         }
         float* v = reinterpret_cast<float*>(r);
+        if (p.dbg & 32) continue;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float y = v[j] + b3[32 * c + j];
-          if (has_ln) y = (y - mean) * rstd * gw[32 * c + j] + gb[32 * c + j];
-          v[j] = y;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b = *reinterpret_cast<const float4*>(b3 + 32 * c + 4 * j4);
+          float y0 = v[4 * j4] + b.x, y1 = v[4 * j4 + 1] + b.y, y2 = v[4 * j4 + 2] + b.z, y3 = v[4 * j4 + 3] + b.w;
+          if (has_ln) {
+            const float4 w = *reinterpret_cast<const float4*>(gw + 32 * c + 4 * j4);
+            const float4 o = *reinterpret_cast<const float4*>(gb + 32 * c + 4 * j4);
+            y0 = (y0 - mean) * rstd * w.x + o.x; y1 = (y1 - mean) * rstd * w.y + o.y;
+            y2 = (y2 - mean) * rstd * w.z + o.z; y3 = (y3 - mean) * rstd * w.w + o.w;
+          }
+          v[4 * j4] = y0; v[4 * j4 + 1] = y1; v[4 * j4 + 2] = y2; v[4 * j4 + 3] = y3;
         }
         if (staged) {
 #pragma unroll
