@@ -23,9 +23,9 @@ namespace x3 {
 constexpr int TM = 128, HIDN = 128, KTILE = 64;
 constexpr int TILE_BYTES = TC_TILE_BYTES, SLOT_BYTES = 3 * TILE_BYTES;  // one K-tile step = three split sub-tiles
 constexpr int ARING = 2, WRING = 2;
-constexpr int NEPI = 128, NPROD = 256, NPW = NPROD / 32;
+constexpr int NEPI = 256, NPROD = 256, NPW = NPROD / 32;  // epilogue: 8 warps = two threads (column halves) per tile row
 constexpr int WARP_PROD0 = NEPI / 32, WARP_MMA = WARP_PROD0 + NPW, WARP_LOAD = WARP_MMA + 1;
-constexpr int NTHREADS = (WARP_LOAD + 1) * 32;  // 448
+constexpr int NTHREADS = (WARP_LOAD + 1) * 32;  // 576
 constexpr int RPT = TM / (NPROD / 16);          // 8 rows per producer thread per K-tile
 constexpr uint32_t TMEM_COLS = 512;             // acc0 [0,128) | acc1 [128,256) | H split 0 [256,320) | 1 [320,384) | 2 [384,448)
 constexpr uint32_t TMEM_H0 = 256;
@@ -78,16 +78,39 @@ __device__ __forceinline__ void st_slot_f4(unsigned char* slot, int r, int hl, f
   *reinterpret_cast<uint2*>(slot + 2 * TILE_BYTES + off) = q2;
 }
 
+// 32 lanes x 16 consecutive 32-bit TMEM columns (asynchronous: valid after tmem_ld16_wait)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 struct SmemLayout {
-  uint32_t a_off, w_off, stage_off, par_off, bar_off, total;
+  uint32_t a_off, w_off, stage_off, par_off, red_off, bar_off, total;
 };
 __host__ __device__ inline SmemLayout smem_layout() {
   SmemLayout L;
   uint32_t o = 0;
   L.a_off = o; o += ARING * SLOT_BYTES;   // 96 KB
   L.w_off = o; o += WRING * SLOT_BYTES;   // 96 KB
-  L.stage_off = o; o += 4 * 4096;         // 16 KB per-epilogue-warp output staging
+  L.stage_off = o; o += 8 * 2048;         // 16 KB per-epilogue-warp output staging [32 rows][16 fp32]
   L.par_off = o; o += 5 * 128 * 4;
+  L.red_off = o; o += 2 * 2 * 128 * 4;    // LayerNorm exchange between the two column halves of a row
   L.bar_off = o; o += 256;
   L.total = o;
   return L;
@@ -119,8 +142,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     if (smem_u32(smem) & 1023u) { printf("fvgn mlp_tc3: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < ARING; ++i) { mbar_init(BAR(B_AFULL + i), NPW); mbar_init(BAR(B_AEMPTY + i), 1); }
     for (int i = 0; i < WRING; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(BAR(B_DFULL + a), 1); mbar_init(BAR(B_DFREE + a), 4); }
-    mbar_init(BAR(B_HREADY), 4);
+    for (int a = 0; a < 2; ++a) { mbar_init(BAR(B_DFULL + a), 1); mbar_init(BAR(B_DFREE + a), 8); }
+    mbar_init(BAR(B_HREADY), 8);
     fence_mbar_init();
   }
   if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -301,12 +324,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     }
     __syncwarp();
   } else {
-    // ================================================================= epilogue warps 0-3: one thread per row
-    const int q = warp & 3;
+    // ================================================================= epilogue warps 0-7: two threads per row (column halves),
+    // 16-column sub-chunks (register budget 96: 576 threads)
+    const int q = warp & 3, h = warp >> 2;  // TMEM lane quadrant = warp id % 4; column half
     const int erow = 32 * q + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
     const uint32_t t_h = t_lane + TMEM_H0;
-    unsigned char* stage = smem + L.stage_off + warp * 4096;
+    unsigned char* stage = smem + L.stage_off + warp * 2048;  // [32 rows][64 B], 16-byte chunks XOR-swizzled by ((row >> 1) & 3)
+    float* sRed = reinterpret_cast<float*>(smem + L.red_off);
     const bool has_ln = (p.ln_w != nullptr);
     const bool staged = (MODE != TC_ROWS) || (p.n_out == HIDN && (p.ld_out & 3) == 0);
     const float* b3 = sPar + 2 * 128;
@@ -319,31 +344,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       const uint32_t t_acc = t_lane + 128u * (uint32_t)acc;
       const uint32_t dfull = BAR(B_DFULL + acc);
       const uint32_t use0 = 3u * (uint32_t)(jl >> 1);
-      uint32_t r[32];
+      uint32_t r[16];
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
         mbar_wait(dfull, (use0 + (uint32_t)layer) & 1, 8);
         tc_fence_after();
         const float* bias = sPar + layer * 128;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld32_issue(t_acc + 32 * c, r);
-          tmem_ld_wait(r);
-          uint32_t p0[16], p1[16], p2[16];
+        for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {  // 16-column sub-chunk index 0..7
+          tmem_ld16_issue(t_acc + 16 * sc, r);
+          tmem_ld16_wait(r);
+          uint32_t p0[8], p1[8], p2[8];
           if (p.dbg & 2) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { p0[j] = r[j]; p1[j] = r[j + 16]; p2[j] = 0; }
+            for (int j = 0; j < 8; ++j) { p0[j] = r[j]; p1[j] = r[j + 8]; p2[j] = 0; }
           } else
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + 32 * c + 4 * j4);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + 16 * sc + 4 * j4);
             split3_pair(silu_x3(__uint_as_float(r[4 * j4]) + b.x), silu_x3(__uint_as_float(r[4 * j4 + 1]) + b.y), p0[2 * j4], p1[2 * j4], p2[2 * j4]);
             split3_pair(silu_x3(__uint_as_float(r[4 * j4 + 2]) + b.z), silu_x3(__uint_as_float(r[4 * j4 + 3]) + b.w), p0[2 * j4 + 1], p1[2 * j4 + 1],
                         p2[2 * j4 + 1]);
           }
-          tmem_st16(t_h + 16 * c, p0);
-          tmem_st16(t_h + 64 + 16 * c, p1);
-          tmem_st16(t_h + 128 + 16 * c, p2);
+          tmem_st8(t_h + 8 * sc, p0);
+          tmem_st8(t_h + 64 + 8 * sc, p1);
+          tmem_st8(t_h + 128 + 8 * sc, p2);
         }
         tmem_wait_st();
         tc_fence_before();
@@ -353,28 +378,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       mbar_wait(dfull, (use0 + 2u) & 1, 9);
       tc_fence_after();
       float mean = 0.f, rstd = 1.f;
-      if (has_ln && !(p.dbg & 32)) {  // two-pass LayerNorm statistics, as torch
+      if (has_ln && !(p.dbg & 32)) {  // two-pass LayerNorm statistics, as torch; the two column halves exchange partial sums
         float s = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld32_issue(t_acc + 32 * c, r);
-          tmem_ld_wait(r);
+        for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
+          tmem_ld16_issue(t_acc + 16 * sc, r);
+          tmem_ld16_wait(r);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = *reinterpret_cast<const float4*>(b3 + 32 * c + 4 * j4);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
             s += __uint_as_float(r[4 * j4]) + b.x; s += __uint_as_float(r[4 * j4 + 1]) + b.y;
             s += __uint_as_float(r[4 * j4 + 2]) + b.z; s += __uint_as_float(r[4 * j4 + 3]) + b.w;
           }
         }
-        mean = s * (1.0f / 128.0f);
+        sRed[h * 128 + erow] = s;
+        named_bar_sync(1, NEPI);
+        mean = (sRed[erow] + sRed[128 + erow]) * (1.0f / 128.0f);
         float qv = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld32_issue(t_acc + 32 * c, r);
-          tmem_ld_wait(r);
+        for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
+          tmem_ld16_issue(t_acc + 16 * sc, r);
+          tmem_ld16_wait(r);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = *reinterpret_cast<const float4*>(b3 + 32 * c + 4 * j4);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
             float d;
             d = (__uint_as_float(r[4 * j4]) + b.x) - mean; qv = fmaf(d, d, qv);
             d = (__uint_as_float(r[4 * j4 + 1]) + b.y) - mean; qv = fmaf(d, d, qv);
@@ -382,14 +409,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             d = (__uint_as_float(r[4 * j4 + 3]) + b.w) - mean; qv = fmaf(d, d, qv);
           }
         }
-        rstd = 1.0f / sqrtf(qv * (1.0f / 128.0f) + 1e-5f);
+        sRed[256 + h * 128 + erow] = qv;
+        named_bar_sync(1, NEPI);
+        rstd = 1.0f / sqrtf((sRed[256 + erow] + sRed[256 + 128 + erow]) * (1.0f / 128.0f) + 1e-5f);
       }
       const float* res = (MODE == TC_CELL) ? p.src0 : p.src1;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld32_issue(t_acc + 32 * c, r);
-        tmem_ld_wait(r);
-        if (c == 3) {
+      for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
+        tmem_ld16_issue(t_acc + 16 * sc, r);
+        tmem_ld16_wait(r);
+        if (sc == 4 * h + 3) {  // this warp's last TMEM read of the tile
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_DFREE + acc));
@@ -397,12 +426,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         float* v = reinterpret_cast<float*>(r);
         if (p.dbg & 32) continue;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b = *reinterpret_cast<const float4*>(b3 + 32 * c + 4 * j4);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
           float y0 = v[4 * j4] + b.x, y1 = v[4 * j4 + 1] + b.y, y2 = v[4 * j4 + 2] + b.z, y3 = v[4 * j4 + 3] + b.w;
           if (has_ln) {
-            const float4 w = *reinterpret_cast<const float4*>(gw + 32 * c + 4 * j4);
-            const float4 o = *reinterpret_cast<const float4*>(gb + 32 * c + 4 * j4);
+            const float4 w = *reinterpret_cast<const float4*>(gw + 16 * sc + 4 * j4);
+            const float4 o = *reinterpret_cast<const float4*>(gb + 16 * sc + 4 * j4);
             y0 = (y0 - mean) * rstd * w.x + o.x; y1 = (y1 - mean) * rstd * w.y + o.y;
             y2 = (y2 - mean) * rstd * w.z + o.z; y3 = (y3 - mean) * rstd * w.w + o.w;
           }
@@ -410,47 +439,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         }
         if (staged) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<float4*>(stage + (uint32_t)lane * 128u + (((uint32_t)k ^ ((uint32_t)lane & 7u)) << 4)) =
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(stage + (uint32_t)lane * 64u + (((uint32_t)k ^ (((uint32_t)lane >> 1) & 3u)) << 4)) =
                 make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           __syncwarp();
-          const int rr0 = lane >> 3, cp = lane & 7;
-          if (MODE == TC_ROWS) {
+          // coalesced read-out: 4 lanes per row (64 contiguous bytes), 8 rows per warp access
+          const int rr0 = lane >> 2, cp = lane & 3;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = 4 * it + rr0, grow = row0 + 32 * q + rr;
-              if (grow < p.rows)
-                *reinterpret_cast<float4*>(p.out0 + (size_t)grow * p.ld_out + 32 * c + 4 * (cp ^ (rr & 7))) =
-                    *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 128u + ((uint32_t)cp << 4));
-            }
-          } else if (RED) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = 4 * it + rr0, grow = row0 + 32 * q + rr;
-              if (grow < p.rows) {
-                const float4 y = *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 128u + ((uint32_t)cp << 4));
-                const size_t off = (size_t)grow * 128 + 32 * c + 4 * (cp ^ (rr & 7));
+          for (int it = 0; it < 4; ++it) {
+            const int rr = 8 * it + rr0, grow = row0 + 32 * q + rr;
+            const float4 y = *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 64u + ((uint32_t)cp << 4));
+            const int col = 16 * sc + 4 * (cp ^ ((rr >> 1) & 3));
+            if (grow < p.rows) {
+              if (MODE == TC_ROWS) {
+                *reinterpret_cast<float4*>(p.out0 + (size_t)grow * p.ld_out + col) = y;
+              } else {
+                const size_t off = (size_t)grow * 128 + col;
                 if (p.out0) *reinterpret_cast<float4*>(p.out0 + off) = y;
-                red_add_f4(p.out1 + off, y);
-              }
-            }
-          } else {
-            float4 rv[8];
-            if (p.out1) {
-#pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int rr = 4 * it + rr0, grow = min(row0 + 32 * q + rr, p.rows - 1);
-                rv[it] = *reinterpret_cast<const float4*>(res + (size_t)grow * 128 + 32 * c + 4 * (cp ^ (rr & 7)));
-              }
-            }
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = 4 * it + rr0, grow = row0 + 32 * q + rr;
-              if (grow < p.rows) {
-                const float4 y = *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 128u + ((uint32_t)cp << 4));
-                const size_t off = (size_t)grow * 128 + 32 * c + 4 * (cp ^ (rr & 7));
-                if (p.out0) *reinterpret_cast<float4*>(p.out0 + off) = y;
-                if (p.out1) *reinterpret_cast<float4*>(p.out1 + off) = make_float4(rv[it].x + y.x, rv[it].y + y.y, rv[it].z + y.z, rv[it].w + y.w);
+                if (RED) red_add_f4(p.out1 + off, y);
+                else if (p.out1) {
+                  const float4 rv = *reinterpret_cast<const float4*>(res + off);
+                  *reinterpret_cast<float4*>(p.out1 + off) = make_float4(rv.x + y.x, rv.y + y.y, rv.z + y.z, rv.w + y.w);
+                }
               }
             }
           }
@@ -459,8 +469,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           const int grow = row0 + erow;
           if (grow < p.rows) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = 32 * c + j;
+            for (int j = 0; j < 16; ++j) {
+              const int col = 16 * sc + j;
               if (col < p.n_out) p.out0[(size_t)grow * p.ld_out + col] = v[j];
             }
           }
