@@ -191,6 +191,45 @@ def measure_forward(args, workload, math, steps, rank, local_rank, dev, dist):
                 kern=kern, clocks=clk.summary(), meshes=meshes, steps=steps)
 
 
+def rollout_config0(args, dev):
+    """BASELINE configs[0]: 1-step forward + 10-step rollout, batch 1, one cylinder_flow-shaped mesh — the reference's own CPU-runnable
+    case.  Eager loop vs the CUDA-graph rollout (fvgn_b200.GraphedRollout: zero host work per step)."""
+    import fvgn_b200 as fv
+
+    m = fv.synthetic.make("cyl", seed=0, T=3)
+    gn, ge, gc, mi, mb = device_batch([m], dev)
+    C = gc.x.shape[0]
+    torch.manual_seed(0)
+    model = fv.FVGN(device="cpu", params=params()).to(dev).eval().set_math_mode(args.math)
+    state = fv.dataset.RolloutState(gc, ge)
+
+    def eager(n):
+        for _ in range(n):
+            uvp, nuv = model(graph=gc, graph_edge=ge, graph_node=gn, rho=RHO, mu=MU, dt=DT, edge_one_hot=9, cell_one_hot=0)
+            state.advance_(gc, nuv)
+
+    def timed(fn, reps=5):
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)) * 1e3
+
+    with torch.no_grad():
+        eager(3)
+        e1, e10 = timed(lambda: eager(1)), timed(lambda: eager(10))
+        gn2, ge2, gc2, _, _ = device_batch([m], dev)
+        roll = fv.GraphedRollout(model, gn2, ge2, gc2, RHO, MU, DT)
+        roll.run(3)
+        g1, g10 = timed(lambda: roll.run(1)), timed(lambda: roll.run(10))
+    return {"workload": "1 cylinder_flow-shaped mesh, batch 1 (BASELINE configs[0])", "cells": C, "math": args.math,
+            "eager_ms": {"1_step": e1, "10_step_rollout": e10}, "cuda_graph_ms": {"1_step": g1, "10_step_rollout": g10},
+            "cell_updates_per_sec_cuda_graph": C * 10 / (g10 * 1e-3), "timing": "host wall clock around a synchronised call, median of 5"}
+
+
 def roofline_of(m, math, workload):
     """roofline object of the dominant kernel (the fused EdgeBlock kernel) from a measure_forward() result"""
     peaks = {}
@@ -283,6 +322,8 @@ def native(args, rank, world, local_rank):
                                           "ms_per_step": fm["ms"] / fm["steps"], "steps": fm["steps"], "dtype": DTYPES["fp32"],
                                           "note": "the same workload on the strict FFMA kernels (bit-level evaluation order of the reference)"}
         del fm
+    if rank == 0 and not args.no_config0:
+        result["rollout_config0"] = rollout_config0(args, dev)
     train = None
     if not args.no_training:
         torch.cuda.empty_cache()
@@ -479,6 +520,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-training", action="store_true", help="skip the training graphs/s leg")
     ap.add_argument("--no-strict-leg", action="store_true", help="skip the strict-FFMA comparison leg")
+    ap.add_argument("--no-config0", action="store_true", help="skip the batch-1 rollout latency leg (configs[0])")
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--sweep", default="mesh1m:bf16", help="<workload>:<math> of the kernel roofline sweep leg, or 'none'")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
