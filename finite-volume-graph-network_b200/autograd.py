@@ -36,17 +36,23 @@ class NetFunction(torch.autograd.Function):
         # forward arithmetic: strict FFMA ("fp32") or the fp32-equivalent tensor-core mode ("bf16x3"); the backward recomputes each
         # tile from the saved layer inputs in FFMA either way
         mm = {"fp32": 0, "bf16x3": 2}[model.math_mode]
-        x = ops.mlp_rows_fwd(enc_c.mlp_ref(), cell_in, mm)
-        e = ops.mlp_rows_fwd(enc_e.mlp_ref(), edge_in, mm)
+        # bf16x3: the forward also stores every MLP's pre-activations (z1 | z2 | z3, 1.5 KB per row): the backward reads them
+        # instead of recomputing the forward in its tiles (a third of its FLOPs)
+        zbuf = (lambda rows: torch.empty((rows, 384), dtype=torch.float32, device=cell_in.device)) if mm == 2 else (lambda rows: None)
+        z_enc_c, z_enc_e = zbuf(topo.C), zbuf(topo.F)
+        x = ops.mlp_rows_fwd(enc_c.mlp_ref(), cell_in, mm, z_save=z_enc_c)
+        e = ops.mlp_rows_fwd(enc_e.mlp_ref(), edge_in, mm, z_save=z_enc_e)
         saved = []
         for blk in epd.processer_list:
             cb, eb = blk.cb_module.net, blk.eb_module.net
             na = ops.node_aggregate_fwd(e, topo.node_ptr, topo.node_items, topo.N)
-            xp, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, na, topo.cnT, mm)
-            _, e_new = ops.edge_block_fwd(eb.mlp_ref(), xp, e, topo.nc, mm)
-            saved.append((x, e, xp, na))
+            zc, ze = zbuf(topo.C), zbuf(topo.F)
+            xp, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, na, topo.cnT, mm, z_save=zc)
+            _, e_new = ops.edge_block_fwd(eb.mlp_ref(), xp, e, topo.nc, mm, z_save=ze)
+            saved.append((x, e, xp, na, zc, ze))
             x, e = x_new, e_new
-        decoded = ops.mlp_rows_fwd(epd.decoder.edge_decode_module.mlp_ref(), e, mm)
+        z_dec = zbuf(topo.F)
+        decoded = ops.mlp_rows_fwd(epd.decoder.edge_decode_module.mlp_ref(), e, mm, z_save=z_dec)
         bn = model._grid_feature_normalizer
         use_batch = model.training or not bn.track_running_stats
         if use_batch and parallel.is_distributed():
@@ -67,6 +73,7 @@ class NetFunction(torch.autograd.Function):
         # detached aliases: storing the OUTPUT tensors themselves on ctx would close a reference cycle (output -> grad_fn -> ctx ->
         # output) that only the cyclic GC can free, i.e. ~2 GB per layer of saved latents would pile up between collections
         ctx.aux = (cell_in.detach(), edge_in.detach(), e, decoded.detach(), face_area.detach(), raw, stats, unv.detach())
+        ctx.zs = (z_enc_c, z_enc_e, z_dec)
         ctx.mark_non_differentiable(face_area)
         return decoded, delta_u, face_area
 
@@ -76,6 +83,7 @@ class NetFunction(torch.autograd.Function):
         epd = model.model
         cell_in, edge_in, e_final, decoded, face_area, raw, stats, unv = ctx.aux
         saved_layers, ctx.saved, ctx.aux = ctx.saved, None, None  # release the saved latents as the backward sweep consumes them
+        (z_enc_c, z_enc_e, z_dec), ctx.zs = ctx.zs, None
         bt = topo.backward_tables()
         dev = decoded.device
         g_dec = (g_decoded.contiguous().clone() if g_decoded is not None else torch.zeros_like(decoded))
@@ -87,23 +95,23 @@ class NetFunction(torch.autograd.Function):
         g_bn = ops.face_area_bn_bwd(g_fa, raw, stats)
         grads = {}
         dec = epd.decoder.edge_decode_module
-        grads[id(dec)], g_e = ops.mlp_rows_bwd(dec.mlp_ref(), e_final, g_dec, want_d_in=True)
+        grads[id(dec)], g_e = ops.mlp_rows_bwd(dec.mlp_ref(), e_final, g_dec, want_d_in=True, z_saved=z_dec)
         g_x = None  # the last layer's cell latent feeds nothing but its own EdgeBlock
         cptr, citems = bt["cell_from_face"]
         nptr, nitems = bt["node_from_cell"]
         for blk in reversed(epd.processer_list):
-            x_in, e_in, xp, na = saved_layers.pop()
+            x_in, e_in, xp, na, zc, ze = saved_layers.pop()
             cb, eb = blk.cb_module.net, blk.eb_module.net
-            grads[id(eb)], dA_e = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e)
+            grads[id(eb)], dA_e = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e, z_saved=ze)
             # d x' = residual path + transpose of the x'[s], x'[r] gathers (cell <- face segment sum)
             g_xp = ops.segment_sum_rows(dA_e, topo.F, 0, 128, 128, cptr, citems, topo.C, base=g_x, scale=1.0)
-            grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, topo.cnT, g_xp, d_x_base=g_x)
+            grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, topo.cnT, g_xp, d_x_base=g_x, z_saved=zc)
             # transposes of the twice-message aggregation: cell -> node (x 1/3), node -> face halves
             g_na = ops.segment_sum_rows(dA_c, topo.C, 128, 0, 64, nptr, nitems, topo.N, base=None, scale=1.0 / 3.0)
             g_e = ops.edge_grad_combine(g_e, dA_e, g_na, topo.fn)
             g_x = dA_c[:, 0:128]
-        grads[id(epd.encoder.cb_encoder)], _ = ops.mlp_rows_bwd(epd.encoder.cb_encoder.mlp_ref(), cell_in, g_x)
-        grads[id(epd.encoder.eb_encoder)], _ = ops.mlp_rows_bwd(epd.encoder.eb_encoder.mlp_ref(), edge_in, g_e)
+        grads[id(epd.encoder.cb_encoder)], _ = ops.mlp_rows_bwd(epd.encoder.cb_encoder.mlp_ref(), cell_in, g_x, z_saved=z_enc_c)
+        grads[id(epd.encoder.eb_encoder)], _ = ops.mlp_rows_bwd(epd.encoder.eb_encoder.mlp_ref(), edge_in, g_e, z_saved=z_enc_e)
         flat = [g for m in network_mlps(model) for g in grads[id(m)]]
         flat += [g_bn[0:1], g_bn[1:2]]
         return (None,) * 9 + tuple(flat)

@@ -288,6 +288,34 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_simt_kernel(const BwdParams p) 
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int row0 = tile * BM;
     float acc[4][8];
+    const float* zs = p.mlp.z_save;
+    if (zs != nullptr) {
+      // ---------------------------------------------------------------- saved pre-activations (z1 | z2 | z3) instead of the recompute
+      __syncthreads();  // the previous tile's last products may still be reading A1 / T1
+      float v[4][8], hh[4][8];
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int g = min(row0 + tr * 4 + i, p.rows - 1);
+          const float4 a = ldg4(zs + (size_t)g * 384 + 128 * l + tc * 4), b = ldg4(zs + (size_t)g * 384 + 128 * l + 64 + tc * 4);
+          v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+        }
+        if (l < 2) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hh[i][j] = silu_f(v[i][j]);
+          st_tile(l == 0 ? A1 : A2, v, tid);
+          st_tile(l == 0 ? T1 : T2, hh, tid);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = v[i][j];  // z3 already holds the bias
+        }
+      }
+    } else {
     // ------------------------------------------------------------------ forward recompute
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -318,6 +346,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_simt_kernel(const BwdParams p) 
       st_tile(T2, hh, tid);
     }
     gemm_nt<HLD>(T2, p.mlp.w3, 128, 128, n_out, Wt, acc, tid);
+    }
     // ------------------------------------------------------------------ dOut, LayerNorm backward -> dy (registers)
     float dy[4][8];
 #pragma unroll
@@ -332,7 +361,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_simt_kernel(const BwdParams p) 
       for (int i = 0; i < 4; ++i) {
         float v[8], s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { v[j] = acc[i][j] + __ldg(p.mlp.b3 + col[j]); }
+        for (int j = 0; j < 8; ++j) { v[j] = (zs != nullptr) ? acc[i][j] : acc[i][j] + __ldg(p.mlp.b3 + col[j]); }
         s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
 #pragma unroll
         for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);

@@ -38,6 +38,7 @@ struct Params {
   const float* src0; const float* src1; const int32_t* idx;  // CELL: x, node_agg, cells_node_T ; EDGE: x', e, neighbour_cell
   float* out0; int ld_out;
   float* out1;
+  float* zsave;                 // optional [rows, 384]: pre-activations (z1 | z2 | z3) for the backward
   const unsigned char* packed;  // [kt1 + 4] steps x [3 splits] x 16 KB
   const float* b1; const float* b2; const float* b3; const float* ln_w; const float* ln_b;
 };
@@ -337,6 +338,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     const float* b3 = sPar + 2 * 128;
     const float* gw = sPar + 3 * 128;
     const float* gb = sPar + 4 * 128;
+    // 16 fp32 of this thread's row -> the warp's swizzled staging tile -> 64-byte row segments of a [rows, ld] matrix at column col0
+    auto store_rows16 = [&](const float* v, float* dst, int ld, int col0, int row_base) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4*>(stage + (uint32_t)lane * 64u + (((uint32_t)k ^ (((uint32_t)lane >> 1) & 3u)) << 4)) =
+            make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      __syncwarp();
+      const int rr0 = lane >> 2, cp = lane & 3;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = 8 * it + rr0, grow = row_base + rr;
+        if (grow < p.rows)
+          *reinterpret_cast<float4*>(dst + (size_t)grow * ld + col0 + 4 * (cp ^ ((rr >> 1) & 3))) =
+              *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 64u + ((uint32_t)cp << 4));
+      }
+      __syncwarp();
+    };
 #pragma unroll 1
     for (int jl = 0; jl < n_local; ++jl) {
       const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
@@ -362,10 +380,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(bias + 16 * sc + 4 * j4);
-            split3_pair(silu_x3(__uint_as_float(r[4 * j4]) + b.x), silu_x3(__uint_as_float(r[4 * j4 + 1]) + b.y), p0[2 * j4], p1[2 * j4], p2[2 * j4]);
-            split3_pair(silu_x3(__uint_as_float(r[4 * j4 + 2]) + b.z), silu_x3(__uint_as_float(r[4 * j4 + 3]) + b.w), p0[2 * j4 + 1], p1[2 * j4 + 1],
-                        p2[2 * j4 + 1]);
+            const float z0 = __uint_as_float(r[4 * j4]) + b.x, z1 = __uint_as_float(r[4 * j4 + 1]) + b.y;
+            const float z2 = __uint_as_float(r[4 * j4 + 2]) + b.z, z3 = __uint_as_float(r[4 * j4 + 3]) + b.w;
+            r[4 * j4] = __float_as_uint(z0); r[4 * j4 + 1] = __float_as_uint(z1); r[4 * j4 + 2] = __float_as_uint(z2); r[4 * j4 + 3] = __float_as_uint(z3);
+            split3_pair(silu_x3(z0), silu_x3(z1), p0[2 * j4], p1[2 * j4], p2[2 * j4]);
+            split3_pair(silu_x3(z2), silu_x3(z3), p0[2 * j4 + 1], p1[2 * j4 + 1], p2[2 * j4 + 1]);
           }
+          if (p.zsave) store_rows16(reinterpret_cast<const float*>(r), p.zsave, 384, 128 * layer + 16 * sc, row0 + 32 * q);
           tmem_st8(t_h + 8 * sc, p0);
           tmem_st8(t_h + 64 + 8 * sc, p1);
           tmem_st8(t_h + 128 + 8 * sc, p2);
@@ -425,9 +446,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         }
         float* v = reinterpret_cast<float*>(r);
         if (p.dbg & 32) continue;
+        if (p.zsave) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
+            v[4 * j4] += b.x; v[4 * j4 + 1] += b.y; v[4 * j4 + 2] += b.z; v[4 * j4 + 3] += b.w;
+          }
+          store_rows16(v, p.zsave, 384, 256 + 16 * sc, row0 + 32 * q);
+        }
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
+          const float4 b = p.zsave ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
           float y0 = v[4 * j4] + b.x, y1 = v[4 * j4 + 1] + b.y, y2 = v[4 * j4 + 2] + b.z, y3 = v[4 * j4 + 3] + b.w;
           if (has_ln) {
             const float4 w = *reinterpret_cast<const float4*>(gw + 16 * sc + 4 * j4);
@@ -539,6 +568,8 @@ static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t
   p.packed = reinterpret_cast<const unsigned char*>(m->packed_x3);
   p.b1 = m->b1; p.b2 = m->b2; p.b3 = m->b3; p.ln_w = m->ln_w; p.ln_b = m->ln_b;
   p.k_in = m->k_in; p.n_out = m->n_out;
+  p.zsave = m->z_save;
+  if (p.zsave) FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(p.zsave) & 15) == 0, "z_save must be 16B aligned");
   p.kt1 = kt_of(m->k_in);
   p.ntiles = cdiv(p.rows, TM);
   const SmemLayout L = smem_layout();

@@ -110,7 +110,7 @@ class MlpRef:
         self.k_in, self.n_out = int(w1.shape[1]), int(w3.shape[0])
         self.struct = MlpT(w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(),
                            ln_w.data_ptr() if ln_w is not None else None, ln_b.data_ptr() if ln_b is not None else None,
-                           self.k_in, self.n_out, None, None)
+                           self.k_in, self.n_out, None, None, None)
         self.packed = None
         self.packed_versions = None
         self.packed3 = None
@@ -143,7 +143,26 @@ class MlpRef:
         return self
 
 
-def mlp_rows_fwd(mlp: MlpRef, x, math_mode=0, out=None):
+class _zsave:
+    """sets fvgn_mlp_t.z_save = z[rows, 384] for the duration of one call (forward in bf16x3 mode writes the three layers'
+    pre-activations there; the backward reads them instead of recomputing the forward)"""
+
+    def __init__(self, mlp, z, rows):
+        self.mlp, self.z = mlp, z
+        if z is not None:
+            _req(z, torch.float32, "z_save", 2)
+            if tuple(z.shape) != (rows, 384) or not z.is_contiguous():
+                raise ValueError(f"z_save must be a contiguous [rows, 384] fp32 tensor, got {tuple(z.shape)}")
+
+    def __enter__(self):
+        self.mlp.struct.z_save = self.z.data_ptr() if self.z is not None else None
+
+    def __exit__(self, *a):
+        self.mlp.struct.z_save = None
+        return False
+
+
+def mlp_rows_fwd(mlp: MlpRef, x, math_mode=0, out=None, z_save=None):
     _req(x, torch.float32, "x", 2)
     rows = x.shape[0]
     if x.shape[1] != mlp.k_in:
@@ -153,7 +172,9 @@ def mlp_rows_fwd(mlp: MlpRef, x, math_mode=0, out=None):
     if math_mode != 0:
         mlp.ensure_packed(math_mode)
     _count(1)
-    with _timed("mlp_rows"):
+    if z_save is not None and math_mode != 2:
+        raise ValueError("z_save is written by the bf16x3 forward only")
+    with _timed("mlp_rows"), _zsave(mlp, z_save, rows):
         check(_lib.lib().fvgn_mlp_rows_fwd(C.byref(mlp.struct), _p(x), _ld(x), rows, _p(out), _ld(out), math_mode, _stream()), "mlp_rows_fwd")
     return out
 
@@ -172,7 +193,7 @@ def node_aggregate_fwd(e, node_ptr, node_items, n_nodes, out=None):
     return out
 
 
-def cell_block_fwd(mlp: MlpRef, x, node_agg, cells_node_T, math_mode=0, x_prime=None, x_out=None, want_out=True):
+def cell_block_fwd(mlp: MlpRef, x, node_agg, cells_node_T, math_mode=0, x_prime=None, x_out=None, want_out=True, z_save=None):
     _req(x, torch.float32, "x", 2)
     _req(node_agg, torch.float32, "node_agg", 2)
     _req(cells_node_T, torch.int32, "cells_node_T", 2)
@@ -186,13 +207,16 @@ def cell_block_fwd(mlp: MlpRef, x, node_agg, cells_node_T, math_mode=0, x_prime=
     if math_mode != 0:
         mlp.ensure_packed(math_mode)
     _count(1)
-    with _timed("cell_block"):
+    if z_save is not None and math_mode != 2:
+        raise ValueError("z_save is written by the bf16x3 forward only")
+    with _timed("cell_block"), _zsave(mlp, z_save, Cn):
         check(_lib.lib().fvgn_cell_block_fwd(C.byref(mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(x_prime), _p(x_out), math_mode,
                                              _stream()), "cell_block_fwd")
     return x_prime, x_out
 
 
-def edge_block_fwd(mlp: MlpRef, x_prime, e, neighbour_cell, math_mode=0, e_prime=None, e_out=None, want_prime=False, want_out=True):
+def edge_block_fwd(mlp: MlpRef, x_prime, e, neighbour_cell, math_mode=0, e_prime=None, e_out=None, want_prime=False, want_out=True,
+                   z_save=None):
     _req(x_prime, torch.float32, "x_prime", 2)
     _req(e, torch.float32, "edge_attr", 2)
     _req(neighbour_cell, torch.int32, "neighbour_cell", 2)
@@ -206,7 +230,9 @@ def edge_block_fwd(mlp: MlpRef, x_prime, e, neighbour_cell, math_mode=0, e_prime
     if math_mode != 0:
         mlp.ensure_packed(math_mode)
     _count(1)
-    with _timed("edge_block"):
+    if z_save is not None and math_mode != 2:
+        raise ValueError("z_save is written by the bf16x3 forward only")
+    with _timed("edge_block"), _zsave(mlp, z_save, F):
         check(_lib.lib().fvgn_edge_block_fwd(C.byref(mlp.struct), _p(x_prime), _p(e), _p(neighbour_cell), F, _p(e_prime), _p(e_out), math_mode,
                                              _stream()), "edge_block_fwd")
     return e_prime, e_out
@@ -431,35 +457,39 @@ def _bwd_buffers(mlp: MlpRef, device):
     return grads, ws
 
 
-def mlp_rows_bwd(mlp: MlpRef, x, d_out, want_d_in=False):
+def mlp_rows_bwd(mlp: MlpRef, x, d_out, want_d_in=False, z_saved=None):
     _req(x, torch.float32, "x", 2), _req(d_out, torch.float32, "d_out", 2)
     grads, ws = _bwd_buffers(mlp, x.device)
     d_in = torch.empty((x.shape[0], mlp.k_in), dtype=torch.float32, device=x.device) if want_d_in else None
     _count(2)
-    check(_lib.lib().fvgn_mlp_rows_bwd(C.byref(mlp.struct), _p(x), _ld(x), x.shape[0], _p(d_out), _ld(d_out), _p(d_in),
-                                       _ld(d_in) if d_in is not None else 0, _p(grads), _p(ws), _stream()), "mlp_rows_bwd")
+    with _zsave(mlp, z_saved, x.shape[0]):
+        check(_lib.lib().fvgn_mlp_rows_bwd(C.byref(mlp.struct), _p(x), _ld(x), x.shape[0], _p(d_out), _ld(d_out), _p(d_in),
+                                           _ld(d_in) if d_in is not None else 0, _p(grads), _p(ws), _stream()), "mlp_rows_bwd")
     return _mlp_grad_views(mlp, grads), d_in
 
 
-def cell_block_bwd(mlp: MlpRef, x, node_agg, cells_node_T, d_x_prime, d_x_base=None):
+def cell_block_bwd(mlp: MlpRef, x, node_agg, cells_node_T, d_x_prime, d_x_base=None, z_saved=None):
     _cf(x, "x"), _cf(node_agg, "node_agg"), _ci(cells_node_T, "cells_node_T", 3), _cf(d_x_prime, "d_x_prime")
     Cn = x.shape[0]
     grads, ws = _bwd_buffers(mlp, x.device)
     d_in = torch.empty((Cn, 192), dtype=torch.float32, device=x.device)
     _count(2)
-    check(_lib.lib().fvgn_cell_block_bwd(C.byref(mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(d_x_prime), _p(d_x_base),
-                                         _ld(d_x_base) if d_x_base is not None else 0, _p(d_in), _p(grads), _p(ws), _stream()), "cell_block_bwd")
+    with _zsave(mlp, z_saved, Cn):
+        check(_lib.lib().fvgn_cell_block_bwd(C.byref(mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(d_x_prime), _p(d_x_base),
+                                             _ld(d_x_base) if d_x_base is not None else 0, _p(d_in), _p(grads), _p(ws), _stream()),
+              "cell_block_bwd")
     return _mlp_grad_views(mlp, grads), d_in
 
 
-def edge_block_bwd(mlp: MlpRef, x_prime, e, neighbour_cell, d_e_prime):
+def edge_block_bwd(mlp: MlpRef, x_prime, e, neighbour_cell, d_e_prime, z_saved=None):
     _cf(x_prime, "x_prime"), _cf(e, "e"), _ci(neighbour_cell, "neighbour_cell", 2), _cf(d_e_prime, "d_e_prime")
     F = e.shape[0]
     grads, ws = _bwd_buffers(mlp, e.device)
     d_in = torch.empty((F, 384), dtype=torch.float32, device=e.device)
     _count(2)
-    check(_lib.lib().fvgn_edge_block_bwd(C.byref(mlp.struct), _p(x_prime), _p(e), _p(neighbour_cell), F, _p(d_e_prime), _p(d_in), _p(grads), _p(ws),
-                                         _stream()), "edge_block_bwd")
+    with _zsave(mlp, z_saved, F):
+        check(_lib.lib().fvgn_edge_block_bwd(C.byref(mlp.struct), _p(x_prime), _p(e), _p(neighbour_cell), F, _p(d_e_prime), _p(d_in), _p(grads),
+                                             _p(ws), _stream()), "edge_block_bwd")
     return _mlp_grad_views(mlp, grads), d_in
 
 

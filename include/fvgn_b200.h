@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FVGN_ABI_VERSION 2
+#define FVGN_ABI_VERSION 3
 #define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
 
 #define FVGN_E_BADARG (-1)
@@ -60,6 +60,9 @@ typedef struct {
   int n_out;
   const void* packed;    /* FVGN_MATH_BF16_TC only: buffer filled by fvgn_mlp_pack_bf16 for the CURRENT weights; NULL otherwise */
   const void* packed_x3; /* FVGN_MATH_BF16X3_TC only: buffer filled by fvgn_mlp_pack_bf16x3 for the CURRENT weights; NULL otherwise */
+  float* z_save;         /* optional [rows, 384] fp32 = (z1 | z2 | z3): the pre-activations of the three layers (bias added, before SiLU /
+                            LayerNorm).  Forward in FVGN_MATH_BF16X3_TC mode: written when non-NULL.  Backward (fvgn_*_bwd): read when
+                            non-NULL instead of recomputing the forward inside the tile (a third of the backward's FLOPs). */
 } fvgn_mlp_t;
 
 /* Tensor-core modes read the weights as pre-swizzled bf16 tiles.  Re-pack whenever the fp32 weights change. */
