@@ -13,7 +13,8 @@ MATH_MODES = {"fp32": MATH_FP32_SIMT, "bf16": MATH_BF16_TC, "bf16x3": MATH_BF16X
 class MlpT(C.Structure):
     _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p),
                 ("b3", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("k_in", C.c_int), ("n_out", C.c_int), ("packed", C.c_void_p),
-                ("packed_x3", C.c_void_p), ("z_save", C.c_void_p)]
+                ("packed_x3", C.c_void_p), ("z_save", C.c_void_p), ("packed_x3_bwd", C.c_void_p),
+                ("da_in", C.c_void_p)]
 
 
 _P, _I, _F, _S = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -36,6 +37,10 @@ _SIGS = {
     "fvgn_mlp_pack_bf16": (_I, [C.POINTER(MlpT), _P, _S, _P]),
     "fvgn_mlp_packed_x3_bytes": (_S, [_I]),
     "fvgn_mlp_pack_bf16x3": (_I, [C.POINTER(MlpT), _P, _S, _P]),
+    "fvgn_mlp_packed_x3_bwd_bytes": (_S, [_I]),
+    "fvgn_mlp_pack_bf16x3_bwd": (_I, [C.POINTER(MlpT), _P, _S, _P]),
+    "fvgn_ln_bwd": (_I, [_P, _I, _P, _P, _I, _P, _P]),
+    "fvgn_mlp_dgrad_x3": (_I, [C.POINTER(MlpT), _P, _I, _I, _P, _P, _I, _P, _I, _P]),
     "fvgn_mlp_rows_fwd": (_I, [C.POINTER(MlpT), _P, _I, _I, _P, _I, _I, _P]),
     "fvgn_node_aggregate_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "fvgn_cell_block_fwd": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P, _I, _P]),
@@ -79,7 +84,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.fvgn_abi_version() != 3:
+        if L.fvgn_abi_version() != 4:
             raise RuntimeError("libfvgn_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -95,23 +95,43 @@ class NetFunction(torch.autograd.Function):
         g_bn = ops.face_area_bn_bwd(g_fa, raw, stats)
         grads = {}
         dec = epd.decoder.edge_decode_module
-        grads[id(dec)], g_e = ops.mlp_rows_bwd(dec.mlp_ref(), e_final, g_dec, want_d_in=True, z_saved=z_dec)
+        tc = z_dec is not None  # bf16x3 forward: the data-gradient chain runs on the tensor cores, the FFMA kernel keeps the TN products
+        if tc:
+            da, g_e = ops.mlp_dgrad_x3(dec.mlp_ref(), g_dec, z_dec, want_dA=True)
+            grads[id(dec)], _ = ops.mlp_rows_bwd(dec.mlp_ref(), e_final, g_dec, z_saved=z_dec, da_in=da)
+        else:
+            grads[id(dec)], g_e = ops.mlp_rows_bwd(dec.mlp_ref(), e_final, g_dec, want_d_in=True, z_saved=z_dec)
         g_x = None  # the last layer's cell latent feeds nothing but its own EdgeBlock
         cptr, citems = bt["cell_from_face"]
         nptr, nitems = bt["node_from_cell"]
         for blk in reversed(epd.processer_list):
             x_in, e_in, xp, na, zc, ze = saved_layers.pop()
             cb, eb = blk.cb_module.net, blk.eb_module.net
-            grads[id(eb)], dA_e = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e, z_saved=ze)
+            if tc:
+                dz = ops.ln_bwd(g_e, ze, eb[1].weight)
+                da, dA_e = ops.mlp_dgrad_x3(eb.mlp_ref(), dz, ze, want_dA=True)
+                grads[id(eb)], _ = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e, z_saved=ze, da_in=da)
+            else:
+                grads[id(eb)], dA_e = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e, z_saved=ze)
             # d x' = residual path + transpose of the x'[s], x'[r] gathers (cell <- face segment sum)
             g_xp = ops.segment_sum_rows(dA_e, topo.F, 0, 128, 128, cptr, citems, topo.C, base=g_x, scale=1.0)
-            grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, topo.cnT, g_xp, d_x_base=g_x, z_saved=zc)
+            if tc:
+                dz = ops.ln_bwd(g_xp, zc, cb[1].weight)
+                da, dA_c = ops.mlp_dgrad_x3(cb.mlp_ref(), dz, zc, want_dA=True, dA_base=g_x)
+                grads[id(cb)], _ = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, topo.cnT, g_xp, z_saved=zc, da_in=da)
+            else:
+                grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, topo.cnT, g_xp, d_x_base=g_x, z_saved=zc)
             # transposes of the twice-message aggregation: cell -> node (x 1/3), node -> face halves
             g_na = ops.segment_sum_rows(dA_c, topo.C, 128, 0, 64, nptr, nitems, topo.N, base=None, scale=1.0 / 3.0)
             g_e = ops.edge_grad_combine(g_e, dA_e, g_na, topo.fn)
             g_x = dA_c[:, 0:128]
-        grads[id(epd.encoder.cb_encoder)], _ = ops.mlp_rows_bwd(epd.encoder.cb_encoder.mlp_ref(), cell_in, g_x, z_saved=z_enc_c)
-        grads[id(epd.encoder.eb_encoder)], _ = ops.mlp_rows_bwd(epd.encoder.eb_encoder.mlp_ref(), edge_in, g_e, z_saved=z_enc_e)
+        for enc, inp, g, z in ((epd.encoder.cb_encoder, cell_in, g_x, z_enc_c), (epd.encoder.eb_encoder, edge_in, g_e, z_enc_e)):
+            if tc:
+                dz = ops.ln_bwd(g.contiguous() if g.stride(-1) != 1 else g, z, enc[1].weight)
+                da, _ = ops.mlp_dgrad_x3(enc.mlp_ref(), dz, z, want_dA=False)
+                grads[id(enc)], _ = ops.mlp_rows_bwd(enc.mlp_ref(), inp, g, z_saved=z, da_in=da)
+            else:
+                grads[id(enc)], _ = ops.mlp_rows_bwd(enc.mlp_ref(), inp, g, z_saved=z)
         flat = [g for m in network_mlps(model) for g in grads[id(m)]]
         flat += [g_bn[0:1], g_bn[1:2]]
         return (None,) * 9 + tuple(flat)

@@ -40,6 +40,10 @@ int tc3_cell_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*
 int tc3_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, cudaStream_t);
 size_t tc3_packed_bytes(int k_in);
 int tc3_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
+size_t tc3_packed_bwd_bytes(int k_in);
+int tc3_pack_bwd(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
+int tc3_ln_bwd(const float*, int, const float*, const float*, int, float*, cudaStream_t);
+int tc3_dgrad(const fvgn_mlp_t*, const float*, int, int, float*, float*, int, const float*, int, cudaStream_t);
 
 size_t tc_packed_bytes(int k_in);
 int tc_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
@@ -144,4 +148,22 @@ extern "C" int fvgn_edge_block_fwd_xbf16(const fvgn_mlp_t* mlp, const uint16_t* 
   if (math_mode != FVGN_MATH_BF16_TC) { set_error("fvgn_edge_block_fwd_xbf16: tensor-core math mode only"); return FVGN_E_BADARG; }
   if (!x_prime_bf16) { set_error("fvgn_edge_block_fwd_xbf16: x_prime_bf16 is NULL"); return FVGN_E_BADARG; }
   return tc_edge_block(mlp, nullptr, e, neighbour_cell, n_faces, nullptr, e, math_mode, as_stream(stream), x_prime_bf16);
+}
+
+extern "C" size_t fvgn_mlp_packed_x3_bwd_bytes(int k_in) { return tc3_packed_bwd_bytes(k_in); }
+
+extern "C" int fvgn_mlp_pack_bf16x3_bwd(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  return tc3_pack_bwd(mlp, packed, packed_bytes, as_stream(stream));
+}
+
+extern "C" int fvgn_ln_bwd(const float* d_out, int ld_dout, const float* z_save, const float* ln_w, int rows, float* dz, fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  return tc3_ln_bwd(d_out, ld_dout, z_save, ln_w, rows, dz, as_stream(stream));
+}
+
+extern "C" int fvgn_mlp_dgrad_x3(const fvgn_mlp_t* mlp, const float* dz, int ld_dz, int rows, float* da, float* dA, int ld_dA,
+                                 const float* dA_base, int ld_base, fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  return tc3_dgrad(mlp, dz, ld_dz, rows, da, dA, ld_dA, dA_base, ld_base, as_stream(stream));
 }

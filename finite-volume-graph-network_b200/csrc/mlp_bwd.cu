@@ -411,6 +411,20 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_simt_kernel(const BwdParams p) 
     if (tid < 128) s_db3 += colsum64(S, tid);
     // ------------------------------------------------------------------ layer 3
     gemm_tn_rmw<HLD>(S, T2, pW3, 128, n_out, 128, first, tid);                 // dW3[o][i] += dy[.,o] h2[.,i]
+    const float* da_in = p.mlp.da_in;  // (da2 | da1) precomputed on the tensor cores: only the TN products remain here
+    if (da_in != nullptr) {
+      float t[4][8];
+      __syncthreads();  // the TN product above still reads T2 (h2)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int g = min(row0 + tr * 4 + i, p.rows - 1);
+        const bool ok = row0 + tr * 4 + i < p.rows;
+        const float4 a = ldg4(da_in + (size_t)g * 256 + tc * 4), b = ldg4(da_in + (size_t)g * 256 + 64 + tc * 4);
+        t[i][0] = ok ? a.x : 0.f; t[i][1] = ok ? a.y : 0.f; t[i][2] = ok ? a.z : 0.f; t[i][3] = ok ? a.w : 0.f;
+        t[i][4] = ok ? b.x : 0.f; t[i][5] = ok ? b.y : 0.f; t[i][6] = ok ? b.z : 0.f; t[i][7] = ok ? b.w : 0.f;
+      }
+      st_tile(T2, t, tid);
+    } else {
     gemm_nn<HLD>(S, p.mlp.w3, 128, n_out, 0, 128, Wt, acc, tid);               // dh2 = dy . W3
     {
       float t[4][8];
@@ -423,10 +437,24 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_simt_kernel(const BwdParams p) 
         }
       st_tile(T2, t, tid);  // da2 (h2 is dead: the TN and NN products that read it are behind a barrier)
     }
+    }
     __syncthreads();
     if (tid < 128) s_db2 += colsum64(T2, tid);
     // ------------------------------------------------------------------ layer 2
     gemm_tn_rmw<HLD>(T2, T1, pW2, 128, 128, 128, first, tid);                  // dW2 += da2^T h1
+    if (da_in != nullptr) {
+      float t[4][8];
+      __syncthreads();  // the TN product above still reads T1 (h1)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int g = min(row0 + tr * 4 + i, p.rows - 1);
+        const bool ok = row0 + tr * 4 + i < p.rows;
+        const float4 a = ldg4(da_in + (size_t)g * 256 + 128 + tc * 4), b = ldg4(da_in + (size_t)g * 256 + 128 + 64 + tc * 4);
+        t[i][0] = ok ? a.x : 0.f; t[i][1] = ok ? a.y : 0.f; t[i][2] = ok ? a.z : 0.f; t[i][3] = ok ? a.w : 0.f;
+        t[i][4] = ok ? b.x : 0.f; t[i][5] = ok ? b.y : 0.f; t[i][6] = ok ? b.z : 0.f; t[i][7] = ok ? b.w : 0.f;
+      }
+      st_tile(T1, t, tid);
+    } else {
     gemm_nn<HLD>(T2, p.mlp.w2, 128, 128, 0, 128, Wt, acc, tid);                // dh1 = da2 . W2
     {
       float t[4][8];
@@ -439,6 +467,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_simt_kernel(const BwdParams p) 
         }
       st_tile(T1, t, tid);  // da1
     }
+    }
     __syncthreads();
     if (tid < 128) s_db1 += colsum64(T1, tid);
     // ------------------------------------------------------------------ layer 1: per 128-wide K segment
@@ -447,7 +476,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_bwd_simt_kernel(const BwdParams p) 
       __syncthreads();
       const int kv = min(128, k_in - seg * 128);
       gemm_tn_rmw<HLD>(T1, S, pW1 + seg * 128, k_in, 128, kv, first, tid);     // dW1[:, seg] += da1^T A_seg
-      if (p.d_in != nullptr) {
+      if (p.d_in != nullptr && da_in == nullptr) {
         gemm_nn<HLD>(T1, p.mlp.w1, k_in, 128, seg * 128, kv, Wt, acc, tid);   // dA_seg = da1 . W1[:, seg]
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -570,7 +599,7 @@ extern "C" int fvgn_mlp_rows_bwd(const fvgn_mlp_t* mlp, const float* in, int ld_
 extern "C" int fvgn_cell_block_bwd(const fvgn_mlp_t* mlp, const float* x, const float* node_agg, const int32_t* cells_node_T, int n_cells,
                                    const float* d_x_prime, const float* d_x_base, int ld_base, float* d_in /*[C,192]*/, float* grads,
                                    float* workspace, fvgn_stream_t stream) {
-  FVGN_CHECK_ARG(mlp && x && node_agg && cells_node_T && d_in, "NULL pointer");
+  FVGN_CHECK_ARG(mlp && x && node_agg && cells_node_T && (d_in || mlp->da_in), "NULL pointer");
   FVGN_CHECK_ARG(mlp->k_in == 192 && mlp->ln_w, "CellBlock MLP must be 192 -> 128 with LayerNorm");
   BwdParams p{};
   p.mlp = *mlp; p.mode = BW_CELL; p.rows = n_cells; p.src0 = x; p.src1 = node_agg; p.idx = cells_node_T; p.d_out = d_x_prime; p.ld_dout = 128;
@@ -580,7 +609,7 @@ extern "C" int fvgn_cell_block_bwd(const fvgn_mlp_t* mlp, const float* x, const 
 
 extern "C" int fvgn_edge_block_bwd(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, const int32_t* neighbour_cell, int n_faces,
                                    const float* d_e_prime, float* d_in /*[F,384]*/, float* grads, float* workspace, fvgn_stream_t stream) {
-  FVGN_CHECK_ARG(mlp && x_prime && e && neighbour_cell && d_in, "NULL pointer");
+  FVGN_CHECK_ARG(mlp && x_prime && e && neighbour_cell && (d_in || mlp->da_in), "NULL pointer");
   FVGN_CHECK_ARG(mlp->k_in == 384 && mlp->ln_w, "EdgeBlock MLP must be 384 -> 128 with LayerNorm");
   BwdParams p{};
   p.mlp = *mlp; p.mode = BW_EDGE; p.rows = n_faces; p.src0 = x_prime; p.src1 = e; p.idx = neighbour_cell; p.d_out = d_e_prime; p.ld_dout = 128;

@@ -515,6 +515,326 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
   }
 }
 
+// =====================================================================================================================
+// Backward data-gradient chain of one MLP on the tensor cores (training with the bf16x3 forward):
+//   dh2 = dz . W3            da2 = dh2 * silu'(z2)
+//   dh1 = da2 . W2           da1 = dh1 * silu'(z1)
+//   dA[:, seg] = da1 . W1[:, seg]   (+ residual-path gradient on the first 128 columns)
+// dz [rows, n_out] is the gradient behind the (optional) LayerNorm (ln_bwd_kernel below), z1/z2 the saved pre-activations
+// (fvgn_mlp_t.z_save).  Same pipeline as the forward kernel with the transposed weights packed in consumption order
+// (W3^T: 2 K-tile steps, W2^T: 2, W1[:, seg]^T: 2 per 128-column segment); da2 | da1 are also written to HBM [rows, 256] for the
+// weight-gradient kernel (mlp_bwd.cu), which then has no GEMM left but the TN products.
+struct DgParams {
+  int rows, ntiles, nseg, k_in, n_out, want_dA;
+  const float* dz; int ld_dz;
+  const float* zsave;
+  float* da;
+  float* dA; int ld_dA;
+  const float* dA_base; int ld_base;
+  const unsigned char* packed;
+};
+
+__device__ __forceinline__ float dsilu_x3(float z) {
+  float e, s;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + e));
+  return s * (1.0f + z * (1.0f - s));
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const SmemLayout L = smem_layout();
+  unsigned char* sA = smem + L.a_off;
+  unsigned char* sW = smem + L.w_off;
+  const uint32_t bar0 = smem_u32(smem + L.bar_off);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * B_COUNT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nseg3 = p.want_dA ? p.nseg : 0;
+
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) { printf("fvgn dgrad_tc3: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
+    for (int i = 0; i < ARING; ++i) { mbar_init(BAR(B_AFULL + i), NPW); mbar_init(BAR(B_AEMPTY + i), 1); }
+    for (int i = 0; i < WRING; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(BAR(B_DFULL + a), 1); mbar_init(BAR(B_DFREE + a), 8); }
+    mbar_init(BAR(B_HREADY), 8);
+    fence_mbar_init();
+  }
+  if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= WARP_PROD0 && warp < WARP_MMA) {
+    // ================================================================= producers: dz rows -> split -> A ring (2 K-tile steps per tile)
+    constexpr int NHW = NPROD / 16;
+    const int ptid = tid - NEPI;
+    const int hw = ptid >> 4, hl = ptid & 15;
+    const int S = n_local * 2;
+    const bool vec = ((p.ld_dz & 3) == 0) && p.n_out == 128 && ((reinterpret_cast<uintptr_t>(p.dz) & 15) == 0);
+    auto load = [&](int s, float4* v) {
+      const int jl = s >> 1, t = s & 1;
+      const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int gr = min(row0 + hw + NHW * i, p.rows - 1);
+        const int k0 = t * KTILE + hl * 4;
+        if (vec) v[i] = ldg4(p.dz + (size_t)gr * p.ld_dz + k0);
+        else {
+          float x4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (k0 + j < p.n_out) x4[j] = p.dz[(size_t)gr * p.ld_dz + k0 + j];
+          v[i] = make_float4(x4[0], x4[1], x4[2], x4[3]);
+        }
+      }
+    };
+    auto store = [&](int s, const float4* v) {
+      const uint32_t slot = (uint32_t)s % ARING;
+      if (s >= ARING) mbar_wait(BAR(B_AEMPTY + slot), (((uint32_t)s / ARING) - 1) & 1, 1);
+      unsigned char* dst = sA + slot * SLOT_BYTES;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) st_slot_f4(dst, hw + NHW * i, hl, v[i]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_AFULL + slot));
+    };
+    float4 va[RPT], vb[RPT];
+#pragma unroll 1
+    for (int s = -1; s < S; s += 2) {
+      if (s + 1 < S) load(s + 1, va);
+      if (s >= 0) store(s, vb);
+      if (s + 2 < S) load(s + 2, vb);
+      if (s + 1 < S) store(s + 1, va);
+    }
+  } else if (warp == WARP_LOAD) {
+    if (lane == 0 && n_local > 0) {
+      uint32_t wl = 0;
+      const int nsteps = 4 + 2 * nseg3;
+#pragma unroll 1
+      for (int jl = 0; jl < n_local; ++jl)
+#pragma unroll 1
+        for (int step = 0; step < nsteps; ++step, ++wl) {
+          const uint32_t slot = wl % WRING;
+          if (wl >= WRING) mbar_wait(BAR(B_WEMPTY + slot), ((wl / WRING) - 1) & 1, 2);
+          mbar_arrive_expect_tx(BAR(B_WFULL + slot), SLOT_BYTES);
+          bulk_g2s(smem_u32(sW + slot * SLOT_BYTES), p.packed + (size_t)step * SLOT_BYTES, SLOT_BYTES, BAR(B_WFULL + slot));
+        }
+    }
+    __syncwarp();
+  } else if (warp == WARP_MMA) {
+    // ================================================================= MMA issuer: batches S1 (acc0), S2 (acc1), S3[seg] (acc seg & 1)
+    if (lane == 0 && n_local > 0) {
+      uint32_t ak = 0, wk = 0, hphase = 0, use0 = 0, use1 = 0;
+      auto acquire = [&](int a) {  // the previous batch on accumulator a has been read out
+        uint32_t& u = a ? use1 : use0;
+        if (u > 0) mbar_wait(BAR(B_DFREE + a), (u - 1) & 1, 3);
+        ++u;
+      };
+      auto w_steps = [&](uint32_t d, bool a_from_ring) {
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t, ++wk) {
+          const uint32_t sw = wk % WRING;
+          uint32_t sa = 0;
+          if (a_from_ring) { sa = ak % ARING; mbar_wait(BAR(B_AFULL + sa), (ak / ARING) & 1, 4); }
+          mbar_wait(BAR(B_WFULL + sw), (wk / WRING) & 1, 5);
+          tc_fence_after();
+          const uint32_t b_base = smem_u32(sW + sw * SLOT_BYTES);
+          if (a_from_ring) {
+            const uint32_t a_base = smem_u32(sA + sa * SLOT_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+              for (int q = 0; q < 6; ++q)
+                umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
+                          IDESC_BF16_M128_N128, (t | kk | q) != 0);
+            umma_commit(BAR(B_AEMPTY + sa));
+            ++ak;
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+              for (int q = 0; q < 6; ++q)
+                umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
+                             umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32), IDESC_BF16_M128_N128, (t | kk | q) != 0);
+          }
+          umma_commit(BAR(B_WEMPTY + sw));
+        }
+      };
+#pragma unroll 1
+      for (int jl = 0; jl < n_local; ++jl) {
+        acquire(0);
+        w_steps(tmem_base, true);  // S1: dz . W3
+        umma_commit(BAR(B_DFULL + 0));
+        mbar_wait(BAR(B_HREADY), hphase, 7); hphase ^= 1;
+        acquire(1);
+        w_steps(tmem_base + 128u, false);  // S2: da2 . W2
+        umma_commit(BAR(B_DFULL + 1));
+        mbar_wait(BAR(B_HREADY), hphase, 7); hphase ^= 1;
+#pragma unroll 1
+        for (int seg = 0; seg < nseg3; ++seg) {  // S3: da1 . W1[:, seg]
+          acquire(seg & 1);
+          w_steps(tmem_base + 128u * (uint32_t)(seg & 1), false);
+          umma_commit(BAR(B_DFULL + (seg & 1)));
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================= epilogue warps 0-7: two threads per row, 16-column sub-chunks
+    const int q = warp & 3, h = warp >> 2;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t t_h = t_lane + TMEM_H0;
+    unsigned char* stage = smem + L.stage_off + warp * 2048;
+    auto store_rows16 = [&](const float* v, float* dst, int ld, int col0, int row_base) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4*>(stage + (uint32_t)lane * 64u + (((uint32_t)k ^ (((uint32_t)lane >> 1) & 3u)) << 4)) =
+            make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      __syncwarp();
+      const int rr0 = lane >> 2, cp = lane & 3;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = 8 * it + rr0, grow = row_base + rr;
+        if (grow < p.rows)
+          *reinterpret_cast<float4*>(dst + (size_t)grow * ld + col0 + 4 * (cp ^ ((rr >> 1) & 3))) =
+              *reinterpret_cast<const float4*>(stage + (uint32_t)rr * 64u + ((uint32_t)cp << 4));
+      }
+      __syncwarp();
+    };
+    uint32_t e0 = 0, e1 = 0;  // DFULL completions consumed per accumulator
+    auto wait_acc = [&](int a) {
+      uint32_t& u = a ? e1 : e0;
+      mbar_wait(BAR(B_DFULL + a), u & 1, 8);
+      ++u;
+      tc_fence_after();
+    };
+    auto release_acc = [&](int a) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_DFREE + a));
+    };
+#pragma unroll 1
+    for (int jl = 0; jl < n_local; ++jl) {
+      const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+      const int grow_c = min(row0 + 32 * q + lane, p.rows - 1);  // this thread's row (clamped for loads)
+      uint32_t r[16];
+      // ---- batches S1, S2: d(hidden) * silu'(z) -> da (HBM) + split planes (TMEM)
+#pragma unroll 1
+      for (int b = 0; b < 2; ++b) {
+        wait_acc(b);
+        const float* zrow = p.zsave + (size_t)grow_c * 384 + (b == 0 ? 128 : 0);  // S1 pairs with z2, S2 with z1
+#pragma unroll 1
+        for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
+          tmem_ld16_issue(t_lane + 128u * (uint32_t)b + 16 * sc, r);
+          tmem_ld16_wait(r);
+          if (sc == 4 * h + 3) release_acc(b);
+          float v[16];
+          uint32_t p0[8], p1[8], p2[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 z = ldg4(zrow + 16 * sc + 4 * j4);
+            v[4 * j4] = __uint_as_float(r[4 * j4]) * dsilu_x3(z.x); v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) * dsilu_x3(z.y);
+            v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) * dsilu_x3(z.z); v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) * dsilu_x3(z.w);
+            split3_pair(v[4 * j4], v[4 * j4 + 1], p0[2 * j4], p1[2 * j4], p2[2 * j4]);
+            split3_pair(v[4 * j4 + 2], v[4 * j4 + 3], p0[2 * j4 + 1], p1[2 * j4 + 1], p2[2 * j4 + 1]);
+          }
+          tmem_st8(t_h + 8 * sc, p0);
+          tmem_st8(t_h + 64 + 8 * sc, p1);
+          tmem_st8(t_h + 128 + 8 * sc, p2);
+          store_rows16(v, p.da, 256, 128 * b + 16 * sc, row0 + 32 * q);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_HREADY));
+      }
+      // ---- batches S3[seg]: dA[:, 128 seg ..] (+ the residual-path gradient on segment 0)
+#pragma unroll 1
+      for (int seg = 0; seg < nseg3; ++seg) {
+        const int a = seg & 1;
+        wait_acc(a);
+        const int kv = min(128, p.k_in - 128 * seg);
+#pragma unroll 1
+        for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
+          tmem_ld16_issue(t_lane + 128u * (uint32_t)a + 16 * sc, r);
+          tmem_ld16_wait(r);
+          if (sc == 4 * h + 3) release_acc(a);
+          if (16 * sc >= kv) continue;  // columns past the segment's valid width (k_in % 16 == 0 is checked on the host)
+          float* v = reinterpret_cast<float*>(r);
+          if (seg == 0 && p.dA_base != nullptr) {
+            const float* brow = p.dA_base + (size_t)grow_c * p.ld_base + 16 * sc;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bb = ldg4(brow + 4 * j4);
+              v[4 * j4] += bb.x; v[4 * j4 + 1] += bb.y; v[4 * j4 + 2] += bb.z; v[4 * j4 + 3] += bb.w;
+            }
+          }
+          store_rows16(v, p.dA, p.ld_dA, 128 * seg + 16 * sc, row0 + 32 * q);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// LayerNorm backward of a row block: dz = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)), xhat from the saved z3.
+// One warp per row (4 columns per lane); the affine-parameter gradients are formed by the weight-gradient kernel.
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d_out, int ld_dout, const float* __restrict__ zsave,
+                                                     const float* __restrict__ gamma, int rows, float* __restrict__ dz) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4 z = ldg4(zsave + (size_t)row * 384 + 256 + lane * 4);
+  const float4 g = ldg4(d_out + (size_t)row * ld_dout + lane * 4);
+  const float4 w = ldg4(gamma + lane * 4);
+  float s = (z.x + z.y) + (z.z + z.w);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / 128.0f);
+  const float d0 = z.x - mean, d1 = z.y - mean, d2 = z.z - mean, d3 = z.w - mean;
+  float qv = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
+  const float rstd = 1.0f / sqrtf(qv * (1.0f / 128.0f) + 1e-5f);
+  const float x0 = d0 * rstd, x1 = d1 * rstd, x2 = d2 * rstd, x3v = d3 * rstd;
+  const float h0 = g.x * w.x, h1 = g.y * w.y, h2 = g.z * w.z, h3 = g.w * w.w;
+  float m1 = (h0 + h1) + (h2 + h3), m2 = fmaf(h0, x0, fmaf(h1, x1, fmaf(h2, x2, h3 * x3v)));
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) { m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o); }
+  m1 *= (1.0f / 128.0f); m2 *= (1.0f / 128.0f);
+  *reinterpret_cast<float4*>(dz + (size_t)row * 128 + lane * 4) =
+      make_float4(rstd * (h0 - m1 - x0 * m2), rstd * (h1 - m1 - x1 * m2), rstd * (h2 - m1 - x2 * m2), rstd * (h3 - m1 - x3v * m2));
+}
+
+// transposed packing for the backward: element (n, k) of the packed "weight" is W[k * ldw + n0 + n]  (W^T restricted to columns n0..)
+__global__ void pack_tiles3_t_kernel(const float* __restrict__ W, int ldw, int n0, int n_valid, int k_valid, int kt, unsigned char* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (tile, n, chunk)
+  if (idx >= kt * 128 * 8) return;
+  const int c = idx & 7, n = (idx >> 3) & 127, t = idx >> 10;
+  uint4 q0, q1, q2;
+  uint32_t* a0 = reinterpret_cast<uint32_t*>(&q0);
+  uint32_t* a1 = reinterpret_cast<uint32_t*>(&q1);
+  uint32_t* a2 = reinterpret_cast<uint32_t*>(&q2);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = t * KTILE + c * 8 + 2 * j;
+    const float x = (n < n_valid && k < k_valid) ? W[(size_t)k * ldw + n0 + n] : 0.f;
+    const float y = (n < n_valid && k + 1 < k_valid) ? W[(size_t)(k + 1) * ldw + n0 + n] : 0.f;
+    split3_pair(x, y, a0[j], a1[j], a2[j]);
+  }
+  const size_t off = (size_t)t * SLOT_BYTES + (size_t)n * 128 + (((uint32_t)c ^ ((uint32_t)n & 7u)) << 4);
+  *reinterpret_cast<uint4*>(out + off) = q0;
+  *reinterpret_cast<uint4*>(out + TILE_BYTES + off) = q1;
+  *reinterpret_cast<uint4*>(out + 2 * TILE_BYTES + off) = q2;
+}
+
 // W [n_valid, k_valid] fp32 row-major -> steps [kt][3 splits][128 rows][64 k] bf16, each sub-tile a byte image of the swizzled layout
 __global__ void pack_tiles3_kernel(const float* __restrict__ W, int ldw, int n_valid, int k_valid, int kt, unsigned char* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (tile, n, chunk)
@@ -629,6 +949,66 @@ int tc3_edge_block(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, 
   x3::Params p{};
   p.mode = x3::TC_EDGE; p.rows = n_faces; p.src0 = x_prime; p.src1 = e; p.idx = neighbour_cell; p.out0 = e_prime; p.out1 = e_out; p.ld_out = 128;
   return launch_tc3(p, mlp, e_out != nullptr && e_out == e, st);
+}
+
+
+// ---- backward (data-gradient chain) host side
+size_t tc3_packed_bwd_bytes(int k_in) { return (size_t)(4 + 2 * ((k_in + 127) / 128)) * x3::SLOT_BYTES; }
+
+int tc3_pack_bwd(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t st) {
+  using namespace x3;
+  FVGN_CHECK_ARG(m && packed, "NULL pointer");
+  FVGN_CHECK_ARG(m->k_in >= 1 && m->k_in <= 384 && m->n_out >= 1 && m->n_out <= 128, "bad mlp dims");
+  FVGN_CHECK_ARG(bytes >= tc3_packed_bwd_bytes(m->k_in), "packed buffer too small");
+  FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed buffer must be 16B aligned");
+  unsigned char* o = reinterpret_cast<unsigned char*>(packed);
+  const int nseg = (m->k_in + 127) / 128;
+  // dh2[., i] = sum_o dz[., o] W3[o][i]: "weight" rows n = i (128), K = o (n_out valid)
+  pack_tiles3_t_kernel<<<cdiv(2 * 1024, 256), 256, 0, st>>>(m->w3, 128, 0, 128, m->n_out, 2, o);
+  FVGN_LAUNCH_CHECK();
+  pack_tiles3_t_kernel<<<cdiv(2 * 1024, 256), 256, 0, st>>>(m->w2, 128, 0, 128, 128, 2, o + 2 * (size_t)SLOT_BYTES);
+  FVGN_LAUNCH_CHECK();
+  for (int seg = 0; seg < nseg; ++seg) {  // dA[., 128 seg + n] = sum_o da1[., o] W1[o][128 seg + n]
+    const int nv = m->k_in - 128 * seg < 128 ? m->k_in - 128 * seg : 128;
+    pack_tiles3_t_kernel<<<cdiv(2 * 1024, 256), 256, 0, st>>>(m->w1, m->k_in, 128 * seg, nv, 128, 2, o + (size_t)(4 + 2 * seg) * SLOT_BYTES);
+    FVGN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int tc3_ln_bwd(const float* d_out, int ld_dout, const float* z_save, const float* ln_w, int rows, float* dz, cudaStream_t st) {
+  FVGN_CHECK_ARG(d_out && z_save && ln_w && dz, "NULL pointer");
+  FVGN_CHECK_ARG((ld_dout & 3) == 0, "d_out row stride must be a multiple of 4 floats");
+  if (rows <= 0) return 0;
+  x3::ln_bwd_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(d_out, ld_dout, z_save, ln_w, rows, dz);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc3_dgrad(const fvgn_mlp_t* m, const float* dz, int ld_dz, int rows, float* da, float* dA, int ld_dA, const float* dA_base, int ld_base,
+              cudaStream_t st) {
+  using namespace x3;
+  FVGN_CHECK_ARG(m && dz && da, "NULL pointer");
+  FVGN_CHECK_ARG(m->z_save != nullptr, "the data-gradient chain needs the saved pre-activations (fvgn_mlp_t.z_save)");
+  FVGN_CHECK_ARG(m->packed_x3_bwd != nullptr, "call fvgn_mlp_pack_bf16x3_bwd first");
+  FVGN_CHECK_ARG(m->k_in >= 1 && m->k_in <= 384 && m->n_out >= 1 && m->n_out <= 128 && ld_dz >= m->n_out, "bad dims");
+  FVGN_CHECK_ARG(!dA || ((m->k_in & 15) == 0 && (ld_dA & 3) == 0 && ld_dA >= m->k_in), "dA needs k_in % 16 == 0 and a 16B-aligned row stride");
+  FVGN_CHECK_ARG(!dA_base || (ld_base & 3) == 0, "dA_base row stride must be a multiple of 4 floats");
+  if (rows <= 0) return 0;
+  DgParams p{};
+  p.rows = rows; p.ntiles = cdiv(rows, TM); p.nseg = (m->k_in + 127) / 128; p.k_in = m->k_in; p.n_out = m->n_out; p.want_dA = dA ? 1 : 0;
+  p.dz = dz; p.ld_dz = ld_dz; p.zsave = m->z_save; p.da = da; p.dA = dA; p.ld_dA = ld_dA; p.dA_base = dA_base; p.ld_base = ld_base;
+  p.packed = reinterpret_cast<const unsigned char*>(m->packed_x3_bwd);
+  const SmemLayout L = smem_layout();
+  static bool configured = false;
+  if (!configured) {
+    FVGN_CUDA(cudaFuncSetAttribute(dgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    configured = true;
+  }
+  const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
+  dgrad_tc3_kernel<<<grid, NTHREADS, L.total, st>>>(p);
+  FVGN_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace fvgn

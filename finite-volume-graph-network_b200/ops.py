@@ -96,7 +96,8 @@ def as_i32(t):
 class MlpRef:
     """Borrowed pointers to one build_mlp's parameters (reference state_dict layout)."""
 
-    __slots__ = ("tensors", "struct", "k_in", "n_out", "packed", "packed_versions", "packed3", "packed3_versions")
+    __slots__ = ("tensors", "struct", "k_in", "n_out", "packed", "packed_versions", "packed3", "packed3_versions", "packed3b",
+                 "packed3b_versions")
 
     def __init__(self, w1, b1, w2, b2, w3, b3, ln_w=None, ln_b=None):
         ts = [w1, b1, w2, b2, w3, b3] + ([ln_w, ln_b] if ln_w is not None else [])
@@ -110,11 +111,27 @@ class MlpRef:
         self.k_in, self.n_out = int(w1.shape[1]), int(w3.shape[0])
         self.struct = MlpT(w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(),
                            ln_w.data_ptr() if ln_w is not None else None, ln_b.data_ptr() if ln_b is not None else None,
-                           self.k_in, self.n_out, None, None, None)
+                           self.k_in, self.n_out, None, None, None, None, None)
+        self.packed3b = None
+        self.packed3b_versions = None
         self.packed = None
         self.packed_versions = None
         self.packed3 = None
         self.packed3_versions = None
+
+    def ensure_packed_bwd(self):
+        """transposed 3-way-split weight tiles of the tensor-core data-gradient chain (fvgn_mlp_dgrad_x3)"""
+        ver = tuple(t._version for t in self.tensors[:6:2])
+        if self.packed3b is None or self.packed3b_versions != ver:
+            L = _lib.lib()
+            nbytes = L.fvgn_mlp_packed_x3_bwd_bytes(self.k_in)
+            if self.packed3b is None:
+                self.packed3b = torch.empty(nbytes, dtype=torch.uint8, device=self.tensors[0].device)
+                self.struct.packed_x3_bwd = self.packed3b.data_ptr()
+            _count(2 + (self.k_in + 127) // 128)
+            check(L.fvgn_mlp_pack_bf16x3_bwd(C.byref(self.struct), _p(self.packed3b), nbytes, _stream()), "mlp_pack_bf16x3_bwd")
+            self.packed3b_versions = ver
+        return self
 
     def ensure_packed(self, math_mode=1):
         """(Re)build the swizzled weight tiles the tcgen05 paths read (math_mode 1: bf16; 2: exact 3-way bf16 split), if the fp32
@@ -147,8 +164,12 @@ class _zsave:
     """sets fvgn_mlp_t.z_save = z[rows, 384] for the duration of one call (forward in bf16x3 mode writes the three layers'
     pre-activations there; the backward reads them instead of recomputing the forward)"""
 
-    def __init__(self, mlp, z, rows):
-        self.mlp, self.z = mlp, z
+    def __init__(self, mlp, z, rows, da_in=None):
+        self.mlp, self.z, self.da = mlp, z, da_in
+        if da_in is not None:
+            _req(da_in, torch.float32, "da_in", 2)
+            if tuple(da_in.shape) != (rows, 256) or not da_in.is_contiguous():
+                raise ValueError(f"da_in must be a contiguous [rows, 256] fp32 tensor, got {tuple(da_in.shape)}")
         if z is not None:
             _req(z, torch.float32, "z_save", 2)
             if tuple(z.shape) != (rows, 384) or not z.is_contiguous():
@@ -156,9 +177,11 @@ class _zsave:
 
     def __enter__(self):
         self.mlp.struct.z_save = self.z.data_ptr() if self.z is not None else None
+        self.mlp.struct.da_in = self.da.data_ptr() if self.da is not None else None
 
     def __exit__(self, *a):
         self.mlp.struct.z_save = None
+        self.mlp.struct.da_in = None
         return False
 
 
@@ -457,37 +480,61 @@ def _bwd_buffers(mlp: MlpRef, device):
     return grads, ws
 
 
-def mlp_rows_bwd(mlp: MlpRef, x, d_out, want_d_in=False, z_saved=None):
+def ln_bwd(d_out, z_saved, ln_w):
+    """dz[rows,128]: LayerNorm backward of d_out with the statistics of the saved z3 (input of fvgn_mlp_dgrad_x3)"""
+    _req(d_out, torch.float32, "d_out", 2), _cf(z_saved, "z_saved"), _cf(ln_w, "ln_w")
+    rows = d_out.shape[0]
+    dz = torch.empty((rows, 128), dtype=torch.float32, device=d_out.device)
+    _count(1)
+    check(_lib.lib().fvgn_ln_bwd(_p(d_out), _ld(d_out), _p(z_saved), _p(ln_w), rows, _p(dz), _stream()), "ln_bwd")
+    return dz
+
+
+def mlp_dgrad_x3(mlp: MlpRef, dz, z_saved, want_dA=True, dA_base=None):
+    """tensor-core data-gradient chain: returns (da[rows,256] = da2 | da1, dA[rows,k_in] or None)"""
+    _req(dz, torch.float32, "dz", 2)
+    rows = dz.shape[0]
+    mlp.ensure_packed_bwd()
+    da = torch.empty((rows, 256), dtype=torch.float32, device=dz.device)
+    dA = torch.empty((rows, mlp.k_in), dtype=torch.float32, device=dz.device) if want_dA else None
+    _count(1)
+    with _zsave(mlp, z_saved, rows):
+        check(_lib.lib().fvgn_mlp_dgrad_x3(C.byref(mlp.struct), _p(dz), _ld(dz), rows, _p(da), _p(dA), mlp.k_in if want_dA else 0, _p(dA_base),
+                                           _ld(dA_base) if dA_base is not None else 0, _stream()), "mlp_dgrad_x3")
+    return da, dA
+
+
+def mlp_rows_bwd(mlp: MlpRef, x, d_out, want_d_in=False, z_saved=None, da_in=None):
     _req(x, torch.float32, "x", 2), _req(d_out, torch.float32, "d_out", 2)
     grads, ws = _bwd_buffers(mlp, x.device)
     d_in = torch.empty((x.shape[0], mlp.k_in), dtype=torch.float32, device=x.device) if want_d_in else None
     _count(2)
-    with _zsave(mlp, z_saved, x.shape[0]):
+    with _zsave(mlp, z_saved, x.shape[0], da_in):
         check(_lib.lib().fvgn_mlp_rows_bwd(C.byref(mlp.struct), _p(x), _ld(x), x.shape[0], _p(d_out), _ld(d_out), _p(d_in),
                                            _ld(d_in) if d_in is not None else 0, _p(grads), _p(ws), _stream()), "mlp_rows_bwd")
     return _mlp_grad_views(mlp, grads), d_in
 
 
-def cell_block_bwd(mlp: MlpRef, x, node_agg, cells_node_T, d_x_prime, d_x_base=None, z_saved=None):
+def cell_block_bwd(mlp: MlpRef, x, node_agg, cells_node_T, d_x_prime, d_x_base=None, z_saved=None, da_in=None):
     _cf(x, "x"), _cf(node_agg, "node_agg"), _ci(cells_node_T, "cells_node_T", 3), _cf(d_x_prime, "d_x_prime")
     Cn = x.shape[0]
     grads, ws = _bwd_buffers(mlp, x.device)
-    d_in = torch.empty((Cn, 192), dtype=torch.float32, device=x.device)
+    d_in = torch.empty((Cn, 192), dtype=torch.float32, device=x.device) if da_in is None else None
     _count(2)
-    with _zsave(mlp, z_saved, Cn):
+    with _zsave(mlp, z_saved, Cn, da_in):
         check(_lib.lib().fvgn_cell_block_bwd(C.byref(mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(d_x_prime), _p(d_x_base),
                                              _ld(d_x_base) if d_x_base is not None else 0, _p(d_in), _p(grads), _p(ws), _stream()),
               "cell_block_bwd")
     return _mlp_grad_views(mlp, grads), d_in
 
 
-def edge_block_bwd(mlp: MlpRef, x_prime, e, neighbour_cell, d_e_prime, z_saved=None):
+def edge_block_bwd(mlp: MlpRef, x_prime, e, neighbour_cell, d_e_prime, z_saved=None, da_in=None):
     _cf(x_prime, "x_prime"), _cf(e, "e"), _ci(neighbour_cell, "neighbour_cell", 2), _cf(d_e_prime, "d_e_prime")
     F = e.shape[0]
     grads, ws = _bwd_buffers(mlp, e.device)
-    d_in = torch.empty((F, 384), dtype=torch.float32, device=e.device)
+    d_in = torch.empty((F, 384), dtype=torch.float32, device=e.device) if da_in is None else None
     _count(2)
-    with _zsave(mlp, z_saved, F):
+    with _zsave(mlp, z_saved, F, da_in):
         check(_lib.lib().fvgn_edge_block_bwd(C.byref(mlp.struct), _p(x_prime), _p(e), _p(neighbour_cell), F, _p(d_e_prime), _p(d_in), _p(grads),
                                              _p(ws), _stream()), "edge_block_bwd")
     return _mlp_grad_views(mlp, grads), d_in

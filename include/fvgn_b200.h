@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FVGN_ABI_VERSION 3
+#define FVGN_ABI_VERSION 4
 #define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
 
 #define FVGN_E_BADARG (-1)
@@ -63,6 +63,9 @@ typedef struct {
   float* z_save;         /* optional [rows, 384] fp32 = (z1 | z2 | z3): the pre-activations of the three layers (bias added, before SiLU /
                             LayerNorm).  Forward in FVGN_MATH_BF16X3_TC mode: written when non-NULL.  Backward (fvgn_*_bwd): read when
                             non-NULL instead of recomputing the forward inside the tile (a third of the backward's FLOPs). */
+  const void* packed_x3_bwd; /* fvgn_mlp_dgrad_x3 only: buffer filled by fvgn_mlp_pack_bf16x3_bwd for the CURRENT weights */
+  const float* da_in;    /* optional [rows, 256] = (da2 | da1) from fvgn_mlp_dgrad_x3.  Backward (fvgn_*_bwd): when non-NULL the FFMA
+                            kernel skips its data-gradient GEMMs (and writes no d_in): only weight / bias / LayerNorm gradients remain. */
 } fvgn_mlp_t;
 
 /* Tensor-core modes read the weights as pre-swizzled bf16 tiles.  Re-pack whenever the fp32 weights change. */
@@ -220,6 +223,17 @@ FVGN_API int fvgn_cell_block_bwd(const fvgn_mlp_t* mlp, const float* x, const fl
 FVGN_API int fvgn_edge_block_bwd(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, const int32_t* neighbour_cell, int n_faces,
                                  const float* d_e_prime /*[F,128]*/, float* d_in /*[F,384] = d[x'_s | x'_r | e]*/, float* grads, float* workspace,
                                  fvgn_stream_t stream);
+/* Tensor-core data-gradient chain of one MLP (training with the FVGN_MATH_BF16X3_TC forward; needs mlp->z_save and mlp->packed_x3_bwd):
+ *   fvgn_ln_bwd:        dz[rows,128] = LayerNorm backward of d_out (statistics from the saved z3); MLPs without LayerNorm pass d_out itself
+ *   fvgn_mlp_dgrad_x3:  da[rows,256] = (da2 | da1);  dA[rows,k_in] (optional) = da1 . W1 (+ dA_base on the first 128 columns)
+ * followed by fvgn_*_bwd with mlp->da_in = da for the weight gradients. */
+FVGN_API size_t fvgn_mlp_packed_x3_bwd_bytes(int k_in);
+FVGN_API int fvgn_mlp_pack_bf16x3_bwd(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream);
+FVGN_API int fvgn_ln_bwd(const float* d_out, int ld_dout, const float* z_save /*[rows,384]*/, const float* ln_w, int rows, float* dz /*[rows,128]*/,
+                         fvgn_stream_t stream);
+FVGN_API int fvgn_mlp_dgrad_x3(const fvgn_mlp_t* mlp, const float* dz, int ld_dz, int rows, float* da /*[rows,256]*/, float* dA /*or NULL*/,
+                               int ld_dA, const float* dA_base /*or NULL*/, int ld_base, fvgn_stream_t stream);
+
 /* Transposes of the gathers as deterministic CSR segment sums:
  *   out[d, 0:width] = base[d] + scale * sum_{pos in CSR(d)} src[pos % n_src, col0 + (pos / n_src) * part_stride + 0:width] */
 FVGN_API int fvgn_segment_sum_rows(const float* src, int ld_src, int n_src, int col0, int part_stride, int width, const int32_t* ptr,
