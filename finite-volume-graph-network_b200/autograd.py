@@ -98,7 +98,7 @@ class NetFunction(torch.autograd.Function):
         tc = z_dec is not None  # bf16x3 forward: the data-gradient chain runs on the tensor cores, the FFMA kernel keeps the TN products
         if tc:
             da, g_e = ops.mlp_dgrad_x3(dec.mlp_ref(), g_dec, z_dec, want_dA=True)
-            grads[id(dec)], _ = ops.mlp_rows_bwd(dec.mlp_ref(), e_final, g_dec, z_saved=z_dec, da_in=da)
+            grads[id(dec)] = ops.mlp_wgrad_x3(dec.mlp_ref(), 0, g_dec, None, None, z_dec, da, x=e_final)
         else:
             grads[id(dec)], g_e = ops.mlp_rows_bwd(dec.mlp_ref(), e_final, g_dec, want_d_in=True, z_saved=z_dec)
         g_x = None  # the last layer's cell latent feeds nothing but its own EdgeBlock
@@ -108,17 +108,17 @@ class NetFunction(torch.autograd.Function):
             x_in, e_in, xp, na, zc, ze = saved_layers.pop()
             cb, eb = blk.cb_module.net, blk.eb_module.net
             if tc:
-                dz = ops.ln_bwd(g_e, ze, eb[1].weight)
+                dz, gxh = ops.ln_bwd(g_e, ze, eb[1].weight)
                 da, dA_e = ops.mlp_dgrad_x3(eb.mlp_ref(), dz, ze, want_dA=True)
-                grads[id(eb)], _ = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e, z_saved=ze, da_in=da)
+                grads[id(eb)] = ops.mlp_wgrad_x3(eb.mlp_ref(), 2, g_e, dz, gxh, ze, da, src0=xp, src1=e_in, idx=topo.nc)
             else:
                 grads[id(eb)], dA_e = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e, z_saved=ze)
             # d x' = residual path + transpose of the x'[s], x'[r] gathers (cell <- face segment sum)
             g_xp = ops.segment_sum_rows(dA_e, topo.F, 0, 128, 128, cptr, citems, topo.C, base=g_x, scale=1.0)
             if tc:
-                dz = ops.ln_bwd(g_xp, zc, cb[1].weight)
+                dz, gxh = ops.ln_bwd(g_xp, zc, cb[1].weight)
                 da, dA_c = ops.mlp_dgrad_x3(cb.mlp_ref(), dz, zc, want_dA=True, dA_base=g_x)
-                grads[id(cb)], _ = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, topo.cnT, g_xp, z_saved=zc, da_in=da)
+                grads[id(cb)] = ops.mlp_wgrad_x3(cb.mlp_ref(), 1, g_xp, dz, gxh, zc, da, src0=x_in, src1=na, idx=topo.cnT)
             else:
                 grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, topo.cnT, g_xp, d_x_base=g_x, z_saved=zc)
             # transposes of the twice-message aggregation: cell -> node (x 1/3), node -> face halves
@@ -127,9 +127,9 @@ class NetFunction(torch.autograd.Function):
             g_x = dA_c[:, 0:128]
         for enc, inp, g, z in ((epd.encoder.cb_encoder, cell_in, g_x, z_enc_c), (epd.encoder.eb_encoder, edge_in, g_e, z_enc_e)):
             if tc:
-                dz = ops.ln_bwd(g.contiguous() if g.stride(-1) != 1 else g, z, enc[1].weight)
+                dz, gxh = ops.ln_bwd(g, z, enc[1].weight)
                 da, _ = ops.mlp_dgrad_x3(enc.mlp_ref(), dz, z, want_dA=False)
-                grads[id(enc)], _ = ops.mlp_rows_bwd(enc.mlp_ref(), inp, g, z_saved=z, da_in=da)
+                grads[id(enc)] = ops.mlp_wgrad_x3(enc.mlp_ref(), 0, g, dz, gxh, z, da, x=inp)
             else:
                 grads[id(enc)], _ = ops.mlp_rows_bwd(enc.mlp_ref(), inp, g, z_saved=z)
         flat = [g for m in network_mlps(model) for g in grads[id(m)]]

@@ -42,7 +42,10 @@ size_t tc3_packed_bytes(int k_in);
 int tc3_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
 size_t tc3_packed_bwd_bytes(int k_in);
 int tc3_pack_bwd(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
-int tc3_ln_bwd(const float*, int, const float*, const float*, int, float*, cudaStream_t);
+int tc3_ln_bwd(const float*, int, const float*, const float*, int, float*, float*, cudaStream_t);
+size_t tc3_wgrad_workspace_floats(int k_in);
+int tc3_wgrad(const fvgn_mlp_t*, int, const float*, int, const float*, const float*, const int32_t*, int, const float*, int, const float*,
+              const float*, float*, float*, cudaStream_t);
 int tc3_dgrad(const fvgn_mlp_t*, const float*, int, int, float*, float*, int, const float*, int, cudaStream_t);
 
 size_t tc_packed_bytes(int k_in);
@@ -157,9 +160,19 @@ extern "C" int fvgn_mlp_pack_bf16x3_bwd(const fvgn_mlp_t* mlp, void* packed, siz
   return tc3_pack_bwd(mlp, packed, packed_bytes, as_stream(stream));
 }
 
-extern "C" int fvgn_ln_bwd(const float* d_out, int ld_dout, const float* z_save, const float* ln_w, int rows, float* dz, fvgn_stream_t stream) {
+extern "C" int fvgn_ln_bwd(const float* d_out, int ld_dout, const float* z_save, const float* ln_w, int rows, float* dz, float* gxhat,
+                           fvgn_stream_t stream) {
   if (int e = check_device()) return e;
-  return tc3_ln_bwd(d_out, ld_dout, z_save, ln_w, rows, dz, as_stream(stream));
+  return tc3_ln_bwd(d_out, ld_dout, z_save, ln_w, rows, dz, gxhat, as_stream(stream));
+}
+
+extern "C" size_t fvgn_mlp_wgrad_x3_workspace_floats(int k_in) { return tc3_wgrad_workspace_floats(k_in); }
+
+extern "C" int fvgn_mlp_wgrad_x3(const fvgn_mlp_t* mlp, int mode, const float* in, int ld_in, const float* src0, const float* src1,
+                                 const int32_t* idx, int rows, const float* d_out, int ld_dout, const float* dz, const float* gxhat,
+                                 float* grads, float* workspace, fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  return tc3_wgrad(mlp, mode, in, ld_in, src0, src1, idx, rows, d_out, ld_dout, dz, gxhat, grads, workspace, as_stream(stream));
 }
 
 extern "C" int fvgn_mlp_dgrad_x3(const fvgn_mlp_t* mlp, const float* dz, int ld_dz, int rows, float* da, float* dA, int ld_dA,

@@ -788,7 +788,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
 // LayerNorm backward of a row block: dz = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)), xhat from the saved z3.
 // One warp per row (4 columns per lane); the affine-parameter gradients are formed by the weight-gradient kernel.
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d_out, int ld_dout, const float* __restrict__ zsave,
-                                                     const float* __restrict__ gamma, int rows, float* __restrict__ dz) {
+                                                     const float* __restrict__ gamma, int rows, float* __restrict__ dz,
+                                                     float* __restrict__ gxhat /*[rows,128] = d_out * xhat (for dLN_w) or NULL*/) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float4 z = ldg4(zsave + (size_t)row * 384 + 256 + lane * 4);
@@ -809,6 +810,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) { m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o); }
   m1 *= (1.0f / 128.0f); m2 *= (1.0f / 128.0f);
+  if (gxhat) *reinterpret_cast<float4*>(gxhat + (size_t)row * 128 + lane * 4) = make_float4(g.x * x0, g.y * x1, g.z * x2, g.w * x3v);
   *reinterpret_cast<float4*>(dz + (size_t)row * 128 + lane * 4) =
       make_float4(rstd * (h0 - m1 - x0 * m2), rstd * (h1 - m1 - x1 * m2), rstd * (h2 - m1 - x2 * m2), rstd * (h3 - m1 - x3v * m2));
 }
@@ -833,6 +835,241 @@ __global__ void pack_tiles3_t_kernel(const float* __restrict__ W, int ldw, int n
   *reinterpret_cast<uint4*>(out + off) = q0;
   *reinterpret_cast<uint4*>(out + TILE_BYTES + off) = q1;
   *reinterpret_cast<uint4*>(out + 2 * TILE_BYTES + off) = q2;
+}
+
+// =====================================================================================================================
+// Weight gradients of one MLP on the tensor cores (training with the bf16x3 forward):
+//   dW3 = dz^T . h2      dW2 = da2^T . h1      dW1[:, 128 s ..] = da1^T . A[:, 128 s ..]        (sums over the rows)
+// Both operands of P^T . Q are stored the way they come, [row][feature] (one 128-byte row per 64 features), and read by the MMA as
+// MN-MAJOR operands (K = rows), 3-way split as everywhere in this mode.  A "job" is one 128 x 128 output block (dW3, dW2, one
+// 128-column segment of dW1); CTA b works on job b % njobs over row range b / njobs, accumulating in ONE TMEM accumulator over all
+// its 64-row chunks — no read-modify-write of partial gradients in memory (the FFMA kernel's cost) — and writes its partial block
+// once; wgrad_reduce_kernel sums the ranges in a fixed order (deterministic).
+constexpr int WG_CHUNK = 64;                 // rows per K chunk
+constexpr int WG_HALF_BYTES = WG_CHUNK * 128;  // one [64 rows][64 features] bf16 tile
+constexpr int WG_MAT_BYTES = 6 * WG_HALF_BYTES;  // 3 splits x 2 feature halves = 48 KB
+constexpr int WG_STAGE_BYTES = 2 * WG_MAT_BYTES;  // P and Q
+constexpr int WG_STAGES = 2;
+constexpr int WG_NTHREADS = (4 + 8 + 1) * 32;  // 4 epilogue warps, 8 producer warps, 1 MMA warp
+
+struct WgParams {
+  int mode, rows, k_in, n_out, njobs, nranges, chunks_per_range, nchunks;
+  const float* dz; int ld_dz;   // gradient behind the LayerNorm [rows, n_out]
+  const float* da;              // [rows, 256] = da2 | da1
+  const float* zsave;           // [rows, 384]
+  const float* in; int ld_in;   // ROWS: layer input
+  const float* src0; const float* src1; const int32_t* idx;  // CELL / EDGE: as the forward
+  float* part;                  // [njobs][nranges][128 * 128]
+};
+
+// MN-major SWIZZLE_128B operand descriptor: 64 features per 128-byte row, 8-row groups 1024 B apart (SBO), the second 64-feature
+// block of the operand one tile (8 KB) further (LBO)
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(WG_HALF_BYTES >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+constexpr uint32_t IDESC_BF16_MN_MN = IDESC_BF16_M128_N128 | (1u << 15) | (1u << 16);
+
+// 4 consecutive fp32 (features 4*hl.. of one 64-feature half) -> row r of the three split tiles of a matrix block
+__device__ __forceinline__ void st_wg_f4(unsigned char* mat, int half, int r, int hl, float4 v) {
+  const uint32_t off = (uint32_t)half * WG_HALF_BYTES + (uint32_t)r * 128u + ((((uint32_t)hl >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)hl & 1u) * 8u;
+  uint2 q0, q1, q2;
+  split3_pair(v.x, v.y, q0.x, q1.x, q2.x);
+  split3_pair(v.z, v.w, q0.y, q1.y, q2.y);
+  *reinterpret_cast<uint2*>(mat + off) = q0;
+  *reinterpret_cast<uint2*>(mat + 2 * WG_HALF_BYTES + off) = q1;
+  *reinterpret_cast<uint2*>(mat + 4 * WG_HALF_BYTES + off) = q2;
+}
+
+__global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sBar = smem + WG_STAGES * WG_STAGE_BYTES;
+  const uint32_t bar0 = smem_u32(sBar);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };  // FULL[2], EMPTY[2], DONE
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sBar + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int job = (int)blockIdx.x % p.njobs, range = (int)blockIdx.x / p.njobs;
+  const int c0 = range * p.chunks_per_range;
+  const int nch = max(0, min(p.chunks_per_range, p.nchunks - c0));
+
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) { printf("fvgn wgrad_tc3: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(BAR(i), 8); mbar_init(BAR(2 + i), 1); }
+    mbar_init(BAR(4), 1);
+    fence_mbar_init();
+  }
+  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 12) {
+    // ================================================================= producers: P (gradient rows) and Q (activation rows) chunks
+    const int ptid = tid - 128;
+    const int hw = ptid >> 4, hl = ptid & 15;  // rows hw + 16 i of the chunk, features 4 hl.. of each half
+    const int seg = job - 2;
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+      const int row0 = (c0 + c) * WG_CHUNK;
+      float4 pv[4][2], qv[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int g = row0 + hw + 16 * i;
+        const bool ok = g < p.rows;
+        const int gc = min(g, p.rows - 1);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int col = 64 * hh + 4 * hl;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+          if (ok) {
+            // ---- P: dz (job 0), da2 (job 1), da1 (jobs >= 2)
+            if (job == 0) {
+              if (p.n_out == 128 && (p.ld_dz & 3) == 0) a = ldg4(p.dz + (size_t)gc * p.ld_dz + col);
+              else {
+                float t[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t[j] = (col + j < p.n_out) ? p.dz[(size_t)gc * p.ld_dz + col + j] : 0.f;
+                a = make_float4(t[0], t[1], t[2], t[3]);
+              }
+            } else {
+              a = ldg4(p.da + (size_t)gc * 256 + (job == 1 ? 0 : 128) + col);
+            }
+            // ---- Q: h2 = silu(z2) (job 0), h1 = silu(z1) (job 1), layer-input segment (jobs >= 2)
+            if (job < 2) {
+              const float4 z = ldg4(p.zsave + (size_t)gc * 384 + (job == 0 ? 128 : 0) + col);
+              b = make_float4(silu_x3(z.x), silu_x3(z.y), silu_x3(z.z), silu_x3(z.w));
+            } else if (p.mode == TC_EDGE) {
+              if (seg < 2) b = ldg4(p.src0 + (size_t)__ldg(p.idx + (size_t)seg * p.rows + gc) * 128 + col);
+              else b = ldg4(p.src1 + (size_t)gc * 128 + col);
+            } else if (p.mode == TC_CELL) {
+              if (seg == 0) b = ldg4(p.src0 + (size_t)gc * 128 + col);
+              else if (hh == 0) {
+                const int C = p.rows;
+                const int n0 = __ldg(p.idx + gc), n1 = __ldg(p.idx + (size_t)C + gc), n2 = __ldg(p.idx + 2 * (size_t)C + gc);
+                const float4 u = ldg4(p.src1 + (size_t)n0 * 64 + 4 * hl), v = ldg4(p.src1 + (size_t)n1 * 64 + 4 * hl),
+                             w = ldg4(p.src1 + (size_t)n2 * 64 + 4 * hl);
+                b = make_float4(__fdiv_rn(__fadd_rn(__fadd_rn(u.x, v.x), w.x), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(u.y, v.y), w.y), 3.0f),
+                                __fdiv_rn(__fadd_rn(__fadd_rn(u.z, v.z), w.z), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(u.w, v.w), w.w), 3.0f));
+              }
+            } else {
+              float t[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int k = 128 * seg + col + j;
+                t[j] = (k < p.k_in) ? p.in[(size_t)gc * p.ld_in + k] : 0.f;
+              }
+              b = make_float4(t[0], t[1], t[2], t[3]);
+            }
+          }
+          pv[i][hh] = a; qv[i][hh] = b;
+        }
+      }
+      const uint32_t stg = (uint32_t)c % WG_STAGES;
+      if (c >= WG_STAGES) mbar_wait(BAR(2 + stg), (((uint32_t)c / WG_STAGES) - 1) & 1, 1);
+      unsigned char* P = smem + stg * WG_STAGE_BYTES;
+      unsigned char* Q = P + WG_MAT_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          st_wg_f4(P, hh, hw + 16 * i, hl, pv[i][hh]);
+          st_wg_f4(Q, hh, hw + 16 * i, hl, qv[i][hh]);
+        }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(stg));
+    }
+  } else if (warp == 12) {
+    // ================================================================= MMA issuer: D[o][i] += sum_rows P[row][o] Q[row][i]
+    if (lane == 0) {
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        const uint32_t stg = (uint32_t)c % WG_STAGES;
+        mbar_wait(BAR(stg), ((uint32_t)c / WG_STAGES) & 1, 4);
+        tc_fence_after();
+        const uint32_t pb = smem_u32(smem + stg * WG_STAGE_BYTES), qb = pb + WG_MAT_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < WG_CHUNK / 16; ++kk)
+#pragma unroll
+          for (int q = 0; q < 6; ++q)
+            umma_bf16(tmem_base, umma_desc_mn(pb + prod_a(q) * 2 * WG_HALF_BYTES + kk * 2048), umma_desc_mn(qb + prod_w(q) * 2 * WG_HALF_BYTES + kk * 2048),
+                      IDESC_BF16_MN_MN, (c | kk | q) != 0);
+        umma_commit(BAR(2 + stg));
+      }
+      umma_commit(BAR(4));
+    }
+    __syncwarp();
+  } else {
+    // ================================================================= epilogue warps 0-3: lane = output row o
+    float* dst = p.part + ((size_t)job * p.nranges + range) * 16384 + (size_t)(32 * warp + lane) * 128;
+    if (nch > 0) {
+      mbar_wait(BAR(4), 0, 8);
+      tc_fence_after();
+    }
+    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * warp) << 16);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      if (nch > 0) {
+        tmem_ld32_issue(t_lane + 32 * c, r);
+        tmem_ld_wait(r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(dst + 32 * c + 4 * j) =
+            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// grads <- sum over row ranges (fixed order) of the per-CTA partial blocks, laid out as dW1[128, k_in] | dW2[128,128] | dW3[128,128]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int njobs, int nranges, int k_in, float* __restrict__ grads) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (job, o, i)
+  if (idx >= njobs * 16384) return;
+  const int job = idx >> 14, o = (idx >> 7) & 127, i = idx & 127;
+  float s = 0.f;
+  for (int r = 0; r < nranges; ++r) s += part[((size_t)job * nranges + r) * 16384 + o * 128 + i];
+  if (job == 0) grads[(size_t)128 * k_in + 16384 + o * 128 + i] = s;       // dW3
+  else if (job == 1) grads[(size_t)128 * k_in + o * 128 + i] = s;          // dW2
+  else {
+    const int k = 128 * (job - 2) + i;
+    if (k < k_in) grads[(size_t)o * k_in + k] = s;                          // dW1
+  }
+}
+
+// deterministic column sums of up to four [rows, ncols] fp32 matrices: blockIdx.y = source, blockIdx.x = row range, thread = column
+struct ColsumSrc { const float* src; int ld, ncols, dst_off; };
+struct ColsumParams { ColsumSrc s[4]; int rows, nb; float* partial; float* grads; };
+__global__ void __launch_bounds__(256) colsum_kernel(const ColsumParams p) {
+  const ColsumSrc cs = p.s[blockIdx.y];
+  const int c = threadIdx.x;
+  if (cs.src == nullptr || c >= cs.ncols) return;
+  const int per = (p.rows + p.nb - 1) / p.nb, r0 = blockIdx.x * per, r1 = min(p.rows, r0 + per);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    a0 += cs.src[(size_t)r * cs.ld + c]; a1 += cs.src[(size_t)(r + 1) * cs.ld + c];
+    a2 += cs.src[(size_t)(r + 2) * cs.ld + c]; a3 += cs.src[(size_t)(r + 3) * cs.ld + c];
+  }
+  for (; r < r1; ++r) a0 += cs.src[(size_t)r * cs.ld + c];
+  p.partial[((size_t)blockIdx.y * p.nb + blockIdx.x) * 256 + c] = (a0 + a1) + (a2 + a3);
+}
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const ColsumParams p) {
+  const ColsumSrc cs = p.s[blockIdx.x];
+  const int c = threadIdx.x;
+  if (cs.src == nullptr || c >= cs.ncols) return;
+  float s = 0.f;
+  for (int b = 0; b < p.nb; ++b) s += p.partial[((size_t)blockIdx.x * p.nb + b) * 256 + c];
+  p.grads[cs.dst_off + c] = s;
 }
 
 // W [n_valid, k_valid] fp32 row-major -> steps [kt][3 splits][128 rows][64 k] bf16, each sub-tile a byte image of the swizzled layout
@@ -976,11 +1213,11 @@ int tc3_pack_bwd(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t s
   return 0;
 }
 
-int tc3_ln_bwd(const float* d_out, int ld_dout, const float* z_save, const float* ln_w, int rows, float* dz, cudaStream_t st) {
+int tc3_ln_bwd(const float* d_out, int ld_dout, const float* z_save, const float* ln_w, int rows, float* dz, float* gxhat, cudaStream_t st) {
   FVGN_CHECK_ARG(d_out && z_save && ln_w && dz, "NULL pointer");
   FVGN_CHECK_ARG((ld_dout & 3) == 0, "d_out row stride must be a multiple of 4 floats");
   if (rows <= 0) return 0;
-  x3::ln_bwd_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(d_out, ld_dout, z_save, ln_w, rows, dz);
+  x3::ln_bwd_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(d_out, ld_dout, z_save, ln_w, rows, dz, gxhat);
   FVGN_LAUNCH_CHECK();
   return 0;
 }
@@ -1008,6 +1245,74 @@ int tc3_dgrad(const fvgn_mlp_t* m, const float* dz, int ld_dz, int rows, float* 
   const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
   dgrad_tc3_kernel<<<grid, NTHREADS, L.total, st>>>(p);
   FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+
+// ---- weight gradients on the tensor cores
+static int wg_njobs(int k_in) { return 2 + (k_in + 127) / 128; }
+static int wg_nranges(int k_in, int rows) {
+  const int nchunks = cdiv(rows, x3::WG_CHUNK), by_sm = sm_count() / wg_njobs(k_in);
+  return nchunks < by_sm ? nchunks : by_sm;
+}
+constexpr int WG_COLSUM_NB = 64;
+size_t tc3_wgrad_workspace_floats(int k_in) {
+  return (size_t)wg_njobs(k_in) * (size_t)(sm_count() / wg_njobs(k_in)) * 16384 + (size_t)4 * WG_COLSUM_NB * 256;
+}
+
+int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const float* src0, const float* src1, const int32_t* idx, int rows,
+              const float* d_out, int ld_dout, const float* dz, const float* gxhat, float* grads, float* workspace, cudaStream_t st) {
+  using namespace x3;
+  FVGN_CHECK_ARG(m && d_out && grads && workspace, "NULL pointer");
+  FVGN_CHECK_ARG(m->z_save && m->da_in, "the tensor-core weight gradients need fvgn_mlp_t.z_save and .da_in (fvgn_mlp_dgrad_x3)");
+  FVGN_CHECK_ARG(m->k_in >= 1 && m->k_in <= 384 && m->n_out >= 1 && m->n_out <= 128, "bad mlp dims");
+  FVGN_CHECK_ARG(mode == TC_ROWS ? in != nullptr : (src0 && src1 && idx), "layer input pointers");
+  FVGN_CHECK_ARG(!m->ln_w || (dz && gxhat), "an MLP with LayerNorm needs dz and gxhat from fvgn_ln_bwd");
+  FVGN_CHECK_ARG(rows > 0, "rows must be > 0");
+  WgParams p{};
+  p.mode = mode; p.rows = rows; p.k_in = m->k_in; p.n_out = m->n_out;
+  p.njobs = wg_njobs(m->k_in); p.nchunks = cdiv(rows, WG_CHUNK); p.nranges = wg_nranges(m->k_in, rows);
+  p.chunks_per_range = cdiv(p.nchunks, p.nranges);
+  p.dz = m->ln_w ? dz : d_out; p.ld_dz = m->ln_w ? 128 : ld_dout;
+  p.da = m->da_in; p.zsave = m->z_save; p.in = in; p.ld_in = ld_in; p.src0 = src0; p.src1 = src1; p.idx = idx;
+  p.part = workspace;
+  const int smem_bytes = WG_STAGES * WG_STAGE_BYTES + 256;
+  static bool configured = false;
+  if (!configured) {
+    FVGN_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  wgrad_tc3_kernel<<<p.njobs * p.nranges, WG_NTHREADS, smem_bytes, st>>>(p);
+  FVGN_LAUNCH_CHECK();
+  wgrad_reduce_kernel<<<cdiv(p.njobs * 16384, 256), 256, 0, st>>>(workspace, p.njobs, p.nranges, m->k_in, grads);
+  FVGN_LAUNCH_CHECK();
+  // bias / LayerNorm-parameter gradients: deterministic column sums.  grads tail: db1 | db2 | db3 | dLN_w | dLN_b
+  const int vec0 = 128 * m->k_in + 2 * 16384;
+  ColsumParams c{};
+  c.rows = rows; c.nb = rows < WG_COLSUM_NB ? rows : WG_COLSUM_NB; c.grads = grads;
+  c.partial = workspace + (size_t)p.njobs * (size_t)(sm_count() / p.njobs) * 16384;
+  c.s[0] = {m->da_in, 256, 128, vec0 + 128};            // db2 = colsum(da2)
+  c.s[1] = {m->da_in + 128, 256, 128, vec0};            // db1 = colsum(da1)
+  if (m->ln_w) {
+    c.s[2] = {dz, 128, 128, vec0 + 256};                // db3 = colsum(dz)
+    c.s[3] = {gxhat, 128, 128, vec0 + 384};             // dLN_w = colsum(d_out * xhat)
+  } else {
+    c.s[2] = {d_out, ld_dout, m->n_out, vec0 + 256};    // db3 = colsum(d_out)
+    c.s[3] = {nullptr, 0, 0, 0};
+  }
+  colsum_kernel<<<dim3(c.nb, 4), 256, 0, st>>>(c);
+  FVGN_LAUNCH_CHECK();
+  colsum_reduce_kernel<<<4, 256, 0, st>>>(c);
+  FVGN_LAUNCH_CHECK();
+  if (m->ln_w) {  // dLN_b = colsum(d_out)
+    ColsumParams c2{};
+    c2.rows = rows; c2.nb = c.nb; c2.grads = grads; c2.partial = c.partial;
+    c2.s[0] = {d_out, ld_dout, 128, vec0 + 512};
+    colsum_kernel<<<dim3(c2.nb, 1), 256, 0, st>>>(c2);
+    FVGN_LAUNCH_CHECK();
+    colsum_reduce_kernel<<<1, 256, 0, st>>>(c2);
+    FVGN_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -481,13 +481,34 @@ def _bwd_buffers(mlp: MlpRef, device):
 
 
 def ln_bwd(d_out, z_saved, ln_w):
-    """dz[rows,128]: LayerNorm backward of d_out with the statistics of the saved z3 (input of fvgn_mlp_dgrad_x3)"""
+    """LayerNorm backward of d_out with the statistics of the saved z3: (dz[rows,128] for fvgn_mlp_dgrad_x3, d_out * xhat [rows,128]
+    whose column sums are dLN_w)"""
     _req(d_out, torch.float32, "d_out", 2), _cf(z_saved, "z_saved"), _cf(ln_w, "ln_w")
     rows = d_out.shape[0]
     dz = torch.empty((rows, 128), dtype=torch.float32, device=d_out.device)
+    gxhat = torch.empty((rows, 128), dtype=torch.float32, device=d_out.device)
     _count(1)
-    check(_lib.lib().fvgn_ln_bwd(_p(d_out), _ld(d_out), _p(z_saved), _p(ln_w), rows, _p(dz), _stream()), "ln_bwd")
-    return dz
+    check(_lib.lib().fvgn_ln_bwd(_p(d_out), _ld(d_out), _p(z_saved), _p(ln_w), rows, _p(dz), _p(gxhat), _stream()), "ln_bwd")
+    return dz, gxhat
+
+
+def mlp_wgrad_x3(mlp: MlpRef, mode, d_out, dz, gxhat, z_saved, da, x=None, src0=None, src1=None, idx=None):
+    """all parameter gradients of one MLP on the tensor cores (MN-major P^T . Q products, deterministic).  mode 0: x = layer input
+    [rows,k_in]; 1 (CellBlock): src0 = x, src1 = node_agg, idx = cells_node_T; 2 (EdgeBlock): src0 = x', src1 = e, idx = neighbour_cell"""
+    _req(d_out, torch.float32, "d_out", 2)
+    rows = d_out.shape[0]
+    L = _lib.lib()
+    grads = torch.empty(L.fvgn_mlp_grad_floats(mlp.k_in), dtype=torch.float32, device=d_out.device)
+    ws = torch.empty(L.fvgn_mlp_wgrad_x3_workspace_floats(mlp.k_in), dtype=torch.float32, device=d_out.device)
+    if mode == 0:
+        _req(x, torch.float32, "x", 2)
+    else:
+        _cf(src0, "src0"), _cf(src1, "src1"), _ci(idx, "idx")
+    _count(4 if dz is None else 6)
+    with _zsave(mlp, z_saved, rows, da):
+        check(L.fvgn_mlp_wgrad_x3(C.byref(mlp.struct), mode, _p(x), _ld(x) if x is not None else 0, _p(src0), _p(src1), _p(idx), rows, _p(d_out),
+                                  _ld(d_out), _p(dz), _p(gxhat), _p(grads), _p(ws), _stream()), "mlp_wgrad_x3")
+    return _mlp_grad_views(mlp, grads)
 
 
 def mlp_dgrad_x3(mlp: MlpRef, dz, z_saved, want_dA=True, dA_base=None):

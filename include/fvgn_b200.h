@@ -230,7 +230,14 @@ FVGN_API int fvgn_edge_block_bwd(const fvgn_mlp_t* mlp, const float* x_prime, co
 FVGN_API size_t fvgn_mlp_packed_x3_bwd_bytes(int k_in);
 FVGN_API int fvgn_mlp_pack_bf16x3_bwd(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream);
 FVGN_API int fvgn_ln_bwd(const float* d_out, int ld_dout, const float* z_save /*[rows,384]*/, const float* ln_w, int rows, float* dz /*[rows,128]*/,
-                         fvgn_stream_t stream);
+                         float* gxhat /*[rows,128] = d_out * xhat, or NULL*/, fvgn_stream_t stream);
+/*   fvgn_mlp_wgrad_x3:  all parameter gradients of the MLP (same `grads` layout as fvgn_mlp_rows_bwd) from dz / gxhat (fvgn_ln_bwd),
+ *                       mlp->da_in (fvgn_mlp_dgrad_x3), mlp->z_save and the layer inputs (mode 0: in/ld_in; 1 CellBlock: x, node_agg,
+ *                       cells_node_T; 2 EdgeBlock: x', e, neighbour_cell): dW = P^T . Q as MN-major tcgen05 MMAs, deterministic. */
+FVGN_API size_t fvgn_mlp_wgrad_x3_workspace_floats(int k_in);
+FVGN_API int fvgn_mlp_wgrad_x3(const fvgn_mlp_t* mlp, int mode, const float* in, int ld_in, const float* src0, const float* src1,
+                               const int32_t* idx, int rows, const float* d_out, int ld_dout, const float* dz, const float* gxhat,
+                               float* grads, float* workspace, fvgn_stream_t stream);
 FVGN_API int fvgn_mlp_dgrad_x3(const fvgn_mlp_t* mlp, const float* dz, int ld_dz, int rows, float* da /*[rows,256]*/, float* dA /*or NULL*/,
                                int ld_dA, const float* dA_base /*or NULL*/, int ld_base, fvgn_stream_t stream);
 
