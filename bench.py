@@ -397,6 +397,26 @@ def training_measure(args, rank, world, dev, meshes, dist):
 
     steps = max(2, min(args.steps, args.train_steps))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    graphed = None
+    if args.train_graph:
+        # the same step captured into one CUDA graph (fvgn_b200.GraphedTrainStep): no Python / launch overhead per step
+        try:
+            opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=True)
+            gn_s, ge_s, gc_s = _shallow(gn0), _shallow(ge0), _shallow(gc0)
+            gn_s.x = node_dev.clone()
+            graphed = fv.GraphedTrainStep(model, opt, p, gn_s, ge_s, gc_s, RHO, MU, DT, all_reduce=bucket.all_reduce_mean_ if world > 1 else None)
+
+            def tstep(h2d):  # noqa: F811
+                if h2d:
+                    graphed.load(node_host)
+                loss4 = graphed.step()
+                if h2d:
+                    loss_host[:4].copy_(loss4, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                return (loss4[0:1],)
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] CUDA-graph training step unavailable ({type(e).__name__}: {e}); eager step", file=sys.stderr)
+            graphed = None
     for _ in range(3):
         tstep(False)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -408,7 +428,7 @@ def training_measure(args, rank, world, dev, meshes, dist):
         tstep(False)
         ev[k][1].record()
     barrier()
-    launches = ops.LAUNCHES - l0
+    launches = ops.LAUNCHES - l0 if graphed is None else graphed.launches_per_step * steps
     ms = sum(a.elapsed_time(b) for a, b in ev)
     tstep(True)
     barrier()
@@ -432,7 +452,8 @@ def training_measure(args, rank, world, dev, meshes, dist):
                     "note": "pinned node fields H2D + loss D2H + host sync every step"},
             "gpu_launches": int(launches), "final_loss": float(loss[0]),
             "parallelism": f"dp{world} over mesh graphs, one flat fp32 gradient all-reduce (8.84 MB) per step" if world > 1 else "single GPU",
-            "step": "train_datapreprocessing + FVGN.forward(train) + compute_FVM_loss + backward + grad all-reduce + AdamW"}
+            "step": "train_datapreprocessing + FVGN.forward(train) + compute_FVM_loss + backward + grad all-reduce + AdamW",
+            "cuda_graph": graphed is not None}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
@@ -521,6 +542,7 @@ def main():
     ap.add_argument("--no-training", action="store_true", help="skip the training graphs/s leg")
     ap.add_argument("--no-strict-leg", action="store_true", help="skip the strict-FFMA comparison leg")
     ap.add_argument("--no-config0", action="store_true", help="skip the batch-1 rollout latency leg (configs[0])")
+    ap.add_argument("--train-graph", type=int, default=1, help="1: time the training step replayed from one CUDA graph; 0: eager")
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--sweep", default="mesh1m:bf16", help="<workload>:<math> of the kernel roofline sweep leg, or 'none'")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -110,3 +110,37 @@ def test_mlp_rows_backward_shapes(fv):
         for gg, w in zip(grads, want):
             assert H.rel_l2(gg.cpu(), w) < GTOL, (k_in, n_out, gg.shape, H.rel_l2(gg.cpu(), w))
         assert H.rel_l2(d_in.cpu(), x.grad) < GTOL
+
+
+def test_graphed_train_step_matches_eager_steps(fv, golden):
+    """the whole training step replayed from one CUDA graph (fvgn_b200.GraphedTrainStep) == the eager loop of train.py:150-225
+    (fixed noise / flip draws so that both see the same pre-processed batch)"""
+    g = golden("train_tiny.npz")
+    f = golden("fwd_tiny.npz")
+    p = H.params(loss="global_mean_sum")
+    pre = dict(cell_noise=dev(g["noise"]), flip_keep=dev(g["flip"]))
+
+    def batch():
+        return fv.dataset.collate([_graphs(fv, f, "tab.", "velocity", "pressure", pair=1), _graphs(fv, f, "tab1.", "velocity1", "pressure1", pair=0)])
+
+    model = _model(fv, f).train().set_math_mode("bf16x3")
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=True)
+    gn0, ge0, gc0 = batch()
+    step = fv.GraphedTrainStep(model, opt, p, gn0, ge0, gc0, H.RHO, H.MU, H.DT, preprocess_kwargs=pre, warmup=2)  # 2 real steps (capture records, it does not run)
+    replayed = [float(step.step()[0]) for _ in range(3)]                                                           # steps 3..5
+    model2 = _model(fv, f).train().set_math_mode("bf16x3")
+    opt2 = torch.optim.AdamW(model2.parameters(), lr=1e-3, capturable=True)
+    eager = []
+    for _ in range(5):
+        gn, ge, gc = batch()
+        gn, ge, gc, mi, mb = fv.dataset.train_datapreprocessing([gn, ge, gc], **pre)
+        opt2.zero_grad()
+        out = model2(graph=gc, graph_edge=ge, graph_node=gn, rho=H.RHO, mu=H.MU, dt=H.DT, edge_one_hot=9, cell_one_hot=0)
+        loss = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=out[3],
+                                   target_face_uvp_normalized=out[4], predicted_delta_u=out[1], target_delta_u=out[2])
+        loss[0].backward()
+        opt2.step()
+        eager.append(float(loss[0]))
+    np.testing.assert_allclose(replayed, eager[2:5], rtol=1e-5)
+    for (k, a), (_, b) in zip(model.named_parameters(), model2.named_parameters()):
+        assert H.rel_l2(a.detach().cpu(), b.detach().cpu()) < 1e-5, k
