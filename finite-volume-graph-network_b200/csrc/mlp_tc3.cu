@@ -904,16 +904,16 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 4 && warp < 12) {
-    // ================================================================= producers: P (gradient rows) and Q (activation rows) chunks
+    // ================================================================= producers: P (gradient rows) and Q (activation rows) chunks,
+    // half a chunk (32 rows) per step with two register buffers: the next step's loads are in flight while this one is split / stored
     const int ptid = tid - 128;
-    const int hw = ptid >> 4, hl = ptid & 15;  // rows hw + 16 i of the chunk, features 4 hl.. of each half
+    const int hw = ptid >> 4, hl = ptid & 15;  // rows 32 half + hw + 16 i (i = 0,1) of the chunk, features 4 hl.. of each 64-feature half
     const int seg = job - 2;
-#pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
-      const int row0 = (c0 + c) * WG_CHUNK;
-      float4 pv[4][2], qv[4][2];
+    const int S = 2 * nch;
+    auto load = [&](int s, float4 (*pv)[2], float4 (*qv)[2]) {
+      const int row0 = (c0 + (s >> 1)) * WG_CHUNK + 32 * (s & 1);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         const int g = row0 + hw + 16 * i;
         const bool ok = g < p.rows;
         const int gc = min(g, p.rows - 1);
@@ -934,10 +934,9 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
             } else {
               a = ldg4(p.da + (size_t)gc * 256 + (job == 1 ? 0 : 128) + col);
             }
-            // ---- Q: h2 = silu(z2) (job 0), h1 = silu(z1) (job 1), layer-input segment (jobs >= 2)
+            // ---- Q: z2 / z1 (SiLU applied at store time: jobs 0, 1), layer-input segment (jobs >= 2)
             if (job < 2) {
-              const float4 z = ldg4(p.zsave + (size_t)gc * 384 + (job == 0 ? 128 : 0) + col);
-              b = make_float4(silu_x3(z.x), silu_x3(z.y), silu_x3(z.z), silu_x3(z.w));
+              b = ldg4(p.zsave + (size_t)gc * 384 + (job == 0 ? 128 : 0) + col);
             } else if (p.mode == TC_EDGE) {
               if (seg < 2) b = ldg4(p.src0 + (size_t)__ldg(p.idx + (size_t)seg * p.rows + gc) * 128 + col);
               else b = ldg4(p.src1 + (size_t)gc * 128 + col);
@@ -964,20 +963,38 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
           pv[i][hh] = a; qv[i][hh] = b;
         }
       }
+    };
+    auto store = [&](int s, float4 (*pv)[2], float4 (*qv)[2]) {
+      const int c = s >> 1, half = s & 1;
       const uint32_t stg = (uint32_t)c % WG_STAGES;
-      if (c >= WG_STAGES) mbar_wait(BAR(2 + stg), (((uint32_t)c / WG_STAGES) - 1) & 1, 1);
+      if (half == 0 && c >= WG_STAGES) mbar_wait(BAR(2 + stg), (((uint32_t)c / WG_STAGES) - 1) & 1, 1);
       unsigned char* P = smem + stg * WG_STAGE_BYTES;
       unsigned char* Q = P + WG_MAT_BYTES;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          st_wg_f4(P, hh, hw + 16 * i, hl, pv[i][hh]);
-          st_wg_f4(Q, hh, hw + 16 * i, hl, qv[i][hh]);
+          const int r = 32 * half + hw + 16 * i;
+          float4 b = qv[i][hh];
+          if (job < 2) {  // Q = silu(z) of the rows that exist (rows past the end were loaded as zeros: silu(0) = 0)
+            b = make_float4(silu_x3(b.x), silu_x3(b.y), silu_x3(b.z), silu_x3(b.w));
+          }
+          st_wg_f4(P, hh, r, hl, pv[i][hh]);
+          st_wg_f4(Q, hh, r, hl, b);
         }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(stg));
+      if (half == 1) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(stg));
+      }
+    };
+    float4 pa[2][2], qa[2][2], pb[2][2], qb[2][2];
+#pragma unroll 1
+    for (int s = -1; s < S; s += 2) {
+      if (s + 1 < S) load(s + 1, pa, qa);
+      if (s >= 0) store(s, pb, qb);
+      if (s + 2 < S) load(s + 2, pb, qb);
+      if (s + 1 < S) store(s + 1, pa, qa);
     }
   } else if (warp == 12) {
     // ================================================================= MMA issuer: D[o][i] += sum_rows P[row][o] Q[row][i]
@@ -1067,9 +1084,14 @@ __global__ void __launch_bounds__(256) colsum_reduce_kernel(const ColsumParams p
   const ColsumSrc cs = p.s[blockIdx.x];
   const int c = threadIdx.x;
   if (cs.src == nullptr || c >= cs.ncols) return;
-  float s = 0.f;
-  for (int b = 0; b < p.nb; ++b) s += p.partial[((size_t)blockIdx.x * p.nb + b) * 256 + c];
-  p.grads[cs.dst_off + c] = s;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four interleaved partial sums, combined in a fixed order
+  int b = 0;
+  for (; b + 4 <= p.nb; b += 4) {
+    a0 += p.partial[((size_t)blockIdx.x * p.nb + b) * 256 + c]; a1 += p.partial[((size_t)blockIdx.x * p.nb + b + 1) * 256 + c];
+    a2 += p.partial[((size_t)blockIdx.x * p.nb + b + 2) * 256 + c]; a3 += p.partial[((size_t)blockIdx.x * p.nb + b + 3) * 256 + c];
+  }
+  for (; b < p.nb; ++b) a0 += p.partial[((size_t)blockIdx.x * p.nb + b) * 256 + c];
+  p.grads[cs.dst_off + c] = (a0 + a1) + (a2 + a3);
 }
 
 // W [n_valid, k_valid] fp32 row-major -> steps [kt][3 splits][128 rows][64 k] bf16, each sub-tile a byte image of the swizzled layout
@@ -1255,7 +1277,7 @@ static int wg_nranges(int k_in, int rows) {
   const int nchunks = cdiv(rows, x3::WG_CHUNK), by_sm = sm_count() / wg_njobs(k_in);
   return nchunks < by_sm ? nchunks : by_sm;
 }
-constexpr int WG_COLSUM_NB = 64;
+constexpr int WG_COLSUM_NB = 1024;  // row ranges of the column sums (partials summed in a fixed order)
 size_t tc3_wgrad_workspace_floats(int k_in) {
   return (size_t)wg_njobs(k_in) * (size_t)(sm_count() / wg_njobs(k_in)) * 16384 + (size_t)4 * WG_COLSUM_NB * 256;
 }
