@@ -1063,35 +1063,51 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int njobs, i
   }
 }
 
-// deterministic column sums of up to four [rows, ncols] fp32 matrices: blockIdx.y = source, blockIdx.x = row range, thread = column
+// deterministic column sums of up to five [rows, ncols <= 128] fp32 matrices: blockIdx.y = source, blockIdx.x = row range; a block is
+// 8 row-lanes x 128 columns, every thread keeps 4 independent partial sums (fixed combination order), the 8 row-lanes are combined
+// through shared memory in a fixed order, and colsum_reduce_kernel sums the row ranges in a fixed order.
 struct ColsumSrc { const float* src; int ld, ncols, dst_off; };
-struct ColsumParams { ColsumSrc s[4]; int rows, nb; float* partial; float* grads; };
-__global__ void __launch_bounds__(256) colsum_kernel(const ColsumParams p) {
+struct ColsumParams { ColsumSrc s[5]; int rows, nb; float* partial; float* grads; };
+__global__ void __launch_bounds__(1024) colsum_kernel(const ColsumParams p) {
+  __shared__ float sh[8][128];
   const ColsumSrc cs = p.s[blockIdx.y];
-  const int c = threadIdx.x;
-  if (cs.src == nullptr || c >= cs.ncols) return;
+  if (cs.src == nullptr) return;
+  const int c = threadIdx.x & 127, rl = threadIdx.x >> 7;  // column, row lane 0..7
   const int per = (p.rows + p.nb - 1) / p.nb, r0 = blockIdx.x * per, r1 = min(p.rows, r0 + per);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int r = r0;
-  for (; r + 4 <= r1; r += 4) {
-    a0 += cs.src[(size_t)r * cs.ld + c]; a1 += cs.src[(size_t)(r + 1) * cs.ld + c];
-    a2 += cs.src[(size_t)(r + 2) * cs.ld + c]; a3 += cs.src[(size_t)(r + 3) * cs.ld + c];
+  if (c < cs.ncols) {
+    int r = r0 + rl;
+    for (; r + 24 < r1; r += 32) {
+      a0 += cs.src[(size_t)r * cs.ld + c]; a1 += cs.src[(size_t)(r + 8) * cs.ld + c];
+      a2 += cs.src[(size_t)(r + 16) * cs.ld + c]; a3 += cs.src[(size_t)(r + 24) * cs.ld + c];
+    }
+    for (; r < r1; r += 8) a0 += cs.src[(size_t)r * cs.ld + c];
   }
-  for (; r < r1; ++r) a0 += cs.src[(size_t)r * cs.ld + c];
-  p.partial[((size_t)blockIdx.y * p.nb + blockIdx.x) * 256 + c] = (a0 + a1) + (a2 + a3);
+  sh[rl][c] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (rl == 0 && c < cs.ncols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sh[k][c];
+    p.partial[((size_t)blockIdx.y * p.nb + blockIdx.x) * 128 + c] = s;
+  }
 }
-__global__ void __launch_bounds__(256) colsum_reduce_kernel(const ColsumParams p) {
+__global__ void __launch_bounds__(1024) colsum_reduce_kernel(const ColsumParams p) {
+  __shared__ float sh[8][128];
   const ColsumSrc cs = p.s[blockIdx.x];
-  const int c = threadIdx.x;
-  if (cs.src == nullptr || c >= cs.ncols) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four interleaved partial sums, combined in a fixed order
-  int b = 0;
-  for (; b + 4 <= p.nb; b += 4) {
-    a0 += p.partial[((size_t)blockIdx.x * p.nb + b) * 256 + c]; a1 += p.partial[((size_t)blockIdx.x * p.nb + b + 1) * 256 + c];
-    a2 += p.partial[((size_t)blockIdx.x * p.nb + b + 2) * 256 + c]; a3 += p.partial[((size_t)blockIdx.x * p.nb + b + 3) * 256 + c];
+  if (cs.src == nullptr) return;
+  const int c = threadIdx.x & 127, rl = threadIdx.x >> 7;
+  float a = 0.f;
+  if (c < cs.ncols)
+    for (int b = rl; b < p.nb; b += 8) a += p.partial[((size_t)blockIdx.x * p.nb + b) * 128 + c];
+  sh[rl][c] = a;
+  __syncthreads();
+  if (rl == 0 && c < cs.ncols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sh[k][c];
+    p.grads[cs.dst_off + c] = s;
   }
-  for (; b < p.nb; ++b) a0 += p.partial[((size_t)blockIdx.x * p.nb + b) * 256 + c];
-  p.grads[cs.dst_off + c] = (a0 + a1) + (a2 + a3);
 }
 
 // W [n_valid, k_valid] fp32 row-major -> steps [kt][3 splits][128 rows][64 k] bf16, each sub-tile a byte image of the swizzled layout
@@ -1277,9 +1293,9 @@ static int wg_nranges(int k_in, int rows) {
   const int nchunks = cdiv(rows, x3::WG_CHUNK), by_sm = sm_count() / wg_njobs(k_in);
   return nchunks < by_sm ? nchunks : by_sm;
 }
-constexpr int WG_COLSUM_NB = 1024;  // row ranges of the column sums (partials summed in a fixed order)
+constexpr int WG_COLSUM_NB = 592;  // at most this many row ranges (>= 256 rows each) for the column sums
 size_t tc3_wgrad_workspace_floats(int k_in) {
-  return (size_t)wg_njobs(k_in) * (size_t)(sm_count() / wg_njobs(k_in)) * 16384 + (size_t)4 * WG_COLSUM_NB * 256;
+  return (size_t)wg_njobs(k_in) * (size_t)(sm_count() / wg_njobs(k_in)) * 16384 + (size_t)5 * WG_COLSUM_NB * 128;
 }
 
 int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const float* src0, const float* src1, const int32_t* idx, int rows,
@@ -1311,30 +1327,23 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
   // bias / LayerNorm-parameter gradients: deterministic column sums.  grads tail: db1 | db2 | db3 | dLN_w | dLN_b
   const int vec0 = 128 * m->k_in + 2 * 16384;
   ColsumParams c{};
-  c.rows = rows; c.nb = rows < WG_COLSUM_NB ? rows : WG_COLSUM_NB; c.grads = grads;
+  c.rows = rows; c.nb = cdiv(rows, 256) < WG_COLSUM_NB ? cdiv(rows, 256) : WG_COLSUM_NB; c.grads = grads;
   c.partial = workspace + (size_t)p.njobs * (size_t)(sm_count() / p.njobs) * 16384;
   c.s[0] = {m->da_in, 256, 128, vec0 + 128};            // db2 = colsum(da2)
   c.s[1] = {m->da_in + 128, 256, 128, vec0};            // db1 = colsum(da1)
   if (m->ln_w) {
     c.s[2] = {dz, 128, 128, vec0 + 256};                // db3 = colsum(dz)
     c.s[3] = {gxhat, 128, 128, vec0 + 384};             // dLN_w = colsum(d_out * xhat)
+    c.s[4] = {d_out, ld_dout, 128, vec0 + 512};         // dLN_b = colsum(d_out)
   } else {
     c.s[2] = {d_out, ld_dout, m->n_out, vec0 + 256};    // db3 = colsum(d_out)
     c.s[3] = {nullptr, 0, 0, 0};
+    c.s[4] = {nullptr, 0, 0, 0};
   }
-  colsum_kernel<<<dim3(c.nb, 4), 256, 0, st>>>(c);
+  colsum_kernel<<<dim3(c.nb, 5), 1024, 0, st>>>(c);
   FVGN_LAUNCH_CHECK();
-  colsum_reduce_kernel<<<4, 256, 0, st>>>(c);
+  colsum_reduce_kernel<<<5, 1024, 0, st>>>(c);
   FVGN_LAUNCH_CHECK();
-  if (m->ln_w) {  // dLN_b = colsum(d_out)
-    ColsumParams c2{};
-    c2.rows = rows; c2.nb = c.nb; c2.grads = grads; c2.partial = c.partial;
-    c2.s[0] = {d_out, ld_dout, 128, vec0 + 512};
-    colsum_kernel<<<dim3(c2.nb, 1), 256, 0, st>>>(c2);
-    FVGN_LAUNCH_CHECK();
-    colsum_reduce_kernel<<<1, 256, 0, st>>>(c2);
-    FVGN_LAUNCH_CHECK();
-  }
   return 0;
 }
 

@@ -504,7 +504,7 @@ def mlp_wgrad_x3(mlp: MlpRef, mode, d_out, dz, gxhat, z_saved, da, x=None, src0=
         _req(x, torch.float32, "x", 2)
     else:
         _cf(src0, "src0"), _cf(src1, "src1"), _ci(idx, "idx")
-    _count(4 if dz is None else 6)
+    _count(4)
     with _zsave(mlp, z_saved, rows, da):
         check(L.fvgn_mlp_wgrad_x3(C.byref(mlp.struct), mode, _p(x), _ld(x) if x is not None else 0, _p(src0), _p(src1), _p(idx), rows, _p(d_out),
                                   _ld(d_out), _p(dz), _p(gxhat), _p(grads), _p(ws), _stream()), "mlp_wgrad_x3")
