@@ -445,7 +445,7 @@ def training_measure(args, rank, world, dev, meshes, dist):
     ms, e2e_ms = float(tms[0]), float(tms[1])
     g = len(meshes) * world
     return {"metric": "training_graphs_per_sec", "value": g * steps / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms / steps, "steps": steps,
-            "global_batch": g, "cells_per_rank": C, "faces_per_rank": F, "dtype": DTYPES[train_math] + " forward, f32 FFMA backward", "loss": p.loss, "optimizer": "AdamW lr 1e-3",
+            "global_batch": g, "cells_per_rank": C, "faces_per_rank": F, "dtype": DTYPES[train_math] + (" (forward and backward GEMMs)" if train_math == "bf16x3" else " forward and backward"), "loss": p.loss, "optimizer": "AdamW lr 1e-3",
             "cell_updates_per_sec": C * world * steps / (ms * 1e-3),
             "e2e": {"value": g * steps / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / steps,
                     "h2d_bytes_per_step": int(node_host.numel() * 4), "d2h_bytes_per_step": 20,

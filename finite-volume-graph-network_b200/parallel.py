@@ -84,7 +84,8 @@ def sync_normalizer_increments_(model, before, group=None):
 
 def global_bn_stats(sums, count, eps=1e-5, group=None):
     """local float64 [sum, sumsq] + count -> (stats=[mean, invstd] fp32, mean, biased var, total count) over all ranks"""
-    t = torch.cat([sums.to(torch.float64), torch.tensor([float(count)], dtype=torch.float64, device=sums.device)])
+    # (torch.full, not torch.tensor: no host -> device copy, so the step stays CUDA-graph capturable)
+    t = torch.cat([sums.to(torch.float64), torch.full((1,), float(count), dtype=torch.float64, device=sums.device)])
     if is_distributed():
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     n = t[2]
