@@ -365,7 +365,7 @@ def training_measure(args, rank, world, dev, meshes, dist):
     p.loss = "global_mean_sum"  # the reference's default (utils/get_param.py:68)
     torch.manual_seed(0)
     model = fv.FVGN(device="cpu", params=p).to(dev).train()
-    train_math = args.math if args.math in ("fp32", "bf16x3") else "fp32"
+    train_math = args.math  # "bf16": the bf16x3 kernels with the leading split product only (bf16 tiles, fp32 accumulation)
     model.set_math_mode(train_math)  # forward arithmetic; the backward kernels are FFMA
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3)  # train.py:45, get_param.py:80
     bucket = parallel.GradBucket(model.parameters())
@@ -445,7 +445,7 @@ def training_measure(args, rank, world, dev, meshes, dist):
     ms, e2e_ms = float(tms[0]), float(tms[1])
     g = len(meshes) * world
     return {"metric": "training_graphs_per_sec", "value": g * steps / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms / steps, "steps": steps,
-            "global_batch": g, "cells_per_rank": C, "faces_per_rank": F, "dtype": DTYPES[train_math] + (" (forward and backward GEMMs)" if train_math == "bf16x3" else " forward and backward"), "loss": p.loss, "optimizer": "AdamW lr 1e-3",
+            "global_batch": g, "cells_per_rank": C, "faces_per_rank": F, "dtype": DTYPES[train_math] + (" (forward and backward GEMMs on tcgen05)" if train_math != "fp32" else " forward and backward"), "loss": p.loss, "optimizer": "AdamW lr 1e-3",
             "cell_updates_per_sec": C * world * steps / (ms * 1e-3),
             "e2e": {"value": g * steps / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / steps,
                     "h2d_bytes_per_step": int(node_host.numel() * 4), "d2h_bytes_per_step": 20,

@@ -37,6 +37,9 @@ class FusedMLP(nn.Sequential):
             ln = self[1] if self._lay_norm else None
             self._ref = ops.MlpRef(l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias,
                                    ln.weight if ln is not None else None, ln.bias if ln is not None else None)
+        # split-product count of the bf16x3 kernels: all six (fp32-equivalent) unless the module is in plain "bf16" mode, where the
+        # training path runs the same kernels with the leading product only (bf16 tiles, fp32 accumulation)
+        self._ref.struct.n_products = 1 if self.math_mode == "bf16" else 0
         return self._ref
 
     def math_mode_id(self):

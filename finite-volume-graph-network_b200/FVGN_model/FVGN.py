@@ -95,8 +95,8 @@ class FVGN(nn.Module):
             capture["cell_in"], capture["edge_in"] = x_in, e_in
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # differentiable path: forward and backward both run in libfvgn_b200 kernels (autograd.NetFunction)
-            if self.math_mode not in ("fp32", "bf16x3"):
-                raise NotImplementedError("training runs in fp32 arithmetic: set_math_mode('fp32') (FFMA) or 'bf16x3' (fp32-equivalent tensor-core forward)")
+            if self.math_mode not in ("fp32", "bf16x3", "bf16"):
+                raise NotImplementedError("training modes: 'fp32' (FFMA), 'bf16x3' (fp32-equivalent tensor cores), 'bf16' (bf16 tiles)")
             from ..autograd import NetFunction, network_params
 
             decoded, delta_u, face_area = NetFunction.apply(self, topo, x_in, e_in, graph_edge.x.contiguous(), graph.cell_area.contiguous(),

@@ -14,7 +14,7 @@ class MlpT(C.Structure):
     _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p),
                 ("b3", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("k_in", C.c_int), ("n_out", C.c_int), ("packed", C.c_void_p),
                 ("packed_x3", C.c_void_p), ("z_save", C.c_void_p), ("packed_x3_bwd", C.c_void_p),
-                ("da_in", C.c_void_p)]
+                ("da_in", C.c_void_p), ("n_products", C.c_int)]
 
 
 _P, _I, _F, _S = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -86,7 +86,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.fvgn_abi_version() != 4:
+        if L.fvgn_abi_version() != 5:
             raise RuntimeError("libfvgn_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -33,9 +33,9 @@ class NetFunction(torch.autograd.Function):
     def forward(ctx, model, topo, cell_in, edge_in, graph_edge_x, cell_area, unv, rho, dt, *params):
         epd = model.model
         enc_c, enc_e = epd.encoder.cb_encoder, epd.encoder.eb_encoder
-        # forward arithmetic: strict FFMA ("fp32") or the fp32-equivalent tensor-core mode ("bf16x3"); the backward recomputes each
-        # tile from the saved layer inputs in FFMA either way
-        mm = {"fp32": 0, "bf16x3": 2}[model.math_mode]
+        # forward arithmetic: strict FFMA ("fp32": FFMA backward that recomputes each tile from the saved layer inputs), the
+        # fp32-equivalent tensor-core mode ("bf16x3") or plain bf16 tiles ("bf16"): tensor-core backward from the saved pre-activations
+        mm = {"fp32": 0, "bf16x3": 2, "bf16": 2}[model.math_mode]  # "bf16": the bf16x3 kernels with the leading split product only
         # bf16x3: the forward also stores every MLP's pre-activations (z1 | z2 | z3, 1.5 KB per row): the backward reads them
         # instead of recomputing the forward in its tiles (a third of its FLOPs)
         zbuf = (lambda rows: torch.empty((rows, 384), dtype=torch.float32, device=cell_in.device)) if mm == 2 else (lambda rows: None)

@@ -33,7 +33,7 @@ constexpr uint32_t TMEM_H0 = 256;
 enum { TC_ROWS = 0, TC_CELL = 1, TC_EDGE = 2 };
 
 struct Params {
-  int mode, rows, ntiles, kt1, k_in, n_out, dbg;
+  int mode, rows, ntiles, kt1, k_in, n_out, dbg, nprod;
   const float* in; int ld_in;                               // ROWS
   const float* src0; const float* src1; const int32_t* idx;  // CELL: x, node_agg, cells_node_T ; EDGE: x', e, neighbour_cell
   float* out0; int ld_out;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
             for (int q = 0; q < 6; ++q)
-              if (!(p.dbg & 8) || q == 0) umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
+              if (q < p.nprod && (!(p.dbg & 8) || q == 0)) umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
                         IDESC_BF16_M128_N128, (t | kk | q) != 0);
           umma_commit(BAR(B_AEMPTY + sa));
           umma_commit(BAR(B_WEMPTY + sw));
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
               for (int q = 0; q < 6; ++q)
-                if (!(p.dbg & 8) || q == 0) umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
+                if (q < p.nprod && (!(p.dbg & 8) || q == 0)) umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
                              umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32), IDESC_BF16_M128_N128, (t | kk | q) != 0);
             umma_commit(BAR(B_WEMPTY + sw));
           }
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
 // (W3^T: 2 K-tile steps, W2^T: 2, W1[:, seg]^T: 2 per 128-column segment); da2 | da1 are also written to HBM [rows, 256] for the
 // weight-gradient kernel (mlp_bwd.cu), which then has no GEMM left but the TN products.
 struct DgParams {
-  int rows, ntiles, nseg, k_in, n_out, want_dA;
+  int rows, ntiles, nseg, k_in, n_out, want_dA, nprod;
   const float* dz; int ld_dz;
   const float* zsave;
   float* da;
@@ -648,8 +648,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
               for (int q = 0; q < 6; ++q)
-                umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
-                          IDESC_BF16_M128_N128, (t | kk | q) != 0);
+                if (q < p.nprod)
+                  umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
+                            IDESC_BF16_M128_N128, (t | kk | q) != 0);
             umma_commit(BAR(B_AEMPTY + sa));
             ++ak;
           } else {
@@ -657,8 +658,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
               for (int q = 0; q < 6; ++q)
-                umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
-                             umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32), IDESC_BF16_M128_N128, (t | kk | q) != 0);
+                if (q < p.nprod)
+                  umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
+                               umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32), IDESC_BF16_M128_N128, (t | kk | q) != 0);
           }
           umma_commit(BAR(B_WEMPTY + sw));
         }
@@ -853,7 +855,7 @@ constexpr int WG_STAGES = 2;
 constexpr int WG_NTHREADS = (4 + 8 + 1) * 32;  // 4 epilogue warps, 8 producer warps, 1 MMA warp
 
 struct WgParams {
-  int mode, rows, k_in, n_out, njobs, nranges, chunks_per_range, nchunks;
+  int mode, rows, k_in, n_out, njobs, nranges, chunks_per_range, nchunks, nprod;
   const float* dz; int ld_dz;   // gradient behind the LayerNorm [rows, n_out]
   const float* da;              // [rows, 256] = da2 | da1
   const float* zsave;           // [rows, 384]
@@ -1009,8 +1011,9 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
         for (int kk = 0; kk < WG_CHUNK / 16; ++kk)
 #pragma unroll
           for (int q = 0; q < 6; ++q)
-            umma_bf16(tmem_base, umma_desc_mn(pb + prod_a(q) * 2 * WG_HALF_BYTES + kk * 2048), umma_desc_mn(qb + prod_w(q) * 2 * WG_HALF_BYTES + kk * 2048),
-                      IDESC_BF16_MN_MN, (c | kk | q) != 0);
+            if (q < p.nprod)
+              umma_bf16(tmem_base, umma_desc_mn(pb + prod_a(q) * 2 * WG_HALF_BYTES + kk * 2048),
+                        umma_desc_mn(qb + prod_w(q) * 2 * WG_HALF_BYTES + kk * 2048), IDESC_BF16_MN_MN, (c | kk | q) != 0);
         umma_commit(BAR(2 + stg));
       }
       umma_commit(BAR(4));
@@ -1163,6 +1166,7 @@ static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t
   p.packed = reinterpret_cast<const unsigned char*>(m->packed_x3);
   p.b1 = m->b1; p.b2 = m->b2; p.b3 = m->b3; p.ln_w = m->ln_w; p.ln_b = m->ln_b;
   p.k_in = m->k_in; p.n_out = m->n_out;
+  p.nprod = m->n_products == 1 ? 1 : 6;
   p.zsave = m->z_save;
   if (p.zsave) FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(p.zsave) & 15) == 0, "z_save must be 16B aligned");
   p.kt1 = kt_of(m->k_in);
@@ -1274,6 +1278,7 @@ int tc3_dgrad(const fvgn_mlp_t* m, const float* dz, int ld_dz, int rows, float* 
   p.rows = rows; p.ntiles = cdiv(rows, TM); p.nseg = (m->k_in + 127) / 128; p.k_in = m->k_in; p.n_out = m->n_out; p.want_dA = dA ? 1 : 0;
   p.dz = dz; p.ld_dz = ld_dz; p.zsave = m->z_save; p.da = da; p.dA = dA; p.ld_dA = ld_dA; p.dA_base = dA_base; p.ld_base = ld_base;
   p.packed = reinterpret_cast<const unsigned char*>(m->packed_x3_bwd);
+  p.nprod = m->n_products == 1 ? 1 : 6;
   const SmemLayout L = smem_layout();
   static bool configured = false;
   if (!configured) {
@@ -1314,6 +1319,7 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
   p.dz = m->ln_w ? dz : d_out; p.ld_dz = m->ln_w ? 128 : ld_dout;
   p.da = m->da_in; p.zsave = m->z_save; p.in = in; p.ld_in = ld_in; p.src0 = src0; p.src1 = src1; p.idx = idx;
   p.part = workspace;
+  p.nprod = m->n_products == 1 ? 1 : 6;
   const int smem_bytes = WG_STAGES * WG_STAGE_BYTES + 256;
   static bool configured = false;
   if (!configured) {

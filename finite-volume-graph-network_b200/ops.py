@@ -111,7 +111,7 @@ class MlpRef:
         self.k_in, self.n_out = int(w1.shape[1]), int(w3.shape[0])
         self.struct = MlpT(w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(),
                            ln_w.data_ptr() if ln_w is not None else None, ln_b.data_ptr() if ln_b is not None else None,
-                           self.k_in, self.n_out, None, None, None, None, None)
+                           self.k_in, self.n_out, None, None, None, None, None, 0)
         self.packed3b = None
         self.packed3b_versions = None
         self.packed = None

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FVGN_ABI_VERSION 4
+#define FVGN_ABI_VERSION 5
 #define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
 
 #define FVGN_E_BADARG (-1)
@@ -66,6 +66,8 @@ typedef struct {
   const void* packed_x3_bwd; /* fvgn_mlp_dgrad_x3 only: buffer filled by fvgn_mlp_pack_bf16x3_bwd for the CURRENT weights */
   const float* da_in;    /* optional [rows, 256] = (da2 | da1) from fvgn_mlp_dgrad_x3.  Backward (fvgn_*_bwd): when non-NULL the FFMA
                             kernel skips its data-gradient GEMMs (and writes no d_in): only weight / bias / LayerNorm gradients remain. */
+  int n_products;        /* FVGN_MATH_BF16X3_TC kernels (forward, dgrad, wgrad): 0 or 6 = all six split products (fp32-equivalent);
+                            1 = the leading product only, i.e. plain bf16 tiles with fp32 accumulation ("bf16" training, BASELINE configs[2]) */
 } fvgn_mlp_t;
 
 /* Tensor-core modes read the weights as pre-swizzled bf16 tiles.  Re-pack whenever the fp32 weights change. */
