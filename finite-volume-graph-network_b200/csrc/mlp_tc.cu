@@ -22,6 +22,17 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+// Timing experiments (skip loads / epilogue math / MMAs to isolate pipeline stages; results are garbage): compiled in only with
+// -DFVGN_TC_TIMING_EXPERIMENTS=1, then selected at run time by the FVGN_TC_DBG environment variable.  Product builds have no such path.
+#ifndef FVGN_TC_TIMING_EXPERIMENTS
+#define FVGN_TC_TIMING_EXPERIMENTS 0
+#endif
+#if FVGN_TC_TIMING_EXPERIMENTS
+#define FVGN_DBG(p) ((p).dbg)
+#else
+#define FVGN_DBG(p) 0
+#endif
+
 namespace fvgn {
 
 constexpr int TM = 128;            // rows per tile (= UMMA M)
@@ -191,7 +202,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
             for (int i = 0; i < 2; ++i) {
               const int r = 16 * bq + hw + 8 * i;
               const int n0 = ix[r], n1 = ix[128 + r], n2 = ix[256 + r];
-              if (p.dbg & 1) { f[i][0] = f[i][1] = f[i][2] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+              if (FVGN_DBG(p) & 1) { f[i][0] = f[i][1] = f[i][2] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
               f[i][0] = ldg4(p.src1 + (size_t)n0 * 64 + hl * 4);
               f[i][1] = ldg4(p.src1 + (size_t)n1 * 64 + hl * 4);
               f[i][2] = ldg4(p.src1 + (size_t)n2 * 64 + hl * 4);
@@ -248,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
             if (gi >= GRING) mbar_wait(BAR(B_AEMPTY + slot), ((gi / GRING) - 1) & 1, 1);
             const uint32_t dst = smem_u32(sA + slot * TILE_BYTES) + sw16;
             const __nv_bfloat16* src = p.xbf_in + (t & 1) * 64 + ch * 8;
-            if (!(p.dbg & 1)) {
+            if (!(FVGN_DBG(p) & 1)) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) cp_async16(dst + (uint32_t)i * 2048u, src + (size_t)(t < 2 ? is_[i] : ir_[i]) * 128);
             }
@@ -278,7 +289,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
           const int jl = s >> 2, u = s & 3;      // u = 2*(t-4) + half
           const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM + 64 * (u & 1);
           const float* base = (MODE == TC_EDGE ? p.src1 : p.src0) + (u >> 1) * 64 + hl * 4;
-          if (p.dbg & 1) {
+          if (FVGN_DBG(p) & 1) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             return;
@@ -318,7 +329,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
     // loads of K-tile step s (tile s / kt1, K-tile s % kt1) into registers.  Rows past the end of the last tile are clamped to
     // the last valid row (their results are never stored), so the hot path carries no bounds predicates.
     auto load = [&](int s, float4* v) {
-      if (p.dbg & 1) {
+      if (FVGN_DBG(p) & 1) {
 #pragma unroll
         for (int i = 0; i < RPT; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
@@ -383,7 +394,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
       const uint32_t slot = (uint32_t)s % ARING;
       if (s >= ARING) mbar_wait(BAR(B_AEMPTY + slot), (((uint32_t)s / ARING) - 1) & 1, 1);
       unsigned char* dst = sA + slot * TILE_BYTES;
-      if (!(p.dbg & 16)) {
+      if (!(FVGN_DBG(p) & 16)) {
 #pragma unroll
         for (int i = 0; i < RPT; ++i) st_tile_f4(dst, hw + NHW * i, hl, v[i]);
       }
@@ -433,7 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
           const uint32_t a_base = smem_u32(sA + sa * TILE_BYTES), b_base = smem_u32(sWr + sw * TILE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            if (!(p.dbg & 8)) umma_bf16(d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (t | kk) != 0);
+            if (!(FVGN_DBG(p) & 8)) umma_bf16(d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (t | kk) != 0);
           umma_commit(BAR(B_AEMPTY + sa));  // both ring slots are free once these MMAs have read them
           if (!w1_resident) umma_commit(BAR(B_WEMPTY + sw));
         }
@@ -460,7 +471,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
           const unsigned char* w = layer == 0 ? sW2 : sW3;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            if (!(p.dbg & 8)) umma_bf16_ts(d, h + 8u * (uint32_t)kk, umma_desc(smem_u32(w + (kk >> 2) * TILE_BYTES) + (kk & 3) * 32), IDESC_BF16_M128_N128, kk != 0);
+            if (!(FVGN_DBG(p) & 8)) umma_bf16_ts(d, h + 8u * (uint32_t)kk, umma_desc(smem_u32(w + (kk >> 2) * TILE_BYTES) + (kk & 3) * 32), IDESC_BF16_M128_N128, kk != 0);
           umma_commit(BAR(B_DFULL + a));
         }
       }
@@ -516,10 +527,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
-          if (p.dbg & 4) continue;
+          if (FVGN_DBG(p) & 4) continue;
           tmem_ld32_issue(t_acc + 32 * c, r);
           tmem_ld_wait(r);
-          if (p.dbg & 2) {
+          if (FVGN_DBG(p) & 2) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = r[j];
           } else silu_chunk(r, bias + 32 * c, pk);
@@ -539,7 +550,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
         float s1 = 0.f, s2 = 0.f, x0 = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          if (p.dbg & 6) continue;
+          if (FVGN_DBG(p) & 6) continue;
           tmem_ld32_issue(t_acc + 32 * c, r);
           tmem_ld_wait(r);
           if (c == 0) x0 = __uint_as_float(r[0]) + b3[0];
@@ -561,7 +572,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         // one 32-column chunk: finish y in place, stage through the warp's swizzled tile, write full 128-byte lines
-        if (!(p.dbg & 4)) {
+        if (!(FVGN_DBG(p) & 4)) {
           tmem_ld32_issue(t_acc + 32 * c, r);
           tmem_ld_wait(r);
         }
@@ -571,7 +582,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
           if (lane == 0) mbar_arrive(BAR(B_DFREE + acc));
         }
         float* v = reinterpret_cast<float*>(r);
-        if (p.dbg & 6) continue;
+        if (FVGN_DBG(p) & 6) continue;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 b = *reinterpret_cast<const float4*>(b3 + 32 * c + 4 * j4);
@@ -706,7 +717,9 @@ static bool red_enabled() {
 
 static int launch_tc(TcParams& p, const fvgn_mlp_t* m, cudaStream_t st) {
   if (p.rows <= 0) return 0;
+#if FVGN_TC_TIMING_EXPERIMENTS
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FVGN_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+#endif
   FVGN_CHECK_ARG(m->packed != nullptr, "tensor-core modes need packed weights: call fvgn_mlp_pack_bf16 first");
   p.packed = reinterpret_cast<const unsigned char*>(m->packed);
   p.b1 = m->b1; p.b2 = m->b2; p.b3 = m->b3; p.ln_w = m->ln_w; p.ln_b = m->ln_b;

@@ -17,6 +17,17 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+// Timing experiments (skip loads / epilogue math / MMAs to isolate pipeline stages; results are garbage): compiled in only with
+// -DFVGN_TC_TIMING_EXPERIMENTS=1, then selected at run time by the FVGN_TC_DBG environment variable.  Product builds have no such path.
+#ifndef FVGN_TC_TIMING_EXPERIMENTS
+#define FVGN_TC_TIMING_EXPERIMENTS 0
+#endif
+#if FVGN_TC_TIMING_EXPERIMENTS
+#define FVGN_DBG(p) ((p).dbg)
+#else
+#define FVGN_DBG(p) 0
+#endif
+
 namespace fvgn {
 namespace x3 {
 
@@ -173,7 +184,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     const int S = n_local * kt1;
     const int last = p.rows - 1;
     auto load = [&](int s, float4* v) {
-      if (p.dbg & 1) {
+      if (FVGN_DBG(p) & 1) {
 #pragma unroll
         for (int i = 0; i < RPT; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       const uint32_t slot = (uint32_t)s % ARING;
       if (s >= ARING) mbar_wait(BAR(B_AEMPTY + slot), (((uint32_t)s / ARING) - 1) & 1, 1);
       unsigned char* dst = sA + slot * SLOT_BYTES;
-      if (!(p.dbg & 64)) {
+      if (!(FVGN_DBG(p) & 64)) {
 #pragma unroll
         for (int i = 0; i < RPT; ++i) st_slot_f4(dst, hw + NHW * i, hl, v[i]);
       }
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       auto put = [&](int step) {
         const uint32_t slot = wl % WRING;
         if (wl >= WRING) mbar_wait(BAR(B_WEMPTY + slot), ((wl / WRING) - 1) & 1, 2);
-        const uint32_t nbytes = (p.dbg & 16) ? TILE_BYTES : SLOT_BYTES;  // timing experiment: a third of the weight bytes
+        const uint32_t nbytes = (FVGN_DBG(p) & 16) ? TILE_BYTES : SLOT_BYTES;  // timing experiment: a third of the weight bytes
         mbar_arrive_expect_tx(BAR(B_WFULL + slot), nbytes);
         bulk_g2s(smem_u32(sW + slot * SLOT_BYTES), p.packed + (size_t)step * SLOT_BYTES, nbytes, BAR(B_WFULL + slot));
         ++wl;
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
             for (int q = 0; q < 6; ++q)
-              if (q < p.nprod && (!(p.dbg & 8) || q == 0)) umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
+              if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
                         IDESC_BF16_M128_N128, (t | kk | q) != 0);
           umma_commit(BAR(B_AEMPTY + sa));
           umma_commit(BAR(B_WEMPTY + sw));
@@ -309,7 +320,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
               for (int q = 0; q < 6; ++q)
-                if (q < p.nprod && (!(p.dbg & 8) || q == 0)) umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
+                if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
                              umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32), IDESC_BF16_M128_N128, (t | kk | q) != 0);
             umma_commit(BAR(B_WEMPTY + sw));
           }
@@ -373,7 +384,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           tmem_ld16_issue(t_acc + 16 * sc, r);
           tmem_ld16_wait(r);
           uint32_t p0[8], p1[8], p2[8];
-          if (p.dbg & 2) {
+          if (FVGN_DBG(p) & 2) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { p0[j] = r[j]; p1[j] = r[j + 8]; p2[j] = 0; }
           } else
@@ -399,7 +410,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       mbar_wait(dfull, (use0 + 2u) & 1, 9);
       tc_fence_after();
       float mean = 0.f, rstd = 1.f;
-      if (has_ln && !(p.dbg & 32)) {  // two-pass LayerNorm statistics, as torch; the two column halves exchange partial sums
+      if (has_ln && !(FVGN_DBG(p) & 32)) {  // two-pass LayerNorm statistics, as torch; the two column halves exchange partial sums
         float s = 0.f;
 #pragma unroll 1
         for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
@@ -445,7 +456,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           if (lane == 0) mbar_arrive(BAR(B_DFREE + acc));
         }
         float* v = reinterpret_cast<float*>(r);
-        if (p.dbg & 32) continue;
+        if (FVGN_DBG(p) & 32) continue;
         if (p.zsave) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
@@ -1161,7 +1172,9 @@ int tc3_pack(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t st) {
 static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t st) {
   using namespace x3;
   if (p.rows <= 0) return 0;
+#if FVGN_TC_TIMING_EXPERIMENTS
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FVGN_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+#endif
   FVGN_CHECK_ARG(m->packed_x3 != nullptr, "FVGN_MATH_BF16X3_TC needs split-packed weights: call fvgn_mlp_pack_bf16x3 first");
   p.packed = reinterpret_cast<const unsigned char*>(m->packed_x3);
   p.b1 = m->b1; p.b2 = m->b2; p.b3 = m->b3; p.ln_w = m->ln_w; p.ln_b = m->ln_b;
