@@ -271,6 +271,8 @@ def native(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:  # host-side setup (mesh generation, collation) of the ranks shares one box: no OpenMP oversubscription
+        torch.set_num_threads(max(1, (os.cpu_count() or world) // world))
     fv._lib.lib()
     dist = None
     if world > 1:
@@ -331,7 +333,7 @@ def native(args, rank, world, local_rank):
     if rank == 0:
         if train is not None:
             result["training"] = train
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only: at N > 1 the other ranks' host threads share the cores
             result["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_seconds)
     if dist is not None:
         dist.barrier()
