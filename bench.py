@@ -253,6 +253,18 @@ def roofline_of(m, math, workload):
         traffic = t["dram_bytes_per_launch"] if t else None
     name = {"fp32": "fused_mlp_simt_kernel<EDGE>", "bf16": "fused_mlp_tc_kernel<TC_EDGE, RED, XBF>",
             "bf16x3": "x3::fused_mlp_tc3_kernel<TC_EDGE, RED>"}[math]
+    if math == "bf16x3" and edge_ms:
+        # the fp32-equivalent kernel is tensor-bound: 6 bf16 MMAs per algorithmic product.  Algorithmic GEMM FLOPs per face:
+        # 2*(384*128 + 2*128^2) = 163,840; executed on the tensor pipe: 6x that.
+        tf_peak = peaks.get("bf16_tflops_sustained", 1375.0)
+        alg = 163840.0 * F / (edge_ms * 1e-3) / 1e12
+        return {"kernel": name, "workload": workload, "math": math, "bound": "tensor", "achieved": 6.0 * alg, "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": 6.0 * alg / tf_peak, "traffic": traffic, "avg_launch_ms": edge_ms,
+                "peak_source": ("measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1375 TFLOP/s"),
+                "algorithmic_tflops_fp32_equivalent": alg, "executed_mma_flops_per_launch": int(6 * 163840 * F),
+                "launches_timed": len(kern["edge_block"]), "share_of_step": shares,
+                "note": "achieved = executed bf16 MMA FLOPs (six 3-way-split products per fp32-equivalent product) / CUDA-event launch time; "
+                        "the algorithmic (fp32-equivalent) rate is a sixth of it: DESIGN.md §4.3"}
     return {"kernel": name, "workload": workload, "math": math, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
             "frac": (ach / hbm) if ach else None, "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": edge_ms,
             "algorithmic_bytes_per_launch": int(edge_bytes), "launches_timed": len(kern["edge_block"]), "share_of_step": shares,
