@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libfvgn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("FVGN_NVCC_EXTRA", "").split()  # e.g. -DFVGN_TC_TIMING_EXPERIMENTS=1
 # per-file extras: the geometry / pre-post kernels must not contract a*b+c into FMA (bit-parity with numpy/torch)
 SOURCES = {
     "api.cu": [],

@@ -1,18 +1,27 @@
-// mlp_tc3.cu — fp32-accurate tensor-core path (FVGN_MATH_BF16X3_TC): every GEMM operand (gathered rows, hidden activations, weights)
-// is split exactly into three bf16 terms a = a0 + a1 + a2 (8 + 8 + 8 significand bits = fp32's 24) and each product is evaluated as
-//   a.w ~= a0.w0 + a0.w1 + a1.w0 + a0.w2 + a1.w1 + a2.w0          (dropped terms <= 2^-24 |a.w|)
-// by six tcgen05.mma (kind::f16, bf16 operands, fp32 accumulation in TMEM).  Bias, SiLU (expf + IEEE division, as the strict FFMA
-// path), LayerNorm (two-pass) and the residual are fp32 in the epilogue, so results stay within the reference's 1e-5 per-step
-// relative tolerance (tests/test_gpu_parity.py runs the whole parity suite in this mode) at ~1/10 of the FFMA path's time.
+// mlp_tc3.cu — fp32-accurate tensor-core path (FVGN_MATH_BF16X3_TC): every GEMM operand is split into narrow terms whose products
+// the tensor cores evaluate exactly, accumulated in fp32 in TMEM.
+//   backward (dgrad / wgrad): activations-gradients and weights are both split into three bf16 terms (8 + 8 + 8 significand bits =
+//     fp32's 24, full fp32 exponent range):  a.w ~= a0.w0 + a0.w1 + a1.w0 + a0.w2 + a1.w1 + a2.w0   (six tcgen05.mma, dropped <= 2^-24)
+//   forward: BOTH operands in two fp16 terms (11 + 11 significand bits), pre-scaled by exact powers of two so that the low terms stay
+//     normal fp16 numbers: activations (gathered rows, hidden activations) by 2^3, each weight matrix by 2^s with max|w| 2^s in
+//     [2^13, 2^14) (the scale is found on the device by the pack kernel and undone, exactly, in the epilogue):
+//       a.w ~= h0.g0 + h0.g1 + h1.g0                      (three tcgen05.mma; dropped / split residuals <= ~2^-22: 7e-8 relative
+//                                                          on N(0,1) data, the level of an fp32 GEMM's own rounding)
+//     Half the MMAs, two thirds of the operand bytes of the 3 x bf16 scheme.  Forward activations are O(1) (normalised inputs,
+//     LayerNorm'd latents, SiLU outputs): |a| >= 8190 overflows the fp16 term to inf and the output row to NaN (loud, not silent).
+//     Gradients have no such bound, hence the backward keeps bf16.
+// Bias, SiLU (ex2.approx / rcp.approx), LayerNorm (two-pass) and the residual are fp32 in the epilogue, so results stay within the
+// reference's 1e-5 per-step relative tolerance (tests/test_gpu_x3.py holds every op to 5e-6 against the fp64 oracle).
 //
-// Tensor-bound (240 MMAs per 128-row EdgeBlock tile), so the pipeline is simpler than mlp_tc.cu: one persistent CTA per SM,
-//   warps 0-3   epilogue  : one thread per row; tcgen05.ld -> bias + SiLU -> 3-way split -> tcgen05.st (hidden activations stay in TMEM
+// 120 MMAs per 128-row EdgeBlock tile; one persistent CTA per SM,
+//   warps 0-7   epilogue  : two threads per row; tcgen05.ld -> bias + SiLU -> fp16 split -> tcgen05.st (hidden activations stay in TMEM
 //                           as the A operand of the next layer); last layer: bias + LayerNorm + residual -> HBM via per-warp staging
-//   warps 4-11  producers : gather / stream the operand rows (fp32), split, write three swizzled bf16 K-tiles per 64 columns
-//   warp 12     MMA issuer: layer 1 of tile j+1 is issued before layers 2/3 of tile j (two accumulators)
-//   warp 13     loader    : ALL weights are streamed (3 x 160 KB per EdgeBlock MLP cannot stay resident): one 48 KB cp.async.bulk
-//                           per K-tile step through a 2-slot ring, in the MMA issuer's consumption order
+//   warps 8-15  producers : gather / stream the operand rows (fp32), split, write two swizzled fp16 K-tiles per 64 columns
+//   warp 16     MMA issuer: layer 1 of tile j+1 is issued before layers 2/3 of tile j (two accumulators)
+//   warp 17     loader    : ALL weights are streamed (2 x 160 KB per EdgeBlock MLP cannot stay resident): one 32 KB cp.async.bulk
+//                           per K-tile step through a 3-slot ring, in the MMA issuer's consumption order
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -31,15 +40,35 @@
 namespace fvgn {
 namespace x3 {
 
+#if FVGN_TC_TIMING_EXPERIMENTS
+// per-role wait-time accounting of the forward kernel (clock64 sums over all CTAs of all launches since the last read): tools/x3_prof.py
+__device__ unsigned long long g_prof[32];
+#define PROF_DECL long long pt_ = 0; unsigned long long pacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_T0() (pt_ = clock64())
+#define PROF_ADD(i) do { const long long n_ = clock64(); pacc_[i] += (unsigned long long)(n_ - pt_); pt_ = n_; } while (0)
+#define PROF_FLUSH(base) do { for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_prof[(base) + i_], pacc_[i_]); } while (0)
+#else
+#define PROF_DECL
+#define PROF_T0()
+#define PROF_ADD(i)
+#define PROF_FLUSH(base)
+#endif
+
 constexpr int TM = 128, HIDN = 128, KTILE = 64;
 constexpr int TILE_BYTES = TC_TILE_BYTES, SLOT_BYTES = 3 * TILE_BYTES;  // one K-tile step = three split sub-tiles
-constexpr int ARING = 2, WRING = 2;
+constexpr int ARING = 2, WRING = 2;                 // backward kernels
+constexpr int FA_SLOT = 2 * TILE_BYTES, FARING = 3;  // forward: two fp16 split sub-tiles per K-tile step, 3-slot rings
+constexpr int FW_SLOT = 2 * TILE_BYTES, FWRING = 3;
+constexpr float ASCALE = 8.0f;                       // power-of-two pre-scale of the forward activation operand
 constexpr int NEPI = 256, NPROD = 256, NPW = NPROD / 32;  // epilogue: 8 warps = two threads (column halves) per tile row
 constexpr int WARP_PROD0 = NEPI / 32, WARP_MMA = WARP_PROD0 + NPW, WARP_LOAD = WARP_MMA + 1;
 constexpr int NTHREADS = (WARP_LOAD + 1) * 32;  // 576
 constexpr int RPT = TM / (NPROD / 16);          // 8 rows per producer thread per K-tile
 constexpr uint32_t TMEM_COLS = 512;             // acc0 [0,128) | acc1 [128,256) | H split 0 [256,320) | 1 [320,384) | 2 [384,448)
-constexpr uint32_t TMEM_H0 = 256;
+constexpr uint32_t TMEM_H0 = 256;               // (the forward kernel has two fp16 H planes: [256,320) | [320,384))
+// kind::f16 instruction descriptor with fp16 operands (a_format bits [7,10) = 0, b_format [10,13) = 0); mixing an fp16 A with a
+// bf16 B is an illegal instruction on sm_100a
+constexpr uint32_t IDESC_F16_M128_N128 = IDESC_BF16_M128_N128 & ~0x480u;
 
 enum { TC_ROWS = 0, TC_CELL = 1, TC_EDGE = 2 };
 
@@ -69,6 +98,15 @@ __device__ __forceinline__ void split3_pair(float a, float b, uint32_t& p0, uint
   p2 = cvt_bf16x2(sa, sb);
 }
 
+// 2-way fp16 split of two fp32 values (forward activation operand): a = h0 + h1 up to 2^-22 relative
+__device__ __forceinline__ void split2_pair(float a, float b, uint32_t& p0, uint32_t& p1) {
+  const __half2 h0 = __floats2half2_rn(a, b);
+  const float2 f0 = __half22float2(h0);
+  const __half2 h1 = __floats2half2_rn(a - f0.x, b - f0.y);  // the differences are exact
+  p0 = *reinterpret_cast<const uint32_t*>(&h0);
+  p1 = *reinterpret_cast<const uint32_t*>(&h1);
+}
+
 // SiLU for the fp32-equivalent mode: x * rcp(1 + 2^(-x log2 e)) with ex2.approx and rcp.approx (each <= 1 ulp-level, 2^-22/2^-23
 // relative): <= ~4e-7 relative overall, well inside this mode's 1e-5 budget.  Both are single MUFU instructions: no slow-path
 // branches (as in expf / IEEE division / __frcp_rn), so the 32 independent elements of a chunk pipeline through the SFU.
@@ -90,6 +128,16 @@ __device__ __forceinline__ void st_slot_f4(unsigned char* slot, int r, int hl, f
   *reinterpret_cast<uint2*>(slot + 2 * TILE_BYTES + off) = q2;
 }
 
+// forward flavour: two fp16 split sub-tiles per slot
+__device__ __forceinline__ void st_slot2_f4(unsigned char* slot, int r, int hl, float4 v) {
+  const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)hl >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)hl & 1u) * 8u;
+  uint2 q0, q1;
+  split2_pair(v.x * ASCALE, v.y * ASCALE, q0.x, q1.x);
+  split2_pair(v.z * ASCALE, v.w * ASCALE, q0.y, q1.y);
+  *reinterpret_cast<uint2*>(slot + off) = q0;
+  *reinterpret_cast<uint2*>(slot + TILE_BYTES + off) = q1;
+}
+
 struct SmemLayout {
   uint32_t a_off, w_off, stage_off, par_off, red_off, bar_off, total;
 };
@@ -106,6 +154,24 @@ __host__ __device__ inline SmemLayout smem_layout() {
   return L;
 }
 
+__host__ __device__ inline SmemLayout smem_layout_fwd() {
+  SmemLayout L;
+  uint32_t o = 0;
+  L.a_off = o; o += FARING * FA_SLOT;     // 96 KB
+  L.w_off = o; o += FWRING * FW_SLOT;     // 96 KB
+  L.stage_off = o; o += 8 * 2048;
+  L.par_off = o; o += 5 * 128 * 4 + 16;   // b1 b2 b3 ln_w ln_b | the three 1 / (ASCALE * weight scale) factors
+  L.red_off = o; o += 2 * 2 * 128 * 4;
+  L.bar_off = o; o += 256;
+  L.total = o;
+  return L;
+}
+enum { FB_AFULL = 0, FB_AEMPTY = FB_AFULL + FARING, FB_WFULL = FB_AEMPTY + FARING, FB_WEMPTY = FB_WFULL + FWRING, FB_DFULL = FB_WEMPTY + FWRING,
+       FB_DFREE = FB_DFULL + 2, FB_HREADY = FB_DFREE + 2, FB_COUNT = FB_HREADY + 1 };
+// the three forward split products, most significant first: (activation split, weight split)
+__host__ __device__ constexpr int fprod_a(int q) { return q == 2 ? 1 : 0; }  // 0 0 1
+__host__ __device__ constexpr int fprod_w(int q) { return q == 1 ? 1 : 0; }  // 0 1 0
+
 enum { B_AFULL = 0, B_AEMPTY = B_AFULL + ARING, B_WFULL = B_AEMPTY + ARING, B_WEMPTY = B_WFULL + WRING, B_DFULL = B_WEMPTY + WRING,
        B_DFREE = B_DFULL + 2, B_HREADY = B_DFREE + 2, B_COUNT = B_HREADY + 1 };
 
@@ -116,24 +182,26 @@ __host__ __device__ constexpr int prod_w(int q) { return q == 1 || q == 4 ? 1 : 
 template <int MODE, bool RED>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const SmemLayout L = smem_layout();
+  const SmemLayout L = smem_layout_fwd();
   unsigned char* sA = smem + L.a_off;
   unsigned char* sW = smem + L.w_off;
   float* sPar = reinterpret_cast<float*>(smem + L.par_off);
   const uint32_t bar0 = smem_u32(smem + L.bar_off);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * B_COUNT);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * FB_COUNT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt1 = (MODE == TC_EDGE) ? 6 : (MODE == TC_CELL) ? 3 : p.kt1;
   const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // layer-1 K-tile steps of the NEXT tile issued during this tile's first / second / third epilogue: [0,l1a) [l1a,l1b) [l1b,kt1)
+  const int l1a = (kt1 - 1) / 2 > 1 ? (kt1 - 1) / 2 : 1, l1b = l1a + (kt1 > l1a ? 1 : 0);
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) { printf("fvgn mlp_tc3: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
-    for (int i = 0; i < ARING; ++i) { mbar_init(BAR(B_AFULL + i), NPW); mbar_init(BAR(B_AEMPTY + i), 1); }
-    for (int i = 0; i < WRING; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(BAR(B_DFULL + a), 1); mbar_init(BAR(B_DFREE + a), 8); }
-    mbar_init(BAR(B_HREADY), 8);
+    for (int i = 0; i < FARING; ++i) { mbar_init(BAR(FB_AFULL + i), NPW); mbar_init(BAR(FB_AEMPTY + i), 1); }
+    for (int i = 0; i < FWRING; ++i) { mbar_init(BAR(FB_WFULL + i), 1); mbar_init(BAR(FB_WEMPTY + i), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(BAR(FB_DFULL + a), 1); mbar_init(BAR(FB_DFREE + a), 8); }
+    mbar_init(BAR(FB_HREADY), 8);
     fence_mbar_init();
   }
   if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -148,6 +216,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       else v = p.ln_b ? p.ln_b[c] : 0.f;
       sPar[i] = v;
     }
+    if (tid - NEPI < 3) sPar[5 * 128 + tid - NEPI] = reinterpret_cast<const float*>(p.packed + (size_t)(kt1 + 4) * FW_SLOT)[tid - NEPI];
   }
   tc_fence_before();
   __syncthreads();
@@ -161,6 +230,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     const int hw = ptid >> 4, hl = ptid & 15;
     const int S = n_local * kt1;
     const int last = p.rows - 1;
+    PROF_DECL;
+    int nidx[RPT];  // EDGE: gather indices of the next gathered K-tile pair
+    if (MODE == TC_EDGE && S > 0) {
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) nidx[i] = __ldg(p.idx + min((int)blockIdx.x * TM + hw + NHW * i, last));
+    }
     auto load = [&](int s, float4* v) {
       if (FVGN_DBG(p) & 1) {
 #pragma unroll
@@ -170,17 +245,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       const int jl = s / kt1, t = s - jl * kt1;
       const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
       if (MODE == TC_EDGE) {
-        const bool gath = t < 4;
-        const int32_t* ip = p.idx + (t >= 2 ? (size_t)p.rows : 0);
-        const float* base = (gath ? p.src0 : p.src1) + (t & 1) * 64 + hl * 4;
-        int src[RPT];
+        if (t < 4) {  // x'[sender] (t = 0, 1), x'[receiver] (t = 2, 3): the indices were fetched two steps ago
+          const float* base = p.src0 + (t & 1) * 64 + hl * 4;
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-          const int f = min(row0 + hw + NHW * i, last);
-          src[i] = gath ? __ldg(ip + f) : f;
+          for (int i = 0; i < RPT; ++i) v[i] = ldg4(base + (size_t)nidx[i] * 128);
+          if (t & 1) {  // this index set is used up: fetch the receivers of this tile / the senders of the next tile
+            const int r0 = (t == 3) ? row0 + (int)gridDim.x * TM : row0;
+            const int32_t* ip = p.idx + (t == 3 ? 0 : (size_t)p.rows);
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) nidx[i] = __ldg(ip + min(r0 + hw + NHW * i, last));
+          }
+        } else {
+          const float* base = p.src1 + (t & 1) * 64 + hl * 4;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) v[i] = ldg4(base + (size_t)min(row0 + hw + NHW * i, last) * 128);
         }
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) v[i] = ldg4(base + (size_t)src[i] * 128);
       } else if (MODE == TC_CELL) {
         const int C = p.rows;
         if (t < 2) {
@@ -216,17 +295,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       }
     };
     auto store = [&](int s, const float4* v) {
-      const uint32_t slot = (uint32_t)s % ARING;
-      if (s >= ARING) mbar_wait(BAR(B_AEMPTY + slot), (((uint32_t)s / ARING) - 1) & 1, 1);
-      unsigned char* dst = sA + slot * SLOT_BYTES;
+      const uint32_t slot = (uint32_t)s % FARING;
+      PROF_ADD(0);  // gather issue
+      if (s >= FARING) mbar_wait(BAR(FB_AEMPTY + slot), (((uint32_t)s / FARING) - 1) & 1, 1);
+      PROF_ADD(1);  // wait for a free A slot
+      unsigned char* dst = sA + slot * FA_SLOT;
       if (!(FVGN_DBG(p) & 64)) {
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) st_slot_f4(dst, hw + NHW * i, hl, v[i]);
+        for (int i = 0; i < RPT; ++i) st_slot2_f4(dst, hw + NHW * i, hl, v[i]);
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_AFULL + slot));
+      if (lane == 0) mbar_arrive(BAR(FB_AFULL + slot));
+      PROF_ADD(2);  // split + store (includes the wait for the gathered data)
     };
+    PROF_T0();
     float4 va[RPT], vb[RPT];
 #pragma unroll 1
     for (int s = -1; s < S; s += 2) {
@@ -235,82 +318,108 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       if (s + 2 < S) load(s + 2, vb);
       if (s + 1 < S) store(s + 1, va);
     }
+    if (ptid == 0) PROF_FLUSH(16);
   } else if (warp == WARP_LOAD) {
     // ================================================================= weight loader: 48 KB per K-tile step, MMA consumption order
     if (lane == 0 && n_local > 0) {
       uint32_t wl = 0;
+      PROF_DECL;
+      PROF_T0();
       auto put = [&](int step) {
-        const uint32_t slot = wl % WRING;
-        if (wl >= WRING) mbar_wait(BAR(B_WEMPTY + slot), ((wl / WRING) - 1) & 1, 2);
-        const uint32_t nbytes = (FVGN_DBG(p) & 16) ? TILE_BYTES : SLOT_BYTES;  // timing experiment: a third of the weight bytes
-        mbar_arrive_expect_tx(BAR(B_WFULL + slot), nbytes);
-        bulk_g2s(smem_u32(sW + slot * SLOT_BYTES), p.packed + (size_t)step * SLOT_BYTES, nbytes, BAR(B_WFULL + slot));
+        const uint32_t slot = wl % FWRING;
+        if (wl >= FWRING) mbar_wait(BAR(FB_WEMPTY + slot), ((wl / FWRING) - 1) & 1, 2);
+        PROF_ADD(0);
+        const uint32_t nbytes = (FVGN_DBG(p) & 16) ? TILE_BYTES : FW_SLOT;  // timing experiment: half of the weight bytes
+        mbar_arrive_expect_tx(BAR(FB_WFULL + slot), nbytes);
+        bulk_g2s(smem_u32(sW + slot * FW_SLOT), p.packed + (size_t)step * FW_SLOT, nbytes, BAR(FB_WFULL + slot));
         ++wl;
       };
       for (int t = 0; t < kt1; ++t) put(t);
 #pragma unroll 1
-      for (int jl = 0; jl < n_local; ++jl) {
-        if (jl + 1 < n_local)
-          for (int t = 0; t < kt1; ++t) put(t);
-        for (int t = 0; t < 4; ++t) put(kt1 + t);  // W2 (2 steps), W3 (2 steps)
+      for (int jl = 0; jl < n_local; ++jl) {  // the MMA issuer's order
+        const bool nxt = jl + 1 < n_local;
+        if (nxt) for (int t = 0; t < l1a; ++t) put(t);
+        put(kt1); put(kt1 + 1);  // W2
+        if (nxt) for (int t = l1a; t < l1b; ++t) put(t);
+        put(kt1 + 2); put(kt1 + 3);  // W3
+        if (nxt) for (int t = l1b; t < kt1; ++t) put(t);
       }
+      PROF_FLUSH(24);
     }
     __syncwarp();
   } else if (warp == WARP_MMA) {
     // ================================================================= MMA issuer
     if (lane == 0 && n_local > 0) {
       uint32_t ak = 0, wk = 0, hphase = 0;
-      auto layer1 = [&](int jl) {
+      PROF_DECL;
+      PROF_T0();
+      auto layer1 = [&](int jl, int t0, int t1) {  // K-tile steps [t0, t1) of layer 1 of tile jl
         const int a = jl & 1;
-        if (jl >= 2) mbar_wait(BAR(B_DFREE + a), (uint32_t)((jl >> 1) - 1) & 1, 3);
+        if (t0 == 0 && jl >= 2) mbar_wait(BAR(FB_DFREE + a), (uint32_t)((jl >> 1) - 1) & 1, 3);
+        PROF_ADD(0);
         const uint32_t d = tmem_base + 128u * (uint32_t)a;
 #pragma unroll 1
-        for (int t = 0; t < kt1; ++t, ++ak, ++wk) {
-          const uint32_t sa = ak % ARING, sw = wk % WRING;
-          mbar_wait(BAR(B_AFULL + sa), (ak / ARING) & 1, 4);
-          mbar_wait(BAR(B_WFULL + sw), (wk / WRING) & 1, 5);
+        for (int t = t0; t < t1; ++t, ++ak, ++wk) {
+          const uint32_t sa = ak % FARING, sw = wk % FWRING;
+          mbar_wait(BAR(FB_AFULL + sa), (ak / FARING) & 1, 4);
+          PROF_ADD(1);
+          mbar_wait(BAR(FB_WFULL + sw), (wk / FWRING) & 1, 5);
+          PROF_ADD(2);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + sa * SLOT_BYTES), b_base = smem_u32(sW + sw * SLOT_BYTES);
+          const uint32_t a_base = smem_u32(sA + sa * FA_SLOT), b_base = smem_u32(sW + sw * FW_SLOT);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-            for (int q = 0; q < 6; ++q)
-              if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
-                        IDESC_BF16_M128_N128, (t | kk | q) != 0);
-          umma_commit(BAR(B_AEMPTY + sa));
-          umma_commit(BAR(B_WEMPTY + sw));
+            for (int q = 0; q < 3; ++q)
+              if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16(d, umma_desc(a_base + fprod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + fprod_w(q) * TILE_BYTES + kk * 32),
+                        IDESC_F16_M128_N128, (t | kk | q) != 0);
+          umma_commit(BAR(FB_AEMPTY + sa));
+          umma_commit(BAR(FB_WEMPTY + sw));
+          PROF_ADD(3);
         }
-        umma_commit(BAR(B_DFULL + a));
+        if (t1 == kt1 && t1 > t0) umma_commit(BAR(FB_DFULL + a));
       };
-      auto layer23 = [&](int jl) {
+      auto layer23 = [&](int jl) {  // layer 2 or 3 of tile jl (whichever hidden activation the epilogue has just published)
         const int a = jl & 1;
         const uint32_t d = tmem_base + 128u * (uint32_t)a;
-#pragma unroll 1
-        for (int layer = 0; layer < 2; ++layer) {
-          mbar_wait(BAR(B_HREADY), hphase, 7); hphase ^= 1;
+        {
+          mbar_wait(BAR(FB_HREADY), hphase, 7); hphase ^= 1;
+          PROF_ADD(4);
 #pragma unroll 1
           for (int t = 0; t < 2; ++t, ++wk) {
-            const uint32_t sw = wk % WRING;
-            mbar_wait(BAR(B_WFULL + sw), (wk / WRING) & 1, 6);
+            const uint32_t sw = wk % FWRING;
+            mbar_wait(BAR(FB_WFULL + sw), (wk / FWRING) & 1, 6);
+            PROF_ADD(5);
             tc_fence_after();
-            const uint32_t b_base = smem_u32(sW + sw * SLOT_BYTES);
+            const uint32_t b_base = smem_u32(sW + sw * FW_SLOT);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-              for (int q = 0; q < 6; ++q)
-                if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
-                             umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32), IDESC_BF16_M128_N128, (t | kk | q) != 0);
-            umma_commit(BAR(B_WEMPTY + sw));
+              for (int q = 0; q < 3; ++q)
+                if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * fprod_a(q) + 8u * (uint32_t)(4 * t + kk),
+                             umma_desc(b_base + fprod_w(q) * TILE_BYTES + kk * 32), IDESC_F16_M128_N128, (t | kk | q) != 0);
+            umma_commit(BAR(FB_WEMPTY + sw));
+            PROF_ADD(6);
           }
-          umma_commit(BAR(B_DFULL + a));
+          umma_commit(BAR(FB_DFULL + a));
         }
       };
-      layer1(0);
+      // Layer 1 of the next tile (second accumulator) is issued in three parts, one inside each epilogue window of this tile, so that
+      // layers 2 / 3 never queue behind a layer-1 step that is still waiting for its gathered operand.
+      layer1(0, 0, kt1);
 #pragma unroll 1
       for (int jl = 0; jl < n_local; ++jl) {
-        if (jl + 1 < n_local) layer1(jl + 1);  // runs under tile jl's epilogues (second accumulator)
+        const bool nxt = jl + 1 < n_local;
+        if (nxt) layer1(jl + 1, 0, l1a);
         layer23(jl);
+        if (nxt) layer1(jl + 1, l1a, l1b);
+        layer23(jl);
+        if (nxt) layer1(jl + 1, l1b, kt1);
       }
+      PROF_FLUSH(0);
+#if FVGN_TC_TIMING_EXPERIMENTS
+      atomicAdd(&g_prof[7], (unsigned long long)n_local);
+#endif
     }
     __syncwarp();
   } else {
@@ -344,49 +453,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       }
       __syncwarp();
     };
+    PROF_DECL;
+    PROF_T0();
 #pragma unroll 1
     for (int jl = 0; jl < n_local; ++jl) {
       const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
       const int acc = jl & 1;
       const uint32_t t_acc = t_lane + 128u * (uint32_t)acc;
-      const uint32_t dfull = BAR(B_DFULL + acc);
+      const uint32_t dfull = BAR(FB_DFULL + acc);
       const uint32_t use0 = 3u * (uint32_t)(jl >> 1);
       uint32_t r[16];
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
         mbar_wait(dfull, (use0 + (uint32_t)layer) & 1, 8);
+        PROF_ADD(layer);  // 0: wait for the layer-1 accumulator, 1: layer 2
         tc_fence_after();
         const float* bias = sPar + layer * 128;
+        const float inv = sPar[5 * 128 + layer];  // undo the power-of-two operand scales (exact)
 #pragma unroll 1
         for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {  // 16-column sub-chunk index 0..7
           tmem_ld16_issue(t_acc + 16 * sc, r);
           tmem_ld16_wait(r);
-          uint32_t p0[8], p1[8], p2[8];
+          uint32_t p0[8], p1[8];
           if (FVGN_DBG(p) & 2) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { p0[j] = r[j]; p1[j] = r[j + 8]; p2[j] = 0; }
+            for (int j = 0; j < 8; ++j) { p0[j] = r[j]; p1[j] = r[j + 8]; }
           } else
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(bias + 16 * sc + 4 * j4);
-            const float z0 = __uint_as_float(r[4 * j4]) + b.x, z1 = __uint_as_float(r[4 * j4 + 1]) + b.y;
-            const float z2 = __uint_as_float(r[4 * j4 + 2]) + b.z, z3 = __uint_as_float(r[4 * j4 + 3]) + b.w;
+            const float z0 = fmaf(__uint_as_float(r[4 * j4]), inv, b.x), z1 = fmaf(__uint_as_float(r[4 * j4 + 1]), inv, b.y);
+            const float z2 = fmaf(__uint_as_float(r[4 * j4 + 2]), inv, b.z), z3 = fmaf(__uint_as_float(r[4 * j4 + 3]), inv, b.w);
             r[4 * j4] = __float_as_uint(z0); r[4 * j4 + 1] = __float_as_uint(z1); r[4 * j4 + 2] = __float_as_uint(z2); r[4 * j4 + 3] = __float_as_uint(z3);
-            split3_pair(silu_x3(z0), silu_x3(z1), p0[2 * j4], p1[2 * j4], p2[2 * j4]);
-            split3_pair(silu_x3(z2), silu_x3(z3), p0[2 * j4 + 1], p1[2 * j4 + 1], p2[2 * j4 + 1]);
+            split2_pair(silu_x3(z0) * ASCALE, silu_x3(z1) * ASCALE, p0[2 * j4], p1[2 * j4]);
+            split2_pair(silu_x3(z2) * ASCALE, silu_x3(z3) * ASCALE, p0[2 * j4 + 1], p1[2 * j4 + 1]);
           }
           if (p.zsave) store_rows16(reinterpret_cast<const float*>(r), p.zsave, 384, 128 * layer + 16 * sc, row0 + 32 * q);
           tmem_st8(t_h + 8 * sc, p0);
           tmem_st8(t_h + 64 + 8 * sc, p1);
-          tmem_st8(t_h + 128 + 8 * sc, p2);
         }
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_HREADY));
+        if (lane == 0) mbar_arrive(BAR(FB_HREADY));
+        PROF_ADD(3);  // hidden-layer epilogue work
       }
       mbar_wait(dfull, (use0 + 2u) & 1, 9);
+      PROF_ADD(2);  // wait for the layer-3 accumulator
       tc_fence_after();
+      const float inv3 = sPar[5 * 128 + 2];
       float mean = 0.f, rstd = 1.f;
       if (has_ln && !(FVGN_DBG(p) & 32)) {  // two-pass LayerNorm statistics, as torch; the two column halves exchange partial sums
         float s = 0.f;
@@ -397,8 +512,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
-            s += __uint_as_float(r[4 * j4]) + b.x; s += __uint_as_float(r[4 * j4 + 1]) + b.y;
-            s += __uint_as_float(r[4 * j4 + 2]) + b.z; s += __uint_as_float(r[4 * j4 + 3]) + b.w;
+            s += fmaf(__uint_as_float(r[4 * j4]), inv3, b.x); s += fmaf(__uint_as_float(r[4 * j4 + 1]), inv3, b.y);
+            s += fmaf(__uint_as_float(r[4 * j4 + 2]), inv3, b.z); s += fmaf(__uint_as_float(r[4 * j4 + 3]), inv3, b.w);
           }
         }
         sRed[h * 128 + erow] = s;
@@ -413,10 +528,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
             float d;
-            d = (__uint_as_float(r[4 * j4]) + b.x) - mean; qv = fmaf(d, d, qv);
-            d = (__uint_as_float(r[4 * j4 + 1]) + b.y) - mean; qv = fmaf(d, d, qv);
-            d = (__uint_as_float(r[4 * j4 + 2]) + b.z) - mean; qv = fmaf(d, d, qv);
-            d = (__uint_as_float(r[4 * j4 + 3]) + b.w) - mean; qv = fmaf(d, d, qv);
+            d = fmaf(__uint_as_float(r[4 * j4]), inv3, b.x) - mean; qv = fmaf(d, d, qv);
+            d = fmaf(__uint_as_float(r[4 * j4 + 1]), inv3, b.y) - mean; qv = fmaf(d, d, qv);
+            d = fmaf(__uint_as_float(r[4 * j4 + 2]), inv3, b.z) - mean; qv = fmaf(d, d, qv);
+            d = fmaf(__uint_as_float(r[4 * j4 + 3]), inv3, b.w) - mean; qv = fmaf(d, d, qv);
           }
         }
         sRed[256 + h * 128 + erow] = qv;
@@ -431,7 +546,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         if (sc == 4 * h + 3) {  // this warp's last TMEM read of the tile
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(B_DFREE + acc));
+          if (lane == 0) mbar_arrive(BAR(FB_DFREE + acc));
         }
         float* v = reinterpret_cast<float*>(r);
         if (FVGN_DBG(p) & 32) continue;
@@ -439,14 +554,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
-            v[4 * j4] += b.x; v[4 * j4 + 1] += b.y; v[4 * j4 + 2] += b.z; v[4 * j4 + 3] += b.w;
+            v[4 * j4] = fmaf(v[4 * j4], inv3, b.x); v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], inv3, b.y);
+            v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], inv3, b.z); v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], inv3, b.w);
           }
           store_rows16(v, p.zsave, 384, 256 + 16 * sc, row0 + 32 * q);
         }
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b = p.zsave ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
-          float y0 = v[4 * j4] + b.x, y1 = v[4 * j4 + 1] + b.y, y2 = v[4 * j4 + 2] + b.z, y3 = v[4 * j4 + 3] + b.w;
+          float y0 = v[4 * j4], y1 = v[4 * j4 + 1], y2 = v[4 * j4 + 2], y3 = v[4 * j4 + 3];
+          if (!p.zsave) {  // (with z_save the bias and scale were applied above)
+            const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
+            y0 = fmaf(y0, inv3, b.x); y1 = fmaf(y1, inv3, b.y); y2 = fmaf(y2, inv3, b.z); y3 = fmaf(y3, inv3, b.w);
+          }
           if (has_ln) {
             const float4 w = *reinterpret_cast<const float4*>(gw + 16 * sc + 4 * j4);
             const float4 o = *reinterpret_cast<const float4*>(gb + 16 * sc + 4 * j4);
@@ -494,7 +613,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           }
         }
       }
+      PROF_ADD(4);  // final epilogue work
     }
+    if (tid == 0) PROF_FLUSH(8);
   }
   tc_fence_before();
   __syncthreads();
@@ -1102,26 +1223,53 @@ __global__ void __launch_bounds__(1024) colsum_reduce_kernel(const ColsumParams 
   }
 }
 
-// W [n_valid, k_valid] fp32 row-major -> steps [kt][3 splits][128 rows][64 k] bf16, each sub-tile a byte image of the swizzled layout
-__global__ void pack_tiles3_kernel(const float* __restrict__ W, int ldw, int n_valid, int k_valid, int kt, unsigned char* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (tile, n, chunk)
-  if (idx >= kt * 128 * 8) return;
-  const int c = idx & 7, n = (idx >> 3) & 127, t = idx >> 10;
-  uint4 q0, q1, q2;
-  uint32_t* a0 = reinterpret_cast<uint32_t*>(&q0);
-  uint32_t* a1 = reinterpret_cast<uint32_t*>(&q1);
-  uint32_t* a2 = reinterpret_cast<uint32_t*>(&q2);
+// Forward weights: one CTA per weight matrix.  W [n_valid, k_valid] fp32 row-major -> scale 2^s with max|W| 2^s in [2^13, 2^14)
+// (found here, on the device: graph-capturable, no host round trip) -> steps [kt][2 fp16 splits][128 rows][64 k], each sub-tile a
+// byte image of the swizzled layout; the epilogue factor 1 / (ASCALE 2^s) goes to the header behind the last step.
+struct PackFwdParams { const float* w[3]; int ldw[3], n_valid[3], k_valid[3], kt[3], step0[3]; unsigned char* out; int nsteps; };
+__global__ void __launch_bounds__(1024) pack_fwd_h2_kernel(const PackFwdParams p) {
+  __shared__ float s_max[32];
+  __shared__ float s_scale;
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const float* W = p.w[m];
+  const int ldw = p.ldw[m], nv = p.n_valid[m], kv = p.k_valid[m], kt = p.kt[m];
+  float mx = 0.f;
+  for (int i = tid; i < nv * kv; i += 1024) mx = fmaxf(mx, fabsf(W[(size_t)(i / kv) * ldw + (i % kv)]));
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k = t * KTILE + c * 8 + 2 * j;
-    const float x = (n < n_valid && k < k_valid) ? W[(size_t)n * ldw + k] : 0.f;
-    const float y = (n < n_valid && k + 1 < k_valid) ? W[(size_t)n * ldw + k + 1] : 0.f;
-    split3_pair(x, y, a0[j], a1[j], a2[j]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) s_max[tid >> 5] = mx;
+  __syncthreads();
+  if (tid < 32) {
+    mx = s_max[tid];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (tid == 0) {
+      // 2^(13 - floor(log2 max)) from the exponent field; a zero / tiny (< 2^-95) / non-finite matrix is left unscaled
+      const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu);
+      const float sc = (e < 32 || e == 255) ? 1.0f : __uint_as_float((uint32_t)(127 + 13 - (e - 127)) << 23);
+      s_scale = sc;
+      reinterpret_cast<float*>(p.out + (size_t)p.nsteps * FW_SLOT)[m] = 1.0f / (ASCALE * sc);  // exact: powers of two
+    }
   }
-  const size_t off = (size_t)t * SLOT_BYTES + (size_t)n * 128 + (((uint32_t)c ^ ((uint32_t)n & 7u)) << 4);
-  *reinterpret_cast<uint4*>(out + off) = q0;
-  *reinterpret_cast<uint4*>(out + TILE_BYTES + off) = q1;
-  *reinterpret_cast<uint4*>(out + 2 * TILE_BYTES + off) = q2;
+  __syncthreads();
+  const float sc = s_scale;
+  unsigned char* out = p.out + (size_t)p.step0[m] * FW_SLOT;
+  for (int idx = tid; idx < kt * 1024; idx += 1024) {  // (tile, n, 16-byte chunk)
+    const int c = idx & 7, n = (idx >> 3) & 127, t = idx >> 10;
+    uint4 q0, q1;
+    uint32_t* a0 = reinterpret_cast<uint32_t*>(&q0);
+    uint32_t* a1 = reinterpret_cast<uint32_t*>(&q1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = t * KTILE + c * 8 + 2 * j;
+      const float x = (n < nv && k < kv) ? W[(size_t)n * ldw + k] * sc : 0.f;
+      const float y = (n < nv && k + 1 < kv) ? W[(size_t)n * ldw + k + 1] * sc : 0.f;
+      split2_pair(x, y, a0[j], a1[j]);
+    }
+    const size_t off = (size_t)t * FW_SLOT + (size_t)n * 128 + (((uint32_t)c ^ ((uint32_t)n & 7u)) << 4);
+    *reinterpret_cast<uint4*>(out + off) = q0;
+    *reinterpret_cast<uint4*>(out + TILE_BYTES + off) = q1;
+  }
 }
 
 static int kt_of(int k_in) { return (k_in + KTILE - 1) / KTILE; }
@@ -1137,15 +1285,25 @@ int tc3_pack(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t st) {
   FVGN_CHECK_ARG(bytes >= tc3_packed_bytes(m->k_in), "packed buffer too small");
   FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed buffer must be 16B aligned");
   const int kt1 = kt_of(m->k_in);
-  unsigned char* o = reinterpret_cast<unsigned char*>(packed);
-  pack_tiles3_kernel<<<cdiv(kt1 * 1024, 256), 256, 0, st>>>(m->w1, m->k_in, 128, m->k_in, kt1, o);
-  FVGN_LAUNCH_CHECK();
-  pack_tiles3_kernel<<<cdiv(2 * 1024, 256), 256, 0, st>>>(m->w2, 128, 128, 128, 2, o + (size_t)kt1 * SLOT_BYTES);
-  FVGN_LAUNCH_CHECK();
-  pack_tiles3_kernel<<<cdiv(2 * 1024, 256), 256, 0, st>>>(m->w3, 128, m->n_out, 128, 2, o + (size_t)(kt1 + 2) * SLOT_BYTES);
+  PackFwdParams p;
+  p.w[0] = m->w1; p.ldw[0] = m->k_in; p.n_valid[0] = 128; p.k_valid[0] = m->k_in; p.kt[0] = kt1; p.step0[0] = 0;
+  p.w[1] = m->w2; p.ldw[1] = 128; p.n_valid[1] = 128; p.k_valid[1] = 128; p.kt[1] = 2; p.step0[1] = kt1;
+  p.w[2] = m->w3; p.ldw[2] = 128; p.n_valid[2] = m->n_out; p.k_valid[2] = 128; p.kt[2] = 2; p.step0[2] = kt1 + 2;
+  p.out = reinterpret_cast<unsigned char*>(packed);
+  p.nsteps = kt1 + 4;
+  pack_fwd_h2_kernel<<<3, 1024, 0, st>>>(p);
   FVGN_LAUNCH_CHECK();
   return 0;
 }
+
+#if FVGN_TC_TIMING_EXPERIMENTS
+extern "C" __attribute__((visibility("default"))) int fvgn_dbg_x3_prof(unsigned long long* out32, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, x3::g_prof, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(x3::g_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t st) {
   using namespace x3;
@@ -1157,12 +1315,12 @@ static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t
   p.packed = reinterpret_cast<const unsigned char*>(m->packed_x3);
   p.b1 = m->b1; p.b2 = m->b2; p.b3 = m->b3; p.ln_w = m->ln_w; p.ln_b = m->ln_b;
   p.k_in = m->k_in; p.n_out = m->n_out;
-  p.nprod = m->n_products == 1 ? 1 : 6;
+  p.nprod = m->n_products == 1 ? 1 : 3;
   p.zsave = m->z_save;
   if (p.zsave) FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(p.zsave) & 15) == 0, "z_save must be 16B aligned");
   p.kt1 = kt_of(m->k_in);
   p.ntiles = cdiv(p.rows, TM);
-  const SmemLayout L = smem_layout();
+  const SmemLayout L = smem_layout_fwd();
   const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
 #define FVGN_TC3_LAUNCH(MODE, RED)                                                                                       \
   do {                                                                                                                   \
