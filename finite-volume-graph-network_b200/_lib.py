@@ -49,6 +49,8 @@ _SIGS = {
     "fvgn_edge_block_fwd": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P, _I, _P]),
     "fvgn_cell_block_fwd_xbf16": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _I, _P]),
     "fvgn_edge_block_fwd_xbf16": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _I, _P]),
+    "fvgn_cell_block_fwd_split": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P]),
+    "fvgn_edge_block_fwd_split": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P]),
     "fvgn_face_area_bn_fwd": (_I, [_P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fvgn_face_area_sums": (_I, [_P, _P, _P, _I, _F, _P, _P, _P, _P]),
     "fvgn_integrator_fwd": (_I, [_P, _P, _P, _P, _I, _F, _F, _P, _P, _P]),
@@ -86,7 +88,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.fvgn_abi_version() != 5:
+        if L.fvgn_abi_version() != 6:
             raise RuntimeError("libfvgn_b200.so ABI version mismatch")
         _lib = L
     return _lib

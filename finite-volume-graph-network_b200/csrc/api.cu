@@ -38,6 +38,8 @@ int tc_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*,
 int tc3_mlp_rows(const fvgn_mlp_t*, const float*, int, int, float*, int, cudaStream_t);
 int tc3_cell_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, cudaStream_t);
 int tc3_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, cudaStream_t);
+int tc3_cell_block_sh(const fvgn_mlp_t*, float*, const float*, const int32_t*, int, void*, cudaStream_t);
+int tc3_edge_block_sh(const fvgn_mlp_t*, const void*, float*, const int32_t*, int, cudaStream_t);
 size_t tc3_packed_bytes(int k_in);
 int tc3_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
 size_t tc3_packed_bwd_bytes(int k_in);
@@ -151,6 +153,18 @@ extern "C" int fvgn_edge_block_fwd_xbf16(const fvgn_mlp_t* mlp, const uint16_t* 
   if (math_mode != FVGN_MATH_BF16_TC) { set_error("fvgn_edge_block_fwd_xbf16: tensor-core math mode only"); return FVGN_E_BADARG; }
   if (!x_prime_bf16) { set_error("fvgn_edge_block_fwd_xbf16: x_prime_bf16 is NULL"); return FVGN_E_BADARG; }
   return tc_edge_block(mlp, nullptr, e, neighbour_cell, n_faces, nullptr, e, math_mode, as_stream(stream), x_prime_bf16);
+}
+
+extern "C" int fvgn_cell_block_fwd_split(const fvgn_mlp_t* mlp, float* x, const float* node_agg, const int32_t* cells_node_T, int n_cells,
+                                         void* x_prime_split, fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  return tc3_cell_block_sh(mlp, x, node_agg, cells_node_T, n_cells, x_prime_split, as_stream(stream));
+}
+
+extern "C" int fvgn_edge_block_fwd_split(const fvgn_mlp_t* mlp, const void* x_prime_split, float* e, const int32_t* neighbour_cell,
+                                         int n_faces, fvgn_stream_t stream) {
+  if (int er = check_device()) return er;
+  return tc3_edge_block_sh(mlp, x_prime_split, e, neighbour_cell, n_faces, as_stream(stream));
 }
 
 extern "C" size_t fvgn_mlp_packed_x3_bwd_bytes(int k_in) { return tc3_packed_bwd_bytes(k_in); }

@@ -79,6 +79,11 @@ struct Params {
   float* out0; int ld_out;
   float* out1;
   float* zsave;                 // optional [rows, 384]: pre-activations (z1 | z2 | z3) for the backward
+  // SH variant (inference): x', which only ever feeds the EdgeBlock's gathers, travels as a "split shadow" [C][hi plane 128 fp16 |
+  // lo plane 128 fp16] (512 B per row, values pre-scaled by ASCALE): written by the CellBlock epilogue, moved by cp.async straight
+  // into the EdgeBlock's A ring (no registers, no conversion work for 4 of its 6 K-tile steps)
+  const unsigned char* sh_in0;  // EDGE: shadow of x' (gathered)
+  unsigned char* sh_prime;      // CELL: shadow of x' (out)
   const unsigned char* packed;  // [kt1 + 4] steps x [3 splits] x 16 KB
   const float* b1; const float* b2; const float* b3; const float* ln_w; const float* ln_b;
 };
@@ -138,6 +143,16 @@ __device__ __forceinline__ void st_slot2_f4(unsigned char* slot, int r, int hl, 
   *reinterpret_cast<uint2*>(slot + TILE_BYTES + off) = q1;
 }
 
+// 4 consecutive latent values of one row -> the two planes of a split shadow row
+__device__ __forceinline__ void st_shadow_f4(unsigned char* base, size_t row, int col, float4 v) {
+  uint2 q0, q1;
+  split2_pair(v.x * ASCALE, v.y * ASCALE, q0.x, q1.x);
+  split2_pair(v.z * ASCALE, v.w * ASCALE, q0.y, q1.y);
+  unsigned char* d = base + row * 512 + (size_t)col * 2;
+  *reinterpret_cast<uint2*>(d) = q0;
+  *reinterpret_cast<uint2*>(d + 256) = q1;
+}
+
 struct SmemLayout {
   uint32_t a_off, w_off, stage_off, par_off, red_off, bar_off, total;
 };
@@ -179,7 +194,7 @@ enum { B_AFULL = 0, B_AEMPTY = B_AFULL + ARING, B_WFULL = B_AEMPTY + ARING, B_WE
 __host__ __device__ constexpr int prod_a(int q) { return q == 2 || q == 4 ? 1 : (q == 5 ? 2 : 0); }  // 0 0 1 0 1 2
 __host__ __device__ constexpr int prod_w(int q) { return q == 1 || q == 4 ? 1 : (q == 3 ? 2 : 0); }  // 0 1 0 2 1 0
 
-template <int MODE, bool RED>
+template <int MODE, bool RED, bool SH>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const SmemLayout L = smem_layout_fwd();
@@ -310,13 +325,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       PROF_ADD(2);  // split + store (includes the wait for the gathered data)
     };
     PROF_T0();
-    float4 va[RPT], vb[RPT];
+    if (SH && MODE == TC_EDGE) {
+      // gathered x' rows come from the split shadow: cp.async 16-byte chunks straight into the swizzled ring slots; 16 lanes move one
+      // row (2 planes x 128 B), 8 rows per thread and K-tile step.  A step is published one step later (its cp.async group done).
+      const int plane = hl >> 3, chunk = hl & 7;
+      auto publish = [&](int s) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(FB_AFULL + (uint32_t)s % FARING));
+      };
 #pragma unroll 1
-    for (int s = -1; s < S; s += 2) {
-      if (s + 1 < S) load(s + 1, va);
-      if (s >= 0) store(s, vb);
-      if (s + 2 < S) load(s + 2, vb);
-      if (s + 1 < S) store(s + 1, va);
+      for (int s = 0; s < S; ++s) {
+        const uint32_t slot = (uint32_t)s % FARING;
+        const int jl = s / kt1, t = s - jl * kt1;
+        const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+        PROF_ADD(0);
+        if (s >= FARING) mbar_wait(BAR(FB_AEMPTY + slot), (((uint32_t)s / FARING) - 1) & 1, 1);
+        PROF_ADD(1);
+        unsigned char* dst = sA + slot * FA_SLOT;
+        if (t >= 4) {  // this tile's own e rows (fp32 master): through registers
+          float4 v[RPT];
+          const float* base = p.src1 + (t & 1) * 64 + hl * 4;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) v[i] = ldg4(base + (size_t)min(row0 + hw + NHW * i, last) * 128);
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) st_slot2_f4(dst, hw + NHW * i, hl, v[i]);
+        } else {
+          const unsigned char* src = p.sh_in0 + plane * 256 + (t & 1) * 128 + chunk * 16;
+          const uint32_t d0 = smem_u32(dst) + (uint32_t)plane * TILE_BYTES;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int r = hw + NHW * i;
+            cp_async16(d0 + (uint32_t)r * 128u + (((uint32_t)chunk ^ ((uint32_t)r & 7u)) << 4), src + (size_t)nidx[i] * 512);
+          }
+          if (t & 1) {  // index set used up: the receivers of this tile / the senders of the next tile
+            const int r0 = (t == 3) ? row0 + (int)gridDim.x * TM : row0;
+            const int32_t* ip = p.idx + (t == 3 ? 0 : (size_t)p.rows);
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) nidx[i] = __ldg(ip + min(r0 + hw + NHW * i, last));
+          }
+        }
+        cp_async_commit();
+        if (s >= 1) { cp_async_wait<1>(); publish(s - 1); }
+        PROF_ADD(2);
+      }
+      if (S > 0) { cp_async_wait<0>(); publish(S - 1); }
+    } else {
+      float4 va[RPT], vb[RPT];
+#pragma unroll 1
+      for (int s = -1; s < S; s += 2) {
+        if (s + 1 < S) load(s + 1, va);
+        if (s >= 0) store(s, vb);
+        if (s + 2 < S) load(s + 2, vb);
+        if (s + 1 < S) store(s + 1, va);
+      }
     }
     if (ptid == 0) PROF_FLUSH(16);
   } else if (warp == WARP_LOAD) {
@@ -593,6 +655,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
               } else {
                 const size_t off = (size_t)grow * 128 + col;
                 if (p.out0) *reinterpret_cast<float4*>(p.out0 + off) = y;
+                if (SH && MODE == TC_CELL) st_shadow_f4(p.sh_prime, (size_t)grow, col, y);
                 if (RED) red_add_f4(p.out1 + off, y);
                 else if (p.out1) {
                   const float4 rv = *reinterpret_cast<const float4*>(res + off);
@@ -1305,7 +1368,7 @@ extern "C" __attribute__((visibility("default"))) int fvgn_dbg_x3_prof(unsigned 
 }
 #endif
 
-static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t st) {
+static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t st, bool sh = false) {
   using namespace x3;
   if (p.rows <= 0) return 0;
 #if FVGN_TC_TIMING_EXPERIMENTS
@@ -1322,20 +1385,24 @@ static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t
   p.ntiles = cdiv(p.rows, TM);
   const SmemLayout L = smem_layout_fwd();
   const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
-#define FVGN_TC3_LAUNCH(MODE, RED)                                                                                       \
+#define FVGN_TC3_LAUNCH(MODE, RED, SH)                                                                                   \
   do {                                                                                                                   \
     static bool configured = false;                                                                                      \
     if (!configured) {                                                                                                   \
-      FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc3_kernel<MODE, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
+      FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc3_kernel<MODE, RED, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
       configured = true;                                                                                                 \
     }                                                                                                                    \
-    fused_mlp_tc3_kernel<MODE, RED><<<grid, NTHREADS, L.total, st>>>(p);                                                 \
+    fused_mlp_tc3_kernel<MODE, RED, SH><<<grid, NTHREADS, L.total, st>>>(p);                                             \
   } while (0)
-  if (p.mode == TC_ROWS) FVGN_TC3_LAUNCH(TC_ROWS, false);
-  else if (p.mode == TC_CELL && red) FVGN_TC3_LAUNCH(TC_CELL, true);
-  else if (p.mode == TC_CELL) FVGN_TC3_LAUNCH(TC_CELL, false);
-  else if (red) FVGN_TC3_LAUNCH(TC_EDGE, true);
-  else FVGN_TC3_LAUNCH(TC_EDGE, false);
+  if (sh) {
+    FVGN_CHECK_ARG(!p.zsave && red && p.mode != TC_ROWS, "the split-shadow (inference) variants update the latent in place and save nothing");
+    if (p.mode == TC_CELL) FVGN_TC3_LAUNCH(TC_CELL, true, true);
+    else FVGN_TC3_LAUNCH(TC_EDGE, true, true);
+  } else if (p.mode == TC_ROWS) FVGN_TC3_LAUNCH(TC_ROWS, false, false);
+  else if (p.mode == TC_CELL && red) FVGN_TC3_LAUNCH(TC_CELL, true, false);
+  else if (p.mode == TC_CELL) FVGN_TC3_LAUNCH(TC_CELL, false, false);
+  else if (red) FVGN_TC3_LAUNCH(TC_EDGE, true, false);
+  else FVGN_TC3_LAUNCH(TC_EDGE, false, false);
 #undef FVGN_TC3_LAUNCH
   FVGN_LAUNCH_CHECK();
   return 0;
@@ -1379,6 +1446,31 @@ int tc3_edge_block(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, 
   return launch_tc3(p, mlp, e_out != nullptr && e_out == e, st);
 }
 
+// ---- split-shadow (inference) variants: latents are fp32, updated in place; x' only exists as the fp16 hi/lo shadow the EdgeBlock gathers
+static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+int tc3_cell_block_sh(const fvgn_mlp_t* mlp, float* x, const float* node_agg, const int32_t* cells_node_T, int n_cells, void* x_prime_sh,
+                      cudaStream_t st) {
+  if (int e = check_mlp3(mlp, true)) return e;
+  FVGN_CHECK_ARG(mlp->k_in == 192, "CellBlock MLP must have k_in == 192");
+  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && node_agg && cells_node_T && x_prime_sh)), "NULL input");
+  FVGN_CHECK_ARG(al16(x) && al16(x_prime_sh) && al16(node_agg), "buffers must be 16B aligned");
+  x3::Params p{};
+  p.mode = x3::TC_CELL; p.rows = n_cells; p.src0 = x; p.src1 = node_agg; p.idx = cells_node_T; p.out1 = x; p.ld_out = 128;
+  p.sh_prime = reinterpret_cast<unsigned char*>(x_prime_sh);
+  return launch_tc3(p, mlp, true, st, true);
+}
+
+int tc3_edge_block_sh(const fvgn_mlp_t* mlp, const void* x_prime_sh, float* e, const int32_t* neighbour_cell, int n_faces, cudaStream_t st) {
+  if (int er = check_mlp3(mlp, true)) return er;
+  FVGN_CHECK_ARG(mlp->k_in == 384, "EdgeBlock MLP must have k_in == 384");
+  FVGN_CHECK_ARG(n_faces >= 0 && (n_faces == 0 || (x_prime_sh && e && neighbour_cell)), "NULL input");
+  FVGN_CHECK_ARG(al16(x_prime_sh) && al16(e), "buffers must be 16B aligned");
+  x3::Params p{};
+  p.mode = x3::TC_EDGE; p.rows = n_faces; p.src1 = e; p.idx = neighbour_cell; p.out1 = e; p.ld_out = 128;
+  p.sh_in0 = reinterpret_cast<const unsigned char*>(x_prime_sh);
+  return launch_tc3(p, mlp, true, st, true);
+}
 
 // ---- backward (data-gradient chain) host side
 size_t tc3_packed_bwd_bytes(int k_in) { return (size_t)(4 + 2 * ((k_in + 127) / 128)) * x3::SLOT_BYTES; }

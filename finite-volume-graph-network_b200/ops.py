@@ -283,6 +283,34 @@ def gn_block_fwd_inplace_bf16(cell_mlp: MlpRef, edge_mlp: MlpRef, x, e, node_agg
     return x, e
 
 
+def _split_ok(t, rows, name):
+    if t.dtype != torch.float16 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != (rows, 2, HID):
+        raise ValueError(f"{name} must be a contiguous CUDA float16 tensor of shape [{rows}, 2, {HID}]")
+    return t
+
+
+def gn_block_fwd_inplace_split(cell_mlp: MlpRef, edge_mlp: MlpRef, x, e, node_agg, cells_node_T, neighbour_cell, x_prime_split):
+    """Inference fast path of one GnBlock in the fp32-equivalent mode after the node aggregation: x += x', e += e' in place; x' only
+    exists as the split fp16 shadow the EdgeBlock gathers (fvgn_cell_block_fwd_split / fvgn_edge_block_fwd_split)."""
+    _req(x, torch.float32, "x", 2), _req(e, torch.float32, "edge_attr", 2), _req(node_agg, torch.float32, "node_agg", 2)
+    _ci(cells_node_T, "cells_node_T", 3), _ci(neighbour_cell, "neighbour_cell", 2)
+    Cn, F = x.shape[0], e.shape[0]
+    if not (x.is_contiguous() and e.is_contiguous() and node_agg.is_contiguous()) or x.shape[1] != HID or e.shape[1] != HID \
+            or cells_node_T.shape[1] != Cn or neighbour_cell.shape[1] != F:
+        raise ValueError("gn_block_fwd_inplace_split: bad shapes/strides")
+    _split_ok(x_prime_split, Cn, "x_prime_split")
+    cell_mlp.ensure_packed(2), edge_mlp.ensure_packed(2)
+    L = _lib.lib()
+    _count(2)
+    with _timed("cell_block"):
+        check(L.fvgn_cell_block_fwd_split(C.byref(cell_mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(x_prime_split), _stream()),
+              "cell_block_fwd_split")
+    with _timed("edge_block"):
+        check(L.fvgn_edge_block_fwd_split(C.byref(edge_mlp.struct), _p(x_prime_split), _p(e), _p(neighbour_cell), F, _stream()),
+              "edge_block_fwd_split")
+    return x, e
+
+
 # ------------------------------------------------------------------------------------------------ connectivity
 def build_connectivity(cells, mesh_pos, node_type, face_rule="B"):
     """a1 on device.  cells int32[C,3], mesh_pos f32[N,2], node_type int32[N] (CUDA) -> dict of tables in the H5 layout of

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FVGN_ABI_VERSION 5
+#define FVGN_ABI_VERSION 6
 #define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
 
 #define FVGN_E_BADARG (-1)
@@ -176,6 +176,16 @@ FVGN_API int fvgn_cell_block_fwd_xbf16(const fvgn_mlp_t* mlp, float* x /*[C,128]
                                        int n_cells, uint16_t* x_prime_bf16 /*[C,128] out*/, int math_mode, fvgn_stream_t stream);
 FVGN_API int fvgn_edge_block_fwd_xbf16(const fvgn_mlp_t* mlp, const uint16_t* x_prime_bf16 /*[C,128]*/, float* e /*[F,128] in/out*/,
                                        const int32_t* neighbour_cell, int n_faces, int math_mode, fvgn_stream_t stream);
+
+/* Inference fast path of one GnBlock in the fp32-equivalent mode (FVGN_MATH_BF16X3_TC): both latents are updated IN PLACE
+ * (x += x', e += e'), and x' — which only ever feeds the EdgeBlock's gathers — travels between the two kernels as a "split shadow"
+ * [C][2][128] of fp16 (512 B per row: the hi plane fp16(8 v), then the lo plane fp16(8 v - hi)), i.e. exactly the two-term
+ * tensor-core operand: the EdgeBlock moves it from HBM into its operand tiles by cp.async, with no conversion work.  Results are
+ * bit-identical to fvgn_cell_block_fwd + fvgn_edge_block_fwd in FVGN_MATH_BF16X3_TC mode. */
+FVGN_API int fvgn_cell_block_fwd_split(const fvgn_mlp_t* mlp, float* x /*[C,128] in/out*/, const float* node_agg, const int32_t* cells_node_T,
+                                       int n_cells, void* x_prime_split /*[C,2,128] fp16 out*/, fvgn_stream_t stream);
+FVGN_API int fvgn_edge_block_fwd_split(const fvgn_mlp_t* mlp, const void* x_prime_split /*[C,2,128] fp16*/, float* e /*[F,128] in/out*/,
+                                       const int32_t* neighbour_cell, int n_faces, fvgn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * a10. face-area feature + BatchNorm1d(1) (FVGN.py:77-79, 209-227 / 286-304):

@@ -60,6 +60,37 @@ def test_x3_cell_and_edge_block(fv, golden):
     assert torch.equal(xp2, xp) and torch.equal(x2, xo) and torch.equal(e2, eo)
 
 
+def _split_of(t):
+    hi = (t * 8.0).half()
+    lo = (t * 8.0 - hi.float()).half()
+    return torch.stack([hi, lo], dim=1)
+
+
+def test_x3_split_shadow_fast_path_is_bit_identical(fv, golden):
+    """The inference fast path (latents in place, x' only as the split fp16 shadow moved by cp.async: fvgn_*_fwd_split) against the
+    generic fp32-equivalent calls: same bits, and the shadow is exactly the two-term fp16 split of x'."""
+    g, tab = _tiny(golden)
+    C, F, N = tab["cells_node"].shape[0], tab["face"].shape[1], tab["mesh_pos"].shape[0]
+    gen = torch.Generator().manual_seed(7)
+    x0, e0 = torch.randn(C, 128, generator=gen).cuda(), torch.randn(F, 128, generator=gen).cuda()
+    cb, _ = _mlp_module(fv, 192, seed=4)
+    eb, _ = _mlp_module(fv, 384, seed=5)
+    cnT = torch.as_tensor(tab["cells_node"]).to(torch.int32).T.contiguous().cuda()
+    nc = torch.as_tensor(np.ascontiguousarray(tab["neighbour_cell"])).to(torch.int32).cuda()
+    ptr, items = fv.ops.build_csr(dev(tab["face"], torch.int32).reshape(-1), N)
+    x, e = x0.clone(), e0.clone()
+    xr, er = x0.clone(), e0.clone()
+    xps = torch.empty((C, 2, 128), dtype=torch.float16, device="cuda")
+    for layer in range(3):
+        na = fv.ops.node_aggregate_fwd(er, ptr, items, N)
+        xp, xr = fv.ops.cell_block_fwd(cb.mlp_ref(), xr, na, cnT, math_mode=X3)
+        _, er = fv.ops.edge_block_fwd(eb.mlp_ref(), xp, er, nc, math_mode=X3)
+        na2 = fv.ops.node_aggregate_fwd(e, ptr, items, N)
+        fv.ops.gn_block_fwd_inplace_split(cb.mlp_ref(), eb.mlp_ref(), x, e, na2, cnT, nc, xps)
+        assert torch.equal(x, xr) and torch.equal(e, er), layer
+        assert torch.equal(xps, _split_of(xp)), layer
+
+
 def test_x3_forward_against_reference_fixture_and_rollout(fv, golden):
     g = golden("fwd_tiny.npz")
     model = _model(fv, g).set_math_mode("bf16x3")

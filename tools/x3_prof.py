@@ -66,3 +66,24 @@ for it in range(2):
     if it:
         print("cell launch %.1f us" % (t * 1e3))
         show("CELL", read(), L)
+
+# split-shadow (inference fast path) variants
+xps = torch.empty((Cn, 2, 128), dtype=torch.float16, device="cuda").normal_()
+import ctypes
+P = lambda t: ctypes.c_void_p(t.data_ptr())
+S = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+for name, call in (("EDGE split", lambda: lib.fvgn_edge_block_fwd_split(ctypes.byref(eb.mlp_ref().struct), P(xps), P(e), P(nc), F, S())),
+                   ("CELL split", lambda: lib.fvgn_cell_block_fwd_split(ctypes.byref(cb.mlp_ref().struct), P(x), P(nagg), P(cnT), Cn, P(xps), S()))):
+    for it in range(2):
+        e.normal_(), x.normal_()
+        read()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(L):
+            rc = call()
+            assert rc == 0, lib.fvgn_last_error()
+        ev1.record()
+        torch.cuda.synchronize()
+        if it:
+            print("%s launch %.1f us" % (name, ev0.elapsed_time(ev1) / L * 1e3))
+            show(name, read(), L)
