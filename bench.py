@@ -126,60 +126,67 @@ def measure_forward(args, workload, math, steps, rank, local_rank, dev, dist):
             getmp.y = ge.y[:, 0, :]
             model(graph=gtmp, graph_edge=getmp, graph_node=gn, rho=RHO, mu=MU, dt=DT, edge_one_hot=9, cell_one_hot=0)
     model.eval()
-    state = fv.dataset.RolloutState(gc, ge)
     x_host0 = gc.x.cpu().pin_memory()
     ea_host0 = gc.edge_attr.cpu().pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def step():
-        uvp, nuv = model(graph=gc, graph_edge=ge, graph_node=gn, rho=RHO, mu=MU, dt=DT, edge_one_hot=9, cell_one_hot=0)
-        state.advance_(gc, nuv)
-        return uvp, nuv
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The step a user runs in a rollout loop: fv.GraphedRollout.step() = FVGN.forward (eval) + create_next_graph captured once into a
+    # CUDA graph (same kernels, same bits as the eager calls; the ~57 Python-side launches per step no longer bound a cylinder-sized step)
+    l0 = ops.LAUNCHES
+    gr = fv.GraphedRollout(model, gn, ge, gc, RHO, MU, DT, edge_one_hot=9, cell_one_hot=0, warmup=2)
+    launches_per_step = (ops.LAUNCHES - l0) // 3  # 2 eager warm-up steps + the captured one
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
-            step()
+            gr.step()
         # ---------------- device-resident timing: K steps, L2 flushed between steps, CUDA events per step
-        ops.TIMING = {"edge_block": [], "cell_block": [], "node_aggregate": []}
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
-        l0 = ops.LAUNCHES
         with ClockSampler(local_rank) as clk:
             for k in range(steps):
                 flush.zero_()
                 ev[k][0].record()
-                step()
+                gr.step()
                 ev[k][1].record()
             barrier()
-        launches = ops.LAUNCHES - l0
+        launches = launches_per_step * steps
         ms = sum(a.elapsed_time(b) for a, b in ev)
-        kern = {k: [a.elapsed_time(b) for a, b in v] for k, v in ops.TIMING.items()}
-        ops.TIMING = None
         # ---------------- end-to-end through the public API with HOST buffers: H2D inputs + D2H results every step
         x_host, ea_host = x_host0.clone().pin_memory(), ea_host0.clone().pin_memory()
         nuv_host = torch.empty((C, 2), dtype=torch.float32).pin_memory()
         uvp_host = torch.empty((F, 3), dtype=torch.float32).pin_memory()
-        for k in range(2):
-            gc.x, gc.edge_attr = x_host.to(dev, non_blocking=True), ea_host.to(dev, non_blocking=True)
-            uvp, nuv = step()
+
+        def e2e_step():
+            gr.state.x0.copy_(x_host, non_blocking=True), gr.state.ea0.copy_(ea_host, non_blocking=True)
+            uvp, nuv = gr.step()
             nuv_host.copy_(nuv, non_blocking=True), uvp_host.copy_(uvp, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller consumes the result on the host every step
+            x_host[:, 2:4].copy_(nuv_host)              # host-side autoregression (next step's input comes from the host)
+
+        for k in range(2):
+            e2e_step()
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for k in range(steps):
-            gc.x, gc.edge_attr = x_host.to(dev, non_blocking=True), ea_host.to(dev, non_blocking=True)
-            uvp, nuv = step()
-            nuv_host.copy_(nuv, non_blocking=True), uvp_host.copy_(uvp, non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller consumes the result on the host every step
-            x_host[:, 2:4].copy_(nuv_host)              # host-side autoregression (next step's input comes from the host)
+            e2e_step()
         t1.record()
         barrier()
         e2e_ms = t0.elapsed_time(t1)
+        # ---------------- per-kernel CUDA-event timings (outside the timed regions): two eager steps of the same model
+        ksteps = 2
+        ops.TIMING = {"edge_block": [], "cell_block": [], "node_aggregate": []}
+        for k in range(ksteps):
+            flush.zero_()
+            gr._eager_step()
+        torch.cuda.synchronize()
+        kern = {k: [a.elapsed_time(b) for a, b in v] for k, v in ops.TIMING.items()}
+        ops.TIMING = None
+    del gr
     tms = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     cells = torch.tensor([float(C)], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -188,7 +195,7 @@ def measure_forward(args, workload, math, steps, rank, local_rank, dev, dist):
     del flush
     torch.cuda.empty_cache()
     return dict(ms=float(tms[0]), e2e_ms=float(tms[1]), total_cells=float(cells[0]), C=C, F=F, N=N, graphs=len(meshes), launches=int(launches),
-                kern=kern, clocks=clk.summary(), meshes=meshes, steps=steps)
+                kern=kern, ksteps=ksteps, clocks=clk.summary(), meshes=meshes, steps=steps)
 
 
 def rollout_config0(args, dev):
@@ -245,37 +252,37 @@ def roofline_of(m, math, workload):
     kern = m["kern"]
     edge_ms = float(np.mean(kern["edge_block"])) if kern["edge_block"] else None
     ach = edge_bytes / (edge_ms * 1e-3) / 1e9 if edge_ms else None
-    shares = {k: (sum(v) / m["ms"] if v else 0.0) for k, v in kern.items()}
+    shares = {k: ((sum(v) / m["ksteps"]) / (m["ms"] / m["steps"]) if v else 0.0) for k, v in kern.items()}
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         t = json.load(open(tp)).get(f"{workload}:{math}:edge_block")
         traffic = t["dram_bytes_per_launch"] if t else None
     name = {"fp32": "fused_mlp_simt_kernel<EDGE>", "bf16": "fused_mlp_tc_kernel<TC_EDGE, RED, XBF>",
-            "bf16x3": "x3::fused_mlp_tc3_kernel<TC_EDGE, RED>"}[math]
+            "bf16x3": "x3::fused_mlp_tc3_kernel<TC_EDGE, RED, SH>"}[math]
     if math == "bf16x3" and edge_ms:
-        # the fp32-equivalent kernel is tensor-bound: 6 bf16 MMAs per algorithmic product.  Algorithmic GEMM FLOPs per face:
-        # 2*(384*128 + 2*128^2) = 163,840; executed on the tensor pipe: 6x that.
+        # the fp32-equivalent forward kernel runs 3 fp16 MMAs per algorithmic product (two-term fp16 split of both operands).  Algorithmic
+        # GEMM FLOPs per face: 2*(384*128 + 2*128^2) = 163,840; executed on the tensor pipe: 3x that.
         tf_peak = peaks.get("bf16_tflops_sustained", 1375.0)
         alg = 163840.0 * F / (edge_ms * 1e-3) / 1e12
-        return {"kernel": name, "workload": workload, "math": math, "bound": "tensor", "achieved": 6.0 * alg, "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": 6.0 * alg / tf_peak, "traffic": traffic, "avg_launch_ms": edge_ms,
+        return {"kernel": name, "workload": workload, "math": math, "bound": "tensor", "achieved": 3.0 * alg, "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": 3.0 * alg / tf_peak, "traffic": traffic, "avg_launch_ms": edge_ms,
                 "peak_source": ("measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1375 TFLOP/s"),
-                "algorithmic_tflops_fp32_equivalent": alg, "executed_mma_flops_per_launch": int(6 * 163840 * F),
+                "algorithmic_tflops_fp32_equivalent": alg, "executed_mma_flops_per_launch": int(3 * 163840 * F),
                 "launches_timed": len(kern["edge_block"]), "share_of_step": shares,
-                "note": "achieved = executed bf16 MMA FLOPs (six 3-way-split products per fp32-equivalent product) / CUDA-event launch time; "
-                        "the algorithmic (fp32-equivalent) rate is a sixth of it: DESIGN.md §4.3"}
+                "note": "achieved = executed 16-bit MMA FLOPs (three two-term-split products per fp32-equivalent product) / CUDA-event launch "
+                        "time; the algorithmic (fp32-equivalent) rate is a third of it: DESIGN.md §4.3"}
     return {"kernel": name, "workload": workload, "math": math, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
             "frac": (ach / hbm) if ach else None, "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": edge_ms,
             "algorithmic_bytes_per_launch": int(edge_bytes), "launches_timed": len(kern["edge_block"]), "share_of_step": shares,
             "note": {"fp32": "strict-fp32 mode is FFMA(compute)-bound (5.68 MFLOP/cell-update on the FP32 pipes), not HBM-bound: DESIGN.md §4.2",
-                     "bf16x3": "fp32-equivalent mode is tensor/L2-bound (6 MMAs per product, all weights streamed from L2), not HBM-bound: "
+                     "bf16x3": "fp32-equivalent mode is tensor/epilogue-bound (3 MMAs per product, all weights streamed from L2), not HBM-bound: "
                                "DESIGN.md §4.3", "bf16": ""}[math]}
 
 
 DTYPES = {"fp32": "f32 (FFMA)", "bf16": "bf16 tiles, f32 accumulate/residual",
-          "bf16x3": "f32-equivalent: exact 3-way bf16 operand split on tcgen05 (6 MMAs/product), f32 accumulate + f32 epilogue; held to the f32 "
-                    "parity bound (rel 1e-5/step)"}
+          "bf16x3": "f32-equivalent: two-term fp16 split of both operands on tcgen05 (3 MMAs/product; training backward: 3-way bf16 split, "
+                    "6 MMAs/product), f32 accumulate + f32 epilogue; held to the f32 parity bound (rel 1e-5/step)"}
 
 
 def native(args, rank, world, local_rank):
@@ -302,7 +309,7 @@ def native(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.math], "data": "synthetic",
             "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "cells_per_rank": C, "faces_per_rank": F,
                        "nodes_per_rank": N, "graphs_per_rank": len(meshes), "message_passing_layers": 15, "hidden": 128, "math": args.math,
-                       "step": "FVGN.forward (eval) + create_next_graph", "l2": "flushed between timed steps (256 MiB write)",
+                       "step": "fv.GraphedRollout.step(): FVGN.forward (eval) + create_next_graph replayed from one CUDA graph", "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": f"replicas x{world} (independent mesh batches, no collective)"},
             "graphs_per_sec": len(meshes) * world * args.steps / (m["ms"] * 1e-3),
             "e2e": {"value": m["total_cells"] * args.steps / (m["e2e_ms"] * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": int(C * 16 + F * 20),

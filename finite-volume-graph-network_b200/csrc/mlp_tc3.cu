@@ -65,7 +65,7 @@ constexpr int WARP_PROD0 = NEPI / 32, WARP_MMA = WARP_PROD0 + NPW, WARP_LOAD = W
 constexpr int NTHREADS = (WARP_LOAD + 1) * 32;  // 576
 constexpr int RPT = TM / (NPROD / 16);          // 8 rows per producer thread per K-tile
 constexpr uint32_t TMEM_COLS = 512;             // acc0 [0,128) | acc1 [128,256) | H split 0 [256,320) | 1 [320,384) | 2 [384,448)
-constexpr uint32_t TMEM_H0 = 256;               // (the forward kernel has two fp16 H planes: [256,320) | [320,384))
+constexpr uint32_t TMEM_H0 = 256;               // (forward kernel: per tile parity a, hi / lo fp16 H planes at 256 + 128 a, + 64)
 // kind::f16 instruction descriptor with fp16 operands (a_format bits [7,10) = 0, b_format [10,13) = 0); mixing an fp16 A with a
 // bf16 B is an illegal instruction on sm_100a
 constexpr uint32_t IDESC_F16_M128_N128 = IDESC_BF16_M128_N128 & ~0x480u;
@@ -182,7 +182,7 @@ __host__ __device__ inline SmemLayout smem_layout_fwd() {
   return L;
 }
 enum { FB_AFULL = 0, FB_AEMPTY = FB_AFULL + FARING, FB_WFULL = FB_AEMPTY + FARING, FB_WEMPTY = FB_WFULL + FWRING, FB_DFULL = FB_WEMPTY + FWRING,
-       FB_DFREE = FB_DFULL + 2, FB_HREADY = FB_DFREE + 2, FB_COUNT = FB_HREADY + 1 };
+       FB_DFREE = FB_DFULL + 2, FB_HREADY = FB_DFREE + 2, FB_COUNT = FB_HREADY + 2 };
 // the three forward split products, most significant first: (activation split, weight split)
 __host__ __device__ constexpr int fprod_a(int q) { return q == 2 ? 1 : 0; }  // 0 0 1
 __host__ __device__ constexpr int fprod_w(int q) { return q == 1 ? 1 : 0; }  // 0 1 0
@@ -208,15 +208,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt1 = (MODE == TC_EDGE) ? 6 : (MODE == TC_CELL) ? 3 : p.kt1;
   const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  // layer-1 K-tile steps of the NEXT tile issued during this tile's first / second / third epilogue: [0,l1a) [l1a,l1b) [l1b,kt1)
-  const int l1a = (kt1 - 1) / 2 > 1 ? (kt1 - 1) / 2 : 1, l1b = l1a + (kt1 > l1a ? 1 : 0);
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) { printf("fvgn mlp_tc3: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < FARING; ++i) { mbar_init(BAR(FB_AFULL + i), NPW); mbar_init(BAR(FB_AEMPTY + i), 1); }
     for (int i = 0; i < FWRING; ++i) { mbar_init(BAR(FB_WFULL + i), 1); mbar_init(BAR(FB_WEMPTY + i), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(BAR(FB_DFULL + a), 1); mbar_init(BAR(FB_DFREE + a), 8); }
-    mbar_init(BAR(FB_HREADY), 8);
+    mbar_init(BAR(FB_HREADY), 8); mbar_init(BAR(FB_HREADY + 1), 8);
     fence_mbar_init();
   }
   if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -396,15 +394,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         bulk_g2s(smem_u32(sW + slot * FW_SLOT), p.packed + (size_t)step * FW_SLOT, nbytes, BAR(FB_WFULL + slot));
         ++wl;
       };
-      for (int t = 0; t < kt1; ++t) put(t);
+      auto put_l1 = [&]() { for (int t = 0; t < kt1; ++t) put(t); };
+      put_l1();
+      if (n_local > 1) put_l1();
 #pragma unroll 1
-      for (int jl = 0; jl < n_local; ++jl) {  // the MMA issuer's order
-        const bool nxt = jl + 1 < n_local;
-        if (nxt) for (int t = 0; t < l1a; ++t) put(t);
-        put(kt1); put(kt1 + 1);  // W2
-        if (nxt) for (int t = l1a; t < l1b; ++t) put(t);
-        put(kt1 + 2); put(kt1 + 3);  // W3
-        if (nxt) for (int t = l1b; t < kt1; ++t) put(t);
+      for (int k = 0; k < n_local; k += 2) {  // the MMA issuer's order: tiles in pairs (A, B)
+        const bool hasB = k + 1 < n_local;
+        put(kt1); put(kt1 + 1);                    // W2 for A
+        if (hasB) { put(kt1); put(kt1 + 1); }      //        B
+        put(kt1 + 2); put(kt1 + 3);                // W3 for A
+        if (hasB) { put(kt1 + 2); put(kt1 + 3); }  //        B
+        if (k + 2 < n_local) put_l1();
+        if (k + 3 < n_local) put_l1();
       }
       PROF_FLUSH(24);
     }
@@ -412,16 +413,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
   } else if (warp == WARP_MMA) {
     // ================================================================= MMA issuer
     if (lane == 0 && n_local > 0) {
-      uint32_t ak = 0, wk = 0, hphase = 0;
+      uint32_t ak = 0, wk = 0, hphase[2] = {0, 0};
       PROF_DECL;
       PROF_T0();
-      auto layer1 = [&](int jl, int t0, int t1) {  // K-tile steps [t0, t1) of layer 1 of tile jl
+      auto layer1 = [&](int jl) {
         const int a = jl & 1;
-        if (t0 == 0 && jl >= 2) mbar_wait(BAR(FB_DFREE + a), (uint32_t)((jl >> 1) - 1) & 1, 3);
+        if (jl >= 2) mbar_wait(BAR(FB_DFREE + a), (uint32_t)((jl >> 1) - 1) & 1, 3);
         PROF_ADD(0);
         const uint32_t d = tmem_base + 128u * (uint32_t)a;
 #pragma unroll 1
-        for (int t = t0; t < t1; ++t, ++ak, ++wk) {
+        for (int t = 0; t < kt1; ++t, ++ak, ++wk) {
           const uint32_t sa = ak % FARING, sw = wk % FWRING;
           mbar_wait(BAR(FB_AFULL + sa), (ak / FARING) & 1, 4);
           PROF_ADD(1);
@@ -439,13 +440,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           umma_commit(BAR(FB_WEMPTY + sw));
           PROF_ADD(3);
         }
-        if (t1 == kt1 && t1 > t0) umma_commit(BAR(FB_DFULL + a));
+        umma_commit(BAR(FB_DFULL + a));
       };
       auto layer23 = [&](int jl) {  // layer 2 or 3 of tile jl (whichever hidden activation the epilogue has just published)
         const int a = jl & 1;
         const uint32_t d = tmem_base + 128u * (uint32_t)a;
         {
-          mbar_wait(BAR(FB_HREADY), hphase, 7); hphase ^= 1;
+          mbar_wait(BAR(FB_HREADY + a), hphase[a], 7); hphase[a] ^= 1;
           PROF_ADD(4);
 #pragma unroll 1
           for (int t = 0; t < 2; ++t, ++wk) {
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
               for (int q = 0; q < 3; ++q)
-                if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * fprod_a(q) + 8u * (uint32_t)(4 * t + kk),
+                if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16_ts(d, tmem_base + TMEM_H0 + 128u * (uint32_t)a + 64u * fprod_a(q) + 8u * (uint32_t)(4 * t + kk),
                              umma_desc(b_base + fprod_w(q) * TILE_BYTES + kk * 32), IDESC_F16_M128_N128, (t | kk | q) != 0);
             umma_commit(BAR(FB_WEMPTY + sw));
             PROF_ADD(6);
@@ -466,17 +467,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           umma_commit(BAR(FB_DFULL + a));
         }
       };
-      // Layer 1 of the next tile (second accumulator) is issued in three parts, one inside each epilogue window of this tile, so that
-      // layers 2 / 3 never queue behind a layer-1 step that is still waiting for its gathered operand.
-      layer1(0, 0, kt1);
+      // Tiles are processed in pairs (A, B) with their own accumulator and hidden-activation columns; the epilogue warps alternate
+      // between the two (ep1 A, ep1 B, ep2 A, ep2 B, ep3 A, ep3 B), so that every layer-2 / layer-3 product and its barrier round trips
+      // run under the other tile's epilogue, and layer 1 of the next pair runs under this pair's last epilogues.
+      layer1(0);
+      if (n_local > 1) layer1(1);
 #pragma unroll 1
-      for (int jl = 0; jl < n_local; ++jl) {
-        const bool nxt = jl + 1 < n_local;
-        if (nxt) layer1(jl + 1, 0, l1a);
-        layer23(jl);
-        if (nxt) layer1(jl + 1, l1a, l1b);
-        layer23(jl);
-        if (nxt) layer1(jl + 1, l1b, kt1);
+      for (int k = 0; k < n_local; k += 2) {
+        const bool hasB = k + 1 < n_local;
+        layer23(k);
+        if (hasB) layer23(k + 1);
+        layer23(k);
+        if (hasB) layer23(k + 1);
+        if (k + 2 < n_local) layer1(k + 2);
+        if (k + 3 < n_local) layer1(k + 3);
       }
       PROF_FLUSH(0);
 #if FVGN_TC_TIMING_EXPERIMENTS
@@ -517,16 +521,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     };
     PROF_DECL;
     PROF_T0();
-#pragma unroll 1
-    for (int jl = 0; jl < n_local; ++jl) {
+    // hidden-layer epilogue of tile jl: accumulator -> bias + SiLU -> split -> this tile's H columns
+    auto hidden = [&](int jl, int layer) {
       const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
       const int acc = jl & 1;
       const uint32_t t_acc = t_lane + 128u * (uint32_t)acc;
+      const uint32_t t_ha = t_h + 128u * (uint32_t)acc;
       const uint32_t dfull = BAR(FB_DFULL + acc);
       const uint32_t use0 = 3u * (uint32_t)(jl >> 1);
       uint32_t r[16];
-#pragma unroll 1
-      for (int layer = 0; layer < 2; ++layer) {
+      {
         mbar_wait(dfull, (use0 + (uint32_t)layer) & 1, 8);
         PROF_ADD(layer);  // 0: wait for the layer-1 accumulator, 1: layer 2
         tc_fence_after();
@@ -551,15 +555,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             split2_pair(silu_x3(z2) * ASCALE, silu_x3(z3) * ASCALE, p0[2 * j4 + 1], p1[2 * j4 + 1]);
           }
           if (p.zsave) store_rows16(reinterpret_cast<const float*>(r), p.zsave, 384, 128 * layer + 16 * sc, row0 + 32 * q);
-          tmem_st8(t_h + 8 * sc, p0);
-          tmem_st8(t_h + 64 + 8 * sc, p1);
+          tmem_st8(t_ha + 8 * sc, p0);
+          tmem_st8(t_ha + 64 + 8 * sc, p1);
         }
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(FB_HREADY));
+        if (lane == 0) mbar_arrive(BAR(FB_HREADY + acc));
         PROF_ADD(3);  // hidden-layer epilogue work
       }
+    };
+    // last-layer epilogue of tile jl: bias + LayerNorm + residual -> HBM
+    auto final_ep = [&](int jl) {
+      const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+      const int acc = jl & 1;
+      const uint32_t t_acc = t_lane + 128u * (uint32_t)acc;
+      const uint32_t dfull = BAR(FB_DFULL + acc);
+      const uint32_t use0 = 3u * (uint32_t)(jl >> 1);
+      uint32_t r[16];
       mbar_wait(dfull, (use0 + 2u) & 1, 9);
       PROF_ADD(2);  // wait for the layer-3 accumulator
       tc_fence_after();
@@ -677,6 +690,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         }
       }
       PROF_ADD(4);  // final epilogue work
+    };
+#pragma unroll 1
+    for (int k = 0; k < n_local; k += 2) {
+      const int nt = (k + 1 < n_local) ? 2 : 1;
+#pragma unroll 1
+      for (int layer = 0; layer < 2; ++layer)
+#pragma unroll 1
+        for (int b = 0; b < nt; ++b) hidden(k + b, layer);
+#pragma unroll 1
+      for (int b = 0; b < nt; ++b) final_ep(k + b);
     }
     if (tid == 0) PROF_FLUSH(8);
   }
