@@ -179,7 +179,7 @@ def measure_forward(args, workload, math, steps, rank, local_rank, dev, dist):
         e2e_ms = t0.elapsed_time(t1)
         # ---------------- per-kernel CUDA-event timings (outside the timed regions): two eager steps of the same model
         ksteps = 2
-        ops.TIMING = {"edge_block": [], "cell_block": [], "node_aggregate": []}
+        ops.TIMING = {"edge_block": [], "cell_block": [], "node_aggregate": [], "cell_mean": []}
         for k in range(ksteps):
             flush.zero_()
             gr._eager_step()

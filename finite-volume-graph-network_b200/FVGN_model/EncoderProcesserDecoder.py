@@ -101,12 +101,13 @@ class GnBlock(nn.Module):
         return Data(x=x, edge_attr=e, edge_index=graph.edge_index)
 
 
-def fused_gn_block(block: GnBlock, topo, x, e, inplace, node_agg=None, x_prime=None, x_prime_bf16=None, x_prime_split=None):
+def fused_gn_block(block: GnBlock, topo, x, e, inplace, node_agg=None, x_prime=None, x_prime_bf16=None, x_prime_split=None,
+                   cell_mean_split=None):
     cb, eb = block.cb_module.net, block.eb_module.net
     node_agg = ops.node_aggregate_fwd(e, topo.node_ptr, topo.node_items, topo.N, out=node_agg)
     if inplace and x_prime_split is not None and cb.math_mode == "bf16x3" and eb.math_mode == "bf16x3":
         # fp32-equivalent fast path: x' lives only as the split fp16 shadow the EdgeBlock gathers (same bits as the two calls below)
-        return ops.gn_block_fwd_inplace_split(cb.mlp_ref(), eb.mlp_ref(), x, e, node_agg, topo.cnT, topo.nc, x_prime_split)
+        return ops.gn_block_fwd_inplace_split(cb.mlp_ref(), eb.mlp_ref(), x, e, node_agg, topo.cnT, topo.nc, x_prime_split, cell_mean_split)
     if inplace and x_prime_bf16 is not None and cb.math_mode == "bf16" and eb.math_mode == "bf16":
         # tensor-core fast path: x' lives only as the bf16 shadow the EdgeBlock gathers (same arithmetic as the two calls below)
         return ops.gn_block_fwd_inplace_bf16(cb.mlp_ref(), eb.mlp_ref(), x, e, node_agg, topo.cnT, topo.nc, x_prime_bf16)
@@ -163,9 +164,10 @@ class EncoderProcesserDecoder(nn.Module):
         x_prime = None if (all_bf16 or all_x3) else torch.empty_like(x)
         x_prime_bf16 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if all_bf16 else None
         x_prime_split = torch.empty((x.shape[0], 2, x.shape[1]), dtype=torch.float16, device=x.device) if all_x3 else None
+        cell_mean_split = torch.empty((x.shape[0], 2, 64), dtype=torch.float16, device=x.device) if all_x3 else None
         for l, block in enumerate(self.processer_list):
             x, e = fused_gn_block(block, topo, x, e, inplace=True, node_agg=node_agg, x_prime=x_prime, x_prime_bf16=x_prime_bf16,
-                                  x_prime_split=x_prime_split)
+                                  x_prime_split=x_prime_split, cell_mean_split=cell_mean_split)
             if capture is not None and l in (0, 1, len(self.processer_list) - 1):
                 capture[f"x_l{l}"], capture[f"e_l{l}"] = x.clone(), e.clone()
         return (False, self.decoder.edge_decode_module(e))

@@ -49,7 +49,8 @@ _SIGS = {
     "fvgn_edge_block_fwd": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P, _I, _P]),
     "fvgn_cell_block_fwd_xbf16": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _I, _P]),
     "fvgn_edge_block_fwd_xbf16": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _I, _P]),
-    "fvgn_cell_block_fwd_split": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _P]),
+    "fvgn_cell_mean_split": (_I, [_P, _P, _I, _P, _P]),
+    "fvgn_cell_block_fwd_split": (_I, [C.POINTER(MlpT), _P, _P, _I, _P, _P]),
     "fvgn_edge_block_fwd_split": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P]),
     "fvgn_face_area_bn_fwd": (_I, [_P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fvgn_face_area_sums": (_I, [_P, _P, _P, _I, _F, _P, _P, _P, _P]),

@@ -82,7 +82,7 @@ struct Params {
   // SH variant (inference): x', which only ever feeds the EdgeBlock's gathers, travels as a "split shadow" [C][hi plane 128 fp16 |
   // lo plane 128 fp16] (512 B per row, values pre-scaled by ASCALE): written by the CellBlock epilogue, moved by cp.async straight
   // into the EdgeBlock's A ring (no registers, no conversion work for 4 of its 6 K-tile steps)
-  const unsigned char* sh_in0;  // EDGE: shadow of x' (gathered)
+  const unsigned char* sh_in0;  // EDGE: shadow of x' (gathered); CELL: split shadow [C][2][64] of the per-cell node mean (cell_mean_split_kernel)
   unsigned char* sh_prime;      // CELL: shadow of x' (out)
   const unsigned char* packed;  // [kt1 + 4] steps x [3 splits] x 16 KB
   const float* b1; const float* b2; const float* b3; const float* ln_w; const float* ln_b;
@@ -323,7 +323,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       PROF_ADD(2);  // split + store (includes the wait for the gathered data)
     };
     PROF_T0();
-    if (SH && MODE == TC_EDGE) {
+    if (SH && MODE == TC_CELL) {
+      // x rows (fp32 master) through registers, loaded one tile ahead; the node mean comes ready-split from cell_mean_split_kernel
+      const int plane = hl >> 3, chunk = hl & 7;
+      auto publish = [&](int s) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(FB_AFULL + (uint32_t)s % FARING));
+      };
+      auto acquire = [&](int s) {
+        if (s >= FARING) mbar_wait(BAR(FB_AEMPTY + (uint32_t)s % FARING), (((uint32_t)s / FARING) - 1) & 1, 1);
+        return sA + ((uint32_t)s % FARING) * FA_SLOT;
+      };
+      auto ldx = [&](int jl, int half, float4* v) {
+        const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+        const float* base = p.src0 + half * 64 + hl * 4;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) v[i] = ldg4(base + (size_t)min(row0 + hw + NHW * i, last) * 128);
+      };
+      float4 va[RPT], vb[RPT];
+      if (n_local > 0) { ldx(0, 0, va); ldx(0, 1, vb); }
+#pragma unroll 1
+      for (int jl = 0; jl < n_local; ++jl) {
+        const int s = 3 * jl;
+        const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
+        PROF_ADD(0);
+        unsigned char* dst = acquire(s);
+        PROF_ADD(1);
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) st_slot2_f4(dst, hw + NHW * i, hl, va[i]);
+        publish(s);
+        dst = acquire(s + 1);
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) st_slot2_f4(dst, hw + NHW * i, hl, vb[i]);
+        publish(s + 1);
+        dst = acquire(s + 2);
+        const unsigned char* src = p.sh_in0 + plane * 128 + chunk * 16;
+        const uint32_t d0 = smem_u32(dst) + (uint32_t)plane * TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = hw + NHW * i;
+          cp_async16(d0 + (uint32_t)r * 128u + (((uint32_t)chunk ^ ((uint32_t)r & 7u)) << 4), src + (size_t)min(row0 + r, last) * 256);
+        }
+        cp_async_commit();
+        if (jl + 1 < n_local) { ldx(jl + 1, 0, va); ldx(jl + 1, 1, vb); }
+        cp_async_wait<0>();
+        publish(s + 2);
+        PROF_ADD(2);
+      }
+    } else if (SH && MODE == TC_EDGE) {
       // gathered x' rows come from the split shadow: cp.async 16-byte chunks straight into the swizzled ring slots; 16 lanes move one
       // row (2 planes x 128 B), 8 rows per thread and K-tile step.  A step is published one step later (its cp.async group done).
       const int plane = hl >> 3, chunk = hl & 7;
@@ -1309,6 +1357,27 @@ __global__ void __launch_bounds__(1024) colsum_reduce_kernel(const ColsumParams 
   }
 }
 
+// Per-cell mean of the three node aggregates (GN_blocks.py:125-129: (a + b) + c, then a true division by 3.0) as the split fp16 shadow
+// [C][2][64] the CellBlock kernel (SH variant) moves into its third K-tile by cp.async.  16 threads per cell, 4 columns each.
+__global__ void __launch_bounds__(256) cell_mean_split_kernel(const float* __restrict__ node_agg, const int32_t* __restrict__ cells_node_T, int C,
+                                                              unsigned char* __restrict__ out) {
+  const int gid = blockIdx.x * 256 + threadIdx.x;
+  const int c = gid >> 4, hl = gid & 15;
+  if (c >= C) return;
+  const int n0 = __ldg(cells_node_T + c), n1 = __ldg(cells_node_T + (size_t)C + c), n2 = __ldg(cells_node_T + 2 * (size_t)C + c);
+  const float4 a = ldg4(node_agg + (size_t)n0 * 64 + hl * 4);
+  const float4 b = ldg4(node_agg + (size_t)n1 * 64 + hl * 4);
+  const float4 d = ldg4(node_agg + (size_t)n2 * 64 + hl * 4);
+  const float4 v = make_float4(__fdiv_rn(__fadd_rn(__fadd_rn(a.x, b.x), d.x), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.y, b.y), d.y), 3.0f),
+                               __fdiv_rn(__fadd_rn(__fadd_rn(a.z, b.z), d.z), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.w, b.w), d.w), 3.0f));
+  uint2 q0, q1;
+  split2_pair(v.x * ASCALE, v.y * ASCALE, q0.x, q1.x);
+  split2_pair(v.z * ASCALE, v.w * ASCALE, q0.y, q1.y);
+  unsigned char* o = out + (size_t)c * 256 + hl * 8;
+  *reinterpret_cast<uint2*>(o) = q0;
+  *reinterpret_cast<uint2*>(o + 128) = q1;
+}
+
 // Forward weights: one CTA per weight matrix.  W [n_valid, k_valid] fp32 row-major -> scale 2^s with max|W| 2^s in [2^13, 2^14)
 // (found here, on the device: graph-capturable, no host round trip) -> steps [kt][2 fp16 splits][128 rows][64 k], each sub-tile a
 // byte image of the swizzled layout; the epilogue factor 1 / (ASCALE 2^s) goes to the header behind the last step.
@@ -1472,14 +1541,23 @@ int tc3_edge_block(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, 
 // ---- split-shadow (inference) variants: latents are fp32, updated in place; x' only exists as the fp16 hi/lo shadow the EdgeBlock gathers
 static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
-int tc3_cell_block_sh(const fvgn_mlp_t* mlp, float* x, const float* node_agg, const int32_t* cells_node_T, int n_cells, void* x_prime_sh,
-                      cudaStream_t st) {
+int tc3_cell_mean_split(const float* node_agg, const int32_t* cells_node_T, int n_cells, void* out, cudaStream_t st) {
+  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (node_agg && cells_node_T && out)), "NULL input");
+  FVGN_CHECK_ARG(al16(node_agg) && al16(out), "buffers must be 16B aligned");
+  if (n_cells == 0) return 0;
+  x3::cell_mean_split_kernel<<<cdiv(n_cells * 16, 256), 256, 0, st>>>(node_agg, cells_node_T, n_cells, reinterpret_cast<unsigned char*>(out));
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc3_cell_block_sh(const fvgn_mlp_t* mlp, float* x, const void* cell_mean_sh, int n_cells, void* x_prime_sh, cudaStream_t st) {
   if (int e = check_mlp3(mlp, true)) return e;
   FVGN_CHECK_ARG(mlp->k_in == 192, "CellBlock MLP must have k_in == 192");
-  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && node_agg && cells_node_T && x_prime_sh)), "NULL input");
-  FVGN_CHECK_ARG(al16(x) && al16(x_prime_sh) && al16(node_agg), "buffers must be 16B aligned");
+  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && cell_mean_sh && x_prime_sh)), "NULL input");
+  FVGN_CHECK_ARG(al16(x) && al16(x_prime_sh) && al16(cell_mean_sh), "buffers must be 16B aligned");
   x3::Params p{};
-  p.mode = x3::TC_CELL; p.rows = n_cells; p.src0 = x; p.src1 = node_agg; p.idx = cells_node_T; p.out1 = x; p.ld_out = 128;
+  p.mode = x3::TC_CELL; p.rows = n_cells; p.src0 = x; p.out1 = x; p.ld_out = 128;
+  p.sh_in0 = reinterpret_cast<const unsigned char*>(cell_mean_sh);
   p.sh_prime = reinterpret_cast<unsigned char*>(x_prime_sh);
   return launch_tc3(p, mlp, true, st, true);
 }

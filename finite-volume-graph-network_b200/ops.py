@@ -289,7 +289,8 @@ def _split_ok(t, rows, name):
     return t
 
 
-def gn_block_fwd_inplace_split(cell_mlp: MlpRef, edge_mlp: MlpRef, x, e, node_agg, cells_node_T, neighbour_cell, x_prime_split):
+def gn_block_fwd_inplace_split(cell_mlp: MlpRef, edge_mlp: MlpRef, x, e, node_agg, cells_node_T, neighbour_cell, x_prime_split,
+                               cell_mean_split=None):
     """Inference fast path of one GnBlock in the fp32-equivalent mode after the node aggregation: x += x', e += e' in place; x' only
     exists as the split fp16 shadow the EdgeBlock gathers (fvgn_cell_block_fwd_split / fvgn_edge_block_fwd_split)."""
     _req(x, torch.float32, "x", 2), _req(e, torch.float32, "edge_attr", 2), _req(node_agg, torch.float32, "node_agg", 2)
@@ -299,11 +300,17 @@ def gn_block_fwd_inplace_split(cell_mlp: MlpRef, edge_mlp: MlpRef, x, e, node_ag
             or cells_node_T.shape[1] != Cn or neighbour_cell.shape[1] != F:
         raise ValueError("gn_block_fwd_inplace_split: bad shapes/strides")
     _split_ok(x_prime_split, Cn, "x_prime_split")
+    if cell_mean_split is None:
+        cell_mean_split = torch.empty((Cn, 2, 64), dtype=torch.float16, device=x.device)
+    if cell_mean_split.dtype != torch.float16 or not cell_mean_split.is_contiguous() or tuple(cell_mean_split.shape) != (Cn, 2, 64):
+        raise ValueError("cell_mean_split must be a contiguous float16 tensor of shape [C, 2, 64]")
     cell_mlp.ensure_packed(2), edge_mlp.ensure_packed(2)
     L = _lib.lib()
-    _count(2)
+    _count(3)
+    with _timed("cell_mean"):
+        check(L.fvgn_cell_mean_split(_p(node_agg), _p(cells_node_T), Cn, _p(cell_mean_split), _stream()), "cell_mean_split")
     with _timed("cell_block"):
-        check(L.fvgn_cell_block_fwd_split(C.byref(cell_mlp.struct), _p(x), _p(node_agg), _p(cells_node_T), Cn, _p(x_prime_split), _stream()),
+        check(L.fvgn_cell_block_fwd_split(C.byref(cell_mlp.struct), _p(x), _p(cell_mean_split), Cn, _p(x_prime_split), _stream()),
               "cell_block_fwd_split")
     with _timed("edge_block"):
         check(L.fvgn_edge_block_fwd_split(C.byref(edge_mlp.struct), _p(x_prime_split), _p(e), _p(neighbour_cell), F, _stream()),

@@ -178,11 +178,16 @@ FVGN_API int fvgn_edge_block_fwd_xbf16(const fvgn_mlp_t* mlp, const uint16_t* x_
                                        const int32_t* neighbour_cell, int n_faces, int math_mode, fvgn_stream_t stream);
 
 /* Inference fast path of one GnBlock in the fp32-equivalent mode (FVGN_MATH_BF16X3_TC): both latents are updated IN PLACE
- * (x += x', e += e'), and x' — which only ever feeds the EdgeBlock's gathers — travels between the two kernels as a "split shadow"
- * [C][2][128] of fp16 (512 B per row: the hi plane fp16(8 v), then the lo plane fp16(8 v - hi)), i.e. exactly the two-term
- * tensor-core operand: the EdgeBlock moves it from HBM into its operand tiles by cp.async, with no conversion work.  Results are
- * bit-identical to fvgn_cell_block_fwd + fvgn_edge_block_fwd in FVGN_MATH_BF16X3_TC mode. */
-FVGN_API int fvgn_cell_block_fwd_split(const fvgn_mlp_t* mlp, float* x /*[C,128] in/out*/, const float* node_agg, const int32_t* cells_node_T,
+ * (x += x', e += e'), and the two operands that only exist to feed a tensor-core tile travel as "split shadows" — per row the hi plane
+ * fp16(8 v), then the lo plane fp16(8 v - hi), i.e. exactly the two-term tensor-core operand, moved from HBM into the operand tiles
+ * by cp.async with no conversion work in the consuming kernel:
+ *   fvgn_cell_mean_split      per-cell mean of the three node aggregates (GN_blocks.py:125-129)      -> [C][2][64] fp16
+ *   fvgn_cell_block_fwd_split CellBlock MLP + LayerNorm (GN_blocks.py:78-145), x += x'; x' is written -> [C][2][128] fp16 only
+ *   fvgn_edge_block_fwd_split EdgeBlock (GN_blocks.py:16-54) gathering x' from its shadow, e += e'
+ * Results are bit-identical to fvgn_cell_block_fwd + fvgn_edge_block_fwd in FVGN_MATH_BF16X3_TC mode. */
+FVGN_API int fvgn_cell_mean_split(const float* node_agg /*[N,64]*/, const int32_t* cells_node_T /*[3,C]*/, int n_cells,
+                                  void* cell_mean_split /*[C,2,64] fp16 out*/, fvgn_stream_t stream);
+FVGN_API int fvgn_cell_block_fwd_split(const fvgn_mlp_t* mlp, float* x /*[C,128] in/out*/, const void* cell_mean_split /*[C,2,64] fp16*/,
                                        int n_cells, void* x_prime_split /*[C,2,128] fp16 out*/, fvgn_stream_t stream);
 FVGN_API int fvgn_edge_block_fwd_split(const fvgn_mlp_t* mlp, const void* x_prime_split /*[C,2,128] fp16*/, float* e /*[F,128] in/out*/,
                                        const int32_t* neighbour_cell, int n_faces, fvgn_stream_t stream);

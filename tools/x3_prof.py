@@ -69,11 +69,13 @@ for it in range(2):
 
 # split-shadow (inference fast path) variants
 xps = torch.empty((Cn, 2, 128), dtype=torch.float16, device="cuda").normal_()
+cms = torch.empty((Cn, 2, 64), dtype=torch.float16, device="cuda").normal_()
 import ctypes
 P = lambda t: ctypes.c_void_p(t.data_ptr())
 S = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 for name, call in (("EDGE split", lambda: lib.fvgn_edge_block_fwd_split(ctypes.byref(eb.mlp_ref().struct), P(xps), P(e), P(nc), F, S())),
-                   ("CELL split", lambda: lib.fvgn_cell_block_fwd_split(ctypes.byref(cb.mlp_ref().struct), P(x), P(nagg), P(cnT), Cn, P(xps), S()))):
+                   ("CELL split", lambda: lib.fvgn_cell_block_fwd_split(ctypes.byref(cb.mlp_ref().struct), P(x), P(cms), Cn, P(xps), S())),
+                   ("cell mean", lambda: lib.fvgn_cell_mean_split(P(nagg), P(cnT), Cn, P(cms), S()))):
     for it in range(2):
         e.normal_(), x.normal_()
         read()
