@@ -65,7 +65,13 @@ constexpr int WARP_PROD0 = NEPI / 32, WARP_MMA = WARP_PROD0 + NPW, WARP_LOAD = W
 constexpr int NTHREADS = (WARP_LOAD + 1) * 32;  // 576
 constexpr int RPT = TM / (NPROD / 16);          // 8 rows per producer thread per K-tile
 constexpr uint32_t TMEM_COLS = 512;             // acc0 [0,128) | acc1 [128,256) | H split 0 [256,320) | 1 [320,384) | 2 [384,448)
-constexpr uint32_t TMEM_H0 = 256;               // (forward kernel: per tile parity a, hi / lo fp16 H planes at 256 + 128 a, + 64)
+constexpr uint32_t TMEM_H0 = 256;               // (forward kernel: see fwd_acc_col / fwd_h_col)
+// Forward kernel TMEM map: tile jl of a CTA (parity a = jl & 1) owns the column regions 128 a and 256 + 128 a; one is its fp32
+// accumulator, the other its two fp16 hidden-activation planes (hi | lo, 64 columns each), and the roles swap from one tile of a
+// parity to the next: layer 1 of tile jl + 2 accumulates into the columns whose last reader was layer 3 of tile jl (the tensor pipe
+// executes in order, so no barrier is needed), while the epilogue of tile jl is still reading that tile's accumulator.
+__host__ __device__ constexpr uint32_t fwd_acc_col(int jl) { return ((jl >> 1) & 1) ? 256u + 128u * (uint32_t)(jl & 1) : 128u * (uint32_t)(jl & 1); }
+__host__ __device__ constexpr uint32_t fwd_h_col(int jl) { return ((jl >> 1) & 1) ? 128u * (uint32_t)(jl & 1) : 256u + 128u * (uint32_t)(jl & 1); }
 // kind::f16 instruction descriptor with fp16 operands (a_format bits [7,10) = 0, b_format [10,13) = 0); mixing an fp16 A with a
 // bf16 B is an illegal instruction on sm_100a
 constexpr uint32_t IDESC_F16_M128_N128 = IDESC_BF16_M128_N128 & ~0x480u;
@@ -182,7 +188,10 @@ __host__ __device__ inline SmemLayout smem_layout_fwd() {
   return L;
 }
 enum { FB_AFULL = 0, FB_AEMPTY = FB_AFULL + FARING, FB_WFULL = FB_AEMPTY + FARING, FB_WEMPTY = FB_WFULL + FWRING, FB_DFULL = FB_WEMPTY + FWRING,
-       FB_DFREE = FB_DFULL + 2, FB_HREADY = FB_DFREE + 2, FB_COUNT = FB_HREADY + 2 };
+       FB_DFULL23 = FB_DFULL + 2, FB_HREADY = FB_DFULL23 + 2, FB_COUNT = FB_HREADY + 2 };
+// FB_DFULL[a]: layer-1 accumulator of a tile of parity a complete (one phase per tile); FB_DFULL23[a]: its layer-2, then layer-3
+// accumulator (two phases per tile).  Separate barriers: layer 1 of tile jl + 2 may complete before the epilogue has waited for layer 3
+// of tile jl (no barrier orders them), and an mbarrier waiter must never fall two phases behind.
 // the three forward split products, most significant first: (activation split, weight split)
 __host__ __device__ constexpr int fprod_a(int q) { return q == 2 ? 1 : 0; }  // 0 0 1
 __host__ __device__ constexpr int fprod_w(int q) { return q == 1 ? 1 : 0; }  // 0 1 0
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     if (smem_u32(smem) & 1023u) { printf("fvgn mlp_tc3: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < FARING; ++i) { mbar_init(BAR(FB_AFULL + i), NPW); mbar_init(BAR(FB_AEMPTY + i), 1); }
     for (int i = 0; i < FWRING; ++i) { mbar_init(BAR(FB_WFULL + i), 1); mbar_init(BAR(FB_WEMPTY + i), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(BAR(FB_DFULL + a), 1); mbar_init(BAR(FB_DFREE + a), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(BAR(FB_DFULL + a), 1); mbar_init(BAR(FB_DFULL23 + a), 1); }
     mbar_init(BAR(FB_HREADY), 8); mbar_init(BAR(FB_HREADY + 1), 8);
     fence_mbar_init();
   }
@@ -466,9 +475,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       PROF_T0();
       auto layer1 = [&](int jl) {
         const int a = jl & 1;
-        if (jl >= 2) mbar_wait(BAR(FB_DFREE + a), (uint32_t)((jl >> 1) - 1) & 1, 3);
         PROF_ADD(0);
-        const uint32_t d = tmem_base + 128u * (uint32_t)a;
+        const uint32_t d = tmem_base + fwd_acc_col(jl);
 #pragma unroll 1
         for (int t = 0; t < kt1; ++t, ++ak, ++wk) {
           const uint32_t sa = ak % FARING, sw = wk % FWRING;
@@ -492,7 +500,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       };
       auto layer23 = [&](int jl) {  // layer 2 or 3 of tile jl (whichever hidden activation the epilogue has just published)
         const int a = jl & 1;
-        const uint32_t d = tmem_base + 128u * (uint32_t)a;
+        const uint32_t d = tmem_base + fwd_acc_col(jl), hcol = tmem_base + fwd_h_col(jl);
         {
           mbar_wait(BAR(FB_HREADY + a), hphase[a], 7); hphase[a] ^= 1;
           PROF_ADD(4);
@@ -507,12 +515,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
               for (int q = 0; q < 3; ++q)
-                if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16_ts(d, tmem_base + TMEM_H0 + 128u * (uint32_t)a + 64u * fprod_a(q) + 8u * (uint32_t)(4 * t + kk),
+                if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16_ts(d, hcol + 64u * fprod_a(q) + 8u * (uint32_t)(4 * t + kk),
                              umma_desc(b_base + fprod_w(q) * TILE_BYTES + kk * 32), IDESC_F16_M128_N128, (t | kk | q) != 0);
             umma_commit(BAR(FB_WEMPTY + sw));
             PROF_ADD(6);
           }
-          umma_commit(BAR(FB_DFULL + a));
+          umma_commit(BAR(FB_DFULL23 + a));
         }
       };
       // Tiles are processed in pairs (A, B) with their own accumulator and hidden-activation columns; the epilogue warps alternate
@@ -542,7 +550,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     const int q = warp & 3, h = warp >> 2;  // TMEM lane quadrant = warp id % 4; column half
     const int erow = 32 * q + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
-    const uint32_t t_h = t_lane + TMEM_H0;
     unsigned char* stage = smem + L.stage_off + warp * 2048;  // [32 rows][64 B], 16-byte chunks XOR-swizzled by ((row >> 1) & 3)
     float* sRed = reinterpret_cast<float*>(smem + L.red_off);
     const bool has_ln = (p.ln_w != nullptr);
@@ -573,13 +580,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     auto hidden = [&](int jl, int layer) {
       const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
       const int acc = jl & 1;
-      const uint32_t t_acc = t_lane + 128u * (uint32_t)acc;
-      const uint32_t t_ha = t_h + 128u * (uint32_t)acc;
-      const uint32_t dfull = BAR(FB_DFULL + acc);
-      const uint32_t use0 = 3u * (uint32_t)(jl >> 1);
+      const uint32_t t_acc = t_lane + fwd_acc_col(jl);
+      const uint32_t t_ha = t_lane + fwd_h_col(jl);
       uint32_t r[16];
       {
-        mbar_wait(dfull, (use0 + (uint32_t)layer) & 1, 8);
+        // layer 0 reads the layer-1 accumulator (phase jl >> 1 of FB_DFULL), layer 1 the layer-2 one (even phases of FB_DFULL23)
+        if (layer == 0) mbar_wait(BAR(FB_DFULL + acc), (uint32_t)(jl >> 1) & 1, 8);
+        else mbar_wait(BAR(FB_DFULL23 + acc), 0, 8);
         PROF_ADD(layer);  // 0: wait for the layer-1 accumulator, 1: layer 2
         tc_fence_after();
         const float* bias = sPar + layer * 128;
@@ -617,11 +624,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     auto final_ep = [&](int jl) {
       const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
       const int acc = jl & 1;
-      const uint32_t t_acc = t_lane + 128u * (uint32_t)acc;
-      const uint32_t dfull = BAR(FB_DFULL + acc);
-      const uint32_t use0 = 3u * (uint32_t)(jl >> 1);
+      const uint32_t t_acc = t_lane + fwd_acc_col(jl);
       uint32_t r[16];
-      mbar_wait(dfull, (use0 + 2u) & 1, 9);
+      mbar_wait(BAR(FB_DFULL23 + acc), 1, 9);  // layer-3 accumulator: the odd phases
       PROF_ADD(2);  // wait for the layer-3 accumulator
       tc_fence_after();
       const float inv3 = sPar[5 * 128 + 2];
@@ -666,11 +671,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
         tmem_ld16_issue(t_acc + 16 * sc, r);
         tmem_ld16_wait(r);
-        if (sc == 4 * h + 3) {  // this warp's last TMEM read of the tile
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(FB_DFREE + acc));
-        }
         float* v = reinterpret_cast<float*>(r);
         if (FVGN_DBG(p) & 32) continue;
         if (p.zsave) {
@@ -748,6 +748,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         for (int b = 0; b < nt; ++b) hidden(k + b, layer);
 #pragma unroll 1
       for (int b = 0; b < nt; ++b) final_ep(k + b);
+      // the next pair's first hidden epilogue overwrites (as H planes) the accumulator columns this pair's last epilogue has been
+      // reading, across the two column-half warps of a lane quadrant: all epilogue warps finish the pair first
+      named_bar_sync(1, NEPI);
     }
     if (tid == 0) PROF_FLUSH(8);
   }
