@@ -1065,7 +1065,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 }
 
 // transposed packing for the backward: element (n, k) of the packed "weight" is W[k * ldw + n0 + n]  (W^T restricted to columns n0..)
-__global__ void pack_tiles3_t_kernel(const float* __restrict__ W, int ldw, int n0, int n_valid, int k_valid, int kt, unsigned char* __restrict__ out) {
+// (blockIdx.y = job: all transposed blocks of one MLP in one launch)
+struct PackTJob { const float* W; int ldw, n0, n_valid, k_valid, step0; };
+struct PackTParams { PackTJob job[5]; int kt; unsigned char* out; };
+__global__ void pack_tiles3_t_kernel(const PackTParams pp) {
+  const PackTJob jb = pp.job[blockIdx.y];
+  const float* __restrict__ W = jb.W;
+  const int ldw = jb.ldw, n0 = jb.n0, n_valid = jb.n_valid, k_valid = jb.k_valid, kt = pp.kt;
+  unsigned char* __restrict__ out = pp.out + (size_t)jb.step0 * SLOT_BYTES;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (tile, n, chunk)
   if (idx >= kt * 128 * 8) return;
   const int c = idx & 7, n = (idx >> 3) & 127, t = idx >> 10;
@@ -1314,32 +1321,46 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int njobs, i
 }
 
 // deterministic column sums of up to five [rows, ncols <= 128] fp32 matrices: blockIdx.y = source, blockIdx.x = row range; a block is
-// 8 row-lanes x 128 columns, every thread keeps 4 independent partial sums (fixed combination order), the 8 row-lanes are combined
-// through shared memory in a fixed order, and colsum_reduce_kernel sums the row ranges in a fixed order.
+// 16 row-lanes x 32 float4 column groups, every thread keeps 4 independent partial sums (fixed combination order), the row-lanes are
+// combined through shared memory in a fixed order, and colsum_reduce_kernel sums the row ranges in a fixed order.
 struct ColsumSrc { const float* src; int ld, ncols, dst_off; };
 struct ColsumParams { ColsumSrc s[5]; int rows, nb; float* partial; float* grads; };
-__global__ void __launch_bounds__(1024) colsum_kernel(const ColsumParams p) {
-  __shared__ float sh[8][128];
+__global__ void __launch_bounds__(512) colsum_kernel(const ColsumParams p) {
+  __shared__ float sh[16][128];
   const ColsumSrc cs = p.s[blockIdx.y];
   if (cs.src == nullptr) return;
-  const int c = threadIdx.x & 127, rl = threadIdx.x >> 7;  // column, row lane 0..7
   const int per = (p.rows + p.nb - 1) / p.nb, r0 = blockIdx.x * per, r1 = min(p.rows, r0 + per);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  if (c < cs.ncols) {
+  const bool vec = cs.ncols == 128 && (cs.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(cs.src) & 15) == 0;
+  if (vec) {
+    // 32 float4 column groups x 16 row lanes; 4 independent 16-byte loads in flight per thread, combined in a fixed order
+    const int c4 = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const float* base = cs.src + c4 * 4;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    auto add4 = [](float4& a, const float4 v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
     int r = r0 + rl;
-    for (; r + 24 < r1; r += 32) {
-      a0 += cs.src[(size_t)r * cs.ld + c]; a1 += cs.src[(size_t)(r + 8) * cs.ld + c];
-      a2 += cs.src[(size_t)(r + 16) * cs.ld + c]; a3 += cs.src[(size_t)(r + 24) * cs.ld + c];
+    for (; r + 48 < r1; r += 64) {
+      const float4 v0 = ldg4(base + (size_t)r * cs.ld), v1 = ldg4(base + (size_t)(r + 16) * cs.ld);
+      const float4 v2 = ldg4(base + (size_t)(r + 32) * cs.ld), v3 = ldg4(base + (size_t)(r + 48) * cs.ld);
+      add4(a0, v0); add4(a1, v1); add4(a2, v2); add4(a3, v3);
     }
-    for (; r < r1; r += 8) a0 += cs.src[(size_t)r * cs.ld + c];
+    for (; r < r1; r += 16) add4(a0, ldg4(base + (size_t)r * cs.ld));
+    *reinterpret_cast<float4*>(&sh[rl][c4 * 4]) = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                                                              (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+  } else {
+    // narrow / unaligned sources (the decoder's [rows, 5] gradient): one column per thread, 4 row lanes
+    const int c = threadIdx.x & 127, rl = threadIdx.x >> 7;
+    float a = 0.f;
+    if (c < cs.ncols)
+      for (int r = r0 + rl; r < r1; r += 4) a += cs.src[(size_t)r * cs.ld + c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sh[4 * k + rl][c] = (k == 0) ? a : 0.f;
   }
-  sh[rl][c] = (a0 + a1) + (a2 + a3);
   __syncthreads();
-  if (rl == 0 && c < cs.ncols) {
+  if (threadIdx.x < 128 && (int)threadIdx.x < cs.ncols) {
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += sh[k][c];
-    p.partial[((size_t)blockIdx.y * p.nb + blockIdx.x) * 128 + c] = s;
+    for (int k = 0; k < 16; ++k) s += sh[k][threadIdx.x];
+    p.partial[((size_t)blockIdx.y * p.nb + blockIdx.x) * 128 + threadIdx.x] = s;
   }
 }
 __global__ void __launch_bounds__(1024) colsum_reduce_kernel(const ColsumParams p) {
@@ -1381,7 +1402,8 @@ __global__ void __launch_bounds__(256) cell_mean_split_kernel(const float* __res
   *reinterpret_cast<uint2*>(o + 128) = q1;
 }
 
-// Forward weights: one CTA per weight matrix.  W [n_valid, k_valid] fp32 row-major -> scale 2^s with max|W| 2^s in [2^13, 2^14)
+// Forward weights: blockIdx.x = weight matrix, blockIdx.y = slice of its tiles (every CTA of a matrix finds the same max|W| itself:
+// 196 KB at most, L2-resident).  W [n_valid, k_valid] fp32 row-major -> scale 2^s with max|W| 2^s in [2^13, 2^14)
 // (found here, on the device: graph-capturable, no host round trip) -> steps [kt][2 fp16 splits][128 rows][64 k], each sub-tile a
 // byte image of the swizzled layout; the epilogue factor 1 / (ASCALE 2^s) goes to the header behind the last step.
 struct PackFwdParams { const float* w[3]; int ldw[3], n_valid[3], k_valid[3], kt[3], step0[3]; unsigned char* out; int nsteps; };
@@ -1392,7 +1414,8 @@ __global__ void __launch_bounds__(1024) pack_fwd_h2_kernel(const PackFwdParams p
   const float* W = p.w[m];
   const int ldw = p.ldw[m], nv = p.n_valid[m], kv = p.k_valid[m], kt = p.kt[m];
   float mx = 0.f;
-  for (int i = tid; i < nv * kv; i += 1024) mx = fmaxf(mx, fabsf(W[(size_t)(i / kv) * ldw + (i % kv)]));
+  for (int r = tid >> 5; r < nv; r += 32)  // a warp per row: coalesced, no integer division
+    for (int c = tid & 31; c < kv; c += 32) mx = fmaxf(mx, fabsf(W[(size_t)r * ldw + c]));
 #pragma unroll
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((tid & 31) == 0) s_max[tid >> 5] = mx;
@@ -1406,13 +1429,13 @@ __global__ void __launch_bounds__(1024) pack_fwd_h2_kernel(const PackFwdParams p
       const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu);
       const float sc = (e < 32 || e == 255) ? 1.0f : __uint_as_float((uint32_t)(127 + 13 - (e - 127)) << 23);
       s_scale = sc;
-      reinterpret_cast<float*>(p.out + (size_t)p.nsteps * FW_SLOT)[m] = 1.0f / (ASCALE * sc);  // exact: powers of two
+      if (blockIdx.y == 0) reinterpret_cast<float*>(p.out + (size_t)p.nsteps * FW_SLOT)[m] = 1.0f / (ASCALE * sc);  // exact: powers of two
     }
   }
   __syncthreads();
   const float sc = s_scale;
   unsigned char* out = p.out + (size_t)p.step0[m] * FW_SLOT;
-  for (int idx = tid; idx < kt * 1024; idx += 1024) {  // (tile, n, 16-byte chunk)
+  for (int idx = blockIdx.y * 1024 + tid; idx < kt * 1024; idx += gridDim.y * 1024) {  // (tile, n, 16-byte chunk)
     const int c = idx & 7, n = (idx >> 3) & 127, t = idx >> 10;
     uint4 q0, q1;
     uint32_t* a0 = reinterpret_cast<uint32_t*>(&q0);
@@ -1449,7 +1472,7 @@ int tc3_pack(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t st) {
   p.w[2] = m->w3; p.ldw[2] = 128; p.n_valid[2] = m->n_out; p.k_valid[2] = 128; p.kt[2] = 2; p.step0[2] = kt1 + 2;
   p.out = reinterpret_cast<unsigned char*>(packed);
   p.nsteps = kt1 + 4;
-  pack_fwd_h2_kernel<<<3, 1024, 0, st>>>(p);
+  pack_fwd_h2_kernel<<<dim3(3, kt1 > 2 ? kt1 : 2), 1024, 0, st>>>(p);
   FVGN_LAUNCH_CHECK();
   return 0;
 }
@@ -1587,16 +1610,17 @@ int tc3_pack_bwd(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t s
   FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed buffer must be 16B aligned");
   unsigned char* o = reinterpret_cast<unsigned char*>(packed);
   const int nseg = (m->k_in + 127) / 128;
+  PackTParams pp{};
+  pp.kt = 2; pp.out = o;
   // dh2[., i] = sum_o dz[., o] W3[o][i]: "weight" rows n = i (128), K = o (n_out valid)
-  pack_tiles3_t_kernel<<<cdiv(2 * 1024, 256), 256, 0, st>>>(m->w3, 128, 0, 128, m->n_out, 2, o);
-  FVGN_LAUNCH_CHECK();
-  pack_tiles3_t_kernel<<<cdiv(2 * 1024, 256), 256, 0, st>>>(m->w2, 128, 0, 128, 128, 2, o + 2 * (size_t)SLOT_BYTES);
-  FVGN_LAUNCH_CHECK();
+  pp.job[0] = {m->w3, 128, 0, 128, m->n_out, 0};
+  pp.job[1] = {m->w2, 128, 0, 128, 128, 2};
   for (int seg = 0; seg < nseg; ++seg) {  // dA[., 128 seg + n] = sum_o da1[., o] W1[o][128 seg + n]
     const int nv = m->k_in - 128 * seg < 128 ? m->k_in - 128 * seg : 128;
-    pack_tiles3_t_kernel<<<cdiv(2 * 1024, 256), 256, 0, st>>>(m->w1, m->k_in, 128 * seg, nv, 128, 2, o + (size_t)(4 + 2 * seg) * SLOT_BYTES);
-    FVGN_LAUNCH_CHECK();
+    pp.job[2 + seg] = {m->w1, m->k_in, 128 * seg, nv, 128, 4 + 2 * seg};
   }
+  pack_tiles3_t_kernel<<<dim3(cdiv(2 * 1024, 256), 2 + nseg), 256, 0, st>>>(pp);
+  FVGN_LAUNCH_CHECK();
   return 0;
 }
 
@@ -1678,7 +1702,9 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
   // bias / LayerNorm-parameter gradients: deterministic column sums.  grads tail: db1 | db2 | db3 | dLN_w | dLN_b
   const int vec0 = 128 * m->k_in + 2 * 16384;
   ColsumParams c{};
-  c.rows = rows; c.nb = cdiv(rows, 256) < WG_COLSUM_NB ? cdiv(rows, 256) : WG_COLSUM_NB; c.grads = grads;
+  // ~4 resident 512-thread blocks per SM over the 5 sources, at least 256 rows per block
+  c.rows = rows; c.nb = cdiv(rows, 256) < (4 * sm_count()) / 5 ? cdiv(rows, 256) : (4 * sm_count()) / 5; c.grads = grads;
+  if (c.nb > WG_COLSUM_NB) c.nb = WG_COLSUM_NB;
   c.partial = workspace + (size_t)p.njobs * (size_t)(sm_count() / p.njobs) * 16384;
   c.s[0] = {m->da_in, 256, 128, vec0 + 128};            // db2 = colsum(da2)
   c.s[1] = {m->da_in + 128, 256, 128, vec0};            // db1 = colsum(da1)
@@ -1691,7 +1717,7 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
     c.s[3] = {nullptr, 0, 0, 0};
     c.s[4] = {nullptr, 0, 0, 0};
   }
-  colsum_kernel<<<dim3(c.nb, 5), 1024, 0, st>>>(c);
+  colsum_kernel<<<dim3(c.nb, 5), 512, 0, st>>>(c);
   FVGN_LAUNCH_CHECK();
   colsum_reduce_kernel<<<5, 1024, 0, st>>>(c);
   FVGN_LAUNCH_CHECK();

@@ -1,0 +1,55 @@
+"""Per-kernel GPU-time breakdown of one eager training step (cyl16, batch 16, default math mode) with the torch profiler (CUPTI).
+usage: python tools/train_breakdown.py"""
+import collections
+import sys
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+sys.path.insert(0, ".")
+import bench
+import fvgn_b200 as fv
+
+dev = torch.device("cuda", 0)
+meshes = bench.make_meshes("cyl16", 0)
+lists = []
+for m in meshes:
+    t = lambda a, dt: torch.as_tensor(a).to(dt).to(dev)
+    tab = fv.ops.build_connectivity(t(m["cells"], torch.int32), t(m["mesh_pos"], torch.float32), t(m["node_type"], torch.int32), "B")
+    lists.append(fv.dataset.build_graphs(tab, m["velocity"], m["pressure"], training_pair=0, device=dev))
+gn0, ge0, gc0 = fv.dataset.collate(lists)
+p = bench.params()
+p.loss = "global_mean_sum"
+torch.manual_seed(0)
+model = fv.FVGN(device="cpu", params=p).to(dev).train()
+model.set_math_mode(sys.argv[1] if len(sys.argv) > 1 else "bf16x3")
+opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+
+
+def tstep():
+    gn, ge, gc = bench._shallow(gn0), bench._shallow(ge0), bench._shallow(gc0)
+    gn, ge, gc, mi, mb = fv.dataset.train_datapreprocessing([gn, ge, gc])
+    opt.zero_grad(set_to_none=False)
+    out = model(graph=gc, graph_edge=ge, graph_node=gn, rho=bench.RHO, mu=bench.MU, dt=bench.DT, edge_one_hot=9, cell_one_hot=0)
+    loss = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=out[3],
+                               target_face_uvp_normalized=out[4], predicted_delta_u=out[1], target_delta_u=out[2])
+    loss[0].backward()
+    opt.step()
+
+
+for _ in range(3):
+    tstep()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    tstep()
+    torch.cuda.synchronize()
+agg = collections.defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        a = agg[e.name[:90]]
+        a[0] += 1
+        a[1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+tot = sum(v[1] for v in agg.values())
+print("one training step: %d kernels, %.2f ms of GPU time" % (sum(v[0] for v in agg.values()), tot / 1e3))
+for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+    print("%8.1f us %5.1f%%  x%-4d %s" % (v, 100 * v / tot, c, k))
