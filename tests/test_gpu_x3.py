@@ -91,6 +91,50 @@ def test_x3_split_shadow_fast_path_is_bit_identical(fv, golden):
         assert torch.equal(xps, _split_of(xp)), layer
 
 
+@pytest.mark.parametrize("nx,ny", [(13, 11), (150, 130), (200, 150)])
+def test_x3_split_fast_path_mid_size_pairs(fv, nx, ny):
+    """Same comparison on meshes that give a CTA several tiles (paired-tile schedule: two pairs + a single tile at ~60k cells, an odd
+    tile count at ~39k), plus the strict-FFMA kernels as the arbiter for the values: 3 GnBlocks, in place."""
+    m = fv.synthetic.make("grid", seed=5, nx=nx, ny=ny, T=2)
+    t = lambda a, dt: torch.as_tensor(a).to(dt).cuda()
+    tab = fv.ops.build_connectivity(t(m["cells"], torch.int32), t(m["mesh_pos"], torch.float32), t(m["node_type"], torch.int32), "B")
+    C, F, N = tab["cells_node"].shape[0], tab["face"].shape[1], m["mesh_pos"].shape[0]
+    gen = torch.Generator().manual_seed(11)
+    x0, e0 = torch.randn(C, 128, generator=gen).cuda(), torch.randn(F, 128, generator=gen).cuda()
+    cb, _ = _mlp_module(fv, 192, seed=4)
+    eb, _ = _mlp_module(fv, 384, seed=5)
+    cnT = tab["cells_node"].T.contiguous()
+    nc = tab["neighbour_cell"].contiguous()
+    ptr, items = fv.ops.build_csr(tab["face"].reshape(-1).contiguous(), N)
+    xs, es = x0.clone(), e0.clone()   # split-shadow fast path
+    xg, eg = x0.clone(), e0.clone()   # generic fp32-equivalent calls
+    xf, ef = x0.clone(), e0.clone()   # strict FFMA
+    xps = torch.empty((C, 2, 128), dtype=torch.float16, device="cuda")
+    for layer in range(3):
+        fv.ops.gn_block_fwd_inplace_split(cb.mlp_ref(), eb.mlp_ref(), xs, es, fv.ops.node_aggregate_fwd(es, ptr, items, N), cnT, nc, xps)
+        xp, xg = fv.ops.cell_block_fwd(cb.mlp_ref(), xg, fv.ops.node_aggregate_fwd(eg, ptr, items, N), cnT, math_mode=X3)
+        _, eg = fv.ops.edge_block_fwd(eb.mlp_ref(), xp, eg, nc, math_mode=X3)
+        xpf, xf = fv.ops.cell_block_fwd(cb.mlp_ref(), xf, fv.ops.node_aggregate_fwd(ef, ptr, items, N), cnT, math_mode=0)
+        _, ef = fv.ops.edge_block_fwd(eb.mlp_ref(), xpf, ef, nc, math_mode=0)
+        assert torch.equal(xs, xg) and torch.equal(es, eg), layer
+    ex, ee = H.rel_l2(xs.cpu(), xf.cpu().double()), H.rel_l2(es.cpu(), ef.cpu().double())
+    print("x3 split path vs strict FFMA after 3 GnBlocks, C=%d F=%d: x %.2e e %.2e" % (C, F, ex, ee))
+    assert ex < 5e-6 and ee < 5e-6
+
+
+def test_x3_activation_overflow_is_loud(fv):
+    """|activation| >= 8190 does not fit the scaled fp16 operand split: the row comes out non-finite (never a silently wrong number)."""
+    m, _ = _mlp_module(fv, 14)
+    m.math_mode = "bf16x3"
+    x = torch.randn(300, 14, generator=torch.Generator().manual_seed(0)).cuda()
+    x[7, 3] = 1.0e5
+    y = m(x)
+    assert not torch.isfinite(y[7]).all()
+    keep = torch.ones(300, dtype=torch.bool, device="cuda")
+    keep[7] = False
+    assert torch.isfinite(y[keep]).all()
+
+
 def test_x3_forward_against_reference_fixture_and_rollout(fv, golden):
     g = golden("fwd_tiny.npz")
     model = _model(fv, g).set_math_mode("bf16x3")
