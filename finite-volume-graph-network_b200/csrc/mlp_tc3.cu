@@ -1106,7 +1106,8 @@ constexpr int WG_HALF_BYTES = WG_CHUNK * 128;  // one [64 rows][64 features] bf1
 constexpr int WG_MAT_BYTES = 6 * WG_HALF_BYTES;  // 3 splits x 2 feature halves = 48 KB
 constexpr int WG_STAGE_BYTES = 2 * WG_MAT_BYTES;  // P and Q
 constexpr int WG_STAGES = 2;
-constexpr int WG_NTHREADS = (4 + 8 + 1) * 32;  // 4 epilogue warps, 8 producer warps, 1 MMA warp
+constexpr int WG_NPW = 16;                       // producer warps (warps 0-3 also run the epilogue once the chunks are done)
+constexpr int WG_NTHREADS = (WG_NPW + 1) * 32;   // + 1 MMA warp
 
 struct WgParams {
   int mode, rows, k_in, n_out, njobs, nranges, chunks_per_range, nchunks, nprod;
@@ -1149,28 +1150,29 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) { printf("fvgn wgrad_tc3: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
-    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(BAR(i), 8); mbar_init(BAR(2 + i), 1); }
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(BAR(i), WG_NPW); mbar_init(BAR(2 + i), 1); }
     mbar_init(BAR(4), 1);
     fence_mbar_init();
   }
-  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 128);
+  if (warp == WG_NPW) tmem_alloc(smem_u32(tmem_slot), 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 12) {
+  if (warp < WG_NPW) {
     // ================================================================= producers: P (gradient rows) and Q (activation rows) chunks,
-    // half a chunk (32 rows) per step with two register buffers: the next step's loads are in flight while this one is split / stored
-    const int ptid = tid - 128;
-    const int hw = ptid >> 4, hl = ptid & 15;  // rows 32 half + hw + 16 i (i = 0,1) of the chunk, features 4 hl.. of each 64-feature half
+    // half a chunk (32 rows) per step with two register buffers: the next step's loads are in flight while this one is split / stored.
+    // 16 warps: the split / store work is latency-bound per warp, so more warps in flight is what makes it faster.
+    const int ptid = tid;
+    const int hw = ptid >> 4, hl = ptid & 15;  // row 32 half + hw of the chunk, features 4 hl.. of each 64-feature half
     const int seg = job - 2;
     const int S = 2 * nch;
     auto load = [&](int s, float4 (*pv)[2], float4 (*qv)[2]) {
       const int row0 = (c0 + (s >> 1)) * WG_CHUNK + 32 * (s & 1);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int g = row0 + hw + 16 * i;
+      for (int i = 0; i < 1; ++i) {
+        const int g = row0 + hw;
         const bool ok = g < p.rows;
         const int gc = min(g, p.rows - 1);
 #pragma unroll
@@ -1227,10 +1229,10 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
       unsigned char* P = smem + stg * WG_STAGE_BYTES;
       unsigned char* Q = P + WG_MAT_BYTES;
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < 1; ++i)
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const int r = 32 * half + hw + 16 * i;
+          const int r = 32 * half + hw;
           float4 b = qv[i][hh];
           if (job < 2) {  // Q = silu(z) of the rows that exist (rows past the end were loaded as zeros: silu(0) = 0)
             b = make_float4(silu_x3(b.x), silu_x3(b.y), silu_x3(b.z), silu_x3(b.w));
@@ -1244,7 +1246,7 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
         if (lane == 0) mbar_arrive(BAR(stg));
       }
     };
-    float4 pa[2][2], qa[2][2], pb[2][2], qb[2][2];
+    float4 pa[1][2], qa[1][2], pb[1][2], qb[1][2];
 #pragma unroll 1
     for (int s = -1; s < S; s += 2) {
       if (s + 1 < S) load(s + 1, pa, qa);
@@ -1252,7 +1254,8 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
       if (s + 2 < S) load(s + 2, pb, qb);
       if (s + 1 < S) store(s + 1, pa, qa);
     }
-  } else if (warp == 12) {
+  }
+  if (warp == WG_NPW) {
     // ================================================================= MMA issuer: D[o][i] += sum_rows P[row][o] Q[row][i]
     if (lane == 0) {
 #pragma unroll 1
@@ -1273,8 +1276,8 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
       umma_commit(BAR(4));
     }
     __syncwarp();
-  } else {
-    // ================================================================= epilogue warps 0-3: lane = output row o
+  } else if (warp < 4) {
+    // ================================================================= epilogue (warps 0-3, after their producer work): lane = output row o
     float* dst = p.part + ((size_t)job * p.nranges + range) * 16384 + (size_t)(32 * warp + lane) * 128;
     if (nch > 0) {
       mbar_wait(BAR(4), 0, 8);
@@ -1299,7 +1302,7 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == WG_NPW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 128);
   }

@@ -134,6 +134,94 @@ def _point_in_poly(pts, poly):
     return inside
 
 
+def _poly_distance(pts, poly):
+    """distance of points to a closed polyline [M,2]"""
+    d = np.full(pts.shape[0], np.inf)
+    a = poly
+    b = np.roll(poly, -1, axis=0)
+    for k in range(poly.shape[0]):
+        ab = b[k] - a[k]
+        t = np.clip(((pts - a[k]) @ ab) / max(float(ab @ ab), 1e-300), 0.0, 1.0)
+        d = np.minimum(d, np.hypot(*(pts - (a[k] + t[:, None] * ab)).T))
+    return d
+
+
+def channel_obstacle_mesh(shape="rect", seed=0, n_target=1900, T=3, xlim=(0.0, 1.6), ylim=(0.0, 0.41)):
+    """Channel with a polygonal obstacle, Delaunay, graded toward the obstacle: the other two geometries of the reference's
+    "hybrid" COMSOL dataset (cylinder / rect / NACA0012 — Extract_mesh/parse_comsol.py:411-418; all-triangle).
+    shape = "rect" (axis-aligned box, random aspect) or "naca" (NACA0012 at a random angle of attack)."""
+    from scipy.spatial import Delaunay
+
+    rng = np.random.default_rng(seed)
+    xmin, xmax = xlim
+    ymin, ymax = ylim
+    cx, cy = 0.33 + 0.02 * (rng.random() - 0.5), 0.2 + 0.02 * (rng.random() - 0.5)
+    scale = np.sqrt(n_target / 1900.0)
+    nper = max(24, int(round(56 * scale)))
+    if shape == "rect":
+        w, hgt = 0.05 + 0.07 * rng.random(), 0.04 + 0.06 * rng.random()
+        k = max(2, nper // 4)
+        tx, ty = np.linspace(-0.5, 0.5, k + 1)[:-1], np.linspace(-0.5, 0.5, k + 1)[:-1]
+        poly = np.concatenate([np.stack([tx * w, np.full(k, -0.5 * hgt)], 1), np.stack([np.full(k, 0.5 * w), ty * hgt], 1),
+                               np.stack([-tx * w, np.full(k, 0.5 * hgt)], 1), np.stack([np.full(k, -0.5 * w), -ty * hgt], 1)])
+        size = max(w, hgt)
+    elif shape == "naca":
+        chord = 0.16 + 0.08 * rng.random()
+        aoa = np.deg2rad(-8.0 + 16.0 * rng.random())
+        f = _naca0012(nper // 2 + 1)
+        f = (f - np.array([0.5, 0.0])) * chord
+        rot = np.array([[np.cos(aoa), np.sin(aoa)], [-np.sin(aoa), np.cos(aoa)]])
+        poly = f @ rot.T
+        size = chord
+    else:
+        raise ValueError(shape)
+    poly = poly + np.array([cx, cy])
+    nx, ny = int(round(60 * scale)), int(round(16 * scale))
+    bx = np.linspace(xmin, xmax, nx + 1)
+    by = np.linspace(ymin, ymax, ny + 1)
+    pts = [np.stack([bx, np.full_like(bx, ymin)], 1), np.stack([bx, np.full_like(bx, ymax)], 1),
+           np.stack([np.full_like(by[1:-1], xmin), by[1:-1]], 1), np.stack([np.full_like(by[1:-1], xmax), by[1:-1]], 1), poly]
+    n_b = sum(p.shape[0] for p in pts)
+    need = max(n_target - n_b, 16)
+    h = np.sqrt((xmax - xmin) * (ymax - ymin) / max(n_target, 1))
+    seg = float(np.hypot(*(np.roll(poly, -1, axis=0) - poly).T).max())
+    out, got = [], 0
+    while got < need:
+        cand = np.stack([xmin + (xmax - xmin) * rng.random(4 * need), ymin + (ymax - ymin) * rng.random(4 * need)], 1)
+        near = np.hypot(cand[:, 0] - cx, cand[:, 1] - cy) < size
+        d = np.full(cand.shape[0], size)
+        d[near] = _poly_distance(cand[near], poly)
+        inside = np.zeros(cand.shape[0], dtype=bool)
+        inside[near] = _point_in_poly(cand[near], poly)
+        wall = np.minimum.reduce([cand[:, 0] - xmin, xmax - cand[:, 0], cand[:, 1] - ymin, ymax - cand[:, 1]])
+        ok = (~inside) & (d > max(0.45 * h, 0.7 * seg)) & (wall > 0.45 * h)
+        dist_c = np.maximum(np.hypot(cand[:, 0] - cx, cand[:, 1] - cy) - 0.5 * size, 0)
+        ok &= rng.random(cand.shape[0]) < 0.25 + 0.75 / (1.0 + (dist_c / 0.12) ** 1.5)
+        out.append(cand[ok])
+        got += out[-1].shape[0]
+    interior = np.concatenate(out)[:need]
+    pos = np.concatenate(pts + [interior]).astype(np.float32).astype(np.float64)
+    key = np.round(pos / (0.2 * h)).astype(np.int64)
+    _, first = np.unique(key[:, 0] * 1000003 + key[:, 1], return_index=True)
+    keep = np.zeros(pos.shape[0], dtype=bool)
+    keep[first] = True
+    keep[:n_b] = True
+    pos = pos[keep]
+    tri = Delaunay(pos).simplices.astype(np.int32)
+    poly32 = pos[n_b - poly.shape[0]:n_b]
+    inside = _point_in_poly(pos[tri].mean(1), poly32)
+    on_poly = np.zeros(pos.shape[0], dtype=bool)
+    on_poly[n_b - poly.shape[0]:n_b] = True
+    inside |= on_poly[tri].all(1)  # slivers spanned by three obstacle nodes (concave trailing edge / chord-crossing triangles)
+    tri = tri[~inside]
+    tri = tri[np.abs(_ccw(pos, tri)) > 1e-12]
+    pos, tri, used = _compact(pos, tri)
+    pos32 = pos.astype(np.float32)
+    nt = _box_types(pos32, np.float32(xmin), np.float32(xmax), np.float32(ymin), np.float32(ymax), on_poly[used])
+    vel, prs = fields(pos32, nt, T, seed, ymin, ymax)
+    return dict(mesh_pos=pos32, cells=tri, node_type=nt, velocity=vel, pressure=prs, meta=dict(kind=shape, seed=seed, cx=cx, cy=cy))
+
+
 def airfoil_mesh(seed=0, n_target=5200, T=3, xlim=(-10.0, 20.0), ylim=(-10.0, 10.0)):
     """NACA0012 (chord 1) in a far-field box with strong grading: N~5.2k, C~10.2k, F~15.4k.
     Foil nodes are typed WALL_BOUNDARY (the incompressible branch has no AIRFOIL face rule)."""
@@ -251,6 +339,8 @@ def grid_mesh(nx=61, ny=31, seed=0, T=3, jitter=0.25, hole=True, xlim=(0.0, 1.6)
 def make(kind, seed=0, T=3, **kw):
     if kind == "cyl":
         return cylinder_mesh(seed=seed, T=T, **kw)
+    if kind in ("rect", "naca"):
+        return channel_obstacle_mesh(shape=kind, seed=seed, T=T, **kw)
     if kind == "foil":
         return airfoil_mesh(seed=seed, T=T, **kw)
     if kind == "grid":

@@ -56,6 +56,19 @@ def test_connectivity_large_vs_oracle(fv):
     assert t["mesh_pos"].shape[0] - t["face"].shape[1] + t["cells_node"].shape[0] == 0
 
 
+@pytest.mark.parametrize("kind,seed,rule", [("rect", 3, "B"), ("naca", 3, "B"), ("naca", 4, "A"), ("cyl", 11, "A")])
+def test_connectivity_hybrid_geometries_vs_oracle(fv, kind, seed, rule):
+    """the three geometries of the reference's hybrid COMSOL set (cylinder / rect / NACA0012 in a channel, all-triangle); the oracle is
+    held to the live reference on the same meshes in tests/test_oracle_vs_reference.py"""
+    m = fv.synthetic.make(kind, seed=seed)
+    t = fv.ops.build_connectivity(dev(m["cells"], torch.int32), dev(m["mesh_pos"]), dev(m["node_type"], torch.int32), face_rule=rule)
+    o = O.build_connectivity(m["mesh_pos"], m["cells"], m["node_type"], rule)
+    for k in ["cells_node", "face", "cells_face", "neighbour_cell", "face_type", "cells_type", "centroid", "cell_factor", "face_length", "unit_norm_v"]:
+        assert np.array_equal(t[k].cpu().numpy(), o[k]), k
+    np.testing.assert_allclose(t["cells_area"].cpu().numpy(), o["cells_area"], rtol=3e-7)
+    assert t["mesh_pos"].shape[0] - t["face"].shape[1] + t["cells_node"].shape[0] == 0
+
+
 def test_csr_is_stable_sort(fv):
     gen = torch.Generator().manual_seed(0)
     for n_items, n_dst in [(1, 1), (17, 5), (10000, 37), (200000, 70001)]:

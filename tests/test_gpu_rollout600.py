@@ -1,10 +1,12 @@
 """GPU (B200): BASELINE config 4 — a 600-step autoregressive rollout with the rollout-error metric of the reference's
-rollout.py:446-482 (cumulative relative squared error of the cell velocities and of the face pressure), on a COMSOL-style
-all-triangle cylinder mesh.  (The reference cannot process quad cells at all — SURVEY.md §0 item 5 — so the tri/quad "hybrid"
-part of that config has no reference behaviour to be equal to; parity is defined on triangle meshes.)
+rollout.py:446-482 (cumulative relative squared error of the cell velocities and of the face pressure), on the three geometries of
+the reference's hybrid COMSOL set (cylinder / rect / NACA0012 in a channel, Extract_mesh/parse_comsol.py:411-418), all-triangle.
+(The reference cannot process quad cells at all — SURVEY.md §0 item 5: its "hybrid" set is hybrid in geometry, not in element
+type — so quad cells have no reference behaviour to be equal to; parity is defined on triangle meshes.)
 
   strict fp32 CUDA path  vs  the oracle's torch-CPU rollout:   sqrt(cumulative relative error) <= 1e-4 over 600 steps, and every
                                                                step's relative L2 <= 1e-4 (1e-5 per step compounds ~linearly)
+  fp32-equivalent tensor-core path (bf16x3, the default)  vs  the oracle: the same bound as the strict path
   bf16 tensor-core path  vs  the strict fp32 CUDA rollout:     sqrt(cumulative relative error) <= 3e-2 on the cell velocities and
                                                                <= 6e-2 on the face pressure (the stated bf16 bound; measured 9e-3 / 3e-2)
 """
@@ -45,8 +47,9 @@ def _cuda_rollout(fv, tab, m, sd, math):
     return torch.stack(uv), torch.stack(p)
 
 
-def test_rollout_600_steps_fp32_vs_oracle_and_bf16_bound(fv):
-    m = fv.synthetic.make("cyl", seed=5, T=3, n_target=700)
+@pytest.mark.parametrize("kind", ["cyl", "rect", "naca"])
+def test_rollout_600_steps_fp32_vs_oracle_and_bf16_bound(fv, kind):
+    m = fv.synthetic.make(kind, seed=5, T=3, n_target=700)
     tab = O.build_connectivity(m["mesh_pos"], m["cells"], m["node_type"], "B")
     sd = H.torch_reference_state_dict(0)
     # oracle rollout (torch CPU, fp32 — the reference's own arithmetic)
@@ -67,6 +70,11 @@ def test_rollout_600_steps_fp32_vs_oracle_and_bf16_bound(fv):
     per_step = ((guv - ouv) ** 2).sum(dim=(1, 2)).sqrt() / (ouv ** 2).sum(dim=(1, 2)).sqrt()
     print("fp32 600-step rollout: sqrt(cum rel err) uv %.2e p %.2e, worst per-step rel-L2 %.2e" % (c_uv[-1].sqrt(), c_p[-1].sqrt(), per_step.max()))
     assert float(c_uv[-1].sqrt()) < 1e-4 and float(c_p[-1].sqrt()) < 1e-4 and float(per_step.max()) < 1e-4
+    xuv, xp = _cuda_rollout(fv, tab, m, sd, "bf16x3")
+    x_uv, x_p = cumulative_relative_error(xuv, ouv, xp, op)
+    per_step = ((xuv - ouv) ** 2).sum(dim=(1, 2)).sqrt() / (ouv ** 2).sum(dim=(1, 2)).sqrt()
+    print("bf16x3 600-step rollout: sqrt(cum rel err) uv %.2e p %.2e, worst per-step rel-L2 %.2e" % (x_uv[-1].sqrt(), x_p[-1].sqrt(), per_step.max()))
+    assert float(x_uv[-1].sqrt()) < 1e-4 and float(x_p[-1].sqrt()) < 1e-4 and float(per_step.max()) < 1e-4
     buv, bp = _cuda_rollout(fv, tab, m, sd, "bf16")
     b_uv, b_p = cumulative_relative_error(buv, guv, bp, gp)
     print("bf16 600-step rollout vs fp32: sqrt(cum rel err) uv %.2e p %.2e" % (b_uv[-1].sqrt(), b_p[-1].sqrt()))

@@ -14,7 +14,8 @@ from tests import helpers as H
 import fvgn_b200.synthetic as S
 
 
-@pytest.mark.parametrize("kind,seed,rule", [("tiny", 7, "A"), ("tiny", 8, "B"), ("cyl", 9, "B"), ("grid", 4, "B")])
+@pytest.mark.parametrize("kind,seed,rule", [("tiny", 7, "A"), ("tiny", 8, "B"), ("cyl", 9, "B"), ("grid", 4, "B"),
+                                            ("rect", 3, "B"), ("naca", 3, "B"), ("naca", 4, "A")])
 def test_connectivity_live(ref, kind, seed, rule):
     m = S.make(kind, seed=seed)
     R = RL.ref_extract_mesh_state(m["mesh_pos"], m["cells"], m["node_type"], m["velocity"], m["pressure"], face_rule=rule)
