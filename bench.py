@@ -422,7 +422,7 @@ def training_measure(args, rank, world, dev, meshes, dist):
     if args.train_graph:
         # the same step captured into one CUDA graph (fvgn_b200.GraphedTrainStep): no Python / launch overhead per step
         try:
-            opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=True)
+            opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=True, fused=True)  # one fused multi-tensor kernel per chunk (the foreach path divides by 0-dim step tensors one parameter at a time: 524 launches)
             gn_s, ge_s, gc_s = _shallow(gn0), _shallow(ge0), _shallow(gc0)
             gn_s.x = node_dev.clone()
             graphed = fv.GraphedTrainStep(model, opt, p, gn_s, ge_s, gc_s, RHO, MU, DT, all_reduce=bucket.all_reduce_mean_ if world > 1 else None)
@@ -508,7 +508,7 @@ def cpu_setup(workload, n_graphs):
 def cpu_baseline(args, budget_s=15.0):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    n_graphs = 1 if args.workload != "tiny" else 2
+    n_graphs = WORKLOADS[args.workload][2]  # the whole batch of one rank: same workload as the GPU arm, bounded in the number of steps
     step, C = cpu_setup(args.workload, n_graphs)
     step()
     t0 = time.perf_counter()
@@ -531,7 +531,7 @@ def reference_arm(args, rank, world):
         return None
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    n_graphs = 1 if args.workload != "tiny" else 2
+    n_graphs = WORKLOADS[args.workload][2]  # the whole batch of one rank (the GPU arm's config), bounded in the number of steps
     step, C = cpu_setup(args.workload, n_graphs)
     for _ in range(max(1, min(args.warmup, 3))):
         step()

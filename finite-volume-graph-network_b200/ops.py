@@ -93,6 +93,26 @@ def as_i32(t):
 
 
 # ------------------------------------------------------------------------------------------------ MLP weights
+# Weight-change detection for the packed tensor-core tiles: the tensors' version counters catch in-place updates made through
+# ordinary ops (copy_, load_state_dict, the foreach / single-tensor optimizers), but torch's FUSED optimizers (AdamW(fused=True) ...)
+# update parameters without bumping `_version`.  A process-wide optimizer-step hook therefore advances an epoch that is part of the
+# pack key: any optimizer step re-packs at the next forward (a few microseconds per MLP, on the device).
+_WEIGHTS_EPOCH = [0]
+
+
+def _on_optimizer_step(optimizer, args, kwargs):
+    _WEIGHTS_EPOCH[0] += 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook  # noqa: E402
+
+_register_step_hook(_on_optimizer_step)
+
+
+def _weights_key(tensors):
+    return (_WEIGHTS_EPOCH[0],) + tuple(t._version for t in tensors[:6:2])
+
+
 class MlpRef:
     """Borrowed pointers to one build_mlp's parameters (reference state_dict layout)."""
 
@@ -121,7 +141,7 @@ class MlpRef:
 
     def ensure_packed_bwd(self):
         """transposed 3-way-split weight tiles of the tensor-core data-gradient chain (fvgn_mlp_dgrad_x3)"""
-        ver = tuple(t._version for t in self.tensors[:6:2])
+        ver = _weights_key(self.tensors)
         if self.packed3b is None or self.packed3b_versions != ver:
             L = _lib.lib()
             nbytes = L.fvgn_mlp_packed_x3_bwd_bytes(self.k_in)
@@ -136,7 +156,7 @@ class MlpRef:
     def ensure_packed(self, math_mode=1):
         """(Re)build the swizzled weight tiles the tcgen05 paths read (math_mode 1: bf16; 2: exact 3-way bf16 split), if the fp32
         weights changed since the last pack."""
-        ver = tuple(t._version for t in self.tensors[:6:2])
+        ver = _weights_key(self.tensors)
         if math_mode == 2:
             if self.packed3 is None or self.packed3_versions != ver:
                 L = _lib.lib()

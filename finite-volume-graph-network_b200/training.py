@@ -19,7 +19,8 @@ class GraphedTrainStep:
     def __init__(self, model, optimizer, params, graph_node, graph_edge, graph_cell, rho, mu, dt, edge_one_hot=9, cell_one_hot=0,
                  all_reduce=None, warmup=3, preprocess_kwargs=None):
         """graph_* = one collated batch in the layout of Data_Pool.get (graph_node.x [N,6]); the index tables are static, the node
-        fields are refreshed per step with `load(node_x)`.  The optimizer must be capturable (e.g. AdamW(..., capturable=True)).
+        fields are refreshed per step with `load(node_x)`.  The optimizer must be capturable (e.g. AdamW(..., capturable=True, fused=True):
+        the fused implementation is a handful of launches, the foreach one ~590).
         `all_reduce`: optional callable run between backward and optimizer.step (parallel.GradBucket.all_reduce_mean_)."""
         self.model, self.opt, self.params = model, optimizer, params
         self.gn, self.ge, self.gc = graph_node, graph_edge, graph_cell

@@ -124,7 +124,7 @@ def test_graphed_train_step_matches_eager_steps(fv, golden):
         return fv.dataset.collate([_graphs(fv, f, "tab.", "velocity", "pressure", pair=1), _graphs(fv, f, "tab1.", "velocity1", "pressure1", pair=0)])
 
     model = _model(fv, f).train().set_math_mode("bf16x3")
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=True, fused=True)  # graphed: the fused multi-tensor AdamW; the eager twin below: the foreach one
     gn0, ge0, gc0 = batch()
     step = fv.GraphedTrainStep(model, opt, p, gn0, ge0, gc0, H.RHO, H.MU, H.DT, preprocess_kwargs=pre, warmup=2)  # 2 real steps (capture records, it does not run)
     replayed = [float(step.step()[0]) for _ in range(3)]                                                           # steps 3..5

@@ -89,3 +89,26 @@ def test_synthetic_meshes_shapes():
     t = O.build_connectivity(cyl["mesh_pos"], cyl["cells"], cyl["node_type"])
     assert cyl["mesh_pos"].shape[0] - t["face"].shape[1] + cyl["cells"].shape[0] == 0  # one hole
     assert (t["cells_area"] > 0).all()
+
+
+def test_fused_optimizer_step_invalidates_packed_weights():
+    """torch's fused optimizers update parameters without bumping Tensor._version; the pack key of the tensor-core weight tiles must
+    change anyway (process-wide optimizer-step hook), or a training loop would run its forward on stale packed weights"""
+    import torch
+
+    from fvgn_b200 import ops
+
+    ws = [torch.nn.Parameter(torch.ones(4, 4)) for _ in range(6)]
+    for w in ws:
+        w.grad = torch.ones_like(w)
+    k0 = ops._weights_key(ws)
+    try:
+        opt = torch.optim.AdamW(ws, lr=1e-3, fused=True)
+    except (RuntimeError, TypeError):
+        opt = torch.optim.AdamW(ws, lr=1e-3)
+    opt.step()
+    assert ops._weights_key(ws) != k0
+    k1 = ops._weights_key(ws)
+    with torch.no_grad():
+        ws[0].mul_(2.0)  # ordinary in-place update: caught by the version counter
+    assert ops._weights_key(ws) != k1

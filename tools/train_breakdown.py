@@ -1,5 +1,5 @@
 """Per-kernel GPU-time breakdown of one eager training step (cyl16, batch 16, default math mode) with the torch profiler (CUPTI).
-usage: python tools/train_breakdown.py"""
+usage: python tools/train_breakdown.py [math] [graph]      ("graph": profile one replay of training.GraphedTrainStep instead)"""
 import collections
 import sys
 
@@ -37,6 +37,12 @@ def tstep():
     opt.step()
 
 
+if "graph" in sys.argv[2:]:
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=True, fused=True)  # one fused multi-tensor kernel per chunk (the foreach path divides by 0-dim step tensors one parameter at a time: 524 launches)
+    gn_s, ge_s, gc_s = bench._shallow(gn0), bench._shallow(ge0), bench._shallow(gc0)
+    gn_s.x = gn0.x.clone()
+    graphed = fv.GraphedTrainStep(model, opt, p, gn_s, ge_s, gc_s, bench.RHO, bench.MU, bench.DT)
+    tstep = graphed.step  # noqa: F811
 for _ in range(3):
     tstep()
 torch.cuda.synchronize()
@@ -46,7 +52,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
-        a = agg[e.name[:90]]
+        a = agg[e.name[:90] if 'elementwise_kernel' not in e.name else e.name[:400]]
         a[0] += 1
         a[1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
 tot = sum(v[1] for v in agg.values())
