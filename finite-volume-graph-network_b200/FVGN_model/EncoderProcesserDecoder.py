@@ -104,14 +104,15 @@ class GnBlock(nn.Module):
 def fused_gn_block(block: GnBlock, topo, x, e, inplace, node_agg=None, x_prime=None, x_prime_bf16=None, x_prime_split=None,
                    cell_mean_split=None):
     cb, eb = block.cb_module.net, block.eb_module.net
-    node_agg = ops.node_aggregate_fwd(e, topo.node_ptr, topo.node_items, topo.N, out=node_agg)
+    a = topo.agg(block.cb_module.mp_times)
+    node_agg = ops.node_aggregate_fwd(e, a.ptr, a.items, a.rows, out=node_agg)
     if inplace and x_prime_split is not None and cb.math_mode == "bf16x3" and eb.math_mode == "bf16x3":
         # fp32-equivalent fast path: x' lives only as the split fp16 shadow the EdgeBlock gathers (same bits as the two calls below)
-        return ops.gn_block_fwd_inplace_split(cb.mlp_ref(), eb.mlp_ref(), x, e, node_agg, topo.cnT, topo.nc, x_prime_split, cell_mean_split)
+        return ops.gn_block_fwd_inplace_split(cb.mlp_ref(), eb.mlp_ref(), x, e, node_agg, a.idx, topo.nc, x_prime_split, cell_mean_split)
     if inplace and x_prime_bf16 is not None and cb.math_mode == "bf16" and eb.math_mode == "bf16":
         # tensor-core fast path: x' lives only as the bf16 shadow the EdgeBlock gathers (same arithmetic as the two calls below)
-        return ops.gn_block_fwd_inplace_bf16(cb.mlp_ref(), eb.mlp_ref(), x, e, node_agg, topo.cnT, topo.nc, x_prime_bf16)
-    x_prime, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, node_agg, topo.cnT, cb.math_mode_id(), x_prime=x_prime, x_out=x if inplace else None)
+        return ops.gn_block_fwd_inplace_bf16(cb.mlp_ref(), eb.mlp_ref(), x, e, node_agg, a.idx, topo.nc, x_prime_bf16)
+    x_prime, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, node_agg, a.idx, cb.math_mode_id(), x_prime=x_prime, x_out=x if inplace else None)
     _, e_new = ops.edge_block_fwd(eb.mlp_ref(), x_prime, e, topo.nc, eb.math_mode_id(), e_out=e if inplace else None)
     return x_new, e_new
 
@@ -158,7 +159,8 @@ class EncoderProcesserDecoder(nn.Module):
         e = self.encoder.eb_encoder(graph.edge_attr)
         if capture is not None:
             capture["enc_x"], capture["enc_e"] = x.clone(), e.clone()
-        node_agg = torch.empty((topo.N, 64), dtype=torch.float32, device=x.device)
+        mp_times = self.processer_list[0].cb_module.mp_times if len(self.processer_list) else 2
+        node_agg = torch.empty((topo.agg(mp_times).rows, 64), dtype=torch.float32, device=x.device)
         all_bf16 = all(b.cb_module.net.math_mode == "bf16" and b.eb_module.net.math_mode == "bf16" for b in self.processer_list)
         all_x3 = all(b.cb_module.net.math_mode == "bf16x3" and b.eb_module.net.math_mode == "bf16x3" for b in self.processer_list)
         x_prime = None if (all_bf16 or all_x3) else torch.empty_like(x)

@@ -36,8 +36,9 @@ class CellBlock(nn.Module):
         super().__init__()
         if attention_size % MultiHead > 0:
             raise ValueError("MultiHead must be the factor of attention_size")
-        if dual_edge or mp_times < 2:
-            raise NotImplementedError("dual_edge=True / mp_times<2 are outside the B200 hot path (SURVEY.md §8f rank 4)")
+        if dual_edge:
+            # (the reference itself cannot run this: GnBlock sizes the cell MLP for 128+64 inputs, dual_edge feeds it 128+128)
+            raise NotImplementedError("dual_edge=True is outside the B200 hot path (SURVEY.md §8f rank 4)")
         self.net = custom_func
         self.mp_times = mp_times
         self.dual_edge = dual_edge
@@ -45,6 +46,7 @@ class CellBlock(nn.Module):
     def forward(self, graph, graph_node, topo=None):
         if topo is None:
             topo = topology_of(graph, graph_node)
-        node_agg = ops.node_aggregate_fwd(graph.edge_attr.contiguous(), topo.node_ptr, topo.node_items, topo.N)
-        x_prime, _ = ops.cell_block_fwd(self.net.mlp_ref(), graph.x.contiguous(), node_agg, topo.cnT, self.net.math_mode_id(), want_out=False)
+        a = topo.agg(self.mp_times)  # mp_times >= 2: faces -> nodes -> cells; 1: faces -> cells (GN_blocks.py:110-138)
+        node_agg = ops.node_aggregate_fwd(graph.edge_attr.contiguous(), a.ptr, a.items, a.rows)
+        x_prime, _ = ops.cell_block_fwd(self.net.mlp_ref(), graph.x.contiguous(), node_agg, a.idx, self.net.math_mode_id(), want_out=False)
         return Data(x=x_prime, edge_attr=graph.edge_attr, edge_index=graph.edge_index)

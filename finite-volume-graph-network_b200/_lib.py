@@ -89,7 +89,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.fvgn_abi_version() != 6:
+        if L.fvgn_abi_version() != 7:
             raise RuntimeError("libfvgn_b200.so ABI version mismatch")
         _lib = L
     return _lib

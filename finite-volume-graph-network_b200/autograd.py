@@ -45,9 +45,10 @@ class NetFunction(torch.autograd.Function):
         saved = []
         for blk in epd.processer_list:
             cb, eb = blk.cb_module.net, blk.eb_module.net
-            na = ops.node_aggregate_fwd(e, topo.node_ptr, topo.node_items, topo.N)
+            ag = topo.agg(blk.cb_module.mp_times)
+            na = ops.node_aggregate_fwd(e, ag.ptr, ag.items, ag.rows)
             zc, ze = zbuf(topo.C), zbuf(topo.F)
-            xp, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, na, topo.cnT, mm, z_save=zc)
+            xp, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, na, ag.idx, mm, z_save=zc)
             _, e_new = ops.edge_block_fwd(eb.mlp_ref(), xp, e, topo.nc, mm, z_save=ze)
             saved.append((x, e, xp, na, zc, ze))
             x, e = x_new, e_new
@@ -107,6 +108,7 @@ class NetFunction(torch.autograd.Function):
         for blk in reversed(epd.processer_list):
             x_in, e_in, xp, na, zc, ze = saved_layers.pop()
             cb, eb = blk.cb_module.net, blk.eb_module.net
+            ag = topo.agg(blk.cb_module.mp_times)
             if tc:
                 dz, gxh = ops.ln_bwd(g_e, ze, eb[1].weight)
                 da, dA_e = ops.mlp_dgrad_x3(eb.mlp_ref(), dz, ze, want_dA=True)
@@ -118,12 +120,15 @@ class NetFunction(torch.autograd.Function):
             if tc:
                 dz, gxh = ops.ln_bwd(g_xp, zc, cb[1].weight)
                 da, dA_c = ops.mlp_dgrad_x3(cb.mlp_ref(), dz, zc, want_dA=True, dA_base=g_x)
-                grads[id(cb)] = ops.mlp_wgrad_x3(cb.mlp_ref(), 1, g_xp, dz, gxh, zc, da, src0=x_in, src1=na, idx=topo.cnT)
+                grads[id(cb)] = ops.mlp_wgrad_x3(cb.mlp_ref(), 1, g_xp, dz, gxh, zc, da, src0=x_in, src1=na, idx=ag.idx)
             else:
-                grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, topo.cnT, g_xp, d_x_base=g_x, z_saved=zc)
+                grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, ag.idx, g_xp, d_x_base=g_x, z_saved=zc)
             # transposes of the twice-message aggregation: cell -> node (x 1/3), node -> face halves
-            g_na = ops.segment_sum_rows(dA_c, topo.C, 128, 0, 64, nptr, nitems, topo.N, base=None, scale=1.0 / 3.0)
-            g_e = ops.edge_grad_combine(g_e, dA_e, g_na, topo.fn)
+            if ag.idx is not None:
+                g_na = ops.segment_sum_rows(dA_c, topo.C, 128, 0, 64, nptr, nitems, topo.N, base=None, scale=1.0 / 3.0)
+            else:  # mp_times = 1: the aggregate is per cell and enters the MLP as it is; its transpose is the identity
+                g_na = dA_c[:, 128:192].contiguous()
+            g_e = ops.edge_grad_combine(g_e, dA_e, g_na, ag.face)
             g_x = dA_c[:, 0:128]
         for enc, inp, g, z in ((epd.encoder.cb_encoder, cell_in, g_x, z_enc_c), (epd.encoder.eb_encoder, edge_in, g_e, z_enc_e)):
             if tc:

@@ -40,6 +40,16 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 int sm_count();
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// CellBlock second aggregation (GN_blocks.py:110-138), 4 columns of one cell's 64-wide aggregate.  idx != NULL (mp_times >= 2): mean of
+// the cell's three node aggregates, ((a + b) + c) / 3.0 in the reference's order (add, add, true division: no FMA contraction possible).
+// idx == NULL (mp_times = 1): `na` already is the per-cell scatter-add [C,64] (GN_blocks.py:130-138) and is read as it is.
+__device__ __forceinline__ float4 cell_agg4(const float* na, const int32_t* idx, size_t C, int c, int col) {
+  if (idx == nullptr) return ldg4(na + (size_t)c * 64 + col);
+  const int n0 = __ldg(idx + c), n1 = __ldg(idx + C + c), n2 = __ldg(idx + 2 * C + c);
+  const float4 a = ldg4(na + (size_t)n0 * 64 + col), b = ldg4(na + (size_t)n1 * 64 + col), d = ldg4(na + (size_t)n2 * 64 + col);
+  return make_float4(__fdiv_rn(__fadd_rn(__fadd_rn(a.x, b.x), d.x), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.y, b.y), d.y), 3.0f),
+                     __fdiv_rn(__fadd_rn(__fadd_rn(a.z, b.z), d.z), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.w, b.w), d.w), 3.0f));
+}
 __device__ __forceinline__ float silu_f(float v) {
   // x * sigmoid(x) with IEEE division; expf (not __expf) keeps the strict-fp32 path within ~1 ulp of torch's SiLU
   return v / (1.0f + expf(-v));

@@ -241,14 +241,7 @@ __device__ __forceinline__ void gather_seg(const BwdParams& p, int seg, int row0
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = warp * 8 + i * 2 + hw, c = row0 + r;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < C) {
-          const int n0 = __ldg(p.idx + c), n1 = __ldg(p.idx + C + c), n2 = __ldg(p.idx + 2 * (size_t)C + c);
-          const float4 a = ldg4(p.src1 + (size_t)n0 * 64 + hl * 4), b = ldg4(p.src1 + (size_t)n1 * 64 + hl * 4),
-                       d = ldg4(p.src1 + (size_t)n2 * 64 + hl * 4);
-          o.x = __fdiv_rn(__fadd_rn(__fadd_rn(a.x, b.x), d.x), 3.0f); o.y = __fdiv_rn(__fadd_rn(__fadd_rn(a.y, b.y), d.y), 3.0f);
-          o.z = __fdiv_rn(__fadd_rn(__fadd_rn(a.z, b.z), d.z), 3.0f); o.w = __fdiv_rn(__fadd_rn(__fadd_rn(a.w, b.w), d.w), 3.0f);
-        }
+        const float4 o = (c < C) ? cell_agg4(p.src1, p.idx, (size_t)C, c, hl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4*>(S + r * HLD + hl * 4) = o;
         *reinterpret_cast<float4*>(S + r * HLD + 64 + hl * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -599,7 +592,7 @@ extern "C" int fvgn_mlp_rows_bwd(const fvgn_mlp_t* mlp, const float* in, int ld_
 extern "C" int fvgn_cell_block_bwd(const fvgn_mlp_t* mlp, const float* x, const float* node_agg, const int32_t* cells_node_T, int n_cells,
                                    const float* d_x_prime, const float* d_x_base, int ld_base, float* d_in /*[C,192]*/, float* grads,
                                    float* workspace, fvgn_stream_t stream) {
-  FVGN_CHECK_ARG(mlp && x && node_agg && cells_node_T && (d_in || mlp->da_in), "NULL pointer");
+  FVGN_CHECK_ARG(mlp && x && node_agg && (d_in || mlp->da_in), "NULL pointer");  // cells_node_T == NULL: mp_times = 1
   FVGN_CHECK_ARG(mlp->k_in == 192 && mlp->ln_w, "CellBlock MLP must be 192 -> 128 with LayerNorm");
   BwdParams p{};
   p.mlp = *mlp; p.mode = BW_CELL; p.rows = n_cells; p.src0 = x; p.src1 = node_agg; p.idx = cells_node_T; p.d_out = d_x_prime; p.ld_dout = 128;

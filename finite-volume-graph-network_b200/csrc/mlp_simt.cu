@@ -63,18 +63,7 @@ __global__ void __launch_bounds__(NT, 1) fused_mlp_simt_kernel(const SimtParams 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = row0 + warp * 8 + i * 2 + hw;
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < C) {
-        const int n0 = __ldg(p.idx + c), n1 = __ldg(p.idx + C + c), n2 = __ldg(p.idx + 2 * (size_t)C + c);
-        const float4 a = ldg4(na + (size_t)n0 * 64 + hl * 4);
-        const float4 b = ldg4(na + (size_t)n1 * 64 + hl * 4);
-        const float4 d = ldg4(na + (size_t)n2 * 64 + hl * 4);
-        // ((a+b)+c)/3.0 exactly as GN_blocks.py:125-129 (no FMA contraction possible: add, add, div)
-        o.x = __fdiv_rn(__fadd_rn(__fadd_rn(a.x, b.x), d.x), 3.0f);
-        o.y = __fdiv_rn(__fadd_rn(__fadd_rn(a.y, b.y), d.y), 3.0f);
-        o.z = __fdiv_rn(__fadd_rn(__fadd_rn(a.z, b.z), d.z), 3.0f);
-        o.w = __fdiv_rn(__fadd_rn(__fadd_rn(a.w, b.w), d.w), 3.0f);
-      }
+      const float4 o = (c < C) ? cell_agg4(na, p.idx, (size_t)C, c, hl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       ag[i] = o;
     }
 #pragma unroll
@@ -230,7 +219,7 @@ int simt_cell_block(const fvgn_mlp_t* mlp, const float* x, const float* node_agg
                     float* x_prime, float* x_out, cudaStream_t st) {
   if (int e = check_mlp(mlp, true)) return e;
   FVGN_CHECK_ARG(mlp->k_in == 192, "CellBlock MLP must have k_in == 192 (128 + 64)");
-  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && node_agg && cells_node_T)), "NULL input");
+  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && node_agg)), "NULL input");  // cells_node_T == NULL: mp_times = 1
   SimtParams p{};
   p.mlp = *mlp; p.rows = n_cells; p.src0 = x; p.src1 = node_agg; p.idx = cells_node_T; p.out0 = x_prime; p.out1 = x_out; p.ld_out = HID;
   return launch_simt<MODE_CELL, 192>(p, st);

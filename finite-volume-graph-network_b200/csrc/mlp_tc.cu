@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
         const int C = p.rows;
         int32_t* sIdx = reinterpret_cast<int32_t*>(smem + L.total);  // [4 tiles][3][128]
         auto issue_idx = [&](int jl) {
-          if (jl < n_local) {
+          if (jl < n_local && p.idx != nullptr) {  // (idx == NULL: mp_times = 1, node_agg is per cell and read directly)
             const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
             int32_t* dst = sIdx + (jl & 3) * 384;
 #pragma unroll
@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
         issue_idx(0);
         issue_idx(1);
         float4 fa[2][3], fb[2][3];
-        constexpr float k3 = 1.0f / 3.0f;  // rounded to bf16 right after: indistinguishable from the reference's division by 3
+        // 1/3: rounded to bf16 right after, indistinguishable from the reference's division by 3; mp_times = 1: the row as it is
+        const float k3 = p.idx != nullptr ? 1.0f / 3.0f : 1.0f;
 #pragma unroll 1
         for (int jl = 0; jl < n_local; ++jl) {
           issue_idx(jl + 2);
@@ -201,6 +202,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const int r = 16 * bq + hw + 8 * i;
+              if (p.idx == nullptr) {
+                f[i][0] = ldg4(p.src1 + (size_t)min(((int)blockIdx.x + jl * (int)gridDim.x) * TM + r, last) * 64 + hl * 4);
+                f[i][1] = f[i][2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+              }
               const int n0 = ix[r], n1 = ix[128 + r], n2 = ix[256 + r];
               if (FVGN_DBG(p) & 1) { f[i][0] = f[i][1] = f[i][2] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
               f[i][0] = ldg4(p.src1 + (size_t)n0 * 64 + hl * 4);
@@ -356,6 +362,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
           const float* base = p.src0 + t * 64 + hl * 4;
 #pragma unroll
           for (int i = 0; i < RPT; ++i) v[i] = ldg4_hint(base + (size_t)min(row0 + hw + NHW * i, C - 1) * 128, pol_keep);
+        } else if (p.idx == nullptr) {  // mp_times = 1: node_agg is the per-cell scatter-add, read as it is
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) v[i] = ldg4(p.src1 + (size_t)min(row0 + hw + NHW * i, C - 1) * 64 + hl * 4);
         } else {
           int n0[RPT], n1[RPT], n2[RPT];
 #pragma unroll
@@ -773,7 +782,7 @@ int tc_cell_block(const fvgn_mlp_t* mlp, const float* x, const float* node_agg, 
                   float* x_out, int math_mode, cudaStream_t st, uint16_t* x_prime_bf16) {
   if (int e = check_tc_mlp(mlp, true, math_mode)) return e;
   FVGN_CHECK_ARG(mlp->k_in == 192, "CellBlock MLP must have k_in == 192");
-  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && node_agg && cells_node_T)), "NULL input");
+  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && node_agg)), "NULL input");  // cells_node_T == NULL: mp_times = 1
   TcParams p{};
   p.mode = TC_CELL; p.rows = n_cells; p.src0 = x; p.src1 = node_agg; p.idx = cells_node_T; p.out0 = x_prime; p.out1 = x_out; p.ld_out = 128;
   p.use_red = (x_out != nullptr && x_out == x && red_enabled()) ? 1 : 0;

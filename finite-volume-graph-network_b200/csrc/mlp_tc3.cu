@@ -291,14 +291,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         } else {
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
-            const int c = min(row0 + hw + NHW * i, last);
-            const int n0 = __ldg(p.idx + c), n1 = __ldg(p.idx + (size_t)C + c), n2 = __ldg(p.idx + 2 * (size_t)C + c);
-            const float4 a = ldg4(p.src1 + (size_t)n0 * 64 + hl * 4);
-            const float4 b = ldg4(p.src1 + (size_t)n1 * 64 + hl * 4);
-            const float4 d = ldg4(p.src1 + (size_t)n2 * 64 + hl * 4);
-            // the reference's arithmetic: (a + b) + c, then a true division by 3.0 (GN_blocks.py:125-129)
-            v[i] = make_float4(__fdiv_rn(__fadd_rn(__fadd_rn(a.x, b.x), d.x), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.y, b.y), d.y), 3.0f),
-                               __fdiv_rn(__fadd_rn(__fadd_rn(a.z, b.z), d.z), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.w, b.w), d.w), 3.0f));
+            // the reference's arithmetic: (a + b) + c, then a true division by 3.0 (GN_blocks.py:125-129); mp_times = 1: the row itself
+            v[i] = cell_agg4(p.src1, p.idx, (size_t)C, min(row0 + hw + NHW * i, last), hl * 4);
           }
         }
       } else {  // TC_ROWS
@@ -1201,12 +1195,7 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
             } else if (p.mode == TC_CELL) {
               if (seg == 0) b = ldg4(p.src0 + (size_t)gc * 128 + col);
               else if (hh == 0) {
-                const int C = p.rows;
-                const int n0 = __ldg(p.idx + gc), n1 = __ldg(p.idx + (size_t)C + gc), n2 = __ldg(p.idx + 2 * (size_t)C + gc);
-                const float4 u = ldg4(p.src1 + (size_t)n0 * 64 + 4 * hl), v = ldg4(p.src1 + (size_t)n1 * 64 + 4 * hl),
-                             w = ldg4(p.src1 + (size_t)n2 * 64 + 4 * hl);
-                b = make_float4(__fdiv_rn(__fadd_rn(__fadd_rn(u.x, v.x), w.x), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(u.y, v.y), w.y), 3.0f),
-                                __fdiv_rn(__fadd_rn(__fadd_rn(u.z, v.z), w.z), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(u.w, v.w), w.w), 3.0f));
+                b = cell_agg4(p.src1, p.idx, (size_t)p.rows, gc, 4 * hl);
               }
             } else {
               float t[4];
@@ -1391,12 +1380,7 @@ __global__ void __launch_bounds__(256) cell_mean_split_kernel(const float* __res
   const int gid = blockIdx.x * 256 + threadIdx.x;
   const int c = gid >> 4, hl = gid & 15;
   if (c >= C) return;
-  const int n0 = __ldg(cells_node_T + c), n1 = __ldg(cells_node_T + (size_t)C + c), n2 = __ldg(cells_node_T + 2 * (size_t)C + c);
-  const float4 a = ldg4(node_agg + (size_t)n0 * 64 + hl * 4);
-  const float4 b = ldg4(node_agg + (size_t)n1 * 64 + hl * 4);
-  const float4 d = ldg4(node_agg + (size_t)n2 * 64 + hl * 4);
-  const float4 v = make_float4(__fdiv_rn(__fadd_rn(__fadd_rn(a.x, b.x), d.x), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.y, b.y), d.y), 3.0f),
-                               __fdiv_rn(__fadd_rn(__fadd_rn(a.z, b.z), d.z), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.w, b.w), d.w), 3.0f));
+  const float4 v = cell_agg4(node_agg, cells_node_T, (size_t)C, c, hl * 4);  // cells_node_T == NULL (mp_times = 1): node_agg is per cell
   uint2 q0, q1;
   split2_pair(v.x * ASCALE, v.y * ASCALE, q0.x, q1.x);
   split2_pair(v.z * ASCALE, v.w * ASCALE, q0.y, q1.y);
@@ -1551,7 +1535,7 @@ int tc3_cell_block(const fvgn_mlp_t* mlp, const float* x, const float* node_agg,
                    float* x_out, cudaStream_t st) {
   if (int e = check_mlp3(mlp, true)) return e;
   FVGN_CHECK_ARG(mlp->k_in == 192, "CellBlock MLP must have k_in == 192");
-  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && node_agg && cells_node_T)), "NULL input");
+  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (x && node_agg)), "NULL input");  // cells_node_T == NULL: mp_times = 1
   x3::Params p{};
   p.mode = x3::TC_CELL; p.rows = n_cells; p.src0 = x; p.src1 = node_agg; p.idx = cells_node_T; p.out0 = x_prime; p.out1 = x_out; p.ld_out = 128;
   return launch_tc3(p, mlp, x_out != nullptr && x_out == x, st);
@@ -1571,7 +1555,7 @@ int tc3_edge_block(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, 
 static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 int tc3_cell_mean_split(const float* node_agg, const int32_t* cells_node_T, int n_cells, void* out, cudaStream_t st) {
-  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (node_agg && cells_node_T && out)), "NULL input");
+  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (node_agg && out)), "NULL input");  // cells_node_T == NULL: mp_times = 1
   FVGN_CHECK_ARG(al16(node_agg) && al16(out), "buffers must be 16B aligned");
   if (n_cells == 0) return 0;
   x3::cell_mean_split_kernel<<<cdiv(n_cells * 16, 256), 256, 0, st>>>(node_agg, cells_node_T, n_cells, reinterpret_cast<unsigned char*>(out));
@@ -1681,7 +1665,7 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
   FVGN_CHECK_ARG(m && d_out && grads && workspace, "NULL pointer");
   FVGN_CHECK_ARG(m->z_save && m->da_in, "the tensor-core weight gradients need fvgn_mlp_t.z_save and .da_in (fvgn_mlp_dgrad_x3)");
   FVGN_CHECK_ARG(m->k_in >= 1 && m->k_in <= 384 && m->n_out >= 1 && m->n_out <= 128, "bad mlp dims");
-  FVGN_CHECK_ARG(mode == TC_ROWS ? in != nullptr : (src0 && src1 && idx), "layer input pointers");
+  FVGN_CHECK_ARG(mode == TC_ROWS ? in != nullptr : (src0 && src1 && (idx || mode == TC_CELL)), "layer input pointers");  // CELL, idx == NULL: mp_times = 1
   FVGN_CHECK_ARG(!m->ln_w || (dz && gxhat), "an MLP with LayerNorm needs dz and gxhat from fvgn_ln_bwd");
   FVGN_CHECK_ARG(rows > 0, "rows must be > 0");
   WgParams p{};

@@ -236,12 +236,23 @@ def node_aggregate_fwd(e, node_ptr, node_items, n_nodes, out=None):
     return out
 
 
+def _cell_table_ok(cells_node_T, node_agg, n_cells, who):
+    """cells_node_T [3,C] int32 (mp_times >= 2: node_agg is per node), or None (mp_times = 1: node_agg is the per-cell aggregate [C,64])"""
+    if cells_node_T is None:
+        if tuple(node_agg.shape) != (n_cells, 64):
+            raise ValueError(f"{who}: cells_node_T=None (mp_times=1) needs a per-cell aggregate of shape [{n_cells}, 64], got {tuple(node_agg.shape)}")
+        return
+    _ci(cells_node_T, "cells_node_T", 3)
+    if cells_node_T.dim() != 2 or cells_node_T.shape[1] != n_cells:
+        raise ValueError(f"{who}: cells_node_T must have shape [3, {n_cells}], got {tuple(cells_node_T.shape)}")
+
+
 def cell_block_fwd(mlp: MlpRef, x, node_agg, cells_node_T, math_mode=0, x_prime=None, x_out=None, want_out=True, z_save=None):
     _req(x, torch.float32, "x", 2)
     _req(node_agg, torch.float32, "node_agg", 2)
-    _req(cells_node_T, torch.int32, "cells_node_T", 2)
     Cn = x.shape[0]
-    if not (x.is_contiguous() and node_agg.is_contiguous() and cells_node_T.is_contiguous()) or x.shape[1] != HID or cells_node_T.shape != (3, Cn):
+    _cell_table_ok(cells_node_T, node_agg, Cn, "cell_block_fwd")
+    if not (x.is_contiguous() and node_agg.is_contiguous()) or x.shape[1] != HID:
         raise ValueError("cell_block_fwd: bad shapes/strides")
     if x_prime is None:
         x_prime = torch.empty_like(x)
@@ -286,10 +297,11 @@ def gn_block_fwd_inplace_bf16(cell_mlp: MlpRef, edge_mlp: MlpRef, x, e, node_agg
     bf16 shadow the EdgeBlock gathers (fvgn_cell_block_fwd_xbf16 / fvgn_edge_block_fwd_xbf16)."""
     _req(x, torch.float32, "x", 2), _req(e, torch.float32, "edge_attr", 2), _req(node_agg, torch.float32, "node_agg", 2)
     _req(x_prime_bf16, torch.bfloat16, "x_prime_bf16", 2)
-    _ci(cells_node_T, "cells_node_T", 3), _ci(neighbour_cell, "neighbour_cell", 2)
+    _ci(neighbour_cell, "neighbour_cell", 2)
     Cn, F = x.shape[0], e.shape[0]
+    _cell_table_ok(cells_node_T, node_agg, Cn, "gn_block_fwd_inplace_bf16")
     if not (x.is_contiguous() and e.is_contiguous() and node_agg.is_contiguous() and x_prime_bf16.is_contiguous()) or x.shape[1] != HID \
-            or e.shape[1] != HID or tuple(x_prime_bf16.shape) != (Cn, HID) or cells_node_T.shape[1] != Cn or neighbour_cell.shape[1] != F:
+            or e.shape[1] != HID or tuple(x_prime_bf16.shape) != (Cn, HID) or neighbour_cell.shape[1] != F:
         raise ValueError("gn_block_fwd_inplace_bf16: bad shapes/strides")
     cell_mlp.ensure_packed(), edge_mlp.ensure_packed()
     L = _lib.lib()
@@ -314,10 +326,11 @@ def gn_block_fwd_inplace_split(cell_mlp: MlpRef, edge_mlp: MlpRef, x, e, node_ag
     """Inference fast path of one GnBlock in the fp32-equivalent mode after the node aggregation: x += x', e += e' in place; x' only
     exists as the split fp16 shadow the EdgeBlock gathers (fvgn_cell_block_fwd_split / fvgn_edge_block_fwd_split)."""
     _req(x, torch.float32, "x", 2), _req(e, torch.float32, "edge_attr", 2), _req(node_agg, torch.float32, "node_agg", 2)
-    _ci(cells_node_T, "cells_node_T", 3), _ci(neighbour_cell, "neighbour_cell", 2)
+    _ci(neighbour_cell, "neighbour_cell", 2)
     Cn, F = x.shape[0], e.shape[0]
+    _cell_table_ok(cells_node_T, node_agg, Cn, "gn_block_fwd_inplace_split")
     if not (x.is_contiguous() and e.is_contiguous() and node_agg.is_contiguous()) or x.shape[1] != HID or e.shape[1] != HID \
-            or cells_node_T.shape[1] != Cn or neighbour_cell.shape[1] != F:
+            or neighbour_cell.shape[1] != F:
         raise ValueError("gn_block_fwd_inplace_split: bad shapes/strides")
     _split_ok(x_prime_split, Cn, "x_prime_split")
     if cell_mean_split is None:
@@ -557,6 +570,8 @@ def mlp_wgrad_x3(mlp: MlpRef, mode, d_out, dz, gxhat, z_saved, da, x=None, src0=
     ws = torch.empty(L.fvgn_mlp_wgrad_x3_workspace_floats(mlp.k_in), dtype=torch.float32, device=d_out.device)
     if mode == 0:
         _req(x, torch.float32, "x", 2)
+    elif mode == 1:
+        _cf(src0, "src0"), _cf(src1, "src1"), _cell_table_ok(idx, src1, rows, "mlp_wgrad_x3")
     else:
         _cf(src0, "src0"), _cf(src1, "src1"), _ci(idx, "idx")
     _count(4)
@@ -592,8 +607,9 @@ def mlp_rows_bwd(mlp: MlpRef, x, d_out, want_d_in=False, z_saved=None, da_in=Non
 
 
 def cell_block_bwd(mlp: MlpRef, x, node_agg, cells_node_T, d_x_prime, d_x_base=None, z_saved=None, da_in=None):
-    _cf(x, "x"), _cf(node_agg, "node_agg"), _ci(cells_node_T, "cells_node_T", 3), _cf(d_x_prime, "d_x_prime")
+    _cf(x, "x"), _cf(node_agg, "node_agg"), _cf(d_x_prime, "d_x_prime")
     Cn = x.shape[0]
+    _cell_table_ok(cells_node_T, node_agg, Cn, "cell_block_bwd")
     grads, ws = _bwd_buffers(mlp, x.device)
     d_in = torch.empty((Cn, 192), dtype=torch.float32, device=x.device) if da_in is None else None
     _count(2)

@@ -10,6 +10,13 @@ import torch
 from . import ops
 
 
+class _Agg:
+    __slots__ = ("ptr", "items", "rows", "idx", "face")
+
+    def __init__(self, ptr, items, rows, idx, face):
+        self.ptr, self.items, self.rows, self.idx, self.face = ptr, items, rows, idx, face
+
+
 class MeshTopology:
     def __init__(self, neighbour_cell, face_node, cells_node_T, cells_face_T, n_nodes):
         self.nc = ops.as_i32(neighbour_cell)      # [2,F]
@@ -22,6 +29,15 @@ class MeshTopology:
         # node <- (face, half): stable CSR over cat(face[0], face[1])  ==  the reference's scatter_add order (GN_blocks.py:111-122)
         self.node_ptr, self.node_items = ops.build_csr(self.fn.reshape(-1), self.N)
         self._bwd = None
+
+    def agg(self, mp_times=2):
+        """What the CellBlock's edge aggregation walks (GN_blocks.py:110-138).  mp_times >= 2: faces -> nodes -> cells (rows = N, the cell
+        kernel gathers through cells_node_T, backward scatters through face_node); mp_times = 1: faces -> their two cells directly (rows = C,
+        stable CSR over cat(edge_index[0], edge_index[1]) == the reference's scatter_add order; no second gather: idx = None)."""
+        if mp_times >= 2:
+            return _Agg(self.node_ptr, self.node_items, self.N, self.cnT, self.fn)
+        ptr, items = self.backward_tables()["cell_from_face"]
+        return _Agg(ptr, items, self.C, None, self.nc)
 
     def backward_tables(self):
         """CSR transposes needed by the backward kernels: cell<-(face,side), node<-(cell,k), face<-(cell,k)."""

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FVGN_ABI_VERSION 6
+#define FVGN_ABI_VERSION 7 /* v7: cells_node_T == NULL selects the mp_times = 1 CellBlock in every cell-block entry point */
 #define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
 
 #define FVGN_E_BADARG (-1)
@@ -156,7 +156,11 @@ FVGN_API int fvgn_node_aggregate_fwd(const float* e /*[F,128]*/, const int32_t* 
                             float* node_agg /*[N,64]*/, fvgn_stream_t stream);
 /* second aggregation + cell MLP + (fused GnBlock residual, EncoderProcesserDecoder.py:121-122):
  *   x_prime = LN(MLP([x[c] | (na[n0]+na[n1]+na[n2])/3]))      -> x_prime [C,128] (what EdgeBlock gathers)
- *   x_out   = x + x_prime                                     -> x_out  [C,128] (may alias x; NULL to skip) */
+ *   x_out   = x + x_prime                                     -> x_out  [C,128] (may alias x; NULL to skip)
+ * mp_times = 1 (GN_blocks.py:130-138: the edge halves are scatter-added straight onto the face's two cells): pass cells_node_T = NULL
+ * and node_agg = the per-cell aggregate [C,64] (fvgn_node_aggregate_fwd over the CSR of cat(neighbour_cell[0], neighbour_cell[1]));
+ * it is concatenated as it is, no mean.  The same convention holds for fvgn_cell_block_fwd_xbf16, fvgn_cell_mean_split,
+ * fvgn_cell_block_bwd and fvgn_mlp_wgrad_x3 (mode 1). */
 FVGN_API int fvgn_cell_block_fwd(const fvgn_mlp_t* mlp, const float* x /*[C,128]*/, const float* node_agg /*[N,64]*/,
                         const int32_t* cells_node_T /*[3,C]*/, int n_cells, float* x_prime, float* x_out, int math_mode,
                         fvgn_stream_t stream);

@@ -344,9 +344,14 @@ def mlp(sd, prefix, x, layer_norm=True):
     return h
 
 
-def cell_block(sd, prefix, x, edge_attr, node_edge_index, node_face, num_nodes):
-    """CellBlock.forward, mp_times>=2, dual_edge=False (GN_blocks.py:78-145)."""
+def cell_block(sd, prefix, x, edge_attr, node_edge_index, node_face, num_nodes, mp_times=2, edge_index=None):
+    """CellBlock.forward, dual_edge=False (GN_blocks.py:78-145); mp_times >= 2: faces -> nodes -> cells, mp_times = 1 (needs the
+    cell graph's edge_index): faces -> their two cells directly."""
     twoway = torch.cat(torch.chunk(edge_attr, 2, dim=-1), dim=0)  # :91
+    if mp_times < 2:
+        cidx = torch.cat([edge_index[0], edge_index[1]], dim=0)  # :131-132
+        cell_agg = torch.zeros((x.shape[0], twoway.shape[1]), dtype=x.dtype).index_add_(0, cidx, twoway)  # :133-138
+        return mlp(sd, prefix + "net.", torch.cat((x, cell_agg), dim=-1))  # :140-143
     idx = torch.cat([node_edge_index[0], node_edge_index[1]], dim=0)  # :111-114
     node_agg = torch.zeros((num_nodes, twoway.shape[1]), dtype=x.dtype).index_add_(0, idx, twoway)  # :117-122
     cell_agg = (torch.index_select(node_agg, 0, node_face[0]) + torch.index_select(node_agg, 0, node_face[1])
@@ -360,22 +365,22 @@ def edge_block(sd, prefix, x, edge_attr, edge_index):
     return mlp(sd, prefix + "net.", collected)
 
 
-def gn_block(sd, prefix, x, e, edge_index, node_edge_index, node_face, num_nodes):
+def gn_block(sd, prefix, x, e, edge_index, node_edge_index, node_face, num_nodes, mp_times=2):
     """GnBlock.forward (EncoderProcesserDecoder.py:112-124): Cell then Edge, residuals at the end."""
-    xn = cell_block(sd, prefix + "cb_module.", x, e, node_edge_index, node_face, num_nodes)
+    xn = cell_block(sd, prefix + "cb_module.", x, e, node_edge_index, node_face, num_nodes, mp_times, edge_index)
     en = edge_block(sd, prefix + "eb_module.", xn, e, edge_index)
     return x + xn, e + en
 
 
 def epd_forward(sd, prefix, x, edge_attr, edge_index, node_edge_index, node_face, num_nodes, n_mp=15,
-                capture=None):
+                capture=None, mp_times=2):
     """EncoderProcesserDecoder.forward (EncoderProcesserDecoder.py:224-238)."""
     xc = mlp(sd, prefix + "encoder.cb_encoder.", x)  # Encoder :65-76
     e = mlp(sd, prefix + "encoder.eb_encoder.", edge_attr)
     if capture is not None:
         capture["enc_x"], capture["enc_e"] = xc, e
     for l in range(n_mp):
-        xc, e = gn_block(sd, f"{prefix}processer_list.{l}.", xc, e, edge_index, node_edge_index, node_face, num_nodes)
+        xc, e = gn_block(sd, f"{prefix}processer_list.{l}.", xc, e, edge_index, node_edge_index, node_face, num_nodes, mp_times)
         if capture is not None and l in (0, 1, n_mp - 1):
             capture[f"x_l{l}"], capture[f"e_l{l}"] = xc, e
     return mlp(sd, prefix + "decoder.edge_decode_module.", e, layer_norm=False)  # Decoder :161-169
@@ -478,7 +483,7 @@ class FVGNOracle:
         if capture is not None:
             capture["cell_in"], capture["edge_in"] = graph.x, graph.edge_attr
         pred = epd_forward(self.sd, "model.", graph.x, graph.edge_attr, graph.edge_index, graph_node.edge_index,
-                           graph_node.face, graph_node.num_nodes, p.message_passing_num, capture)
+                           graph_node.face, graph_node.num_nodes, p.message_passing_num, capture, getattr(p, "mp_times", 2))
         face_area, raw = self._face_area(graph, graph_edge, dt)
         cont, delta_u = integrator(pred[:, 0:2], pred[:, 2:3].clone().detach(), pred[:, 3:5], graph.unv, rho, 1.0,
                                    face_area, graph_edge.face, p.loss_cont)

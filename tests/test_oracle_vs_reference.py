@@ -49,3 +49,38 @@ def test_eval_and_rollout_live(ref):
             assert torch.equal(uvp, ouvp) and torch.equal(nuv, onuv)
             gc = ref.Data_Pool.create_next_graph(gc, ge, mb, nuv, ct, Re, rmp)
             oc = O.create_next_graph(oc, oe, omb, onuv, ct, Re, rmp)
+
+
+def test_mp_times_1_eval_live(ref):
+    """the reference's mp_times=1 variant (GN_blocks.py:130-138: edge halves scatter-added straight onto the face's two cells):
+    oracle == reference bitwise in eval over 3 rollout steps"""
+    params = RL.default_params(train_traj_length=2, mp_times=1, loss="global_mean_sum")
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = ref.FVGN(device="cpu", model_dir=None, params=params).eval()
+    m = S.make("tiny", seed=22, T=4)
+    R = RL.ref_extract_mesh_state(m["mesh_pos"], m["cells"], m["node_type"], m["velocity"], m["pressure"])
+    dp = RL.ref_data_pool([R], params)
+    gn, ge, gc, mi, mb = dp.require_one_mesh(start_epoch=0, rollout_index=0)
+    T = {k: (v[0] if v.ndim > 0 and v.shape[0] == 1 else v) for k, v in R.items()}
+    on, oe, oc = O.build_graphs(T, m["velocity"], m["pressure"])
+    on, oe, oc, omi, omb = O.valid_datapreprocessing(on, oe, oc, 0)
+    orc = O.FVGNOracle(model.state_dict(), params)
+    ct, Re, rmp = gc.x[:, 0:1].clone(), gc.x[:, 1:2].clone(), gc.edge_attr[:, 2:5].clone()
+    with torch.no_grad():
+        for _ in range(3):
+            uvp, nuv = model(graph=gc, graph_edge=ge, graph_node=gn, rho=1.0, mu=1e-3, dt=0.01, edge_one_hot=9, cell_one_hot=0, device="cpu")
+            ouvp, onuv = orc(oc, oe, on, 1.0, 1e-3, 0.01, 9, 0)
+            assert torch.equal(uvp, ouvp) and torch.equal(nuv, onuv)
+            gc = ref.Data_Pool.create_next_graph(gc, ge, mb, nuv, ct, Re, rmp)
+            oc = O.create_next_graph(oc, oe, omb, onuv, ct, Re, rmp)
+    # and it is a different network from mp_times=2 on the same weights
+    p2 = RL.default_params(train_traj_length=2, mp_times=2)
+    on2, oe2, oc2 = O.build_graphs(T, m["velocity"], m["pressure"])
+    on2, oe2, oc2, _, _ = O.valid_datapreprocessing(on2, oe2, oc2, 0)
+    with torch.no_grad():
+        _, nuv2 = O.FVGNOracle(model.state_dict(), p2)(oc2, oe2, on2, 1.0, 1e-3, 0.01, 9, 0)
+        on1, oe1, oc1 = O.build_graphs(T, m["velocity"], m["pressure"])
+        on1, oe1, oc1, _, _ = O.valid_datapreprocessing(on1, oe1, oc1, 0)
+        _, nuv1 = O.FVGNOracle(model.state_dict(), params)(oc1, oe1, on1, 1.0, 1e-3, 0.01, 9, 0)
+    assert not torch.allclose(nuv1, nuv2)
