@@ -465,12 +465,55 @@ def training_measure(args, rank, world, dev, meshes, dist):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(tms[0]), float(tms[1])
     g = len(meshes) * world
+    # ---------------- the reference's DataLoader regime (train.py:119-160): every batch is 16 random (mesh, time step) samples, so the
+    # batch TOPOLOGY changes every step and one captured graph cannot be replayed: collate + CSR tables + the eager step, per step
+    import random
+
+    kind, kw, _, _ = WORKLOADS[args.workload]
+    pool = list(lists)
+    for i in range(len(meshes)):
+        m = fv.synthetic.make(kind, seed=77000 + 1000 * rank + i, T=3, **kw)
+        t = lambda a, dt: torch.as_tensor(a).to(dt).to(dev)
+        tab = fv.ops.build_connectivity(t(m["cells"], torch.int32), t(m["mesh_pos"], torch.float32), t(m["node_type"], torch.int32), "B")
+        pool.append(fv.dataset.build_graphs(tab, m["velocity"], m["pressure"], training_pair=0, device=dev))
+    rng = random.Random(rank)
+    opt_e = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+
+    def fresh_step():
+        bl = [[_shallow(b) for b in pool[i]] for i in rng.sample(range(len(pool)), len(meshes))]
+        gn, ge, gc = fv.dataset.collate(bl)
+        gn, ge, gc, mi, mb = fv.dataset.train_datapreprocessing([gn, ge, gc])
+        opt_e.zero_grad(set_to_none=True)
+        out = model(graph=gc, graph_edge=ge, graph_node=gn, rho=RHO, mu=MU, dt=DT, edge_one_hot=9, cell_one_hot=0)
+        lo = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=out[3],
+                                 target_face_uvp_normalized=out[4], predicted_delta_u=out[1], target_delta_u=out[2])
+        lo[0].backward()
+        bucket.all_reduce_mean_()
+        opt_e.step()
+
+    fsteps = 2 * steps
+    for _ in range(10):  # the batch sizes vary from step to step: let the caching allocator see the range of block sizes first
+        fresh_step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(fsteps):
+        fresh_step()
+    t1.record()
+    barrier()
+    fresh = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(fresh, op=dist.ReduceOp.MAX)
+    fresh_ms = float(fresh[0])
     return {"metric": "training_graphs_per_sec", "value": g * steps / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms / steps, "steps": steps,
             "global_batch": g, "cells_per_rank": C, "faces_per_rank": F, "dtype": DTYPES[train_math] + (" (forward and backward GEMMs on tcgen05)" if train_math != "fp32" else " forward and backward"), "loss": p.loss, "optimizer": "AdamW lr 1e-3",
             "cell_updates_per_sec": C * world * steps / (ms * 1e-3),
             "e2e": {"value": g * steps / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / steps,
                     "h2d_bytes_per_step": int(node_host.numel() * 4), "d2h_bytes_per_step": 20,
                     "note": "pinned node fields H2D + loss D2H + host sync every step"},
+            "fresh_batches": {"value": g * fsteps / (fresh_ms * 1e-3), "unit": "graphs/s", "ms_per_step": fresh_ms / fsteps, "steps": fsteps, "cuda_graph": False,
+                              "note": f"every step a new random batch of {len(meshes)} meshes out of {2 * len(meshes)} (new topology: collate + CSR tables + "
+                                      "eager step inside the timed region; host-bound)"},
             "gpu_launches": int(launches), "final_loss": float(loss[0]),
             "parallelism": f"dp{world} over mesh graphs, one flat fp32 gradient all-reduce (8.84 MB) per step" if world > 1 else "single GPU",
             "step": "train_datapreprocessing + FVGN.forward(train) + compute_FVM_loss + backward + grad all-reduce + AdamW",

@@ -28,8 +28,11 @@ class FusedMLP(nn.Sequential):
         return super()._apply(fn, *a, **k)
 
     def _linears(self):
-        seq = self[0] if self._lay_norm else self
-        return seq[0], seq[2], seq[4]
+        lin = self.__dict__.get("_lin")
+        if lin is None:  # (indexing an nn.Sequential costs ~1.5 us per item; this runs for every launch)
+            seq = self[0] if self._lay_norm else self
+            lin = self.__dict__["_lin"] = (seq[0], seq[2], seq[4])
+        return lin
 
     def mlp_ref(self) -> ops.MlpRef:
         l1, l2, l3 = self._linears()
