@@ -96,11 +96,14 @@ class FVGN(nn.Module):
         graph.x, graph.edge_attr = x_in, e_in
         if capture is not None:
             capture["cell_in"], capture["edge_in"] = x_in, e_in
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        from ..autograd import NetFunction, network_mlps, network_params
+
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in network_params(self)):
             # differentiable path: forward and backward both run in libfvgn_b200 kernels (autograd.NetFunction)
             if self.math_mode not in ("fp32", "bf16x3", "bf16"):
                 raise NotImplementedError("training modes: 'fp32' (FFMA), 'bf16x3' (fp32-equivalent tensor cores), 'bf16' (bf16 tiles)")
-            from ..autograd import NetFunction, network_params
+            if self.math_mode != "fp32":  # the tensor-core forward reads packed weight tiles: one launch re-packs every MLP an optimizer step changed
+                ops.ensure_packed_many([m.mlp_ref() for m in network_mlps(self)], 2)
 
             decoded, delta_u, face_area = NetFunction.apply(self, topo, x_in, e_in, graph_edge.x.contiguous(), graph.cell_area.contiguous(),
                                                             graph.unv.contiguous(), rho, dt, *network_params(self))

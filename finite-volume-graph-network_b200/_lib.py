@@ -37,6 +37,7 @@ _SIGS = {
     "fvgn_mlp_pack_bf16": (_I, [C.POINTER(MlpT), _P, _S, _P]),
     "fvgn_mlp_packed_x3_bytes": (_S, [_I]),
     "fvgn_mlp_pack_bf16x3": (_I, [C.POINTER(MlpT), _P, _S, _P]),
+    "fvgn_mlp_pack_bf16x3_many": (_I, [C.POINTER(MlpT), _I, _P]),
     "fvgn_mlp_packed_x3_bwd_bytes": (_S, [_I]),
     "fvgn_mlp_pack_bf16x3_bwd": (_I, [C.POINTER(MlpT), _P, _S, _P]),
     "fvgn_ln_bwd": (_I, [_P, _I, _P, _P, _I, _P, _P, _P]),

@@ -43,6 +43,7 @@ int tc3_cell_block_sh(const fvgn_mlp_t*, float*, const void*, int, void*, cudaSt
 int tc3_edge_block_sh(const fvgn_mlp_t*, const void*, float*, const int32_t*, int, cudaStream_t);
 size_t tc3_packed_bytes(int k_in);
 int tc3_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
+int tc3_pack_many(const fvgn_mlp_t*, int, cudaStream_t);
 size_t tc3_packed_bwd_bytes(int k_in);
 int tc3_pack_bwd(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
 int tc3_ln_bwd(const float*, int, const float*, const float*, int, float*, float*, cudaStream_t);
@@ -102,6 +103,11 @@ extern "C" size_t fvgn_mlp_packed_x3_bytes(int k_in) { return tc3_packed_bytes(k
 extern "C" int fvgn_mlp_pack_bf16x3(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream) {
   if (int e = check_device()) return e;
   return tc3_pack(mlp, packed, packed_bytes, as_stream(stream));
+}
+
+extern "C" int fvgn_mlp_pack_bf16x3_many(const fvgn_mlp_t* mlps, int n_mlps, fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  return tc3_pack_many(mlps, n_mlps, as_stream(stream));
 }
 
 extern "C" int fvgn_mlp_rows_fwd(const fvgn_mlp_t* mlp, const float* in, int ld_in, int rows, float* out, int ld_out, int math_mode,

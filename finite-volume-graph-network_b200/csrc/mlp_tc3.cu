@@ -1393,13 +1393,20 @@ __global__ void __launch_bounds__(256) cell_mean_split_kernel(const float* __res
 // 196 KB at most, L2-resident).  W [n_valid, k_valid] fp32 row-major -> scale 2^s with max|W| 2^s in [2^13, 2^14)
 // (found here, on the device: graph-capturable, no host round trip) -> steps [kt][2 fp16 splits][128 rows][64 k], each sub-tile a
 // byte image of the swizzled layout; the epilogue factor 1 / (ASCALE 2^s) goes to the header behind the last step.
-struct PackFwdParams { const float* w[3]; int ldw[3], n_valid[3], k_valid[3], kt[3], step0[3]; unsigned char* out; int nsteps; };
-__global__ void __launch_bounds__(1024) pack_fwd_h2_kernel(const PackFwdParams p) {
+// blockIdx.z = MLP: all the MLPs whose weights an optimizer step changed are re-packed by ONE launch (33 per training step).
+struct PackFwdJob { const float* w[3]; unsigned char* out; int k_in, n_out; };
+constexpr int PACK_MAX_JOBS = 48;
+struct PackFwdBatch { PackFwdJob job[PACK_MAX_JOBS]; };
+__global__ void __launch_bounds__(1024) pack_fwd_h2_kernel(const __grid_constant__ PackFwdBatch batch) {
   __shared__ float s_max[32];
   __shared__ float s_scale;
+  const PackFwdJob& jb = batch.job[blockIdx.z];
   const int m = blockIdx.x, tid = threadIdx.x;
-  const float* W = p.w[m];
-  const int ldw = p.ldw[m], nv = p.n_valid[m], kv = p.k_valid[m], kt = p.kt[m];
+  const int kt1 = (jb.k_in + KTILE - 1) / KTILE;
+  const float* W = jb.w[m];
+  const int ldw = m == 0 ? jb.k_in : 128, nv = m == 2 ? jb.n_out : 128, kv = m == 0 ? jb.k_in : 128, kt = m == 0 ? kt1 : 2;
+  if ((int)blockIdx.y >= (kt > 2 ? kt : 2)) return;  // the grid's y extent is that of the widest layer 1 in the batch
+  struct { unsigned char* out; int nsteps; int step0[3]; } p = {jb.out, kt1 + 4, {0, kt1, kt1 + 2}};
   float mx = 0.f;
   for (int r = tid >> 5; r < nv; r += 32)  // a warp per row: coalesced, no integer division
     for (int c = tid & 31; c < kv; c += 32) mx = fmaxf(mx, fabsf(W[(size_t)r * ldw + c]));
@@ -1422,7 +1429,8 @@ __global__ void __launch_bounds__(1024) pack_fwd_h2_kernel(const PackFwdParams p
   __syncthreads();
   const float sc = s_scale;
   unsigned char* out = p.out + (size_t)p.step0[m] * FW_SLOT;
-  for (int idx = blockIdx.y * 1024 + tid; idx < kt * 1024; idx += gridDim.y * 1024) {  // (tile, n, 16-byte chunk)
+  const int ny = kt > 2 ? kt : 2;  // CTAs of this matrix
+  for (int idx = blockIdx.y * 1024 + tid; idx < kt * 1024; idx += ny * 1024) {  // (tile, n, 16-byte chunk)
     const int c = idx & 7, n = (idx >> 3) & 127, t = idx >> 10;
     uint4 q0, q1;
     uint32_t* a0 = reinterpret_cast<uint32_t*>(&q0);
@@ -1453,14 +1461,31 @@ int tc3_pack(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t st) {
   FVGN_CHECK_ARG(bytes >= tc3_packed_bytes(m->k_in), "packed buffer too small");
   FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed buffer must be 16B aligned");
   const int kt1 = kt_of(m->k_in);
-  PackFwdParams p;
-  p.w[0] = m->w1; p.ldw[0] = m->k_in; p.n_valid[0] = 128; p.k_valid[0] = m->k_in; p.kt[0] = kt1; p.step0[0] = 0;
-  p.w[1] = m->w2; p.ldw[1] = 128; p.n_valid[1] = 128; p.k_valid[1] = 128; p.kt[1] = 2; p.step0[1] = kt1;
-  p.w[2] = m->w3; p.ldw[2] = 128; p.n_valid[2] = m->n_out; p.k_valid[2] = 128; p.kt[2] = 2; p.step0[2] = kt1 + 2;
-  p.out = reinterpret_cast<unsigned char*>(packed);
-  p.nsteps = kt1 + 4;
-  pack_fwd_h2_kernel<<<dim3(3, kt1 > 2 ? kt1 : 2), 1024, 0, st>>>(p);
+  PackFwdBatch b;
+  b.job[0] = {{m->w1, m->w2, m->w3}, reinterpret_cast<unsigned char*>(packed), m->k_in, m->n_out};
+  pack_fwd_h2_kernel<<<dim3(3, kt1 > 2 ? kt1 : 2, 1), 1024, 0, st>>>(b);
   FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+// every MLP of the array into its own m->packed_x3 (each at least tc3_packed_bytes(k_in) large), PACK_MAX_JOBS per launch
+int tc3_pack_many(const fvgn_mlp_t* mlps, int n, cudaStream_t st) {
+  using namespace x3;
+  FVGN_CHECK_ARG(n >= 0 && (n == 0 || mlps), "NULL pointer");
+  for (int i0 = 0; i0 < n; i0 += PACK_MAX_JOBS) {
+    const int nb = n - i0 < PACK_MAX_JOBS ? n - i0 : PACK_MAX_JOBS;
+    PackFwdBatch b;
+    int ktmax = 2;
+    for (int i = 0; i < nb; ++i) {
+      const fvgn_mlp_t* m = mlps + i0 + i;
+      FVGN_CHECK_ARG(m->k_in >= 1 && m->k_in <= 384 && m->n_out >= 1 && m->n_out <= 128, "bad mlp dims");
+      FVGN_CHECK_ARG(m->packed_x3 && (reinterpret_cast<uintptr_t>(m->packed_x3) & 15) == 0, "packed_x3 must be set and 16B aligned");
+      b.job[i] = {{m->w1, m->w2, m->w3}, reinterpret_cast<unsigned char*>(const_cast<void*>(m->packed_x3)), m->k_in, m->n_out};
+      if (kt_of(m->k_in) > ktmax) ktmax = kt_of(m->k_in);
+    }
+    pack_fwd_h2_kernel<<<dim3(3, ktmax, nb), 1024, 0, st>>>(b);
+    FVGN_LAUNCH_CHECK();
+  }
   return 0;
 }
 

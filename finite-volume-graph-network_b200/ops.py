@@ -192,6 +192,31 @@ class MlpRef:
         return self
 
 
+def ensure_packed_many(mlps, math_mode=2):
+    """fvgn_mlp_pack_bf16x3_many: re-packs, in one launch, every MlpRef of `mlps` whose fp32 weights changed since its last pack (after an
+    optimizer step: all of them).  The per-call MlpRef.ensure_packed(2) that follows finds them current."""
+    if math_mode != 2:
+        return
+    key = None
+    stale = []
+    for m in mlps:
+        ver = _weights_key(m.tensors)
+        if m.packed3 is None or m.packed3_versions != ver:
+            stale.append((m, ver))
+    if not stale:
+        return
+    L = _lib.lib()
+    for m, _ in stale:
+        if m.packed3 is None:
+            m.packed3 = torch.empty(L.fvgn_mlp_packed_x3_bytes(m.k_in), dtype=torch.uint8, device=m.tensors[0].device)
+            m.struct.packed_x3 = m.packed3.data_ptr()
+    arr = (MlpT * len(stale))(*[m.struct for m, _ in stale])
+    _count((len(stale) + 47) // 48)
+    check(L.fvgn_mlp_pack_bf16x3_many(arr, len(stale), _stream()), "mlp_pack_bf16x3_many")
+    for m, ver in stale:
+        m.packed3_versions = ver
+
+
 class _zsave:
     """sets fvgn_mlp_t.z_save = z[rows, 384] for the duration of one call (forward in bf16x3 mode writes the three layers'
     pre-activations there; the backward reads them instead of recomputing the forward)"""

@@ -76,6 +76,9 @@ FVGN_API int fvgn_mlp_pack_bf16(const fvgn_mlp_t* mlp, void* packed, size_t pack
 /* FVGN_MATH_BF16X3_TC: every weight split exactly into three bf16 terms (w = w0 + w1 + w2), three swizzled tiles per K-tile. */
 FVGN_API size_t fvgn_mlp_packed_x3_bytes(int k_in);
 FVGN_API int fvgn_mlp_pack_bf16x3(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream);
+/* The same for an array of MLPs in ONE launch (a training step re-packs all 33 after the optimizer step): mlps[i].packed_x3 is the
+ * destination of MLP i (>= fvgn_mlp_packed_x3_bytes(mlps[i].k_in) bytes, 16-byte aligned). */
+FVGN_API int fvgn_mlp_pack_bf16x3_many(const fvgn_mlp_t* mlps, int n_mlps, fvgn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * a1. connectivity + geometry tables  — replaces extract_mesh_state + triangles_to_faces + reorder_face
