@@ -109,6 +109,12 @@ __device__ __forceinline__ void split3_pair(float a, float b, uint32_t& p0, uint
   p2 = cvt_bf16x2(sa, sb);
 }
 
+// the two leading bf16 terms only (backward kernels run with the three leading split products: the third term is never read)
+__device__ __forceinline__ void split3_pair_lead2(float a, float b, uint32_t& p0, uint32_t& p1) {
+  p0 = cvt_bf16x2(a, b);
+  p1 = cvt_bf16x2(a - __uint_as_float(p0 << 16), b - __uint_as_float(p0 & 0xffff0000u));
+}
+
 // 2-way fp16 split of two fp32 values (forward activation operand): a = h0 + h1 up to 2^-22 relative
 __device__ __forceinline__ void split2_pair(float a, float b, uint32_t& p0, uint32_t& p1) {
   const __half2 h0 = __floats2half2_rn(a, b);
@@ -129,9 +135,16 @@ __device__ __forceinline__ float silu_x3(float v) {
 }
 
 // 4 consecutive fp32 (columns 4*hl .. 4*hl+3 of a 64-wide K-tile) -> row r of the three swizzled split sub-tiles of one ring slot
-__device__ __forceinline__ void st_slot_f4(unsigned char* slot, int r, int hl, float4 v) {
+__device__ __forceinline__ void st_slot_f4(unsigned char* slot, int r, int hl, float4 v, bool third) {
   const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)hl >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)hl & 1u) * 8u;
   uint2 q0, q1, q2;
+  if (!third) {
+    split3_pair_lead2(v.x, v.y, q0.x, q1.x);
+    split3_pair_lead2(v.z, v.w, q0.y, q1.y);
+    *reinterpret_cast<uint2*>(slot + off) = q0;
+    *reinterpret_cast<uint2*>(slot + TILE_BYTES + off) = q1;
+    return;
+  }
   split3_pair(v.x, v.y, q0.x, q1.x, q2.x);
   split3_pair(v.z, v.w, q0.y, q1.y, q2.y);
   *reinterpret_cast<uint2*>(slot + off) = q0;
@@ -782,6 +795,7 @@ __device__ __forceinline__ float dsilu_x3(float z) {
   return s * (1.0f + z * (1.0f - s));
 }
 
+template <bool THIRD>  // THIRD: the operands carry all three split terms (six products); false: the two leading terms (<= 3 products)
 __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const SmemLayout L = smem_layout();
@@ -793,6 +807,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int nseg3 = p.want_dA ? p.nseg : 0;
+  constexpr bool third = THIRD;  // products 4-6 read the third split term of an operand: with <= 3 products it is neither made nor moved
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) { printf("fvgn dgrad_tc3: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
@@ -837,7 +852,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
       if (s >= ARING) mbar_wait(BAR(B_AEMPTY + slot), (((uint32_t)s / ARING) - 1) & 1, 1);
       unsigned char* dst = sA + slot * SLOT_BYTES;
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) st_slot_f4(dst, hw + NHW * i, hl, v[i]);
+      for (int i = 0; i < RPT; ++i) st_slot_f4(dst, hw + NHW * i, hl, v[i], third);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_AFULL + slot));
@@ -860,8 +875,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
         for (int step = 0; step < nsteps; ++step, ++wl) {
           const uint32_t slot = wl % WRING;
           if (wl >= WRING) mbar_wait(BAR(B_WEMPTY + slot), ((wl / WRING) - 1) & 1, 2);
-          mbar_arrive_expect_tx(BAR(B_WFULL + slot), SLOT_BYTES);
-          bulk_g2s(smem_u32(sW + slot * SLOT_BYTES), p.packed + (size_t)step * SLOT_BYTES, SLOT_BYTES, BAR(B_WFULL + slot));
+          const uint32_t nbytes = third ? SLOT_BYTES : 2 * TILE_BYTES;  // (the sub-tiles of a step are contiguous, most significant first)
+          mbar_arrive_expect_tx(BAR(B_WFULL + slot), nbytes);
+          bulk_g2s(smem_u32(sW + slot * SLOT_BYTES), p.packed + (size_t)step * SLOT_BYTES, nbytes, BAR(B_WFULL + slot));
         }
     }
     __syncwarp();
@@ -888,7 +904,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-              for (int q = 0; q < 6; ++q)
+              for (int q = 0; q < (THIRD ? 6 : 3); ++q)
                 if (q < p.nprod)
                   umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
                             IDESC_BF16_M128_N128, (t | kk | q) != 0);
@@ -898,7 +914,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-              for (int q = 0; q < 6; ++q)
+              for (int q = 0; q < (THIRD ? 6 : 3); ++q)
                 if (q < p.nprod)
                   umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
                                umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32), IDESC_BF16_M128_N128, (t | kk | q) != 0);
@@ -981,12 +997,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
             const float4 z = ldg4(zrow + 16 * sc + 4 * j4);
             v[4 * j4] = __uint_as_float(r[4 * j4]) * dsilu_x3(z.x); v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) * dsilu_x3(z.y);
             v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) * dsilu_x3(z.z); v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) * dsilu_x3(z.w);
-            split3_pair(v[4 * j4], v[4 * j4 + 1], p0[2 * j4], p1[2 * j4], p2[2 * j4]);
-            split3_pair(v[4 * j4 + 2], v[4 * j4 + 3], p0[2 * j4 + 1], p1[2 * j4 + 1], p2[2 * j4 + 1]);
+            if (third) {
+              split3_pair(v[4 * j4], v[4 * j4 + 1], p0[2 * j4], p1[2 * j4], p2[2 * j4]);
+              split3_pair(v[4 * j4 + 2], v[4 * j4 + 3], p0[2 * j4 + 1], p1[2 * j4 + 1], p2[2 * j4 + 1]);
+            } else {
+              split3_pair_lead2(v[4 * j4], v[4 * j4 + 1], p0[2 * j4], p1[2 * j4]);
+              split3_pair_lead2(v[4 * j4 + 2], v[4 * j4 + 3], p0[2 * j4 + 1], p1[2 * j4 + 1]);
+            }
           }
           tmem_st8(t_h + 8 * sc, p0);
           tmem_st8(t_h + 64 + 8 * sc, p1);
-          tmem_st8(t_h + 128 + 8 * sc, p2);
+          if (third) tmem_st8(t_h + 128 + 8 * sc, p2);
           store_rows16(v, p.da, 256, 128 * b + 16 * sc, row0 + 32 * q);
         }
         tmem_wait_st();
@@ -1121,9 +1142,16 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
 constexpr uint32_t IDESC_BF16_MN_MN = IDESC_BF16_M128_N128 | (1u << 15) | (1u << 16);
 
 // 4 consecutive fp32 (features 4*hl.. of one 64-feature half) -> row r of the three split tiles of a matrix block
-__device__ __forceinline__ void st_wg_f4(unsigned char* mat, int half, int r, int hl, float4 v) {
+__device__ __forceinline__ void st_wg_f4(unsigned char* mat, int half, int r, int hl, float4 v, bool third) {
   const uint32_t off = (uint32_t)half * WG_HALF_BYTES + (uint32_t)r * 128u + ((((uint32_t)hl >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)hl & 1u) * 8u;
   uint2 q0, q1, q2;
+  if (!third) {
+    split3_pair_lead2(v.x, v.y, q0.x, q1.x);
+    split3_pair_lead2(v.z, v.w, q0.y, q1.y);
+    *reinterpret_cast<uint2*>(mat + off) = q0;
+    *reinterpret_cast<uint2*>(mat + 2 * WG_HALF_BYTES + off) = q1;
+    return;
+  }
   split3_pair(v.x, v.y, q0.x, q1.x, q2.x);
   split3_pair(v.z, v.w, q0.y, q1.y, q2.y);
   *reinterpret_cast<uint2*>(mat + off) = q0;
@@ -1131,6 +1159,7 @@ __device__ __forceinline__ void st_wg_f4(unsigned char* mat, int half, int r, in
   *reinterpret_cast<uint2*>(mat + 4 * WG_HALF_BYTES + off) = q2;
 }
 
+template <bool THIRD>
 __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sBar = smem + WG_STAGES * WG_STAGE_BYTES;
@@ -1141,6 +1170,7 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
   const int job = (int)blockIdx.x % p.njobs, range = (int)blockIdx.x / p.njobs;
   const int c0 = range * p.chunks_per_range;
   const int nch = max(0, min(p.chunks_per_range, p.nchunks - c0));
+  constexpr bool third = THIRD;  // the third split term is only read by products 4-6
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) { printf("fvgn wgrad_tc3: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
@@ -1226,8 +1256,8 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
           if (job < 2) {  // Q = silu(z) of the rows that exist (rows past the end were loaded as zeros: silu(0) = 0)
             b = make_float4(silu_x3(b.x), silu_x3(b.y), silu_x3(b.z), silu_x3(b.w));
           }
-          st_wg_f4(P, hh, r, hl, pv[i][hh]);
-          st_wg_f4(Q, hh, r, hl, b);
+          st_wg_f4(P, hh, r, hl, pv[i][hh], third);
+          st_wg_f4(Q, hh, r, hl, b, third);
         }
       if (half == 1) {
         fence_proxy_async();
@@ -1256,7 +1286,7 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
 #pragma unroll
         for (int kk = 0; kk < WG_CHUNK / 16; ++kk)
 #pragma unroll
-          for (int q = 0; q < 6; ++q)
+          for (int q = 0; q < (THIRD ? 6 : 3); ++q)
             if (q < p.nprod)
               umma_bf16(tmem_base, umma_desc_mn(pb + prod_a(q) * 2 * WG_HALF_BYTES + kk * 2048),
                         umma_desc_mn(qb + prod_w(q) * 2 * WG_HALF_BYTES + kk * 2048), IDESC_BF16_MN_MN, (c | kk | q) != 0);
@@ -1659,15 +1689,17 @@ int tc3_dgrad(const fvgn_mlp_t* m, const float* dz, int ld_dz, int rows, float* 
   p.rows = rows; p.ntiles = cdiv(rows, TM); p.nseg = (m->k_in + 127) / 128; p.k_in = m->k_in; p.n_out = m->n_out; p.want_dA = dA ? 1 : 0;
   p.dz = dz; p.ld_dz = ld_dz; p.zsave = m->z_save; p.da = da; p.dA = dA; p.ld_dA = ld_dA; p.dA_base = dA_base; p.ld_base = ld_base;
   p.packed = reinterpret_cast<const unsigned char*>(m->packed_x3_bwd);
-  p.nprod = m->n_products == 1 ? 1 : 6;
+  p.nprod = m->n_products == 1 ? 1 : (m->n_products == 3 ? 3 : 6);
   const SmemLayout L = smem_layout();
   static bool configured = false;
   if (!configured) {
-    FVGN_CUDA(cudaFuncSetAttribute(dgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    FVGN_CUDA(cudaFuncSetAttribute(dgrad_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    FVGN_CUDA(cudaFuncSetAttribute(dgrad_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     configured = true;
   }
   const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
-  dgrad_tc3_kernel<<<grid, NTHREADS, L.total, st>>>(p);
+  if (p.nprod > 3) dgrad_tc3_kernel<true><<<grid, NTHREADS, L.total, st>>>(p);
+  else dgrad_tc3_kernel<false><<<grid, NTHREADS, L.total, st>>>(p);
   FVGN_LAUNCH_CHECK();
   return 0;
 }
@@ -1700,14 +1732,16 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
   p.dz = m->ln_w ? dz : d_out; p.ld_dz = m->ln_w ? 128 : ld_dout;
   p.da = m->da_in; p.zsave = m->z_save; p.in = in; p.ld_in = ld_in; p.src0 = src0; p.src1 = src1; p.idx = idx;
   p.part = workspace;
-  p.nprod = m->n_products == 1 ? 1 : 6;
+  p.nprod = m->n_products == 1 ? 1 : (m->n_products == 3 ? 3 : 6);
   const int smem_bytes = WG_STAGES * WG_STAGE_BYTES + 256;
   static bool configured = false;
   if (!configured) {
-    FVGN_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    FVGN_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    FVGN_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  wgrad_tc3_kernel<<<p.njobs * p.nranges, WG_NTHREADS, smem_bytes, st>>>(p);
+  if (p.nprod > 3) wgrad_tc3_kernel<true><<<p.njobs * p.nranges, WG_NTHREADS, smem_bytes, st>>>(p);
+  else wgrad_tc3_kernel<false><<<p.njobs * p.nranges, WG_NTHREADS, smem_bytes, st>>>(p);
   FVGN_LAUNCH_CHECK();
   wgrad_reduce_kernel<<<cdiv(p.njobs * 16384, 256), 256, 0, st>>>(workspace, p.njobs, p.nranges, m->k_in, grads);
   FVGN_LAUNCH_CHECK();

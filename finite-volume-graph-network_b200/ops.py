@@ -3,6 +3,7 @@ all arithmetic happens in libfvgn_b200.so on the current CUDA stream.  CPU tenso
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -215,6 +216,25 @@ def ensure_packed_many(mlps, math_mode=2):
     check(L.fvgn_mlp_pack_bf16x3_many(arr, len(stale), _stream()), "mlp_pack_bf16x3_many")
     for m, ver in stale:
         m.packed3_versions = ver
+
+
+# split products of the tensor-core BACKWARD kernels (dgrad / wgrad) in the fp32-equivalent mode: 6 = exact 3-way bf16 splits of both
+# operands, 3 = the three leading products (relative error of a product <= 3 * 2^-17, i.e. gradients to ~1e-5; half the MMAs)
+BWD_PRODUCTS = int(os.environ.get("FVGN_BWD_PRODUCTS", "3"))
+
+
+class _bwd_products:
+    def __init__(self, mlp):
+        self.mlp = mlp
+
+    def __enter__(self):
+        self.saved = self.mlp.struct.n_products
+        if self.saved != 1:
+            self.mlp.struct.n_products = BWD_PRODUCTS
+
+    def __exit__(self, *a):
+        self.mlp.struct.n_products = self.saved
+        return False
 
 
 class _zsave:
@@ -612,7 +632,7 @@ def mlp_wgrad_x3(mlp: MlpRef, mode, d_out, dz, gxhat, z_saved, da, x=None, src0=
     else:
         _cf(src0, "src0"), _cf(src1, "src1"), _ci(idx, "idx")
     _count(4)
-    with _zsave(mlp, z_saved, rows, da):
+    with _zsave(mlp, z_saved, rows, da), _bwd_products(mlp):
         check(L.fvgn_mlp_wgrad_x3(C.byref(mlp.struct), mode, _p(x), _ld(x) if x is not None else 0, _p(src0), _p(src1), _p(idx), rows, _p(d_out),
                                   _ld(d_out), _p(dz), _p(gxhat), _p(grads), _p(ws), _stream()), "mlp_wgrad_x3")
     return _mlp_grad_views(mlp, grads)
@@ -626,7 +646,7 @@ def mlp_dgrad_x3(mlp: MlpRef, dz, z_saved, want_dA=True, dA_base=None):
     da = torch.empty((rows, 256), dtype=torch.float32, device=dz.device)
     dA = torch.empty((rows, mlp.k_in), dtype=torch.float32, device=dz.device) if want_dA else None
     _count(1)
-    with _zsave(mlp, z_saved, rows):
+    with _zsave(mlp, z_saved, rows), _bwd_products(mlp):
         check(_lib.lib().fvgn_mlp_dgrad_x3(C.byref(mlp.struct), _p(dz), _ld(dz), rows, _p(da), _p(dA), mlp.k_in if want_dA else 0, _p(dA_base),
                                            _ld(dA_base) if dA_base is not None else 0, _stream()), "mlp_dgrad_x3")
     return da, dA

@@ -67,7 +67,9 @@ typedef struct {
   const float* da_in;    /* optional [rows, 256] = (da2 | da1) from fvgn_mlp_dgrad_x3.  Backward (fvgn_*_bwd): when non-NULL the FFMA
                             kernel skips its data-gradient GEMMs (and writes no d_in): only weight / bias / LayerNorm gradients remain. */
   int n_products;        /* FVGN_MATH_BF16X3_TC kernels (forward, dgrad, wgrad): 0 or 6 = all six split products (fp32-equivalent);
-                            1 = the leading product only, i.e. plain bf16 tiles with fp32 accumulation ("bf16" training, BASELINE configs[2]) */
+                            1 = the leading product only, i.e. plain bf16 tiles with fp32 accumulation ("bf16" training, BASELINE configs[2]);
+                            3 (dgrad / wgrad only) = the three leading products a0 w0 + a0 w1 + a1 w0 of the 3-way bf16 splits: the dropped
+                            terms are <= 3 * 2^-17 of a product, well inside the 1e-4 gradient tolerance, for half the MMAs */
 } fvgn_mlp_t;
 
 /* Tensor-core modes read the weights as pre-swizzled bf16 tiles.  Re-pack whenever the fp32 weights change. */
