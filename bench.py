@@ -281,8 +281,8 @@ def roofline_of(m, math, workload):
 
 
 DTYPES = {"fp32": "f32 (FFMA)", "bf16": "bf16 tiles, f32 accumulate/residual",
-          "bf16x3": "f32-equivalent: two-term fp16 split of both operands on tcgen05 (3 MMAs/product; training backward: 3-way bf16 split, "
-                    "6 MMAs/product), f32 accumulate + f32 epilogue; held to the f32 parity bound (rel 1e-5/step)"}
+          "bf16x3": "f32-equivalent: two-term fp16 split of both operands on tcgen05 (3 MMAs/product; training backward: the 3 leading products "
+                    "of 3-way bf16 splits, gradients held to 1e-4), f32 accumulate + f32 epilogue; held to the f32 parity bound (rel 1e-5/step)"}
 
 
 def native(args, rank, world, local_rank):
@@ -492,7 +492,7 @@ def training_measure(args, rank, world, dev, meshes, dist):
         opt_e.step()
 
     fsteps = 2 * steps
-    for _ in range(10):  # the batch sizes vary from step to step: let the caching allocator see the range of block sizes first
+    for _ in range(20):  # the batch sizes vary from step to step: let the caching allocator see the range of block sizes first
         fresh_step()
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

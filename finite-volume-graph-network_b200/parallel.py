@@ -34,25 +34,24 @@ class GradBucket:
         dev = self.params[0].device
         if self.flat is None or self.flat.device != dev:
             self.flat = torch.empty(self.numel, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
-            n = p.numel()
+            self.views, off = [], 0
+            for p in self.params:
+                self.views.append(self.flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        # gather / scatter with one multi-tensor copy each (two launches per step instead of one per parameter)
+        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
+        for v, p in zip(self.views, self.params):
             if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
+                v.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         self.flat.div_(dist.get_world_size(group))
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            g = self.flat[off:off + n].view_as(p)
+        if have:
+            torch._foreach_copy_([g for _, g in have], [v for v, _ in have])
+        for v, p in zip(self.views, self.params):
             if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-            off += n
+                p.grad = v.clone()
 
 
 def snapshot_normalizers(model):
