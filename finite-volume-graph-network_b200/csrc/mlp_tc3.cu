@@ -983,18 +983,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
       // ---- batches S1, S2: d(hidden) * silu'(z) -> da (HBM) + split planes (TMEM)
 #pragma unroll 1
       for (int b = 0; b < 2; ++b) {
-        wait_acc(b);
         const float* zrow = p.zsave + (size_t)grow_c * 384 + (b == 0 ? 128 : 0);  // S1 pairs with z2, S2 with z1
+        // the saved pre-activations of a sub-chunk are fetched one sub-chunk ahead (the first one before the accumulator wait): their
+        // global-load latency was the epilogue's largest stall (37 % of its samples, profiles/r01c_ncu_backward_summary.txt)
+        float4 zn[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) zn[j4] = ldg4(zrow + 16 * (4 * h) + 4 * j4);
+        wait_acc(b);
 #pragma unroll 1
         for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
           tmem_ld16_issue(t_lane + 128u * (uint32_t)b + 16 * sc, r);
+          float4 zc[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) zc[j4] = zn[j4];
+          if (sc + 1 < 4 * h + 4) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) zn[j4] = ldg4(zrow + 16 * (sc + 1) + 4 * j4);
+          }
           tmem_ld16_wait(r);
           if (sc == 4 * h + 3) release_acc(b);
           float v[16];
           uint32_t p0[8], p1[8], p2[8];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 z = ldg4(zrow + 16 * sc + 4 * j4);
+            const float4 z = zc[j4];
             v[4 * j4] = __uint_as_float(r[4 * j4]) * dsilu_x3(z.x); v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) * dsilu_x3(z.y);
             v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) * dsilu_x3(z.z); v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) * dsilu_x3(z.w);
             if (third) {
@@ -1265,6 +1277,9 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
         if (lane == 0) mbar_arrive(BAR(stg));
       }
     };
+    // (a third register buffer — rows requested two steps ahead — was measured and rejected: 17 warps cap the kernel at 96 registers, the
+    // rotation spills and the launch gets 4 % slower; the producers wait for these loads a third of their samples,
+    // profiles/r01c_ncu_backward_summary.txt: the next step is a cp.async staging ring in the shared memory the two-term slots free)
     float4 pa[1][2], qa[1][2], pb[1][2], qb[1][2];
 #pragma unroll 1
     for (int s = -1; s < S; s += 2) {
