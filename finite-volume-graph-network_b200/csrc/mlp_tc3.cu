@@ -1135,6 +1135,18 @@ constexpr int WG_STAGE_BYTES = 2 * WG_MAT_BYTES;  // P and Q
 constexpr int WG_STAGES = 2;
 constexpr int WG_NPW = 16;                       // producer warps (warps 0-3 also run the epilogue once the chunks are done)
 constexpr int WG_NTHREADS = (WG_NPW + 1) * 32;   // + 1 MMA warp
+// Two-term variant (THIRD = false): an operand block holds two split tiles per feature half (32 KB), a stage 64 KB; the 64 KB of shared
+// memory the third terms no longer take + 32 KB hold a ring of three RAW half-chunks ([P | Q] x 32 rows x 128 fp32 = 32 KB each) that the
+// producers fill by cp.async two steps ahead: the row loads need no registers while in flight, ~64 KB per SM instead of ~32-48 KB.
+constexpr int WG_RAW_BYTES = WG_NPW * 32 * 64;   // one half-chunk: 512 producer threads x 4 x 16 bytes
+constexpr int WG_RAW_DEPTH = 3;
+template <bool THIRD> struct WgLayout {
+  static constexpr int MAT = (THIRD ? 6 : 4) * WG_HALF_BYTES;
+  static constexpr int STAGE = 2 * MAT;
+  static constexpr int RAW_OFF = WG_STAGES * STAGE;
+  static constexpr int BAR_OFF = RAW_OFF + (THIRD ? 0 : WG_RAW_DEPTH * WG_RAW_BYTES);
+  static constexpr int TOTAL = BAR_OFF + 256;
+};
 
 struct WgParams {
   int mode, rows, k_in, n_out, njobs, nranges, chunks_per_range, nchunks, nprod;
@@ -1174,7 +1186,8 @@ __device__ __forceinline__ void st_wg_f4(unsigned char* mat, int half, int r, in
 template <bool THIRD>
 __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* sBar = smem + WG_STAGES * WG_STAGE_BYTES;
+  using WL = WgLayout<THIRD>;
+  unsigned char* sBar = smem + WL::BAR_OFF;
   const uint32_t bar0 = smem_u32(sBar);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };  // FULL[2], EMPTY[2], DONE
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sBar + 64);
@@ -1257,8 +1270,8 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
       const int c = s >> 1, half = s & 1;
       const uint32_t stg = (uint32_t)c % WG_STAGES;
       if (half == 0 && c >= WG_STAGES) mbar_wait(BAR(2 + stg), (((uint32_t)c / WG_STAGES) - 1) & 1, 1);
-      unsigned char* P = smem + stg * WG_STAGE_BYTES;
-      unsigned char* Q = P + WG_MAT_BYTES;
+      unsigned char* P = smem + stg * WL::STAGE;
+      unsigned char* Q = P + WL::MAT;
 #pragma unroll
       for (int i = 0; i < 1; ++i)
 #pragma unroll
@@ -1280,13 +1293,69 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
     // (a third register buffer — rows requested two steps ahead — was measured and rejected: 17 warps cap the kernel at 96 registers, the
     // rotation spills and the launch gets 4 % slower; the producers wait for these loads a third of their samples,
     // profiles/r01c_ncu_backward_summary.txt: the next step is a cp.async staging ring in the shared memory the two-term slots free)
-    float4 pa[1][2], qa[1][2], pb[1][2], qb[1][2];
+    // jobs whose P and Q rows are plain 16-byte-aligned global rows go through the cp.async ring (all of an EdgeBlock MLP's jobs, three of
+    // a CellBlock MLP's four); the 3-gather mean segment, the narrow encoder / decoder operands and the six-product variant keep the
+    // register double buffer
+    const bool p_plain = job > 0 || (p.n_out == 128 && (p.ld_dz & 3) == 0);
+    const bool q_plain = job < 2 || p.mode == TC_EDGE || (p.mode == TC_CELL && (seg == 0 || p.idx == nullptr)) ||
+                         (p.mode == TC_ROWS && (p.k_in & 127) == 0 && (p.ld_in & 3) == 0);
+    if (!THIRD && p_plain && q_plain) {
+      unsigned char* raw = smem + WL::RAW_OFF;
+      const uint32_t raw_me = smem_u32(raw) + (uint32_t)ptid * 16u;  // [buffer][k = P0 P1 Q0 Q1][thread]: conflict-free 16-byte slots
+      const bool gather = p.mode == TC_EDGE && job >= 2 && seg < 2;
+      auto row_of = [&](int s) { return (c0 + (s >> 1)) * WG_CHUNK + 32 * (s & 1) + hw; };
+      int nidx = 0;  // EdgeBlock x' gather: the row index of step s + 1 is fetched while step s is issued
+      if (gather && S > 0) nidx = __ldg(p.idx + (size_t)seg * p.rows + min(row_of(0), p.rows - 1));
+      auto issue = [&](int s) {
+        const int g = row_of(s);
+        const uint32_t nbytes = g < p.rows ? 16u : 0u;  // rows past the end: zero fill
+        const int gc = min(g, p.rows - 1);
+        const float* ps = job == 0 ? p.dz + (size_t)gc * p.ld_dz : p.da + (size_t)gc * 256 + (job == 1 ? 0 : 128);
+        const float* qs;
+        bool q_half_only = false;
+        if (job < 2) qs = p.zsave + (size_t)gc * 384 + (job == 0 ? 128 : 0);
+        else if (p.mode == TC_EDGE) qs = seg < 2 ? p.src0 + (size_t)nidx * 128 : p.src1 + (size_t)gc * 128;
+        else if (p.mode == TC_CELL) { qs = seg == 0 ? p.src0 + (size_t)gc * 128 : p.src1 + (size_t)gc * 64; q_half_only = seg != 0; }
+        else qs = p.in + (size_t)gc * p.ld_in + 128 * seg;
+        if (gather && s + 1 < S) nidx = __ldg(p.idx + (size_t)seg * p.rows + min(row_of(s + 1), p.rows - 1));
+        const uint32_t dst = raw_me + (uint32_t)(s % WG_RAW_DEPTH) * WG_RAW_BYTES;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)hh * 8192u), "l"(ps + 64 * hh + 4 * hl), "r"(nbytes)
+                       : "memory");
+          // (mp_times = 1 CellBlock: the per-cell aggregate is 64 wide, the upper half of that segment is zero)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16384u + (uint32_t)hh * 8192u),
+                       "l"(qs + (q_half_only ? 0 : 64 * hh) + 4 * hl), "r"((q_half_only && hh == 1) ? 0u : nbytes)
+                       : "memory");
+        }
+      };
+      if (0 < S) issue(0);
+      cp_async_commit();
+      if (1 < S) issue(1);
+      cp_async_commit();
 #pragma unroll 1
-    for (int s = -1; s < S; s += 2) {
-      if (s + 1 < S) load(s + 1, pa, qa);
-      if (s >= 0) store(s, pb, qb);
-      if (s + 2 < S) load(s + 2, pb, qb);
-      if (s + 1 < S) store(s + 1, pa, qa);
+      for (int s = 0; s < S; ++s) {
+        if (s + 2 < S) issue(s + 2);
+        cp_async_commit();    // (an empty group when nothing is left keeps the group count uniform)
+        cp_async_wait<2>();   // step s has landed; the slots are private to this thread: no barrier
+        const unsigned char* src = raw + (size_t)(s % WG_RAW_DEPTH) * WG_RAW_BYTES + (size_t)ptid * 16;
+        float4 pv[1][2], qv[1][2];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          pv[0][hh] = *reinterpret_cast<const float4*>(src + hh * 8192);
+          qv[0][hh] = *reinterpret_cast<const float4*>(src + 16384 + hh * 8192);
+        }
+        store(s, pv, qv);
+      }
+    } else {
+      float4 pa[1][2], qa[1][2], pb[1][2], qb[1][2];
+#pragma unroll 1
+      for (int s = -1; s < S; s += 2) {
+        if (s + 1 < S) load(s + 1, pa, qa);
+        if (s >= 0) store(s, pb, qb);
+        if (s + 2 < S) load(s + 2, pb, qb);
+        if (s + 1 < S) store(s + 1, pa, qa);
+      }
     }
   }
   if (warp == WG_NPW) {
@@ -1297,7 +1366,7 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
         const uint32_t stg = (uint32_t)c % WG_STAGES;
         mbar_wait(BAR(stg), ((uint32_t)c / WG_STAGES) & 1, 4);
         tc_fence_after();
-        const uint32_t pb = smem_u32(smem + stg * WG_STAGE_BYTES), qb = pb + WG_MAT_BYTES;
+        const uint32_t pb = smem_u32(smem + stg * WL::STAGE), qb = pb + WL::MAT;
 #pragma unroll
         for (int kk = 0; kk < WG_CHUNK / 16; ++kk)
 #pragma unroll
@@ -1748,11 +1817,11 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
   p.da = m->da_in; p.zsave = m->z_save; p.in = in; p.ld_in = ld_in; p.src0 = src0; p.src1 = src1; p.idx = idx;
   p.part = workspace;
   p.nprod = m->n_products == 1 ? 1 : (m->n_products == 3 ? 3 : 6);
-  const int smem_bytes = WG_STAGES * WG_STAGE_BYTES + 256;
+  const int smem_bytes = p.nprod > 3 ? WgLayout<true>::TOTAL : WgLayout<false>::TOTAL;
   static bool configured = false;
   if (!configured) {
-    FVGN_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    FVGN_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    FVGN_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgLayout<true>::TOTAL));
+    FVGN_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgLayout<false>::TOTAL));
     configured = true;
   }
   if (p.nprod > 3) wgrad_tc3_kernel<true><<<p.njobs * p.nranges, WG_NTHREADS, smem_bytes, st>>>(p);
