@@ -975,6 +975,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_DFREE + a));
     };
+    // The saved pre-activations z2 / z1 of a tile (their global-load latency was the epilogue's largest stall: 37 % of its samples,
+    // profiles/r01c_ncu_backward_summary.txt).  Two-term variant: this thread's 256 bytes of a batch are fetched by cp.async into the
+    // third sub-tile of ring slot q — 16 KB that variant neither writes nor multiplies — a whole phase before they are read: z1 of the
+    // tile as soon as batch S1 has consumed z2 (the layer-2 MMAs run meanwhile), z2 of the next tile after batch S2 (three S3 batches
+    // follow).  Slots are private to the thread ([16-byte chunk][64 threads]: conflict-free), so cp.async.wait_group is the only sync.
+    // Six-product variant: one sub-chunk ahead through registers.
+    const uint32_t z_me = smem_u32((q < 2 ? sA + q * SLOT_BYTES : sW + (q - 2) * SLOT_BYTES) + 2 * TILE_BYTES) + (uint32_t)(32 * h + lane) * 16u;
+    auto issue_z = [&](int jl_, int b_) {
+      if (jl_ < n_local) {
+        const int row = min(((int)blockIdx.x + jl_ * (int)gridDim.x) * TM + 32 * q + lane, p.rows - 1);
+        const float* zp = p.zsave + (size_t)row * 384 + (b_ == 0 ? 128 : 0) + 64 * h;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(z_me + 1024u * (uint32_t)k), "l"(zp + 4 * k) : "memory");
+      }
+      cp_async_commit();
+    };
+    if (!THIRD) issue_z(0, 0);
 #pragma unroll 1
     for (int jl = 0; jl < n_local; ++jl) {
       const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
@@ -984,21 +1002,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
 #pragma unroll 1
       for (int b = 0; b < 2; ++b) {
         const float* zrow = p.zsave + (size_t)grow_c * 384 + (b == 0 ? 128 : 0);  // S1 pairs with z2, S2 with z1
-        // the saved pre-activations of a sub-chunk are fetched one sub-chunk ahead (the first one before the accumulator wait): their
-        // global-load latency was the epilogue's largest stall (37 % of its samples, profiles/r01c_ncu_backward_summary.txt)
         float4 zn[4];
+        if (THIRD) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) zn[j4] = ldg4(zrow + 16 * (4 * h) + 4 * j4);
+          for (int j4 = 0; j4 < 4; ++j4) zn[j4] = ldg4(zrow + 16 * (4 * h) + 4 * j4);
+        }
         wait_acc(b);
+        if (!THIRD) cp_async_wait<0>();
 #pragma unroll 1
         for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
           tmem_ld16_issue(t_lane + 128u * (uint32_t)b + 16 * sc, r);
           float4 zc[4];
+          if (THIRD) {
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) zc[j4] = zn[j4];
-          if (sc + 1 < 4 * h + 4) {
+            for (int j4 = 0; j4 < 4; ++j4) zc[j4] = zn[j4];
+            if (sc + 1 < 4 * h + 4) {
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) zn[j4] = ldg4(zrow + 16 * (sc + 1) + 4 * j4);
+              for (int j4 = 0; j4 < 4; ++j4) zn[j4] = ldg4(zrow + 16 * (sc + 1) + 4 * j4);
+            }
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint32_t a = z_me + 1024u * (uint32_t)(4 * (sc - 4 * h) + j4);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(zc[j4].x), "=f"(zc[j4].y), "=f"(zc[j4].z), "=f"(zc[j4].w) : "r"(a));
+            }
           }
           tmem_ld16_wait(r);
           if (sc == 4 * h + 3) release_acc(b);
@@ -1021,6 +1048,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
           tmem_st8(t_h + 64 + 8 * sc, p1);
           if (third) tmem_st8(t_h + 128 + 8 * sc, p2);
           store_rows16(v, p.da, 256, 128 * b + 16 * sc, row0 + 32 * q);
+        }
+        if (!THIRD) {  // this batch's z has been consumed: request the next batch's (z1 of this tile, or z2 of the next tile)
+          if (b == 0) issue_z(jl, 1);
+          else issue_z(jl + 1, 0);
         }
         tmem_wait_st();
         tc_fence_before();
