@@ -51,6 +51,7 @@ _SIGS = {
     "fvgn_cell_block_fwd_xbf16": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P, _I, _P]),
     "fvgn_edge_block_fwd_xbf16": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _I, _P]),
     "fvgn_cell_mean_split": (_I, [_P, _P, _I, _P, _P]),
+    "fvgn_cell_mean": (_I, [_P, _P, _I, _P, _P]),
     "fvgn_cell_block_fwd_split": (_I, [C.POINTER(MlpT), _P, _P, _I, _P, _P]),
     "fvgn_edge_block_fwd_split": (_I, [C.POINTER(MlpT), _P, _P, _P, _I, _P]),
     "fvgn_face_area_bn_fwd": (_I, [_P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -90,7 +91,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.fvgn_abi_version() != 7:
+        if L.fvgn_abi_version() != 8:
             raise RuntimeError("libfvgn_b200.so ABI version mismatch")
         _lib = L
     return _lib

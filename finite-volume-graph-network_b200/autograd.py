@@ -55,8 +55,12 @@ class NetFunction(torch.autograd.Function):
             cb, eb = blk.cb_module.net, blk.eb_module.net
             ag = topo.agg(blk.cb_module.mp_times)
             na = ops.node_aggregate_fwd(e, ag.ptr, ag.items, ag.rows)
+            if mm == 2 and ag.idx is not None:
+                # tensor-core training: the per-cell mean once per layer (same arithmetic), then the forward and the weight-gradient
+                # kernel read it as a plain per-cell row (cells_node_T = NULL) instead of three gathered node rows each
+                na = ops.cell_mean(na, ag.idx)
             zc, ze = zbuf(topo.C), zbuf(topo.F)
-            xp, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, na, ag.idx, mm, z_save=zc)
+            xp, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, na, ag.idx if mm != 2 else None, mm, z_save=zc)
             _, e_new = ops.edge_block_fwd(eb.mlp_ref(), xp, e, topo.nc, mm, z_save=ze)
             saved.append((x, e, xp, na, zc, ze))
             x, e = x_new, e_new
@@ -128,7 +132,7 @@ class NetFunction(torch.autograd.Function):
             if tc:
                 dz, gxh = ops.ln_bwd(g_xp, zc, cb[1].weight)
                 da, dA_c = ops.mlp_dgrad_x3(cb.mlp_ref(), dz, zc, want_dA=True, dA_base=g_x)
-                grads[id(cb)] = ops.mlp_wgrad_x3(cb.mlp_ref(), 1, g_xp, dz, gxh, zc, da, src0=x_in, src1=na, idx=ag.idx)
+                grads[id(cb)] = ops.mlp_wgrad_x3(cb.mlp_ref(), 1, g_xp, dz, gxh, zc, da, src0=x_in, src1=na, idx=None)  # na = the per-cell aggregate
             else:
                 grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, ag.idx, g_xp, d_x_base=g_x, z_saved=zc)
             # transposes of the twice-message aggregation: cell -> node (x 1/3), node -> face halves

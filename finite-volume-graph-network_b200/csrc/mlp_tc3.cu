@@ -1534,6 +1534,16 @@ __global__ void __launch_bounds__(256) cell_mean_split_kernel(const float* __res
   *reinterpret_cast<uint2*>(o + 128) = q1;
 }
 
+// The same mean as plain fp32 [C][64] (training: the forward and the weight-gradient kernel then read it as a per-cell row — the
+// cells_node_T = NULL convention — instead of gathering three node rows each).
+__global__ void __launch_bounds__(256) cell_mean_kernel(const float* __restrict__ node_agg, const int32_t* __restrict__ cells_node_T, int C,
+                                                        float* __restrict__ out) {
+  const int gid = blockIdx.x * 256 + threadIdx.x;
+  const int c = gid >> 4, hl = gid & 15;
+  if (c >= C) return;
+  *reinterpret_cast<float4*>(out + (size_t)c * 64 + hl * 4) = cell_agg4(node_agg, cells_node_T, (size_t)C, c, hl * 4);
+}
+
 // Forward weights: blockIdx.x = weight matrix, blockIdx.y = slice of its tiles (every CTA of a matrix finds the same max|W| itself:
 // 196 KB at most, L2-resident).  W [n_valid, k_valid] fp32 row-major -> scale 2^s with max|W| 2^s in [2^13, 2^14)
 // (found here, on the device: graph-capturable, no host round trip) -> steps [kt][2 fp16 splits][128 rows][64 k], each sub-tile a
@@ -1723,6 +1733,15 @@ int tc3_edge_block(const fvgn_mlp_t* mlp, const float* x_prime, const float* e, 
 
 // ---- split-shadow (inference) variants: latents are fp32, updated in place; x' only exists as the fp16 hi/lo shadow the EdgeBlock gathers
 static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+int tc3_cell_mean(const float* node_agg, const int32_t* cells_node_T, int n_cells, float* out, cudaStream_t st) {
+  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (node_agg && cells_node_T && out)), "NULL input");
+  FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "output must be 16B aligned");
+  if (n_cells == 0) return 0;
+  x3::cell_mean_kernel<<<cdiv((long long)n_cells * 16, 256), 256, 0, st>>>(node_agg, cells_node_T, n_cells, out);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
 
 int tc3_cell_mean_split(const float* node_agg, const int32_t* cells_node_T, int n_cells, void* out, cudaStream_t st) {
   FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (node_agg && out)), "NULL input");  // cells_node_T == NULL: mp_times = 1

@@ -293,6 +293,17 @@ def node_aggregate_fwd(e, node_ptr, node_items, n_nodes, out=None):
     return out
 
 
+def cell_mean(node_agg, cells_node_T):
+    """per-cell mean of the three node aggregates, fp32 [C,64] (fvgn_cell_mean)"""
+    _cf(node_agg, "node_agg"), _ci(cells_node_T, "cells_node_T", 3)
+    Cn = cells_node_T.shape[1]
+    out = torch.empty((Cn, 64), dtype=torch.float32, device=node_agg.device)
+    _count(1)
+    with _timed("cell_mean"):
+        check(_lib.lib().fvgn_cell_mean(_p(node_agg), _p(cells_node_T), Cn, _p(out), _stream()), "cell_mean")
+    return out
+
+
 def _cell_table_ok(cells_node_T, node_agg, n_cells, who):
     """cells_node_T [3,C] int32 (mp_times >= 2: node_agg is per node), or None (mp_times = 1: node_agg is the per-cell aggregate [C,64])"""
     if cells_node_T is None:

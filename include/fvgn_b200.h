@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FVGN_ABI_VERSION 7 /* v7: cells_node_T == NULL selects the mp_times = 1 CellBlock in every cell-block entry point */
+#define FVGN_ABI_VERSION 8 /* v7: cells_node_T == NULL selects the mp_times = 1 CellBlock in every cell-block entry point; v8: fvgn_mlp_pack_bf16x3_many, fvgn_cell_mean, n_products = 3 */
 #define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
 
 #define FVGN_E_BADARG (-1)
@@ -196,6 +196,11 @@ FVGN_API int fvgn_edge_block_fwd_xbf16(const fvgn_mlp_t* mlp, const uint16_t* x_
  * Results are bit-identical to fvgn_cell_block_fwd + fvgn_edge_block_fwd in FVGN_MATH_BF16X3_TC mode. */
 FVGN_API int fvgn_cell_mean_split(const float* node_agg /*[N,64]*/, const int32_t* cells_node_T /*[3,C]*/, int n_cells,
                                   void* cell_mean_split /*[C,2,64] fp16 out*/, fvgn_stream_t stream);
+/* The same per-cell mean as plain fp32 [C,64] (GN_blocks.py:125-129, same arithmetic): the training path computes it once per layer and
+ * hands it to fvgn_cell_block_fwd / fvgn_mlp_wgrad_x3 as a per-cell aggregate with cells_node_T = NULL (bit-identical results; the
+ * weight-gradient producers then read plain rows through their cp.async ring instead of gathering three node rows). */
+FVGN_API int fvgn_cell_mean(const float* node_agg /*[N,64]*/, const int32_t* cells_node_T /*[3,C]*/, int n_cells,
+                            float* cell_mean /*[C,64] out*/, fvgn_stream_t stream);
 FVGN_API int fvgn_cell_block_fwd_split(const fvgn_mlp_t* mlp, float* x /*[C,128] in/out*/, const void* cell_mean_split /*[C,2,64] fp16*/,
                                        int n_cells, void* x_prime_split /*[C,2,128] fp16 out*/, fvgn_stream_t stream);
 FVGN_API int fvgn_edge_block_fwd_split(const fvgn_mlp_t* mlp, const void* x_prime_split /*[C,2,128] fp16*/, float* e /*[F,128] in/out*/,
