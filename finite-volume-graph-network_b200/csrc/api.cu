@@ -48,6 +48,7 @@ int tc3_pack_many(const fvgn_mlp_t*, int, cudaStream_t);
 size_t tc3_packed_bwd_bytes(int k_in);
 int tc3_pack_bwd(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
 int tc3_ln_bwd(const float*, int, const float*, const float*, int, float*, float*, cudaStream_t);
+size_t tc3_ln_bwd_sums_floats(int rows);
 size_t tc3_wgrad_workspace_floats(int k_in);
 int tc3_wgrad(const fvgn_mlp_t*, int, const float*, int, const float*, const float*, const int32_t*, int, const float*, int, const float*,
               const float*, float*, float*, cudaStream_t);
@@ -191,6 +192,8 @@ extern "C" int fvgn_mlp_pack_bf16x3_bwd(const fvgn_mlp_t* mlp, void* packed, siz
   if (int e = check_device()) return e;
   return tc3_pack_bwd(mlp, packed, packed_bytes, as_stream(stream));
 }
+
+extern "C" size_t fvgn_ln_bwd_sums_floats(int rows) { return tc3_ln_bwd_sums_floats(rows); }
 
 extern "C" int fvgn_ln_bwd(const float* d_out, int ld_dout, const float* z_save, const float* ln_w, int rows, float* dz, float* gxhat,
                            fvgn_stream_t stream) {

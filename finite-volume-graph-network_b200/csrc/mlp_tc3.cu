@@ -1122,6 +1122,65 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
       make_float4(rstd * (h0 - m1 - x0 * m2), rstd * (h1 - m1 - x1 * m2), rstd * (h2 - m1 - x2 * m2), rstd * (h3 - m1 - x3v * m2));
 }
 
+// The same with the three column sums the parameter gradients need folded in (db3 = colsum(dz), dLN_w = colsum(d_out * xhat),
+// dLN_b = colsum(d_out)): d_out * xhat is never written, and the column-sum kernel does not re-read the three matrices.  Block b owns the
+// row range [b per, (b + 1) per); warp w walks rows w, w + 8, ... of it keeping 12 running sums per lane; the eight warps are combined
+// through shared memory in a fixed order and the block writes sums[src][b][128] — the layout colsum_reduce_kernel finishes.  Fixed
+// row -> (block, warp) mapping and fixed combination orders: deterministic.
+constexpr int LN_BWD_NB = 592;  // at most this many row ranges, at least 64 rows each
+__host__ __device__ inline int ln_bwd_blocks(int rows) { const int n = (rows + 63) / 64; return n < LN_BWD_NB ? (n > 0 ? n : 1) : LN_BWD_NB; }
+__global__ void __launch_bounds__(256) ln_bwd_sums_kernel(const float* __restrict__ d_out, int ld_dout, const float* __restrict__ zsave,
+                                                          const float* __restrict__ gamma, int rows, float* __restrict__ dz,
+                                                          float* __restrict__ sums /*[3][gridDim.x][128]*/) {
+  __shared__ float sh[3][8][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = (rows + (int)gridDim.x - 1) / (int)gridDim.x, r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+  const float4 w = ldg4(gamma + lane * 4);
+  float4 s_dz = make_float4(0.f, 0.f, 0.f, 0.f), s_gx = s_dz, s_g = s_dz;
+  int row = r0 + warp;
+  float4 z, g;
+  if (row < r1) { z = ldg4(zsave + (size_t)row * 384 + 256 + lane * 4); g = ldg4(d_out + (size_t)row * ld_dout + lane * 4); }
+#pragma unroll 1
+  for (; row < r1; row += 8) {
+    const float4 zc = z, gc = g;
+    if (row + 8 < r1) {  // the next row of this warp is in flight while this one goes through its three reductions
+      z = ldg4(zsave + (size_t)(row + 8) * 384 + 256 + lane * 4);
+      g = ldg4(d_out + (size_t)(row + 8) * ld_dout + lane * 4);
+    }
+    float s = (zc.x + zc.y) + (zc.z + zc.w);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / 128.0f);
+    const float d0 = zc.x - mean, d1 = zc.y - mean, d2 = zc.z - mean, d3 = zc.w - mean;
+    float qv = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
+    const float rstd = 1.0f / sqrtf(qv * (1.0f / 128.0f) + 1e-5f);
+    const float x0 = d0 * rstd, x1 = d1 * rstd, x2 = d2 * rstd, x3v = d3 * rstd;
+    const float h0 = gc.x * w.x, h1 = gc.y * w.y, h2 = gc.z * w.z, h3 = gc.w * w.w;
+    float m1 = (h0 + h1) + (h2 + h3), m2 = fmaf(h0, x0, fmaf(h1, x1, fmaf(h2, x2, h3 * x3v)));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) { m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o); }
+    m1 *= (1.0f / 128.0f); m2 *= (1.0f / 128.0f);
+    const float4 dzv = make_float4(rstd * (h0 - m1 - x0 * m2), rstd * (h1 - m1 - x1 * m2), rstd * (h2 - m1 - x2 * m2), rstd * (h3 - m1 - x3v * m2));
+    *reinterpret_cast<float4*>(dz + (size_t)row * 128 + lane * 4) = dzv;
+    s_dz.x += dzv.x; s_dz.y += dzv.y; s_dz.z += dzv.z; s_dz.w += dzv.w;
+    s_gx.x += gc.x * x0; s_gx.y += gc.y * x1; s_gx.z += gc.z * x2; s_gx.w += gc.w * x3v;
+    s_g.x += gc.x; s_g.y += gc.y; s_g.z += gc.z; s_g.w += gc.w;
+  }
+  *reinterpret_cast<float4*>(&sh[0][warp][lane * 4]) = s_dz;
+  *reinterpret_cast<float4*>(&sh[1][warp][lane * 4]) = s_gx;
+  *reinterpret_cast<float4*>(&sh[2][warp][lane * 4]) = s_g;
+  __syncthreads();
+  for (int t = threadIdx.x; t < 384; t += 256) {
+    const int src = t >> 7, c = t & 127;
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += sh[src][k][c];
+    sums[((size_t)src * gridDim.x + blockIdx.x) * 128 + c] = a;
+  }
+}
+
 // transposed packing for the backward: element (n, k) of the packed "weight" is W[k * ldw + n0 + n]  (W^T restricted to columns n0..)
 // (blockIdx.y = job: all transposed blocks of one MLP in one launch)
 struct PackTJob { const float* W; int ldw, n0, n_valid, k_valid, step0; };
@@ -1460,12 +1519,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int njobs, i
 // deterministic column sums of up to five [rows, ncols <= 128] fp32 matrices: blockIdx.y = source, blockIdx.x = row range; a block is
 // 16 row-lanes x 32 float4 column groups, every thread keeps 4 independent partial sums (fixed combination order), the row-lanes are
 // combined through shared memory in a fixed order, and colsum_reduce_kernel sums the row ranges in a fixed order.
-struct ColsumSrc { const float* src; int ld, ncols, dst_off; };
+struct ColsumSrc { const float* src; int ld, ncols, dst_off; const float* pre; int pre_nb; };  // pre: partials [pre_nb][128] already formed (ln_bwd_sums_kernel)
 struct ColsumParams { ColsumSrc s[5]; int rows, nb; float* partial; float* grads; };
 __global__ void __launch_bounds__(512) colsum_kernel(const ColsumParams p) {
   __shared__ float sh[16][128];
   const ColsumSrc cs = p.s[blockIdx.y];
-  if (cs.src == nullptr) return;
+  if (cs.src == nullptr || cs.pre != nullptr) return;
   const int per = (p.rows + p.nb - 1) / p.nb, r0 = blockIdx.x * per, r1 = min(p.rows, r0 + per);
   const bool vec = cs.ncols == 128 && (cs.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(cs.src) & 15) == 0;
   if (vec) {
@@ -1501,20 +1560,25 @@ __global__ void __launch_bounds__(512) colsum_kernel(const ColsumParams p) {
   }
 }
 __global__ void __launch_bounds__(1024) colsum_reduce_kernel(const ColsumParams p) {
-  __shared__ float sh[8][128];
+  __shared__ float sh[32][128];
   const ColsumSrc cs = p.s[blockIdx.x];
-  if (cs.src == nullptr) return;
-  const int c = threadIdx.x & 127, rl = threadIdx.x >> 7;
-  float a = 0.f;
-  if (c < cs.ncols)
-    for (int b = rl; b < p.nb; b += 8) a += p.partial[((size_t)blockIdx.x * p.nb + b) * 128 + c];
-  sh[rl][c] = a;
+  if (cs.src == nullptr && cs.pre == nullptr) return;
+  // 32 float4 column groups x 32 row lanes (up to 592 partial rows per source: 19 loads per thread), fixed combination order
+  const int c4 = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const float* part = cs.pre ? cs.pre : p.partial + (size_t)blockIdx.x * p.nb * 128;
+  const int nb = cs.pre ? cs.pre_nb : p.nb;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = rl; b < nb; b += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(part + (size_t)b * 128 + c4 * 4);  // (columns >= ncols of a narrow source: never stored)
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  *reinterpret_cast<float4*>(&sh[rl][c4 * 4]) = a;
   __syncthreads();
-  if (rl == 0 && c < cs.ncols) {
+  if (threadIdx.x < 128 && (int)threadIdx.x < cs.ncols) {
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += sh[k][c];
-    p.grads[cs.dst_off + c] = s;
+    for (int k = 0; k < 32; ++k) s += sh[k][threadIdx.x];
+    p.grads[cs.dst_off + threadIdx.x] = s;
   }
 }
 
@@ -1804,7 +1868,9 @@ int tc3_ln_bwd(const float* d_out, int ld_dout, const float* z_save, const float
   FVGN_CHECK_ARG(d_out && z_save && ln_w && dz, "NULL pointer");
   FVGN_CHECK_ARG((ld_dout & 3) == 0, "d_out row stride must be a multiple of 4 floats");
   if (rows <= 0) return 0;
-  x3::ln_bwd_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(d_out, ld_dout, z_save, ln_w, rows, dz, gxhat);
+  // `gxhat` is the column-sum partial buffer [3][ln_bwd_blocks(rows)][128] (dz | d_out * xhat | d_out), or NULL for dz alone
+  if (gxhat) x3::ln_bwd_sums_kernel<<<x3::ln_bwd_blocks(rows), 256, 0, st>>>(d_out, ld_dout, z_save, ln_w, rows, dz, gxhat);
+  else x3::ln_bwd_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(d_out, ld_dout, z_save, ln_w, rows, dz, nullptr);
   FVGN_LAUNCH_CHECK();
   return 0;
 }
@@ -1845,6 +1911,7 @@ static int wg_nranges(int k_in, int rows) {
   const int nchunks = cdiv(rows, x3::WG_CHUNK), by_sm = sm_count() / wg_njobs(k_in);
   return nchunks < by_sm ? nchunks : by_sm;
 }
+size_t tc3_ln_bwd_sums_floats(int rows) { return (size_t)3 * x3::ln_bwd_blocks(rows) * 128; }
 constexpr int WG_COLSUM_NB = 592;  // at most this many row ranges (>= 256 rows each) for the column sums
 size_t tc3_wgrad_workspace_floats(int k_in) {
   return (size_t)wg_njobs(k_in) * (size_t)(sm_count() / wg_njobs(k_in)) * 16384 + (size_t)5 * WG_COLSUM_NB * 128;
@@ -1883,21 +1950,23 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
   const int vec0 = 128 * m->k_in + 2 * 16384;
   ColsumParams c{};
   // ~4 resident 512-thread blocks per SM over the 5 sources, at least 256 rows per block
-  c.rows = rows; c.nb = cdiv(rows, 256) < (4 * sm_count()) / 5 ? cdiv(rows, 256) : (4 * sm_count()) / 5; c.grads = grads;
+  c.rows = rows; c.nb = cdiv(rows, 256) < (4 * sm_count()) / 2 ? cdiv(rows, 256) : (4 * sm_count()) / 2; c.grads = grads;
   if (c.nb > WG_COLSUM_NB) c.nb = WG_COLSUM_NB;
   c.partial = workspace + (size_t)p.njobs * (size_t)(sm_count() / p.njobs) * 16384;
-  c.s[0] = {m->da_in, 256, 128, vec0 + 128};            // db2 = colsum(da2)
-  c.s[1] = {m->da_in + 128, 256, 128, vec0};            // db1 = colsum(da1)
+  c.s[0] = {m->da_in, 256, 128, vec0 + 128, nullptr, 0};            // db2 = colsum(da2)
+  c.s[1] = {m->da_in + 128, 256, 128, vec0, nullptr, 0};            // db1 = colsum(da1)
   if (m->ln_w) {
-    c.s[2] = {dz, 128, 128, vec0 + 256};                // db3 = colsum(dz)
-    c.s[3] = {gxhat, 128, 128, vec0 + 384};             // dLN_w = colsum(d_out * xhat)
-    c.s[4] = {d_out, ld_dout, 128, vec0 + 512};         // dLN_b = colsum(d_out)
+    // db3 = colsum(dz), dLN_w = colsum(d_out * xhat), dLN_b = colsum(d_out): per-block partials formed by fvgn_ln_bwd (`gxhat` = that buffer)
+    const int lnb = ln_bwd_blocks(rows);
+    c.s[2] = {nullptr, 0, 128, vec0 + 256, gxhat, lnb};
+    c.s[3] = {nullptr, 0, 128, vec0 + 384, gxhat + (size_t)lnb * 128, lnb};
+    c.s[4] = {nullptr, 0, 128, vec0 + 512, gxhat + (size_t)2 * lnb * 128, lnb};
   } else {
-    c.s[2] = {d_out, ld_dout, m->n_out, vec0 + 256};    // db3 = colsum(d_out)
-    c.s[3] = {nullptr, 0, 0, 0};
-    c.s[4] = {nullptr, 0, 0, 0};
+    c.s[2] = {d_out, ld_dout, m->n_out, vec0 + 256, nullptr, 0};    // db3 = colsum(d_out)
+    c.s[3] = {nullptr, 0, 0, 0, nullptr, 0};
+    c.s[4] = {nullptr, 0, 0, 0, nullptr, 0};
   }
-  colsum_kernel<<<dim3(c.nb, 5), 512, 0, st>>>(c);
+  colsum_kernel<<<dim3(c.nb, m->ln_w ? 2 : 3), 512, 0, st>>>(c);
   FVGN_LAUNCH_CHECK();
   colsum_reduce_kernel<<<5, 1024, 0, st>>>(c);
   FVGN_LAUNCH_CHECK();

@@ -617,12 +617,12 @@ def _bwd_buffers(mlp: MlpRef, device):
 
 
 def ln_bwd(d_out, z_saved, ln_w):
-    """LayerNorm backward of d_out with the statistics of the saved z3: (dz[rows,128] for fvgn_mlp_dgrad_x3, d_out * xhat [rows,128]
-    whose column sums are dLN_w)"""
+    """LayerNorm backward of d_out with the statistics of the saved z3: (dz[rows,128] for fvgn_mlp_dgrad_x3, the per-row-range partial
+    column sums of dz | d_out * xhat | d_out that fvgn_mlp_wgrad_x3 finishes into db3, dLN_w, dLN_b)"""
     _req(d_out, torch.float32, "d_out", 2), _cf(z_saved, "z_saved"), _cf(ln_w, "ln_w")
     rows = d_out.shape[0]
     dz = torch.empty((rows, 128), dtype=torch.float32, device=d_out.device)
-    gxhat = torch.empty((rows, 128), dtype=torch.float32, device=d_out.device)
+    gxhat = torch.empty(_lib.lib().fvgn_ln_bwd_sums_floats(rows), dtype=torch.float32, device=d_out.device)
     _count(1)
     check(_lib.lib().fvgn_ln_bwd(_p(d_out), _ld(d_out), _p(z_saved), _p(ln_w), rows, _p(dz), _p(gxhat), _stream()), "ln_bwd")
     return dz, gxhat

@@ -260,9 +260,13 @@ FVGN_API int fvgn_edge_block_bwd(const fvgn_mlp_t* mlp, const float* x_prime, co
  * followed by fvgn_*_bwd with mlp->da_in = da for the weight gradients. */
 FVGN_API size_t fvgn_mlp_packed_x3_bwd_bytes(int k_in);
 FVGN_API int fvgn_mlp_pack_bf16x3_bwd(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream);
+/*                       `ln_sums` (optional, fvgn_ln_bwd_sums_floats(rows) floats): per-row-range partial COLUMN SUMS of dz, d_out * xhat and
+ *                       d_out — what db3, dLN_w and dLN_b are — formed in the same pass (d_out * xhat is never written, nothing is re-read) */
+FVGN_API size_t fvgn_ln_bwd_sums_floats(int rows);
 FVGN_API int fvgn_ln_bwd(const float* d_out, int ld_dout, const float* z_save /*[rows,384]*/, const float* ln_w, int rows, float* dz /*[rows,128]*/,
-                         float* gxhat /*[rows,128] = d_out * xhat, or NULL*/, fvgn_stream_t stream);
-/*   fvgn_mlp_wgrad_x3:  all parameter gradients of the MLP (same `grads` layout as fvgn_mlp_rows_bwd) from dz / gxhat (fvgn_ln_bwd),
+                         float* ln_sums /*or NULL*/, fvgn_stream_t stream);
+/*   fvgn_mlp_wgrad_x3:  all parameter gradients of the MLP (same `grads` layout as fvgn_mlp_rows_bwd) from dz / ln_sums (fvgn_ln_bwd; the
+ *                       parameter named gxhat below is that buffer),
  *                       mlp->da_in (fvgn_mlp_dgrad_x3), mlp->z_save and the layer inputs (mode 0: in/ld_in; 1 CellBlock: x, node_agg,
  *                       cells_node_T; 2 EdgeBlock: x', e, neighbour_cell): dW = P^T . Q as MN-major tcgen05 MMAs, deterministic. */
 FVGN_API size_t fvgn_mlp_wgrad_x3_workspace_floats(int k_in);
