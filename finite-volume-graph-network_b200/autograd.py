@@ -36,6 +36,58 @@ def network_params(model):
     return out
 
 
+# The weight-gradient kernels are off the backward's critical path (nothing downstream reads dW before the optimizer): with
+# FVGN_WGRAD_STREAM=1 they are enqueued on a side stream, forked from and joined back into the current stream with events (CUDA-graph
+# capturable), so that the small memory-bound kernels of the main chain (segment sums, LayerNorm backward, gradient combination) run
+# next to them instead of alone.  Inputs of a side-stream launch are kept alive until the main stream has waited for that launch.
+import os as _os
+
+WGRAD_SIDE_STREAM = _os.environ.get("FVGN_WGRAD_STREAM", "1") != "0"
+_SIDE = {}
+
+
+def _side_stream(dev):
+    s = _SIDE.get(dev)
+    if s is None:
+        s = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
+class _SideQueue:
+    """runs callables on the side stream; `retire()` makes the main stream wait for everything enqueued BEFORE the previous retire() and
+    drops those launches' inputs (one-stage delay: the side stream may lag the main chain by up to one layer)"""
+
+    def __init__(self, dev, enabled):
+        self.enabled = enabled
+        self.side = _side_stream(dev) if enabled else None
+        self.keep, self.pending = [], None
+
+    def run(self, fn, *alive):
+        if not self.enabled:
+            return fn()
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            out = fn()
+        self.keep.extend(alive)
+        return out
+
+    def retire(self, final=False):
+        if not self.enabled:
+            return
+        main = torch.cuda.current_stream()
+        if self.pending is not None:
+            main.wait_event(self.pending[0])
+            self.pending[1].clear()
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        self.pending, self.keep = (ev, self.keep), []
+        if final:
+            main.wait_event(ev)
+            self.pending[1].clear()
+            self.pending = None
+
+
 class NetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, topo, cell_in, edge_in, graph_edge_x, cell_area, unv, rho, dt, *params):
@@ -109,9 +161,11 @@ class NetFunction(torch.autograd.Function):
         grads = {}
         dec = epd.decoder.edge_decode_module
         tc = z_dec is not None  # bf16x3 forward: the data-gradient chain runs on the tensor cores, the FFMA kernel keeps the TN products
+        sq = _SideQueue(dev, WGRAD_SIDE_STREAM and tc)
         if tc:
             da, g_e = ops.mlp_dgrad_x3(dec.mlp_ref(), g_dec, z_dec, want_dA=True)
-            grads[id(dec)] = ops.mlp_wgrad_x3(dec.mlp_ref(), 0, g_dec, None, None, z_dec, da, x=e_final)
+            grads[id(dec)] = sq.run(lambda da=da: ops.mlp_wgrad_x3(dec.mlp_ref(), 0, g_dec, None, None, z_dec, da, x=e_final),
+                                    g_dec, z_dec, da, e_final)
         else:
             grads[id(dec)], g_e = ops.mlp_rows_bwd(dec.mlp_ref(), e_final, g_dec, want_d_in=True, z_saved=z_dec)
         g_x = None  # the last layer's cell latent feeds nothing but its own EdgeBlock
@@ -124,7 +178,9 @@ class NetFunction(torch.autograd.Function):
             if tc:
                 dz, gxh = ops.ln_bwd(g_e, ze, eb[1].weight)
                 da, dA_e = ops.mlp_dgrad_x3(eb.mlp_ref(), dz, ze, want_dA=True)
-                grads[id(eb)] = ops.mlp_wgrad_x3(eb.mlp_ref(), 2, g_e, dz, gxh, ze, da, src0=xp, src1=e_in, idx=topo.nc)
+                grads[id(eb)] = sq.run(lambda g_e=g_e, dz=dz, gxh=gxh, da=da: ops.mlp_wgrad_x3(eb.mlp_ref(), 2, g_e, dz, gxh, ze, da, src0=xp,
+                                                                                              src1=e_in, idx=topo.nc),
+                                       g_e, dz, gxh, ze, da, xp, e_in)
             else:
                 grads[id(eb)], dA_e = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e, z_saved=ze)
             # d x' = residual path + transpose of the x'[s], x'[r] gathers (cell <- face segment sum)
@@ -132,7 +188,9 @@ class NetFunction(torch.autograd.Function):
             if tc:
                 dz, gxh = ops.ln_bwd(g_xp, zc, cb[1].weight)
                 da, dA_c = ops.mlp_dgrad_x3(cb.mlp_ref(), dz, zc, want_dA=True, dA_base=g_x)
-                grads[id(cb)] = ops.mlp_wgrad_x3(cb.mlp_ref(), 1, g_xp, dz, gxh, zc, da, src0=x_in, src1=na, idx=None)  # na = the per-cell aggregate
+                grads[id(cb)] = sq.run(lambda g_xp=g_xp, dz=dz, gxh=gxh, da=da: ops.mlp_wgrad_x3(cb.mlp_ref(), 1, g_xp, dz, gxh, zc, da, src0=x_in,
+                                                                                                src1=na, idx=None),  # na = the per-cell aggregate
+                                       g_xp, dz, gxh, zc, da, x_in, na)
             else:
                 grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, ag.idx, g_xp, d_x_base=g_x, z_saved=zc)
             # transposes of the twice-message aggregation: cell -> node (x 1/3), node -> face halves
@@ -142,13 +200,17 @@ class NetFunction(torch.autograd.Function):
                 g_na = dA_c[:, 128:192].contiguous()
             g_e = ops.edge_grad_combine(g_e, dA_e, g_na, ag.face)
             g_x = dA_c[:, 0:128]
+            sq.retire()
         for enc, inp, g, z in ((epd.encoder.cb_encoder, cell_in, g_x, z_enc_c), (epd.encoder.eb_encoder, edge_in, g_e, z_enc_e)):
             if tc:
                 dz, gxh = ops.ln_bwd(g, z, enc[1].weight)
                 da, _ = ops.mlp_dgrad_x3(enc.mlp_ref(), dz, z, want_dA=False)
-                grads[id(enc)] = ops.mlp_wgrad_x3(enc.mlp_ref(), 0, g, dz, gxh, z, da, x=inp)
+                grads[id(enc)] = sq.run(lambda enc=enc, g=g, dz=dz, gxh=gxh, z=z, da=da, inp=inp: ops.mlp_wgrad_x3(enc.mlp_ref(), 0, g, dz, gxh, z, da,
+                                                                                                                  x=inp),
+                                        g, dz, gxh, z, da, inp)
             else:
                 grads[id(enc)], _ = ops.mlp_rows_bwd(enc.mlp_ref(), inp, g, z_saved=z)
+        sq.retire(final=True)
         flat = [g for m in network_mlps(model) for g in grads[id(m)]]
         flat += [g_bn[0:1], g_bn[1:2]]
         return (None,) * 9 + tuple(flat)
