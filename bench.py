@@ -492,7 +492,7 @@ def training_measure(args, rank, world, dev, meshes, dist):
         opt_e.step()
 
     fsteps = 2 * steps
-    for _ in range(20):  # the batch sizes vary from step to step: let the caching allocator see the range of block sizes first
+    for _ in range(40):  # the batch sizes vary from step to step: let the caching allocator (two streams) see the range of block sizes first
         fresh_step()
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

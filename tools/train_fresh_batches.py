@@ -62,4 +62,4 @@ for _ in range(5):
 torch.cuda.synchronize()
 pr.disable()
 st = pstats.Stats(pr)
-st.sort_stats("tottime").print_stats(30)
+st.sort_stats("cumulative").print_stats(45)
