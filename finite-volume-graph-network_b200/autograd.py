@@ -62,14 +62,18 @@ class _SideQueue:
         self.side = _side_stream(dev) if enabled else None
         self.keep, self.pending = [], None
 
-    def run(self, fn, *alive):
+    def wgrad(self, mlp, *args, alive=(), **kw):
+        """ops.mlp_wgrad_x3 on the side stream; its output / workspace buffers come from the MAIN stream's allocator pool (a second
+        per-stream pool would have to grow through its own cudaMalloc phase whenever the batch sizes change)"""
         if not self.enabled:
-            return fn()
+            return ops.mlp_wgrad_x3(mlp, *args, **kw)
+        bufs = ops.mlp_wgrad_x3_buffers(mlp, mlp.tensors[0].device)
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            out = fn()
+            out = ops.mlp_wgrad_x3(mlp, *args, buffers=bufs, **kw)
         self.keep.extend(alive)
+        self.keep.append(bufs[1])
         return out
 
     def retire(self, final=False):
@@ -164,8 +168,7 @@ class NetFunction(torch.autograd.Function):
         sq = _SideQueue(dev, WGRAD_SIDE_STREAM and tc)
         if tc:
             da, g_e = ops.mlp_dgrad_x3(dec.mlp_ref(), g_dec, z_dec, want_dA=True)
-            grads[id(dec)] = sq.run(lambda da=da: ops.mlp_wgrad_x3(dec.mlp_ref(), 0, g_dec, None, None, z_dec, da, x=e_final),
-                                    g_dec, z_dec, da, e_final)
+            grads[id(dec)] = sq.wgrad(dec.mlp_ref(), 0, g_dec, None, None, z_dec, da, x=e_final, alive=(g_dec, z_dec, da, e_final))
         else:
             grads[id(dec)], g_e = ops.mlp_rows_bwd(dec.mlp_ref(), e_final, g_dec, want_d_in=True, z_saved=z_dec)
         g_x = None  # the last layer's cell latent feeds nothing but its own EdgeBlock
@@ -178,9 +181,8 @@ class NetFunction(torch.autograd.Function):
             if tc:
                 dz, gxh = ops.ln_bwd(g_e, ze, eb[1].weight)
                 da, dA_e = ops.mlp_dgrad_x3(eb.mlp_ref(), dz, ze, want_dA=True)
-                grads[id(eb)] = sq.run(lambda g_e=g_e, dz=dz, gxh=gxh, da=da: ops.mlp_wgrad_x3(eb.mlp_ref(), 2, g_e, dz, gxh, ze, da, src0=xp,
-                                                                                              src1=e_in, idx=topo.nc),
-                                       g_e, dz, gxh, ze, da, xp, e_in)
+                grads[id(eb)] = sq.wgrad(eb.mlp_ref(), 2, g_e, dz, gxh, ze, da, src0=xp, src1=e_in, idx=topo.nc,
+                                         alive=(g_e, dz, gxh, ze, da, xp, e_in))
             else:
                 grads[id(eb)], dA_e = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e, z_saved=ze)
             # d x' = residual path + transpose of the x'[s], x'[r] gathers (cell <- face segment sum)
@@ -188,9 +190,8 @@ class NetFunction(torch.autograd.Function):
             if tc:
                 dz, gxh = ops.ln_bwd(g_xp, zc, cb[1].weight)
                 da, dA_c = ops.mlp_dgrad_x3(cb.mlp_ref(), dz, zc, want_dA=True, dA_base=g_x)
-                grads[id(cb)] = sq.run(lambda g_xp=g_xp, dz=dz, gxh=gxh, da=da: ops.mlp_wgrad_x3(cb.mlp_ref(), 1, g_xp, dz, gxh, zc, da, src0=x_in,
-                                                                                                src1=na, idx=None),  # na = the per-cell aggregate
-                                       g_xp, dz, gxh, zc, da, x_in, na)
+                grads[id(cb)] = sq.wgrad(cb.mlp_ref(), 1, g_xp, dz, gxh, zc, da, src0=x_in, src1=na, idx=None,  # na = the per-cell aggregate
+                                         alive=(g_xp, dz, gxh, zc, da, x_in, na))
             else:
                 grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, ag.idx, g_xp, d_x_base=g_x, z_saved=zc)
             # transposes of the twice-message aggregation: cell -> node (x 1/3), node -> face halves
@@ -205,9 +206,7 @@ class NetFunction(torch.autograd.Function):
             if tc:
                 dz, gxh = ops.ln_bwd(g, z, enc[1].weight)
                 da, _ = ops.mlp_dgrad_x3(enc.mlp_ref(), dz, z, want_dA=False)
-                grads[id(enc)] = sq.run(lambda enc=enc, g=g, dz=dz, gxh=gxh, z=z, da=da, inp=inp: ops.mlp_wgrad_x3(enc.mlp_ref(), 0, g, dz, gxh, z, da,
-                                                                                                                  x=inp),
-                                        g, dz, gxh, z, da, inp)
+                grads[id(enc)] = sq.wgrad(enc.mlp_ref(), 0, g, dz, gxh, z, da, x=inp, alive=(g, dz, gxh, z, da, inp))
             else:
                 grads[id(enc)], _ = ops.mlp_rows_bwd(enc.mlp_ref(), inp, g, z_saved=z)
         sq.retire(final=True)

@@ -628,14 +628,21 @@ def ln_bwd(d_out, z_saved, ln_w):
     return dz, gxhat
 
 
-def mlp_wgrad_x3(mlp: MlpRef, mode, d_out, dz, gxhat, z_saved, da, x=None, src0=None, src1=None, idx=None):
+def mlp_wgrad_x3_buffers(mlp: MlpRef, device):
+    """(grads, workspace) of one fvgn_mlp_wgrad_x3 call — allocated by the caller when the call itself is enqueued on another stream
+    (the caching allocator's pools are per stream; the workspace must then stay alive until that stream has been waited for)"""
+    L = _lib.lib()
+    return (torch.empty(L.fvgn_mlp_grad_floats(mlp.k_in), dtype=torch.float32, device=device),
+            torch.empty(L.fvgn_mlp_wgrad_x3_workspace_floats(mlp.k_in), dtype=torch.float32, device=device))
+
+
+def mlp_wgrad_x3(mlp: MlpRef, mode, d_out, dz, gxhat, z_saved, da, x=None, src0=None, src1=None, idx=None, buffers=None):
     """all parameter gradients of one MLP on the tensor cores (MN-major P^T . Q products, deterministic).  mode 0: x = layer input
     [rows,k_in]; 1 (CellBlock): src0 = x, src1 = node_agg, idx = cells_node_T; 2 (EdgeBlock): src0 = x', src1 = e, idx = neighbour_cell"""
     _req(d_out, torch.float32, "d_out", 2)
     rows = d_out.shape[0]
     L = _lib.lib()
-    grads = torch.empty(L.fvgn_mlp_grad_floats(mlp.k_in), dtype=torch.float32, device=d_out.device)
-    ws = torch.empty(L.fvgn_mlp_wgrad_x3_workspace_floats(mlp.k_in), dtype=torch.float32, device=d_out.device)
+    grads, ws = buffers if buffers is not None else mlp_wgrad_x3_buffers(mlp, d_out.device)
     if mode == 0:
         _req(x, torch.float32, "x", 2)
     elif mode == 1:
