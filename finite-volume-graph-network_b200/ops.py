@@ -41,13 +41,14 @@ class _timed:
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
 
 
 def _stream():
     """the current CUDA stream of the current device as a void* (called once per kernel launch: the raw getter costs ~0.3 us, the
     torch.cuda.current_stream() object ~16 us)"""
     if _raw_stream is not None:
-        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
+        return C.c_void_p(_raw_stream(_raw_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
