@@ -1246,6 +1246,8 @@ struct WgParams {
   const float* in; int ld_in;   // ROWS: layer input
   const float* src0; const float* src1; const int32_t* idx;  // CELL / EDGE: as the forward
   float* part;                  // [njobs][nranges][128 * 128]
+  float* csum;                  // [3][nranges * WG_NPW][128]: per-(range, producer warp) column sums of the P operand of jobs 0 / 1 / 2
+  int csum_job0;                //   (= dz or d_out -> db3 when the MLP has no LayerNorm, da2 -> db2, da1 -> db1): the rows pass through anyway
 };
 
 // MN-major SWIZZLE_128B operand descriptor: 64 features per 128-byte row, 8-row groups 1024 B apart (SBO), the second 64-feature
@@ -1356,7 +1358,13 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
         }
       }
     };
+    const bool do_cs = p.csum != nullptr && (job == 1 || job == 2 || (job == 0 && p.csum_job0 != 0));
+    float4 cs0 = make_float4(0.f, 0.f, 0.f, 0.f), cs1 = cs0;  // this thread's 8 columns, rows hw, hw + 32, ... of the range in order
     auto store = [&](int s, float4 (*pv)[2], float4 (*qv)[2]) {
+      if (do_cs) {
+        cs0.x += pv[0][0].x; cs0.y += pv[0][0].y; cs0.z += pv[0][0].z; cs0.w += pv[0][0].w;
+        cs1.x += pv[0][1].x; cs1.y += pv[0][1].y; cs1.z += pv[0][1].z; cs1.w += pv[0][1].w;
+      }
       const int c = s >> 1, half = s & 1;
       const uint32_t stg = (uint32_t)c % WG_STAGES;
       if (half == 0 && c >= WG_STAGES) mbar_wait(BAR(2 + stg), (((uint32_t)c / WG_STAGES) - 1) & 1, 1);
@@ -1445,6 +1453,17 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
         if (s >= 0) store(s, pb, qb);
         if (s + 2 < S) load(s + 2, pb, qb);
         if (s + 1 < S) store(s + 1, pa, qa);
+      }
+    }
+    if (do_cs) {  // the two row lanes of a warp combined, then one 128-column partial per (range, warp): fixed order, no shared memory
+      cs0.x += __shfl_xor_sync(0xffffffffu, cs0.x, 16); cs0.y += __shfl_xor_sync(0xffffffffu, cs0.y, 16);
+      cs0.z += __shfl_xor_sync(0xffffffffu, cs0.z, 16); cs0.w += __shfl_xor_sync(0xffffffffu, cs0.w, 16);
+      cs1.x += __shfl_xor_sync(0xffffffffu, cs1.x, 16); cs1.y += __shfl_xor_sync(0xffffffffu, cs1.y, 16);
+      cs1.z += __shfl_xor_sync(0xffffffffu, cs1.z, 16); cs1.w += __shfl_xor_sync(0xffffffffu, cs1.w, 16);
+      if (lane < 16) {
+        float* d = p.csum + (((size_t)job * p.nranges + range) * WG_NPW + warp) * 128 + 4 * hl;
+        *reinterpret_cast<float4*>(d) = cs0;
+        *reinterpret_cast<float4*>(d + 64) = cs1;
       }
     }
   }
@@ -1933,6 +1952,8 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
   p.dz = m->ln_w ? dz : d_out; p.ld_dz = m->ln_w ? 128 : ld_dout;
   p.da = m->da_in; p.zsave = m->z_save; p.in = in; p.ld_in = ld_in; p.src0 = src0; p.src1 = src1; p.idx = idx;
   p.part = workspace;
+  p.csum = workspace + (size_t)p.njobs * (size_t)(sm_count() / p.njobs) * 16384;  // (the column-sum kernel's partial region: it no longer runs)
+  p.csum_job0 = m->ln_w ? 0 : 1;
   p.nprod = m->n_products == 1 ? 1 : (m->n_products == 3 ? 3 : 6);
   const int smem_bytes = p.nprod > 3 ? WgLayout<true>::TOTAL : WgLayout<false>::TOTAL;
   static bool configured = false;
@@ -1953,8 +1974,12 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
   c.rows = rows; c.nb = cdiv(rows, 256) < (4 * sm_count()) / 2 ? cdiv(rows, 256) : (4 * sm_count()) / 2; c.grads = grads;
   if (c.nb > WG_COLSUM_NB) c.nb = WG_COLSUM_NB;
   c.partial = workspace + (size_t)p.njobs * (size_t)(sm_count() / p.njobs) * 16384;
-  c.s[0] = {m->da_in, 256, 128, vec0 + 128, nullptr, 0};            // db2 = colsum(da2)
-  c.s[1] = {m->da_in + 128, 256, 128, vec0, nullptr, 0};            // db1 = colsum(da1)
+  // db2 = colsum(da2), db1 = colsum(da1) (and db3 = colsum(d_out) without LayerNorm): per-(range, warp) partials formed by the producers of
+  // weight-gradient jobs 1, 2 (and 0) as the rows passed through them
+  const int nr16 = p.nranges * WG_NPW;
+  const size_t cs_stride = (size_t)nr16 * 128;
+  c.s[0] = {nullptr, 0, 128, vec0 + 128, p.csum + cs_stride, nr16};
+  c.s[1] = {nullptr, 0, 128, vec0, p.csum + 2 * cs_stride, nr16};
   if (m->ln_w) {
     // db3 = colsum(dz), dLN_w = colsum(d_out * xhat), dLN_b = colsum(d_out): per-block partials formed by fvgn_ln_bwd (`gxhat` = that buffer)
     const int lnb = ln_bwd_blocks(rows);
@@ -1962,12 +1987,10 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
     c.s[3] = {nullptr, 0, 128, vec0 + 384, gxhat + (size_t)lnb * 128, lnb};
     c.s[4] = {nullptr, 0, 128, vec0 + 512, gxhat + (size_t)2 * lnb * 128, lnb};
   } else {
-    c.s[2] = {d_out, ld_dout, m->n_out, vec0 + 256, nullptr, 0};    // db3 = colsum(d_out)
+    c.s[2] = {nullptr, 0, m->n_out, vec0 + 256, p.csum, nr16};      // db3 = colsum(d_out)
     c.s[3] = {nullptr, 0, 0, 0, nullptr, 0};
     c.s[4] = {nullptr, 0, 0, 0, nullptr, 0};
   }
-  colsum_kernel<<<dim3(c.nb, m->ln_w ? 2 : 3), 512, 0, st>>>(c);
-  FVGN_LAUNCH_CHECK();
   colsum_reduce_kernel<<<5, 1024, 0, st>>>(c);
   FVGN_LAUNCH_CHECK();
   return 0;

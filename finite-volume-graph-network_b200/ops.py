@@ -650,7 +650,7 @@ def mlp_wgrad_x3(mlp: MlpRef, mode, d_out, dz, gxhat, z_saved, da, x=None, src0=
         _cf(src0, "src0"), _cf(src1, "src1"), _cell_table_ok(idx, src1, rows, "mlp_wgrad_x3")
     else:
         _cf(src0, "src0"), _cf(src1, "src1"), _ci(idx, "idx")
-    _count(4)
+    _count(3)  # wgrad, range reduction, column-sum finish
     with _zsave(mlp, z_saved, rows, da), _bwd_products(mlp):
         check(L.fvgn_mlp_wgrad_x3(C.byref(mlp.struct), mode, _p(x), _ld(x) if x is not None else 0, _p(src0), _p(src1), _p(idx), rows, _p(d_out),
                                   _ld(d_out), _p(dz), _p(gxhat), _p(grads), _p(ws), _stream()), "mlp_wgrad_x3")
