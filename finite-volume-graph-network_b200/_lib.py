@@ -40,6 +40,7 @@ _SIGS = {
     "fvgn_mlp_pack_bf16x3_many": (_I, [C.POINTER(MlpT), _I, _P]),
     "fvgn_mlp_packed_x3_bwd_bytes": (_S, [_I]),
     "fvgn_mlp_pack_bf16x3_bwd": (_I, [C.POINTER(MlpT), _P, _S, _P]),
+    "fvgn_mlp_pack_bf16x3_bwd_many": (_I, [C.POINTER(MlpT), _I, _P]),
     "fvgn_ln_bwd": (_I, [_P, _I, _P, _P, _I, _P, _P, _P]),
     "fvgn_ln_bwd_sums_floats": (_S, [_I]),
     "fvgn_mlp_wgrad_x3_workspace_floats": (_S, [_I]),

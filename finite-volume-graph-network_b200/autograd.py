@@ -167,6 +167,7 @@ class NetFunction(torch.autograd.Function):
         tc = z_dec is not None  # bf16x3 forward: the data-gradient chain runs on the tensor cores, the FFMA kernel keeps the TN products
         sq = _SideQueue(dev, WGRAD_SIDE_STREAM and tc)
         if tc:
+            ops.ensure_packed_bwd_many([m.mlp_ref() for m in network_mlps(model)])  # one launch instead of one per MLP before its dgrad
             da, g_e = ops.mlp_dgrad_x3(dec.mlp_ref(), g_dec, z_dec, want_dA=True)
             grads[id(dec)] = sq.wgrad(dec.mlp_ref(), 0, g_dec, None, None, z_dec, da, x=e_final, alive=(g_dec, z_dec, da, e_final))
         else:

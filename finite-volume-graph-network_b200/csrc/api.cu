@@ -47,6 +47,7 @@ int tc3_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
 int tc3_pack_many(const fvgn_mlp_t*, int, cudaStream_t);
 size_t tc3_packed_bwd_bytes(int k_in);
 int tc3_pack_bwd(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
+int tc3_pack_bwd_many(const fvgn_mlp_t*, int, cudaStream_t);
 int tc3_ln_bwd(const float*, int, const float*, const float*, int, float*, float*, cudaStream_t);
 size_t tc3_ln_bwd_sums_floats(int rows);
 size_t tc3_wgrad_workspace_floats(int k_in);
@@ -187,6 +188,11 @@ extern "C" int fvgn_edge_block_fwd_split(const fvgn_mlp_t* mlp, const void* x_pr
 }
 
 extern "C" size_t fvgn_mlp_packed_x3_bwd_bytes(int k_in) { return tc3_packed_bwd_bytes(k_in); }
+
+extern "C" int fvgn_mlp_pack_bf16x3_bwd_many(const fvgn_mlp_t* mlps, int n_mlps, fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  return tc3_pack_bwd_many(mlps, n_mlps, as_stream(stream));
+}
 
 extern "C" int fvgn_mlp_pack_bf16x3_bwd(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream) {
   if (int e = check_device()) return e;

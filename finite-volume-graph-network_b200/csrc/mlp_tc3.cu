@@ -1210,6 +1210,42 @@ __global__ void pack_tiles3_t_kernel(const PackTParams pp) {
   *reinterpret_cast<uint4*>(out + 2 * TILE_BYTES + off) = q2;
 }
 
+// The same for an array of MLPs in one launch (blockIdx.z = MLP; the jobs of an MLP are derived from its dimensions): a training step
+// re-packs every MLP's transposed tiles after the optimizer step.
+constexpr int PACK_MAX_JOBS = 48;  // MLPs per batched pack launch (forward and backward tiles)
+struct PackTMlp { const float* w1; const float* w2; const float* w3; unsigned char* out; int k_in, n_out; };
+struct PackTBatch { PackTMlp m[PACK_MAX_JOBS]; };
+__global__ void pack_tiles3_t_many_kernel(const __grid_constant__ PackTBatch b) {
+  const PackTMlp& mm = b.m[blockIdx.z];
+  const int nseg = (mm.k_in + 127) / 128, j = blockIdx.y;
+  if (j >= 2 + nseg) return;
+  PackTJob jb;
+  if (j == 0) jb = {mm.w3, 128, 0, 128, mm.n_out, 0};
+  else if (j == 1) jb = {mm.w2, 128, 0, 128, 128, 2};
+  else { const int seg = j - 2; jb = {mm.w1, mm.k_in, 128 * seg, min(128, mm.k_in - 128 * seg), 128, 4 + 2 * seg}; }
+  const float* __restrict__ W = jb.W;
+  const int ldw = jb.ldw, n0 = jb.n0, n_valid = jb.n_valid, k_valid = jb.k_valid, kt = 2;
+  unsigned char* __restrict__ out = mm.out + (size_t)jb.step0 * SLOT_BYTES;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (tile, n, chunk)
+  if (idx >= kt * 128 * 8) return;
+  const int c = idx & 7, n = (idx >> 3) & 127, t = idx >> 10;
+  uint4 q0, q1, q2;
+  uint32_t* a0 = reinterpret_cast<uint32_t*>(&q0);
+  uint32_t* a1 = reinterpret_cast<uint32_t*>(&q1);
+  uint32_t* a2 = reinterpret_cast<uint32_t*>(&q2);
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int k = t * KTILE + c * 8 + 2 * jj;
+    const float x = (n < n_valid && k < k_valid) ? W[(size_t)k * ldw + n0 + n] : 0.f;
+    const float y = (n < n_valid && k + 1 < k_valid) ? W[(size_t)(k + 1) * ldw + n0 + n] : 0.f;
+    split3_pair(x, y, a0[jj], a1[jj], a2[jj]);
+  }
+  const size_t off = (size_t)t * SLOT_BYTES + (size_t)n * 128 + (((uint32_t)c ^ ((uint32_t)n & 7u)) << 4);
+  *reinterpret_cast<uint4*>(out + off) = q0;
+  *reinterpret_cast<uint4*>(out + TILE_BYTES + off) = q1;
+  *reinterpret_cast<uint4*>(out + 2 * TILE_BYTES + off) = q2;
+}
+
 // =====================================================================================================================
 // Weight gradients of one MLP on the tensor cores (training with the bf16x3 forward):
 //   dW3 = dz^T . h2      dW2 = da2^T . h1      dW1[:, 128 s ..] = da1^T . A[:, 128 s ..]        (sums over the rows)
@@ -1633,7 +1669,6 @@ __global__ void __launch_bounds__(256) cell_mean_kernel(const float* __restrict_
 // byte image of the swizzled layout; the epilogue factor 1 / (ASCALE 2^s) goes to the header behind the last step.
 // blockIdx.z = MLP: all the MLPs whose weights an optimizer step changed are re-packed by ONE launch (33 per training step).
 struct PackFwdJob { const float* w[3]; unsigned char* out; int k_in, n_out; };
-constexpr int PACK_MAX_JOBS = 48;
 struct PackFwdBatch { PackFwdJob job[PACK_MAX_JOBS]; };
 __global__ void __launch_bounds__(1024) pack_fwd_h2_kernel(const __grid_constant__ PackFwdBatch batch) {
   __shared__ float s_max[32];
@@ -1880,6 +1915,25 @@ int tc3_pack_bwd(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t s
   }
   pack_tiles3_t_kernel<<<dim3(cdiv(2 * 1024, 256), 2 + nseg), 256, 0, st>>>(pp);
   FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+// every MLP of the array into its own m->packed_x3_bwd (each at least tc3_packed_bwd_bytes(k_in) large)
+int tc3_pack_bwd_many(const fvgn_mlp_t* mlps, int n, cudaStream_t st) {
+  using namespace x3;
+  FVGN_CHECK_ARG(n >= 0 && (n == 0 || mlps), "NULL pointer");
+  for (int i0 = 0; i0 < n; i0 += PACK_MAX_JOBS) {
+    const int nb = n - i0 < PACK_MAX_JOBS ? n - i0 : PACK_MAX_JOBS;
+    PackTBatch b;
+    for (int i = 0; i < nb; ++i) {
+      const fvgn_mlp_t* m = mlps + i0 + i;
+      FVGN_CHECK_ARG(m->k_in >= 1 && m->k_in <= 384 && m->n_out >= 1 && m->n_out <= 128, "bad mlp dims");
+      FVGN_CHECK_ARG(m->packed_x3_bwd && (reinterpret_cast<uintptr_t>(m->packed_x3_bwd) & 15) == 0, "packed_x3_bwd must be set and 16B aligned");
+      b.m[i] = {m->w1, m->w2, m->w3, reinterpret_cast<unsigned char*>(const_cast<void*>(m->packed_x3_bwd)), m->k_in, m->n_out};
+    }
+    pack_tiles3_t_many_kernel<<<dim3(cdiv(2 * 1024, 256), 5, nb), 256, 0, st>>>(b);
+    FVGN_LAUNCH_CHECK();
+  }
   return 0;
 }
 

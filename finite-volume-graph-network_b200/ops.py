@@ -194,6 +194,27 @@ class MlpRef:
         return self
 
 
+def ensure_packed_bwd_many(mlps):
+    """fvgn_mlp_pack_bf16x3_bwd_many: the transposed tiles of the data-gradient chain of every stale MlpRef in one launch"""
+    stale = []
+    for m in mlps:
+        ver = _weights_key(m.tensors)
+        if m.packed3b is None or m.packed3b_versions != ver:
+            stale.append((m, ver))
+    if not stale:
+        return
+    L = _lib.lib()
+    for m, _ in stale:
+        if m.packed3b is None:
+            m.packed3b = torch.empty(L.fvgn_mlp_packed_x3_bwd_bytes(m.k_in), dtype=torch.uint8, device=m.tensors[0].device)
+            m.struct.packed_x3_bwd = m.packed3b.data_ptr()
+    arr = (MlpT * len(stale))(*[m.struct for m, _ in stale])
+    _count((len(stale) + 47) // 48)
+    check(L.fvgn_mlp_pack_bf16x3_bwd_many(arr, len(stale), _stream()), "mlp_pack_bf16x3_bwd_many")
+    for m, ver in stale:
+        m.packed3b_versions = ver
+
+
 def ensure_packed_many(mlps, math_mode=2):
     """fvgn_mlp_pack_bf16x3_many: re-packs, in one launch, every MlpRef of `mlps` whose fp32 weights changed since its last pack (after an
     optimizer step: all of them).  The per-call MlpRef.ensure_packed(2) that follows finds them current."""

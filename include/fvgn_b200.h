@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FVGN_ABI_VERSION 8 /* v7: cells_node_T == NULL selects the mp_times = 1 CellBlock in every cell-block entry point; v8: fvgn_mlp_pack_bf16x3_many, fvgn_cell_mean, n_products = 3 */
+#define FVGN_ABI_VERSION 8 /* v7: cells_node_T == NULL selects the mp_times = 1 CellBlock in every cell-block entry point; v8: fvgn_mlp_pack_bf16x3_many, fvgn_mlp_pack_bf16x3_bwd_many, fvgn_cell_mean, fvgn_ln_bwd column-sum partials, n_products = 3 */
 #define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
 
 #define FVGN_E_BADARG (-1)
@@ -260,6 +260,8 @@ FVGN_API int fvgn_edge_block_bwd(const fvgn_mlp_t* mlp, const float* x_prime, co
  * followed by fvgn_*_bwd with mlp->da_in = da for the weight gradients. */
 FVGN_API size_t fvgn_mlp_packed_x3_bwd_bytes(int k_in);
 FVGN_API int fvgn_mlp_pack_bf16x3_bwd(const fvgn_mlp_t* mlp, void* packed, size_t packed_bytes, fvgn_stream_t stream);
+/* the same for an array of MLPs in one launch: mlps[i].packed_x3_bwd is the destination of MLP i */
+FVGN_API int fvgn_mlp_pack_bf16x3_bwd_many(const fvgn_mlp_t* mlps, int n_mlps, fvgn_stream_t stream);
 /*                       `ln_sums` (optional, fvgn_ln_bwd_sums_floats(rows) floats): per-row-range partial COLUMN SUMS of dz, d_out * xhat and
  *                       d_out — what db3, dLN_w and dLN_b are — formed in the same pass (d_out * xhat is never written, nothing is re-read) */
 FVGN_API size_t fvgn_ln_bwd_sums_floats(int rows);
