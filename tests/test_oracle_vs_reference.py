@@ -84,3 +84,44 @@ def test_mp_times_1_eval_live(ref):
         on1, oe1, oc1, _, _ = O.valid_datapreprocessing(on1, oe1, oc1, 0)
         _, nuv1 = O.FVGNOracle(model.state_dict(), params)(oc1, oe1, on1, 1.0, 1e-3, 0.01, 9, 0)
     assert not torch.allclose(nuv1, nuv2)
+
+
+@pytest.mark.parametrize("mp_times", [1, 2])
+def test_training_loss_and_gradients_live(ref, mp_times):
+    """training mode, live: the reference's FVGN.forward (train) + compute_FVM_loss + backward against torch autograd over the oracle on
+    the same batch, noise and flips — loss and every parameter gradient, for the default network and the mp_times=1 variant"""
+    from oracle import make_golden as MG
+
+    params = RL.default_params(train_traj_length=2, mp_times=mp_times, loss="global_mean_sum")
+    meshes = [S.make("tiny", seed=31 + i, T=4) for i in range(2)]
+    Rs = [RL.ref_extract_mesh_state(m["mesh_pos"], m["cells"], m["node_type"], m["velocity"], m["pressure"]) for m in meshes]
+    dp = RL.ref_data_pool(Rs, params, is_training=True)
+    model = MG.new_model(ref, params, 0).train()
+    gn, ge, gc, mi, mb, noise, flip = MG.train_batch(ref, dp, params, [(0, 1), (1, 0)], 321)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    res = model(graph=gc, graph_edge=ge, graph_node=gn, rho=1.0, mu=1e-3, dt=0.01, edge_one_hot=9, cell_one_hot=0, device="cpu")
+    loss = ref.compute_FVM_loss(params=params, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=res[3],
+                                target_face_uvp_normalized=res[4], predicted_delta_u=res[1], target_delta_u=res[2],
+                                loss_function=torch.nn.MSELoss(reduction="mean"))
+    loss[0].backward()
+    want = {k: p.grad for k, p in model.named_parameters()}
+    # oracle on the same inputs
+    orc = O.FVGNOracle(sd0, params).train()
+    for k, v in list(orc.sd.items()):
+        if v.is_floating_point() and ("model." in k or k in ("_grid_feature_normalizer.weight", "_grid_feature_normalizer.bias")):
+            orc.sd[k] = v.clone().requires_grad_(True)
+    orc.bn["weight"], orc.bn["bias"] = orc.sd["_grid_feature_normalizer.weight"], orc.sd["_grid_feature_normalizer.bias"]
+    bags = []
+    for R, m, pair in zip(Rs, meshes, (1, 0)):
+        T = {k: (v[0] if v.ndim > 0 and v.shape[0] == 1 else v) for k, v in R.items()}
+        bags.append(O.build_graphs(T, m["velocity"], m["pressure"], training_pair=pair))
+    on, oe, oc = [O.batch_graphs([b[k] for b in bags]) for k in range(3)]
+    on, oe, oc, omi, omb = O.train_datapreprocessing(on, oe, oc, noise, flip)
+    out = orc(oc, oe, on, 1.0, 1e-3, 0.01, 9, 0)
+    oloss = O.compute_fvm_loss(params, oc.batch, oe.batch, omi, out[3], out[4], out[1], out[2], num_graphs=2)
+    oloss[0].backward()
+    assert abs(float(oloss[0].detach()) - float(loss[0].detach())) < 1e-6
+    got = {k: v.grad for k, v in orc.sd.items() if v.requires_grad}
+    assert set(got) == set(want)
+    for k, w in want.items():
+        assert H.rel_l2(got[k], w) < 1e-5, (k, H.rel_l2(got[k], w))
