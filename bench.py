@@ -48,8 +48,33 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
 
-    def _run(self):
+    def _run_nvml(self):
+        """in-process NVML polling every ~5 ms (the timed region of the default workload is ~50 ms: one nvidia-smi process per sample sees it
+        once); returns False when NVML is not usable, and the nvidia-smi loop takes over"""
+        try:
+            import pynvml as N
+
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), reasons_fn(h)  # probe once before committing to this path
+        except Exception:
+            return False
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
         while not self.stop.is_set():
+            try:
+                sm, r = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), int(reasons_fn(h))
+                self.rows.append([str(sm), str(mx), ""] + ["Active" if r & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self.stop.wait(0.005)
+        return True
+
+    def _run(self):
+        if self._run_nvml() and self.rows:
+            return
+        while True:  # at least one nvidia-smi sample even if the region has already ended
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -57,7 +82,8 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            if self.stop.wait(0.2):
+                break
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
