@@ -125,3 +125,17 @@ def test_training_loss_and_gradients_live(ref, mp_times):
     assert set(got) == set(want)
     for k, w in want.items():
         assert H.rel_l2(got[k], w) < 1e-5, (k, H.rel_l2(got[k], w))
+
+
+@pytest.mark.parametrize("seed", range(40, 52))
+def test_connectivity_live_random_small_meshes(ref, seed):
+    """a sweep of small random meshes of every generator (both face-typing rules): the oracle's tables against the live reference"""
+    kind = ("cyl", "rect", "naca", "grid")[seed % 4]
+    kw = dict(n_target=260 + 17 * (seed % 5)) if kind != "grid" else dict(nx=9 + seed % 7, ny=6 + seed % 5, jitter=0.3)
+    m = S.make(kind, seed=seed, **kw)
+    rule = "AB"[seed % 2]
+    R = RL.ref_extract_mesh_state(m["mesh_pos"], m["cells"], m["node_type"], m["velocity"], m["pressure"], face_rule=rule)
+    T = O.build_connectivity(m["mesh_pos"], m["cells"], m["node_type"], face_rule=rule)
+    for k in ["cells_node", "face", "cells_face", "neighbour_cell", "face_type", "cells_type", "centroid", "cell_factor", "face_length", "unit_norm_v"]:
+        assert np.array_equal(R[k][0], T[k]), (kind, seed, k)
+    np.testing.assert_allclose(T["cells_area"], R["cells_area"][0], rtol=3e-7, atol=0)
