@@ -23,6 +23,7 @@ SOURCES = {
     "mlp_simt.cu": [],
     "mlp_tc.cu": [],
     "mlp_tc3.cu": ["--fmad=false"],
+    "mlp_tc3_bwd.cu": ["--fmad=false"],
     "mlp_bwd.cu": [],
     "connectivity.cu": ["--fmad=false"],
     "prepost.cu": ["--fmad=false"],
