@@ -56,11 +56,15 @@ def test_mp_times_1_rollout_all_math_modes(fv, golden, fixture, steps):
     g = golden(fixture)
     want = _oracle_rollout(g, steps)
     two = O.FVGNOracle(H.load_state(H.torch_reference_state_dict(0), g), H.params()).eval()  # mp_times=2 on the same inputs: a different answer
+    ref_fixture = golden("fwd_tiny_mp1.npz") if fixture == "fwd_tiny.npz" else None  # the unmodified reference run with mp_times=1
     for math, tol in (("fp32", TOL), ("bf16x3", TOL), ("bf16", 3e-2)):
         got, _ = _cuda_rollout(fv, g, math, steps)
         for k, ((uvp, nuv), (ouvp, onuv)) in enumerate(zip(got, want)):
             assert H.rel_l2(nuv.cpu(), onuv) < tol * (k + 1), (math, k, H.rel_l2(nuv.cpu(), onuv))
             assert H.rel_l2(uvp.cpu(), ouvp) < tol * (k + 1), (math, k, H.rel_l2(uvp.cpu(), ouvp))
+            if ref_fixture is not None:
+                assert H.rel_l2(nuv.cpu(), ref_fixture["roll_uv"][k]) < 1.2 * tol * (k + 1), (math, k)
+                assert H.rel_l2(uvp.cpu(), ref_fixture["roll_uvp"][k]) < 1.2 * tol * (k + 1), (math, k)
     on, oe, oc = O.build_graphs(H.tables_from(g, "tab."), g["velocity"], g["pressure"])
     on, oe, oc, _, _ = O.valid_datapreprocessing(on, oe, oc, 0)
     with torch.no_grad():

@@ -105,3 +105,20 @@ def test_training_step(golden, loss_name, tag):
         if k.startswith(tag + ".grad."):
             name = k[len(tag) + 6:]
             assert H.rel_l2(orc.sd[name].grad, g[k]) < 1e-5, name
+
+
+def test_mp_times_1_rollout_against_reference_fixture(golden):
+    """the oracle's mp_times=1 CellBlock branch against 3 rollout steps of the unmodified reference run with mp_times=1 on fwd_tiny's mesh,
+    weights and primed state (oracle/make_golden_mp1.py) — and the fixture is NOT what mp_times=2 gives"""
+    g, g1 = golden("fwd_tiny.npz"), golden("fwd_tiny_mp1.npz")
+    sd = H.load_state(H.torch_reference_state_dict(0), g)
+    gn, ge, gc = _graphs(g)
+    gn, ge, gc, mi, mb = O.valid_datapreprocessing(gn, ge, gc, 0)
+    orc = O.FVGNOracle(sd, H.params(mp_times=1)).eval()
+    ct, Re, rmp = gc.x[:, 0:1].clone(), gc.x[:, 1:2].clone(), gc.edge_attr[:, 2:5].clone()
+    with torch.no_grad():
+        for step in range(3):
+            uvp, nuv = orc(gc, ge, gn, H.RHO, H.MU, H.DT, 9, 0)
+            assert H.rel_l2(nuv, g1["roll_uv"][step]) < 1e-6 and H.rel_l2(uvp, g1["roll_uvp"][step]) < 1e-6
+            O.create_next_graph(gc, ge, mb, nuv, ct, Re, rmp)
+    assert H.rel_l2(g["roll_uv"][0], g1["roll_uv"][0]) > 1e-3
