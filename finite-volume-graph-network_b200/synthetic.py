@@ -336,6 +336,52 @@ def grid_mesh(nx=61, ny=31, seed=0, T=3, jitter=0.25, hole=True, xlim=(0.0, 1.6)
                 meta=dict(kind="grid", seed=seed, nx=nx, ny=ny))
 
 
+def hybrid_mesh(nx=25, ny=17, seed=0, T=3, jitter=0.25, quad_fraction=0.5, hole=True, xlim=(0.0, 1.6), ylim=(0.0, 0.41)):
+    """Jittered structured mesh whose grid quads are either kept as QUADRILATERAL cells (probability `quad_fraction`) or split into two
+    triangles (random diagonal): a tri/quad hybrid in the shape BASELINE configs[3] names.  `cells` is int32 [C,4], 4th column -1 on
+    triangles, in random order.  The reference cannot read such a mesh (triangles only); oracle/fvgn_oracle_poly.py defines the tables."""
+    rng = np.random.default_rng(seed)
+    xmin, xmax = xlim
+    ymin, ymax = ylim
+    xs, ys = np.linspace(xmin, xmax, nx), np.linspace(ymin, ymax, ny)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    hx, hy = xs[1] - xs[0], ys[1] - ys[0]
+    ii, jj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    if hole:
+        i0, i1 = int(nx * 0.18), max(int(nx * 0.18) + 2, int(nx * 0.26))
+        j0, j1 = int(ny * 0.40), max(int(ny * 0.40) + 2, int(ny * 0.60))
+    else:
+        i0 = i1 = j0 = j1 = -10
+    on_hole = (ii >= i0) & (ii <= i1) & (jj >= j0) & (jj <= j1)
+    border = (ii == 0) | (ii == nx - 1) | (jj == 0) | (jj == ny - 1)
+    free = ~(border | on_hole)
+    X = X + np.where(free, jitter * hx * (rng.random(X.shape) - 0.5), 0.0)
+    Y = Y + np.where(free, jitter * hy * (rng.random(Y.shape) - 0.5), 0.0)
+    pos = np.stack([X.reshape(-1), Y.reshape(-1)], 1)
+    nid = jj * nx + ii
+    q_i, q_j = np.meshgrid(np.arange(nx - 1), np.arange(ny - 1), indexing="xy")
+    a, b = nid[q_j, q_i].reshape(-1), nid[q_j, q_i + 1].reshape(-1)
+    c, d = nid[q_j + 1, q_i + 1].reshape(-1), nid[q_j + 1, q_i].reshape(-1)
+    in_hole = ((q_i >= i0) & (q_i < i1) & (q_j >= j0) & (q_j < j1)).reshape(-1)
+    as_quad = (rng.random(a.shape[0]) < quad_fraction) & ~in_hole
+    flip = rng.random(a.shape[0]) < 0.5
+    minus = np.full(a.shape[0], -1)
+    t1 = np.where(flip[:, None], np.stack([a, b, d, minus], 1), np.stack([a, b, c, minus], 1))
+    t2 = np.where(flip[:, None], np.stack([b, c, d, minus], 1), np.stack([a, c, d, minus], 1))
+    tri = ~as_quad & ~in_hole
+    cells = np.concatenate([np.stack([a, b, c, d], 1)[as_quad], t1[tri], t2[tri]]).astype(np.int64)
+    cells = cells[rng.permutation(cells.shape[0])]
+    used = np.zeros(pos.shape[0], dtype=bool)
+    used[cells[cells >= 0]] = True
+    remap = np.cumsum(used) - 1
+    cells = np.where(cells >= 0, remap[np.maximum(cells, 0)], -1).astype(np.int32)
+    pos32 = pos[used].astype(np.float32)
+    nt = _box_types(pos32, np.float32(xmin), np.float32(xmax), np.float32(ymin), np.float32(ymax), on_hole.reshape(-1)[used])
+    vel, prs = fields(pos32, nt, T, seed, ymin, ymax)
+    return dict(mesh_pos=pos32, cells=cells, node_type=nt, velocity=vel, pressure=prs,
+                meta=dict(kind="hybrid", seed=seed, nx=nx, ny=ny, quads=int(as_quad.sum()), triangles=int(2 * tri.sum())))
+
+
 def make(kind, seed=0, T=3, **kw):
     if kind == "cyl":
         return cylinder_mesh(seed=seed, T=T, **kw)
@@ -345,6 +391,8 @@ def make(kind, seed=0, T=3, **kw):
         return airfoil_mesh(seed=seed, T=T, **kw)
     if kind == "grid":
         return grid_mesh(seed=seed, T=T, **kw)
+    if kind == "hybrid":
+        return hybrid_mesh(seed=seed, T=T, **kw)
     if kind == "tiny":
         return grid_mesh(nx=9, ny=7, seed=seed, T=T, **kw)
     if kind == "1m":

@@ -200,7 +200,7 @@ def batch_graphs(bags: list):
         n = g.num_nodes
         for k in cols:
             v = getattr(g, k)
-            cols[k].append(v + off if ("index" in k or k == "face") else v)
+            cols[k].append(torch.where(v >= 0, v + off, v) if ("index" in k or k == "face") else v)  # (-1 = padding of [4,C] polygon tables)
         bvec.append(torch.full((n,), gi, dtype=torch.long))
         off += n
     for k, vs in cols.items():
@@ -226,6 +226,8 @@ def valid_datapreprocessing(graph_node, graph_edge, graph_cell, start_epoch=0):
     target_on_cell = (cf[:, 0:1].unsqueeze(1) * torch.index_select(x, 0, graph_node.face[0])
                       + cf[:, 1:2].unsqueeze(1) * torch.index_select(x, 0, graph_node.face[1])
                       + cf[:, 2:3].unsqueeze(1) * torch.index_select(x, 0, graph_node.face[2]))
+    if graph_node.face.shape[0] == 4:  # tri/quad tables (oracle/fvgn_oracle_poly.py): 4th node, weight 0 / index -1 on triangles
+        target_on_cell = target_on_cell + cf[:, 3:4].unsqueeze(1) * torch.index_select(x, 0, graph_node.face[3].clamp(min=0))
     target_on_edge = (torch.index_select(x, 0, graph_node.edge_index[0])
                       + torch.index_select(x, 0, graph_node.edge_index[1])) / 2.0
     graph_cell.y = target_on_cell[:, start_epoch + 1:, :]
@@ -250,6 +252,8 @@ def train_datapreprocessing(graph_node, graph_edge, graph_cell, cell_noise, flip
     target_on_cell = (cf[:, 0:1] * torch.index_select(x, 0, graph_node.face[0])
                       + cf[:, 1:2] * torch.index_select(x, 0, graph_node.face[1])
                       + cf[:, 2:3] * torch.index_select(x, 0, graph_node.face[2]))
+    if graph_node.face.shape[0] == 4:
+        target_on_cell = target_on_cell + cf[:, 3:4] * torch.index_select(x, 0, graph_node.face[3].clamp(min=0))
     target_on_edge = (torch.index_select(x, 0, graph_node.edge_index[0])
                       + torch.index_select(x, 0, graph_node.edge_index[1])) / 2.0
     graph_cell.y = target_on_cell[:, 3:5]
@@ -354,6 +358,13 @@ def cell_block(sd, prefix, x, edge_attr, node_edge_index, node_face, num_nodes, 
         return mlp(sd, prefix + "net.", torch.cat((x, cell_agg), dim=-1))  # :140-143
     idx = torch.cat([node_edge_index[0], node_edge_index[1]], dim=0)  # :111-114
     node_agg = torch.zeros((num_nodes, twoway.shape[1]), dtype=x.dtype).index_add_(0, idx, twoway)  # :117-122
+    if node_face.shape[0] == 4:  # tri/quad tables: (a + b + c [+ d]) / k, the 4th term absent (index -1) on triangles
+        has4 = (node_face[3] >= 0).unsqueeze(1)
+        s = (torch.index_select(node_agg, 0, node_face[0]) + torch.index_select(node_agg, 0, node_face[1])
+             + torch.index_select(node_agg, 0, node_face[2]))
+        s = torch.where(has4, s + torch.index_select(node_agg, 0, node_face[3].clamp(min=0)), s)
+        cell_agg = s / torch.where(has4, 4.0, 3.0).to(s.dtype)
+        return mlp(sd, prefix + "net.", torch.cat((x, cell_agg), dim=-1))
     cell_agg = (torch.index_select(node_agg, 0, node_face[0]) + torch.index_select(node_agg, 0, node_face[1])
                 + torch.index_select(node_agg, 0, node_face[2])) / 3.0  # :125-129
     return mlp(sd, prefix + "net.", torch.cat((x, cell_agg), dim=-1))  # :140-143
@@ -390,6 +401,8 @@ def epd_forward(sd, prefix, x, edge_attr, edge_index, node_edge_index, node_face
 # a11. Intergrator: EncoderProcesserDecoder.py:251-331
 # ----------------------------------------------------------------------------------------------
 def integrator(uv_face, p_face, flux_D, unv, rho, rhs_coef, face_area, cell_face, loss_cont=0):
+    if cell_face.shape[0] == 4:
+        return _integrator_poly(uv_face, p_face, flux_D, unv, rho, rhs_coef, face_area, cell_face, loss_cont)
     e = [torch.index_select(face_area, 0, cell_face[k]) for k in range(3)]
     uu_vu = torch.cat((uv_face[:, 0:1] * uv_face, uv_face[:, 1:2] * uv_face), dim=-1)
 
@@ -409,6 +422,38 @@ def integrator(uv_face, p_face, flux_D, unv, rho, rhs_coef, face_area, cell_face
     P = (torch.index_select(p_face, 0, cell_face[0]) * unv[:, 0, :] * e[0]
          + torch.index_select(p_face, 0, cell_face[1]) * unv[:, 1, :] * e[1]
          + torch.index_select(p_face, 0, cell_face[2]) * unv[:, 2, :] * e[2])
+    return cont, rhs_coef * ((-A - (1.0 / rho) * P)) + D
+
+
+def _integrator_poly(uv_face, p_face, flux_D, unv, rho, rhs_coef, face_area, cell_face, loss_cont=0):
+    """the same sums over the k = 3 or 4 faces of a cell ([4,C] table, -1 = no 4th face; oracle/fvgn_oracle_poly.py): the first three terms
+    are added exactly as above, the 4th only where it exists"""
+    has4 = (cell_face[3] >= 0).unsqueeze(1)
+    cf = cell_face.clamp(min=0)
+    e = [torch.index_select(face_area, 0, cf[k]) for k in range(4)]
+    uu_vu = torch.cat((uv_face[:, 0:1] * uv_face, uv_face[:, 1:2] * uv_face), dim=-1)
+
+    def dot(a, b):
+        return torch.sum(a * b, dim=-1, keepdim=True)
+
+    def flux_dot(a, b):
+        return torch.cat([dot(a[:, i:i + 2], b) for i in range(0, a.size(1), 2)], dim=-1)
+
+    def plus4(s, t):
+        return torch.where(has4, s + t, s)
+
+    cont = 0
+    if loss_cont > 0:
+        cont = sum(dot(torch.index_select(uv_face, 0, cf[k]), unv[:, k, :]) * e[k] for k in range(3))
+        cont = plus4(cont, dot(torch.index_select(uv_face, 0, cf[3]), unv[:, 3, :]) * e[3])
+    A = (flux_dot(uu_vu[cf[0]], unv[:, 0, :]) * e[0] + flux_dot(uu_vu[cf[1]], unv[:, 1, :]) * e[1]
+         + flux_dot(uu_vu[cf[2]], unv[:, 2, :]) * e[2])
+    A = plus4(A, flux_dot(uu_vu[cf[3]], unv[:, 3, :]) * e[3])
+    D = (torch.index_select(flux_D, 0, cf[0]) + torch.index_select(flux_D, 0, cf[1]) + torch.index_select(flux_D, 0, cf[2]))
+    D = plus4(D, torch.index_select(flux_D, 0, cf[3]))
+    P = (torch.index_select(p_face, 0, cf[0]) * unv[:, 0, :] * e[0] + torch.index_select(p_face, 0, cf[1]) * unv[:, 1, :] * e[1]
+         + torch.index_select(p_face, 0, cf[2]) * unv[:, 2, :] * e[2])
+    P = plus4(P, torch.index_select(p_face, 0, cf[3]) * unv[:, 3, :] * e[3])
     return cont, rhs_coef * ((-A - (1.0 / rho) * P)) + D
 
 
