@@ -132,3 +132,42 @@ def test_reference_arm_prints_the_contract_line():
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0 and d["config"]["workload"] == "tiny"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_sass_of_the_tensor_core_kernels_is_blackwell_native():
+    """cuobjdump -sass of the built library: the fused MLP kernels issue tcgen05.mma (UTCHMMA), read / write TMEM (LDTM / STTM), stream their
+    weight tiles with cp.async.bulk (UBLKCP) and use mbarriers (SYNCS); no legacy HMMA anywhere; the strict path is FFMA.  (The mnemonics of
+    /opt/skills/guides/B200_PROFILING.md "What proves a Blackwell-native kernel"; skipped where cuobjdump is not installed.)"""
+    import re
+    import shutil
+    import subprocess
+
+    import fvgn_b200 as fv
+
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        sass = subprocess.run([exe, "-sass", fv._lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    except (FileNotFoundError, subprocess.TimeoutExpired):
+        pytest.skip("cuobjdump not available")
+    if "Function :" not in sass:
+        pytest.skip("cuobjdump printed no SASS")
+    per, cur = {}, None
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per[cur] = set()
+        elif cur:
+            per[cur].update(re.findall(r"\b(UTCHMMA|LDTM|STTM|UBLKCP|LDGSTS|SYNCS|HMMA|FFMA)\b", line))
+    assert not any("HMMA" in v for v in per.values()), "legacy mma.sync / wmma path found"
+    want = {"fused_mlp_tc_kernel": {"UTCHMMA", "LDTM", "STTM", "UBLKCP", "SYNCS"}, "fused_mlp_tc3_kernel": {"UTCHMMA", "LDTM", "STTM", "UBLKCP", "SYNCS"},
+            "dgrad_tc3_kernel": {"UTCHMMA", "LDTM", "STTM", "UBLKCP", "SYNCS"}, "wgrad_tc3_kernel": {"UTCHMMA", "LDTM", "SYNCS"},
+            "fused_mlp_simt_kernel": {"FFMA"}}
+    for name, need in want.items():
+        ks = [k for k in per if name in k]
+        assert ks, name
+        for k in ks:
+            assert need <= per[k], (k, need - per[k])
+    # the two-term backward variants move their rows with cp.async (the staging rings of this round)
+    assert any("wgrad_tc3_kernelILb0" in k and "LDGSTS" in v for k, v in per.items())
+    assert any("dgrad_tc3_kernelILb0" in k and "LDGSTS" in v for k, v in per.items())
