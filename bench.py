@@ -35,10 +35,26 @@ WORKLOADS = {
 }
 
 
-def params():
-    from tests.helpers import params as P
+def params(**over):
+    """the hot-path fields of the reference's utils/get_param.py:50-144 with their defaults (what train.py / rollout.py pass to FVGN)"""
+    import types
 
-    return P()
+    p = dict(edge_input_size=5, edge_one_hot=9, cell_input_size=2, cell_one_hot=0, dual_edge=False, message_passing_num=15,
+             cell_output_size=2, edge_output_size=5, drop_out=False, mp_times=2, multihead=1, nn_act="SiLU", loss_cont=0,
+             loss_mom=10, loss_face_uv=1, loss_face_p=1, loss="direct_mean_loss", cell_target_input_size=2,
+             face_flux_target_input_size=3, dataset_size=1000, batch_size=16, cumulative_length=600, grid_feature_size=1,
+             dataset_type="h5", n_epochs=1, train_traj_length=2, Noise_injection_factor=0.02, rho=RHO, mu=MU, dt=DT)
+    p.update(over)
+    return types.SimpleNamespace(**p)
+
+
+def config_of(workload, C, F, N, graphs, world):
+    """the `config` object — IDENTICAL in the native and the reference arm (same workload, same sizes, same step)"""
+    return {"workload": workload, "description": WORKLOADS[workload][3], "cells_per_rank": int(C), "faces_per_rank": int(F),
+            "nodes_per_rank": int(N), "graphs_per_rank": int(graphs), "message_passing_layers": 15, "hidden": 128,
+            "step": "one autoregressive rollout step: FVGN.forward (eval) + create_next_graph over the whole batch",
+            "l2": "GPU arms: flushed between timed steps (256 MiB write); CPU arm: not applicable",
+            "parallelism": f"replicas x{world} (independent mesh batches, no collective)"}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -333,10 +349,9 @@ def native(args, rank, world, local_rank):
             "metric": "cell_updates_per_sec", "value": m["total_cells"] * args.steps / (m["ms"] * 1e-3), "unit": "cell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": m["ms"] / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.math], "data": "synthetic",
-            "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "cells_per_rank": C, "faces_per_rank": F,
-                       "nodes_per_rank": N, "graphs_per_rank": len(meshes), "message_passing_layers": 15, "hidden": 128, "math": args.math,
-                       "step": "fv.GraphedRollout.step(): FVGN.forward (eval) + create_next_graph replayed from one CUDA graph", "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": f"replicas x{world} (independent mesh batches, no collective)"},
+            "config": config_of(args.workload, C, F, N, len(meshes), world),
+            "math_mode": args.math,
+            "implementation": "fv.GraphedRollout.step(): FVGN.forward (eval) + create_next_graph replayed from one CUDA graph of libfvgn_b200 kernels",
             "graphs_per_sec": len(meshes) * world * args.steps / (m["ms"] * 1e-3),
             "e2e": {"value": m["total_cells"] * args.steps / (m["e2e_ms"] * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": int(C * 16 + F * 20),
                     "d2h_bytes_per_step": int(C * 8 + F * 12), "ms_per_step": m["e2e_ms"] / args.steps,
@@ -345,21 +360,21 @@ def native(args, rank, world, local_rank):
             "clocks": m["clocks"],
             "roofline": roofline_of(m, args.math, args.workload),
         }
-    # ---- kernel roofline sweep (BASELINE configs[4]): the tcgen05 kernels on the 1M-cell mesh; its EdgeBlock kernel is the one the
-    # north star's ">= 50 % of HBM roofline" refers to, so it becomes the line's `roofline` (the default-mode kernel stays beside it)
+    # ---- kernel roofline sweep (BASELINE configs[4]): the tcgen05 kernels on the 1M-cell mesh, with its own roofline object under
+    # `sweep.roofline` (the line's `roofline` describes the kernel that produced the line's `value`)
     if args.sweep != "none" and tuple(args.sweep.split(":")) != (args.workload, args.math):
         sw_work, sw_math = args.sweep.split(":")
         sm = measure_forward(args, sw_work, sw_math, min(args.steps, 5), rank, local_rank, dev, dist)
         if rank == 0:
-            result["roofline_default_mode"] = result["roofline"]
-            result["roofline"] = roofline_of(sm, sw_math, sw_work)
+            sweep_roof = roofline_of(sm, sw_math, sw_work)
             result["sweep"] = {"workload": sw_work, "math": sw_math, "dtype": DTYPES[sw_math], "cells_per_rank": sm["C"], "faces_per_rank": sm["F"],
+                               "roofline": sweep_roof,
                                "value": sm["total_cells"] * sm["steps"] / (sm["ms"] * 1e-3), "unit": "cell-updates/s",
                                "ms_per_step": sm["ms"] / sm["steps"], "steps": sm["steps"],
                                "e2e": {"value": sm["total_cells"] * sm["steps"] / (sm["e2e_ms"] * 1e-3), "unit": "cell-updates/s"},
-                               "whole_step_roofline": {"bytes_per_cell_update": 64200, "peak": result["roofline"]["peak"], "unit": "GB/s",
+                               "whole_step_roofline": {"bytes_per_cell_update": 64200, "peak": sweep_roof["peak"], "unit": "GB/s",
                                                        "frac": 64200 * sm["total_cells"] * sm["steps"] / (sm["ms"] * 1e-3) / 1e9 / world
-                                                       / result["roofline"]["peak"]},
+                                                       / sweep_roof["peak"]},
                                "clocks": sm["clocks"], "gpu_launches": sm["launches"]}
         del sm
     if args.math != "fp32" and not args.no_strict_leg:
@@ -378,11 +393,29 @@ def native(args, rank, world, local_rank):
     if rank == 0:
         if train is not None:
             result["training"] = train
+        if not args.no_torch_eager and world == 1:
+            te = torch_eager_cuda(args, dev, args.steps)
+            result["torch_eager_cuda"] = te
+            if "unavailable" not in te:  # the speed-ups that matter: over the reference's own PyTorch path on the same GPU
+                sp = {f"rollout_vs_{k}": result["value"] / v["value"] for k, v in te["rollout"].items()}
+                if train is not None:
+                    sp.update({f"training_vs_{k}": train["value"] / v["value"] for k, v in te["training"].items()})
+                    sp.update({f"training_fresh_batches_vs_{k}": train["fresh_batches"]["value"] / v["value"] for k, v in te["training"].items()})
+                result["speedup_over_torch_eager_cuda"] = sp
         if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only: at N > 1 the other ranks' host threads share the cores
             result["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_seconds)
+    if dist is not None and (args.check or world == 2):
+        chk = dp_parity_check(rank, world, dev, dist)
+        if rank == 0:
+            result["dp_check"] = chk
+            if not chk["pass"]:
+                print(f"[bench] DATA-PARALLEL PARITY CHECK FAILED: {chk}", file=sys.stderr)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and result.get("dp_check", {}).get("pass") is False and args.check:
+        print(json.dumps(result))
+        sys.exit(3)
     return result
 
 
@@ -546,10 +579,98 @@ def training_measure(args, rank, world, dev, meshes, dist):
             "cuda_graph": graphed is not None}
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_setup(workload, n_graphs):
-    """The reference's torch-CPU path restated (oracle/fvgn_oracle.py, kind 'port': the reference itself is Python and is not
-    present on the GPU box).  Bounded sample: `n_graphs` meshes of the workload."""
+# ------------------------------------------------------------------------------------------------ data-parallel parity check
+def dp_parity_check(rank, world, dev, dist, graphs_per_rank=4):
+    """DP-N == single process (SURVEY §4 'distributed', §5): every rank trains one step on ITS `graphs_per_rank` meshes with the
+    statistic / loss / gradient collectives of fvgn_b200.parallel over NCCL, and — redundantly, collectives disabled — one step on the
+    WHOLE batch of N x graphs_per_rank meshes.  Strict fp32 kernels (deterministic), same weights, same noise / flip draws.
+    Compared on every rank: loss, all 266 gradients, the four normalisers' buffers, the face-area BatchNorm running statistics, for
+    both loss flavours the reference trains with (global_mean_sum = get_param.py default; direct_mean_loss = run_train.sh:17, whose
+    single log over the batch means needs the partial sums reduced before the log)."""
+    import fvgn_b200 as fv
+    from fvgn_b200 import parallel
+
+    n = graphs_per_rank
+    lists, sizes = [], []
+    for r in range(world):
+        for i in range(n):
+            m = fv.synthetic.make("cyl", seed=5000 + 1000 * r + i, T=3)
+            t = lambda a, dt: torch.as_tensor(a).to(dt).to(dev)
+            tab = fv.ops.build_connectivity(t(m["cells"], torch.int32), t(m["mesh_pos"], torch.float32), t(m["node_type"], torch.int32), "B")
+            lists.append(fv.dataset.build_graphs(tab, m["velocity"], m["pressure"], training_pair=0, device=dev))
+            sizes.append((int(tab["cells_node"].shape[0]), int(tab["face"].shape[1])))
+    Ct, Ft = sum(c for c, _ in sizes), sum(f for _, f in sizes)
+    gen = torch.Generator().manual_seed(123)
+    noise = (torch.randn((Ct, 2), generator=gen) * 0.02).to(dev)
+    flip = (torch.rand(Ft, generator=gen) < 0.5).to(dev)
+    c0 = sum(c for c, _ in sizes[:rank * n]); c1 = c0 + sum(c for c, _ in sizes[rank * n:(rank + 1) * n])
+    f0 = sum(f for _, f in sizes[:rank * n]); f1 = f0 + sum(f for _, f in sizes[rank * n:(rank + 1) * n])
+    out = {"graphs_per_rank": n, "world": world, "cells_total": Ct, "math": "fp32 (strict FFMA, deterministic)", "losses": {}}
+
+    def one_step(model, p, sel, cn, fk):
+        gn, ge, gc = fv.dataset.collate([[_shallow(b) for b in lists[i]] for i in sel])
+        gn, ge, gc, mi, mb = fv.dataset.train_datapreprocessing([gn, ge, gc], cell_noise=cn, flip_keep=fk)
+        o = model(graph=gc, graph_edge=ge, graph_node=gn, rho=RHO, mu=MU, dt=DT, edge_one_hot=9, cell_one_hot=0)
+        lo = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=o[3],
+                                 target_face_uvp_normalized=o[4], predicted_delta_u=o[1], target_delta_u=o[2])
+        lo[0].backward()
+        return lo[0].detach()
+
+    def buffers(model):
+        b = {f"{nm}.{k}": getattr(getattr(model, nm), k).detach().double().reshape(-1) for nm in parallel.NORMALIZERS
+             for k in ("acc_sum", "acc_sum_squared", "acc_count", "num_accumulations")}
+        bn = model._grid_feature_normalizer
+        b["bn.running_mean"], b["bn.running_var"] = bn.running_mean.double(), bn.running_var.double()
+        return b
+
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-30))
+    ok = True
+    for loss_name in ("global_mean_sum", "direct_mean_loss"):
+        p = params(loss=loss_name)
+        torch.manual_seed(0)
+        ref = fv.FVGN(device="cpu", params=p).to(dev).train().set_math_mode("fp32")
+        with parallel.single_process():
+            l_ref = one_step(ref, p, range(world * n), noise, flip)
+        torch.manual_seed(0)
+        dp = fv.FVGN(device="cpu", params=p).to(dev).train().set_math_mode("fp32")
+        l_dp = one_step(dp, p, range(rank * n, (rank + 1) * n), noise[c0:c1], flip[f0:f1])
+        parallel.GradBucket(dp.parameters()).all_reduce_mean_()
+        l_mean = l_dp.clone().reshape(1)
+        dist.all_reduce(l_mean)
+        l_mean /= world
+        g_err = max(rel(a.grad, b.grad) for a, b in zip(dp.parameters(), ref.parameters()))
+        b_dp, b_ref = buffers(dp), buffers(ref)
+        b_err = max(rel(b_dp[k], b_ref[k]) for k in b_ref)
+        l_err = abs(float(l_mean) - float(l_ref))
+        errs = torch.tensor([g_err, b_err, l_err], dtype=torch.float64, device=dev)
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        out["losses"][loss_name] = {"loss_single_process": float(l_ref), "loss_dp_mean_over_ranks": float(l_mean), "loss_abs_err": float(errs[2]),
+                                    "worst_gradient_rel_l2": float(errs[0]), "worst_buffer_rel_l2": float(errs[1])}
+        ok = ok and float(errs[0]) < 1e-5 and float(errs[1]) < 1e-6 and float(errs[2]) < 1e-5
+    out["tolerance"] = {"gradients_rel_l2": 1e-5, "buffers_rel_l2": 1e-6, "loss_abs": 1e-5}
+    out["pass"] = bool(ok)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arms
+# The reference's own implementation of the path (the UNMODIFIED FVGN-src/main modules: /root/reference in the build container, the
+# byte-for-byte copy oracle/make_ref.py places under the git-ignored oracle/_ref/ on the GPU box) driven through its own Data_Pool /
+# FVGN / compute_FVM_loss objects by oracle/ref_harness.py — on the host cores (`--impl reference`, `cpu_baseline`: kind "reference")
+# and on the GPU (`torch_eager_cuda`: what a user of the reference runs on a B200 today).  Where the copy is missing the CPU arm falls
+# back to the oracle port (oracle/fvgn_oracle.py, kind "port").  These legs are the only place bench.py executes anything under oracle/.
+def _ref_harness(workload, n_graphs, device, loss="global_mean_sum"):
+    import fvgn_b200 as fv
+    from oracle import ref_harness as RH
+
+    if not RH.available():
+        return None
+    kind, kw, _, _ = WORKLOADS[workload]
+    meshes = [fv.synthetic.make(kind, seed=i, T=3, **kw) for i in range(n_graphs)]  # rank 0's meshes of the native arm
+    return RH.RefHarness(meshes, params(), device=device, loss=loss)
+
+
+def cpu_setup_port(workload, n_graphs):
+    """fallback CPU arm (kind "port"): the reference's torch-CPU path restated (oracle/fvgn_oracle.py, pinned against the reference)"""
     import fvgn_b200 as fv
     from oracle import fvgn_oracle as O
     from tests import helpers as H
@@ -562,7 +683,7 @@ def cpu_setup(workload, n_graphs):
         bags.append(O.build_graphs(tab, m["velocity"], m["pressure"]))
     gn, ge, gc = [O.batch_graphs([b[k] for b in bags]) for k in range(3)]
     gn, ge, gc, mi, mb = O.valid_datapreprocessing(gn, ge, gc, 0)
-    orc = O.FVGNOracle(H.torch_reference_state_dict(0), H.params()).eval()
+    orc = O.FVGNOracle(H.torch_reference_state_dict(0), params()).eval()
     ct, Re, rmp = gc.x[:, 0:1].clone(), gc.x[:, 1:2].clone(), gc.edge_attr[:, 2:5].clone()
 
     def step(gc=gc):
@@ -571,14 +692,24 @@ def cpu_setup(workload, n_graphs):
             O.create_next_graph(gc, ge, mb, nuv, ct, Re, rmp)
         return nuv
 
-    return step, gc.x.shape[0]
+    return step, gc.x.shape[0], ge.x.shape[0], gn.x.shape[0]
+
+
+def _cpu_arm(workload, n_graphs):
+    """(kind, rollout_step, train_step or None, C, F, N, description)"""
+    h = _ref_harness(workload, n_graphs, "cpu")
+    if h is not None:
+        return ("reference", h.rollout_step, h.train_step, h.C, h.F, int(h.gn.x.shape[0]),
+                "the UNMODIFIED reference (FVGN-src/main via oracle/_ref + shims for torch_geometric / torch_scatter)")
+    step, C, F, N = cpu_setup_port(workload, n_graphs)
+    return ("port", step, None, C, F, N, "oracle/fvgn_oracle.py (restatement of the reference's torch path, pinned against it)")
 
 
 def cpu_baseline(args, budget_s=15.0):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     n_graphs = WORKLOADS[args.workload][2]  # the whole batch of one rank: same workload as the GPU arm, bounded in the number of steps
-    step, C = cpu_setup(args.workload, n_graphs)
+    kind, step, tstep, C, F, N, what = _cpu_arm(args.workload, n_graphs)
     step()
     t0 = time.perf_counter()
     step()
@@ -588,20 +719,80 @@ def cpu_baseline(args, budget_s=15.0):
     for _ in range(n):
         step()
     dt = time.perf_counter() - t0
-    return {"value": C * n / dt, "unit": "cell-updates/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} rollout steps of {n_graphs} {WORKLOADS[args.workload][0]} mesh(es) ({C} cells) on the host CPU, torch {torch.__version__}, "
-                      f"{threads} threads; oracle/fvgn_oracle.py (restatement of the reference's torch path, pinned against it)",
-            "ms_per_step": dt / n * 1e3}
+    out = {"value": C * n / dt, "unit": "cell-updates/s", "cores": torch.get_num_threads(), "kind": kind,
+           "sample": f"{n} rollout steps of {n_graphs} {WORKLOADS[args.workload][0]} mesh(es) ({C} cells) on the host CPU, torch {torch.__version__}, "
+                     f"{threads} threads; {what}",
+           "ms_per_step": dt / n * 1e3}
+    if tstep is not None:  # the batch-16 training step of train.py:150-225 on the host cores (the metric's "training graphs/sec vs CPU torch")
+        tstep()
+        t0 = time.perf_counter()
+        tstep()
+        one = time.perf_counter() - t0
+        nt = int(max(2, min(20, budget_s / max(one, 1e-3))))
+        t0 = time.perf_counter()
+        for _ in range(nt):
+            tstep()
+        dtt = time.perf_counter() - t0
+        out["training"] = {"value": n_graphs * nt / dtt, "unit": "graphs/s", "ms_per_step": dtt / nt * 1e3, "cores": torch.get_num_threads(),
+                           "kind": kind, "sample": f"{nt} training steps (train_datapreprocessing + FVGN.forward + compute_FVM_loss + backward + AdamW, "
+                                                   f"train.py:150-225) on one batch of {n_graphs} meshes ({C} cells), loss global_mean_sum"}
+    return out
+
+
+def torch_eager_cuda(args, dev, steps):
+    """The reference's own PyTorch path on the B200 ("the bar is torch-eager on B200"): the unmodified reference modules
+    on `dev`, same 16 meshes / same initial weights, rollout step and batch-16 training step, in strict fp32 matmuls and with TF32 allowed
+    (what the authors' torch 1.9 did by default).  CUDA-event timed, L2 flushed between steps; outside the native timed regions."""
+    try:
+        h = _ref_harness(args.workload, WORKLOADS[args.workload][2], dev)
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    if h is None:
+        return {"unavailable": "oracle/_ref (copy of the reference made by oracle/make_ref.py in the build container) is not present"}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    out = {"impl": "UNMODIFIED reference modules (oracle/_ref) through their own Data_Pool / FVGN / compute_FVM_loss API on cuda; torch_scatter / "
+                   "torch_geometric replaced by index_add_ shims (oracle/shims); eager, one CUDA stream",
+           "torch": torch.__version__, "cells": h.C, "faces": h.F, "graphs": h.n_graphs, "rollout": {}, "training": {}}
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        torch.cuda.synchronize()
+        for k in range(n):
+            flush.zero_()
+            ev[k][0].record()
+            fn()
+            ev[k][1].record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ev) / n
+
+    try:
+        for leg, fn, per, unit in (("rollout", h.rollout_step, h.C, "cell-updates/s"), ("training", h.train_step, h.n_graphs, "graphs/s")):
+            for name, tf32 in (("fp32", False), ("tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+                if leg == "rollout":
+                    h.reset_rollout()
+                n = steps if leg == "rollout" else max(2, min(steps, args.train_steps))
+                ms = timed(fn, n)
+                out[leg][name] = {"value": per / (ms * 1e-3), "unit": unit, "ms_per_step": ms, "steps": n}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    del h, flush
+    torch.cuda.empty_cache()
+    return out
 
 
 def reference_arm(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port), all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, all host threads, on the native arm's config."""
     if rank != 0:
         return None
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     n_graphs = WORKLOADS[args.workload][2]  # the whole batch of one rank (the GPU arm's config), bounded in the number of steps
-    step, C = cpu_setup(args.workload, n_graphs)
+    kind, step, _, C, F, N, what = _cpu_arm(args.workload, n_graphs)
     for _ in range(max(1, min(args.warmup, 3))):
         step()
     t0 = time.perf_counter()
@@ -609,13 +800,12 @@ def reference_arm(args, rank, world):
         step()
     dt = time.perf_counter() - t0
     v = C * args.steps / dt
-    sample = f"{args.steps} rollout steps of {n_graphs} {WORKLOADS[args.workload][0]} mesh(es) ({C} cells): bounded sample of workload {args.workload}"
+    sample = (f"{args.steps} rollout steps of {n_graphs} {WORKLOADS[args.workload][0]} mesh(es) ({C} cells): bounded sample of workload {args.workload}; "
+              f"{what}; torch {torch.__version__}, {threads} threads")
     return {"impl": "reference", "metric": "cell_updates_per_sec", "value": v, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "sample_cells": C, "message_passing_layers": 15,
-                       "hidden": 128, "step": "FVGN.forward (eval) + create_next_graph"},
-            "cpu_baseline": {"value": v, "unit": "cell-updates/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": config_of(args.workload, C, F, N, n_graphs, world),
+            "cpu_baseline": {"value": v, "unit": "cell-updates/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
 
 
@@ -629,6 +819,8 @@ def main():
     ap.add_argument("--math", default="bf16x3", choices=["fp32", "bf16", "bf16x3"],
                     help="bf16x3 (default): fp32-equivalent tensor-core mode; fp32: strict FFMA; bf16: bf16 tiles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check", action="store_true", help="N > 1: run the data-parallel parity check (DP-N step == single-process batch; always on at N = 2) and exit 3 if it fails")
+    ap.add_argument("--no-torch-eager", action="store_true", help="skip the torch-eager CUDA leg (the unmodified reference on the GPU)")
     ap.add_argument("--no-training", action="store_true", help="skip the training graphs/s leg")
     ap.add_argument("--no-strict-leg", action="store_true", help="skip the strict-FFMA comparison leg")
     ap.add_argument("--no-config0", action="store_true", help="skip the batch-1 rollout latency leg (configs[0])")

@@ -44,11 +44,19 @@ class FVGN(nn.Module):
         self.set_math_mode("bf16x3")
 
     def set_math_mode(self, mode):
-        """'fp32' (strict, FFMA), 'bf16' (tcgen05 bf16 tiles, inference), 'bf16x3' (tcgen05, exact 3-way bf16 operand split:
-        fp32-equivalent, rel 1e-5/step, ~3x faster than FFMA)."""
+        """'fp32'   strict fp32 on the FFMA pipes (the reference's evaluation order per row);
+        'bf16x3' (default) fp32-equivalent on tcgen05: forward = two-term fp16 split of both operands, 3 MMAs per product (rel ~1e-6 per
+                 step, held to the 1e-5 bound; ~5x the FFMA path), backward = the three leading products of 3-way bf16 splits.  Range: the
+                 fp16 terms overflow for |activation| >= ~8190 — such a row turns NaN and sets the device status word, which
+                 `check_finite()` / GraphedRollout.run(check=True) / GraphedTrainStep.check() turn into a FloatingPointError;
+        'bf16'   plain bf16 tiles with fp32 accumulation (stated rollout-error bound, tests/test_gpu_rollout600.py)."""
         self.model.set_math_mode(mode)
         self.math_mode = mode
         return self
+
+    def check_finite(self):
+        """synchronises; raises FloatingPointError if a fp32-equivalent forward tile produced a non-finite row since the last check"""
+        ops.raise_if_nonfinite("forward")
 
     # -- feature assembly (FVGN.py:83-138): one-hot + normalise happen in one kernel, nothing is concatenated in HBM
     def update_cell_attr(self, frames, one_hot: int, types: torch.Tensor, accumulation=True, normalizer=None):
@@ -67,8 +75,17 @@ class FVGN(nn.Module):
     def _face_area(self, graph, graph_edge, topo, dt, want_raw=False):
         bn = self._grid_feature_normalizer
         use_batch_stats = self.training or not bn.track_running_stats
-        out, raw, stats = ops.face_area_bn_fwd(graph_edge.x, graph.cell_area, topo.nc, dt, use_batch_stats, bn.weight, bn.bias,
-                                               bn.running_mean, bn.running_var, want_raw=want_raw)
+        if use_batch_stats and parallel.is_distributed():
+            # data parallel (also under torch.no_grad(): the reference's pre_statistics rounds, train.py:170-185): batch statistics and
+            # running-stat updates are those of the WHOLE batch, as in autograd.NetFunction — the ranks' BatchNorm buffers stay identical
+            _, sums = ops.face_area_sums(graph_edge.x, graph.cell_area, topo.nc, dt)
+            gstats, mean, var, n = parallel.global_bn_stats(sums, topo.F)
+            parallel.update_running_stats_(bn, mean, var, n)
+            out, raw, stats = ops.face_area_bn_fwd(graph_edge.x, graph.cell_area, topo.nc, dt, True, bn.weight.detach(), bn.bias.detach(),
+                                                   bn.running_mean, bn.running_var, want_raw=want_raw, stats=gstats)
+        else:
+            out, raw, stats = ops.face_area_bn_fwd(graph_edge.x, graph.cell_area, topo.nc, dt, use_batch_stats, bn.weight, bn.bias,
+                                                   bn.running_mean, bn.running_var, want_raw=want_raw)
         if self.training:
             bn.num_batches_tracked += 1
         return out, raw, stats

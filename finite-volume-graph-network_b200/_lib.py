@@ -22,6 +22,7 @@ _SIGS = {
     "fvgn_abi_version": (C.c_int, []),
     "fvgn_last_error": (C.c_char_p, []),
     "fvgn_device_check": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "fvgn_status_read": (_I, [C.POINTER(C.c_uint), _I]),
     "fvgn_connectivity_workspace_bytes": (_S, [_I]),
     "fvgn_connectivity_faces": (_I, [_P, _I, _I, _P, C.POINTER(C.c_int), _P, _S, _P]),
     "fvgn_connectivity_tables": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S, _P]),
@@ -61,6 +62,8 @@ _SIGS = {
     "fvgn_integrator_fwd": (_I, [_P, _P, _P, _P, _I, _F, _F, _P, _P, _P]),
     "fvgn_loss_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P]),
     "fvgn_loss_workspace_floats": (_S, [_I]),
+    "fvgn_loss_partials": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "fvgn_loss_finish": (_I, [_I, _I, _F, _F, _F, _P, _P, _P]),
     "fvgn_mlp_grad_floats": (_S, [_I]),
     "fvgn_mlp_bwd_workspace_floats": (_S, [_I]),
     "fvgn_mlp_rows_bwd": (_I, [C.POINTER(MlpT), _P, _I, _I, _P, _I, _P, _I, _P, _P, _P]),
@@ -93,7 +96,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.fvgn_abi_version() != 8:
+        if L.fvgn_abi_version() != 9:
             raise RuntimeError("libfvgn_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -222,13 +222,21 @@ class LossFunction(torch.autograd.Function):
         m8 = mask.to(torch.uint8).contiguous()
         pred_du, target_du = pred_du.contiguous(), target_du.contiguous()
         pred_edge, target_face = pred_edge.contiguous(), target_face.contiguous()
-        out, ws = ops.loss_fwd(pred_du, target_du, pred_edge, target_face, m8, cell_batch, face_batch, n_graphs, mode, w_mom, w_uv, w_p)
+        # data parallel + direct_mean_loss: the numerators / denominators of the three batch means are summed over the ranks before the
+        # log, so every rank holds the single-process loss; the per-element gradient then is the single-process one,
+        # and since the gradient bucket is AVERAGED over the ranks the incoming gradient is scaled by the world size in backward
+        dp = mode == 0 and parallel.is_distributed()
+        out, ws = ops.loss_fwd(pred_du, target_du, pred_edge, target_face, m8, cell_batch, face_batch, n_graphs, mode, w_mom, w_uv, w_p,
+                               reduce_partials=parallel.all_reduce_sum_ if dp else None)
         ctx.args = (pred_du, target_du, pred_edge, target_face, m8, cell_batch, face_batch, n_graphs, mode, w_mom, w_uv, w_p, ws)
+        ctx.gscale = float(parallel.world_size()) if dp else 1.0
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         pred_du, target_du, pred_edge, target_face, m8, cb, fb, n_graphs, mode, w_mom, w_uv, w_p, ws = ctx.args
         g_loss = g_out[0:1].contiguous()  # only out[0] (the loss) is a differentiable quantity; stays on the device
+        if ctx.gscale != 1.0:
+            g_loss = g_loss * ctx.gscale
         g_du, g_edge = ops.loss_bwd(pred_du, target_du, pred_edge, target_face, m8, cb, fb, n_graphs, mode, w_mom, w_uv, w_p, g_loss, ws)
         return (g_du, None, g_edge) + (None,) * 9

@@ -15,10 +15,12 @@ void set_error(const char* fmt, ...) {
 }
 
 int sm_count() {
-  static int n = 0;
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& n = cached[dev & 63];
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
   return n;
@@ -42,6 +44,7 @@ int tc3_cell_mean_split(const float*, const int32_t*, int, void*, cudaStream_t);
 int tc3_cell_mean(const float*, const int32_t*, int, float*, cudaStream_t);
 int tc3_cell_block_sh(const fvgn_mlp_t*, float*, const void*, int, void*, cudaStream_t);
 int tc3_edge_block_sh(const fvgn_mlp_t*, const void*, float*, const int32_t*, int, cudaStream_t);
+int tc3_status_read(unsigned int*, int);
 size_t tc3_packed_bytes(int k_in);
 int tc3_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
 int tc3_pack_many(const fvgn_mlp_t*, int, cudaStream_t);
@@ -81,6 +84,8 @@ using namespace fvgn;
 
 extern "C" int fvgn_abi_version(void) { return FVGN_ABI_VERSION; }
 extern "C" const char* fvgn_last_error(void) { return g_err; }
+
+extern "C" int fvgn_status_read(unsigned int* status_host, int clear) { return tc3_status_read(status_host, clear); }
 
 extern "C" int fvgn_device_check(int* sm, int* major, int* minor) {
   int dev = 0, a = 0, b = 0, n = 0;

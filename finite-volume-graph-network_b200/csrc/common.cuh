@@ -38,6 +38,18 @@ void set_error(const char* fmt, ...);
 static inline cudaStream_t as_stream(fvgn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int sm_count();
+// cudaFuncSetAttribute (the dynamic shared-memory opt-in) is per DEVICE, not per process: first() is true once per device
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 // CellBlock second aggregation (GN_blocks.py:110-138), 4 columns of one cell's 64-wide aggregate.  idx != NULL (mp_times >= 2): mean of

@@ -569,10 +569,9 @@ static int launch_bwd(BwdParams& p, float* grads, float* workspace, cudaStream_t
   p.part_stride = part_stride_of(p.mlp.k_in);
   p.part = workspace;
   const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
-  static bool configured = false;
-  if (!configured) {
+  static ::fvgn::PerDeviceOnce configured;
+  if (configured.first()) {
     FVGN_CUDA(cudaFuncSetAttribute(mlp_bwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes()));
-    configured = true;
   }
   mlp_bwd_simt_kernel<<<grid, NT, bwd_smem_bytes(), st>>>(p);
   FVGN_LAUNCH_CHECK();

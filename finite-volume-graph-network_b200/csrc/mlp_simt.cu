@@ -180,10 +180,9 @@ template <int MODE, int KPAD>
 static int launch_simt(const SimtParams& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
   constexpr size_t smem = simt_smem_bytes<KPAD>();
-  static bool configured = false;  // per (MODE,KPAD) instantiation
-  if (!configured) {
+  static ::fvgn::PerDeviceOnce configured;  // per (MODE,KPAD) instantiation
+  if (configured.first()) {
     FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_simt_kernel<MODE, KPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   fused_mlp_simt_kernel<MODE, KPAD><<<cdiv(p.rows, BM), NT, smem, st>>>(p);
   FVGN_LAUNCH_CHECK();

@@ -740,10 +740,9 @@ static int launch_tc(TcParams& p, const fvgn_mlp_t* m, cudaStream_t st) {
   const bool xbf = (p.mode == TC_CELL && p.xbf_out) || (p.mode == TC_EDGE && p.xbf_in);
 #define FVGN_TC_LAUNCH(MODE, RED, XBF)                                                                                           \
   do {                                                                                                                           \
-    static bool configured = false;                                                                                              \
-    if (!configured) {                                                                                                           \
+    static ::fvgn::PerDeviceOnce configured;                                                                                              \
+    if (configured.first()) {                                                                                                           \
       FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc_kernel<MODE, RED, XBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MODE))); \
-      configured = true;                                                                                                         \
     }                                                                                                                            \
     fused_mlp_tc_kernel<MODE, RED, XBF><<<grid, NTHREADS, smem_bytes(MODE), st>>>(p);                                            \
   } while (0)

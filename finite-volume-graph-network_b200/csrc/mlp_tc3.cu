@@ -29,6 +29,11 @@
 namespace fvgn {
 namespace x3 {
 
+// Device status word (one per device: a __device__ variable is instantiated per context).  bit 0: a row of a fp32-equivalent forward
+// tile came out non-finite — the fp16 operand terms overflow for |activation| >= ~8190 (tc3_common.cuh: ASCALE), inf turns the row into
+// NaN, and NaN reaches the row's last-layer statistics.  One compare per row and launch; read / cleared by fvgn_status_read.
+__device__ unsigned int g_status = 0;
+
 template <int MODE, bool RED, bool SH>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -485,6 +490,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         sRed[256 + h * 128 + erow] = qv;
         named_bar_sync(1, NEPI);
         rstd = 1.0f / sqrtf((sRed[256 + erow] + sRed[256 + 128 + erow]) * (1.0f / 128.0f) + 1e-5f);
+        if (h == 0 && !(rstd * 0.0f == 0.0f) && row0 + erow < p.rows) atomicOr(&g_status, 1u);  // inf / NaN anywhere in the row
       }
       const float* res = (MODE == TC_CELL) ? p.src0 : p.src1;
 #pragma unroll 1
@@ -549,11 +555,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         } else {
           const int grow = row0 + erow;
           if (grow < p.rows) {
+            float acc0 = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int col = 16 * sc + j;
-              if (col < p.n_out) p.out0[(size_t)grow * p.ld_out + col] = v[j];
+              if (col < p.n_out) { p.out0[(size_t)grow * p.ld_out + col] = v[j]; acc0 += v[j] * 0.0f; }
             }
+            if (!has_ln && !(acc0 == 0.0f)) atomicOr(&g_status, 1u);  // decoder rows (no LayerNorm statistics to look at)
           }
         }
       }
@@ -715,6 +723,18 @@ extern "C" __attribute__((visibility("default"))) int fvgn_dbg_x3_prof(unsigned 
 }
 #endif
 
+// synchronous: waits for the device, returns the status word and (optionally) clears it
+int tc3_status_read(unsigned int* out_host, int clear) {
+  FVGN_CHECK_ARG(out_host != nullptr, "NULL pointer");
+  FVGN_CUDA(cudaDeviceSynchronize());
+  FVGN_CUDA(cudaMemcpyFromSymbol(out_host, x3::g_status, sizeof(unsigned int)));
+  if (clear && *out_host) {
+    const unsigned int z = 0;
+    FVGN_CUDA(cudaMemcpyToSymbol(x3::g_status, &z, sizeof(z)));
+  }
+  return 0;
+}
+
 static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t st, bool sh = false) {
   using namespace x3;
   if (p.rows <= 0) return 0;
@@ -734,10 +754,9 @@ static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t
   const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
 #define FVGN_TC3_LAUNCH(MODE, RED, SH)                                                                                   \
   do {                                                                                                                   \
-    static bool configured = false;                                                                                      \
-    if (!configured) {                                                                                                   \
+    static ::fvgn::PerDeviceOnce configured;                                                                                      \
+    if (configured.first()) {                                                                                                   \
       FVGN_CUDA(cudaFuncSetAttribute(fused_mlp_tc3_kernel<MODE, RED, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
-      configured = true;                                                                                                 \
     }                                                                                                                    \
     fused_mlp_tc3_kernel<MODE, RED, SH><<<grid, NTHREADS, L.total, st>>>(p);                                             \
   } while (0)

@@ -946,11 +946,10 @@ int tc3_dgrad(const fvgn_mlp_t* m, const float* dz, int ld_dz, int rows, float* 
   p.packed = reinterpret_cast<const unsigned char*>(m->packed_x3_bwd);
   p.nprod = m->n_products == 1 ? 1 : (m->n_products == 3 ? 3 : 6);
   const SmemLayout L = smem_layout();
-  static bool configured = false;
-  if (!configured) {
+  static ::fvgn::PerDeviceOnce configured;
+  if (configured.first()) {
     FVGN_CUDA(cudaFuncSetAttribute(dgrad_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     FVGN_CUDA(cudaFuncSetAttribute(dgrad_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    configured = true;
   }
   const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
   if (p.nprod > 3) dgrad_tc3_kernel<true><<<grid, NTHREADS, L.total, st>>>(p);
@@ -992,11 +991,10 @@ int tc3_wgrad(const fvgn_mlp_t* m, int mode, const float* in, int ld_in, const f
   p.csum_job0 = m->ln_w ? 0 : 1;
   p.nprod = m->n_products == 1 ? 1 : (m->n_products == 3 ? 3 : 6);
   const int smem_bytes = p.nprod > 3 ? WgLayout<true>::TOTAL : WgLayout<false>::TOTAL;
-  static bool configured = false;
-  if (!configured) {
+  static ::fvgn::PerDeviceOnce configured;
+  if (configured.first()) {
     FVGN_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgLayout<true>::TOTAL));
     FVGN_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgLayout<false>::TOTAL));
-    configured = true;
   }
   if (p.nprod > 3) wgrad_tc3_kernel<true><<<p.njobs * p.nranges, WG_NTHREADS, smem_bytes, st>>>(p);
   else wgrad_tc3_kernel<false><<<p.njobs * p.nranges, WG_NTHREADS, smem_bytes, st>>>(p);

@@ -544,23 +544,40 @@ extern "C" size_t fvgn_loss_workspace_floats(int n_graphs) {
   return 2 * (g * LOSS_CHUNKS * 6) + 4 * g + 8;
 }
 
-extern "C" int fvgn_loss_fwd(const float* pred_delta_u, const float* target_delta_u, const float* pred_edge, const float* target_face,
-                             const uint8_t* mask_interior, const int32_t* cell_batch, const int32_t* face_batch, int n_cells, int n_faces,
-                             int n_graphs, int mode, float w_mom, float w_uv, float w_p, float* out, float* workspace, fvgn_stream_t stream) {
-  FVGN_CHECK_ARG(pred_delta_u && target_delta_u && pred_edge && target_face && mask_interior && out && workspace, "NULL pointer");
+extern "C" int fvgn_loss_partials(const float* pred_delta_u, const float* target_delta_u, const float* pred_edge, const float* target_face,
+                                  const uint8_t* mask_interior, const int32_t* cell_batch, const int32_t* face_batch, int n_cells, int n_faces,
+                                  int n_graphs, int mode, float* workspace, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(pred_delta_u && target_delta_u && pred_edge && target_face && mask_interior && workspace, "NULL pointer");
   FVGN_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0,1,2");
   FVGN_CHECK_ARG(mode == 0 || (cell_batch && face_batch && n_graphs >= 1 && n_graphs <= 1024), "global_mean needs batch vectors, 1..1024 graphs");
   FVGN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "workspace must be 8B aligned");
   const int n_seg = (mode == 0) ? 1 : n_graphs;
   double* part = reinterpret_cast<double*>(workspace);
-  float* seg_terms = reinterpret_cast<float*>(part + (size_t)n_seg * LOSS_CHUNKS * 6);
-  cudaStream_t st = as_stream(stream);
-  loss_partial_kernel<<<dim3(LOSS_CHUNKS, n_seg), RED_THREADS, 0, st>>>(pred_delta_u, target_delta_u, pred_edge, target_face, mask_interior,
-                                                                        cell_batch, face_batch, n_cells, n_faces, mode != 0, part);
-  FVGN_LAUNCH_CHECK();
-  loss_final_kernel<<<1, 256, 0, st>>>(part, n_seg, mode, w_mom, w_uv, w_p, out, seg_terms);
+  loss_partial_kernel<<<dim3(LOSS_CHUNKS, n_seg), RED_THREADS, 0, as_stream(stream)>>>(pred_delta_u, target_delta_u, pred_edge, target_face,
+                                                                                      mask_interior, cell_batch, face_batch, n_cells, n_faces,
+                                                                                      mode != 0, part);
   FVGN_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int fvgn_loss_finish(int n_graphs, int mode, float w_mom, float w_uv, float w_p, float* out, float* workspace, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(out && workspace, "NULL pointer");
+  FVGN_CHECK_ARG(mode >= 0 && mode <= 2 && (mode == 0 || (n_graphs >= 1 && n_graphs <= 1024)), "mode must be 0,1,2; 1..1024 graphs");
+  const int n_seg = (mode == 0) ? 1 : n_graphs;
+  double* part = reinterpret_cast<double*>(workspace);
+  float* seg_terms = reinterpret_cast<float*>(part + (size_t)n_seg * LOSS_CHUNKS * 6);
+  loss_final_kernel<<<1, 256, 0, as_stream(stream)>>>(part, n_seg, mode, w_mom, w_uv, w_p, out, seg_terms);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fvgn_loss_fwd(const float* pred_delta_u, const float* target_delta_u, const float* pred_edge, const float* target_face,
+                             const uint8_t* mask_interior, const int32_t* cell_batch, const int32_t* face_batch, int n_cells, int n_faces,
+                             int n_graphs, int mode, float w_mom, float w_uv, float w_p, float* out, float* workspace, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(out != nullptr, "NULL pointer");
+  if (int e = fvgn_loss_partials(pred_delta_u, target_delta_u, pred_edge, target_face, mask_interior, cell_batch, face_batch, n_cells, n_faces,
+                                 n_graphs, mode, workspace, stream)) return e;
+  return fvgn_loss_finish(n_graphs, mode, w_mom, w_uv, w_p, out, workspace, stream);
 }
 
 extern "C" int fvgn_loss_bwd(const float* pred_delta_u, const float* target_delta_u, const float* pred_edge, const float* target_face,

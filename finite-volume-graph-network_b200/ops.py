@@ -59,6 +59,9 @@ def _p(t):
 def _req(t, dtype, name, dim=None, rowmajor=True):
     try:  # fast accept (one validator call per tensor argument of every launch): a contiguous CUDA tensor of the right dtype / rank
         if t.is_cuda and t.dtype is dtype and (dim is None or t.dim() == dim) and t.is_contiguous():
+            if t.device.index != _raw_device():
+                raise RuntimeError(f"{name}: tensor lives on {t.device} but the current CUDA device is {_raw_device()} (kernels launch on "
+                                   "the current device's stream: wrap the call in torch.cuda.device(tensor.device))")
             return t
     except AttributeError:
         pass
@@ -604,16 +607,54 @@ def integrator_fwd(decoded, unv, face_area, cells_face_T, rho, rhs_coef=1.0, wan
 LOSS_MODES = {"direct_mean_loss": 0, "global_mean_sum": 1, "global_mean": 2}
 
 
-def loss_fwd(pred_du, target_du, pred_edge, target_face, mask_interior, cell_batch, face_batch, n_graphs, mode, w_mom, w_uv, w_p):
+LOSS_CHUNKS = 32  # partial sums per segment in the loss workspace (csrc/prepost.cu)
+
+
+def loss_fwd(pred_du, target_du, pred_edge, target_face, mask_interior, cell_batch, face_batch, n_graphs, mode, w_mom, w_uv, w_p,
+             reduce_partials=None):
+    """compute_FVM_loss forward.  `reduce_partials` (data-parallel direct_mean_loss): callable that all-reduces (SUM, in place) the
+    float64 [n_seg, 6] column sums {sq momentum error, n_cells, sq interior uv error, n_interior, sq p error, n_faces} over the ranks
+    BEFORE the log is taken (utils/loss_compute.py:92-113 takes one log over the batch means)."""
     dev = pred_du.device
     L = _lib.lib()
     out = torch.empty(5, dtype=torch.float32, device=dev)
     ws = torch.empty(L.fvgn_loss_workspace_floats(n_graphs) // 2 + 8, dtype=torch.float64, device=dev)
     m8 = mask_interior.to(torch.uint8).contiguous()
     _count(2)
-    check(L.fvgn_loss_fwd(_p(pred_du), _p(target_du), _p(pred_edge), _p(target_face), _p(m8), _p(cell_batch), _p(face_batch), pred_du.shape[0],
-                          pred_edge.shape[0], n_graphs, mode, float(w_mom), float(w_uv), float(w_p), _p(out), _p(ws), _stream()), "loss_fwd")
+    if reduce_partials is None:
+        check(L.fvgn_loss_fwd(_p(pred_du), _p(target_du), _p(pred_edge), _p(target_face), _p(m8), _p(cell_batch), _p(face_batch), pred_du.shape[0],
+                              pred_edge.shape[0], n_graphs, mode, float(w_mom), float(w_uv), float(w_p), _p(out), _p(ws), _stream()), "loss_fwd")
+        return out, ws
+    check(L.fvgn_loss_partials(_p(pred_du), _p(target_du), _p(pred_edge), _p(target_face), _p(m8), _p(cell_batch), _p(face_batch), pred_du.shape[0],
+                               pred_edge.shape[0], n_graphs, mode, _p(ws), _stream()), "loss_partials")
+    n_seg = 1 if mode == 0 else n_graphs
+    part = ws[:n_seg * LOSS_CHUNKS * 6].view(n_seg, LOSS_CHUNKS, 6)
+    tot = part.sum(dim=1)
+    tot[:, 1], tot[:, 5] = part[:, 0, 1], part[:, 0, 5]  # the counts are per segment, repeated in every chunk
+    reduce_partials(tot)
+    part.zero_()
+    part[:, 0, :] = tot
+    check(L.fvgn_loss_finish(n_graphs, mode, float(w_mom), float(w_uv), float(w_p), _p(out), _p(ws), _stream()), "loss_finish")
     return out, ws
+
+
+STATUS_NONFINITE_X3 = 1
+
+
+def status(clear=True):
+    """device status word (fvgn_status_read; synchronises the device).  Bit STATUS_NONFINITE_X3: a row of a fp32-equivalent ('bf16x3')
+    forward tile came out non-finite since the last clear (fp16 operand terms overflow for |activation| >= ~8190)."""
+    v = C.c_uint(0)
+    check(_lib.lib().fvgn_status_read(C.byref(v), 1 if clear else 0), "status_read")
+    return int(v.value)
+
+
+def raise_if_nonfinite(what="forward"):
+    if status(clear=True) & STATUS_NONFINITE_X3:
+        raise FloatingPointError(
+            f"fvgn_b200: non-finite rows in the fp32-equivalent ('bf16x3') tensor-core {what}: an activation reached the fp16 operand range "
+            "(|a| >= ~8190) or the inputs held inf/NaN.  The reference's fp32 path stays finite on large activations: re-run with "
+            "model.set_math_mode('fp32').")
 
 
 # ------------------------------------------------------------------------------------------------ backward (training)

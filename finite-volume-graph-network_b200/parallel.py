@@ -6,8 +6,11 @@ single-process batch is:
   2. all-reduce(SUM) of the four online normalisers' per-step INCREMENTS (46 floats + 4 counts) so every rank holds the
      statistics of the whole batch (utils/normalization.py:56-67)
   3. all-reduce(SUM) of the face-area BatchNorm (sum, sum of squares, count) so the batch statistics are global (FVGN.py:209-227)
-With `global_mean_*` losses (per-graph log, mean over graphs) and the same number of graphs per rank, DP-N then equals the
-single-process batch; `direct_mean_loss` takes the log of per-rank means (standard DDP semantics).  There is no collective
+  4. `direct_mean_loss` (run_train.sh:17, utils/loss_compute.py:92-113: ONE log over the batch means): all-reduce(SUM) of the three
+     numerators / denominators BEFORE the log (autograd.LossFunction -> ops.loss_fwd(reduce_partials=...)), gradient scaled by the
+     world size to undo the bucket's averaging
+With `global_mean_*` losses (per-graph log, mean over graphs) and the same number of graphs per rank, DP-N equals the
+single-process batch without item 4.  There is no collective
 in inference/rollout: ranks are independent replicas."""
 import torch
 import torch.distributed as dist
@@ -16,8 +19,34 @@ NORMALIZERS = ("_acc_output_normalizer", "_face_uvp_flux_output_normalizer", "_e
 _NORM_BUFS = ("acc_sum", "acc_sum_squared", "acc_count", "num_accumulations")
 
 
+_DISABLED = [0]
+
+
 def is_distributed():
-    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    return not _DISABLED[0] and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class single_process:
+    """context: treat this rank as a single process (no statistic / loss / gradient collectives) although a process group exists —
+    used to compute the single-process batch-(N x b) result that DP-N must reproduce (bench.py --check, tests)"""
+
+    def __enter__(self):
+        _DISABLED[0] += 1
+
+    def __exit__(self, *a):
+        _DISABLED[0] -= 1
+        return False
+
+
+def world_size():
+    return dist.get_world_size() if is_distributed() else 1
+
+
+def all_reduce_sum_(t, group=None):
+    """in-place SUM over the ranks (identity in a single process)"""
+    if is_distributed():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
 
 
 class GradBucket:

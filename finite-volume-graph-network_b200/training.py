@@ -63,4 +63,12 @@ class GraphedTrainStep:
     def step(self):
         """replays the captured step; returns the persistent [loss, loss_mom, loss_face_uv, loss_face_p] tensor of this step"""
         self.graph.replay()
+        # the replay has stepped the optimizer without running any of the Python-side signals the packed-weight caches key on (the
+        # optimizer-step hook, Tensor._version): advance the epoch so that the next EAGER forward (validation between replays, a
+        # GraphedRollout captured earlier, an eval after set_math_mode) re-packs its tensor-core weight tiles instead of reading stale ones
+        ops._WEIGHTS_EPOCH[0] += 1
         return self.loss
+
+    def check(self):
+        """synchronises; raises FloatingPointError if a fp32-equivalent forward tile produced a non-finite row since the last check"""
+        ops.raise_if_nonfinite("training step")

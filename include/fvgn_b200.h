@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FVGN_ABI_VERSION 8 /* v7: cells_node_T == NULL selects the mp_times = 1 CellBlock in every cell-block entry point; v8: fvgn_mlp_pack_bf16x3_many, fvgn_mlp_pack_bf16x3_bwd_many, fvgn_cell_mean, fvgn_ln_bwd column-sum partials, n_products = 3 */
+#define FVGN_ABI_VERSION 9 /* v9: fvgn_status_read, fvgn_loss_partials / fvgn_loss_finish (data-parallel reduce-before-log); [4,C] tri/quad tables;  v7: cells_node_T == NULL selects the mp_times = 1 CellBlock in every cell-block entry point; v8: fvgn_mlp_pack_bf16x3_many, fvgn_mlp_pack_bf16x3_bwd_many, fvgn_cell_mean, fvgn_ln_bwd column-sum partials, n_products = 3 */
 #define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
 
 #define FVGN_E_BADARG (-1)
@@ -47,6 +47,12 @@ FVGN_API int fvgn_abi_version(void);
 FVGN_API const char* fvgn_last_error(void);
 /* 0 if the current device is sm_100; fills sm count. */
 FVGN_API int fvgn_device_check(int* sm_count, int* cc_major, int* cc_minor);
+/* Device status word of the current device (SYNCHRONOUS: waits for the device; not for use inside a stream capture).
+ * FVGN_STATUS_NONFINITE_X3: some row of a FVGN_MATH_BF16X3_TC forward tile came out non-finite since the last clear — the mode's fp16
+ * operand terms overflow for |activation| >= ~8190 (the reference's fp32 torch path, FVGN_model/EncoderProcesserDecoder.py:12-48,
+ * would stay finite on such an input), or the input already held inf / NaN.  Re-run the step with FVGN_MATH_FP32_SIMT. */
+#define FVGN_STATUS_NONFINITE_X3 1u
+FVGN_API int fvgn_status_read(unsigned int* status_host, int clear);
 
 /* One MLP of build_mlp (FVGN_model/EncoderProcesserDecoder.py:12-48): Linear(k_in,128)-SiLU-Linear(128,128)-SiLU-
  * Linear(128,n_out) [+ LayerNorm(n_out), eps 1e-5].  Pointers are the nn.Linear tensors as they sit in the
@@ -236,6 +242,17 @@ FVGN_API int fvgn_loss_fwd(const float* pred_delta_u, const float* target_delta_
                   const int32_t* face_batch, int n_cells, int n_faces, int n_graphs, int mode, float w_mom, float w_uv,
                   float w_p, float* out /*[5]*/, float* workspace /*>= fvgn_loss_workspace_floats(n_graphs)*/, fvgn_stream_t stream);
 FVGN_API size_t fvgn_loss_workspace_floats(int n_graphs);
+/* The two halves of fvgn_loss_fwd, for data-parallel training with direct_mean_loss (utils/loss_compute.py:92-113: ONE log over the
+ * batch means): fvgn_loss_partials fills workspace with the per-(segment, chunk) partials, 6 doubles each =
+ * {sum sq momentum error, n_cells, sum sq interior face uv error, n_interior, sum sq face p error, n_faces}, 32 chunks per segment
+ * (the counts n_cells / n_faces are read from chunk 0); the caller all-reduces the column sums over the ranks and writes them back
+ * (chunk 0 = the global sums, the other chunks 0) BEFORE fvgn_loss_finish takes the log — so every rank holds the single-process
+ * loss, and fvgn_loss_bwd (which reads the same workspace) the single-process per-element gradient. */
+FVGN_API int fvgn_loss_partials(const float* pred_delta_u, const float* target_delta_u, const float* pred_edge, const float* target_face,
+                       const uint8_t* mask_interior, const int32_t* cell_batch, const int32_t* face_batch, int n_cells, int n_faces,
+                       int n_graphs, int mode, float* workspace, fvgn_stream_t stream);
+FVGN_API int fvgn_loss_finish(int n_graphs, int mode, float w_mom, float w_uv, float w_p, float* out /*[5]*/, float* workspace,
+                     fvgn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Backward (training) path — the reference gets these from torch autograd over train.py:194-218.  Strict fp32 (FFMA).

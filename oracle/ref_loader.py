@@ -6,17 +6,29 @@ attribute-bag stand-ins for the two PyG/torch_scatter pieces that carry arithmet
 (`Data`, `Batch.from_data_list`, `global_mean_pool`, `scatter_add`); everything else is a
 `MagicMock`.  Nothing is copied from the reference: its modules are imported from where they lie.
 
-Only available where /root/reference exists (the build container).  It does not travel to the
-GPU box: tests that need it are skipped there and rely on the committed fixtures in tests/golden/
-that `oracle/make_golden.py` produced with this loader.
+Available where /root/reference exists (the build container) or where `oracle/make_ref.py` has placed its
+byte-for-byte copy under `oracle/_ref/` (git-ignored; it travels to the GPU box with the snapshot, where bench.py's
+reference arm / torch-eager CUDA leg and the drop-in tests use it).  The committed fixtures in tests/golden/ that
+`oracle/make_golden.py` produced with this loader cover the boxes that have neither.
 """
 import os
 import sys
 import types
 import importlib
+import importlib.machinery
 from unittest import mock
 
-REF_ROOT = os.environ.get("FVGN_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    """$FVGN_REFERENCE_ROOT, else /root/reference (the build container), else oracle/_ref (the byte-for-byte copy oracle/make_ref.py
+    placed there; git-ignored, travels to the GPU box)"""
+    cands = [os.environ.get("FVGN_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "FVGN-src", "main", "FVGN_model", "FVGN.py")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 REF_MAIN = os.path.join(REF_ROOT, "FVGN-src", "main")
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 
@@ -57,7 +69,8 @@ def load():
                  "matplotlib.cm", "matplotlib.colors", "circle_fit", "pandas_stub_unused",
                  "natsort", "statsmodels"]:
         if name not in sys.modules:
-            sys.modules[name] = mock.MagicMock()
+            m = sys.modules[name] = mock.MagicMock()
+            m.__spec__ = importlib.machinery.ModuleSpec(name, None)  # importlib.util.find_spec(name) must not raise (torch._dynamo probes it)
     for p in (_SHIMS, REF_MAIN, os.path.join(REF_MAIN, "Extract_mesh")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -145,7 +158,27 @@ def ref_extract_mesh_state(mesh_pos, cells, node_type, velocity, pressure, rho=1
     return dict(w.groups["0"])
 
 
-def ref_data_pool(mesh_dicts, params=None, is_training=False):
+def h5_group_from_tables(tab, velocity, pressure, rho=1.0, mu=1e-3):
+    """The H5 group extract_mesh_state writes (parse_tfrecord_refactor.py:890-899, 962-965, 1045-1094) assembled from
+    already-built tables (oracle.fvgn_oracle.build_connectivity: bit-identical to the reference's, tests/test_oracle_*).
+    Static arrays get the leading [1, ...] axis, the fields stay [T, N, .]; scalars as 0-dim arrays."""
+    import numpy as np
+
+    g = {k: np.asarray(tab[k])[None] for k in ("cells_node", "centroid", "face", "face_length", "face_type", "cells_face", "cells_type",
+                                                "unit_norm_v", "neighbour_cell", "cell_factor", "cells_area")}
+    g["mesh_pos"] = np.asarray(tab["mesh_pos"], dtype=np.float32)[None]
+    g["node_type"] = np.asarray(tab["node_type"]).reshape(1, -1, 1).astype(np.int32)
+    g["target|velocity_on_node"] = np.asarray(velocity, dtype=np.float32)
+    g["target|pressure_on_node"] = np.asarray(pressure, dtype=np.float32)
+    g["mean_u"] = np.float32(1.0)
+    g["charac_scale"] = np.float32(0.1)
+    g["aoa"] = np.float32(0.0)
+    g["rho"], g["mu"] = np.array(rho), np.array(mu)
+    g["reynolds_num"] = np.array(float(g["mean_u"]) * float(g["charac_scale"]) / mu)
+    return g
+
+
+def ref_data_pool(mesh_dicts, params=None, is_training=False, device="cpu"):
     """A reference Data_Pool (Load_mesh.py) whose `pool` is a dict of extract_mesh_state outputs."""
     ref = load()
     params = params or default_params()
@@ -153,6 +186,6 @@ def ref_data_pool(mesh_dicts, params=None, is_training=False):
     import contextlib
 
     with contextlib.redirect_stdout(io.StringIO()):
-        dp = ref.Data_Pool(params, is_traning=is_training, device="cpu")
+        dp = ref.Data_Pool(params, is_traning=is_training, device=device)
     dp.pool = {str(i): m for i, m in enumerate(mesh_dicts)}
     return dp

@@ -1,0 +1,224 @@
+"""GPU (B200), round 2: parity at BENCHMARK scale and the host-side staleness / overflow guards.
+
+  * the full cyl16 batch-16 training step (BASELINE configs[1]: 16 meshes, ~56k cells, ~86k faces): loss and ALL 266 gradients of the
+    default (fp32-equivalent tensor-core) mode against (a) the strict-FFMA path and (b) fp64 autograd over the oracle
+    (train.py:194-218).  Stated tolerance: relative L2 <= 1e-4 per parameter tensor, loss <= 2e-5 absolute.
+  * GraphedTrainStep replay -> eval -> replay -> eval reads fresh weight tiles ('bf16' and 'bf16x3')
+  * the device status word of the fp16-split forward (fvgn_status_read)
+  * direct_mean_loss with the partial sums reduced BEFORE the log (what data-parallel ranks do, utils/loss_compute.py:92-113)
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fvgn_oracle as O
+from tests import helpers as H
+from tests.test_gpu_parity import fv, dev  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+GTOL = 1e-4
+
+
+def _cyl_batch(fv, n, training_pair=0):
+    meshes = [fv.synthetic.make("cyl", seed=i, T=3) for i in range(n)]
+    tabs = [O.build_connectivity(m["mesh_pos"], m["cells"], m["node_type"], "B") for m in meshes]
+    return meshes, tabs
+
+
+def _train_step(fv, model, lists, p, noise, flip):
+    gn, ge, gc = fv.dataset.collate([[b for b in l] for l in lists])
+    gn, ge, gc, mi, mb = fv.dataset.train_datapreprocessing([gn, ge, gc], cell_noise=noise, flip_keep=flip)
+    out = model(graph=gc, graph_edge=ge, graph_node=gn, rho=H.RHO, mu=H.MU, dt=H.DT, edge_one_hot=9, cell_one_hot=0)
+    loss = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=out[3],
+                               target_face_uvp_normalized=out[4], predicted_delta_u=out[1], target_delta_u=out[2])
+    loss[0].backward()
+    return loss
+
+
+@pytest.mark.parametrize("loss_name", ["global_mean_sum", "direct_mean_loss"])
+def test_cyl16_training_step_gradients_vs_strict_and_fp64(fv, loss_name):
+    n = 16
+    meshes, tabs = _cyl_batch(fv, n)
+    p = H.params(loss=loss_name)
+    lists = [fv.dataset.build_graphs(t, m["velocity"], m["pressure"], training_pair=0, device="cuda") for t, m in zip(tabs, meshes)]
+    C = sum(int(t["cells_node"].shape[0]) for t in tabs)
+    F = sum(int(t["face"].shape[1]) for t in tabs)
+    assert C > 50000 and F > 80000  # benchmark scale (configs[1])
+    gen = torch.Generator().manual_seed(11)
+    noise = torch.randn((C, 2), generator=gen) * 0.02
+    flip = torch.rand(F, generator=gen) < 0.5
+    sd0 = H.torch_reference_state_dict(0)
+    res = {}
+    for mode in ("bf16x3", "fp32"):
+        torch.manual_seed(0)
+        model = fv.FVGN(device="cpu", params=p)
+        model.load_state_dict(sd0)
+        model = model.cuda().train().set_math_mode(mode)
+        loss = _train_step(fv, model, lists, p, noise.cuda(), flip.cuda())
+        res[mode] = (float(loss[0].detach()), {k: v.grad.detach().double().cpu() for k, v in model.named_parameters()})
+    assert fv.ops.status(clear=True) == 0
+    # fp64 autograd over the oracle on the same batch / draws / weights
+    orc = O.FVGNOracle(sd0, p, dtype=torch.float64).train()
+    for k, v in list(orc.sd.items()):
+        if v.is_floating_point() and ("model." in k or k in ("_grid_feature_normalizer.weight", "_grid_feature_normalizer.bias")):
+            orc.sd[k] = v.clone().requires_grad_(True)
+    orc.bn["weight"], orc.bn["bias"] = orc.sd["_grid_feature_normalizer.weight"], orc.sd["_grid_feature_normalizer.bias"]
+    bags = [O.build_graphs(t, m["velocity"], m["pressure"], training_pair=0) for t, m in zip(tabs, meshes)]
+    gn, ge, gc = [O.batch_graphs([b[k] for b in bags]) for k in range(3)]
+    for g in (gn, ge, gc):
+        for k, v in list(g.__dict__.items()):
+            if torch.is_tensor(v) and v.is_floating_point():
+                setattr(g, k, v.double())
+    gn, ge, gc, mi, mb = O.train_datapreprocessing(gn, ge, gc, noise.double(), flip)
+    out = orc(gc, ge, gn, H.RHO, H.MU, H.DT, 9, 0)
+    loss64 = O.compute_fvm_loss(p, gc.batch, ge.batch, mi, out[3], out[4], out[1], out[2], num_graphs=n)
+    loss64[0].backward()
+    want = {k: v.grad for k, v in orc.sd.items() if v.requires_grad}
+    l3, g3 = res["bf16x3"]
+    l0, g0 = res["fp32"]
+    assert abs(l3 - float(loss64[0])) < 2e-5 and abs(l0 - float(loss64[0])) < 2e-5, (l3, l0, float(loss64[0]))
+    assert set(g3) == set(want) and len(want) == 266
+    worst = {"x3_vs_fp64": ("", 0.0), "ffma_vs_fp64": ("", 0.0), "x3_vs_ffma": ("", 0.0)}
+    for k, w in want.items():
+        for tag, a, b in (("x3_vs_fp64", g3[k], w), ("ffma_vs_fp64", g0[k], w), ("x3_vs_ffma", g3[k], g0[k])):
+            e = H.rel_l2(a, b)
+            if e > worst[tag][1]:
+                worst[tag] = (k, e)
+    print(f"cyl16 batch-16 training step ({loss_name}, C={C}, F={F}): worst relative L2 of the 266 gradients:", worst)
+    for tag, (k, e) in worst.items():
+        assert e < GTOL, (tag, k, e)
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_graphed_replay_then_eval_reads_fresh_weights(fv, golden, mode):
+    """a CUDA-graph replay steps the optimizer without any Python-side signal; an eval forward after further
+    replays must still re-pack its tensor-core weight tiles.  replay, eval, replay x2, eval — against an eagerly trained twin."""
+    from tests.test_gpu_parity import _model, _graphs
+
+    g = golden("train_tiny.npz")
+    f = golden("fwd_tiny.npz")
+    p = H.params(loss="global_mean_sum")
+    pre = dict(cell_noise=dev(g["noise"]), flip_keep=dev(g["flip"]))
+
+    def batch():
+        return fv.dataset.collate([_graphs(fv, f, "tab.", "velocity", "pressure", pair=1), _graphs(fv, f, "tab1.", "velocity1", "pressure1", pair=0)])
+
+    def evaluate(model):
+        gn, ge, gc = _graphs(fv, f)
+        gn, ge, gc, mi, mb = fv.dataset.valid_datapreprocessing(gn, ge, gc, 0)
+        model.eval()
+        with torch.no_grad():
+            uvp, nuv = model(graph=gc, graph_edge=ge, graph_node=gn, rho=H.RHO, mu=H.MU, dt=H.DT, edge_one_hot=9, cell_one_hot=0)
+        model.train()
+        return uvp.clone(), nuv.clone()
+
+    model = _model(fv, f).train().set_math_mode(mode)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, capturable=True, fused=True)  # (a large step so stale tiles would show)
+    gn0, ge0, gc0 = batch()
+    step = fv.GraphedTrainStep(model, opt, p, gn0, ge0, gc0, H.RHO, H.MU, H.DT, preprocess_kwargs=pre, warmup=2)
+    twin = _model(fv, f).train().set_math_mode(mode)
+    opt2 = torch.optim.AdamW(twin.parameters(), lr=1e-2, capturable=True)
+
+    def eager(nsteps):
+        for _ in range(nsteps):
+            gl = batch()
+            opt2.zero_grad()
+            gn, ge, gc, mi, mb = fv.dataset.train_datapreprocessing(gl, **pre)
+            out = twin(graph=gc, graph_edge=ge, graph_node=gn, rho=H.RHO, mu=H.MU, dt=H.DT, edge_one_hot=9, cell_one_hot=0)
+            loss = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=out[3],
+                                       target_face_uvp_normalized=out[4], predicted_delta_u=out[1], target_delta_u=out[2])
+            loss[0].backward()
+            opt2.step()
+
+    eager(2)  # the two warm-up steps of GraphedTrainStep are real steps
+    tol = 2e-4 if mode == "bf16x3" else 5e-2
+    prev = None
+    for nrep in (1, 2):
+        for _ in range(nrep):
+            step.step()
+        eager(nrep)
+        a, b = evaluate(model), evaluate(twin)
+        e = max(H.rel_l2(a[0].cpu(), b[0].cpu()), H.rel_l2(a[1].cpu(), b[1].cpu()))
+        assert e < tol, (mode, nrep, e)
+        if prev is not None:  # and the evaluation moved with the weights (a frozen tile set would repeat the previous outputs)
+            assert H.rel_l2(a[0].cpu(), prev[0].cpu()) > 10 * tol or mode == "bf16", "eval output did not change after further replays"
+            assert not torch.equal(a[0], prev[0])
+        prev = a
+
+
+def test_graphed_rollout_follows_weight_updates(fv, golden):
+    """a GraphedRollout captured BEFORE an optimizer step re-packs its (persistent) weight tiles before the next replay"""
+    from tests.test_gpu_parity import _model, _graphs
+
+    f = golden("fwd_tiny.npz")
+    model = _model(fv, f).eval().set_math_mode("bf16x3")
+    gn, ge, gc = _graphs(fv, f)
+    gn, ge, gc, mi, mb = fv.dataset.valid_datapreprocessing(gn, ge, gc, 0)
+    roll = fv.GraphedRollout(model, gn, ge, gc, H.RHO, H.MU, H.DT)
+    u0 = roll.step()[1].clone()
+    with torch.no_grad():
+        for q in model.model.parameters():
+            q.mul_(1.01)  # in-place change (bumps Tensor._version, like load_state_dict)
+    roll.reset()
+    u1 = roll.step()[1].clone()
+    gn2, ge2, gc2 = _graphs(fv, f)
+    gn2, ge2, gc2, _, _ = fv.dataset.valid_datapreprocessing(gn2, ge2, gc2, 0)
+    with torch.no_grad():
+        want = model(graph=gc2, graph_edge=ge2, graph_node=gn2, rho=H.RHO, mu=H.MU, dt=H.DT, edge_one_hot=9, cell_one_hot=0)[1]
+    assert not torch.equal(u0, u1)
+    assert torch.equal(u1, want)
+
+
+def test_fp16_split_overflow_sets_the_status_word(fv):
+    """|activation| >= ~8190 overflows the fp16 operand terms of the fp32-equivalent forward: the row turns NaN AND the device status
+    word says so (fvgn_status_read), which FVGN.check_finite / GraphedRollout.check turn into a FloatingPointError; the strict path is finite"""
+    torch.manual_seed(0)
+    m = fv.build_mlp(128, 128, 128, drop_out=False).cuda()
+    x = torch.randn(300, 128, device="cuda")
+    fv.ops.status(clear=True)
+    m.math_mode = "bf16x3"
+    y = m(x)
+    assert torch.isfinite(y).all() and fv.ops.status(clear=True) == 0
+    x[7, 3] = 9000.0
+    y = m(x)
+    assert not torch.isfinite(y[7]).all()
+    assert torch.isfinite(y[:7]).all() and torch.isfinite(y[8:]).all()
+    assert fv.ops.status(clear=False) & fv.ops.STATUS_NONFINITE_X3
+    with pytest.raises(FloatingPointError):
+        fv.ops.raise_if_nonfinite("test")
+    assert fv.ops.status(clear=True) == 0  # cleared by the raise
+    m.math_mode = "fp32"
+    assert torch.isfinite(m(x)).all() and fv.ops.status(clear=True) == 0
+    # decoder-shaped MLP (no LayerNorm statistics): the flag comes from the output values
+    d = fv.build_mlp(128, 128, 5, drop_out=False, lay_norm=False).cuda()
+    d.math_mode = "bf16x3"
+    d(x)
+    assert fv.ops.status(clear=True) & fv.ops.STATUS_NONFINITE_X3
+
+
+def test_direct_mean_loss_reduced_before_the_log(fv):
+    """two 'ranks' = the two halves of a batch: with the partial sums added BEFORE the log, each half returns the whole-batch loss and
+    the whole-batch per-element gradients (utils/loss_compute.py:92-113); the log of per-rank means would not"""
+    gen = torch.Generator().manual_seed(5)
+    C, F = 5000, 7600
+    pdu, tdu = torch.randn(C, 2, generator=gen).cuda(), torch.randn(C, 2, generator=gen).cuda()
+    pe, tf = torch.randn(F, 5, generator=gen).cuda(), torch.randn(F, 3, generator=gen).cuda()
+    pe[F // 2:] *= 3.0  # the two halves have different error levels
+    mask = (torch.rand(F, generator=gen) < 0.8).cuda()
+    w = (10.0, 1.0, 1.0)
+    full, ws_full = fv.ops.loss_fwd(pdu, tdu, pe, tf, mask, None, None, 1, 0, *w)
+    g_du_full, g_e_full = fv.ops.loss_bwd(pdu, tdu, pe, tf, mask.to(torch.uint8), None, None, 1, 0, *w, None, ws_full)
+    cs, fs = [slice(0, C // 2), slice(C // 2, C)], [slice(0, F // 2), slice(F // 2, F)]
+    tots = []
+    for r in range(2):
+        fv.ops.loss_fwd(pdu[cs[r]].contiguous(), tdu[cs[r]].contiguous(), pe[fs[r]].contiguous(), tf[fs[r]].contiguous(), mask[fs[r]].contiguous(),
+                        None, None, 1, 0, *w, reduce_partials=lambda t: tots.append(t.clone()))
+    total = tots[0] + tots[1]
+    for r in range(2):
+        args = (pdu[cs[r]].contiguous(), tdu[cs[r]].contiguous(), pe[fs[r]].contiguous(), tf[fs[r]].contiguous(), mask[fs[r]].contiguous())
+        out, ws = fv.ops.loss_fwd(*args, None, None, 1, 0, *w, reduce_partials=lambda t: t.copy_(total))
+        assert torch.allclose(out, full, rtol=1e-6, atol=1e-7), (out, full)
+        g_du, g_e = fv.ops.loss_bwd(args[0], args[1], args[2], args[3], args[4].to(torch.uint8), None, None, 1, 0, *w, None, ws)
+        assert H.rel_l2(g_du.cpu(), g_du_full[cs[r]].cpu()) < 1e-6 and H.rel_l2(g_e.cpu(), g_e_full[fs[r]].cpu()) < 1e-6
+        local, _ = fv.ops.loss_fwd(*args, None, None, 1, 0, *w)
+        assert abs(float(local[0]) - float(full[0])) > 1e-2  # the per-rank log differs: this is what reduce-before-log fixes

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(fv._lib.LIB_PATH)
     for s in declared:
         assert hasattr(L, s), s
-    assert L.fvgn_abi_version() == 8
+    assert L.fvgn_abi_version() == 9
     # size queries are pure host code and must work without a device
     L.fvgn_norm_workspace_floats.restype = ctypes.c_size_t
     assert L.fvgn_norm_workspace_floats(14) > 0
@@ -115,7 +115,8 @@ def test_fused_optimizer_step_invalidates_packed_weights():
 
 
 def test_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the CPU arm: oracle port on the host cores) prints ONE JSON line with the contract's keys"""
+    """`bench.py --impl reference` (the CPU arm: the unmodified reference via oracle/_ref where oracle/make_ref.py has placed it, else the
+    oracle port) prints ONE JSON line with the contract's keys, and its `config` is the native arm's"""
     import json
     import os
     import subprocess
@@ -130,7 +131,15 @@ def test_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "cell_updates_per_sec" and d["unit"] == "cell-updates/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0 and d["config"]["workload"] == "tiny"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_loader as RL
+
+    assert d["cpu_baseline"]["kind"] == ("reference" if RL.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    sys.path.insert(0, root)
+    import bench
+
+    c = d["config"]
+    assert c == bench.config_of("tiny", c["cells_per_rank"], c["faces_per_rank"], c["nodes_per_rank"], c["graphs_per_rank"], 1)
     assert d["e2e"] == {"value": d["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

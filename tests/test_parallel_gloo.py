@@ -62,6 +62,23 @@ def _worker(rank, world, port, ret):
         ref(raw.float().view(-1, 1))
         parallel.update_running_stats_(bn, mean, var, cnt)
         assert torch.allclose(bn.running_mean, ref.running_mean, rtol=1e-5) and torch.allclose(bn.running_var, ref.running_var, rtol=1e-5)
+        # ---- 4. direct_mean_loss: the numerators / denominators of the batch means are summed over the ranks BEFORE the log
+        #         (utils/loss_compute.py:92-113); host emulation of what ops.loss_fwd(reduce_partials=parallel.all_reduce_sum_) does
+        err = torch.rand(40, 2, generator=gen, dtype=torch.float64) * (1.0 + 3.0 * (torch.arange(40) >= 20).double().view(-1, 1))
+        mine = err[rank * 20:(rank + 1) * 20]
+        tot = torch.tensor([[float((mine ** 2).sum()), 20.0, 0.0, 0.0, 0.0, 0.0]], dtype=torch.float64)
+        parallel.all_reduce_sum_(tot)
+        assert abs(float(tot[0, 0]) - float((err ** 2).sum())) < 1e-12 and float(tot[0, 1]) == 40.0
+        want = torch.log((err ** 2).mean())
+        assert abs(float(torch.log(tot[0, 0] / (2 * tot[0, 1]))) - float(want)) < 1e-12
+        assert abs(float(torch.log((mine ** 2).mean())) - float(want)) > 1e-2  # the log of a per-rank mean is a different number
+        assert parallel.world_size() == 2
+        with parallel.single_process():  # the switch bench.py --check uses to compute the single-process result next to the DP one
+            assert not parallel.is_distributed() and parallel.world_size() == 1
+            t = torch.ones(1)
+            parallel.all_reduce_sum_(t)
+            assert float(t) == 1.0
+        assert parallel.is_distributed()
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
         import traceback
