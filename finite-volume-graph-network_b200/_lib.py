@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfvgn_b200.so")
+# FVGN_B200_LIB: an experimental build of the same ABI (build.py --variant ...), for A/B measurements of kernel variants
+LIB_PATH = os.environ.get("FVGN_B200_LIB") or os.path.join(_HERE, "libfvgn_b200.so")
 
 MATH_FP32_SIMT, MATH_BF16_TC, MATH_BF16X3_TC = 0, 1, 2
 MATH_MODES = {"fp32": MATH_FP32_SIMT, "bf16": MATH_BF16_TC, "bf16x3": MATH_BF16X3_TC}

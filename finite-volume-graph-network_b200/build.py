@@ -54,6 +54,31 @@ def _compile(name, extra, force, verbose):
     return name, "built", r.stderr if verbose else ""
 
 
+def build_variant(name, defines, only=("mlp_tc3.cu",), verbose=False):
+    """experimental build `libfvgn_b200_<name>.so` (git-ignored; selected at run time with FVGN_B200_LIB=<path>): the sources in `only`
+    recompiled with extra -D flags into csrc/_build_<name>/, every other object shared with the product build"""
+    build()
+    vobj = os.path.join(CSRC, "_build_" + name)
+    os.makedirs(vobj, exist_ok=True)
+    objs, logs = [], []
+    for n, extra in SOURCES.items():
+        if n in only:
+            o = os.path.join(vobj, n.replace(".cu", ".o"))
+            cmd = [NVCC] + ARCH + COMMON + extra + list(defines) + ["-c", os.path.join(CSRC, n), "-o", o]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {n} [{name}]:\n{r.stdout}\n{r.stderr}")
+            logs.append(r.stderr)
+            objs.append(o)
+        else:
+            objs.append(os.path.join(OBJ, n.replace(".cu", ".o")))
+    lib = os.path.join(HERE, f"libfvgn_b200_{name}.so")
+    r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-Xcompiler", "-fPIC", "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib, "\n".join(logs)
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
@@ -67,6 +92,12 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB, results
 
+
+if __name__ == "__main__" and "--variant" in sys.argv:
+    i = sys.argv.index("--variant")
+    lib, log = build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")])
+    print(log if "-v" in sys.argv else "", lib)
+    sys.exit(0)
 
 if __name__ == "__main__":
     lib, res = build(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -34,6 +34,17 @@ namespace x3 {
 // NaN, and NaN reaches the row's last-layer statistics.  One compare per row and launch; read / cleared by fvgn_status_read.
 __device__ unsigned int g_status = 0;
 
+// the four 16-column sub-chunks of this thread's column half (t_acc, h, r in scope): fn(sc, registers).  (Keeping the TMEM load of
+// sub-chunk sc + 1 in flight while fn works on sc was measured and rejected: profiles/r02_forward_epilogue_variants.txt.)
+#define FVGN_FOR_SUBCHUNKS(fn)                                                      \
+  do {                                                                              \
+    _Pragma("unroll 1") for (int sc_ = 4 * h; sc_ < 4 * h + 4; ++sc_) {             \
+      tmem_ld16_issue(t_acc + 16 * sc_, r);                                         \
+      tmem_ld16_wait(r);                                                            \
+      fn(sc_, r);                                                                   \
+    }                                                                               \
+  } while (0)
+
 template <int MODE, bool RED, bool SH>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -416,28 +427,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         tc_fence_after();
         const float* bias = sPar + layer * 128;
         const float inv = sPar[5 * 128 + layer];  // undo the power-of-two operand scales (exact)
-#pragma unroll 1
-        for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {  // 16-column sub-chunk index 0..7
-          tmem_ld16_issue(t_acc + 16 * sc, r);
-          tmem_ld16_wait(r);
-          uint32_t p0[8], p1[8];
-          if (FVGN_DBG(p) & 2) {
+        // one 16-column sub-chunk: accumulator registers r -> bias + SiLU -> fp16 split -> this tile's H columns
+        auto sub = [&](int sc, uint32_t* r) {
+            uint32_t p0[8], p1[8];
+            if (FVGN_DBG(p) & 2) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { p0[j] = r[j]; p1[j] = r[j + 8]; }
-          } else
+              for (int j = 0; j < 8; ++j) { p0[j] = r[j]; p1[j] = r[j + 8]; }
+            } else
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + 16 * sc + 4 * j4);
-            const float z0 = fmaf(__uint_as_float(r[4 * j4]), inv, b.x), z1 = fmaf(__uint_as_float(r[4 * j4 + 1]), inv, b.y);
-            const float z2 = fmaf(__uint_as_float(r[4 * j4 + 2]), inv, b.z), z3 = fmaf(__uint_as_float(r[4 * j4 + 3]), inv, b.w);
-            r[4 * j4] = __float_as_uint(z0); r[4 * j4 + 1] = __float_as_uint(z1); r[4 * j4 + 2] = __float_as_uint(z2); r[4 * j4 + 3] = __float_as_uint(z3);
-            split2_pair(silu_x3(z0) * ASCALE, silu_x3(z1) * ASCALE, p0[2 * j4], p1[2 * j4]);
-            split2_pair(silu_x3(z2) * ASCALE, silu_x3(z3) * ASCALE, p0[2 * j4 + 1], p1[2 * j4 + 1]);
-          }
-          if (p.zsave) store_rows16(reinterpret_cast<const float*>(r), p.zsave, 384, 128 * layer + 16 * sc, row0 + 32 * q);
-          tmem_st8(t_ha + 8 * sc, p0);
-          tmem_st8(t_ha + 64 + 8 * sc, p1);
-        }
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b = *reinterpret_cast<const float4*>(bias + 16 * sc + 4 * j4);
+              const float z0 = fmaf(__uint_as_float(r[4 * j4]), inv, b.x), z1 = fmaf(__uint_as_float(r[4 * j4 + 1]), inv, b.y);
+              const float z2 = fmaf(__uint_as_float(r[4 * j4 + 2]), inv, b.z), z3 = fmaf(__uint_as_float(r[4 * j4 + 3]), inv, b.w);
+              r[4 * j4] = __float_as_uint(z0); r[4 * j4 + 1] = __float_as_uint(z1); r[4 * j4 + 2] = __float_as_uint(z2); r[4 * j4 + 3] = __float_as_uint(z3);
+              split2_pair(silu_x3(z0) * ASCALE, silu_x3(z1) * ASCALE, p0[2 * j4], p1[2 * j4]);
+              split2_pair(silu_x3(z2) * ASCALE, silu_x3(z3) * ASCALE, p0[2 * j4 + 1], p1[2 * j4 + 1]);
+            }
+            if (p.zsave) store_rows16(reinterpret_cast<const float*>(r), p.zsave, 384, 128 * layer + 16 * sc, row0 + 32 * q);
+            tmem_st8(t_ha + 8 * sc, p0);
+            tmem_st8(t_ha + 64 + 8 * sc, p1);
+        };
+        FVGN_FOR_SUBCHUNKS(sub);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -458,25 +468,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       float mean = 0.f, rstd = 1.f;
       if (has_ln && !(FVGN_DBG(p) & 32)) {  // two-pass LayerNorm statistics, as torch; the two column halves exchange partial sums
         float s = 0.f;
-#pragma unroll 1
-        for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
-          tmem_ld16_issue(t_acc + 16 * sc, r);
-          tmem_ld16_wait(r);
+        auto sum16 = [&](int sc, const uint32_t* r) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
             s += fmaf(__uint_as_float(r[4 * j4]), inv3, b.x); s += fmaf(__uint_as_float(r[4 * j4 + 1]), inv3, b.y);
             s += fmaf(__uint_as_float(r[4 * j4 + 2]), inv3, b.z); s += fmaf(__uint_as_float(r[4 * j4 + 3]), inv3, b.w);
           }
-        }
+        };
+        FVGN_FOR_SUBCHUNKS(sum16);
         sRed[h * 128 + erow] = s;
         named_bar_sync(1, NEPI);
         mean = (sRed[erow] + sRed[128 + erow]) * (1.0f / 128.0f);
         float qv = 0.f;
-#pragma unroll 1
-        for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
-          tmem_ld16_issue(t_acc + 16 * sc, r);
-          tmem_ld16_wait(r);
+        auto dev16 = [&](int sc, const uint32_t* r) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
@@ -486,19 +491,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             d = fmaf(__uint_as_float(r[4 * j4 + 2]), inv3, b.z) - mean; qv = fmaf(d, d, qv);
             d = fmaf(__uint_as_float(r[4 * j4 + 3]), inv3, b.w) - mean; qv = fmaf(d, d, qv);
           }
-        }
+        };
+        FVGN_FOR_SUBCHUNKS(dev16);
         sRed[256 + h * 128 + erow] = qv;
         named_bar_sync(1, NEPI);
         rstd = 1.0f / sqrtf((sRed[256 + erow] + sRed[256 + 128 + erow]) * (1.0f / 128.0f) + 1e-5f);
         if (h == 0 && !(rstd * 0.0f == 0.0f) && row0 + erow < p.rows) atomicOr(&g_status, 1u);  // inf / NaN anywhere in the row
       }
       const float* res = (MODE == TC_CELL) ? p.src0 : p.src1;
-#pragma unroll 1
-      for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
-        tmem_ld16_issue(t_acc + 16 * sc, r);
-        tmem_ld16_wait(r);
+      auto out16 = [&](int sc, uint32_t* r) {
         float* v = reinterpret_cast<float*>(r);
-        if (FVGN_DBG(p) & 32) continue;
+        if (FVGN_DBG(p) & 32) return;
         if (p.zsave) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
@@ -564,7 +567,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             if (!has_ln && !(acc0 == 0.0f)) atomicOr(&g_status, 1u);  // decoder rows (no LayerNorm statistics to look at)
           }
         }
-      }
+      };
+      FVGN_FOR_SUBCHUNKS(out16);
       PROF_ADD(4);  // final epilogue work
     };
 #pragma unroll 1

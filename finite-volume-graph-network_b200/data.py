@@ -47,11 +47,14 @@ class Batch(Data):
         off = 0
         cols = {k: [] for k in lst[0].keys}
         bvec, ptr = [], [0]
+        iptr = {k: [0] for k in cols if _is_index(k)}
         for gi, g in enumerate(lst):
             n = g.num_nodes
             for k in cols:
                 v = getattr(g, k)
                 cols[k].append(v + off if _is_index(k) else v)
+                if k in iptr:
+                    iptr[k].append(iptr[k][-1] + int(v.shape[-1]))
             bvec.append(torch.full((n,), gi, dtype=torch.long, device=g.x.device))
             off += n
             ptr.append(off)
@@ -63,6 +66,37 @@ class Batch(Data):
         out.batch = torch.cat(bvec)
         out.ptr = torch.tensor(ptr, dtype=torch.long)
         out.num_graphs = len(lst)
+        out._index_ptr = iptr
+        return out
+
+    def to_data_list(self):
+        """inverse of from_data_list for tensors whose leading (or, for index tables, last) dimension is the batched one
+        (rollout.py:271-273 splits the minibatch back into per-mesh graphs)"""
+        ptr = [int(v) for v in self.ptr]
+        out = []
+        for gi in range(self.num_graphs):
+            a, b = ptr[gi], ptr[gi + 1]
+            d = Data()
+            for k, v in self.__dict__.items():
+                if k in ("batch", "ptr", "num_graphs") or k.startswith("_"):
+                    continue
+                if not torch.is_tensor(v):
+                    d.__dict__[k] = v[gi] if isinstance(v, (list, tuple)) and len(v) == self.num_graphs else v
+                elif _is_index(k):
+                    # tables indexed by another bag's rows (e.g. graph_edge.face: per CELL) cannot be split by this bag's ptr: select
+                    # the columns whose entries fall into this graph's own node range of the table's TARGET — done by the caller
+                    cols = self.__dict__.get("_index_ptr", {}).get(k)
+                    if cols is None:
+                        d.__dict__[k] = v
+                    else:
+                        d.__dict__[k] = v[:, cols[gi]:cols[gi + 1]] - a
+                elif v.dim() > 0 and v.shape[0] == ptr[-1]:
+                    d.__dict__[k] = v[a:b]
+                elif v.dim() > 0 and v.shape[0] == self.num_graphs:
+                    d.__dict__[k] = v[gi]
+                else:
+                    d.__dict__[k] = v
+            out.append(d)
         return out
 
 
