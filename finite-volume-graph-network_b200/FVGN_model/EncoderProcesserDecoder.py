@@ -112,10 +112,16 @@ def fused_gn_block(block: GnBlock, topo, x, e, inplace, node_agg=None, x_prime=N
     if inplace and x_prime_split is not None and cb.math_mode == "bf16x3" and eb.math_mode == "bf16x3":
         # fp32-equivalent fast path: x' lives only as the split fp16 shadow the EdgeBlock gathers (same bits as the two calls below)
         return ops.gn_block_fwd_inplace_split(cb.mlp_ref(), eb.mlp_ref(), x, e, node_agg, a.idx, topo.nc, x_prime_split, cell_mean_split)
-    if inplace and x_prime_bf16 is not None and cb.math_mode == "bf16" and eb.math_mode == "bf16":
+    if inplace and x_prime_bf16 is not None and cb.math_mode == "bf16" and eb.math_mode == "bf16" and not (a.idx is not None and a.idx.shape[0] == 4):
         # tensor-core fast path: x' lives only as the bf16 shadow the EdgeBlock gathers (same arithmetic as the two calls below)
         return ops.gn_block_fwd_inplace_bf16(cb.mlp_ref(), eb.mlp_ref(), x, e, node_agg, a.idx, topo.nc, x_prime_bf16)
-    x_prime, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, node_agg, a.idx, cb.math_mode_id(), x_prime=x_prime, x_out=x if inplace else None)
+    idx = a.idx
+    if idx is not None and idx.shape[0] == 4:
+        # tri / quad hybrid mesh: the k-wide mean once (fvgn_cell_mean_poly), then the per-cell-row convention of the fused kernels
+        node_agg, idx = ops.cell_mean_poly(node_agg, idx), None
+    if inplace and x_prime_bf16 is not None and cb.math_mode == "bf16" and eb.math_mode == "bf16":
+        return ops.gn_block_fwd_inplace_bf16(cb.mlp_ref(), eb.mlp_ref(), x, e, node_agg, idx, topo.nc, x_prime_bf16)
+    x_prime, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, node_agg, idx, cb.math_mode_id(), x_prime=x_prime, x_out=x if inplace else None)
     _, e_new = ops.edge_block_fwd(eb.mlp_ref(), x_prime, e, topo.nc, eb.math_mode_id(), e_out=e if inplace else None)
     return x_new, e_new
 

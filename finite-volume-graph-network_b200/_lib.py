@@ -27,6 +27,12 @@ _SIGS = {
     "fvgn_connectivity_workspace_bytes": (_S, [_I]),
     "fvgn_connectivity_faces": (_I, [_P, _I, _I, _P, C.POINTER(C.c_int), _P, _S, _P]),
     "fvgn_connectivity_tables": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S, _P]),
+    "fvgn_connectivity_poly_workspace_bytes": (_S, [_I]),
+    "fvgn_connectivity_poly_faces": (_I, [_P, _I, _I, _P, C.POINTER(C.c_int), _P, _S, _P]),
+    "fvgn_connectivity_poly_tables": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S, _P]),
+    "fvgn_cell_mean_poly": (_I, [_P, _P, _I, _P, _P, _P]),
+    "fvgn_interp_cells_poly": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P]),
+    "fvgn_integrator_fwd_poly": (_I, [_P, _P, _P, _P, _I, _F, _F, _P, _P, _P]),
     "fvgn_csr_workspace_bytes": (_S, [_I]),
     "fvgn_build_csr": (_I, [_P, _I, _I, _P, _P, _P, _S, _P]),
     "fvgn_interp_nodes": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),

@@ -97,6 +97,8 @@ class NetFunction(torch.autograd.Function):
     def forward(ctx, model, topo, cell_in, edge_in, graph_edge_x, cell_area, unv, rho, dt, *params):
         epd = model.model
         enc_c, enc_e = epd.encoder.cb_encoder, epd.encoder.eb_encoder
+        if topo.poly:
+            raise NotImplementedError("training on tri / quad hybrid meshes ([4,C] tables) is not built (inference / rollout is)")
         # forward arithmetic: strict FFMA ("fp32": FFMA backward that recomputes each tile from the saved layer inputs), the
         # fp32-equivalent tensor-core mode ("bf16x3") or plain bf16 tiles ("bf16"): tensor-core backward from the saved pre-activations
         mm = {"fp32": 0, "bf16x3": 2, "bf16": 2}[model.math_mode]  # "bf16": the bf16x3 kernels with the leading split product only

@@ -42,6 +42,7 @@ int tc3_cell_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*
 int tc3_edge_block(const fvgn_mlp_t*, const float*, const float*, const int32_t*, int, float*, float*, cudaStream_t);
 int tc3_cell_mean_split(const float*, const int32_t*, int, void*, cudaStream_t);
 int tc3_cell_mean(const float*, const int32_t*, int, float*, cudaStream_t);
+int tc3_cell_mean_poly(const float*, const int32_t*, int, float*, void*, cudaStream_t);
 int tc3_cell_block_sh(const fvgn_mlp_t*, float*, const void*, int, void*, cudaStream_t);
 int tc3_edge_block_sh(const fvgn_mlp_t*, const void*, float*, const int32_t*, int, cudaStream_t);
 int tc3_status_read(unsigned int*, int);
@@ -178,6 +179,12 @@ extern "C" int fvgn_cell_mean_split(const float* node_agg, const int32_t* cells_
 extern "C" int fvgn_cell_mean(const float* node_agg, const int32_t* cells_node_T, int n_cells, float* cell_mean, fvgn_stream_t stream) {
   if (int e = check_device()) return e;
   return tc3_cell_mean(node_agg, cells_node_T, n_cells, cell_mean, as_stream(stream));
+}
+
+extern "C" int fvgn_cell_mean_poly(const float* node_agg, const int32_t* cells_node4_T, int n_cells, float* cell_mean, void* cell_mean_split,
+                                   fvgn_stream_t stream) {
+  if (int e = check_device()) return e;
+  return tc3_cell_mean_poly(node_agg, cells_node4_T, n_cells, cell_mean, cell_mean_split, as_stream(stream));
 }
 
 extern "C" int fvgn_cell_block_fwd_split(const fvgn_mlp_t* mlp, float* x, const void* cell_mean_split, int n_cells, void* x_prime_split,

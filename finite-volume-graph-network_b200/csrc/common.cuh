@@ -62,6 +62,21 @@ __device__ __forceinline__ float4 cell_agg4(const float* na, const int32_t* idx,
   return make_float4(__fdiv_rn(__fadd_rn(__fadd_rn(a.x, b.x), d.x), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.y, b.y), d.y), 3.0f),
                      __fdiv_rn(__fadd_rn(__fadd_rn(a.z, b.z), d.z), 3.0f), __fdiv_rn(__fadd_rn(__fadd_rn(a.w, b.w), d.w), 3.0f));
 }
+// tri / quad hybrid meshes ([4,C] table, 4th row -1 on triangles; oracle/fvgn_oracle.py::cell_block): ((a + b) + c) [+ d], then a true
+// division by k = 3 or 4.  Bit-identical to cell_agg4 on triangles.
+__device__ __forceinline__ float4 cell_agg4_poly(const float* na, const int32_t* idx4, size_t C, int c, int col) {
+  const int n0 = __ldg(idx4 + c), n1 = __ldg(idx4 + C + c), n2 = __ldg(idx4 + 2 * C + c), n3 = __ldg(idx4 + 3 * C + c);
+  const float4 a = ldg4(na + (size_t)n0 * 64 + col), b = ldg4(na + (size_t)n1 * 64 + col), d = ldg4(na + (size_t)n2 * 64 + col);
+  float4 s = make_float4(__fadd_rn(__fadd_rn(a.x, b.x), d.x), __fadd_rn(__fadd_rn(a.y, b.y), d.y), __fadd_rn(__fadd_rn(a.z, b.z), d.z),
+                         __fadd_rn(__fadd_rn(a.w, b.w), d.w));
+  float k = 3.0f;
+  if (n3 >= 0) {
+    const float4 e = ldg4(na + (size_t)n3 * 64 + col);
+    s = make_float4(__fadd_rn(s.x, e.x), __fadd_rn(s.y, e.y), __fadd_rn(s.z, e.z), __fadd_rn(s.w, e.w));
+    k = 4.0f;
+  }
+  return make_float4(__fdiv_rn(s.x, k), __fdiv_rn(s.y, k), __fdiv_rn(s.z, k), __fdiv_rn(s.w, k));
+}
 __device__ __forceinline__ float silu_f(float v) {
   // x * sigmoid(x) with IEEE division; expf (not __expf) keeps the strict-fp32 path within ~1 ulp of torch's SiLU
   return v / (1.0f + expf(-v));

@@ -33,8 +33,8 @@ static size_t cub_conn_bytes(int n) {
   return a > b ? a : b;
 }
 
-static ConnWs carve_conn(void* base, int C) {
-  const size_t n = (size_t)3 * C;
+static ConnWs carve_conn(void* base, int C, int K = 3) {
+  const size_t n = (size_t)K * C;
   ConnWs w{};
   size_t off = 0;
   char* p = reinterpret_cast<char*>(base);
@@ -230,6 +230,164 @@ __global__ void cell_finalize(const float* __restrict__ pos, const int32_t* __re
   cells_area[c] = __fsqrt_rn(__fmul_rn(__fmul_rn(__fmul_rn(p, __fsub_rn(p, len[0])), __fsub_rn(p, len[1])), __fsub_rn(p, len[2])));
 }
 
+
+// ------------------------------------------------------------------------------------------------ tri / quad hybrid meshes
+// Cells with k = 3 or 4 nodes ([C,4] tables, 4th column -1 on triangles) — BASELINE configs[3].  The reference is triangles only
+// (SURVEY.md §0 item 5); these kernels follow oracle/fvgn_oracle_poly.py, i.e. the reference's rules with "3" read as "k", and reduce to
+// the triangle kernels above bit for bit when every cell is a triangle (tests/test_gpu_poly.py).
+constexpr unsigned long long POLY_NOKEY = ~0ull;
+
+__global__ void canon_cells_pack_edges_poly(const int32_t* __restrict__ cells, int C, int32_t* __restrict__ cells_node,
+                                            unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  int n[4] = {cells[4 * c], cells[4 * c + 1], cells[4 * c + 2], cells[4 * c + 3]};
+  const bool quad = n[3] >= 0;
+  if (!quad) {  // triangles: sorted ascending (:431)
+    if (n[0] > n[1]) { int t = n[0]; n[0] = n[1]; n[1] = t; }
+    if (n[1] > n[2]) { int t = n[1]; n[1] = n[2]; n[2] = t; }
+    if (n[0] > n[1]) { int t = n[0]; n[0] = n[1]; n[1] = t; }
+  } else {      // quads: cyclic order kept, smallest id first, reflected so that node[1] < node[3]
+    int r = 0;
+    for (int j = 1; j < 4; ++j) if (n[j] < n[r]) r = j;
+    const int m[4] = {n[r], n[(r + 1) & 3], n[(r + 2) & 3], n[(r + 3) & 3]};
+    n[0] = m[0]; n[2] = m[2];
+    if (m[1] > m[3]) { n[1] = m[3]; n[3] = m[1]; } else { n[1] = m[1]; n[3] = m[3]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cells_node[4 * c + j] = n[j];
+  const int k = quad ? 4 : 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    unsigned long long key = POLY_NOKEY;
+    if (j < k) {
+      const int a = n[j], b = n[(j + 1 == k) ? 0 : j + 1];
+      key = ((unsigned long long)(unsigned)max(a, b) << 32) | (unsigned)min(a, b);
+    }
+    keys[(size_t)j * C + c] = key;
+    vals[(size_t)j * C + c] = j * C + c;
+  }
+}
+
+__global__ void head_flags_poly(const unsigned long long* __restrict__ keys, int n, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flag[i] = (keys[i] != POLY_NOKEY && (i == 0 || keys[i] != keys[i - 1])) ? 1 : 0;
+}
+
+__device__ __forceinline__ float2 centroid_poly(const float* __restrict__ pos, const int32_t* __restrict__ cn, int c) {
+  const int n0 = cn[4 * c], n1 = cn[4 * c + 1], n2 = cn[4 * c + 2], n3 = cn[4 * c + 3];
+  float sx = __fadd_rn(__fadd_rn(pos[2 * n0], pos[2 * n1]), pos[2 * n2]);
+  float sy = __fadd_rn(__fadd_rn(pos[2 * n0 + 1], pos[2 * n1 + 1]), pos[2 * n2 + 1]);
+  float2 r;
+  if (n3 >= 0) { r.x = __fdiv_rn(__fadd_rn(sx, pos[2 * n3]), 4.0f); r.y = __fdiv_rn(__fadd_rn(sy, pos[2 * n3 + 1]), 4.0f); }
+  else { r.x = __fdiv_rn(sx, 3.0f); r.y = __fdiv_rn(sy, 3.0f); }
+  return r;
+}
+
+__global__ void cell_geometry_poly(const float* __restrict__ pos, const int32_t* __restrict__ cn, int C, float* __restrict__ centroid,
+                                   float* __restrict__ cell_factor) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float2 g = centroid_poly(pos, cn, c);
+  centroid[2 * c] = g.x; centroid[2 * c + 1] = g.y;
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  const int k = cn[4 * c + 3] >= 0 ? 4 : 3;
+  for (int j = 0; j < k; ++j) {
+    const int n = cn[4 * c + j];
+    const float dx = __fsub_rn(pos[2 * n], g.x), dy = __fsub_rn(pos[2 * n + 1], g.y);
+    d[j] = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  }
+  float tot = __fadd_rn(__fadd_rn(d[0], d[1]), d[2]);
+  if (k == 4) tot = __fadd_rn(tot, d[3]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cell_factor[4 * c + j] = __fdiv_rn(d[j], tot);
+}
+
+__global__ void faces_from_sorted_poly(const unsigned long long* __restrict__ keys, const int* __restrict__ vals, const int* __restrict__ face_id,
+                                       int n, int C, int F, const float* __restrict__ pos, const int32_t* __restrict__ cn,
+                                       int32_t* __restrict__ face, int32_t* __restrict__ cells_face, int32_t* __restrict__ neighbour_cell) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int packed = vals[i];
+  const int j = packed / C, c = packed - j * C;
+  const unsigned long long key = keys[i];
+  if (key == POLY_NOKEY) { cells_face[4 * c + j] = -1; return; }
+  const int fid = face_id[i] - 1;
+  cells_face[4 * c + j] = fid;
+  if (i == 0 || keys[i - 1] != key) {
+    face[fid] = (int)(key >> 32);
+    face[(size_t)F + fid] = (int)(key & 0xffffffffu);
+    int first = c * 4 + j, last = first;  // scan order c = 0..C-1, j = 0..k-1
+    for (int t = i + 1; t < n && keys[t] == key; ++t) {
+      const int pk = vals[t];
+      const int jj = pk / C, cc = pk - jj * C;
+      const int s = cc * 4 + jj;
+      first = min(first, s);
+      last = max(last, s);
+    }
+    const int ca = first / 4, cb = last / 4;
+    const float2 ga = centroid_poly(pos, cn, ca), gb = centroid_poly(pos, cn, cb);
+    const float dx = __fsub_rn(ga.x, gb.x), dy = __fsub_rn(ga.y, gb.y);
+    const bool keep = (dx > 0.f) || (dx == 0.f && dy > 0.f);
+    neighbour_cell[fid] = keep ? ca : cb;
+    neighbour_cell[(size_t)F + fid] = keep ? cb : ca;
+  }
+}
+
+__global__ void cell_finalize_poly(const float* __restrict__ pos, const int32_t* __restrict__ cn, const int32_t* __restrict__ face,
+                                   const int32_t* __restrict__ cells_face, const int32_t* __restrict__ face_type,
+                                   const float* __restrict__ face_length, const float* __restrict__ centroid, int C, int F,
+                                   int32_t* __restrict__ cells_type, float* __restrict__ unv, float* __restrict__ cells_area) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  int n_in = 0, n_wall = 0, n_out = 0, n_foil = 0, n_norm = 0;
+  float len[3] = {0.f, 0.f, 0.f};
+  const float gx = centroid[2 * c], gy = centroid[2 * c + 1];
+  const int k = cn[4 * c + 3] >= 0 ? 4 : 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float nx = 0.f, ny = 0.f;
+    if (j < k) {
+      const int f = cells_face[4 * c + j];
+      const int t = face_type[f];
+      if (t == 4) ++n_in; else if (t == 6) ++n_wall; else if (t == 5) ++n_out; else if (t == 2) ++n_foil; else ++n_norm;
+      if (j < 3) len[j] = face_length[f];
+      const int s = face[f], r = face[(size_t)F + f];
+      const float dx = __fsub_rn(pos[2 * s], pos[2 * r]), dy = __fsub_rn(pos[2 * s + 1], pos[2 * r + 1]);
+      const float nx0 = -dy, ny0 = dx;
+      const float nrm = __fsqrt_rn(__fmaf_rn(ny0, ny0, __fmul_rn(nx0, nx0)));
+      nx = __fdiv_rn(nx0, nrm); ny = __fdiv_rn(ny0, nrm);
+      const float fcx = __fdiv_rn(__fadd_rn(pos[2 * s], pos[2 * r]), 2.0f), fcy = __fdiv_rn(__fadd_rn(pos[2 * s + 1], pos[2 * r + 1]), 2.0f);
+      const float vx = __fsub_rn(gx, fcx), vy = __fsub_rn(gy, fcy);
+      const float dot = __fadd_rn(__fmul_rn(nx, vx), __fmul_rn(ny, vy));
+      if (dot > 0.f) { nx = __fmul_rn(nx, -1.0f); ny = __fmul_rn(ny, -1.0f); }
+    }
+    unv[(size_t)c * 8 + 2 * j] = nx;
+    unv[(size_t)c * 8 + 2 * j + 1] = ny;
+  }
+  int t = 0;
+  if (n_wall > 0 && ((n_norm > 0 && n_in == 0 && n_out == 0) || (n_norm == 0 && n_in > 0 && n_out == 0) ||
+                     (n_norm == 0 && n_in == 0 && n_out > 0) || (n_norm > 0 && n_in > 0 && n_out == 0) ||
+                     (n_norm > 0 && n_in == 0 && n_out > 0)))
+    t = 6;
+  else if (n_foil > 0 && n_norm > 0 && n_in == 0 && n_out == 0) t = 2;
+  else if (n_in > 0 && n_norm > 0 && n_wall == 0 && n_out == 0) t = 4;
+  else if (n_out > 0 && n_norm > 0 && n_wall == 0 && n_in == 0) t = 5;
+  cells_type[c] = t;
+  if (k == 3) {  // Heron (:876-884)
+    const float p = __fmul_rn(0.5f, __fadd_rn(__fadd_rn(len[0], len[1]), len[2]));
+    cells_area[c] = __fsqrt_rn(fmaxf(__fmul_rn(__fmul_rn(__fmul_rn(p, __fsub_rn(p, len[0])), __fsub_rn(p, len[1])), __fsub_rn(p, len[2])), 0.0f));
+  } else {       // shoelace over the cyclic node order
+    float x[4], y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int nd = cn[4 * c + j]; x[j] = pos[2 * nd]; y[j] = pos[2 * nd + 1]; }
+    auto cr = [&](int a, int b) { return __fsub_rn(__fmul_rn(x[a], y[b]), __fmul_rn(x[b], y[a])); };
+    const float sh = __fadd_rn(__fadd_rn(__fadd_rn(cr(0, 1), cr(1, 2)), cr(2, 3)), cr(3, 0));
+    cells_area[c] = __fmul_rn(0.5f, fabsf(sh));
+  }
+}
+
 static int bits_for(long long n) {
   int b = 1;
   while ((1LL << b) < n) ++b;
@@ -296,6 +454,64 @@ extern "C" int fvgn_connectivity_tables(const float* mesh_pos, const int32_t* no
   FVGN_LAUNCH_CHECK();
   cell_finalize<<<cdiv(n_cells, 256), 256, 0, st>>>(mesh_pos, face, cells_face, face_type, face_length, centroid, n_cells, n_faces,
                                                     cells_type, unit_norm_v, cells_area);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t fvgn_connectivity_poly_workspace_bytes(int n_cells) {
+  if (n_cells <= 0) return 256;
+  return carve_conn(nullptr, n_cells, 4).total;
+}
+
+extern "C" int fvgn_connectivity_poly_faces(const int32_t* cells4, int n_cells, int n_nodes, int32_t* cells_node4, int* n_faces_host,
+                                            void* workspace, size_t workspace_bytes, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(n_cells > 0 && n_nodes > 0, "empty mesh");
+  FVGN_CHECK_ARG(cells4 && cells_node4 && n_faces_host && workspace, "NULL pointer");
+  FVGN_CHECK_ARG((long long)n_cells * 4 < 2147483647LL, "4*C must fit int32");
+  ConnWs w = carve_conn(workspace, n_cells, 4);
+  if (workspace_bytes < w.total) { set_error("connectivity workspace too small: %zu < %zu", workspace_bytes, w.total); return FVGN_E_WORKSPACE; }
+  cudaStream_t st = as_stream(stream);
+  const int n = 4 * n_cells;
+  canon_cells_pack_edges_poly<<<cdiv(n_cells, 256), 256, 0, st>>>(cells4, n_cells, cells_node4, w.keys_in, w.vals_in);
+  FVGN_LAUNCH_CHECK();
+  size_t tmp = w.cub_bytes;
+  FVGN_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, n, 0, 64, st));  // (the padding key is all ones)
+  int* flags = reinterpret_cast<int*>(w.keys_in);
+  head_flags_poly<<<cdiv(n, 256), 256, 0, st>>>(w.keys_out, n, flags);
+  FVGN_LAUNCH_CHECK();
+  tmp = w.cub_bytes;
+  FVGN_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, tmp, flags, w.face_id, n, st));
+  FVGN_CUDA(cudaMemcpyAsync(n_faces_host, w.face_id + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  FVGN_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int fvgn_connectivity_poly_tables(const float* mesh_pos, const int32_t* node_type, const int32_t* cells_node4, int n_cells,
+                                             int n_nodes, int n_faces, int face_rule, int32_t* face, int32_t* cells_face4,
+                                             int32_t* neighbour_cell, int32_t* face_type, int32_t* cells_type, float* face_length,
+                                             float* unit_norm_v, float* centroid, float* cells_area, float* cell_factor4,
+                                             void* workspace, size_t workspace_bytes, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(n_cells > 0 && n_nodes > 0 && n_faces > 0, "empty mesh");
+  FVGN_CHECK_ARG(face_rule == 0 || face_rule == 1, "face_rule must be 0 (A) or 1 (B)");
+  FVGN_CHECK_ARG(mesh_pos && node_type && cells_node4 && face && cells_face4 && neighbour_cell && face_type && cells_type &&
+                 face_length && unit_norm_v && centroid && cells_area && cell_factor4 && workspace, "NULL pointer");
+  ConnWs w = carve_conn(workspace, n_cells, 4);
+  if (workspace_bytes < w.total) { set_error("connectivity workspace too small"); return FVGN_E_WORKSPACE; }
+  cudaStream_t st = as_stream(stream);
+  const int n = 4 * n_cells;
+  const unsigned init[2] = {0xffffffffu, 0u};
+  FVGN_CUDA(cudaMemcpyAsync(w.minmax, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  cell_geometry_poly<<<cdiv(n_cells, 256), 256, 0, st>>>(mesh_pos, cells_node4, n_cells, centroid, cell_factor4);
+  FVGN_LAUNCH_CHECK();
+  faces_from_sorted_poly<<<cdiv(n, 256), 256, 0, st>>>(w.keys_out, w.vals_out, w.face_id, n, n_cells, n_faces, mesh_pos, cells_node4, face,
+                                                       cells_face4, neighbour_cell);
+  FVGN_LAUNCH_CHECK();
+  face_geometry<<<cdiv(n_faces, 256), 256, 0, st>>>(mesh_pos, face, n_faces, face_length, w.minmax);
+  FVGN_LAUNCH_CHECK();
+  face_typing<<<cdiv(n_faces, 256), 256, 0, st>>>(mesh_pos, node_type, face, n_faces, face_rule, w.minmax, face_type);
+  FVGN_LAUNCH_CHECK();
+  cell_finalize_poly<<<cdiv(n_cells, 256), 256, 0, st>>>(mesh_pos, cells_node4, face, cells_face4, face_type, face_length, centroid, n_cells,
+                                                         n_faces, cells_type, unit_norm_v, cells_area);
   FVGN_LAUNCH_CHECK();
   return 0;
 }

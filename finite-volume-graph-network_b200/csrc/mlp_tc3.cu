@@ -620,6 +620,25 @@ __global__ void __launch_bounds__(256) cell_mean_kernel(const float* __restrict_
   *reinterpret_cast<float4*>(out + (size_t)c * 64 + hl * 4) = cell_agg4(node_agg, cells_node_T, (size_t)C, c, hl * 4);
 }
 
+// tri / quad hybrid meshes: the same two means over a [4,C] table (cell_agg4_poly); the fused kernels then take the per-cell row
+// (cells_node_T = NULL convention), so every math mode handles quad cells without a k-wide gather of its own
+__global__ void __launch_bounds__(256) cell_mean_poly_kernel(const float* __restrict__ node_agg, const int32_t* __restrict__ cells_node4_T, int C,
+                                                             float* __restrict__ out, unsigned char* __restrict__ out_split) {
+  const int gid = blockIdx.x * 256 + threadIdx.x;
+  const int c = gid >> 4, hl = gid & 15;
+  if (c >= C) return;
+  const float4 v = cell_agg4_poly(node_agg, cells_node4_T, (size_t)C, c, hl * 4);
+  if (out) *reinterpret_cast<float4*>(out + (size_t)c * 64 + hl * 4) = v;
+  if (out_split) {
+    uint2 q0, q1;
+    split2_pair(v.x * ASCALE, v.y * ASCALE, q0.x, q1.x);
+    split2_pair(v.z * ASCALE, v.w * ASCALE, q0.y, q1.y);
+    unsigned char* o = out_split + (size_t)c * 256 + hl * 8;
+    *reinterpret_cast<uint2*>(o) = q0;
+    *reinterpret_cast<uint2*>(o + 128) = q1;
+  }
+}
+
 // Forward weights: blockIdx.x = weight matrix, blockIdx.y = slice of its tiles (every CTA of a matrix finds the same max|W| itself:
 // 196 KB at most, L2-resident).  W [n_valid, k_valid] fp32 row-major -> scale 2^s with max|W| 2^s in [2^13, 2^14)
 // (found here, on the device: graph-capturable, no host round trip) -> steps [kt][2 fp16 splits][128 rows][64 k], each sub-tile a
@@ -833,6 +852,16 @@ int tc3_cell_mean_split(const float* node_agg, const int32_t* cells_node_T, int 
   FVGN_CHECK_ARG(al16(node_agg) && al16(out), "buffers must be 16B aligned");
   if (n_cells == 0) return 0;
   x3::cell_mean_split_kernel<<<cdiv(n_cells * 16, 256), 256, 0, st>>>(node_agg, cells_node_T, n_cells, reinterpret_cast<unsigned char*>(out));
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc3_cell_mean_poly(const float* node_agg, const int32_t* cells_node4_T, int n_cells, float* out, void* out_split, cudaStream_t st) {
+  FVGN_CHECK_ARG(n_cells >= 0 && (n_cells == 0 || (node_agg && cells_node4_T && (out || out_split))), "NULL input");
+  FVGN_CHECK_ARG(al16(node_agg) && al16(out) && al16(out_split), "buffers must be 16B aligned");
+  if (n_cells == 0) return 0;
+  x3::cell_mean_poly_kernel<<<cdiv((long long)n_cells * 16, 256), 256, 0, st>>>(node_agg, cells_node4_T, n_cells, out,
+                                                                                reinterpret_cast<unsigned char*>(out_split));
   FVGN_LAUNCH_CHECK();
   return 0;
 }

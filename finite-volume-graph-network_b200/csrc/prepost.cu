@@ -47,6 +47,22 @@ __global__ void interp_nodes_kernel(const float* __restrict__ nf, int ld, int co
   }
 }
 
+// tri / quad hybrid meshes: [4,C] node table (4th row -1 on triangles) and four weights per cell (oracle/fvgn_oracle.py:
+// ((f0 a + f1 b) + f2 c) + f3 d, the last term only where the cell has a 4th node)
+__global__ void interp_cells_poly_kernel(const float* __restrict__ nf, int ld, int col0, int width, const int32_t* __restrict__ cn4T,
+                                         const float* __restrict__ cf4, int C, float* __restrict__ on_cell) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  const int n0 = cn4T[i], n1 = cn4T[(size_t)C + i], n2 = cn4T[2 * (size_t)C + i], n3 = cn4T[3 * (size_t)C + i];
+  const float f0 = cf4[4 * i], f1 = cf4[4 * i + 1], f2 = cf4[4 * i + 2], f3 = cf4[4 * i + 3];
+  for (int w = 0; w < width; ++w) {
+    const float a = nf[(size_t)n0 * ld + col0 + w], b = nf[(size_t)n1 * ld + col0 + w], c = nf[(size_t)n2 * ld + col0 + w];
+    float v = (f0 * a + f1 * b) + f2 * c;
+    if (n3 >= 0) v = v + f3 * nf[(size_t)n3 * ld + col0 + w];
+    on_cell[(size_t)i * width + w] = v;
+  }
+}
+
 __device__ __forceinline__ bool is_interior(float t) { return t == 0.0f || t == 5.0f; }  // NORMAL or OUTFLOW (:931-934)
 
 __global__ void assemble_edge_attr_kernel(const float* __restrict__ uv, int ld_uv, const float* __restrict__ cen, const int32_t* __restrict__ nc,
@@ -228,6 +244,40 @@ __global__ void integrator_kernel(const float* __restrict__ dec, const float* __
   du[2 * (size_t)c] = rhs * (-A_x - inv_rho * P_x) + D_x;      // (:320-331)
   du[2 * (size_t)c + 1] = rhs * (-A_y - inv_rho * P_y) + D_y;
   if (cont) cont[c] = (Ct[0] + Ct[1]) + Ct[2];
+}
+
+// tri / quad hybrid meshes: [4,C] face table (-1 = no 4th face), unv [C,4,2]; the first three terms are summed exactly as above, the 4th
+// is added where it exists (oracle/fvgn_oracle.py::_integrator_poly)
+__global__ void integrator_poly_kernel(const float* __restrict__ dec, const float* __restrict__ unv, const float* __restrict__ fa,
+                                       const int32_t* __restrict__ cf4T, int C, float inv_rho, float rhs, float* __restrict__ du,
+                                       float* __restrict__ cont) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float A0[4], A1[4], P0[4], P1[4], D0[4], D1[4], Ct[4];
+  const bool quad = cf4T[3 * (size_t)C + c] >= 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int f = cf4T[(size_t)k * C + c];
+    if (f < 0) { A0[k] = A1[k] = P0[k] = P1[k] = D0[k] = D1[k] = Ct[k] = 0.f; continue; }
+    const float u = dec[5 * (size_t)f], v = dec[5 * (size_t)f + 1], p = dec[5 * (size_t)f + 2];
+    D0[k] = dec[5 * (size_t)f + 3];
+    D1[k] = dec[5 * (size_t)f + 4];
+    const float nx = unv[(size_t)c * 8 + 2 * k], ny = unv[(size_t)c * 8 + 2 * k + 1];
+    const float a = fa[f];
+    A0[k] = ((u * u) * nx + (u * v) * ny) * a;
+    A1[k] = ((v * u) * nx + (v * v) * ny) * a;
+    P0[k] = (p * nx) * a;
+    P1[k] = (p * ny) * a;
+    Ct[k] = (u * nx + v * ny) * a;
+  }
+  float A_x = (A0[0] + A0[1]) + A0[2], A_y = (A1[0] + A1[1]) + A1[2];
+  float P_x = (P0[0] + P0[1]) + P0[2], P_y = (P1[0] + P1[1]) + P1[2];
+  float D_x = (D0[0] + D0[1]) + D0[2], D_y = (D1[0] + D1[1]) + D1[2];
+  float Cs = (Ct[0] + Ct[1]) + Ct[2];
+  if (quad) { A_x = A_x + A0[3]; A_y = A_y + A1[3]; P_x = P_x + P0[3]; P_y = P_y + P1[3]; D_x = D_x + D0[3]; D_y = D_y + D1[3]; Cs = Cs + Ct[3]; }
+  du[2 * (size_t)c] = rhs * (-A_x - inv_rho * P_x) + D_x;
+  du[2 * (size_t)c + 1] = rhs * (-A_y - inv_rho * P_y) + D_y;
+  if (cont) cont[c] = Cs;
 }
 
 // ------------------------------------------------------------------------------------------------ a12
@@ -535,6 +585,28 @@ extern "C" int fvgn_integrator_fwd(const float* decoded, const float* unv, const
   if (n_cells <= 0) return 0;
   integrator_kernel<<<cdiv(n_cells, 256), 256, 0, as_stream(stream)>>>(decoded, unv, face_area, cells_face_T, n_cells, 1.0f / rho, rhs_coef,
                                                                        delta_u, continuity);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fvgn_integrator_fwd_poly(const float* decoded, const float* unv4, const float* face_area, const int32_t* cells_face4_T, int n_cells,
+                                        float rho, float rhs_coef, float* delta_u, float* continuity, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(decoded && unv4 && face_area && cells_face4_T && delta_u, "NULL pointer");
+  FVGN_CHECK_ARG(rho != 0.f, "rho must be non-zero");
+  if (n_cells <= 0) return 0;
+  integrator_poly_kernel<<<cdiv(n_cells, 256), 256, 0, as_stream(stream)>>>(decoded, unv4, face_area, cells_face4_T, n_cells, 1.0f / rho, rhs_coef,
+                                                                            delta_u, continuity);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fvgn_interp_cells_poly(const float* node_field, int ld, int col0, int width, const int32_t* cells_node4_T, const float* cell_factor4,
+                                      int n_cells, float* on_cell, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(node_field && cells_node4_T && cell_factor4 && on_cell, "NULL pointer");
+  FVGN_CHECK_ARG(width >= 1 && col0 >= 0 && ld >= col0 + width, "bad column range");
+  if (n_cells <= 0) return 0;
+  interp_cells_poly_kernel<<<cdiv(n_cells, 256), 256, 0, as_stream(stream)>>>(node_field, ld, col0, width, cells_node4_T, cell_factor4, n_cells,
+                                                                              on_cell);
   FVGN_LAUNCH_CHECK();
   return 0;
 }

@@ -52,7 +52,8 @@ class Batch(Data):
             n = g.num_nodes
             for k in cols:
                 v = getattr(g, k)
-                cols[k].append(v + off if _is_index(k) else v)
+                # (entries < 0 are the padding of [4, C] tri / quad tables and stay as they are)
+                cols[k].append((torch.where(v >= 0, v + off, v) if v.shape[0] == 4 else v + off) if _is_index(k) else v)
                 if k in iptr:
                     iptr[k].append(iptr[k][-1] + int(v.shape[-1]))
             bvec.append(torch.full((n,), gi, dtype=torch.long, device=g.x.device))

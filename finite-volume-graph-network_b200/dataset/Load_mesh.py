@@ -181,7 +181,7 @@ class PinnedBatcher:
                 flat = buf.t()  # [r, tot] view (strided)
                 o = 0
                 for v, off in zip(vs, offs[:-1]):
-                    flat[:, o:o + v.shape[-1]] = v + int(off)
+                    flat[:, o:o + v.shape[-1]] = torch.where(v >= 0, v + int(off), v) if r == 4 else v + int(off)
                     o += v.shape[-1]
                 setattr(out, k, flat)
             else:

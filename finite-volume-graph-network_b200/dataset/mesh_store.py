@@ -105,8 +105,12 @@ def open_store(dataset_dir, split, mode="r"):
     h5 = os.path.join(dataset_dir, f"{split}.h5")
     if mode == "r" and os.path.exists(h5):
         try:
+            import types
+
             import h5py
 
+            if not isinstance(h5py, types.ModuleType):
+                raise ImportError("h5py is not installed")
             return h5py.File(h5, "r")
         except ImportError as e:
             raise RuntimeError(f"{h5} needs h5py, which is not installed: convert to {split}.fvgn.npz with fvgn_b200.convert") from e

@@ -329,6 +329,18 @@ def cell_mean(node_agg, cells_node_T):
     return out
 
 
+def cell_mean_poly(node_agg, cells_node4_T, want_fp32=True, split_out=None):
+    """tri / quad hybrid meshes: per-cell mean over the k = 3 or 4 node aggregates ([4,C] table, 4th row -1 on triangles) as fp32 [C,64]
+    and / or into the split fp16 shadow [C,2,64] (fvgn_cell_mean_poly)"""
+    _cf(node_agg, "node_agg"), _ci(cells_node4_T, "cells_node4_T", 4)
+    Cn = cells_node4_T.shape[1]
+    out = torch.empty((Cn, 64), dtype=torch.float32, device=node_agg.device) if want_fp32 else None
+    _count(1)
+    with _timed("cell_mean"):
+        check(_lib.lib().fvgn_cell_mean_poly(_p(node_agg), _p(cells_node4_T), Cn, _p(out), _p(split_out), _stream()), "cell_mean_poly")
+    return out
+
+
 def _cell_table_ok(cells_node_T, node_agg, n_cells, who):
     """cells_node_T [3,C] int32 (mp_times >= 2: node_agg is per node), or None (mp_times = 1: node_agg is the per-cell aggregate [C,64])"""
     if cells_node_T is None:
@@ -421,7 +433,8 @@ def gn_block_fwd_inplace_split(cell_mlp: MlpRef, edge_mlp: MlpRef, x, e, node_ag
     _req(x, torch.float32, "x", 2), _req(e, torch.float32, "edge_attr", 2), _req(node_agg, torch.float32, "node_agg", 2)
     _ci(neighbour_cell, "neighbour_cell", 2)
     Cn, F = x.shape[0], e.shape[0]
-    _cell_table_ok(cells_node_T, node_agg, Cn, "gn_block_fwd_inplace_split")
+    if cells_node_T is None or cells_node_T.shape[0] != 4:
+        _cell_table_ok(cells_node_T, node_agg, Cn, "gn_block_fwd_inplace_split")
     if not (x.is_contiguous() and e.is_contiguous() and node_agg.is_contiguous()) or x.shape[1] != HID or e.shape[1] != HID \
             or neighbour_cell.shape[1] != F:
         raise ValueError("gn_block_fwd_inplace_split: bad shapes/strides")
@@ -434,7 +447,10 @@ def gn_block_fwd_inplace_split(cell_mlp: MlpRef, edge_mlp: MlpRef, x, e, node_ag
     L = _lib.lib()
     _count(3)
     with _timed("cell_mean"):
-        check(L.fvgn_cell_mean_split(_p(node_agg), _p(cells_node_T), Cn, _p(cell_mean_split), _stream()), "cell_mean_split")
+        if cells_node_T is not None and cells_node_T.shape[0] == 4:  # tri / quad hybrid mesh
+            check(L.fvgn_cell_mean_poly(_p(node_agg), _p(cells_node_T), Cn, None, _p(cell_mean_split), _stream()), "cell_mean_poly")
+        else:
+            check(L.fvgn_cell_mean_split(_p(node_agg), _p(cells_node_T), Cn, _p(cell_mean_split), _stream()), "cell_mean_split")
     with _timed("cell_block"):
         check(L.fvgn_cell_block_fwd_split(C.byref(cell_mlp.struct), _p(x), _p(cell_mean_split), Cn, _p(x_prime_split), _stream()),
               "cell_block_fwd_split")
@@ -454,6 +470,26 @@ def build_connectivity(cells, mesh_pos, node_type, face_rule="B"):
     Cn, N = cells.shape[0], mesh_pos.shape[0]
     dev = cells.device
     L = _lib.lib()
+    if cells.shape[1] == 4:  # tri / quad hybrid mesh: [C,4] tables, 4th column -1 on triangles (fvgn_connectivity_poly_*)
+        nbytes = L.fvgn_connectivity_poly_workspace_bytes(Cn)
+        ws = _ws(nbytes, dev)
+        cells_node = torch.empty((Cn, 4), dtype=torch.int32, device=dev)
+        nf = C.c_int(0)
+        check(L.fvgn_connectivity_poly_faces(_p(cells), Cn, N, _p(cells_node), C.byref(nf), _p(ws), nbytes, _stream()), "connectivity_poly_faces")
+        F = nf.value
+        i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
+        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        t = dict(cells_node=cells_node, face=i32(2, F), cells_face=i32(Cn, 4), neighbour_cell=i32(2, F), face_type=i32(F, 1), cells_type=i32(Cn, 1),
+                 face_length=f32(F, 1), unit_norm_v=f32(Cn, 4, 2), centroid=f32(Cn, 2), cells_area=f32(Cn, 1), cell_factor=f32(Cn, 4))
+        check(L.fvgn_connectivity_poly_tables(_p(mesh_pos), _p(node_type), _p(cells_node), Cn, N, F, {"A": 0, "B": 1}[face_rule], _p(t["face"]),
+                                              _p(t["cells_face"]), _p(t["neighbour_cell"]), _p(t["face_type"]), _p(t["cells_type"]),
+                                              _p(t["face_length"]), _p(t["unit_norm_v"]), _p(t["centroid"]), _p(t["cells_area"]),
+                                              _p(t["cell_factor"]), _p(ws), nbytes, _stream()), "connectivity_poly_tables")
+        t["mesh_pos"], t["node_type"] = mesh_pos, node_type.view(-1, 1)
+        t["cell_k"] = (cells_node >= 0).sum(1).to(torch.int32)
+        return t
+    if cells.shape[1] != 3:
+        raise ValueError(f"cells must be [C,3] (triangles) or [C,4] (tri / quad, -1 padded), got {tuple(cells.shape)}")
     nbytes = L.fvgn_connectivity_workspace_bytes(Cn)
     ws = _ws(nbytes, dev)
     cells_node = torch.empty((Cn, 3), dtype=torch.int32, device=dev)
@@ -489,6 +525,18 @@ def build_csr(dst, n_dst):
 # ------------------------------------------------------------------------------------------------ pre / post
 def interp_nodes(node_field, col0, width, cells_node_T=None, cell_factor=None, face_node=None, want_cell=True, want_face=True):
     _req(node_field, torch.float32, "node_field", 2)
+    if want_cell and cells_node_T is not None and cells_node_T.dim() == 2 and cells_node_T.shape[0] == 4:
+        # tri / quad hybrid mesh: cells through fvgn_interp_cells_poly, faces through the common kernel
+        _ci(cells_node_T, "cells_node4_T", 4), _cf(cell_factor, "cell_factor4")
+        Cn = cells_node_T.shape[1]
+        if tuple(cell_factor.shape) != (Cn, 4):
+            raise ValueError(f"cell_factor must be [{Cn}, 4] for a [4,C] node table, got {tuple(cell_factor.shape)}")
+        on_cell = torch.empty((Cn, width), dtype=torch.float32, device=node_field.device)
+        _count(1)
+        check(_lib.lib().fvgn_interp_cells_poly(_p(node_field), _ld(node_field), col0, width, _p(cells_node_T), _p(cell_factor), Cn, _p(on_cell),
+                                                _stream()), "interp_cells_poly")
+        on_face = interp_nodes(node_field, col0, width, face_node=face_node, want_cell=False, want_face=True)[1] if want_face else None
+        return on_cell, on_face
     if want_cell:
         _ci(cells_node_T, "cells_node_T", 3), _cf(cell_factor, "cell_factor")
     if want_face:
@@ -591,8 +639,18 @@ def face_area_bn_fwd(face_type_len, cell_area, neighbour_cell, dt, training, bn_
 
 
 def integrator_fwd(decoded, unv, face_area, cells_face_T, rho, rhs_coef=1.0, want_continuity=False):
-    _ci(cells_face_T, "cells_face_T", 3)
+    poly = cells_face_T.dim() == 2 and cells_face_T.shape[0] == 4  # tri / quad hybrid mesh: [4,C] face table, unv [C,4,2]
+    _ci(cells_face_T, "cells_face_T", 4 if poly else 3)
     Cn = cells_face_T.shape[1]
+    if poly:
+        if tuple(unv.shape) != (Cn, 4, 2) or not (decoded.is_contiguous() and unv.is_contiguous() and face_area.is_contiguous()):
+            raise ValueError(f"integrator_fwd: a [4,C] face table needs contiguous unv [{Cn},4,2], got {tuple(unv.shape)}")
+        du = torch.empty((Cn, 2), dtype=torch.float32, device=decoded.device)
+        cont = torch.empty((Cn, 1), dtype=torch.float32, device=decoded.device) if want_continuity else None
+        _count(1)
+        check(_lib.lib().fvgn_integrator_fwd_poly(_p(decoded), _p(unv), _p(face_area), _p(cells_face_T), Cn, float(rho), float(rhs_coef), _p(du),
+                                                  _p(cont), _stream()), "integrator_fwd_poly")
+        return du, cont
     dev = decoded.device
     du = torch.empty((Cn, 2), dtype=torch.float32, device=dev)
     cont = torch.empty((Cn, 1), dtype=torch.float32, device=dev) if want_continuity else None

@@ -21,8 +21,9 @@ class MeshTopology:
     def __init__(self, neighbour_cell, face_node, cells_node_T, cells_face_T, n_nodes):
         self.nc = ops.as_i32(neighbour_cell)      # [2,F]
         self.fn = ops.as_i32(face_node)           # [2,F]
-        self.cnT = ops.as_i32(cells_node_T)       # [3,C]
-        self.cfT = ops.as_i32(cells_face_T)       # [3,C]
+        self.cnT = ops.as_i32(cells_node_T)       # [3,C]; [4,C] with -1 padding on tri / quad hybrid meshes
+        self.cfT = ops.as_i32(cells_face_T)       # [3,C] / [4,C]
+        self.poly = self.cnT.shape[0] == 4
         self.F = int(self.nc.shape[1])
         self.C = int(self.cnT.shape[1])
         self.N = int(n_nodes)
@@ -36,11 +37,17 @@ class MeshTopology:
         stable CSR over cat(edge_index[0], edge_index[1]) == the reference's scatter_add order; no second gather: idx = None)."""
         if mp_times >= 2:
             return _Agg(self.node_ptr, self.node_items, self.N, self.cnT, self.fn)
+        if self.poly:
+            ptr, items = self.__dict__.get("_cff") or self.__dict__.setdefault("_cff", ops.build_csr(self.nc.reshape(-1), self.C))
+            return _Agg(ptr, items, self.C, None, self.nc)
         ptr, items = self.backward_tables()["cell_from_face"]
         return _Agg(ptr, items, self.C, None, self.nc)
 
     def backward_tables(self):
         """CSR transposes needed by the backward kernels: cell<-(face,side), node<-(cell,k), face<-(cell,k)."""
+        if self.poly:
+            raise NotImplementedError("training on tri / quad hybrid meshes ([4,C] tables) is not built: the backward's CSR transposes and "
+                                      "per-cell 1/k scales take [3,C] tables (inference / rollout is: BASELINE configs[3])")
         if self._bwd is None:
             self._bwd = dict(
                 cell_from_face=ops.build_csr(self.nc.reshape(-1), self.C),

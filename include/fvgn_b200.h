@@ -255,6 +255,29 @@ FVGN_API int fvgn_loss_finish(int n_graphs, int mode, float w_mom, float w_uv, f
                      fvgn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Tri / quad hybrid meshes (BASELINE configs[3]).  The reference processes triangles only (its quad branch,
+ * Extract_mesh/parse_tfrecord_refactor.py:1459-1491, is never reached: SURVEY.md section 0 item 5); these entry points take cells
+ * with k = 3 or 4 nodes as [C,4] tables whose 4th column is -1 on triangles, follow the reference's rules with "3" read as "k"
+ * (oracle/fvgn_oracle_poly.py) and reduce to the triangle entry points bit for bit on all-triangle meshes.  Inference only: the
+ * per-cell mean of the node aggregates (fvgn_cell_mean_poly, fp32 [C,64] and / or the split fp16 shadow [C,2,64]) feeds the
+ * CellBlock entry points through their cells_node_T == NULL convention in every math mode. */
+FVGN_API size_t fvgn_connectivity_poly_workspace_bytes(int n_cells);
+FVGN_API int fvgn_connectivity_poly_faces(const int32_t* cells4 /*[C,4], -1 padded*/, int n_cells, int n_nodes, int32_t* cells_node4 /*[C,4]*/,
+                                 int* n_faces_host, void* workspace, size_t workspace_bytes, fvgn_stream_t stream); /* synchronous */
+FVGN_API int fvgn_connectivity_poly_tables(const float* mesh_pos, const int32_t* node_type, const int32_t* cells_node4, int n_cells, int n_nodes,
+                                  int n_faces, int face_rule, int32_t* face /*[2,F]*/, int32_t* cells_face4 /*[C,4]*/,
+                                  int32_t* neighbour_cell /*[2,F]*/, int32_t* face_type, int32_t* cells_type, float* face_length,
+                                  float* unit_norm_v /*[C,4,2]*/, float* centroid, float* cells_area, float* cell_factor4 /*[C,4]*/,
+                                  void* workspace, size_t workspace_bytes, fvgn_stream_t stream);
+FVGN_API int fvgn_cell_mean_poly(const float* node_agg /*[N,64]*/, const int32_t* cells_node4_T /*[4,C]*/, int n_cells,
+                        float* cell_mean /*[C,64] or NULL*/, void* cell_mean_split /*[C,2,64] fp16 or NULL*/, fvgn_stream_t stream);
+FVGN_API int fvgn_interp_cells_poly(const float* node_field, int ld, int col0, int width, const int32_t* cells_node4_T /*[4,C]*/,
+                           const float* cell_factor4 /*[C,4]*/, int n_cells, float* on_cell /*[C,width]*/, fvgn_stream_t stream);
+FVGN_API int fvgn_integrator_fwd_poly(const float* decoded /*[F,5]*/, const float* unv4 /*[C,4,2]*/, const float* face_area,
+                             const int32_t* cells_face4_T /*[4,C]*/, int n_cells, float rho, float rhs_coef, float* delta_u,
+                             float* continuity /*or NULL*/, fvgn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Backward (training) path — the reference gets these from torch autograd over train.py:194-218.  Strict fp32 (FFMA).
  * MLP gradients come back in one buffer `grads` of fvgn_mlp_grad_floats(k_in) floats laid out as
  *   dW1[128,k_in] | dW2[128,128] | dW3[128,128] (rows >= n_out unused) | db1[128] | db2[128] | db3[128] | dLN_w[128] | dLN_b[128].

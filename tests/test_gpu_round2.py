@@ -131,7 +131,9 @@ def test_graphed_replay_then_eval_reads_fresh_weights(fv, golden, mode):
             opt2.step()
 
     eager(2)  # the two warm-up steps of GraphedTrainStep are real steps
-    tol = 2e-4 if mode == "bf16x3" else 5e-2
+    # (graphed: fused AdamW; twin: foreach AdamW; lr 1e-2 amplifies their rounding differences step by step — a STALE tile set is off by
+    # the whole weight update, orders of magnitude more: the second assertion below)
+    tol = 2e-3 if mode == "bf16x3" else 5e-2
     prev = None
     for nrep in (1, 2):
         for _ in range(nrep):
@@ -141,8 +143,8 @@ def test_graphed_replay_then_eval_reads_fresh_weights(fv, golden, mode):
         e = max(H.rel_l2(a[0].cpu(), b[0].cpu()), H.rel_l2(a[1].cpu(), b[1].cpu()))
         assert e < tol, (mode, nrep, e)
         if prev is not None:  # and the evaluation moved with the weights (a frozen tile set would repeat the previous outputs)
-            assert H.rel_l2(a[0].cpu(), prev[0].cpu()) > 10 * tol or mode == "bf16", "eval output did not change after further replays"
-            assert not torch.equal(a[0], prev[0])
+            moved = H.rel_l2(a[0].cpu(), prev[0].cpu())
+            assert moved > 10 * e, ("eval output did not follow the replays' weight updates", mode, moved, e)
         prev = a
 
 
