@@ -390,6 +390,24 @@ def native(args, rank, world, local_rank):
     if not args.no_training:
         torch.cuda.empty_cache()
         train = training_measure(args, rank, world, dev, meshes, dist)
+    if not args.no_foil_leg and (args.workload, args.math) != ("foil16", "bf16"):
+        # BASELINE configs[2] on every N: airfoil-shaped meshes (~5k nodes, far field), bf16 MLP tiles, data-parallel training
+        import copy
+
+        a2 = copy.copy(args)
+        a2.workload, a2.math = "foil16", "bf16"
+        torch.cuda.empty_cache()
+        fm = measure_forward(a2, "foil16", "bf16", min(args.steps, 10), rank, local_rank, dev, dist)
+        ft = training_measure(a2, rank, world, dev, fm["meshes"], dist, fresh=False) if not args.no_training else None
+        if rank == 0:
+            result["foil16_bf16"] = {
+                "workload": "foil16", "description": WORKLOADS["foil16"][3] + " (BASELINE configs[2])", "math": "bf16", "dtype": DTYPES["bf16"],
+                "cells_per_rank": fm["C"], "faces_per_rank": fm["F"], "nodes_per_rank": fm["N"], "graphs_per_rank": fm["graphs"],
+                "rollout": {"value": fm["total_cells"] * fm["steps"] / (fm["ms"] * 1e-3), "unit": "cell-updates/s", "ms_per_step": fm["ms"] / fm["steps"],
+                            "steps": fm["steps"], "e2e": {"value": fm["total_cells"] * fm["steps"] / (fm["e2e_ms"] * 1e-3), "unit": "cell-updates/s"},
+                            "gpu_launches": fm["launches"], "clocks": fm["clocks"]},
+                "training": ft}
+        del fm
     if rank == 0:
         if train is not None:
             result["training"] = train
@@ -427,7 +445,7 @@ def _shallow(bag):
     return out
 
 
-def training_measure(args, rank, world, dev, meshes, dist):
+def training_measure(args, rank, world, dev, meshes, dist, fresh=True):
     """training graphs/s: per step = H2D of the batch's node fields (e2e leg only) + train_datapreprocessing on device (a2) +
     FVGN.forward (training) + compute_FVM_loss + backward (all in libfvgn_b200 kernels) + flat-bucket gradient all-reduce
     (N>1, NCCL) + AdamW (train.py:150-225).  Strict fp32."""
@@ -449,6 +467,11 @@ def training_measure(args, rank, world, dev, meshes, dist):
     model.set_math_mode(train_math)  # forward arithmetic; the backward kernels are FFMA
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3)  # train.py:45, get_param.py:80
     bucket = parallel.GradBucket(model.parameters())
+    reducer = None
+    if world > 1 and train_math != "fp32" and not args.no_overlap:
+        # tensor-core training path: the gradient all-reduce is issued group by group from inside the backward (overlapped with it)
+        reducer = parallel.OverlappedGradReducer(model, n_groups=args.dp_groups).attach(model)
+    dp_sync = (lambda: None) if reducer is not None else bucket.all_reduce_mean_
     node_host = gn0.x.cpu().pin_memory()
     node_dev = gn0.x
     loss_host = torch.empty(5, dtype=torch.float32).pin_memory()
@@ -462,7 +485,7 @@ def training_measure(args, rank, world, dev, meshes, dist):
         loss = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=out[3],
                                    target_face_uvp_normalized=out[4], predicted_delta_u=out[1], target_delta_u=out[2])
         loss[0].backward()
-        bucket.all_reduce_mean_()
+        dp_sync()
         opt.step()
         if h2d:
             loss_host.copy_(torch.stack([loss[0].detach().reshape(()), loss[2].mean(), loss[3].mean(), loss[4].mean(), loss[0].detach().reshape(())]),
@@ -484,7 +507,7 @@ def training_measure(args, rank, world, dev, meshes, dist):
             opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=True, fused=True)  # one fused multi-tensor kernel per chunk (the foreach path divides by 0-dim step tensors one parameter at a time: 524 launches)
             gn_s, ge_s, gc_s = _shallow(gn0), _shallow(ge0), _shallow(gc0)
             gn_s.x = node_dev.clone()
-            graphed = fv.GraphedTrainStep(model, opt, p, gn_s, ge_s, gc_s, RHO, MU, DT, all_reduce=bucket.all_reduce_mean_ if world > 1 else None)
+            graphed = fv.GraphedTrainStep(model, opt, p, gn_s, ge_s, gc_s, RHO, MU, DT, all_reduce=dp_sync if world > 1 else None)
 
             def tstep(h2d):  # noqa: F811
                 if h2d:
@@ -524,57 +547,62 @@ def training_measure(args, rank, world, dev, meshes, dist):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(tms[0]), float(tms[1])
     g = len(meshes) * world
-    # ---------------- the reference's DataLoader regime (train.py:119-160): every batch is 16 random (mesh, time step) samples, so the
-    # batch TOPOLOGY changes every step and one captured graph cannot be replayed: collate + CSR tables + the eager step, per step
-    import random
+    fresh_ms, fsteps = None, 0
+    if fresh:
+        # ---------------- the reference's DataLoader regime (train.py:119-160): every batch is 16 random (mesh, time step) samples, so the
+        # batch TOPOLOGY changes every step and one captured graph cannot be replayed: collate + CSR tables + the eager step, per step
+        import random
 
-    kind, kw, _, _ = WORKLOADS[args.workload]
-    pool = list(lists)
-    for i in range(len(meshes)):
-        m = fv.synthetic.make(kind, seed=77000 + 1000 * rank + i, T=3, **kw)
-        t = lambda a, dt: torch.as_tensor(a).to(dt).to(dev)
-        tab = fv.ops.build_connectivity(t(m["cells"], torch.int32), t(m["mesh_pos"], torch.float32), t(m["node_type"], torch.int32), "B")
-        pool.append(fv.dataset.build_graphs(tab, m["velocity"], m["pressure"], training_pair=0, device=dev))
-    rng = random.Random(rank)
-    opt_e = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+        kind, kw, _, _ = WORKLOADS[args.workload]
+        pool = list(lists)
+        for i in range(len(meshes)):
+            m = fv.synthetic.make(kind, seed=77000 + 1000 * rank + i, T=3, **kw)
+            t = lambda a, dt: torch.as_tensor(a).to(dt).to(dev)
+            tab = fv.ops.build_connectivity(t(m["cells"], torch.int32), t(m["mesh_pos"], torch.float32), t(m["node_type"], torch.int32), "B")
+            pool.append(fv.dataset.build_graphs(tab, m["velocity"], m["pressure"], training_pair=0, device=dev))
+        rng = random.Random(rank)
+        opt_e = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
 
-    def fresh_step():
-        bl = [[_shallow(b) for b in pool[i]] for i in rng.sample(range(len(pool)), len(meshes))]
-        gn, ge, gc = fv.dataset.collate(bl)
-        gn, ge, gc, mi, mb = fv.dataset.train_datapreprocessing([gn, ge, gc])
-        opt_e.zero_grad(set_to_none=True)
-        out = model(graph=gc, graph_edge=ge, graph_node=gn, rho=RHO, mu=MU, dt=DT, edge_one_hot=9, cell_one_hot=0)
-        lo = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=out[3],
-                                 target_face_uvp_normalized=out[4], predicted_delta_u=out[1], target_delta_u=out[2])
-        lo[0].backward()
-        bucket.all_reduce_mean_()
-        opt_e.step()
+        def fresh_step():
+            bl = [[_shallow(b) for b in pool[i]] for i in rng.sample(range(len(pool)), len(meshes))]
+            gn, ge, gc = fv.dataset.collate(bl)
+            gn, ge, gc, mi, mb = fv.dataset.train_datapreprocessing([gn, ge, gc])
+            opt_e.zero_grad(set_to_none=True)
+            out = model(graph=gc, graph_edge=ge, graph_node=gn, rho=RHO, mu=MU, dt=DT, edge_one_hot=9, cell_one_hot=0)
+            lo = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=out[3],
+                                     target_face_uvp_normalized=out[4], predicted_delta_u=out[1], target_delta_u=out[2])
+            lo[0].backward()
+            dp_sync()
+            opt_e.step()
 
-    fsteps = 2 * steps
-    for _ in range(40):  # the batch sizes vary from step to step: let the caching allocator (two streams) see the range of block sizes first
-        fresh_step()
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(fsteps):
-        fresh_step()
-    t1.record()
-    barrier()
-    fresh = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(fresh, op=dist.ReduceOp.MAX)
-    fresh_ms = float(fresh[0])
+        fsteps = 2 * steps
+        for _ in range(40):  # the batch sizes vary from step to step: let the caching allocator (two streams) see the range of block sizes first
+            fresh_step()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(fsteps):
+            fresh_step()
+        t1.record()
+        barrier()
+        fresh = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(fresh, op=dist.ReduceOp.MAX)
+        fresh_ms = float(fresh[0])
     return {"metric": "training_graphs_per_sec", "value": g * steps / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms / steps, "steps": steps,
             "global_batch": g, "cells_per_rank": C, "faces_per_rank": F, "dtype": DTYPES[train_math] + (" (forward and backward GEMMs on tcgen05)" if train_math != "fp32" else " forward and backward"), "loss": p.loss, "optimizer": "AdamW lr 1e-3",
             "cell_updates_per_sec": C * world * steps / (ms * 1e-3),
             "e2e": {"value": g * steps / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / steps,
                     "h2d_bytes_per_step": int(node_host.numel() * 4), "d2h_bytes_per_step": 20,
                     "note": "pinned node fields H2D + loss D2H + host sync every step"},
-            "fresh_batches": {"value": g * fsteps / (fresh_ms * 1e-3), "unit": "graphs/s", "ms_per_step": fresh_ms / fsteps, "steps": fsteps, "cuda_graph": False,
-                              "note": f"every step a new random batch of {len(meshes)} meshes out of {2 * len(meshes)} (new topology: collate + CSR tables + "
-                                      "eager step inside the timed region; host-bound)"},
+            "fresh_batches": None if not fresh else {
+                "value": g * fsteps / (fresh_ms * 1e-3), "unit": "graphs/s", "ms_per_step": fresh_ms / fsteps, "steps": fsteps, "cuda_graph": False,
+                "note": f"every step a new random batch of {len(meshes)} meshes out of {2 * len(meshes)} (new topology: collate + CSR tables + "
+                        "eager step inside the timed region)"},
             "gpu_launches": int(launches), "final_loss": float(loss[0]),
-            "parallelism": f"dp{world} over mesh graphs, one flat fp32 gradient all-reduce (8.84 MB) per step" if world > 1 else "single GPU",
+            "parallelism": (f"dp{world} over mesh graphs; " + (f"gradient all-reduce (8.84 MB, AVG) in {args.dp_groups} groups issued from inside the backward "
+                            "(overlapped with it; parallel.OverlappedGradReducer)" if reducer is not None else "one flat fp32 gradient all-reduce (8.84 MB) per step"))
+            if world > 1 else "single GPU",
             "step": "train_datapreprocessing + FVGN.forward(train) + compute_FVM_loss + backward + grad all-reduce + AdamW",
             "cuda_graph": graphed is not None}
 
@@ -605,7 +633,7 @@ def dp_parity_check(rank, world, dev, dist, graphs_per_rank=4):
     flip = (torch.rand(Ft, generator=gen) < 0.5).to(dev)
     c0 = sum(c for c, _ in sizes[:rank * n]); c1 = c0 + sum(c for c, _ in sizes[rank * n:(rank + 1) * n])
     f0 = sum(f for _, f in sizes[:rank * n]); f1 = f0 + sum(f for _, f in sizes[rank * n:(rank + 1) * n])
-    out = {"graphs_per_rank": n, "world": world, "cells_total": Ct, "math": "fp32 (strict FFMA, deterministic)", "losses": {}}
+    out = {"graphs_per_rank": n, "world": world, "cells_total": Ct, "losses": {}}
 
     def one_step(model, p, sel, cn, fk):
         gn, ge, gc = fv.dataset.collate([[_shallow(b) for b in lists[i]] for i in sel])
@@ -625,16 +653,19 @@ def dp_parity_check(rank, world, dev, dist, graphs_per_rank=4):
 
     rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-30))
     ok = True
-    for loss_name in ("global_mean_sum", "direct_mean_loss"):
+    for loss_name, math in (("global_mean_sum", "fp32"), ("direct_mean_loss", "fp32"), ("global_mean_sum", "bf16x3")):
         p = params(loss=loss_name)
         torch.manual_seed(0)
-        ref = fv.FVGN(device="cpu", params=p).to(dev).train().set_math_mode("fp32")
+        ref = fv.FVGN(device="cpu", params=p).to(dev).train().set_math_mode(math)
         with parallel.single_process():
             l_ref = one_step(ref, p, range(world * n), noise, flip)
         torch.manual_seed(0)
-        dp = fv.FVGN(device="cpu", params=p).to(dev).train().set_math_mode("fp32")
+        dp = fv.FVGN(device="cpu", params=p).to(dev).train().set_math_mode(math)
+        if math != "fp32":  # tensor-core path: the all-reduce runs in groups from inside the backward, .grad are views of the reduced buffer
+            parallel.OverlappedGradReducer(dp, n_groups=4).attach(dp)
         l_dp = one_step(dp, p, range(rank * n, (rank + 1) * n), noise[c0:c1], flip[f0:f1])
-        parallel.GradBucket(dp.parameters()).all_reduce_mean_()
+        if math == "fp32":
+            parallel.GradBucket(dp.parameters()).all_reduce_mean_()
         l_mean = l_dp.clone().reshape(1)
         dist.all_reduce(l_mean)
         l_mean /= world
@@ -644,7 +675,8 @@ def dp_parity_check(rank, world, dev, dist, graphs_per_rank=4):
         l_err = abs(float(l_mean) - float(l_ref))
         errs = torch.tensor([g_err, b_err, l_err], dtype=torch.float64, device=dev)
         dist.all_reduce(errs, op=dist.ReduceOp.MAX)
-        out["losses"][loss_name] = {"loss_single_process": float(l_ref), "loss_dp_mean_over_ranks": float(l_mean), "loss_abs_err": float(errs[2]),
+        out["losses"][f"{loss_name}:{math}"] = {"gradient_all_reduce": "flat bucket after the backward" if math == "fp32" else "4 groups overlapped with the backward",
+                                    "loss_single_process": float(l_ref), "loss_dp_mean_over_ranks": float(l_mean), "loss_abs_err": float(errs[2]),
                                     "worst_gradient_rel_l2": float(errs[0]), "worst_buffer_rel_l2": float(errs[1])}
         ok = ok and float(errs[0]) < 1e-5 and float(errs[1]) < 1e-6 and float(errs[2]) < 1e-5
     out["tolerance"] = {"gradients_rel_l2": 1e-5, "buffers_rel_l2": 1e-6, "loss_abs": 1e-5}
@@ -819,10 +851,13 @@ def main():
     ap.add_argument("--math", default="bf16x3", choices=["fp32", "bf16", "bf16x3"],
                     help="bf16x3 (default): fp32-equivalent tensor-core mode; fp32: strict FFMA; bf16: bf16 tiles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one flat gradient all-reduce after the backward instead of the overlapped groups")
+    ap.add_argument("--dp-groups", type=int, default=4, help="N > 1: number of gradient all-reduce groups issued from inside the backward")
     ap.add_argument("--check", action="store_true", help="N > 1: run the data-parallel parity check (DP-N step == single-process batch; always on at N = 2) and exit 3 if it fails")
     ap.add_argument("--no-torch-eager", action="store_true", help="skip the torch-eager CUDA leg (the unmodified reference on the GPU)")
     ap.add_argument("--no-training", action="store_true", help="skip the training graphs/s leg")
     ap.add_argument("--no-strict-leg", action="store_true", help="skip the strict-FFMA comparison leg")
+    ap.add_argument("--no-foil-leg", action="store_true", help="skip the foil16 / bf16 leg (BASELINE configs[2])")
     ap.add_argument("--no-config0", action="store_true", help="skip the batch-1 rollout latency leg (configs[0])")
     ap.add_argument("--train-graph", type=int, default=1, help="1: time the training step replayed from one CUDA graph; 0: eager")
     ap.add_argument("--train-steps", type=int, default=10)

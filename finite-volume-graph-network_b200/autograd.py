@@ -63,12 +63,16 @@ class _SideQueue:
         self.main = torch.cuda.current_stream() if enabled else None  # (the stream object costs ~15 us to look up: once per backward)
         self.keep, self.pending = [], None
 
-    def wgrad(self, mlp, *args, alive=(), **kw):
+    def wgrad(self, mlp, *args, alive=(), slot=None, **kw):
         """ops.mlp_wgrad_x3 on the side stream; its output / workspace buffers come from the MAIN stream's allocator pool (a second
         per-stream pool would have to grow through its own cudaMalloc phase whenever the batch sizes change)"""
         if not self.enabled:
+            if slot is not None:
+                kw["buffers"] = (slot, ops.mlp_wgrad_x3_buffers(mlp, mlp.tensors[0].device)[1])
             return ops.mlp_wgrad_x3(mlp, *args, **kw)
         bufs = ops.mlp_wgrad_x3_buffers(mlp, mlp.tensors[0].device)
+        if slot is not None:  # data parallel: the gradients land in their slot of the flat all-reduce buffer (parallel.OverlappedGradReducer)
+            bufs = (slot, bufs[1])
         self.side.wait_stream(self.main)
         with torch.cuda.stream(self.side):
             out = ops.mlp_wgrad_x3(mlp, *args, buffers=bufs, **kw)
@@ -168,13 +172,17 @@ class NetFunction(torch.autograd.Function):
         dec = epd.decoder.edge_decode_module
         tc = z_dec is not None  # bf16x3 forward: the data-gradient chain runs on the tensor cores, the FFMA kernel keeps the TN products
         sq = _SideQueue(dev, WGRAD_SIDE_STREAM and tc)
+        red = model.__dict__.get("_dp_reducer") if (tc and parallel.is_distributed()) else None
+        slot = (lambda m: red.slot(m)) if red is not None else (lambda m: None)
+        red_stream = (sq.side if sq.enabled else torch.cuda.current_stream()) if red is not None else None
         if tc:
             ops.ensure_packed_bwd_many([m.mlp_ref() for m in network_mlps(model)])  # one launch instead of one per MLP before its dgrad
             da, g_e = ops.mlp_dgrad_x3(dec.mlp_ref(), g_dec, z_dec, want_dA=True)
-            grads[id(dec)] = sq.wgrad(dec.mlp_ref(), 0, g_dec, None, None, z_dec, da, x=e_final, alive=(g_dec, z_dec, da, e_final))
+            grads[id(dec)] = sq.wgrad(dec.mlp_ref(), 0, g_dec, None, None, z_dec, da, x=e_final, alive=(g_dec, z_dec, da, e_final), slot=slot(dec))
         else:
             grads[id(dec)], g_e = ops.mlp_rows_bwd(dec.mlp_ref(), e_final, g_dec, want_d_in=True, z_saved=z_dec)
         g_x = None  # the last layer's cell latent feeds nothing but its own EdgeBlock
+        n_done = 0
         cptr, citems = bt["cell_from_face"]
         nptr, nitems = bt["node_from_cell"]
         for blk in reversed(epd.processer_list):
@@ -185,7 +193,7 @@ class NetFunction(torch.autograd.Function):
                 dz, gxh = ops.ln_bwd(g_e, ze, eb[1].weight)
                 da, dA_e = ops.mlp_dgrad_x3(eb.mlp_ref(), dz, ze, want_dA=True)
                 grads[id(eb)] = sq.wgrad(eb.mlp_ref(), 2, g_e, dz, gxh, ze, da, src0=xp, src1=e_in, idx=topo.nc,
-                                         alive=(g_e, dz, gxh, ze, da, xp, e_in))
+                                         alive=(g_e, dz, gxh, ze, da, xp, e_in), slot=slot(eb))
             else:
                 grads[id(eb)], dA_e = ops.edge_block_bwd(eb.mlp_ref(), xp, e_in, topo.nc, g_e, z_saved=ze)
             # d x' = residual path + transpose of the x'[s], x'[r] gathers (cell <- face segment sum)
@@ -194,7 +202,7 @@ class NetFunction(torch.autograd.Function):
                 dz, gxh = ops.ln_bwd(g_xp, zc, cb[1].weight)
                 da, dA_c = ops.mlp_dgrad_x3(cb.mlp_ref(), dz, zc, want_dA=True, dA_base=g_x)
                 grads[id(cb)] = sq.wgrad(cb.mlp_ref(), 1, g_xp, dz, gxh, zc, da, src0=x_in, src1=na, idx=None,  # na = the per-cell aggregate
-                                         alive=(g_xp, dz, gxh, zc, da, x_in, na))
+                                         alive=(g_xp, dz, gxh, zc, da, x_in, na), slot=slot(cb))
             else:
                 grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, ag.idx, g_xp, d_x_base=g_x, z_saved=zc)
             # transposes of the twice-message aggregation: cell -> node (x 1/3), node -> face halves
@@ -205,13 +213,23 @@ class NetFunction(torch.autograd.Function):
             g_e = ops.edge_grad_combine(g_e, dA_e, g_na, ag.face)
             g_x = dA_c[:, 0:128]
             sq.retire()
+            if red is not None:
+                n_done += 1
+                red.layer_done(n_done, red_stream)
         for enc, inp, g, z in ((epd.encoder.cb_encoder, cell_in, g_x, z_enc_c), (epd.encoder.eb_encoder, edge_in, g_e, z_enc_e)):
             if tc:
                 dz, gxh = ops.ln_bwd(g, z, enc[1].weight)
                 da, _ = ops.mlp_dgrad_x3(enc.mlp_ref(), dz, z, want_dA=False)
-                grads[id(enc)] = sq.wgrad(enc.mlp_ref(), 0, g, dz, gxh, z, da, x=inp, alive=(g, dz, gxh, z, da, inp))
+                grads[id(enc)] = sq.wgrad(enc.mlp_ref(), 0, g, dz, gxh, z, da, x=inp, alive=(g, dz, gxh, z, da, inp), slot=slot(enc))
             else:
                 grads[id(enc)], _ = ops.mlp_rows_bwd(enc.mlp_ref(), inp, g, z_saved=z)
+        if red is not None:
+            # the BatchNorm pair joins the tail group; the copy is ordered before the tail's all-reduce through the side stream's fork
+            red.bn_slot.copy_(g_bn)
+            if sq.enabled:
+                sq.side.wait_stream(sq.main)
+            red.finish(red_stream)
+            g_bn = red.bn_slot
         sq.retire(final=True)
         flat = [g for m in network_mlps(model) for g in grads[id(m)]]
         flat += [g_bn[0:1], g_bn[1:2]]

@@ -83,6 +83,76 @@ class GradBucket:
                 p.grad = v.clone()
 
 
+class OverlappedGradReducer:
+    """Gradient all-reduce OVERLAPPED with the backward (tensor-core training path).  The weight-gradient kernels of every MLP write
+    straight into their slot of one flat fp32 buffer laid out in BACKWARD order (decoder, GnBlock 14 ... 0, encoders, BatchNorm pair);
+    as soon as the weight gradients of a group of layers have been enqueued on the weight-gradient side stream, that group's slice is
+    all-reduced (AVG) from that stream — NCCL runs it on its own stream, next to the main chain's dgrad / LayerNorm-backward / segment-sum
+    kernels of the following layers — and the parameters' .grad tensors are views of the reduced buffer: no gather / scatter copies, no
+    division kernel, one exposed collective (the last group) instead of the whole 8.84 MB bucket at the tail of the step.
+    Attach with `attach(model)`; autograd.NetFunction.backward drives it; CUDA-graph capturable."""
+
+    def __init__(self, model, n_groups=4, group=None):
+        from . import _lib
+        from .autograd import network_mlps
+
+        mlps = network_mlps(model)  # registration order: enc_e, enc_c, (eb_l, cb_l) x L, decoder
+        enc_e, enc_c, dec = mlps[0], mlps[1], mlps[-1]
+        layers = [(mlps[2 + 2 * l], mlps[3 + 2 * l]) for l in range((len(mlps) - 3) // 2)]
+        order = [dec] + [m for eb, cb in reversed(layers) for m in (eb, cb)] + [enc_c, enc_e]
+        L = _lib.lib()
+        sizes = [int(L.fvgn_mlp_grad_floats(m.mlp_ref().k_in)) for m in order]
+        dev = next(model.parameters()).device
+        self.flat = torch.zeros(sum(sizes) + 4, dtype=torch.float32, device=dev)
+        self.slots, off = {}, 0
+        offs = []
+        for m, n in zip(order, sizes):
+            self.slots[id(m)] = self.flat[off:off + n]
+            offs.append(off)
+            off += n
+        self.bn_slot = self.flat[off:off + 2]
+        self.total = off + 4
+        # group boundaries after the decoder + every ceil(L / n_groups) GnBlocks; the last group also takes the encoders and the BN pair
+        per = max(1, -(-len(layers) // n_groups))
+        self.cuts = {}  # number of GnBlocks finished -> (start, end) float range to reduce
+        start = 0
+        nl = len(layers)
+        for done in range(per, nl, per):
+            end = offs[1 + 2 * done]  # first slot of the next (not yet finished) layer
+            self.cuts[done] = (start, end)
+            start = end
+        self.tail = (start, self.total)
+        self.group = group
+        self.works = []
+        self.model_id = id(model)
+
+    def attach(self, model):
+        model.__dict__["_dp_reducer"] = self
+        return self
+
+    def slot(self, mlp_module):
+        return self.slots[id(mlp_module)]
+
+    def _reduce(self, rng, stream):
+        if not is_distributed() or rng[1] <= rng[0]:
+            return
+        with torch.cuda.stream(stream):
+            self.works.append(dist.all_reduce(self.flat[rng[0]:rng[1]], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+
+    def layer_done(self, n_done, stream):
+        """called after the weight gradients of the n_done-th GnBlock (counting from the last layer) were enqueued on `stream`"""
+        rng = self.cuts.get(n_done)
+        if rng is not None:
+            self._reduce(rng, stream)
+
+    def finish(self, stream):
+        """the encoders' weight gradients and the BN pair are in: reduce the tail, then make the current stream wait for every group"""
+        self._reduce(self.tail, stream)
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
 def snapshot_normalizers(model):
     return {n: {b: getattr(getattr(model, n), b).clone() for b in _NORM_BUFS} for n in NORMALIZERS}
 
