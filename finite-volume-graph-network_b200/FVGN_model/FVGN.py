@@ -78,8 +78,10 @@ class FVGN(nn.Module):
         if use_batch_stats and parallel.is_distributed():
             # data parallel (also under torch.no_grad(): the reference's pre_statistics rounds, train.py:170-185): batch statistics and
             # running-stat updates are those of the WHOLE batch, as in autograd.NetFunction — the ranks' BatchNorm buffers stay identical
-            _, sums = ops.face_area_sums(graph_edge.x, graph.cell_area, topo.nc, dt)
-            gstats, mean, var, n = parallel.global_bn_stats(sums, topo.F)
+            red = self.__dict__.get("_dp_bn_reduced")
+            sums = None if red is not None else ops.face_area_sums(graph_edge.x, graph.cell_area, topo.nc, dt)[1]
+            gstats, mean, var, n = parallel.global_bn_stats(sums, topo.F, reduced=red)
+            self.__dict__["_dp_bn_reduced"] = None
             parallel.update_running_stats_(bn, mean, var, n)
             out, raw, stats = ops.face_area_bn_fwd(graph_edge.x, graph.cell_area, topo.nc, dt, True, bn.weight.detach(), bn.bias.detach(),
                                                    bn.running_mean, bn.running_var, want_raw=want_raw, stats=gstats)
@@ -103,9 +105,13 @@ class FVGN(nn.Module):
             target_face = self._face_uvp_flux_output_normalizer(graph_edge.y[:, 0:3], True)
         x_in = self.update_cell_attr(uv, cell_one_hot, cells_type, self.training, normalizer="1")
         e_in = self.update_edge_attr(graph.edge_attr, edge_one_hot, faces_type, self.training, normalizer="1", dual_edge=self.dual_edge)
+        self.__dict__["_dp_bn_reduced"] = None
         if norm_before is not None:
-            # DP: every rank must normalise with the statistics of the WHOLE batch
-            parallel.sync_normalizer_increments_(self, norm_before)
+            # DP: every rank must normalise with the statistics of the WHOLE batch.  The face-area BatchNorm's batch
+            # statistics (a function of the geometry only) ride along in the same collective: one statistic all-reduce per step
+            _, bn_sums = ops.face_area_sums(graph_edge.x, graph.cell_area, topo.nc, dt)
+            extra = torch.cat([bn_sums, torch.full((1,), float(topo.F), dtype=torch.float64, device=bn_sums.device)])
+            self.__dict__["_dp_bn_reduced"] = parallel.sync_normalizer_increments_(self, norm_before, extra=extra)
             target_delta_u = self._acc_output_normalizer(target_acc, False)
             target_face = self._face_uvp_flux_output_normalizer(graph_edge.y[:, 0:3], False)
             x_in = self.update_cell_attr(uv, cell_one_hot, cells_type, False, normalizer="1")

@@ -18,6 +18,12 @@ class MlpT(C.Structure):
                 ("da_in", C.c_void_p), ("n_products", C.c_int)]
 
 
+class TrainTablesT(C.Structure):
+    _fields_ = [("n_cells", C.c_int), ("n_faces", C.c_int), ("n_nodes", C.c_int), ("neighbour_cell", C.c_void_p), ("face_node", C.c_void_p),
+                ("cells_node_T", C.c_void_p), ("node_ptr", C.c_void_p), ("node_items", C.c_void_p), ("cell_from_face_ptr", C.c_void_p),
+                ("cell_from_face_items", C.c_void_p), ("node_from_cell_ptr", C.c_void_p), ("node_from_cell_items", C.c_void_p)]
+
+
 _P, _I, _F, _S = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _SIGS = {
     "fvgn_abi_version": (C.c_int, []),
@@ -33,6 +39,10 @@ _SIGS = {
     "fvgn_cell_mean_poly": (_I, [_P, _P, _I, _P, _P, _P]),
     "fvgn_interp_cells_poly": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P]),
     "fvgn_integrator_fwd_poly": (_I, [_P, _P, _P, _P, _I, _F, _F, _P, _P, _P]),
+    "fvgn_processor_train_fwd": (_I, [C.POINTER(MlpT), C.POINTER(MlpT), _I, _I, C.POINTER(TrainTablesT), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fvgn_processor_train_bwd_scratch_floats": (_S, [_I, _I, _I]),
+    "fvgn_processor_train_bwd": (_I, [C.POINTER(MlpT), C.POINTER(MlpT), _I, _I, _I, _I, C.POINTER(TrainTablesT), _P, _P, _P, _P, _P, _P, _P, _P,
+                                     _P, _P, C.POINTER(C.c_void_p), _P, _S, _P, _P]),
     "fvgn_csr_workspace_bytes": (_S, [_I]),
     "fvgn_build_csr": (_I, [_P, _I, _I, _P, _P, _P, _S, _P]),
     "fvgn_interp_nodes": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),

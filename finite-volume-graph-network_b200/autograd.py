@@ -43,6 +43,9 @@ def network_params(model):
 import os as _os
 
 WGRAD_SIDE_STREAM = _os.environ.get("FVGN_WGRAD_STREAM", "1") != "0"
+# FVGN_EXECUTOR=1 (default): the processor's layer loops of the tensor-core training path are issued by two C calls
+# (csrc/executor.cu: fvgn_processor_train_fwd / _bwd) instead of ~13 ctypes calls per GnBlock — same kernels, order, streams and bits
+EXECUTOR = _os.environ.get("FVGN_EXECUTOR", "1") != "0"
 _SIDE = {}
 
 
@@ -110,10 +113,26 @@ class NetFunction(torch.autograd.Function):
         # instead of recomputing the forward in its tiles (a third of its FLOPs)
         zbuf = (lambda rows: torch.empty((rows, 384), dtype=torch.float32, device=cell_in.device)) if mm == 2 else (lambda rows: None)
         z_enc_c, z_enc_e = zbuf(topo.C), zbuf(topo.F)
-        x = ops.mlp_rows_fwd(enc_c.mlp_ref(), cell_in, mm, z_save=z_enc_c)
-        e = ops.mlp_rows_fwd(enc_e.mlp_ref(), edge_in, mm, z_save=z_enc_e)
+        use_exec = EXECUTOR and mm == 2 and len(epd.processer_list) > 0
+        packed = None
+        if use_exec:
+            L, dev = len(epd.processer_list), cell_in.device
+            f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+            mp = epd.processer_list[0].cb_module.mp_times
+            X, E = f32(L + 1, topo.C, 128), f32(L + 1, topo.F, 128)
+            XP, NA, ZC, ZE = f32(L, topo.C, 128), f32(L, topo.C, 64), f32(L, topo.C, 384), f32(L, topo.F, 384)
+            ops.mlp_rows_fwd(enc_c.mlp_ref(), cell_in, mm, out=X[0], z_save=z_enc_c)
+            ops.mlp_rows_fwd(enc_e.mlp_ref(), edge_in, mm, out=E[0], z_save=z_enc_e)
+            cms = [blk.cb_module.net.mlp_ref() for blk in epd.processer_list]
+            ems = [blk.eb_module.net.mlp_ref() for blk in epd.processer_list]
+            ops.processor_train_fwd(cms, ems, mp, topo.train_tables(mp), X, E, XP, NA, ZC, ZE, f32(topo.N, 64) if mp >= 2 else None)
+            x, e = X[L], E[L]
+            packed = (X, E, XP, NA, ZC, ZE, mp)
+        else:
+            x = ops.mlp_rows_fwd(enc_c.mlp_ref(), cell_in, mm, z_save=z_enc_c)
+            e = ops.mlp_rows_fwd(enc_e.mlp_ref(), edge_in, mm, z_save=z_enc_e)
         saved = []
-        for blk in epd.processer_list:
+        for blk in ([] if use_exec else epd.processer_list):
             cb, eb = blk.cb_module.net, blk.eb_module.net
             ag = topo.agg(blk.cb_module.mp_times)
             na = ops.node_aggregate_fwd(e, ag.ptr, ag.items, ag.rows)
@@ -132,8 +151,10 @@ class NetFunction(torch.autograd.Function):
         use_batch = model.training or not bn.track_running_stats
         if use_batch and parallel.is_distributed():
             # cross-rank batch statistics: 3 floats all-reduced, then the kernel applies the given stats
-            raw0, sums = ops.face_area_sums(graph_edge_x, cell_area, topo.nc, dt)
-            gstats, mean, var, n = parallel.global_bn_stats(sums, topo.F)
+            red = model.__dict__.get("_dp_bn_reduced")  # [sum, sumsq, count] already reduced with the normaliser statistics (FVGN.forward)
+            sums = None if red is not None else ops.face_area_sums(graph_edge_x, cell_area, topo.nc, dt)[1]
+            gstats, mean, var, n = parallel.global_bn_stats(sums, topo.F, reduced=red)
+            model.__dict__["_dp_bn_reduced"] = None
             parallel.update_running_stats_(bn, mean, var, n)
             face_area, raw, stats = ops.face_area_bn_fwd(graph_edge_x, cell_area, topo.nc, dt, True, bn.weight.detach(), bn.bias.detach(),
                                                          bn.running_mean, bn.running_var, want_raw=True, stats=gstats)
@@ -145,6 +166,7 @@ class NetFunction(torch.autograd.Function):
         delta_u, _ = ops.integrator_fwd(decoded, unv, face_area, topo.cfT, rho, 1.0)
         ctx.model, ctx.topo, ctx.rho = model, topo, rho
         ctx.saved = saved
+        ctx.packed = packed
         # detached aliases: storing the OUTPUT tensors themselves on ctx would close a reference cycle (output -> grad_fn -> ctx ->
         # output) that only the cyclic GC can free, i.e. ~2 GB per layer of saved latents would pile up between collections
         ctx.aux = (cell_in.detach(), edge_in.detach(), e, decoded.detach(), face_area.detach(), raw, stats, unv.detach())
@@ -158,6 +180,7 @@ class NetFunction(torch.autograd.Function):
         epd = model.model
         cell_in, edge_in, e_final, decoded, face_area, raw, stats, unv = ctx.aux
         saved_layers, ctx.saved, ctx.aux = ctx.saved, None, None  # release the saved latents as the backward sweep consumes them
+        packed, ctx.packed = ctx.packed, None
         (z_enc_c, z_enc_e, z_dec), ctx.zs = ctx.zs, None
         bt = topo.backward_tables()
         dev = decoded.device
@@ -185,7 +208,44 @@ class NetFunction(torch.autograd.Function):
         n_done = 0
         cptr, citems = bt["cell_from_face"]
         nptr, nitems = bt["node_from_cell"]
-        for blk in reversed(epd.processer_list):
+        if packed is not None:
+            # the whole layer loop from C (csrc/executor.cu), in chunks that end where a data-parallel reduce group ends
+            import ctypes as _C
+
+            X, E, XP, NA, ZC, ZE, mp = packed
+            L = len(epd.processer_list)
+            cms = [blk.cb_module.net.mlp_ref() for blk in epd.processer_list]
+            ems = [blk.eb_module.net.mlp_ref() for blk in epd.processer_list]
+            lib = ops._lib.lib()
+            if red is not None:
+                slots = [s for blk in epd.processer_list for s in (red.slot(blk.eb_module.net), red.slot(blk.cb_module.net))]
+            else:
+                sizes = [int(lib.fvgn_mlp_grad_floats(m.k_in)) for pair in zip(ems, cms) for m in pair]
+                G = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+                slots, o = [], 0
+                for n in sizes:
+                    slots.append(G[o:o + n])
+                    o += n
+            ptrs = (_C.c_void_p * (2 * L))(*[s.data_ptr() for s in slots])
+            scratch = torch.empty(int(lib.fvgn_processor_train_bwd_scratch_floats(topo.C, topo.F, topo.N)), dtype=torch.float32, device=dev)
+            bounds = sorted({0, L} | ({L - nd for nd in red.cuts} if red is not None else set()))
+            g_e = g_e.contiguous()
+            ge_bufs = [torch.empty((topo.F, 128), dtype=torch.float32, device=dev) for _ in range(2)]
+            gx_bufs = [torch.empty((topo.C, 128), dtype=torch.float32, device=dev) for _ in range(2)]
+            side = sq.side if sq.enabled else None
+            k = 0
+            for hi, lo in zip(reversed(bounds[1:]), reversed(bounds[:-1])):
+                ops.processor_train_bwd(cms, ems, lo, hi, mp, topo.train_tables(mp), X, E, XP, NA, ZC, ZE, g_e, ge_bufs[k & 1], g_x, gx_bufs[k & 1],
+                                        ptrs, scratch, side)
+                g_e, g_x = ge_bufs[k & 1], gx_bufs[k & 1]
+                k += 1
+                if red is not None:
+                    red.layer_done(L - lo, red_stream)
+            for l, blk in enumerate(epd.processer_list):
+                grads[id(blk.eb_module.net)] = ops._mlp_grad_views(ems[l], slots[2 * l])
+                grads[id(blk.cb_module.net)] = ops._mlp_grad_views(cms[l], slots[2 * l + 1])
+            del X, E, XP, NA, ZC, ZE, packed
+        for blk in (reversed(epd.processer_list) if saved_layers else []):
             x_in, e_in, xp, na, zc, ze = saved_layers.pop()
             cb, eb = blk.cb_module.net, blk.eb_module.net
             ag = topo.agg(blk.cb_module.mp_times)

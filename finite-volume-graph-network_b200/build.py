@@ -27,6 +27,7 @@ SOURCES = {
     "mlp_bwd.cu": [],
     "connectivity.cu": ["--fmad=false"],
     "prepost.cu": ["--fmad=false"],
+    "executor.cu": [],
 }
 
 

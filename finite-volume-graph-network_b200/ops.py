@@ -876,3 +876,28 @@ def face_area_bn_bwd(g_face_area, raw, stats):
     _count(2)
     check(L.fvgn_face_area_bn_bwd(_p(g_face_area), _p(raw), _p(stats), raw.shape[0], _p(out), _p(ws), _stream()), "face_area_bn_bwd")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ C-side executor (training layer loops)
+def processor_train_fwd(cell_mlps, edge_mlps, mp_times, tables, X, E, XP, NA, ZC, ZE, node_scratch):
+    """fvgn_processor_train_fwd: all GnBlocks of a training forward in one call (layer-major arrays, see include/fvgn_b200.h)"""
+    L = len(cell_mlps)
+    ca = (MlpT * L)(*[m.struct for m in cell_mlps])
+    ea = (MlpT * L)(*[m.struct for m in edge_mlps])
+    _count((4 if mp_times >= 2 else 3) * L)
+    with _timed("processor_fwd"):
+        check(_lib.lib().fvgn_processor_train_fwd(ca, ea, L, int(mp_times), C.byref(tables), _p(X), _p(E), _p(XP), _p(NA), _p(ZC), _p(ZE),
+                                                  _p(node_scratch), _stream()), "processor_train_fwd")
+
+
+def processor_train_bwd(cell_mlps, edge_mlps, lo, hi, mp_times, tables, X, E, XP, NA, ZC, ZE, g_e_in, g_e_out, g_x_in, g_x_out, grad_ptrs,
+                        scratch, side_stream):
+    """fvgn_processor_train_bwd: the backward of the GnBlocks hi-1 ... lo in one call; grad_ptrs = ctypes array [2L] of device pointers"""
+    L = len(cell_mlps)
+    ca = (MlpT * L)(*[m.struct for m in cell_mlps])
+    ea = (MlpT * L)(*[m.struct for m in edge_mlps])
+    _count(13 * (hi - lo) + 1)
+    check(_lib.lib().fvgn_processor_train_bwd(ca, ea, int(lo), int(hi), int(mp_times), BWD_PRODUCTS, C.byref(tables), _p(X), _p(E), _p(XP), _p(NA),
+                                              _p(ZC), _p(ZE), _p(g_e_in), _p(g_e_out), _p(g_x_in), _p(g_x_out), grad_ptrs, _p(scratch),
+                                              scratch.numel(), C.c_void_p(side_stream.cuda_stream) if side_stream is not None else None,
+                                              _stream()), "processor_train_bwd")

@@ -92,7 +92,7 @@ class OverlappedGradReducer:
     division kernel, one exposed collective (the last group) instead of the whole 8.84 MB bucket at the tail of the step.
     Attach with `attach(model)`; autograd.NetFunction.backward drives it; CUDA-graph capturable."""
 
-    def __init__(self, model, n_groups=4, group=None):
+    def __init__(self, model, n_groups=4, group=None, cuts=None):
         from . import _lib
         from .autograd import network_mlps
 
@@ -112,12 +112,16 @@ class OverlappedGradReducer:
             off += n
         self.bn_slot = self.flat[off:off + 2]
         self.total = off + 4
-        # group boundaries after the decoder + every ceil(L / n_groups) GnBlocks; the last group also takes the encoders and the BN pair
+        # group boundaries (number of GnBlocks finished, counted from the last layer): every ceil(L / n_groups) blocks, plus one just before
+        # the first layer so that the EXPOSED tail group (nothing is left to overlap it with) is one GnBlock + the encoders + the BN pair
         per = max(1, -(-len(layers) // n_groups))
         self.cuts = {}  # number of GnBlocks finished -> (start, end) float range to reduce
         start = 0
         nl = len(layers)
-        for done in range(per, nl, per):
+        marks = sorted(set(cuts) if cuts is not None else set(range(per, nl, per)) | ({nl - 1} if nl > 1 else set()))
+        for done in marks:
+            if not 0 < done < nl:
+                continue
             end = offs[1 + 2 * done]  # first slot of the next (not yet finished) layer
             self.cuts[done] = (start, end)
             start = end
@@ -157,17 +161,24 @@ def snapshot_normalizers(model):
     return {n: {b: getattr(getattr(model, n), b).clone() for b in _NORM_BUFS} for n in NORMALIZERS}
 
 
-def sync_normalizer_increments_(model, before, group=None):
-    """after a training forward: buffers <- before + sum over ranks of (after - before); num_accumulations advances by one."""
+def sync_normalizer_increments_(model, before, group=None, extra=None):
+    """after a training forward: buffers <- before + sum over ranks of (after - before); num_accumulations advances by one.
+    `extra`: optional float64 vector that rides along in the same collective (the face-area BatchNorm's [sum, sum of squares, count]:
+    one statistic all-reduce per step instead of two); returns its reduced values."""
     if not is_distributed():
-        return
+        return extra
     parts = []
     for n in NORMALIZERS:
         m = getattr(model, n)
         for b in ("acc_sum", "acc_sum_squared", "acc_count"):
             parts.append((getattr(m, b) - before[n][b]).reshape(-1))
+    n_norm = sum(p.numel() for p in parts)
+    if extra is not None:
+        parts = [p.to(torch.float64) for p in parts] + [extra.to(torch.float64).reshape(-1)]  # (fp32 increments are exact in fp64)
     flat = torch.cat(parts)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    extra_out = flat[n_norm:] if extra is not None else None
+    flat = flat[:n_norm].to(torch.float32) if extra is not None else flat
     off = 0
     for n in NORMALIZERS:
         m = getattr(model, n)
@@ -178,14 +189,19 @@ def sync_normalizer_increments_(model, before, group=None):
             off += k
         # every rank accumulated once (or none did): keep the single-process count
         m.num_accumulations.copy_(torch.maximum(m.num_accumulations, before[n]["num_accumulations"]))
+    return extra_out
 
 
-def global_bn_stats(sums, count, eps=1e-5, group=None):
-    """local float64 [sum, sumsq] + count -> (stats=[mean, invstd] fp32, mean, biased var, total count) over all ranks"""
+def global_bn_stats(sums, count, eps=1e-5, group=None, reduced=None):
+    """local float64 [sum, sumsq] + count -> (stats=[mean, invstd] fp32, mean, biased var, total count) over all ranks
+    (`reduced`: the already all-reduced [sum, sumsq, count], when it rode along with the normaliser statistics)"""
     # (torch.full, not torch.tensor: no host -> device copy, so the step stays CUDA-graph capturable)
-    t = torch.cat([sums.to(torch.float64), torch.full((1,), float(count), dtype=torch.float64, device=sums.device)])
-    if is_distributed():
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    if reduced is not None:
+        t = reduced
+    else:
+        t = torch.cat([sums.to(torch.float64), torch.full((1,), float(count), dtype=torch.float64, device=sums.device)])
+        if is_distributed():
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     n = t[2]
     mean = t[0] / n
     var = torch.clamp(t[1] / n - mean * mean, min=0.0)

@@ -57,6 +57,23 @@ class MeshTopology:
         return self._bwd
 
 
+def _train_tables(topo, mp_times):
+    """fvgn_train_tables_t of this topology (cached; the struct borrows the topology's tensors)"""
+    from ._lib import TrainTablesT
+
+    key = "_tt%d" % (2 if mp_times >= 2 else 1)
+    tt = topo.__dict__.get(key)
+    if tt is None:
+        bt = topo.backward_tables()
+        p = lambda t: t.data_ptr()
+        tt = TrainTablesT(topo.C, topo.F, topo.N, p(topo.nc), p(topo.fn), p(topo.cnT), p(topo.node_ptr), p(topo.node_items),
+                          p(bt["cell_from_face"][0]), p(bt["cell_from_face"][1]), p(bt["node_from_cell"][0]), p(bt["node_from_cell"][1]))
+        topo.__dict__[key] = tt
+    return tt
+
+
+MeshTopology.train_tables = _train_tables
+
 _CACHE: dict = {}
 _CACHE_MAX = 16
 

@@ -255,6 +255,37 @@ FVGN_API int fvgn_loss_finish(int n_graphs, int mode, float w_mom, float w_uv, f
                      fvgn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * The processor's layer loops of one TRAINING step as two calls (tensor-core path, FVGN_MATH_BF16X3_TC kernels) — what the reference
+ * runs as 15 x GnBlock.forward (FVGN_model/EncoderProcesserDecoder.py:112-124, 224-238) under torch autograd (train.py:194-218).
+ * train.py:119-160 draws a new batch topology every step, so the step cannot be replayed from one captured CUDA graph; these entry
+ * points issue the step's kernels from C (same kernels, order, streams and bits as the per-call path).
+ * Layer-major arrays: X [L+1,C,128] (X[0] = encoder output, X[l+1] = cell latent after layer l), E [L+1,F,128], XP [L,C,128] (x'),
+ * NA [L,C,64] (per-cell aggregate), ZC [L,C,384] / ZE [L,F,384] (pre-activations of the Cell / EdgeBlock MLPs). */
+typedef struct {
+  int n_cells, n_faces, n_nodes;
+  const int32_t* neighbour_cell;        /* [2,F] */
+  const int32_t* face_node;             /* [2,F]           (mp_times >= 2) */
+  const int32_t* cells_node_T;          /* [3,C]           (mp_times >= 2) */
+  const int32_t* node_ptr;              /* [N+1] stable CSR of cat(face_node[0], face_node[1]) by node (mp_times >= 2) */
+  const int32_t* node_items;            /* [2F] */
+  const int32_t* cell_from_face_ptr;    /* [C+1] stable CSR of neighbour_cell.reshape(-1) by cell */
+  const int32_t* cell_from_face_items;  /* [2F] */
+  const int32_t* node_from_cell_ptr;    /* [N+1] stable CSR of cells_node_T.reshape(-1) by node (backward, mp_times >= 2) */
+  const int32_t* node_from_cell_items;  /* [3C] */
+} fvgn_train_tables_t;
+FVGN_API int fvgn_processor_train_fwd(const fvgn_mlp_t* cell_mlps /*[L]*/, const fvgn_mlp_t* edge_mlps /*[L]*/, int n_layers, int mp_times,
+                             const fvgn_train_tables_t* tables, float* X, float* E, float* XP, float* NA, float* ZC, float* ZE,
+                             float* node_scratch /*[N,64]*/, fvgn_stream_t stream);
+FVGN_API size_t fvgn_processor_train_bwd_scratch_floats(int n_cells, int n_faces, int n_nodes);
+/* layers hi-1 ... lo; gradients in / out are different buffers; grads[2l], grads[2l+1] = flat gradient buffers of layer l's EdgeBlock /
+ * CellBlock MLP (fvgn_mlp_grad_floats); weight gradients run on side_stream (may be NULL = same stream), joined into stream on return */
+FVGN_API int fvgn_processor_train_bwd(const fvgn_mlp_t* cell_mlps, const fvgn_mlp_t* edge_mlps, int lo, int hi, int mp_times, int n_products,
+                             const fvgn_train_tables_t* tables, const float* X, const float* E, const float* XP, const float* NA,
+                             const float* ZC, const float* ZE, const float* g_e_in, float* g_e_out, const float* g_x_in /*or NULL*/,
+                             float* g_x_out, float* const* grads /*host array [2L] of device pointers*/, float* scratch,
+                             size_t scratch_floats, fvgn_stream_t side_stream, fvgn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Tri / quad hybrid meshes (BASELINE configs[3]).  The reference processes triangles only (its quad branch,
  * Extract_mesh/parse_tfrecord_refactor.py:1459-1491, is never reached: SURVEY.md section 0 item 5); these entry points take cells
  * with k = 3 or 4 nodes as [C,4] tables whose 4th column is -1 on triangles, follow the reference's rules with "3" read as "k"
