@@ -111,13 +111,13 @@ class NetFunction(torch.autograd.Function):
         mm = {"fp32": 0, "bf16x3": 2, "bf16": 2}[model.math_mode]  # "bf16": the bf16x3 kernels with the leading split product only
         # bf16x3: the forward also stores every MLP's pre-activations (z1 | z2 | z3, 1.5 KB per row): the backward reads them
         # instead of recomputing the forward in its tiles (a third of its FLOPs)
-        zbuf = (lambda rows: torch.empty((rows, 384), dtype=torch.float32, device=cell_in.device)) if mm == 2 else (lambda rows: None)
+        zbuf = (lambda rows: ops.bucketed_empty((rows, 384), cell_in.device)) if mm == 2 else (lambda rows: None)
         z_enc_c, z_enc_e = zbuf(topo.C), zbuf(topo.F)
         use_exec = EXECUTOR and mm == 2 and len(epd.processer_list) > 0
         packed = None
         if use_exec:
             L, dev = len(epd.processer_list), cell_in.device
-            f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+            f32 = lambda *shape: ops.bucketed_empty(shape, dev)
             mp = epd.processer_list[0].cb_module.mp_times
             X, E = f32(L + 1, topo.C, 128), f32(L + 1, topo.F, 128)
             XP, NA, ZC, ZE = f32(L, topo.C, 128), f32(L, topo.C, 64), f32(L, topo.C, 384), f32(L, topo.F, 384)
@@ -221,17 +221,17 @@ class NetFunction(torch.autograd.Function):
                 slots = [s for blk in epd.processer_list for s in (red.slot(blk.eb_module.net), red.slot(blk.cb_module.net))]
             else:
                 sizes = [int(lib.fvgn_mlp_grad_floats(m.k_in)) for pair in zip(ems, cms) for m in pair]
-                G = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+                G = ops.bucketed_empty((sum(sizes),), dev)
                 slots, o = [], 0
                 for n in sizes:
                     slots.append(G[o:o + n])
                     o += n
             ptrs = (_C.c_void_p * (2 * L))(*[s.data_ptr() for s in slots])
-            scratch = torch.empty(int(lib.fvgn_processor_train_bwd_scratch_floats(topo.C, topo.F, topo.N)), dtype=torch.float32, device=dev)
+            scratch = ops.bucketed_empty((int(lib.fvgn_processor_train_bwd_scratch_floats(topo.C, topo.F, topo.N)),), dev)
             bounds = sorted({0, L} | ({L - nd for nd in red.cuts} if red is not None else set()))
             g_e = g_e.contiguous()
-            ge_bufs = [torch.empty((topo.F, 128), dtype=torch.float32, device=dev) for _ in range(2)]
-            gx_bufs = [torch.empty((topo.C, 128), dtype=torch.float32, device=dev) for _ in range(2)]
+            ge_bufs = [ops.bucketed_empty((topo.F, 128), dev) for _ in range(2)]
+            gx_bufs = [ops.bucketed_empty((topo.C, 128), dev) for _ in range(2)]
             side = sq.side if sq.enabled else None
             k = 0
             for hi, lo in zip(reversed(bounds[1:]), reversed(bounds[:-1])):

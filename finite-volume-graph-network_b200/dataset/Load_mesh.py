@@ -34,7 +34,14 @@ def collate(lists):
     return [Batch.from_data_list([l[k] for l in lists]) for k in range(3)]
 
 
-def _idx(graph_node, graph_cell):
+def _idx(graph_node, graph_cell, graph_edge=None):
+    """int32 (cells_node_T, face_node, neighbour_cell): the tables of the batch's cached MeshTopology when the edge bag is at hand (the
+    forward that follows builds the same topology: the int64 -> int32 narrowing then happens once per batch), else converted here"""
+    if graph_edge is not None and hasattr(graph_edge, "face"):
+        from ..topology import topology_of
+
+        topo = topology_of(graph_cell, graph_node, graph_edge)
+        return topo.cnT, topo.fn, topo.nc
     return ops.as_i32(graph_node.face), ops.as_i32(graph_node.edge_index), ops.as_i32(graph_cell.edge_index)
 
 
@@ -67,7 +74,7 @@ def train_datapreprocessing(graph_list, cell_noise=None, flip_keep=None, noise_s
     if dual_edge:
         raise NotImplementedError("dual_edge=True is outside the B200 hot path")
     graph_node, graph_edge, graph_cell = graph_list[:3]
-    cnT, fn, nc = _idx(graph_node, graph_cell)
+    cnT, fn, nc = _idx(graph_node, graph_cell, graph_edge)
     dev = graph_node.x.device
     on_cell, on_face = ops.interp_nodes(graph_node.x, 0, 6, cnT, graph_cell.cell_factor.contiguous(), fn)
     graph_cell.y = on_cell[:, 3:5]

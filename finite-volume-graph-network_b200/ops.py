@@ -104,6 +104,18 @@ def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+def bucketed_empty(shape, device, dtype=torch.float32):
+    """torch.empty(shape) whose ALLOCATION is rounded up to a size bucket (1/8 of the next power of two): with a new batch topology every
+    step (train.py:119-160) the big per-step arrays would otherwise each have a new size, miss the caching allocator's free blocks and pay
+    cudaMalloc / cudaFree (a device synchronisation) every step"""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    g = max(1 << 18, (1 << max(n - 1, 1).bit_length()) >> 3)
+    padded = (n + g - 1) // g * g
+    return torch.empty(padded, dtype=dtype, device=device)[:n].view(shape)
+
+
 def as_i32(t):
     """The reference keeps int64 tables (Load_mesh.py:506-507,531-533,542); the kernels take int32."""
     return t.to(torch.int32).contiguous()

@@ -49,6 +49,7 @@ def test_cyl16_training_step_gradients_vs_strict_and_fp64(fv, loss_name):
     flip = torch.rand(F, generator=gen) < 0.5
     sd0 = H.torch_reference_state_dict(0)
     res = {}
+    fv.ops.status(clear=True)  # (the status word is per device and outlives the test that set it)
     for mode in ("bf16x3", "fp32"):
         torch.manual_seed(0)
         model = fv.FVGN(device="cpu", params=p)
