@@ -30,6 +30,7 @@ _SIGS = {
     "fvgn_last_error": (C.c_char_p, []),
     "fvgn_device_check": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "fvgn_status_read": (_I, [C.POINTER(C.c_uint), _I]),
+    "fvgn_x3_pair_enable": (_I, [_I]),
     "fvgn_connectivity_workspace_bytes": (_S, [_I]),
     "fvgn_connectivity_faces": (_I, [_P, _I, _I, _P, C.POINTER(C.c_int), _P, _S, _P]),
     "fvgn_connectivity_tables": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S, _P]),

@@ -46,6 +46,7 @@ int tc3_cell_mean_poly(const float*, const int32_t*, int, float*, void*, cudaStr
 int tc3_cell_block_sh(const fvgn_mlp_t*, float*, const void*, int, void*, cudaStream_t);
 int tc3_edge_block_sh(const fvgn_mlp_t*, const void*, float*, const int32_t*, int, cudaStream_t);
 int tc3_status_read(unsigned int*, int);
+int tc3_pair_enable(int);
 size_t tc3_packed_bytes(int k_in);
 int tc3_pack(const fvgn_mlp_t*, void*, size_t, cudaStream_t);
 int tc3_pack_many(const fvgn_mlp_t*, int, cudaStream_t);
@@ -85,6 +86,8 @@ using namespace fvgn;
 
 extern "C" int fvgn_abi_version(void) { return FVGN_ABI_VERSION; }
 extern "C" const char* fvgn_last_error(void) { return g_err; }
+
+extern "C" int fvgn_x3_pair_enable(int on) { return tc3_pair_enable(on); }
 
 extern "C" int fvgn_status_read(unsigned int* status_host, int clear) { return tc3_status_read(status_host, clear); }
 

@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
     // ================================================================= layer-1 MMA issuer: A ring x W1 ring -> accumulator jl % NACC
     // One thread per dependency stream, each a plain sequential loop of blocking mbarrier waits (an earlier single-thread event loop
     // over all barriers cost ~7k cycles per tile in polling latency alone).
-    if (lane == 0) {
+    {  // (all 32 lanes walk the sequence in uniform control flow, one elected lane issues: tc_common.cuh::umma_bf16_w)
       const bool w1_resident = kt1 <= WRING;
       uint32_t gk = 0;
 #pragma unroll 1
@@ -453,18 +453,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
           const uint32_t a_base = smem_u32(sA + sa * TILE_BYTES), b_base = smem_u32(sWr + sw * TILE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            if (!(FVGN_DBG(p) & 8)) umma_bf16(d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (t | kk) != 0);
-          umma_commit(BAR(B_AEMPTY + sa));  // both ring slots are free once these MMAs have read them
-          if (!w1_resident) umma_commit(BAR(B_WEMPTY + sw));
+            if (!(FVGN_DBG(p) & 8)) umma_bf16_w(d, umma_desc(a_base + kk * 32), umma_desc(b_base + kk * 32), IDESC_BF16_M128_N128, (t | kk) != 0);
+          umma_commit_w(BAR(B_AEMPTY + sa));  // both ring slots are free once these MMAs have read them
+          if (!w1_resident) umma_commit_w(BAR(B_WEMPTY + sw));
         }
-        umma_commit(BAR(B_DFULL + a));
+        umma_commit_w(BAR(B_DFULL + a));
       }
     }
     __syncwarp();
   } else if (warp == WARP_L23 || warp == WARP_L23 + 1) {
     // ================================================================= layer-2/3 MMA issuer of epilogue group g: A = hidden activations
     // in TMEM (written by the group's epilogue), B = resident W2 / W3
-    if (lane == 0) {
+    {  // (all 32 lanes walk the sequence in uniform control flow, one elected lane issues: tc_common.cuh::umma_bf16_w)
       const int g = warp - WARP_L23;
       if (g < n_local) mbar_wait(BAR(B_WRES), 0, 6);
       uint32_t hphase = 0;
@@ -480,8 +480,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc_kernel(const TcParam
           const unsigned char* w = layer == 0 ? sW2 : sW3;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            if (!(FVGN_DBG(p) & 8)) umma_bf16_ts(d, h + 8u * (uint32_t)kk, umma_desc(smem_u32(w + (kk >> 2) * TILE_BYTES) + (kk & 3) * 32), IDESC_BF16_M128_N128, kk != 0);
-          umma_commit(BAR(B_DFULL + a));
+            if (!(FVGN_DBG(p) & 8)) umma_bf16_ts_w(d, h + 8u * (uint32_t)kk, umma_desc(smem_u32(w + (kk >> 2) * TILE_BYTES) + (kk & 3) * 32), IDESC_BF16_M128_N128, kk != 0);
+          umma_commit_w(BAR(B_DFULL + a));
         }
       }
     }

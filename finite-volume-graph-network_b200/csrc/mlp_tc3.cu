@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
     __syncwarp();
   } else if (warp == WARP_MMA) {
     // ================================================================= MMA issuer
-    if (lane == 0 && n_local > 0) {
+    // (all 32 lanes walk the sequence — uniform control flow keeps the descriptors in uniform registers — and one elected lane issues)
+    if (n_local > 0) {
       uint32_t ak = 0, wk = 0, hphase[2] = {0, 0};
       PROF_DECL;
       PROF_T0();
@@ -321,18 +322,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           mbar_wait(BAR(FB_WFULL + sw), (wk / FWRING) & 1, 5);
           PROF_ADD(2);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + sa * FA_SLOT), b_base = smem_u32(sW + sw * FW_SLOT);
+          const uint32_t alo = umma_desc_lo(smem_u32(sA + sa * FA_SLOT)), blo = umma_desc_lo(smem_u32(sW + sw * FW_SLOT));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
             for (int q = 0; q < 3; ++q)
-              if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16(d, umma_desc(a_base + fprod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + fprod_w(q) * TILE_BYTES + kk * 32),
-                        IDESC_F16_M128_N128, (t | kk | q) != 0);
-          umma_commit(BAR(FB_AEMPTY + sa));
-          umma_commit(BAR(FB_WEMPTY + sw));
+              if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0))
+                umma_f16_lo_w(d, alo + (uint32_t)((fprod_a(q) * TILE_BYTES + kk * 32) >> 4), blo + (uint32_t)((fprod_w(q) * TILE_BYTES + kk * 32) >> 4),
+                              IDESC_F16_M128_N128, (t | kk | q) != 0);
+          umma_commit_w(BAR(FB_AEMPTY + sa));
+          umma_commit_w(BAR(FB_WEMPTY + sw));
           PROF_ADD(3);
         }
-        umma_commit(BAR(FB_DFULL + a));
+        umma_commit_w(BAR(FB_DFULL + a));
       };
       auto layer23 = [&](int jl) {  // layer 2 or 3 of tile jl (whichever hidden activation the epilogue has just published)
         const int a = jl & 1;
@@ -346,17 +348,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             mbar_wait(BAR(FB_WFULL + sw), (wk / FWRING) & 1, 6);
             PROF_ADD(5);
             tc_fence_after();
-            const uint32_t b_base = smem_u32(sW + sw * FW_SLOT);
+            const uint32_t blo = umma_desc_lo(smem_u32(sW + sw * FW_SLOT));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
               for (int q = 0; q < 3; ++q)
-                if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0)) umma_bf16_ts(d, hcol + 64u * fprod_a(q) + 8u * (uint32_t)(4 * t + kk),
-                             umma_desc(b_base + fprod_w(q) * TILE_BYTES + kk * 32), IDESC_F16_M128_N128, (t | kk | q) != 0);
-            umma_commit(BAR(FB_WEMPTY + sw));
+                if (q < p.nprod && (!(FVGN_DBG(p) & 8) || q == 0))
+                  umma_f16_ts_lo_w(d, hcol + 64u * fprod_a(q) + 8u * (uint32_t)(4 * t + kk), blo + (uint32_t)((fprod_w(q) * TILE_BYTES + kk * 32) >> 4),
+                                   IDESC_F16_M128_N128, (t | kk | q) != 0);
+            umma_commit_w(BAR(FB_WEMPTY + sw));
             PROF_ADD(6);
           }
-          umma_commit(BAR(FB_DFULL23 + a));
+          umma_commit_w(BAR(FB_DFULL23 + a));
         }
       };
       // Tiles are processed in pairs (A, B) with their own accumulator and hidden-activation columns; the epilogue warps alternate
@@ -374,10 +377,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
         if (k + 2 < n_local) layer1(k + 2);
         if (k + 3 < n_local) layer1(k + 3);
       }
-      PROF_FLUSH(0);
+      if (lane == 0) {
+        PROF_FLUSH(0);
 #if FVGN_TC_TIMING_EXPERIMENTS
-      atomicAdd(&g_prof[7], (unsigned long long)n_local);
+        atomicAdd(&g_prof[7], (unsigned long long)n_local);
 #endif
+      }
     }
     __syncwarp();
   } else {
@@ -700,6 +705,10 @@ __global__ void __launch_bounds__(1024) pack_fwd_h2_kernel(const __grid_constant
 }  // namespace x3
 
 
+}  // namespace fvgn
+#include "mlp_tc3_pair.cuh"
+namespace fvgn {
+
 size_t tc3_packed_bytes(int k_in) { return (size_t)(x3::kt_of(k_in) + 4) * x3::SLOT_BYTES; }
 
 int tc3_pack(const fvgn_mlp_t* m, void* packed, size_t bytes, cudaStream_t st) {
@@ -758,6 +767,16 @@ int tc3_status_read(unsigned int* out_host, int clear) {
   return 0;
 }
 
+// 1: the inference kernels of the fp32-equivalent mode run on CTA pairs (mlp_tc3_pair.cuh: tcgen05.mma.cta_group::2).  Default 0 — measured
+// (profiles/r02_forward_cta_pairs.txt): bit-identical, 1 % faster on the 1M-cell mesh, 9 % slower at cylinder-batch size; FVGN_X3_PAIR=1 in
+// the environment or fvgn_x3_pair_enable(1) selects them
+static int g_pair = -1;
+int tc3_pair_enable(int on) {
+  const int prev = g_pair < 0 ? 0 : g_pair;
+  g_pair = on ? 1 : 0;
+  return prev;
+}
+
 static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t st, bool sh = false) {
   using namespace x3;
   if (p.rows <= 0) return 0;
@@ -785,6 +804,11 @@ static int launch_tc3(x3::Params& p, const fvgn_mlp_t* m, bool red, cudaStream_t
   } while (0)
   if (sh) {
     FVGN_CHECK_ARG(!p.zsave && red && p.mode != TC_ROWS, "the split-shadow (inference) variants update the latent in place and save nothing");
+    if (g_pair < 0) { const char* e = getenv("FVGN_X3_PAIR"); g_pair = (e && e[0] == '1') ? 1 : 0; }
+    if (g_pair && !FVGN_DBG(p)) {
+      const int rc = tc3_launch_pair(p, st);
+      if (rc != FVGN_E_UNSUPPORTED) return rc;
+    }
     if (p.mode == TC_CELL) FVGN_TC3_LAUNCH(TC_CELL, true, true);
     else FVGN_TC3_LAUNCH(TC_EDGE, true, true);
   } else if (p.mode == TC_ROWS) FVGN_TC3_LAUNCH(TC_ROWS, false, false);

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
     __syncwarp();
   } else if (warp == WARP_MMA) {
     // ================================================================= MMA issuer: batches S1 (acc0), S2 (acc1), S3[seg] (acc seg & 1)
-    if (lane == 0 && n_local > 0) {
+    // (all 32 lanes walk the sequence in uniform control flow, one elected lane issues: tc_common.cuh::umma_bf16_w)
+    if (n_local > 0) {
       uint32_t ak = 0, wk = 0, hphase = 0, use0 = 0, use1 = 0;
       auto acquire = [&](int a) {  // the previous batch on accumulator a has been read out
         uint32_t& u = a ? use1 : use0;
@@ -143,9 +144,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
 #pragma unroll
               for (int q = 0; q < (THIRD ? 6 : 3); ++q)
                 if (q < p.nprod)
-                  umma_bf16(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
+                  umma_bf16_w(d, umma_desc(a_base + prod_a(q) * TILE_BYTES + kk * 32), umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32),
                             IDESC_BF16_M128_N128, (t | kk | q) != 0);
-            umma_commit(BAR(B_AEMPTY + sa));
+            umma_commit_w(BAR(B_AEMPTY + sa));
             ++ak;
           } else {
 #pragma unroll
@@ -153,27 +154,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_tc3_kernel(const DgParams p
 #pragma unroll
               for (int q = 0; q < (THIRD ? 6 : 3); ++q)
                 if (q < p.nprod)
-                  umma_bf16_ts(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
+                  umma_bf16_ts_w(d, tmem_base + TMEM_H0 + 64u * prod_a(q) + 8u * (uint32_t)(4 * t + kk),
                                umma_desc(b_base + prod_w(q) * TILE_BYTES + kk * 32), IDESC_BF16_M128_N128, (t | kk | q) != 0);
           }
-          umma_commit(BAR(B_WEMPTY + sw));
+          umma_commit_w(BAR(B_WEMPTY + sw));
         }
       };
 #pragma unroll 1
       for (int jl = 0; jl < n_local; ++jl) {
         acquire(0);
         w_steps(tmem_base, true);  // S1: dz . W3
-        umma_commit(BAR(B_DFULL + 0));
+        umma_commit_w(BAR(B_DFULL + 0));
         mbar_wait(BAR(B_HREADY), hphase, 7); hphase ^= 1;
         acquire(1);
         w_steps(tmem_base + 128u, false);  // S2: da2 . W2
-        umma_commit(BAR(B_DFULL + 1));
+        umma_commit_w(BAR(B_DFULL + 1));
         mbar_wait(BAR(B_HREADY), hphase, 7); hphase ^= 1;
 #pragma unroll 1
         for (int seg = 0; seg < nseg3; ++seg) {  // S3: da1 . W1[:, seg]
           acquire(seg & 1);
           w_steps(tmem_base + 128u * (uint32_t)(seg & 1), false);
-          umma_commit(BAR(B_DFULL + (seg & 1)));
+          umma_commit_w(BAR(B_DFULL + (seg & 1)));
         }
       }
     }
@@ -741,7 +742,7 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
   }
   if (warp == WG_NPW) {
     // ================================================================= MMA issuer: D[o][i] += sum_rows P[row][o] Q[row][i]
-    if (lane == 0) {
+    {  // (all 32 lanes walk the sequence in uniform control flow, one elected lane issues)
 #pragma unroll 1
       for (int c = 0; c < nch; ++c) {
         const uint32_t stg = (uint32_t)c % WG_STAGES;
@@ -753,11 +754,11 @@ __global__ void __launch_bounds__(WG_NTHREADS, 1) wgrad_tc3_kernel(const WgParam
 #pragma unroll
           for (int q = 0; q < (THIRD ? 6 : 3); ++q)
             if (q < p.nprod)
-              umma_bf16(tmem_base, umma_desc_mn(pb + prod_a(q) * 2 * WG_HALF_BYTES + kk * 2048),
+              umma_bf16_w(tmem_base, umma_desc_mn(pb + prod_a(q) * 2 * WG_HALF_BYTES + kk * 2048),
                         umma_desc_mn(qb + prod_w(q) * 2 * WG_HALF_BYTES + kk * 2048), IDESC_BF16_MN_MN, (c | kk | q) != 0);
-        umma_commit(BAR(2 + stg));
+        umma_commit_w(BAR(2 + stg));
       }
-      umma_commit(BAR(4));
+      umma_commit_w(BAR(4));
     }
     __syncwarp();
   } else if (warp < 4) {

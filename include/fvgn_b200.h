@@ -53,6 +53,10 @@ FVGN_API int fvgn_device_check(int* sm_count, int* cc_major, int* cc_minor);
  * would stay finite on such an input), or the input already held inf / NaN.  Re-run the step with FVGN_MATH_FP32_SIMT. */
 #define FVGN_STATUS_NONFINITE_X3 1u
 FVGN_API int fvgn_status_read(unsigned int* status_host, int clear);
+/* Tuning knob (A/B measurements, parity tests): 1 = the split-shadow inference kernels of FVGN_MATH_BF16X3_TC (fvgn_cell_block_fwd_split /
+ * fvgn_edge_block_fwd_split) run on CTA pairs with tcgen05.mma.cta_group::2 (each CTA holds half of every weight K-tile), 0 (default) = on
+ * single CTAs; same results bit for bit.  Returns the previous setting.  FVGN_X3_PAIR=1 in the environment sets the initial value to 1. */
+FVGN_API int fvgn_x3_pair_enable(int on);
 
 /* One MLP of build_mlp (FVGN_model/EncoderProcesserDecoder.py:12-48): Linear(k_in,128)-SiLU-Linear(128,128)-SiLU-
  * Linear(128,n_out) [+ LayerNorm(n_out), eps 1e-5].  Pointers are the nn.Linear tensors as they sit in the

@@ -91,6 +91,40 @@ def test_x3_split_shadow_fast_path_is_bit_identical(fv, golden):
         assert torch.equal(xps, _split_of(xp)), layer
 
 
+@pytest.mark.parametrize("nx,ny", [(9, 7), (13, 11), (150, 130), (200, 150), (331, 160)])
+def test_x3_pair_kernels_are_bit_identical(fv, nx, ny):
+    """The CTA-pair kernels (tcgen05.mma.cta_group::2: each CTA of a pair holds half of every weight K-tile, csrc/mlp_tc3_pair.cuh) against the
+    single-CTA kernels on the same inputs: the same MMAs on the same operands, same epilogue — same bits.  Sizes: one tile, an odd tile
+    count below the SM count, several tiles per CTA (even and odd counts, a ragged last tile), > 2 tiles per CTA pair."""
+    m = fv.synthetic.make("grid", seed=6, nx=nx, ny=ny, T=2)
+    t = lambda a, dt: torch.as_tensor(a).to(dt).cuda()
+    tab = fv.ops.build_connectivity(t(m["cells"], torch.int32), t(m["mesh_pos"], torch.float32), t(m["node_type"], torch.int32), "B")
+    C, F, N = tab["cells_node"].shape[0], tab["face"].shape[1], m["mesh_pos"].shape[0]
+    gen = torch.Generator().manual_seed(12)
+    x0, e0 = torch.randn(C, 128, generator=gen).cuda(), torch.randn(F, 128, generator=gen).cuda()
+    cb, _ = _mlp_module(fv, 192, seed=4)
+    eb, _ = _mlp_module(fv, 384, seed=5)
+    cnT, nc = tab["cells_node"].T.contiguous(), tab["neighbour_cell"].contiguous()
+    ptr, items = fv.ops.build_csr(tab["face"].reshape(-1).contiguous(), N)
+    L = fv._lib.lib()
+    outs = {}
+    prev = L.fvgn_x3_pair_enable(1)
+    try:
+        for on in (1, 0):
+            L.fvgn_x3_pair_enable(on)
+            x, e = x0.clone(), e0.clone()
+            xps = torch.empty((C, 2, 128), dtype=torch.float16, device="cuda")
+            for layer in range(3):
+                fv.ops.gn_block_fwd_inplace_split(cb.mlp_ref(), eb.mlp_ref(), x, e, fv.ops.node_aggregate_fwd(e, ptr, items, N), cnT, nc, xps)
+            torch.cuda.synchronize()
+            outs[on] = (x, e, xps.clone())
+    finally:
+        L.fvgn_x3_pair_enable(prev)
+    assert torch.isfinite(outs[1][0]).all() and torch.isfinite(outs[1][1]).all()
+    for a, b in zip(outs[1], outs[0]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("nx,ny", [(13, 11), (150, 130), (200, 150)])
 def test_x3_split_fast_path_mid_size_pairs(fv, nx, ny):
     """Same comparison on meshes that give a CTA several tiles (paired-tile schedule: two pairs + a single tile at ~60k cells, an odd
