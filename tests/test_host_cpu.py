@@ -167,7 +167,7 @@ def test_sass_of_the_tensor_core_kernels_is_blackwell_native():
             cur = m.group(1)
             per[cur] = set()
         elif cur:
-            per[cur].update(re.findall(r"\b(UTCHMMA|LDTM|STTM|UBLKCP|LDGSTS|SYNCS|HMMA|FFMA)\b", line))
+            per[cur].update(re.findall(r"\b(UTCHMMA\.2CTA|UTCBAR\.2CTA\.MULTICAST|UCGABAR_ARV|UTCHMMA|LDTM|STTM|UBLKCP|LDGSTS|SYNCS|HMMA|FFMA)\b", line))
     assert not any("HMMA" in v for v in per.values()), "legacy mma.sync / wmma path found"
     want = {"fused_mlp_tc_kernel": {"UTCHMMA", "LDTM", "STTM", "UBLKCP", "SYNCS"}, "fused_mlp_tc3_kernel": {"UTCHMMA", "LDTM", "STTM", "UBLKCP", "SYNCS"},
             "dgrad_tc3_kernel": {"UTCHMMA", "LDTM", "STTM", "UBLKCP", "SYNCS"}, "wgrad_tc3_kernel": {"UTCHMMA", "LDTM", "SYNCS"},
@@ -177,6 +177,12 @@ def test_sass_of_the_tensor_core_kernels_is_blackwell_native():
         assert ks, name
         for k in ks:
             assert need <= per[k], (k, need - per[k])
+    # round 2: the CTA-pair inference kernels issue the 2-CTA MMA (tcgen05.mma.cta_group::2), commit with a cluster multicast and synchronise
+    # the pair with the cluster barrier
+    pair = [k for k in per if "fused_mlp_tc3_pair_kernel" in k]
+    assert len(pair) == 2, pair
+    for k in pair:
+        assert {"UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST", "UCGABAR_ARV", "LDTM", "STTM", "UBLKCP", "SYNCS"} <= per[k], (k, per[k])
     # the two-term backward variants move their rows with cp.async (the staging rings of this round)
     assert any("wgrad_tc3_kernelILb0" in k and "LDGSTS" in v for k, v in per.items())
     assert any("dgrad_tc3_kernelILb0" in k and "LDGSTS" in v for k, v in per.items())
