@@ -422,6 +422,13 @@ def native(args, rank, world, local_rank):
                 result["speedup_over_torch_eager_cuda"] = sp
         if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only: at N > 1 the other ranks' host threads share the cores
             result["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_seconds)
+    if dist is not None and not args.no_dd_leg:
+        torch.cuda.empty_cache()
+        dd = domain_decomposition_leg(args, rank, world, dev, dist)
+        if rank == 0:
+            result["domain_decomposition"] = dd
+            if not dd["pass"]:
+                print(f"[bench] DOMAIN-DECOMPOSITION PARITY CHECK FAILED: {dd}", file=sys.stderr)
     if dist is not None and (args.check or world == 2):
         chk = dp_parity_check(rank, world, dev, dist)
         if rank == 0:
@@ -605,6 +612,75 @@ def training_measure(args, rank, world, dev, meshes, dist, fresh=True):
             if world > 1 else "single GPU",
             "step": "train_datapreprocessing + FVGN.forward(train) + compute_FVM_loss + backward + grad all-reduce + AdamW",
             "cuda_graph": graphed is not None}
+
+
+# ------------------------------------------------------------------------------------------------ single-mesh domain decomposition
+def domain_decomposition_leg(args, rank, world, dev, dist, steps=5):
+    """ONE mesh (`--dd-workload`, default the 1M-cell mesh of configs[4]) partitioned over the N GPUs of the box; every
+    rank runs the rollout step on its part (fvgn_b200.domain: two NCCL exchanges per GnBlock + one per step).  Checked against the
+    single-GPU rollout of the same mesh (rank 0 runs it and broadcasts next_uv) and timed next to it."""
+    import fvgn_b200 as fv
+    from fvgn_b200 import domain as D
+
+    kind, kw, _, _ = WORKLOADS[args.dd_workload]
+    m = fv.synthetic.make(kind, seed=4242, T=3, **kw)
+    t = lambda a, dt: torch.as_tensor(a).to(dt).to(dev)
+    tab = fv.ops.build_connectivity(t(m["cells"], torch.int32), t(m["mesh_pos"], torch.float32), t(m["node_type"], torch.int32), "B")
+    torch.manual_seed(0)
+    model = fv.FVGN(device="cpu", params=params()).to(dev).eval().set_math_mode("bf16x3")
+    gn, ge, gc = fv.dataset.build_graphs(tab, m["velocity"], m["pressure"], device=dev)
+    gn, ge, gc, mi, mb = fv.dataset.valid_datapreprocessing(gn, ge, gc, 0)
+    x0, ea0, bc = gc.x.clone(), gc.edge_attr.clone(), ge.y[:, 0, 0:2].clone()
+    C, F = x0.shape[0], ea0.shape[0]
+    # single-GPU rollout (every rank runs it: the comparison needs no broadcast and all ranks stay in step)
+    state = fv.dataset.RolloutState(gc, ge)
+    ref = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        model(graph=gc, graph_edge=ge, graph_node=gn, rho=RHO, mu=MU, dt=DT, edge_one_hot=9, cell_one_hot=0)  # warm-up (tables, packs)
+        gc.x, gc.edge_attr = x0.clone(), ea0.clone()
+        state = fv.dataset.RolloutState(gc, ge)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            uvp, nuv = model(graph=gc, graph_edge=ge, graph_node=gn, rho=RHO, mu=MU, dt=DT, edge_one_hot=9, cell_one_hot=0)
+            ref.append(nuv.clone())
+            state.advance_(gc, nuv)
+        e1.record()
+        torch.cuda.synchronize()
+    single_ms = e0.elapsed_time(e1) / steps
+    parts, _ = D.decompose({k: v for k, v in tab.items()}, world)
+    part = parts[rank]
+    run = D.PartRollout(part, D.KernelBackend(model), *D.initial_part_state(part, x0, ea0, bc), device=dev)
+    ms = dict(D.KernelBackend.state(model), dt=DT, rho=RHO)
+    comm = D.DistComm()
+    with torch.no_grad():
+        D.rollout_steps([run], comm, ms, 1)  # warm-up step (NCCL connections, allocator)
+        run = D.PartRollout(part, D.KernelBackend(model), *D.initial_part_state(part, x0, ea0, bc), device=dev)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        outs = D.rollout_steps([run], comm, ms, steps)[0]
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+    dd_ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(dd_ms, op=dist.ReduceOp.MAX)
+    own = torch.as_tensor(part.own).to(dev)
+    num = torch.stack([((outs[k][1].double() - ref[k][own].double()) ** 2).sum() for k in range(steps)])
+    den = torch.stack([(ref[k][own].double() ** 2).sum() for k in range(steps)])
+    both = torch.stack([num, den])
+    dist.all_reduce(both)
+    rel = torch.sqrt(both[0] / both[1])
+    ghosts = torch.tensor([float(part.G), float(sum(ix.size for ix in part.node_share.values()))], dtype=torch.float64, device=dev)
+    dist.all_reduce(ghosts, op=dist.ReduceOp.MAX)
+    return {"workload": args.dd_workload, "cells": int(C), "faces": int(F), "parts": world, "cells_per_part": int(part.C_own), "math": "bf16x3 (generic kernels)",
+            "max_ghost_cells_per_part": int(ghosts[0]), "max_interface_nodes_per_part": int(ghosts[1]), "steps": steps,
+            "ms_per_step": float(dd_ms[0]), "value": C / (float(dd_ms[0]) * 1e-3), "unit": "cell-updates/s", "scaling": "strong (one mesh over N GPUs)",
+            "single_gpu_eager_ms_per_step": single_ms, "speedup_over_single_gpu_eager": single_ms / float(dd_ms[0]),
+            "rel_l2_next_uv_vs_single_gpu_per_step": [float(v) for v in rel], "tolerance_per_step": 1e-5,
+            "pass": bool(all(float(v) < 1e-5 * (k + 1) for k, v in enumerate(rel))),
+            "exchanges_per_step": "2 per GnBlock (interface-node partial sums; ghost-cell x') + 1 (ghost next_uv), NCCL point-to-point batches"}
 
 
 # ------------------------------------------------------------------------------------------------ data-parallel parity check
@@ -857,6 +933,8 @@ def main():
     ap.add_argument("--no-torch-eager", action="store_true", help="skip the torch-eager CUDA leg (the unmodified reference on the GPU)")
     ap.add_argument("--no-training", action="store_true", help="skip the training graphs/s leg")
     ap.add_argument("--no-strict-leg", action="store_true", help="skip the strict-FFMA comparison leg")
+    ap.add_argument("--no-dd-leg", action="store_true", help="N > 1: skip the single-mesh domain-decomposition leg")
+    ap.add_argument("--dd-workload", default="mesh1m", choices=sorted(WORKLOADS), help="the ONE mesh the domain-decomposition leg partitions over the N GPUs")
     ap.add_argument("--no-foil-leg", action="store_true", help="skip the foil16 / bf16 leg (BASELINE configs[2])")
     ap.add_argument("--no-config0", action="store_true", help="skip the batch-1 rollout latency leg (configs[0])")
     ap.add_argument("--train-graph", type=int, default=1, help="1: time the training step replayed from one CUDA graph; 0: eager")

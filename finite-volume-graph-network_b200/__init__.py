@@ -3,7 +3,7 @@
 
     from fvgn_b200 import FVGN, Data, Batch, dataset
 The arithmetic lives in libfvgn_b200.so (sm_100a CUDA, C-ABI in include/fvgn_b200.h); there is no CPU fallback."""
-from . import _lib, ops, synthetic, parallel  # noqa: F401
+from . import _lib, ops, synthetic, parallel, domain  # noqa: F401
 from .data import Data, Batch  # noqa: F401
 from .topology import MeshTopology, topology_of  # noqa: F401
 from .FVGN_model import (FVGN, EncoderProcesserDecoder, Encoder, GnBlock, Decoder, Intergrator, build_mlp, CellBlock, EdgeBlock)  # noqa: F401
