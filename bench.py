@@ -674,7 +674,7 @@ def domain_decomposition_leg(args, rank, world, dev, dist, steps=5):
     rel = torch.sqrt(both[0] / both[1])
     ghosts = torch.tensor([float(part.G), float(sum(ix.size for ix in part.node_share.values()))], dtype=torch.float64, device=dev)
     dist.all_reduce(ghosts, op=dist.ReduceOp.MAX)
-    return {"workload": args.dd_workload, "cells": int(C), "faces": int(F), "parts": world, "cells_per_part": int(part.C_own), "math": "bf16x3 (generic kernels)",
+    return {"workload": args.dd_workload, "cells": int(C), "faces": int(F), "parts": world, "cells_per_part": int(part.C_own), "math": "bf16x3 (the in-place split-shadow kernels of the single-GPU fast path)",
             "max_ghost_cells_per_part": int(ghosts[0]), "max_interface_nodes_per_part": int(ghosts[1]), "steps": steps,
             "ms_per_step": float(dd_ms[0]), "value": C / (float(dd_ms[0]) * 1e-3), "unit": "cell-updates/s", "scaling": "strong (one mesh over N GPUs)",
             "single_gpu_eager_ms_per_step": single_ms, "speedup_over_single_gpu_eager": single_ms / float(dd_ms[0]),

@@ -142,6 +142,12 @@ class PartRollout:
         self.hsend = {q: t(ix, torch.long) for q, ix in part.halo_send.items()}
         self.hrecv = {q: t(ix, torch.long) for q, ix in part.halo_recv.items()}
         self.agg = backend.build_agg(self.agg_dst, part.N + 1)
+        # interface rows and their positions in the compact accumulation buffer: computed once (torch.unique synchronises)
+        if self.share:
+            self.if_rows = torch.unique(torch.cat([self.share[q] for q in sorted(self.share)]))
+            pos = torch.full((part.N + 1,), -1, dtype=torch.long, device=device)
+            pos[self.if_rows] = torch.arange(self.if_rows.numel(), device=device)
+            self.if_pos = {q: pos[ix] for q, ix in self.share.items()}
 
     # -- exchanges (split in post / finish so that LocalComm can run all parts in one process)
     def node_sends(self, na):
@@ -152,18 +158,15 @@ class PartRollout:
         the same order on every rank, so a node shared by three parts gets the same bits everywhere"""
         if not recvs:
             return na
-        rows = torch.unique(torch.cat([self.share[q] for q in recvs]))
-        pos = torch.full((na.shape[0],), -1, dtype=torch.long, device=na.device)
-        pos[rows] = torch.arange(rows.numel(), device=na.device)
+        rows = self.if_rows
         tot = torch.zeros((rows.numel(), na.shape[1]), dtype=na.dtype, device=na.device)
         for q in sorted(list(recvs) + [self.p.rank]):
             if q == self.p.rank:
                 tot += na.index_select(0, rows)
             else:
-                tot.index_add_(0, pos[self.share[q]], recvs[q])  # (a row not shared with q is not in the list: nothing is added)
-        out = na.clone()
-        out[rows] = tot
-        return out
+                tot.index_add_(0, self.if_pos[q], recvs[q])  # (a row not shared with q is not in q's list: nothing is added)
+        na[rows] = tot  # (na is this layer's own buffer)
+        return na
 
     def halo_sends(self, buf):
         return {q: buf.index_select(0, ix) for q, ix in self.hsend.items()}
@@ -251,15 +254,38 @@ class KernelBackend:
         return self.ops.node_aggregate_fwd(s["e"], ptr, items, n)
 
     def cell_block(self, pr, s, na, layer, ms):
+        import ctypes as C_
+
         blk = self.model.model.processer_list[layer]
         C = pr.p.C_own
+        ops = self.ops
+        if self.mode == 2:
+            # fp32-equivalent mode: the in-place split-shadow kernels of the single-GPU fast path; x' exists only as the fp16 hi / lo shadow
+            # [C_own + G, 2, 128] whose ghost rows the owners send (512 B per row, as an fp32 row)
+            L = ops._lib.lib()
+            xps = torch.empty((C + pr.p.G, 2, 128), dtype=torch.float16, device=s["x"].device)
+            cms = torch.empty((C, 2, 64), dtype=torch.float16, device=s["x"].device)
+            mlp = blk.cb_module.net.mlp_ref().ensure_packed(2)
+            ops._count(2)
+            ops.check(L.fvgn_cell_mean_split(ops._p(na), ops._p(pr.cnT), C, ops._p(cms), ops._stream()), "cell_mean_split")
+            ops.check(L.fvgn_cell_block_fwd_split(C_.byref(mlp.struct), ops._p(s["x"]), ops._p(cms), C, ops._p(xps), ops._stream()), "cell_block_fwd_split")
+            return xps
         buf = torch.empty((C + pr.p.G, 128), dtype=torch.float32, device=s["x"].device)
-        self.ops.cell_block_fwd(blk.cb_module.net.mlp_ref(), s["x"], na, pr.cnT, self.mode, x_prime=buf[:C], x_out=s["x"])
+        ops.cell_block_fwd(blk.cb_module.net.mlp_ref(), s["x"], na, pr.cnT, self.mode, x_prime=buf[:C], x_out=s["x"])
         return buf
 
     def edge_block(self, pr, s, xp, layer, ms):
+        import ctypes as C_
+
         blk = self.model.model.processer_list[layer]
-        self.ops.edge_block_fwd(blk.eb_module.net.mlp_ref(), xp, s["e"], pr.nc, self.mode, e_out=s["e"])
+        ops = self.ops
+        if self.mode == 2:
+            mlp = blk.eb_module.net.mlp_ref().ensure_packed(2)
+            ops._count(1)
+            ops.check(ops._lib.lib().fvgn_edge_block_fwd_split(C_.byref(mlp.struct), ops._p(xp), ops._p(s["e"]), ops._p(pr.nc), pr.p.F, ops._stream()),
+                      "edge_block_fwd_split")
+            return
+        ops.edge_block_fwd(blk.eb_module.net.mlp_ref(), xp, s["e"], pr.nc, self.mode, e_out=s["e"])
 
     def decode_integrate(self, pr, s, ms):
         m, ops = self.model, self.ops
