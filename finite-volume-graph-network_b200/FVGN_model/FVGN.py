@@ -99,16 +99,16 @@ class FVGN(nn.Module):
         faces_type = graph_edge.x[:, 0:1]
         uv = graph.x[:, 2:4]
         norm_before = parallel.snapshot_normalizers(self) if (self.training and parallel.is_distributed()) else None
-        if self.training:
-            target_acc = self.velocity_to_accelation(uv, graph.y[:, 0:2])
-            target_delta_u = self._acc_output_normalizer(target_acc, True)
-            target_face = self._face_uvp_flux_output_normalizer(graph_edge.y[:, 0:3], True)
-        x_in = self.update_cell_attr(uv, cell_one_hot, cells_type, self.training, normalizer="1")
-        e_in = self.update_edge_attr(graph.edge_attr, edge_one_hot, faces_type, self.training, normalizer="1", dual_edge=self.dual_edge)
         self.__dict__["_dp_bn_reduced"] = None
         if norm_before is not None:
-            # DP: every rank must normalise with the statistics of the WHOLE batch.  The face-area BatchNorm's batch
-            # statistics (a function of the geometry only) ride along in the same collective: one statistic all-reduce per step
+            # DP: every rank must normalise with the statistics of the WHOLE batch: accumulate locally (no apply yet),
+            # all-reduce the increments — the face-area BatchNorm's batch statistics (a function of the geometry only) ride along in the
+            # same collective: one statistic all-reduce per step —, then apply once
+            target_acc = self.velocity_to_accelation(uv, graph.y[:, 0:2])
+            self._acc_output_normalizer._accumulate(target_acc)
+            self._face_uvp_flux_output_normalizer._accumulate(graph_edge.y[:, 0:3])
+            self._cell_normalizer._accumulate(uv, cells_type if cell_one_hot > 0 else None, cell_one_hot)
+            self._edge_normalizer._accumulate(graph.edge_attr, faces_type if edge_one_hot > 0 else None, edge_one_hot)
             _, bn_sums = ops.face_area_sums(graph_edge.x, graph.cell_area, topo.nc, dt)
             extra = torch.cat([bn_sums, torch.full((1,), float(topo.F), dtype=torch.float64, device=bn_sums.device)])
             self.__dict__["_dp_bn_reduced"] = parallel.sync_normalizer_increments_(self, norm_before, extra=extra)
@@ -116,6 +116,13 @@ class FVGN(nn.Module):
             target_face = self._face_uvp_flux_output_normalizer(graph_edge.y[:, 0:3], False)
             x_in = self.update_cell_attr(uv, cell_one_hot, cells_type, False, normalizer="1")
             e_in = self.update_edge_attr(graph.edge_attr, edge_one_hot, faces_type, False, normalizer="1", dual_edge=self.dual_edge)
+        else:
+            if self.training:
+                target_acc = self.velocity_to_accelation(uv, graph.y[:, 0:2])
+                target_delta_u = self._acc_output_normalizer(target_acc, True)
+                target_face = self._face_uvp_flux_output_normalizer(graph_edge.y[:, 0:3], True)
+            x_in = self.update_cell_attr(uv, cell_one_hot, cells_type, self.training, normalizer="1")
+            e_in = self.update_edge_attr(graph.edge_attr, edge_one_hot, faces_type, self.training, normalizer="1", dual_edge=self.dual_edge)
         graph.x, graph.edge_attr = x_in, e_in
         if capture is not None:
             capture["cell_in"], capture["edge_in"] = x_in, e_in

@@ -113,7 +113,9 @@ class NetFunction(torch.autograd.Function):
         # instead of recomputing the forward in its tiles (a third of its FLOPs)
         zbuf = (lambda rows: ops.bucketed_empty((rows, 384), cell_in.device)) if mm == 2 else (lambda rows: None)
         z_enc_c, z_enc_e = zbuf(topo.C), zbuf(topo.F)
-        use_exec = EXECUTOR and mm == 2 and len(epd.processer_list) > 0
+        # (inside a CUDA-graph capture the host cost of the per-call path is irrelevant, and its backward interleaves the weight-gradient side
+        # stream and the data-parallel reduce groups layer by layer instead of joining the streams at the end of every chunk)
+        use_exec = EXECUTOR and mm == 2 and len(epd.processer_list) > 0 and not torch.cuda.is_current_stream_capturing()
         packed = None
         if use_exec:
             L, dev = len(epd.processer_list), cell_in.device
