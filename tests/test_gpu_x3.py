@@ -1,6 +1,7 @@
-"""GPU (B200): the fp32-equivalent tensor-core mode (FVGN_MATH_BF16X3_TC, csrc/mlp_tc3.cu: exact 3-way bf16 operand split, six
-tcgen05 MMAs per product, fp32 epilogue) is held to the SAME bound as the strict FFMA path: relative L2 <= 1e-5 per step against
-the oracle / the reference fixtures (north_star), per op <= 5e-6 against the fp64 oracle."""
+"""GPU (B200): the fp32-equivalent tensor-core mode (FVGN_MATH_BF16X3_TC, csrc/mlp_tc3.cu — forward: two-term fp16 split of both
+operands, three tcgen05 MMAs per product; backward: the three leading products of 3-way bf16 splits; fp32 epilogue) is held to the SAME
+bound as the strict FFMA path: relative L2 <= 1e-5 per step against the oracle / the reference fixtures (north_star), per op <= 5e-6
+against the fp64 oracle; the CTA-pair variants of the inference kernels (csrc/mlp_tc3_pair.cuh) to bit-identity with the single-CTA ones."""
 import numpy as np
 import pytest
 import torch
