@@ -25,8 +25,12 @@ namespace x3 {
 
 constexpr int PW_HALF = TILE_BYTES / 2;      // one fp16 plane of half a weight K-tile: [64 rows][128 B] = 8 KB
 constexpr int PW_SLOT = 2 * PW_HALF;         // hi | lo plane = 16 KB
+#ifndef FVGN_PARING
+#define FVGN_PARING 3
+#endif
+constexpr int PARING = FVGN_PARING;          // A-ring depth (the halved weight ring leaves room for a fourth 32 KB slot)
 constexpr int PWRING = 4, PEER_DEPTH = 8;
-enum { PB_AFULL = 0, PB_AEMPTY = PB_AFULL + FARING, PB_WFULL = PB_AEMPTY + FARING, PB_WEMPTY = PB_WFULL + PWRING, PB_DFULL = PB_WEMPTY + PWRING,
+enum { PB_AFULL = 0, PB_AEMPTY = PB_AFULL + PARING, PB_WFULL = PB_AEMPTY + PARING, PB_WEMPTY = PB_WFULL + PWRING, PB_DFULL = PB_WEMPTY + PWRING,
        PB_DFULL23 = PB_DFULL + 2, PB_HREADY = PB_DFULL23 + 2, PB_PEER = PB_HREADY + 2, PB_COUNT = PB_PEER + PEER_DEPTH };
 static_assert(PB_COUNT * 8 + 4 <= 256, "barrier block");
 // kind::f16, fp16 operands, M = 256 (bits [24,29) = M >> 4), N = 128: the pair's MMA
@@ -35,7 +39,7 @@ constexpr uint32_t IDESC_F16_M256_N128 = (IDESC_F16_M128_N128 & ~(0x1fu << 24)) 
 __host__ __device__ inline SmemLayout smem_layout_pair() {
   SmemLayout L;
   uint32_t o = 0;
-  L.a_off = o; o += FARING * FA_SLOT;   // 96 KB
+  L.a_off = o; o += PARING * FA_SLOT;   // 96 KB (128 KB with four slots)
   L.w_off = o; o += PWRING * PW_SLOT;   // 64 KB
   L.stage_off = o; o += 8 * 2048;
   L.par_off = o; o += 5 * 128 * 4 + 16;
@@ -154,7 +158,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_m
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) { printf("fvgn mlp_tc3_pair: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
-    for (int i = 0; i < FARING; ++i) { mbar_init(BAR(PB_AFULL + i), NPW); mbar_init(BAR(PB_AEMPTY + i), 1); }
+    for (int i = 0; i < PARING; ++i) { mbar_init(BAR(PB_AFULL + i), NPW); mbar_init(BAR(PB_AEMPTY + i), 1); }
     for (int i = 0; i < PWRING; ++i) { mbar_init(BAR(PB_WFULL + i), 1); mbar_init(BAR(PB_WEMPTY + i), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(BAR(PB_DFULL + a), 1); mbar_init(BAR(PB_DFULL23 + a), 1); mbar_init(BAR(PB_HREADY + a), 8); }
     for (int i = 0; i < PEER_DEPTH; ++i) mbar_init(BAR(PB_PEER + i), 1);
@@ -190,11 +194,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_m
     auto publish = [&](int s) {
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(PB_AFULL + (uint32_t)s % FARING));
+      if (lane == 0) mbar_arrive(BAR(PB_AFULL + (uint32_t)s % PARING));
     };
     auto acquire = [&](int s) {
-      if (s >= FARING) mbar_wait(BAR(PB_AEMPTY + (uint32_t)s % FARING), (((uint32_t)s / FARING) - 1) & 1, 1);
-      return sA + ((uint32_t)s % FARING) * FA_SLOT;
+      if (s >= PARING) mbar_wait(BAR(PB_AEMPTY + (uint32_t)s % PARING), (((uint32_t)s / PARING) - 1) & 1, 1);
+      return sA + ((uint32_t)s % PARING) * FA_SLOT;
     };
     if (MODE == TC_CELL) {
       auto ldx = [&](int jl, int half, float4* v) {
@@ -239,10 +243,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_m
       }
 #pragma unroll 1
       for (int s = 0; s < S; ++s) {
-        const uint32_t slot = (uint32_t)s % FARING;
+        const uint32_t slot = (uint32_t)s % PARING;
         const int jl = s / kt1, t = s - jl * kt1;
         const int row0 = ((int)blockIdx.x + jl * (int)gridDim.x) * TM;
-        if (s >= FARING) mbar_wait(BAR(PB_AEMPTY + slot), (((uint32_t)s / FARING) - 1) & 1, 1);
+        if (s >= PARING) mbar_wait(BAR(PB_AEMPTY + slot), (((uint32_t)s / PARING) - 1) & 1, 1);
         unsigned char* dst = sA + slot * FA_SLOT;
         if (t >= 4) {
           float4 v[RPT];
@@ -307,7 +311,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_m
       // one step = one weight K-tile slot (+ an A slot in layer 1, + the hidden activations at the start of layers 2 / 3)
       auto step_ready = [&](bool layer1, int a, bool first23, uint32_t& sa, uint32_t& sw) {
         if (first23) { mbar_wait(BAR(PB_HREADY + a), hphase[a], 7); hphase[a] ^= 1; }
-        if (layer1) { sa = ak % FARING; mbar_wait(BAR(PB_AFULL + sa), (ak / FARING) & 1, 4); }
+        if (layer1) { sa = ak % PARING; mbar_wait(BAR(PB_AFULL + sa), (ak / PARING) & 1, 4); }
         sw = wk % PWRING;
         mbar_wait(BAR(PB_WFULL + sw), (wk / PWRING) & 1, 5);
         if (rank == 0) {
