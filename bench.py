@@ -31,6 +31,8 @@ WORKLOADS = {
     "foil16": ("foil", {"n_target": 6400}, 16, "16 synthetic airfoil-shaped meshes (~5k nodes each)"),
     "mesh1m": ("grid", {"nx": 708, "ny": 708}, 1, "one scaled synthetic mesh of ~1.0M cells (BASELINE configs[4] kernel roofline sweep)"),
     "mesh1m_ordered": ("grid", {"nx": 708, "ny": 708, "shuffle": False}, 1, "~1.0M cells, cells numbered in generation (row-major) order"),
+    "mesh1m_renumbered": ("grid", {"nx": 708, "ny": 708, "renumber": "cells"}, 1, "mesh1m (random cell numbering) after fvgn_b200.renumber_mesh (cells along a Z-order curve; same results up to that permutation)"),
+    "mesh1m_renumbered_all": ("grid", {"nx": 708, "ny": 708, "renumber": "all"}, 1, "mesh1m after renumber_mesh(nodes=True): cells, nodes and with them the faces along the Z-order curve (another valid numbering: edge orientations differ)"),
     "tiny": ("grid", {"nx": 25, "ny": 17}, 2, "debug"),
 }
 
@@ -279,12 +281,14 @@ def rollout_config0(args, dev):
             "cell_updates_per_sec_cuda_graph": C * 10 / (g10 * 1e-3), "timing": "host wall clock around a synchronised call, median of 5"}
 
 
+def measured_peaks():
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(pk)) if os.path.exists(pk) else {}
+
+
 def roofline_of(m, math, workload):
     """roofline object of the dominant kernel (the fused EdgeBlock kernel) from a measure_forward() result"""
-    peaks = {}
-    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk):
-        peaks = json.load(open(pk))
+    peaks = measured_peaks()
     hbm = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     C, F = m["C"], m["F"]
@@ -372,11 +376,25 @@ def native(args, rank, world, local_rank):
                                "value": sm["total_cells"] * sm["steps"] / (sm["ms"] * 1e-3), "unit": "cell-updates/s",
                                "ms_per_step": sm["ms"] / sm["steps"], "steps": sm["steps"],
                                "e2e": {"value": sm["total_cells"] * sm["steps"] / (sm["e2e_ms"] * 1e-3), "unit": "cell-updates/s"},
-                               "whole_step_roofline": {"bytes_per_cell_update": 64200, "peak": sweep_roof["peak"], "unit": "GB/s",
+                               "whole_step_roofline": {"bytes_per_cell_update": 64200, "peak": measured_peaks().get("hbm_gbs", 6650.0), "unit": "GB/s",
                                                        "frac": 64200 * sm["total_cells"] * sm["steps"] / (sm["ms"] * 1e-3) / 1e9 / world
-                                                       / sweep_roof["peak"]},
+                                                       / measured_peaks().get("hbm_gbs", 6650.0)},
                                "clocks": sm["clocks"], "gpu_launches": sm["launches"]}
         del sm
+        for suffix in ("_renumbered", "_renumbered_all"):
+            # the same mesh after the converter's renumbering (fvgn_b200.renumber_mesh; "cells": same results up to that permutation, "all":
+            # nodes and faces too — another valid numbering): what the random cell numbering of the sweep mesh costs in gather traffic
+            if sw_work + suffix not in WORKLOADS or args.no_renumbered_leg:
+                continue
+            rm = measure_forward(args, sw_work + suffix, sw_math, min(args.steps, 5), rank, local_rank, dev, dist)
+            if rank == 0:
+                rr = roofline_of(rm, sw_math, sw_work + suffix)
+                v = rm["total_cells"] * rm["steps"] / (rm["ms"] * 1e-3)
+                result["sweep"][suffix[1:]] = {
+                    "workload": sw_work + suffix, "description": WORKLOADS[sw_work + suffix][3], "value": v, "unit": "cell-updates/s",
+                    "ms_per_step": rm["ms"] / rm["steps"], "edge_block_frac": rr["frac"], "share_of_step": rr.get("share_of_step"),
+                    "whole_step_roofline_frac": 64200 * v / 1e9 / world / measured_peaks().get("hbm_gbs", 6650.0)}
+            del rm
     if args.math != "fp32" and not args.no_strict_leg:
         fm = measure_forward(args, args.workload, "fp32", 3, rank, local_rank, dev, dist)
         if rank == 0:
@@ -939,6 +957,7 @@ def main():
     ap.add_argument("--no-config0", action="store_true", help="skip the batch-1 rollout latency leg (configs[0])")
     ap.add_argument("--train-graph", type=int, default=1, help="1: time the training step replayed from one CUDA graph; 0: eager")
     ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--no-renumbered-leg", action="store_true", help="skip the sweep mesh after fvgn_b200.renumber_mesh")
     ap.add_argument("--sweep", default="mesh1m:bf16", help="<workload>:<math> of the kernel roofline sweep leg, or 'none'")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()

@@ -13,5 +13,6 @@ from .dataset import Load_mesh as dataset  # noqa: F401
 from .utils.loss_compute import compute_FVM_loss  # noqa: F401
 from .rollout import GraphedRollout  # noqa: F401
 from .training import GraphedTrainStep  # noqa: F401
+from .renumber import renumber_mesh, inverse_permutation  # noqa: F401
 
 __version__ = "0.1.0"

@@ -204,12 +204,27 @@ def flow_scalars(tab, velocity0, pressure0, rho, mu):
             "reynolds_num": (mean_u_np * L0_np) / np.array(mu)}
 
 
-def extract_mesh_state(dataset, h5_writer, index, solving_params=None, face_rule=None, device="cuda"):
+def extract_mesh_state(dataset, h5_writer, index, solving_params=None, face_rule=None, device="cuda", renumber=False):
     """parse_tfrecord_refactor.py:419-971 on the device.  dataset: mesh_pos [T|1,N,2], cells [T|1,C,3], node_type [T|1,N,1], velocity
     [T,N,2], pressure [T,N,1] (numpy).  Writes group str(index) with the reference's keys / shapes / dtypes into `h5_writer` (h5py.File
     or MeshStore) and returns it as a dict.  face_rule None follows the reference's branch selection — `"compressible" in name` (:491;
-    the shipped name "incompressible" CONTAINS it, Appendix B) -> rule "A", else "B"."""
+    the shipped name "incompressible" CONTAINS it, Appendix B) -> rule "A", else "B".
+    renumber="cells" (or True) / "all": cells (and nodes) are first sorted along a Z-order curve (renumber.py: gathers then hit L2 whatever
+    numbering the source had; "cells" leaves every result unchanged up to that permutation, "all" also reorders the faces but changes the
+    orientation conventions the reference derives from node numbers); the group additionally holds `renumber|node_perm` /
+    `renumber|cell_perm` (new -> old), everything else is an ordinary group."""
     sp = solving_params or {"name": "incompressible", "rho": 1.0, "mu": 1e-3, "dt": 0.01}
+    perms = None
+    if renumber:
+        from .renumber import renumber_mesh
+
+        m1, node_perm, cell_perm = renumber_mesh({"mesh_pos": np.asarray(dataset["mesh_pos"][0]), "cells": np.asarray(dataset["cells"][0]),
+                                                  "node_type": np.asarray(dataset["node_type"][0]).reshape(-1),
+                                                  "velocity": np.asarray(dataset["velocity"]), "pressure": np.asarray(dataset["pressure"])},
+                                                 nodes=(renumber == "all"))
+        dataset = dict(dataset, mesh_pos=m1["mesh_pos"][None], cells=m1["cells"][None], node_type=m1["node_type"].reshape(1, -1, 1),
+                       velocity=m1["velocity"], pressure=m1["pressure"])
+        perms = {"renumber|node_perm": node_perm, "renumber|cell_perm": cell_perm}
     if face_rule is None:
         face_rule = "A" if "compressible" in sp.get("name", "") else "B"
     dev = torch.device(device)
@@ -225,6 +240,8 @@ def extract_mesh_state(dataset, h5_writer, index, solving_params=None, face_rule
     mesh["node_type"] = np.asarray(dataset["node_type"][0]).reshape(1, -1, 1).astype(np.int32)
     mesh["target|velocity_on_node"], mesh["target|pressure_on_node"] = vel, prs
     mesh.update(scal)
+    if perms is not None:
+        mesh.update(perms)
     if h5_writer is not None:
         grp = h5_writer.create_group(str(index))
         for k, v in mesh.items():
@@ -232,7 +249,7 @@ def extract_mesh_state(dataset, h5_writer, index, solving_params=None, face_rule
     return mesh
 
 
-def convert_tfrecord(tf_dataset_path, out_dir, splits=("valid", "train", "test"), solving_params=None, limit=None, device="cuda"):
+def convert_tfrecord(tf_dataset_path, out_dir, splits=("valid", "train", "test"), solving_params=None, limit=None, device="cuda", renumber=False):
     """the __main__ of parse_tfrecord_refactor.py:3019-3084 (saving_h5 branch)"""
     os.makedirs(out_dir, exist_ok=True)
     counts = {}
@@ -242,7 +259,7 @@ def convert_tfrecord(tf_dataset_path, out_dir, splits=("valid", "train", "test")
         w = _writer(out_dir, split)
         n = 0
         for n, traj in enumerate(load_dataset(tf_dataset_path, split), 1):
-            extract_mesh_state(traj, w, n - 1, solving_params, device=device)
+            extract_mesh_state(traj, w, n - 1, solving_params, device=device, renumber=renumber)
             if limit is not None and n >= limit:
                 break
         w.close()
@@ -364,11 +381,11 @@ class ComsolCase:
                 "aoa": self.case_info["aoa"]}
 
 
-def convert_comsol(mesh_file, data_file, h5_writer, index, solving_params=None, device="cuda"):
+def convert_comsol(mesh_file, data_file, h5_writer, index, solving_params=None, device="cuda", renumber=False):
     """Cosmol_manager.extract_mesh (parse_comsol.py:188-332) -> extract_mesh_state.  The reference passes its `path` dict as
     solving_params (:323-330), which has no "name" with "compressible" in it: face-typing rule B."""
     sp = dict(solving_params or {"name": "comsol", "rho": 1.0, "mu": 1e-3, "dt": 0.01})
-    return extract_mesh_state(ComsolCase(mesh_file, data_file).trajectory(), h5_writer, index, sp, device=device)
+    return extract_mesh_state(ComsolCase(mesh_file, data_file).trajectory(), h5_writer, index, sp, device=device, renumber=renumber)
 
 
 def main(argv=None):
@@ -381,17 +398,20 @@ def main(argv=None):
     a.add_argument("--splits", nargs="+", default=["valid", "train", "test"])
     a.add_argument("--name", default="incompressible")
     a.add_argument("--limit", type=int, default=None)
+    a.add_argument("--renumber", choices=["cells", "all"], default=None, help="sort cells (and nodes) along a Z-order curve first (renumber.py)")
     b = sub.add_parser("comsol")
     b.add_argument("mesh_file"), b.add_argument("data_file"), b.add_argument("out_dir")
     b.add_argument("--split", default="train")
     b.add_argument("--index", type=int, default=0)
+    b.add_argument("--renumber", choices=["cells", "all"], default=None)
     args = ap.parse_args(argv)
     if args.cmd == "tfrecord":
-        print(convert_tfrecord(args.dataset_dir, args.out_dir, args.splits, {"name": args.name, "rho": 1.0, "mu": 1e-3, "dt": 0.01}, args.limit))
+        print(convert_tfrecord(args.dataset_dir, args.out_dir, args.splits, {"name": args.name, "rho": 1.0, "mu": 1e-3, "dt": 0.01}, args.limit,
+                               renumber=args.renumber))
     else:
         os.makedirs(args.out_dir, exist_ok=True)
         w = _writer(args.out_dir, args.split)
-        convert_comsol(args.mesh_file, args.data_file, w, args.index)
+        convert_comsol(args.mesh_file, args.data_file, w, args.index, renumber=args.renumber)
         w.close()
 
 

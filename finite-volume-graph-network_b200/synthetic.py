@@ -382,7 +382,12 @@ def hybrid_mesh(nx=25, ny=17, seed=0, T=3, jitter=0.25, quad_fraction=0.5, hole=
                 meta=dict(kind="hybrid", seed=seed, nx=nx, ny=ny, quads=int(as_quad.sum()), triangles=int(2 * tri.sum())))
 
 
-def make(kind, seed=0, T=3, **kw):
+def make(kind, seed=0, T=3, renumber=False, **kw):
+    """renumber="cells" (or True) / "all": the mesh after renumber.renumber_mesh (cells / cells and nodes along a Z-order curve)"""
+    if renumber:
+        from .renumber import renumber_mesh
+
+        return renumber_mesh(make(kind, seed=seed, T=T, **kw), nodes=(renumber == "all"))[0]
     if kind == "cyl":
         return cylinder_mesh(seed=seed, T=T, **kw)
     if kind in ("rect", "naca"):
