@@ -91,6 +91,7 @@ _SIGS = {
     "fvgn_edge_grad_combine": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "fvgn_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     "fvgn_integrator_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P]),
+    "fvgn_integrator_bwd_poly": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P]),
     "fvgn_face_area_bn_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P]),
 }
 
@@ -114,7 +115,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.fvgn_abi_version() != 9:
+        if L.fvgn_abi_version() != 10:
             raise RuntimeError("libfvgn_b200.so ABI version mismatch")
         _lib = L
     return _lib

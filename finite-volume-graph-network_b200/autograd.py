@@ -104,8 +104,6 @@ class NetFunction(torch.autograd.Function):
     def forward(ctx, model, topo, cell_in, edge_in, graph_edge_x, cell_area, unv, rho, dt, *params):
         epd = model.model
         enc_c, enc_e = epd.encoder.cb_encoder, epd.encoder.eb_encoder
-        if topo.poly:
-            raise NotImplementedError("training on tri / quad hybrid meshes ([4,C] tables) is not built (inference / rollout is)")
         # forward arithmetic: strict FFMA ("fp32": FFMA backward that recomputes each tile from the saved layer inputs), the
         # fp32-equivalent tensor-core mode ("bf16x3") or plain bf16 tiles ("bf16"): tensor-core backward from the saved pre-activations
         mm = {"fp32": 0, "bf16x3": 2, "bf16": 2}[model.math_mode]  # "bf16": the bf16x3 kernels with the leading split product only
@@ -115,7 +113,8 @@ class NetFunction(torch.autograd.Function):
         z_enc_c, z_enc_e = zbuf(topo.C), zbuf(topo.F)
         # (inside a CUDA-graph capture the host cost of the per-call path is irrelevant, and its backward interleaves the weight-gradient side
         # stream and the data-parallel reduce groups layer by layer instead of joining the streams at the end of every chunk)
-        use_exec = EXECUTOR and mm == 2 and len(epd.processer_list) > 0 and not torch.cuda.is_current_stream_capturing()
+        # (tri / quad tables: per-call path — the k-wide mean and its transpose are separate small kernels there)
+        use_exec = EXECUTOR and mm == 2 and len(epd.processer_list) > 0 and not torch.cuda.is_current_stream_capturing() and not topo.poly
         packed = None
         if use_exec:
             L, dev = len(epd.processer_list), cell_in.device
@@ -138,12 +137,15 @@ class NetFunction(torch.autograd.Function):
             cb, eb = blk.cb_module.net, blk.eb_module.net
             ag = topo.agg(blk.cb_module.mp_times)
             na = ops.node_aggregate_fwd(e, ag.ptr, ag.items, ag.rows)
-            if mm == 2 and ag.idx is not None:
+            idx_k = ag.idx  # what the fused CellBlock kernel gathers through (None: `na` is the per-cell row already)
+            if ag.idx is not None and (mm == 2 or topo.poly):
                 # tensor-core training: the per-cell mean once per layer (same arithmetic), then the forward and the weight-gradient
-                # kernel read it as a plain per-cell row (cells_node_T = NULL) instead of three gathered node rows each
-                na = ops.cell_mean(na, ag.idx)
+                # kernel read it as a plain per-cell row (cells_node_T = NULL) instead of three gathered node rows each.
+                # tri / quad tables: the k-wide mean (fvgn_cell_mean_poly) in every math mode
+                na = ops.cell_mean_poly(na, ag.idx) if topo.poly else ops.cell_mean(na, ag.idx)
+                idx_k = None
             zc, ze = zbuf(topo.C), zbuf(topo.F)
-            xp, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, na, ag.idx if mm != 2 else None, mm, z_save=zc)
+            xp, x_new = ops.cell_block_fwd(cb.mlp_ref(), x, na, idx_k, mm, z_save=zc)
             _, e_new = ops.edge_block_fwd(eb.mlp_ref(), xp, e, topo.nc, mm, z_save=ze)
             saved.append((x, e, xp, na, zc, ze))
             x, e = x_new, e_new
@@ -266,9 +268,14 @@ class NetFunction(torch.autograd.Function):
                 grads[id(cb)] = sq.wgrad(cb.mlp_ref(), 1, g_xp, dz, gxh, zc, da, src0=x_in, src1=na, idx=None,  # na = the per-cell aggregate
                                          alive=(g_xp, dz, gxh, zc, da, x_in, na), slot=slot(cb))
             else:
-                grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, ag.idx, g_xp, d_x_base=g_x, z_saved=zc)
+                grads[id(cb)], dA_c = ops.cell_block_bwd(cb.mlp_ref(), x_in, na, None if topo.poly else ag.idx, g_xp, d_x_base=g_x, z_saved=zc)
             # transposes of the twice-message aggregation: cell -> node (x 1/3), node -> face halves
-            if ag.idx is not None:
+            if ag.idx is not None and topo.poly:
+                # tri / quad tables: the mean's 1/k differs from cell to cell — scale the rows, then the plain segment sum over the
+                # CSR whose -1 entries sit in an extra row that is not walked
+                dA_c[:, 128:192].mul_(topo.inv_k())
+                g_na = ops.segment_sum_rows(dA_c, topo.C, 128, 0, 64, nptr, nitems, topo.N, base=None, scale=1.0)
+            elif ag.idx is not None:
                 g_na = ops.segment_sum_rows(dA_c, topo.C, 128, 0, 64, nptr, nitems, topo.N, base=None, scale=1.0 / 3.0)
             else:  # mp_times = 1: the aggregate is per cell and enters the MLP as it is; its transpose is the identity
                 g_na = dA_c[:, 128:192].contiguous()

@@ -407,7 +407,8 @@ __global__ void loss_bwd_kernel(const float* __restrict__ pdu, const float* __re
 // transpose of the Intergrator's three gathers: one thread per face walks its incident (cell, k) pairs in CSR order
 __global__ void integrator_bwd_kernel(const float* __restrict__ dec, const float* __restrict__ unv, const float* __restrict__ fa,
                                       const float* __restrict__ g_du, const int32_t* __restrict__ ptr, const int32_t* __restrict__ items,
-                                      int C, int F, float inv_rho, float rhs, float* __restrict__ g_dec, float* __restrict__ g_fa) {
+                                      int C, int F, int kmax /* 3, or 4: [C,4,2] normals of a tri / quad mesh */, float inv_rho, float rhs,
+                                      float* __restrict__ g_dec, float* __restrict__ g_fa) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   const float u = dec[5 * (size_t)f], v = dec[5 * (size_t)f + 1], p = dec[5 * (size_t)f + 2], a = fa[f];
@@ -416,7 +417,7 @@ __global__ void integrator_bwd_kernel(const float* __restrict__ dec, const float
     const int pos = items[i];
     const int k = pos / C, c = pos - k * C;
     const float gx = g_du[2 * (size_t)c], gy = g_du[2 * (size_t)c + 1];
-    const float nx = unv[(size_t)c * 6 + 2 * k], ny = unv[(size_t)c * 6 + 2 * k + 1];
+    const float nx = unv[((size_t)c * kmax + k) * 2], ny = unv[((size_t)c * kmax + k) * 2 + 1];
     gu += -rhs * a * (gx * (2.0f * u * nx + v * ny) + gy * (v * nx));
     gv += -rhs * a * (gx * (u * ny) + gy * (u * nx + 2.0f * v * ny));
     gdx += gx;
@@ -680,7 +681,19 @@ extern "C" int fvgn_integrator_bwd(const float* decoded, const float* unv, const
   FVGN_CHECK_ARG(rho != 0.f, "rho must be non-zero");
   if (n_faces <= 0) return 0;
   integrator_bwd_kernel<<<cdiv(n_faces, 256), 256, 0, as_stream(stream)>>>(decoded, unv, face_area, g_delta_u, face_ptr, face_items, n_cells,
-                                                                           n_faces, 1.0f / rho, rhs_coef, g_decoded, g_face_area);
+                                                                           n_faces, 3, 1.0f / rho, rhs_coef, g_decoded, g_face_area);
+  FVGN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fvgn_integrator_bwd_poly(const float* decoded, const float* unv4, const float* face_area, const float* g_delta_u,
+                                        const int32_t* face_ptr, const int32_t* face_items, int n_cells, int n_faces, float rho, float rhs_coef,
+                                        float* g_decoded, float* g_face_area, fvgn_stream_t stream) {
+  FVGN_CHECK_ARG(decoded && unv4 && face_area && g_delta_u && face_ptr && face_items && g_decoded && g_face_area, "NULL pointer");
+  FVGN_CHECK_ARG(rho != 0.f, "rho must be non-zero");
+  if (n_faces <= 0) return 0;
+  integrator_bwd_kernel<<<cdiv(n_faces, 256), 256, 0, as_stream(stream)>>>(decoded, unv4, face_area, g_delta_u, face_ptr, face_items, n_cells,
+                                                                           n_faces, 4, 1.0f / rho, rhs_coef, g_decoded, g_face_area);
   FVGN_LAUNCH_CHECK();
   return 0;
 }

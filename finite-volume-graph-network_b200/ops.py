@@ -876,8 +876,11 @@ def integrator_bwd_(g_decoded, decoded, unv, face_area, g_delta_u, face_ptr, fac
     F = decoded.shape[0]
     g_fa = torch.empty((F, 1), dtype=torch.float32, device=decoded.device)
     _count(1)
-    check(_lib.lib().fvgn_integrator_bwd(_p(decoded), _p(unv), _p(face_area), _p(g_delta_u), _p(face_ptr), _p(face_items), n_cells, F, float(rho),
-                                         float(rhs_coef), _p(g_decoded), _p(g_fa), _stream()), "integrator_bwd")
+    L = _lib.lib()
+    poly = unv.dim() == 3 and unv.shape[1] == 4  # tri / quad mesh: unv [C,4,2], CSR over the [4,C] face table
+    fn = L.fvgn_integrator_bwd_poly if poly else L.fvgn_integrator_bwd
+    check(fn(_p(decoded), _p(unv), _p(face_area), _p(g_delta_u), _p(face_ptr), _p(face_items), n_cells, F, float(rho), float(rhs_coef),
+             _p(g_decoded), _p(g_fa), _stream()), "integrator_bwd")
     return g_fa
 
 

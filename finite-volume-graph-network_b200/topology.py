@@ -44,17 +44,32 @@ class MeshTopology:
         return _Agg(ptr, items, self.C, None, self.nc)
 
     def backward_tables(self):
-        """CSR transposes needed by the backward kernels: cell<-(face,side), node<-(cell,k), face<-(cell,k)."""
-        if self.poly:
-            raise NotImplementedError("training on tri / quad hybrid meshes ([4,C] tables) is not built: the backward's CSR transposes and "
-                                      "per-cell 1/k scales take [3,C] tables (inference / rollout is: BASELINE configs[3])")
+        """CSR transposes needed by the backward kernels: cell<-(face,side), node<-(cell,k), face<-(cell,k).
+        Tri / quad tables ([4,C], -1 padded): the -1 entries are keyed to an extra destination row that the kernels do not walk (they are given
+        n_dst rows of an (n_dst + 2)-entry pointer array)."""
         if self._bwd is None:
+            def csr(keys, n):
+                if not self.poly:
+                    return ops.build_csr(keys, n)
+                return ops.build_csr(torch.where(keys < 0, torch.full_like(keys, n), keys), n + 1)
+
             self._bwd = dict(
                 cell_from_face=ops.build_csr(self.nc.reshape(-1), self.C),
-                node_from_cell=ops.build_csr(self.cnT.reshape(-1), self.N),
-                face_from_cell=ops.build_csr(self.cfT.reshape(-1), self.F),
+                node_from_cell=csr(self.cnT.reshape(-1), self.N),
+                face_from_cell=csr(self.cfT.reshape(-1), self.F),
             )
         return self._bwd
+
+    def inv_k(self):
+        """[C,1] fp32: 1 / (number of nodes of the cell) — the transpose of the CellBlock's k-wide mean on tri / quad tables"""
+        v = self.__dict__.get("_inv_k")
+        if v is None:
+            if self.poly:
+                v = torch.where(self.cnT[3] >= 0, 0.25, 1.0 / 3.0).to(torch.float32).view(-1, 1).contiguous()
+            else:
+                v = torch.full((self.C, 1), 1.0 / 3.0, dtype=torch.float32, device=self.cnT.device)
+            self.__dict__["_inv_k"] = v
+        return v
 
 
 def _train_tables(topo, mp_times):
@@ -63,6 +78,8 @@ def _train_tables(topo, mp_times):
 
     key = "_tt%d" % (2 if mp_times >= 2 else 1)
     tt = topo.__dict__.get(key)
+    if topo.poly:
+        raise NotImplementedError("the C-side training executor takes [3,C] tables; tri / quad meshes train through the per-call path")
     if tt is None:
         bt = topo.backward_tables()
         p = lambda t: t.data_ptr()

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FVGN_ABI_VERSION 9 /* v9: fvgn_status_read, fvgn_loss_partials / fvgn_loss_finish (data-parallel reduce-before-log); [4,C] tri/quad tables;  v7: cells_node_T == NULL selects the mp_times = 1 CellBlock in every cell-block entry point; v8: fvgn_mlp_pack_bf16x3_many, fvgn_mlp_pack_bf16x3_bwd_many, fvgn_cell_mean, fvgn_ln_bwd column-sum partials, n_products = 3 */
+#define FVGN_ABI_VERSION 10 /* v10: fvgn_integrator_bwd_poly (training on tri / quad tables); v9: fvgn_status_read, fvgn_loss_partials / fvgn_loss_finish (data-parallel reduce-before-log); [4,C] tri/quad tables;  v7: cells_node_T == NULL selects the mp_times = 1 CellBlock in every cell-block entry point; v8: fvgn_mlp_pack_bf16x3_many, fvgn_mlp_pack_bf16x3_bwd_many, fvgn_cell_mean, fvgn_ln_bwd column-sum partials, n_products = 3 */
 #define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
 
 #define FVGN_E_BADARG (-1)
@@ -372,6 +372,12 @@ FVGN_API int fvgn_loss_bwd(const float* pred_delta_u, const float* target_delta_
 FVGN_API int fvgn_integrator_bwd(const float* decoded, const float* unv, const float* face_area, const float* g_delta_u,
                                  const int32_t* face_ptr, const int32_t* face_items, int n_cells, int n_faces, float rho, float rhs_coef,
                                  float* g_decoded /*in/out*/, float* g_face_area, fvgn_stream_t stream);
+/* the same over the [4,C] (-1 padded) face table of a tri / quad mesh: unv4 [C,4,2]; (face_ptr, face_items) = CSR of cells_face4_T.reshape(-1)
+ * by face with the -1 entries collected in an extra row n_faces that is not walked.  No reference counterpart (triangles only): the
+ * transpose of fvgn_integrator_fwd_poly, checked against torch autograd over oracle/fvgn_oracle_poly.py. */
+FVGN_API int fvgn_integrator_bwd_poly(const float* decoded, const float* unv4, const float* face_area, const float* g_delta_u,
+                                      const int32_t* face_ptr, const int32_t* face_items, int n_cells, int n_faces, float rho, float rhs_coef,
+                                      float* g_decoded /*in/out*/, float* g_face_area, fvgn_stream_t stream);
 /* BatchNorm1d(1) affine gradients: g_weight_bias[2] from g_face_area, the saved raw feature and (mean, invstd) */
 FVGN_API int fvgn_face_area_bn_bwd(const float* g_face_area, const float* raw, const float* batch_stats, int n_faces, float* g_weight_bias,
                                    float* workspace, fvgn_stream_t stream);

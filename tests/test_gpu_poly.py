@@ -7,6 +7,8 @@ COMSOL-style mesh").  The reference is triangles only, so
   * on hybrid meshes: connectivity / geometry tables bit-equal to the polygon oracle; one step and a 600-step rollout of the strict
     and the fp32-equivalent path within fp32 rel 1e-5 per step of the oracle's torch-CPU rollout over the same [4,C] tables; bf16 tiles
     within their stated bound; the pre-step (interpolation with four weights) bit-equal
+  * TRAINING on hybrid meshes: loss and all 264 parameter gradients of the strict and the fp32-equivalent backward against torch autograd
+    over the polygon oracle (mp_times 2 and 1)
 """
 import numpy as np
 import pytest
@@ -162,10 +164,57 @@ def test_hybrid_batch_and_mp_times_1(fv):
                 uvp, nuv = model(graph=g2, graph_edge=ge, graph_node=gn, rho=H.RHO, mu=H.MU, dt=H.DT, edge_one_hot=9, cell_one_hot=0)
             e1, e2 = H.rel_l2(uvp.cpu(), ouvp), H.rel_l2(nuv.cpu(), onuv)
             assert e1 < 1e-5 and e2 < 1e-5, (mp, math, e1, e2)
-    with pytest.raises(NotImplementedError):
-        model.train()
-        gt = gc.clone()
-        gt.y = gc.y[:, 0, :]
-        et = ge.clone()
-        et.y = ge.y[:, 0, :]
-        model(graph=gt, graph_edge=et, graph_node=gn, rho=H.RHO, mu=H.MU, dt=H.DT, edge_one_hot=9, cell_one_hot=0)
+
+
+def _oracle_hybrid_grads(ms, sd, p, noise, flip):
+    orc = O.FVGNOracle(sd, p).train()
+    for k, v in list(orc.sd.items()):
+        if v.is_floating_point() and ("model." in k or k in ("_grid_feature_normalizer.weight", "_grid_feature_normalizer.bias")):
+            orc.sd[k] = v.clone().requires_grad_(True)
+    orc.bn["weight"], orc.bn["bias"] = orc.sd["_grid_feature_normalizer.weight"], orc.sd["_grid_feature_normalizer.bias"]
+    bags = [O.build_graphs(P.build_connectivity_poly(m["mesh_pos"], m["cells"], m["node_type"], "B"), m["velocity"], m["pressure"], training_pair=0)
+            for m in ms]
+    gn, ge, gc = [O.batch_graphs([b[k] for b in bags]) for k in range(3)]
+    gn, ge, gc, mi, mb = O.train_datapreprocessing(gn, ge, gc, noise, flip)
+    out = orc(gc, ge, gn, H.RHO, H.MU, H.DT, 9, 0)
+    loss = O.compute_fvm_loss(p, gc.batch, ge.batch, mi, out[3], out[4], out[1], out[2], num_graphs=len(ms))
+    loss[0].backward()
+    return float(loss[0].detach()), {k: v.grad for k, v in orc.sd.items() if v.requires_grad}
+
+
+@pytest.mark.parametrize("mp", [2, 1])
+def test_training_step_on_hybrid_meshes_vs_oracle_autograd(fv, mp):
+    """training on [4,C] tables (no reference counterpart: triangles only): loss and all 264 parameter gradients of the strict and the
+    fp32-equivalent backward against torch autograd over the polygon oracle, on a batch of two tri / quad meshes"""
+    ms = [fv.synthetic.make("hybrid", seed=s, T=3, nx=20 + s, ny=13, quad_fraction=0.5) for s in (1, 2)]
+    sd = H.torch_reference_state_dict(0)
+    p = H.params(loss="global_mean_sum", mp_times=mp)
+    lists = [fv.dataset.build_graphs(_gpu_tables(fv, m), m["velocity"], m["pressure"], training_pair=0, device="cuda") for m in ms]
+    C = sum(l[2].x.shape[0] for l in lists)
+    F = sum(l[1].x.shape[0] for l in lists)
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randn(C, 2, generator=g) * 0.02
+    flip = torch.rand(F, generator=g) < 0.5
+    want_loss, want = _oracle_hybrid_grads(ms, sd, p, noise, flip)
+    for math, tol in (("fp32", 1e-4), ("bf16x3", 2e-4)):
+        model = fv.FVGN(device="cpu", params=p)
+        model.load_state_dict(sd)
+        model = model.cuda().train().set_math_mode(math)
+        gl = fv.dataset.collate([[b.clone() for b in l] for l in lists])
+        gn, ge, gc, mi, mb = fv.dataset.train_datapreprocessing(gl, cell_noise=noise.cuda(), flip_keep=flip.cuda())
+        out = model(graph=gc, graph_edge=ge, graph_node=gn, rho=H.RHO, mu=H.MU, dt=H.DT, edge_one_hot=9, cell_one_hot=0)
+        loss = fv.compute_FVM_loss(params=p, graph_cell=gc, graph_edge=ge, mask_face_interior=mi, predicted_edge_attr=out[3],
+                                   target_face_uvp_normalized=out[4], predicted_delta_u=out[1], target_delta_u=out[2])
+        loss[0].backward()
+        got_loss = float(loss[0].detach())
+        assert abs(got_loss - want_loss) < 5e-5 * max(1.0, abs(want_loss)), (math, got_loss, want_loss)
+        named = dict(model.named_parameters())
+        assert set(named) == set(want)
+        worst = ("", 0.0)
+        for k, w in want.items():
+            err = H.rel_l2(named[k].grad.cpu(), w)
+            if err > worst[1]:
+                worst = (k, err)
+        print(f"hybrid training step mp_times={mp} {math}: worst relative L2 over {len(want)} gradients: {worst}")
+        assert worst[1] < tol, (math, worst)
+    assert fv.ops.status(clear=True) == 0
