@@ -966,7 +966,7 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cyl16", choices=sorted(WORKLOADS))
@@ -984,7 +984,7 @@ def main():
     ap.add_argument("--no-foil-leg", action="store_true", help="skip the foil16 / bf16 leg (BASELINE configs[2])")
     ap.add_argument("--no-config0", action="store_true", help="skip the batch-1 rollout latency leg (configs[0])")
     ap.add_argument("--train-graph", type=int, default=1, help="1: time the training step replayed from one CUDA graph; 0: eager")
-    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--no-renumbered-leg", action="store_true", help="skip the sweep mesh after fvgn_b200.renumber_mesh")
     ap.add_argument("--sweep", default="mesh1m:bf16", help="<workload>:<math> of the kernel roofline sweep leg, or 'none'")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
