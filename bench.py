@@ -671,7 +671,21 @@ def domain_decomposition_leg(args, rank, world, dev, dist, steps=5):
     part = parts[rank]
     run = D.PartRollout(part, D.KernelBackend(model), *D.initial_part_state(part, x0, ea0, bc), device=dev)
     ms = dict(D.KernelBackend.state(model), dt=DT, rho=RHO)
-    comm = D.DistComm()
+    # exchanges: rows stored straight into the neighbours' receive buffers over NVLink peer memory + sequence flags (csrc/halo.cu,
+    # D.SymmPeerComm); `--dd-comm nccl`, or a box where the symmetric allocation is unavailable: NCCL point-to-point batches (D.DistComm)
+    exch = "peer memory (fvgn_exchange_push / _wait_*: stores into the neighbour's buffer over NVLink + sequence flags; 2 launches per exchange)"
+    ok = torch.ones(1, device=dev)
+    comm = None
+    if args.dd_comm == "peer":
+        try:
+            comm = D.SymmPeerComm(parts, run, dev)
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); NCCL point-to-point exchanges", file=sys.stderr)
+            ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if args.dd_comm != "peer" or float(ok[0]) == 0:
+        comm = D.DistComm()
+        exch = "NCCL point-to-point batches (torch.distributed.batch_isend_irecv)"
     with torch.no_grad():
         D.rollout_steps([run], comm, ms, 1)  # warm-up step (NCCL connections, allocator)
         run = D.PartRollout(part, D.KernelBackend(model), *D.initial_part_state(part, x0, ea0, bc), device=dev)
@@ -726,7 +740,7 @@ def domain_decomposition_leg(args, rank, world, dev, dist, steps=5):
             "single_gpu_eager_ms_per_step": single_ms, "speedup_over_single_gpu_eager": single_ms / float(dd_ms[0]),
             "rel_l2_next_uv_vs_single_gpu_per_step": [float(v) for v in rel], "tolerance_per_step": 1e-5,
             "pass": bool(all(float(v) < 1e-5 * (k + 1) for k, v in enumerate(rel))),
-            "exchanges_per_step": "2 per GnBlock (interface-node partial sums; ghost-cell x') + 1 (ghost next_uv), NCCL point-to-point batches"}
+            "exchanges_per_step": "2 per GnBlock (interface-node partial sums; ghost-cell x') + 1 (ghost next_uv)", "exchange": exch}
 
 
 # ------------------------------------------------------------------------------------------------ data-parallel parity check
@@ -980,6 +994,7 @@ def main():
     ap.add_argument("--no-training", action="store_true", help="skip the training graphs/s leg")
     ap.add_argument("--no-strict-leg", action="store_true", help="skip the strict-FFMA comparison leg")
     ap.add_argument("--no-dd-leg", action="store_true", help="N > 1: skip the single-mesh domain-decomposition leg")
+    ap.add_argument("--dd-comm", default="peer", choices=["peer", "nccl"], help="N > 1: exchanges of the domain-decomposition leg over peer memory (csrc/halo.cu) or NCCL point-to-point")
     ap.add_argument("--dd-workload", default="mesh1m", choices=sorted(WORKLOADS), help="the ONE mesh the domain-decomposition leg partitions over the N GPUs")
     ap.add_argument("--no-foil-leg", action="store_true", help="skip the foil16 / bf16 leg (BASELINE configs[2])")
     ap.add_argument("--no-config0", action="store_true", help="skip the batch-1 rollout latency leg (configs[0])")

@@ -24,6 +24,18 @@ class TrainTablesT(C.Structure):
                 ("cell_from_face_items", C.c_void_p), ("node_from_cell_ptr", C.c_void_p), ("node_from_cell_items", C.c_void_p)]
 
 
+EXCHANGE_MAX_PEERS = 8
+
+
+class ExchangePlanT(C.Structure):  # fvgn_exchange_plan_t
+    _M = EXCHANGE_MAX_PEERS
+    _fields_ = [("n_peers", C.c_int), ("row_bytes", C.c_int), ("n_if", C.c_int), ("self_pos", C.c_int), ("local_parity_stride", C.c_longlong),
+                ("seq", C.c_void_p), ("counters", C.c_void_p), ("status", C.c_void_p), ("local_buf", C.c_void_p), ("if_rows", C.c_void_p),
+                ("remote_buf", C.c_void_p * _M), ("remote_off", C.c_longlong * _M), ("remote_parity_stride", C.c_longlong * _M),
+                ("remote_flag", C.c_void_p * _M), ("local_flag", C.c_void_p * _M), ("send_rows", C.c_void_p * _M), ("n_send", C.c_int * _M),
+                ("recv_rows", C.c_void_p * _M), ("n_recv", C.c_int * _M), ("local_off", C.c_longlong * _M)]
+
+
 _P, _I, _F, _S = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _SIGS = {
     "fvgn_abi_version": (C.c_int, []),
@@ -91,6 +103,9 @@ _SIGS = {
     "fvgn_edge_grad_combine": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "fvgn_loss_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     "fvgn_integrator_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P]),
+    "fvgn_exchange_push": (_I, [C.POINTER(ExchangePlanT), _P, C.c_longlong, _P]),
+    "fvgn_exchange_wait_scatter": (_I, [C.POINTER(ExchangePlanT), _P, C.c_longlong, _P]),
+    "fvgn_exchange_wait_node_sum": (_I, [C.POINTER(ExchangePlanT), _P, _P]),
     "fvgn_integrator_bwd_poly": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P]),
     "fvgn_face_area_bn_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P]),
 }
@@ -115,7 +130,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.fvgn_abi_version() != 10:
+        if L.fvgn_abi_version() != 11:
             raise RuntimeError("libfvgn_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -28,6 +28,7 @@ SOURCES = {
     "connectivity.cu": ["--fmad=false"],
     "prepost.cu": ["--fmad=false"],
     "executor.cu": [],
+    "halo.cu": [],
 }
 
 

@@ -123,6 +123,164 @@ class DistComm:
         return recvs
 
 
+# ------------------------------------------------------------------------------------------------ exchanges over peer memory
+EXCHANGE_KINDS = (("node", 256), ("halo", 512), ("uv", 8))  # bytes per row: 64 floats | one x' row (fp32, or the fp16 hi / lo shadow) | next_uv
+
+
+def _align(n, a=256):
+    return (int(n) + a - 1) // a * a
+
+
+def exchange_layout(parts, r):
+    """byte layout of rank r's receive buffer — flag block (one 8-byte sequence flag per kind and source rank), then per kind the regions of
+    its peers in ascending rank order, twice (sequence parity).  Every rank computes every rank's layout from the same `parts`."""
+    p = parts[r]
+    n_parts = len(parts)
+    off = _align(len(EXCHANGE_KINDS) * n_parts * 8, 4096)
+    lay = {}
+    for kind, rb in EXCHANGE_KINDS:
+        if kind == "node":
+            cnt = {q: len(ix) for q, ix in p.node_share.items()}
+        else:
+            cnt = {q: len(p.halo_recv.get(q, ())) for q in set(p.halo_recv) | set(p.halo_send)}
+        offs, o = {}, 0
+        for q in sorted(cnt):
+            offs[q] = o
+            o += _align(cnt[q] * rb)
+        lay[kind] = dict(base=off, stride=o, off=offs, n=cnt)
+        off += 2 * o
+    lay["total"] = off
+    return lay
+
+
+class PeerExchange:
+    """the three exchange plans (fvgn_exchange_plan_t) of one part: csrc/halo.cu stores rows straight into the neighbours' receive buffers and
+    raises a sequence flag there; the neighbour's wait kernel consumes them.  `bufs[q]` = base address of rank q's receive buffer as THIS
+    device sees it (peer mapping of a symmetric allocation, or another tensor on the same device)."""
+
+    def __init__(self, parts, run: "PartRollout", bufs, device):
+        from ._lib import EXCHANGE_MAX_PEERS, ExchangePlanT
+
+        p = run.p
+        r, n_parts = p.rank, len(parts)
+        t32 = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.int32).to(device)
+        self.keep, self.plans = [], {}
+        self.state = torch.zeros(16, dtype=torch.int64, device=device)      # per kind: seq[2]
+        self.counters = torch.zeros(16, dtype=torch.int32, device=device)   # per kind: counters[2]; [15] = status word
+        lays = {q: exchange_layout(parts, q) for q in range(n_parts)}
+        for k, (kind, rb) in enumerate(EXCHANGE_KINDS):
+            mine = lays[r][kind]
+            peers = sorted(mine["n"])
+            if len(peers) > EXCHANGE_MAX_PEERS:
+                raise NotImplementedError(f"a part with {len(peers)} neighbours (the exchange plans hold {EXCHANGE_MAX_PEERS})")
+            pl = ExchangePlanT()
+            pl.n_peers, pl.row_bytes = len(peers), rb
+            pl.local_parity_stride = mine["stride"]
+            pl.seq = self.state.data_ptr() + 16 * k
+            pl.counters = self.counters.data_ptr() + 8 * k
+            pl.status = self.counters.data_ptr() + 4 * 15
+            pl.local_buf = bufs[r] + mine["base"]
+            pl.self_pos = sum(1 for q in peers if q < r)
+            if kind == "node" and peers:
+                if_rows = run.if_rows
+                pl.n_if = int(if_rows.numel())
+                rows32 = if_rows.to(torch.int32).contiguous()
+                self.keep.append(rows32)
+                pl.if_rows = rows32.data_ptr()
+            for i, q in enumerate(peers):
+                theirs = lays[q][kind]
+                pl.remote_buf[i] = bufs[q] + theirs["base"]
+                pl.remote_off[i] = theirs["off"][r]
+                pl.remote_parity_stride[i] = theirs["stride"]
+                pl.remote_flag[i] = bufs[q] + (k * n_parts + r) * 8
+                pl.local_flag[i] = bufs[r] + (k * n_parts + q) * 8
+                pl.local_off[i] = mine["off"][q]
+                if kind == "node":
+                    send = t32(p.node_share[q])
+                    inv = torch.full((pl.n_if,), -1, dtype=torch.int32, device=device)
+                    inv[run.if_pos[q]] = torch.arange(send.numel(), dtype=torch.int32, device=device)
+                    recv, n_recv = inv, int(send.numel())
+                else:
+                    send = t32(p.halo_send.get(q, np.zeros(0, dtype=np.int64)))
+                    recv = t32(p.halo_recv.get(q, np.zeros(0, dtype=np.int64)))
+                    n_recv = int(recv.numel())
+                assert theirs["n"][r] == int(send.numel()) and mine["n"][q] == n_recv, (kind, r, q)
+                self.keep += [send, recv]
+                pl.send_rows[i], pl.n_send[i] = send.data_ptr(), int(send.numel())
+                pl.recv_rows[i], pl.n_recv[i] = recv.data_ptr(), n_recv
+            self.plans[kind] = pl
+
+    def push(self, kind, src):
+        from . import ops
+        import ctypes as C_
+
+        assert src.is_contiguous()
+        ops._count(1)
+        ops.check(ops._lib.lib().fvgn_exchange_push(C_.byref(self.plans[kind]), ops._p(src), src.stride(0) * src.element_size(), ops._stream()), "exchange_push")
+
+    def wait(self, kind, dst):
+        from . import ops
+        import ctypes as C_
+
+        assert dst.is_contiguous()
+        L = ops._lib.lib()
+        ops._count(1)
+        if kind == "node":
+            ops.check(L.fvgn_exchange_wait_node_sum(C_.byref(self.plans[kind]), ops._p(dst), ops._stream()), "exchange_wait_node_sum")
+        else:
+            ops.check(L.fvgn_exchange_wait_scatter(C_.byref(self.plans[kind]), ops._p(dst), dst.stride(0) * dst.element_size(), ops._stream()),
+                      "exchange_wait_scatter")
+
+    def timed_out(self):
+        return int(self.counters[15]) != 0
+
+
+class _PeerCommBase:
+    fused = True  # rollout_steps: exchanges go through `exchange_rows` (push on every part, then wait on every part)
+
+    def exchange_rows(self, kind, runs, tensors):
+        for pr, t in zip(runs, tensors):
+            self.ex[pr.p.rank].push(kind, t)
+        for pr, t in zip(runs, tensors):
+            self.ex[pr.p.rank].wait(kind, t)
+
+    def check(self):
+        bad = [r for r, e in self.ex.items() if e.timed_out()]
+        if bad:
+            raise RuntimeError(f"peer-memory exchange: a wait timed out on rank(s) {bad} (a neighbour never raised its flag)")
+
+
+class LocalPeerComm(_PeerCommBase):
+    """all parts in ONE process on one device: the "peer" buffers are the other parts' tensors (tests; the kernels and plans are the ones a
+    rank per GPU runs)"""
+
+    def __init__(self, parts, runs, device):
+        self.bufs = {p.rank: torch.zeros(exchange_layout(parts, p.rank)["total"], dtype=torch.uint8, device=device) for p in parts}
+        ptr = {r: b.data_ptr() for r, b in self.bufs.items()}
+        self.ex = {pr.p.rank: PeerExchange(parts, pr, ptr, device) for pr in runs}
+
+
+class SymmPeerComm(_PeerCommBase):
+    """one rank per GPU: every rank's receive buffer is a symmetric allocation (torch.distributed._symmetric_memory: CUDA VMM + fabric / fd
+    handles) that all peers map, so a rank's kernels store into its neighbours' HBM over NVLink / NVSwitch directly"""
+
+    def __init__(self, parts, run, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group or dist.group.WORLD
+        total = max(exchange_layout(parts, q)["total"] for q in range(len(parts)))
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        torch.cuda.synchronize(device)
+        self.hdl.barrier()
+        ptr = {q: int(self.hdl.buffer_ptrs[q]) for q in range(len(parts))}
+        self.ex = {run.p.rank: PeerExchange(parts, run, ptr, device)}
+        torch.cuda.synchronize(device)
+        self.hdl.barrier()
+
+
 # ------------------------------------------------------------------------------------------------ the part's rollout step
 class PartRollout:
     """One rank's share of the rollout of ONE mesh.  `backend` supplies the arithmetic on torch tensors of this part:
@@ -190,15 +348,22 @@ def rollout_steps(parts_run, comm, model_state, n_steps):
             return [comm.collect(pr.p.rank) for pr in parts_run]
         return [comm.exchange(s, shapes, like) for (s, shapes, like) in payloads]
 
+    fused = getattr(comm, "fused", False)  # peer-memory exchanges (csrc/halo.cu): two launches per exchange, rows consumed in place
     for _ in range(n_steps):
         st = [pr.be.encode(pr, model_state) for pr in parts_run]  # (x latent [C_own,128], e latent [F,128], uv_own)
         for layer in range(model_state["n_layers"]):
             nas = [pr.be.node_partial(pr, s, layer) for pr, s in zip(parts_run, st)]
-            rec = exchange("node", [(pr.node_sends(na), {q: (ix.numel(), na.shape[1]) for q, ix in pr.share.items()}, na) for pr, na in zip(parts_run, nas)])
-            nas = [pr.node_finish(na, r) for pr, na, r in zip(parts_run, nas, rec)]
+            if fused:
+                comm.exchange_rows("node", parts_run, nas)
+            else:
+                rec = exchange("node", [(pr.node_sends(na), {q: (ix.numel(), na.shape[1]) for q, ix in pr.share.items()}, na) for pr, na in zip(parts_run, nas)])
+                nas = [pr.node_finish(na, r) for pr, na, r in zip(parts_run, nas, rec)]
             xps = [pr.be.cell_block(pr, s, na, layer, model_state) for pr, s, na in zip(parts_run, st, nas)]  # buffers [C_own+G, .]: owned rows filled
-            rec = exchange("halo", [(pr.halo_sends(xp), {q: (ix.numel(),) + tuple(xp.shape[1:]) for q, ix in pr.hrecv.items()}, xp) for pr, xp in zip(parts_run, xps)])
-            xps = [pr.halo_finish(xp, r) for pr, xp, r in zip(parts_run, xps, rec)]
+            if fused:
+                comm.exchange_rows("halo", parts_run, xps)
+            else:
+                rec = exchange("halo", [(pr.halo_sends(xp), {q: (ix.numel(),) + tuple(xp.shape[1:]) for q, ix in pr.hrecv.items()}, xp) for pr, xp in zip(parts_run, xps)])
+                xps = [pr.halo_finish(xp, r) for pr, xp, r in zip(parts_run, xps, rec)]
             for pr, s, xp in zip(parts_run, st, xps):
                 pr.be.edge_block(pr, s, xp, layer, model_state)
         res = [pr.be.decode_integrate(pr, s, model_state) for pr, s in zip(parts_run, st)]  # (uvp [F,3], next_uv_own [C_own,2])
@@ -207,9 +372,13 @@ def rollout_steps(parts_run, comm, model_state, n_steps):
             b = torch.zeros((pr.p.C_own + pr.p.G, 2), dtype=nuv.dtype, device=nuv.device)
             b[:pr.p.C_own] = nuv
             uvb.append(b)
-        rec = exchange("uv", [(pr.halo_sends(b), {q: (ix.numel(), 2) for q, ix in pr.hrecv.items()}, b) for pr, b in zip(parts_run, uvb)])
-        for pr, b, r, (uvp, nuv), o in zip(parts_run, uvb, rec, res, outs):
-            pr.halo_finish(b, r)
+        if fused:
+            comm.exchange_rows("uv", parts_run, uvb)
+        else:
+            rec = exchange("uv", [(pr.halo_sends(b), {q: (ix.numel(), 2) for q, ix in pr.hrecv.items()}, b) for pr, b in zip(parts_run, uvb)])
+            for pr, b, r in zip(parts_run, uvb, rec):
+                pr.halo_finish(b, r)
+        for pr, b, (uvp, nuv), o in zip(parts_run, uvb, res, outs):
             pr.be.next_graph(pr, b)
             o.append((uvp, nuv))
     return outs

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FVGN_ABI_VERSION 10 /* v10: fvgn_integrator_bwd_poly (training on tri / quad tables); v9: fvgn_status_read, fvgn_loss_partials / fvgn_loss_finish (data-parallel reduce-before-log); [4,C] tri/quad tables;  v7: cells_node_T == NULL selects the mp_times = 1 CellBlock in every cell-block entry point; v8: fvgn_mlp_pack_bf16x3_many, fvgn_mlp_pack_bf16x3_bwd_many, fvgn_cell_mean, fvgn_ln_bwd column-sum partials, n_products = 3 */
+#define FVGN_ABI_VERSION 11 /* v11: fvgn_exchange_* (domain-decomposition exchanges over peer memory); v10: fvgn_integrator_bwd_poly (training on tri / quad tables); v9: fvgn_status_read, fvgn_loss_partials / fvgn_loss_finish (data-parallel reduce-before-log); [4,C] tri/quad tables;  v7: cells_node_T == NULL selects the mp_times = 1 CellBlock in every cell-block entry point; v8: fvgn_mlp_pack_bf16x3_many, fvgn_mlp_pack_bf16x3_bwd_many, fvgn_cell_mean, fvgn_ln_bwd column-sum partials, n_products = 3 */
 #define FVGN_HIDDEN 128 /* latent width; the reference ignores --hidden_size */
 
 #define FVGN_E_BADARG (-1)
@@ -381,6 +381,39 @@ FVGN_API int fvgn_integrator_bwd_poly(const float* decoded, const float* unv4, c
 /* BatchNorm1d(1) affine gradients: g_weight_bias[2] from g_face_area, the saved raw feature and (mean, invstd) */
 FVGN_API int fvgn_face_area_bn_bwd(const float* g_face_area, const float* raw, const float* batch_stats, int n_faces, float* g_weight_bias,
                                    float* workspace, fvgn_stream_t stream);
+
+/* ---- single-mesh domain decomposition: the exchange steps over PEER MEMORY (no reference counterpart — the
+ * reference runs one mesh on one device).  One plan per exchange kind (interface-node partial sums, ghost-cell x', ghost next_uv) and rank:
+ * peers in ascending rank order; every buffer / flag pointer is a device pointer valid on THIS device (the peers' ones are peer mappings of
+ * a symmetric allocation, or plain pointers when all parts live on one device).  Receive regions exist twice (sequence parity). */
+#define FVGN_EXCHANGE_MAX_PEERS 8
+typedef struct {
+  int n_peers, row_bytes /* multiple of 4, <= 512 */, n_if /* node kind: interface nodes */, self_pos /* node kind: peers with a lower rank */;
+  long long local_parity_stride;      /* bytes between the two parity copies of my receive regions */
+  unsigned long long* seq;            /* device [2]: pushes / waits completed (advanced by the kernels: graph replays keep counting) */
+  unsigned int* counters;             /* device [2], zero: last-CTA counters */
+  unsigned int* status;               /* device word: bit 0 = a wait gave up after ~2 s */
+  void* local_buf;                    /* my receive buffer */
+  const int32_t* if_rows;             /* node kind: [n_if] local rows of the interface nodes */
+  void* remote_buf[FVGN_EXCHANGE_MAX_PEERS];               /* peer p's receive buffer */
+  long long remote_off[FVGN_EXCHANGE_MAX_PEERS];           /* byte offset of MY region in it (parity 0) */
+  long long remote_parity_stride[FVGN_EXCHANGE_MAX_PEERS];
+  unsigned long long* remote_flag[FVGN_EXCHANGE_MAX_PEERS];      /* my flag in peer p's flag block */
+  const unsigned long long* local_flag[FVGN_EXCHANGE_MAX_PEERS]; /* peer p's flag in mine */
+  const int32_t* send_rows[FVGN_EXCHANGE_MAX_PEERS];       /* [n_send] local rows sent to peer p, in the order both sides agreed on */
+  int n_send[FVGN_EXCHANGE_MAX_PEERS];
+  const int32_t* recv_rows[FVGN_EXCHANGE_MAX_PEERS];       /* scatter kinds: [n_recv] local destination rows; node kind: [n_if] position of
+                                                              each interface node in peer p's message, -1 = not shared with p */
+  int n_recv[FVGN_EXCHANGE_MAX_PEERS];
+  long long local_off[FVGN_EXCHANGE_MAX_PEERS];            /* byte offset of peer p's region in my buffer (parity 0) */
+} fvgn_exchange_plan_t;
+/* rows src[send_rows[p][i]] -> peer p's region (the gather is fused with the peer store), then the sequence flag is raised at every peer */
+FVGN_API int fvgn_exchange_push(const fvgn_exchange_plan_t* plan, const void* src, long long src_row_stride_bytes, fvgn_stream_t stream);
+/* waits for every peer's flag, then dst[recv_rows[p][i]] <- row i of peer p's region */
+FVGN_API int fvgn_exchange_wait_scatter(const fvgn_exchange_plan_t* plan, void* dst, long long dst_row_stride_bytes, fvgn_stream_t stream);
+/* waits, then every interface node's aggregate [.,64] <- own partial + the peers' partials in ascending rank order (deterministic, the same
+ * bits on every rank that holds the node): the domain-decomposed form of the scatter-add of GN_blocks.py:111-122 */
+FVGN_API int fvgn_exchange_wait_node_sum(const fvgn_exchange_plan_t* plan, float* node_agg, fvgn_stream_t stream);
 
 #ifdef __cplusplus
 }

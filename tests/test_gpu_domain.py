@@ -53,6 +53,24 @@ def test_decomposed_rollout_on_the_kernels(fv, math, n_parts):
         e1, e2 = H.rel_l2(nuv.cpu(), want[k][1].cpu()), H.rel_l2(uvp.cpu(), want[k][0].cpu())
         assert e1 < 1e-5 * (k + 1) and e2 < 1e-5 * (k + 1), (math, n_parts, k, e1, e2)
     assert fv.ops.status(clear=True) == 0
+    # the exchanges over peer memory (csrc/halo.cu: rows stored straight into the neighbour's receive buffer + sequence flags; here the
+    # "peers" are the other parts' buffers on the same device): same bits as the torch index ops + copies above, eager and as a graph
+    runs = [D.PartRollout(p, be, *D.initial_part_state(p, x0, ea0, bc), device="cuda") for p in parts]
+    pcomm = D.LocalPeerComm(parts, runs, "cuda")
+    with torch.no_grad():
+        pouts = D.rollout_steps(runs, pcomm, ms, steps)
+    pcomm.check()
+    for o, g in zip(outs, pouts):
+        for k in range(steps):
+            assert torch.equal(o[k][0], g[k][0]) and torch.equal(o[k][1], g[k][1]), ("peer", math, n_parts, k)
+    runs = [D.PartRollout(p, be, *D.initial_part_state(p, x0, ea0, bc), device="cuda") for p in parts]
+    pcomm = D.LocalPeerComm(parts, runs, "cuda")
+    gr = D.GraphedPartRollout(runs, pcomm, ms)
+    for k in range(steps):
+        got = gr.step()
+        for o, g in zip(outs, got):
+            assert torch.equal(o[k][0], g[0]) and torch.equal(o[k][1], g[1]), ("peer graph", math, n_parts, k)
+    pcomm.check()
     # the same steps as ONE CUDA graph over all parts (D.GraphedPartRollout; one graph per rank with NCCL exchanges on a multi-GPU box): same bits
     runs = [D.PartRollout(p, be, *D.initial_part_state(p, x0, ea0, bc), device="cuda") for p in parts]
     gr = D.GraphedPartRollout(runs, D.LocalComm(n_parts), ms)

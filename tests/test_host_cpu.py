@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(fv._lib.LIB_PATH)
     for s in declared:
         assert hasattr(L, s), s
-    assert L.fvgn_abi_version() == 10
+    assert L.fvgn_abi_version() == 11
     # size queries are pure host code and must work without a device
     L.fvgn_norm_workspace_floats.restype = ctypes.c_size_t
     assert L.fvgn_norm_workspace_floats(14) > 0
