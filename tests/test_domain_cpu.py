@@ -102,6 +102,22 @@ def test_partition_tables_and_exchange_plans(n_parts):
         for q, ix in p.node_share.items():
             assert np.array_equal(p.nodes[ix], parts[q].nodes[parts[q].node_share[p.rank]])
     assert (owners == 1).all()                                                                  # every face aggregated by exactly one part
+    # receive-buffer layouts of the peer-memory exchanges (csrc/halo.cu): every rank derives every rank's layout from `parts`; a sender's
+    # count equals the receiver's region, regions are 256-byte aligned, disjoint, inside the two parity copies, behind the flag block
+    lays = [D.exchange_layout(parts, r) for r in range(n_parts)]
+    for p, lay in zip(parts, lays):
+        spans = [(0, len(D.EXCHANGE_KINDS) * n_parts * 8)]
+        for kind, rb in D.EXCHANGE_KINDS:
+            k = lay[kind]
+            sends = p.node_share if kind == "node" else p.halo_send
+            for q in sends:
+                assert lays[q][kind]["n"][p.rank] == len(sends[q]), (kind, p.rank, q)
+            for q, n in k["n"].items():
+                assert k["off"][q] % 256 == 0 and k["off"][q] + n * rb <= k["stride"]
+                for parity in (0, 1):
+                    spans.append((k["base"] + parity * k["stride"] + k["off"][q], k["base"] + parity * k["stride"] + k["off"][q] + n * rb))
+        spans.sort()
+        assert all(a[1] <= b[0] for a, b in zip(spans[:-1], spans[1:])) and spans[-1][1] <= lay["total"]
 
 
 @pytest.mark.parametrize("kind,n_parts", [("cyl", 2), ("cyl", 3), ("grid", 4)])
