@@ -25,6 +25,9 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc3_common.cuh"
+#ifndef FVGN_COLLECTOR
+#define FVGN_COLLECTOR 0  // 1: A-collector reuse between the two layer-1 products that share a_hi (UTCHMMA .A_KEEP / .A_REUSE): measured +-0
+#endif
 
 namespace fvgn {
 namespace x3 {
@@ -323,6 +326,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           PROF_ADD(2);
           tc_fence_after();
           const uint32_t alo = umma_desc_lo(smem_u32(sA + sa * FA_SLOT)), blo = umma_desc_lo(smem_u32(sW + sw * FW_SLOT));
+#if FVGN_COLLECTOR
+          if (p.nprod == 3) {
+            // products 0 and 1 of a K slice share their A operand (a_hi): the first MMA keeps it in the A collector, the second takes it there
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t a0 = alo + (uint32_t)((kk * 32) >> 4), a1 = alo + (uint32_t)((TILE_BYTES + kk * 32) >> 4);
+              const uint32_t b0 = blo + (uint32_t)((kk * 32) >> 4), b1 = blo + (uint32_t)((TILE_BYTES + kk * 32) >> 4);
+              umma_f16_lo_w_col<1>(d, a0, b0, IDESC_F16_M128_N128, (t | kk) != 0);
+              umma_f16_lo_w_col<2>(d, a0, b1, IDESC_F16_M128_N128, 1);
+              umma_f16_lo_w_col<0>(d, a1, b0, IDESC_F16_M128_N128, 1);
+            }
+          } else
+#endif
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
 #pragma unroll

@@ -124,6 +124,33 @@ __device__ __forceinline__ void umma_f16_lo_w(uint32_t tmem_d, uint32_t alo, uin
       ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
       : "memory");
 }
+// the same with an A-collector hint: MODE 1 = .collector::a::fill (keep the A operand for the next MMA), 2 = .collector::a::lastuse (take
+// it from the collector instead of shared memory), 0 = default (discard)
+template <int MODE>
+__device__ __forceinline__ void umma_f16_lo_w_col(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+  if (MODE == 1)
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+        : "memory");
+  else if (MODE == 2)
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+        : "memory");
+  else
+    umma_f16_lo_w(tmem_d, alo, blo, idesc, accumulate);
+}
 __device__ __forceinline__ void umma_f16_ts_lo_w(uint32_t tmem_d, uint32_t tmem_a, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
