@@ -487,36 +487,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
       tc_fence_after();
       const float inv3 = sPar[5 * 128 + 2];
       float mean = 0.f, rstd = 1.f;
-      if (has_ln && !(FVGN_DBG(p) & 32)) {  // two-pass LayerNorm statistics, as torch; the two column halves exchange partial sums
-        float s = 0.f;
-        auto sum16 = [&](int sc, const uint32_t* r) {
+      if (has_ln && !(FVGN_DBG(p) & 32)) {
+        // LayerNorm statistics in ONE read of the accumulator: shifted sums of this thread's 64 columns (shift = its first value, so the
+        // subtraction s2 - s1^2/64 cancels nothing that matters), then the two column halves of a row are combined with the pairwise
+        // (Chan) update — mean and variance to fp32 rounding, like the two-pass form it replaces.  Each accumulator read-out costs the
+        // MMAs TMEM-port time (profiles/r02_tmem_port_sharing.txt): three reads per tile in this layer are now two.
+        float s1 = 0.f, s2 = 0.f, c = 0.f;
+        auto stat16 = [&](int sc, const uint32_t* r) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
-            s += fmaf(__uint_as_float(r[4 * j4]), inv3, b.x); s += fmaf(__uint_as_float(r[4 * j4 + 1]), inv3, b.y);
-            s += fmaf(__uint_as_float(r[4 * j4 + 2]), inv3, b.z); s += fmaf(__uint_as_float(r[4 * j4 + 3]), inv3, b.w);
-          }
-        };
-        FVGN_FOR_SUBCHUNKS(sum16);
-        sRed[h * 128 + erow] = s;
-        named_bar_sync(1, NEPI);
-        mean = (sRed[erow] + sRed[128 + erow]) * (1.0f / 128.0f);
-        float qv = 0.f;
-        auto dev16 = [&](int sc, const uint32_t* r) {
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
+            const float y0 = fmaf(__uint_as_float(r[4 * j4]), inv3, b.x), y1 = fmaf(__uint_as_float(r[4 * j4 + 1]), inv3, b.y);
+            const float y2 = fmaf(__uint_as_float(r[4 * j4 + 2]), inv3, b.z), y3 = fmaf(__uint_as_float(r[4 * j4 + 3]), inv3, b.w);
+            if (j4 == 0 && sc == 4 * h) c = y0;
             float d;
-            d = fmaf(__uint_as_float(r[4 * j4]), inv3, b.x) - mean; qv = fmaf(d, d, qv);
-            d = fmaf(__uint_as_float(r[4 * j4 + 1]), inv3, b.y) - mean; qv = fmaf(d, d, qv);
-            d = fmaf(__uint_as_float(r[4 * j4 + 2]), inv3, b.z) - mean; qv = fmaf(d, d, qv);
-            d = fmaf(__uint_as_float(r[4 * j4 + 3]), inv3, b.w) - mean; qv = fmaf(d, d, qv);
+            d = y0 - c; s1 += d; s2 = fmaf(d, d, s2);
+            d = y1 - c; s1 += d; s2 = fmaf(d, d, s2);
+            d = y2 - c; s1 += d; s2 = fmaf(d, d, s2);
+            d = y3 - c; s1 += d; s2 = fmaf(d, d, s2);
           }
         };
-        FVGN_FOR_SUBCHUNKS(dev16);
-        sRed[256 + h * 128 + erow] = qv;
+        FVGN_FOR_SUBCHUNKS(stat16);
+        const float mh = c + s1 * (1.0f / 64.0f);             // mean of this half
+        const float m2 = s2 - s1 * s1 * (1.0f / 64.0f);       // sum of squared deviations from it
+        float* red = sRed + 512 * acc;  // (double-buffered by tile parity: one barrier per tile orders writes and reads of a buffer)
+        red[h * 128 + erow] = mh;
+        red[256 + h * 128 + erow] = m2;
         named_bar_sync(1, NEPI);
-        rstd = 1.0f / sqrtf((sRed[256 + erow] + sRed[256 + 128 + erow]) * (1.0f / 128.0f) + 1e-5f);
+        const float m0 = red[erow], m1 = red[128 + erow];
+        const float dm = m0 - m1;
+        mean = 0.5f * (m0 + m1);
+        const float var = (red[256 + erow] + red[256 + 128 + erow] + dm * dm * 32.0f) * (1.0f / 128.0f);
+        rstd = 1.0f / sqrtf((var < 0.0f ? 0.0f : var) + 1e-5f);  // (a NaN variance stays NaN: the status check below needs it)
         if (h == 0 && !(rstd * 0.0f == 0.0f) && row0 + erow < p.rows) atomicOr(&g_status, 1u);  // inf / NaN anywhere in the row
       }
       const float* res = (MODE == TC_CELL) ? p.src0 : p.src1;

@@ -43,7 +43,7 @@ __host__ __device__ inline SmemLayout smem_layout_pair() {
   L.w_off = o; o += PWRING * PW_SLOT;   // 64 KB
   L.stage_off = o; o += 8 * 2048;
   L.par_off = o; o += 5 * 128 * 4 + 16;
-  L.red_off = o; o += 2 * 2 * 128 * 4;
+  L.red_off = o; o += 2 * 2 * 2 * 128 * 4;
   L.bar_off = o; o += 256;
   L.total = o;
   return L;
@@ -430,7 +430,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_m
       mbar_wait(BAR(PB_DFULL23 + acc), 1, 9);
       tc_fence_after();
       const float inv3 = sPar[5 * 128 + 2];
-      float s = 0.f;
+      // one-read LayerNorm statistics: the arithmetic of mlp_tc3.cu's final epilogue, operation for operation (bit-identical results)
+      float s1 = 0.f, s2 = 0.f, c = 0.f;
 #pragma unroll 1
       for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
         tmem_ld16_issue(t_acc + 16 * sc, r);
@@ -438,31 +439,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_m
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
-          s += fmaf(__uint_as_float(r[4 * j4]), inv3, b.x); s += fmaf(__uint_as_float(r[4 * j4 + 1]), inv3, b.y);
-          s += fmaf(__uint_as_float(r[4 * j4 + 2]), inv3, b.z); s += fmaf(__uint_as_float(r[4 * j4 + 3]), inv3, b.w);
-        }
-      }
-      sRed[h * 128 + erow] = s;
-      named_bar_sync(1, NEPI);
-      const float mean = (sRed[erow] + sRed[128 + erow]) * (1.0f / 128.0f);
-      float qv = 0.f;
-#pragma unroll 1
-      for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {
-        tmem_ld16_issue(t_acc + 16 * sc, r);
-        tmem_ld16_wait(r);
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b = *reinterpret_cast<const float4*>(b3 + 16 * sc + 4 * j4);
+          const float y0 = fmaf(__uint_as_float(r[4 * j4]), inv3, b.x), y1 = fmaf(__uint_as_float(r[4 * j4 + 1]), inv3, b.y);
+          const float y2 = fmaf(__uint_as_float(r[4 * j4 + 2]), inv3, b.z), y3 = fmaf(__uint_as_float(r[4 * j4 + 3]), inv3, b.w);
+          if (j4 == 0 && sc == 4 * h) c = y0;
           float d;
-          d = fmaf(__uint_as_float(r[4 * j4]), inv3, b.x) - mean; qv = fmaf(d, d, qv);
-          d = fmaf(__uint_as_float(r[4 * j4 + 1]), inv3, b.y) - mean; qv = fmaf(d, d, qv);
-          d = fmaf(__uint_as_float(r[4 * j4 + 2]), inv3, b.z) - mean; qv = fmaf(d, d, qv);
-          d = fmaf(__uint_as_float(r[4 * j4 + 3]), inv3, b.w) - mean; qv = fmaf(d, d, qv);
+          d = y0 - c; s1 += d; s2 = fmaf(d, d, s2);
+          d = y1 - c; s1 += d; s2 = fmaf(d, d, s2);
+          d = y2 - c; s1 += d; s2 = fmaf(d, d, s2);
+          d = y3 - c; s1 += d; s2 = fmaf(d, d, s2);
         }
       }
-      sRed[256 + h * 128 + erow] = qv;
+      const float mh = c + s1 * (1.0f / 64.0f);
+      const float m2 = s2 - s1 * s1 * (1.0f / 64.0f);
+      float* red = sRed + 512 * acc;
+      red[h * 128 + erow] = mh;
+      red[256 + h * 128 + erow] = m2;
       named_bar_sync(1, NEPI);
-      const float rstd = 1.0f / sqrtf((sRed[256 + erow] + sRed[256 + 128 + erow]) * (1.0f / 128.0f) + 1e-5f);
+      const float m0 = red[erow], m1 = red[128 + erow];
+      const float dm = m0 - m1;
+      const float mean = 0.5f * (m0 + m1);
+      const float var = (red[256 + erow] + red[256 + 128 + erow] + dm * dm * 32.0f) * (1.0f / 128.0f);
+      const float rstd = 1.0f / sqrtf((var < 0.0f ? 0.0f : var) + 1e-5f);
       if (h == 0 && !(rstd * 0.0f == 0.0f) && row0 + erow < p.rows) atomicOr(&g_status, 1u);
 #pragma unroll 1
       for (int sc = 4 * h; sc < 4 * h + 4; ++sc) {

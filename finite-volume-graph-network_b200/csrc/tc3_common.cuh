@@ -176,7 +176,7 @@ __host__ __device__ inline SmemLayout smem_layout_fwd() {
   L.w_off = o; o += FWRING * FW_SLOT;     // 96 KB
   L.stage_off = o; o += 8 * 2048;
   L.par_off = o; o += 5 * 128 * 4 + 16;   // b1 b2 b3 ln_w ln_b | the three 1 / (ASCALE * weight scale) factors
-  L.red_off = o; o += 2 * 2 * 128 * 4;
+  L.red_off = o; o += 2 * 2 * 2 * 128 * 4;  // LayerNorm exchange (mean, M2) between the two column halves of a row, double-buffered by tile parity
   L.bar_off = o; o += 256;
   L.total = o;
   return L;
