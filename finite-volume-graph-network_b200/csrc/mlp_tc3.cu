@@ -26,7 +26,7 @@
 #include "common.cuh"
 #include "tc3_common.cuh"
 #ifndef FVGN_COLLECTOR
-#define FVGN_COLLECTOR 0  // 1: A-collector reuse between the two layer-1 products that share a_hi (UTCHMMA .A_KEEP / .A_REUSE): measured +-0
+#define FVGN_COLLECTOR 3  // A-collector reuse between the two products of a K slice that share their A operand (UTCHMMA .A_KEEP / .A_REUSE): bit 0 = layer 1 (A in shared memory), bit 1 = layers 2 / 3 (A in TMEM)
 #endif
 
 namespace fvgn {
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
           PROF_ADD(2);
           tc_fence_after();
           const uint32_t alo = umma_desc_lo(smem_u32(sA + sa * FA_SLOT)), blo = umma_desc_lo(smem_u32(sW + sw * FW_SLOT));
-#if FVGN_COLLECTOR
+#if FVGN_COLLECTOR & 1
           if (p.nprod == 3) {
             // products 0 and 1 of a K slice share their A operand (a_hi): the first MMA keeps it in the A collector, the second takes it there
 #pragma unroll
@@ -365,6 +365,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
             PROF_ADD(5);
             tc_fence_after();
             const uint32_t blo = umma_desc_lo(smem_u32(sW + sw * FW_SLOT));
+#if FVGN_COLLECTOR >= 2
+            if (p.nprod == 3) {
+              // products 0 and 1 of a K slice share h_hi: read from TMEM once, the second MMA takes it from the A collector
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t a0 = hcol + 8u * (uint32_t)(4 * t + kk), a1 = a0 + 64u;
+                const uint32_t b0 = blo + (uint32_t)((kk * 32) >> 4), b1 = blo + (uint32_t)((TILE_BYTES + kk * 32) >> 4);
+                umma_f16_ts_lo_w_col<1>(d, a0, b0, IDESC_F16_M128_N128, (t | kk) != 0);
+                umma_f16_ts_lo_w_col<2>(d, a0, b1, IDESC_F16_M128_N128, 1);
+                umma_f16_ts_lo_w_col<0>(d, a1, b0, IDESC_F16_M128_N128, 1);
+              }
+            } else
+#endif
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll

@@ -110,6 +110,34 @@ __device__ __forceinline__ void umma_bf16_ts_w(uint32_t tmem_d, uint32_t tmem_a,
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the two above with an A-collector hint: MODE 1 = .collector::a::fill (keep A for the next MMA), 2 = .collector::a::lastuse (take it from the
+// collector instead of shared memory / TMEM), 0 = default
+template <int MODE>
+__device__ __forceinline__ void umma_bf16_w_col(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (MODE == 1)
+    asm volatile("{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else if (MODE == 2)
+    asm volatile("{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    umma_bf16_w(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+template <int MODE>
+__device__ __forceinline__ void umma_bf16_ts_w_col(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (MODE == 1)
+    asm volatile("{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else if (MODE == 2)
+    asm volatile("{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    umma_bf16_ts_w(tmem_d, tmem_a, bdesc, idesc, accumulate);
+}
 // ... with the operand descriptors given by their LOW words only (start address >> 4 | LBO; the high word — SBO 1024 B, version 1,
 // SWIZZLE_128B — is the constant 0x40004040): stepping to the next 32-byte K slice / the other split plane is ONE integer add on the low word
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
@@ -160,6 +188,31 @@ __device__ __forceinline__ void umma_f16_ts_lo_w(uint32_t tmem_d, uint32_t tmem_
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "r"(blo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
       : "memory");
+}
+// A in TMEM with an A-collector hint (MODE as umma_f16_lo_w_col): the second of two MMAs on the same A takes it from the collector instead
+// of reading TMEM again — tcgen05.ld / .st and the MMAs share the TMEM port (profiles/r02_tmem_port_sharing.txt)
+template <int MODE>
+__device__ __forceinline__ void umma_f16_ts_lo_w_col(uint32_t tmem_d, uint32_t tmem_a, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+  if (MODE == 1)
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], [%1], db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(blo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+        : "memory");
+  else if (MODE == 2)
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], [%1], db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(blo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+        : "memory");
+  else
+    umma_f16_ts_lo_w(tmem_d, tmem_a, blo, idesc, accumulate);
 }
 __device__ __forceinline__ void umma_commit_w(uint32_t bar) {
   asm volatile(

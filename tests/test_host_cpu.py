@@ -168,6 +168,7 @@ def test_sass_of_the_tensor_core_kernels_is_blackwell_native():
             per[cur] = set()
         elif cur:
             per[cur].update(re.findall(r"\b(UTCHMMA\.2CTA|UTCBAR\.2CTA\.MULTICAST|UCGABAR_ARV|UTCHMMA|LDTM|STTM|UBLKCP|LDGSTS|SYNCS|HMMA|FFMA)\b", line))
+            per[cur].update(re.findall(r"\.(A_KEEP|A_REUSE)\b", line))
     assert not any("HMMA" in v for v in per.values()), "legacy mma.sync / wmma path found"
     want = {"fused_mlp_tc_kernel": {"UTCHMMA", "LDTM", "STTM", "UBLKCP", "SYNCS"}, "fused_mlp_tc3_kernel": {"UTCHMMA", "LDTM", "STTM", "UBLKCP", "SYNCS"},
             "dgrad_tc3_kernel": {"UTCHMMA", "LDTM", "STTM", "UBLKCP", "SYNCS"}, "wgrad_tc3_kernel": {"UTCHMMA", "LDTM", "SYNCS"},
@@ -183,6 +184,10 @@ def test_sass_of_the_tensor_core_kernels_is_blackwell_native():
     assert len(pair) == 2, pair
     for k in pair:
         assert {"UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST", "UCGABAR_ARV", "LDTM", "STTM", "UBLKCP", "SYNCS"} <= per[k], (k, per[k])
+    # the fp32-equivalent forward reuses the A operand of two consecutive split products through the A collector (shared-memory A in layer 1,
+    # TMEM A in layers 2 / 3: one TMEM read less per K slice next to the epilogue's tcgen05.ld traffic)
+    for k in [k for k in per if "fused_mlp_tc3_kernel" in k]:
+        assert {"A_KEEP", "A_REUSE"} <= per[k], (k, per[k])
     # the two-term backward variants move their rows with cp.async (the staging rings of this round)
     assert any("wgrad_tc3_kernelILb0" in k and "LDGSTS" in v for k, v in per.items())
     assert any("dgrad_tc3_kernelILb0" in k and "LDGSTS" in v for k, v in per.items())
