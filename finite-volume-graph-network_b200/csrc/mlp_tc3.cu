@@ -474,8 +474,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_mlp_tc3_kernel(const Params
               const float z0 = fmaf(__uint_as_float(r[4 * j4]), inv, b.x), z1 = fmaf(__uint_as_float(r[4 * j4 + 1]), inv, b.y);
               const float z2 = fmaf(__uint_as_float(r[4 * j4 + 2]), inv, b.z), z3 = fmaf(__uint_as_float(r[4 * j4 + 3]), inv, b.w);
               r[4 * j4] = __float_as_uint(z0); r[4 * j4 + 1] = __float_as_uint(z1); r[4 * j4 + 2] = __float_as_uint(z2); r[4 * j4 + 3] = __float_as_uint(z3);
-              split2_pair(silu_x3(z0) * ASCALE, silu_x3(z1) * ASCALE, p0[2 * j4], p1[2 * j4]);
-              split2_pair(silu_x3(z2) * ASCALE, silu_x3(z3) * ASCALE, p0[2 * j4 + 1], p1[2 * j4 + 1]);
+              split2_pair(silu_x3_scaled(z0), silu_x3_scaled(z1), p0[2 * j4], p1[2 * j4]);
+              split2_pair(silu_x3_scaled(z2), silu_x3_scaled(z3), p0[2 * j4 + 1], p1[2 * j4 + 1]);
             }
             if (p.zsave) store_rows16(reinterpret_cast<const float*>(r), p.zsave, 384, 128 * layer + 16 * sc, row0 + 32 * q);
             tmem_st8(t_ha + 8 * sc, p0);

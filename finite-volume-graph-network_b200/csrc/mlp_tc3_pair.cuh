@@ -411,8 +411,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_m
           const float4 b = *reinterpret_cast<const float4*>(bias + 16 * sc + 4 * j4);
           const float z0 = fmaf(__uint_as_float(r[4 * j4]), inv, b.x), z1 = fmaf(__uint_as_float(r[4 * j4 + 1]), inv, b.y);
           const float z2 = fmaf(__uint_as_float(r[4 * j4 + 2]), inv, b.z), z3 = fmaf(__uint_as_float(r[4 * j4 + 3]), inv, b.w);
-          split2_pair(silu_x3(z0) * ASCALE, silu_x3(z1) * ASCALE, p0[2 * j4], p1[2 * j4]);
-          split2_pair(silu_x3(z2) * ASCALE, silu_x3(z3) * ASCALE, p0[2 * j4 + 1], p1[2 * j4 + 1]);
+          split2_pair(silu_x3_scaled(z0), silu_x3_scaled(z1), p0[2 * j4], p1[2 * j4]);
+          split2_pair(silu_x3_scaled(z2), silu_x3_scaled(z3), p0[2 * j4 + 1], p1[2 * j4 + 1]);
         }
         tmem_st8(t_ha + 8 * sc, p0);
         tmem_st8(t_ha + 64 + 8 * sc, p1);

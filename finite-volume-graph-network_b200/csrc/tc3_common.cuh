@@ -115,6 +115,15 @@ __device__ __forceinline__ float silu_x3(float v) {
   return v * r;
 }
 
+// ASCALE * silu(v) in one instruction less: ASCALE / (1 + e) = rcp((1 + e) / ASCALE), the power-of-two scale folded into the FMA that
+// forms the reciprocal's argument (rcp.approx works on the mantissa: the same bits as scaling afterwards)
+__device__ __forceinline__ float silu_x3_scaled(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(e, 1.0f / ASCALE, 1.0f / ASCALE)));
+  return v * r;
+}
+
 // 4 consecutive fp32 (columns 4*hl .. 4*hl+3 of a 64-wide K-tile) -> row r of the three swizzled split sub-tiles of one ring slot
 __device__ __forceinline__ void st_slot_f4(unsigned char* slot, int r, int hl, float4 v, bool third) {
   const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)hl >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)hl & 1u) * 8u;
