@@ -88,6 +88,19 @@ for a, b in iv:
     else:
         cur_e = max(cur_e, b)
 busy += (cur_e - cur_s) if cur_e is not None else 0.0
+ev = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda t: t[0])
+gaps, end, last = [], None, None
+for a, b, n in ev:
+    if end is not None and a > end:
+        gaps.append((a - end, last, n))
+    if end is None or b > end:
+        end, last = b, n
+print("largest idle gaps of the GPU timeline (us, kernel before -> kernel after):")
+for g, x, y in sorted(gaps, key=lambda t: -t[0])[:14]:
+    print("  %7.1f  %s -> %s" % (g, x[:70], y[:70]))
+print("gaps > 20 us: %d, total %.0f us; gaps <= 20 us: %d, total %.0f us (over %d step(s))"
+      % (sum(1 for g in gaps if g[0] > 20), sum(g[0] for g in gaps if g[0] > 20), sum(1 for g in gaps if g[0] <= 20),
+         sum(g[0] for g in gaps if g[0] <= 20), NPROF))
 print("GPU timeline of the %d profiled step(s): span %.2f ms/step, some kernel running %.2f ms/step, idle %.2f ms/step"
       % (NPROF, (iv[-1][1] - iv[0][0]) / 1e3 / NPROF, busy / 1e3 / NPROF, ((iv[-1][1] - iv[0][0]) - busy) / 1e3 / NPROF))
 agg = collections.defaultdict(lambda: [0, 0.0])
