@@ -10,7 +10,7 @@
 //     Half the MMAs, two thirds of the operand bytes of the 3 x bf16 scheme.  Forward activations are O(1) (normalised inputs,
 //     LayerNorm'd latents, SiLU outputs): |a| >= 8190 overflows the fp16 term to inf and the output row to NaN (loud, not silent).
 //     Gradients have no such bound, hence the backward keeps bf16.
-// Bias, SiLU (ex2.approx / rcp.approx), LayerNorm (two-pass) and the residual are fp32 in the epilogue, so results stay within the
+// Bias, SiLU (ex2.approx / rcp.approx), LayerNorm (shifted sums in one read of the accumulator, the two column halves combined pairwise) and the residual are fp32 in the epilogue, so results stay within the
 // reference's 1e-5 per-step relative tolerance (tests/test_gpu_x3.py holds every op to 5e-6 against the fp64 oracle).
 //
 // 120 MMAs per 128-row EdgeBlock tile; one persistent CTA per SM,
